@@ -1,0 +1,282 @@
+/*
+ * vtgs.h -- C ABI of the B200-native differentiable Gaussian-splatting hot path.
+ *
+ * This is the drop-in boundary for the one path VTGaussian-SLAM spends its time in:
+ * the rasteriser binding that the reference imports as the pip module
+ * `diff_gaussian_rasterization` (reference requirements.txt:18; import sites
+ * src/vtgaussian_slam.py:38, utils/recon_helpers.py:2, utils/eval_helpers.py:17) and
+ * calls at src/vtgaussian_slam.py:461,466,747 and utils/eval_helpers.py:240,247,431,443.
+ * That module's pybind layer exports `_C.rasterize_gaussians`,
+ * `_C.rasterize_gaussians_backward` and `_C.mark_visible`; the three entry points
+ * vtgs_forward / vtgs_backward / vtgs_mark_visible below are what a maintainer binds in
+ * their place.  The fused entry points further down replace the
+ * pure-PyTorch work the reference wraps around every rasteriser call
+ * (utils/slam_helpers.py:127-160,217-234,255-287,323-385; src/vtgaussian_slam.py:407-689,
+ * 180-187) with single launches.
+ *
+ * Rules of the ABI
+ *   - plain C: raw device pointers, sizes, PODs.  No torch / C++ types, no exceptions.
+ *   - every function returns 0 on success, a negative VTGS_E_* code otherwise;
+ *     vtgs_last_error() returns a thread-local message for the last failure.
+ *   - every function only enqueues work on `stream` (a cudaStream_t passed as void*);
+ *     nothing synchronises the device or the host, so call sequences are CUDA-graph
+ *     capturable.  The number of (tile, Gaussian) pairs R is never read back by the
+ *     library: the caller provides `pair_capacity` slots and polls
+ *     VtgsCounters.overflow when convenient.
+ *   - all arrays are caller-owned device memory, fp32/int32 contiguous, layouts as the
+ *     reference passes them (AoS [N,3] / [N,4] / [C,H,W]).
+ *   - re-entrant per (VtgsBuffers, stream); no hidden global state.
+ */
+#ifndef VTGS_H_
+#define VTGS_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VTGS_ABI_VERSION 1
+
+/* ---- named constants of the splatting arithmetic ---------- */
+#define VTGS_TILE            16          /* BLOCK_X = BLOCK_Y                          */
+#define VTGS_NEAR_CULL       0.2f        /* cull p_view.z <= 0.2                       */
+#define VTGS_FRUSTUM_MULT    1.3f        /* clamp of t.x/t.z in the EWA Jacobian       */
+#define VTGS_LOWPASS         0.3f        /* screen-space dilation                      */
+#define VTGS_LAMBDA_FLOOR    0.1f
+#define VTGS_ALPHA_MAX       0.99f
+#define VTGS_ALPHA_MIN       (1.0f / 255.0f)
+#define VTGS_T_MIN           0.0001f
+#define VTGS_EPS_W           0.0000001f
+#define VTGS_RADIUS_SIGMA_MULT_DEFAULT 3.0f   /* the fork's "smallerGSradii" delta is
+                                                  unknown offline: runtime parameter   */
+
+/* ---- error codes -------------------------------------------------------------------- */
+#define VTGS_OK               0
+#define VTGS_E_INVALID       -1          /* bad argument                               */
+#define VTGS_E_CUDA          -2          /* a CUDA runtime call failed                 */
+#define VTGS_E_UNSUPPORTED   -3          /* e.g. SH colours, cov3D_precomp             */
+
+/*
+ * Camera / raster settings.  Mirrors GaussianRasterizationSettings as built by
+ * setup_camera (reference utils/recon_helpers.py:14-26): matrices are the flat
+ * row-vector-convention arrays the reference passes (viewmatrix = w2c^T, projmatrix =
+ * (proj*w2c)^T), i.e. p_view.x = m[0]x + m[4]y + m[8]z + m[12].
+ * tile_row_begin/end select a band of 16-px tile rows (multi-GPU tracking shards the
+ * image by tile bands); 0,0 means "all rows".
+ */
+typedef struct VtgsCamera {
+    int32_t image_width;
+    int32_t image_height;
+    float   tanfovx;
+    float   tanfovy;
+    float   viewmatrix[16];
+    float   projmatrix[16];
+    float   bg[3];
+    float   scale_modifier;
+    float   radius_sigma_mult;
+    int32_t tile_row_begin;
+    int32_t tile_row_end;
+} VtgsCamera;
+
+/* Device-side counters; the library writes them, the caller may read them lazily. */
+typedef struct VtgsCounters {
+    uint32_t num_rendered;      /* R = sum of tiles_touched (before clamping)           */
+    uint32_t overflow;          /* 1 if R > pair_capacity (results are then truncated)  */
+    uint32_t max_tile_pairs;    /* longest per-tile list                                */
+    uint32_t scan_ticket;       /* internal                                             */
+} VtgsCounters;
+
+/*
+ * Workspace handed to forward and kept alive by the caller until backward (the
+ * equivalent of the reference binding's geomBuffer / binningBuffer / imgBuffer).
+ * Sizes come from vtgs_workspace_query.
+ */
+typedef struct VtgsBuffers {
+    void*         geom;           /* N records of VTGS_GEOM_RECORD_BYTES                  */
+    uint32_t*     tiles_touched;  /* [N]                                                   */
+    uint32_t*     tile_counts;    /* [tiles]  scratch (zeroed by forward)                  */
+    uint32_t*     tile_ranges;    /* [tiles][2] = {begin, end} into point_list             */
+    uint64_t*     pair_keys;      /* [pair_capacity] (depth_bits<<32 | gaussian id)        */
+    uint32_t*     point_list;     /* [pair_capacity] sorted Gaussian ids                   */
+    float*        final_T;        /* [H*W]                                                 */
+    uint32_t*     n_contrib;      /* [H*W]                                                 */
+    float*        grad_geom;      /* [N][VTGS_GRAD_GEOM_FLOATS] scratch of backward        */
+    VtgsCounters* counters;       /* 1                                                     */
+    uint64_t      pair_capacity;
+} VtgsBuffers;
+
+#define VTGS_GEOM_RECORD_BYTES 64
+#define VTGS_GRAD_GEOM_FLOATS  16
+
+typedef struct VtgsWorkspaceSizes {
+    uint64_t geom_bytes;
+    uint64_t tiles_touched_bytes;
+    uint64_t tile_counts_bytes;
+    uint64_t tile_ranges_bytes;
+    uint64_t pair_keys_bytes;
+    uint64_t point_list_bytes;
+    uint64_t final_T_bytes;
+    uint64_t n_contrib_bytes;
+    uint64_t grad_geom_bytes;
+    uint64_t counters_bytes;
+    uint32_t tiles_x;
+    uint32_t tiles_y;
+} VtgsWorkspaceSizes;
+
+/* ---- library ------------------------------------------------------------------------ */
+int         vtgs_abi_version(void);
+const char* vtgs_last_error(void);
+const char* vtgs_build_info(void);        /* arch / flags the library was built with     */
+
+int vtgs_workspace_query(int32_t image_width, int32_t image_height, int64_t num_gaussians,
+                         uint64_t pair_capacity, VtgsWorkspaceSizes* sizes);
+
+/*
+ * Forward: replaces _C.rasterize_gaussians (K1..K5 of SURVEY.md section 2.3).
+ *   means3D[N,3] scales[N,3] rotations[N,4] opacities[N] colors[N,3]  ->
+ *   out_color[3,H,W]  out_depth[H,W]  radii[N]
+ * Colours are precomputed (the reference never passes SHs: sh_degree = 0).
+ */
+int vtgs_forward(const VtgsCamera* cam, int64_t num_gaussians,
+                 const float* means3D, const float* scales, const float* rotations,
+                 const float* opacities, const float* colors,
+                 float* out_color, float* out_depth, int32_t* radii,
+                 VtgsBuffers* buf, void* stream);
+
+/*
+ * Backward: replaces _C.rasterize_gaussians_backward (K6, K7).
+ *   dL_dout_color[3,H,W] + the forward's inputs and buffers ->
+ *   dL_dmeans2D[N,3] (z = 0), dL_dcolors[N,3], dL_dopacity[N], dL_dmeans3D[N,3],
+ *   dL_dscales[N,3], dL_drotations[N,4].  No gradient flows through out_depth or radii
+ *   (as in the reference's "-w-depth" rasteriser).
+ */
+int vtgs_backward(const VtgsCamera* cam, int64_t num_gaussians,
+                  const float* means3D, const float* scales, const float* rotations,
+                  const float* opacities, const float* colors,
+                  const float* dL_dout_color,
+                  float* dL_dmeans2D, float* dL_dcolors, float* dL_dopacity,
+                  float* dL_dmeans3D, float* dL_dscales, float* dL_drotations,
+                  VtgsBuffers* buf, void* stream);
+
+/* Replaces _C.mark_visible: present[i] = (p_view.z > near cull). */
+int vtgs_mark_visible(const VtgsCamera* cam, int64_t num_gaussians, const float* means3D,
+                      uint8_t* present, void* stream);
+
+/*
+ * Parity/debug view of the binning stage in the reference's own representation:
+ * point_list_keys[R] = (tile_id << 32) | float_bits(depth) in sorted order, as
+ * cub::DeviceRadixSort leaves them in the reference's binningBuffer.
+ */
+int vtgs_export_sorted_keys(const VtgsCamera* cam, int64_t num_gaussians, const VtgsBuffers* buf,
+                            uint64_t* keys_out, uint64_t keys_capacity, void* stream);
+
+/* Geometry the forward computed, unpacked for parity checks:
+ * means2D[N,2], depths[N], conic_opacity[N,4]. Any pointer may be NULL. */
+int vtgs_export_geometry(int64_t num_gaussians, const VtgsBuffers* buf,
+                         float* means2D, float* depths, float* conic_opacity, void* stream);
+
+/* ===================================================================================== *
+ *  Fused view-tied path (what get_loss + backward + Adam do per iteration)              *
+ * ===================================================================================== */
+
+/*
+ * View-tied Gaussian parameters exactly as the reference's `params` dict stores them
+ * (src/vtgaussian_slam.py:132-177): means3D[N,3], rgb_colors[N,3],
+ * unnorm_rotations[N,4], logit_opacities[N,1], log_scales[N,1] (isotropic) or [N,3].
+ */
+typedef struct VtgsParams {
+    const float* means3D;
+    const float* rgb_colors;
+    const float* unnorm_rotations;
+    const float* logit_opacities;
+    const float* log_scales;
+    int32_t      log_scales_dim;   /* 1 (isotropic) or 3 */
+    int32_t      pad_;
+    int64_t      num_gaussians;
+} VtgsParams;
+
+/* Camera pose of the frame being rendered: the slices params['cam_unnorm_rots'][0,:,t]
+ * and params['cam_trans'][0,:,t] (device pointers to 4 and 3 floats, any stride-1). */
+typedef struct VtgsPose {
+    const float* cam_unnorm_rot;   /* [4] (w,x,y,z), un-normalised */
+    const float* cam_trans;        /* [3] */
+} VtgsPose;
+
+/*
+ * Fused forward for one view: transform_to_frame + transformed_params2rendervar +
+ * transformed_params2depthplussilhouette + both rasteriser passes of get_loss
+ * (src/vtgaussian_slam.py:432-466) as ONE six-channel pass.
+ *   out_image7[7,H,W] = {r, g, b, depth, silhouette, depth^2, <unused>}: channel order
+ *   is im[0..2] then depth_sil[0..2] of the reference.  Only 6 planes are written.
+ *   radii[N] as the RGB pass would return them.
+ */
+int vtgs_fused_forward(const VtgsCamera* cam, const VtgsParams* params, const VtgsPose* pose,
+                       float* out_image6, int32_t* radii, VtgsBuffers* buf, void* stream);
+
+/*
+ * Tracking / mapping loss of get_loss (src/vtgaussian_slam.py:513-612,678-679) evaluated
+ * on the six rendered planes against the frame, producing the scalar terms and
+ * dL/d(image6) in place of autograd.
+ *   mode 0: tracking   losses = sum|d|[mask] (depth), sum|rgb diff|[mask] (im)
+ *   mode 1: mapping    losses = mean|d|[depth>0] (depth), 0.8*L1mean + 0.2*(1-SSIM) (im)
+ * loss_terms[8] = {loss, w_im*im, w_depth*depth, mask_count, l1_im, ssim, 0, 0}.
+ */
+typedef struct VtgsLossConfig {
+    int32_t mode;                   /* 0 tracking, 1 mapping                              */
+    int32_t use_sil_for_loss;
+    int32_t ignore_outlier_depth;   /* median-based mask: NOT fused (returns UNSUPPORTED) */
+    int32_t use_l1;
+    float   sil_thres;
+    float   w_im;
+    float   w_depth;
+    float   far_depth_thres;        /* <= 0: disabled                                     */
+} VtgsLossConfig;
+
+int vtgs_loss(const VtgsCamera* cam, const VtgsLossConfig* cfg,
+              const float* image6, const float* gt_rgb, const float* gt_depth,
+              float* dL_dimage6 /* [4,H,W]: r,g,b,depth */, float* loss_terms /* [8] */,
+              float* scratch /* vtgs_loss_scratch_floats() floats */, void* stream);
+uint64_t vtgs_loss_scratch_floats(int32_t image_width, int32_t image_height, int32_t mode);
+
+/*
+ * Fused backward: K6 + K7 + the autograd chain through get_depth_and_silhouette,
+ * the activations and transform_to_frame.
+ *   want_gaussian_grads: write dL/d{means3D, rgb_colors, unnorm_rotations,
+ *       logit_opacities, log_scales} (mapping) -- any pointer may be NULL to skip it.
+ *   want_pose_grads: reduce dL/d(cam_unnorm_rot)[4] and dL/d(cam_trans)[3] (tracking / BA).
+ *   dL_dmeans2D[N,3] (optional) is what means2D.grad exposes in the reference.
+ */
+typedef struct VtgsParamGrads {
+    float* means3D;
+    float* rgb_colors;
+    float* unnorm_rotations;
+    float* logit_opacities;
+    float* log_scales;
+    float* means2D;
+    float* cam_unnorm_rot;   /* [4] */
+    float* cam_trans;        /* [3] */
+    float* pose_scratch;     /* vtgs_pose_scratch_floats(N) floats                        */
+} VtgsParamGrads;
+
+uint64_t vtgs_pose_scratch_floats(int64_t num_gaussians);
+
+int vtgs_fused_backward(const VtgsCamera* cam, const VtgsParams* params, const VtgsPose* pose,
+                        const float* dL_dimage4 /* [4,H,W]: r,g,b,depth */,
+                        int32_t accumulate /* 0: overwrite grads, 1: += (multi-keyframe) */,
+                        VtgsParamGrads* grads, VtgsBuffers* buf, void* stream);
+
+/*
+ * Adam exactly as torch.optim.Adam(betas=(0.9,0.999), eps, weight_decay=0) applies it to
+ * one tensor (reference src/vtgaussian_slam.py:180-187): step is the 1-based step count
+ * read from *step_dev (device int32, incremented by the caller via vtgs_adam_tick or kept
+ * on the host and passed in `step` when step_dev == NULL).
+ */
+int vtgs_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+              float lr, float beta1, float beta2, float eps, int32_t step,
+              const int32_t* step_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VTGS_H_ */
