@@ -36,6 +36,12 @@
 extern "C" {
 #endif
 
+#if defined(__GNUC__)
+#define VTGS_API __attribute__((visibility("default")))
+#else
+#define VTGS_API
+#endif
+
 #define VTGS_ABI_VERSION 1
 
 /* ---- named constants of the splatting arithmetic ---------- */
@@ -84,7 +90,14 @@ typedef struct VtgsCounters {
     uint32_t num_rendered;      /* R = sum of tiles_touched (before clamping)           */
     uint32_t overflow;          /* 1 if R > pair_capacity (results are then truncated)  */
     uint32_t max_tile_pairs;    /* longest per-tile list                                */
-    uint32_t scan_ticket;       /* internal                                             */
+    uint32_t reserved0;
+    /* pose of the fused path, written by the library each fused forward (device-resident so
+     * that a captured CUDA graph follows the optimiser): p_cam = pose_R * p + pose_t        */
+    float    pose_R[9];
+    float    pose_t[3];
+    float    pose_q[4];         /* cam quaternion after F.normalize (once)                  */
+    float    pose_qnorm[2];     /* |q_unnorm|, |F.normalize(q)| (the two normalisations)    */
+    float    reserved1[10];
 } VtgsCounters;
 
 /*
@@ -125,11 +138,11 @@ typedef struct VtgsWorkspaceSizes {
 } VtgsWorkspaceSizes;
 
 /* ---- library ------------------------------------------------------------------------ */
-int         vtgs_abi_version(void);
-const char* vtgs_last_error(void);
-const char* vtgs_build_info(void);        /* arch / flags the library was built with     */
+VTGS_API int         vtgs_abi_version(void);
+VTGS_API const char* vtgs_last_error(void);
+VTGS_API const char* vtgs_build_info(void);        /* arch / flags the library was built with     */
 
-int vtgs_workspace_query(int32_t image_width, int32_t image_height, int64_t num_gaussians,
+VTGS_API int vtgs_workspace_query(int32_t image_width, int32_t image_height, int64_t num_gaussians,
                          uint64_t pair_capacity, VtgsWorkspaceSizes* sizes);
 
 /*
@@ -138,7 +151,7 @@ int vtgs_workspace_query(int32_t image_width, int32_t image_height, int64_t num_
  *   out_color[3,H,W]  out_depth[H,W]  radii[N]
  * Colours are precomputed (the reference never passes SHs: sh_degree = 0).
  */
-int vtgs_forward(const VtgsCamera* cam, int64_t num_gaussians,
+VTGS_API int vtgs_forward(const VtgsCamera* cam, int64_t num_gaussians,
                  const float* means3D, const float* scales, const float* rotations,
                  const float* opacities, const float* colors,
                  float* out_color, float* out_depth, int32_t* radii,
@@ -151,7 +164,7 @@ int vtgs_forward(const VtgsCamera* cam, int64_t num_gaussians,
  *   dL_dscales[N,3], dL_drotations[N,4].  No gradient flows through out_depth or radii
  *   (as in the reference's "-w-depth" rasteriser).
  */
-int vtgs_backward(const VtgsCamera* cam, int64_t num_gaussians,
+VTGS_API int vtgs_backward(const VtgsCamera* cam, int64_t num_gaussians,
                   const float* means3D, const float* scales, const float* rotations,
                   const float* opacities, const float* colors,
                   const float* dL_dout_color,
@@ -160,7 +173,7 @@ int vtgs_backward(const VtgsCamera* cam, int64_t num_gaussians,
                   VtgsBuffers* buf, void* stream);
 
 /* Replaces _C.mark_visible: present[i] = (p_view.z > near cull). */
-int vtgs_mark_visible(const VtgsCamera* cam, int64_t num_gaussians, const float* means3D,
+VTGS_API int vtgs_mark_visible(const VtgsCamera* cam, int64_t num_gaussians, const float* means3D,
                       uint8_t* present, void* stream);
 
 /*
@@ -168,12 +181,12 @@ int vtgs_mark_visible(const VtgsCamera* cam, int64_t num_gaussians, const float*
  * point_list_keys[R] = (tile_id << 32) | float_bits(depth) in sorted order, as
  * cub::DeviceRadixSort leaves them in the reference's binningBuffer.
  */
-int vtgs_export_sorted_keys(const VtgsCamera* cam, int64_t num_gaussians, const VtgsBuffers* buf,
+VTGS_API int vtgs_export_sorted_keys(const VtgsCamera* cam, int64_t num_gaussians, const VtgsBuffers* buf,
                             uint64_t* keys_out, uint64_t keys_capacity, void* stream);
 
 /* Geometry the forward computed, unpacked for parity checks:
  * means2D[N,2], depths[N], conic_opacity[N,4]. Any pointer may be NULL. */
-int vtgs_export_geometry(int64_t num_gaussians, const VtgsBuffers* buf,
+VTGS_API int vtgs_export_geometry(int64_t num_gaussians, const VtgsBuffers* buf,
                          float* means2D, float* depths, float* conic_opacity, void* stream);
 
 /* ===================================================================================== *
@@ -199,8 +212,11 @@ typedef struct VtgsParams {
 /* Camera pose of the frame being rendered: the slices params['cam_unnorm_rots'][0,:,t]
  * and params['cam_trans'][0,:,t] (device pointers to 4 and 3 floats, any stride-1). */
 typedef struct VtgsPose {
-    const float* cam_unnorm_rot;   /* [4] (w,x,y,z), un-normalised */
-    const float* cam_trans;        /* [3] */
+    const float* cam_unnorm_rot;   /* [4] (w,x,y,z), un-normalised, device                 */
+    const float* cam_trans;        /* [3] device                                            */
+    float        depth_row[4];     /* third row of curr_data['w2c'] used by
+                                      get_depth_and_silhouette (utils/slam_helpers.py:217-234);
+                                      {0,0,1,0} for the reference's relative poses          */
 } VtgsPose;
 
 /*
@@ -211,7 +227,7 @@ typedef struct VtgsPose {
  *   is im[0..2] then depth_sil[0..2] of the reference.  Only 6 planes are written.
  *   radii[N] as the RGB pass would return them.
  */
-int vtgs_fused_forward(const VtgsCamera* cam, const VtgsParams* params, const VtgsPose* pose,
+VTGS_API int vtgs_fused_forward(const VtgsCamera* cam, const VtgsParams* params, const VtgsPose* pose,
                        float* out_image6, int32_t* radii, VtgsBuffers* buf, void* stream);
 
 /*
@@ -233,11 +249,11 @@ typedef struct VtgsLossConfig {
     float   far_depth_thres;        /* <= 0: disabled                                     */
 } VtgsLossConfig;
 
-int vtgs_loss(const VtgsCamera* cam, const VtgsLossConfig* cfg,
+VTGS_API int vtgs_loss(const VtgsCamera* cam, const VtgsLossConfig* cfg,
               const float* image6, const float* gt_rgb, const float* gt_depth,
               float* dL_dimage6 /* [4,H,W]: r,g,b,depth */, float* loss_terms /* [8] */,
               float* scratch /* vtgs_loss_scratch_floats() floats */, void* stream);
-uint64_t vtgs_loss_scratch_floats(int32_t image_width, int32_t image_height, int32_t mode);
+VTGS_API uint64_t vtgs_loss_scratch_floats(int32_t image_width, int32_t image_height, int32_t mode);
 
 /*
  * Fused backward: K6 + K7 + the autograd chain through get_depth_and_silhouette,
@@ -259,9 +275,9 @@ typedef struct VtgsParamGrads {
     float* pose_scratch;     /* vtgs_pose_scratch_floats(N) floats                        */
 } VtgsParamGrads;
 
-uint64_t vtgs_pose_scratch_floats(int64_t num_gaussians);
+VTGS_API uint64_t vtgs_pose_scratch_floats(int64_t num_gaussians);
 
-int vtgs_fused_backward(const VtgsCamera* cam, const VtgsParams* params, const VtgsPose* pose,
+VTGS_API int vtgs_fused_backward(const VtgsCamera* cam, const VtgsParams* params, const VtgsPose* pose,
                         const float* dL_dimage4 /* [4,H,W]: r,g,b,depth */,
                         int32_t accumulate /* 0: overwrite grads, 1: += (multi-keyframe) */,
                         VtgsParamGrads* grads, VtgsBuffers* buf, void* stream);
@@ -272,7 +288,7 @@ int vtgs_fused_backward(const VtgsCamera* cam, const VtgsParams* params, const V
  * read from *step_dev (device int32, incremented by the caller via vtgs_adam_tick or kept
  * on the host and passed in `step` when step_dev == NULL).
  */
-int vtgs_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+VTGS_API int vtgs_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
               float lr, float beta1, float beta2, float eps, int32_t step,
               const int32_t* step_dev, void* stream);
 

@@ -1,0 +1,152 @@
+"""-m gpu parity tests of the drop-in rasteriser (vtgs_forward / vtgs_backward through the
+C ABI) against the CPU oracle on identical seeded inputs.
+
+Bars (BASELINE.json north_star): radii, sort keys, tile ranges, per-pixel contributor counts
+bit-exact; image / depth within 1e-4 absolute; gradients within 1e-3 relative."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from helpers import oracle_camera, rel_err
+from vtgaussian_slam_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+
+IMG_ATOL = 1e-4
+GRAD_RTOL = 1e-3
+
+
+def _compare_forward(ref, got, N):
+    assert got["R"] == ref["R"]
+    assert np.array_equal(got["radii"], ref["radii"])
+    assert np.array_equal(got["tiles_touched"], ref["tiles_touched"])
+    assert np.array_equal(got["ranges"], ref["ranges"])
+    assert np.array_equal(got["point_list"], ref["point_list"])
+    assert np.array_equal(got["keys"], ref["keys"])
+    assert np.array_equal(got["n_contrib"], ref["n_contrib"])
+    vis = ref["radii"] > 0
+    if N:
+        assert np.array_equal(got["means2D"][vis], ref["means2D"][vis])
+        assert np.array_equal(got["depths"][vis], ref["depths"][vis])
+        assert np.array_equal(got["conic_opacity"][vis], ref["conic_opacity"][vis])
+    assert np.abs(got["color"] - ref["color"]).max() <= IMG_ATOL
+    assert np.abs(got["depth"] - ref["depth"]).max() <= IMG_ATOL * max(1.0, np.abs(ref["depth"]).max())
+    assert np.abs(got["final_T"] - ref["final_T"]).max() <= IMG_ATOL
+
+
+def _run_case(W, H, sc, K, bg=(0, 0, 0), grads=True, seed=0, sigma_mult=3.0, tile_rows=(0, 0)):
+    from gpu_helpers import cuda_forward_all
+    from vtgaussian_slam_b200 import rasterizer
+    rasterizer.set_radius_sigma_mult(sigma_mult)
+    try:
+        cam_o, s = oracle_camera(W, H, K, bg=bg, sigma_mult=sigma_mult, tile_rows=tile_rows)
+        o = oracle.Oracle()
+        ref = o.forward(cam_o, sc["means3D"], sc["scales"], sc["rotations"], sc["opacities"], sc["colors"])
+        got, cam, ws = cuda_forward_all(s, sc, tile_rows=tile_rows)
+        N = sc["means3D"].shape[0]
+        _compare_forward(ref, got, N)
+        bit_exact = np.array_equal(got["color"], ref["color"]) and np.array_equal(got["final_T"], ref["final_T"])
+        if grads and N:
+            rng = np.random.default_rng(seed)
+            dL = rng.normal(size=(3, H, W)).astype(np.float32)
+            g_ref = o.backward(dL)
+            g = rasterizer.rasterize_backward(cam, ws, torch.tensor(dL, device="cuda:0"))
+            names = ["means3D", "means2D", "colors", "opacities", "scales", "rotations"]
+            for name, t in zip(names, g):
+                e = rel_err(t.cpu().numpy().reshape(g_ref[name].shape), g_ref[name])
+                assert e <= GRAD_RTOL, (name, e)
+        return ref, got, bit_exact
+    finally:
+        rasterizer.set_radius_sigma_mult(3.0)
+
+
+@pytest.mark.parametrize("seed,aniso,n,W,H,bg", [
+    (0, True, 2000, 64, 48, (0, 0, 0)),
+    (1, False, 3000, 100, 70, (0.2, 0.4, 0.1)),       # ragged edge tiles, non-zero background
+    (2, True, 20000, 320, 200, (0, 0, 0)),
+    (3, True, 5000, 33, 17, (0, 0, 0)),                # > 256 entries per tile: several staged batches
+])
+def test_random_scene_parity(seed, aniso, n, W, H, bg):
+    K, sc = synthetic.random_scene(n, W, H, seed=seed, anisotropic=aniso)
+    _, _, bit_exact = _run_case(W, H, sc, K, bg=bg, seed=seed)
+    assert bit_exact, "forward planes are expected to be bit-identical to the oracle"
+
+
+def test_long_tile_lists_take_the_global_sort_path():
+    # one 16x16 tile with > 4096 entries: the per-tile sort leaves shared memory
+    W, H = 16, 16
+    K, sc = synthetic.random_scene(9000, W, H, seed=4, anisotropic=False, scale_px=(0.3, 1.0), opacity_range=(0.02, 0.2))
+    ref, got, _ = _run_case(W, H, sc, K, seed=4)
+    assert (ref["ranges"][:, 1] - ref["ranges"][:, 0]).max() > 4096
+
+
+def test_saturation_and_equal_depth_ties():
+    W, H = 48, 48
+    K, sc = synthetic.random_scene(6000, W, H, seed=5, anisotropic=False, opacity_range=(0.6, 1.0), scale_px=(2.0, 6.0))
+    sc["means3D"][:, 2] = np.round(sc["means3D"][:, 2] * 4) / 4 + 0.25      # many exactly equal depths
+    ref, got, _ = _run_case(W, H, sc, K, seed=5)
+    lens = ref["ranges"][:, 1] - ref["ranges"][:, 0]
+    assert ref["n_contrib"].max() < lens.max()            # early termination happened
+    assert (ref["final_T"] < 2e-4).any()
+
+
+def test_view_tied_frame_parity():
+    fr = synthetic.make_frame("replica", 300, 170, seed=0)
+    p = synthetic.view_tied_gaussians(fr, n_edge=8000, opacity="trained")
+    m, s, r, o, c6 = oracle.frontend(p["means3D"], p["rgb_colors"], p["unnorm_rotations"], p["logit_opacities"],
+                                     p["log_scales"], [1, 0, 0, 0], [0, 0, 0])
+    sc = dict(means3D=m, scales=s, rotations=r, opacities=o, colors=c6[:, :3].copy())
+    _run_case(fr["W"], fr["H"], sc, fr["K"], seed=6)
+    sc["colors"] = c6[:, 3:].copy()                        # the depth / silhouette / depth^2 pass
+    _run_case(fr["W"], fr["H"], sc, fr["K"], seed=7)
+
+
+def test_radius_multiplier_and_tile_band():
+    W, H = 128, 96
+    K, sc = synthetic.random_scene(4000, W, H, seed=8)
+    _run_case(W, H, sc, K, sigma_mult=2.0, seed=8)
+    _run_case(W, H, sc, K, tile_rows=(2, 5), seed=9)
+
+
+def test_empty_and_all_culled():
+    W, H = 40, 24
+    K, sc = synthetic.random_scene(10, W, H, seed=1)
+    empty = {k: v[:0] for k, v in sc.items()}
+    ref, got, _ = _run_case(W, H, empty, K, bg=(0.1, 0.2, 0.3), grads=False)
+    assert got["R"] == 0 and np.allclose(got["color"][:, 0, 0], [0.1, 0.2, 0.3])
+    sc["means3D"][:, 2] = -1.0
+    _run_case(W, H, sc, K)
+
+
+def test_autograd_module_matches_oracle_and_rejects_cpu():
+    from gpu_helpers import settings_from
+    from diff_gaussian_rasterization import GaussianRasterizer
+    W, H = 96, 64
+    K, sc = synthetic.random_scene(2500, W, H, seed=11)
+    cam_o, s = oracle_camera(W, H, K)
+    dev = torch.device("cuda:0")
+    t = {k: torch.tensor(v, device=dev, requires_grad=True) for k, v in sc.items()}
+    m2d = torch.zeros_like(t["means3D"], requires_grad=True)
+    op = t["opacities"][:, None]
+    rend = GaussianRasterizer(raster_settings=settings_from(s, dev))
+    color, radii, depth = rend(means3D=t["means3D"], means2D=m2d, opacities=op, colors_precomp=t["colors"],
+                               scales=t["scales"], rotations=t["rotations"])
+    assert color.shape == (3, H, W) and depth.shape == (1, H, W) and radii.dtype == torch.int32
+    assert not depth.requires_grad and color.requires_grad
+    dL = torch.randn(3, H, W, device=dev)
+    (color * dL).sum().backward()
+    o = oracle.Oracle()
+    ref = o.forward(cam_o, sc["means3D"], sc["scales"], sc["rotations"], sc["opacities"], sc["colors"])
+    g = o.backward(dL.cpu().numpy())
+    assert np.array_equal(radii.cpu().numpy(), ref["radii"])
+    assert rel_err(m2d.grad.cpu().numpy(), g["means2D"]) <= GRAD_RTOL
+    assert rel_err(t["means3D"].grad.cpu().numpy(), g["means3D"]) <= GRAD_RTOL
+    assert rel_err(t["opacities"].grad.cpu().numpy(), g["opacities"]) <= GRAD_RTOL
+    vis = rend.markVisible(t["means3D"]).cpu().numpy()
+    assert np.array_equal(vis, oracle.mark_visible(cam_o, sc["means3D"]))
+    with pytest.raises(Exception):
+        rend(means3D=t["means3D"], means2D=m2d, opacities=op, scales=t["scales"], rotations=t["rotations"])
+    with pytest.raises(RuntimeError):
+        rend(means3D=t["means3D"].cpu(), means2D=m2d.cpu(), opacities=op.cpu(), colors_precomp=t["colors"].cpu(),
+             scales=t["scales"].cpu(), rotations=t["rotations"].cpu())

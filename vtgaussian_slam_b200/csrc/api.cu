@@ -1,0 +1,182 @@
+// api.cu -- the extern "C" boundary declared in include/vtgs.h.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace vtgs {
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+}  // namespace vtgs
+
+using namespace vtgs;
+
+#define VTGS_REQUIRE(cond, msg)                   \
+    do {                                          \
+        if (!(cond)) {                            \
+            set_error("invalid argument: %s", msg); \
+            return VTGS_E_INVALID;                \
+        }                                         \
+    } while (0)
+
+static int check_cam(const VtgsCamera* cam) {
+    VTGS_REQUIRE(cam != nullptr, "cam is NULL");
+    VTGS_REQUIRE(cam->image_width > 0 && cam->image_height > 0, "image size must be positive");
+    VTGS_REQUIRE(cam->tanfovx > 0.f && cam->tanfovy > 0.f, "tanfov must be positive");
+    VTGS_REQUIRE(cam->radius_sigma_mult > 0.f, "radius_sigma_mult must be positive");
+    return VTGS_OK;
+}
+
+static int check_buf(const VtgsBuffers* b, int64_t N) {
+    VTGS_REQUIRE(b != nullptr, "buffers is NULL");
+    VTGS_REQUIRE(b->tile_counts && b->tile_ranges && b->final_T && b->n_contrib && b->counters, "workspace pointer is NULL");
+    if (N > 0) VTGS_REQUIRE(b->geom && b->tiles_touched && b->grad_geom, "per-Gaussian workspace pointer is NULL");
+    VTGS_REQUIRE(b->pair_capacity == 0 || (b->pair_keys && b->point_list), "pair workspace pointer is NULL");
+    VTGS_REQUIRE(b->pair_capacity < 0xffffffffull, "pair_capacity must fit 32 bits");
+    return VTGS_OK;
+}
+
+#pragma GCC visibility push(default)
+extern "C" {
+
+int vtgs_abi_version(void) { return VTGS_ABI_VERSION; }
+const char* vtgs_last_error(void) { return g_err; }
+const char* vtgs_build_info(void) {
+    return "libvtgs_cuda sm_100a (compute_100a) nvcc " VTGS_STR_NVCC " -lineinfo; hand-written CUDA, no CUB/Thrust";
+}
+
+int vtgs_workspace_query(int32_t W, int32_t H, int64_t N, uint64_t pair_capacity, VtgsWorkspaceSizes* s) {
+    VTGS_REQUIRE(s != nullptr, "sizes is NULL");
+    VTGS_REQUIRE(W > 0 && H > 0 && N >= 0, "bad dimensions");
+    const uint64_t gx = (W + VTGS_TILE - 1) / VTGS_TILE, gy = (H + VTGS_TILE - 1) / VTGS_TILE;
+    const uint64_t n = (uint64_t)(N > 0 ? N : 1), P = (uint64_t)W * H;
+    s->geom_bytes = n * VTGS_GEOM_RECORD_BYTES;
+    s->tiles_touched_bytes = n * 4;
+    s->tile_counts_bytes = gx * gy * 4;
+    s->tile_ranges_bytes = gx * gy * 8;
+    s->pair_keys_bytes = (pair_capacity > 0 ? pair_capacity : 1) * 8;
+    s->point_list_bytes = (pair_capacity > 0 ? pair_capacity : 1) * 4;
+    s->final_T_bytes = P * 4;
+    s->n_contrib_bytes = P * 4;
+    s->grad_geom_bytes = n * VTGS_GRAD_GEOM_FLOATS * 4;
+    s->counters_bytes = sizeof(VtgsCounters);
+    s->tiles_x = (uint32_t)gx;
+    s->tiles_y = (uint32_t)gy;
+    return VTGS_OK;
+}
+
+int vtgs_forward(const VtgsCamera* cam, int64_t N, const float* means3D, const float* scales,
+                 const float* rotations, const float* opacities, const float* colors,
+                 float* out_color, float* out_depth, int32_t* radii, VtgsBuffers* buf, void* stream) {
+    if (int e = check_cam(cam)) return e;
+    if (int e = check_buf(buf, N)) return e;
+    VTGS_REQUIRE(N >= 0, "num_gaussians < 0");
+    VTGS_REQUIRE(out_color && out_depth, "output pointer is NULL");
+    if (N > 0) VTGS_REQUIRE(means3D && scales && rotations && opacities && colors && radii, "input pointer is NULL");
+    FrontEnd fe{};
+    return launch_forward(cam, N, false, fe, means3D, scales, rotations, opacities, colors, out_color, out_depth, radii, buf,
+                          (cudaStream_t)stream);
+}
+
+int vtgs_backward(const VtgsCamera* cam, int64_t N, const float* means3D, const float* scales,
+                  const float* rotations, const float* opacities, const float* colors,
+                  const float* dL_dout_color, float* dL_dmeans2D, float* dL_dcolors, float* dL_dopacity,
+                  float* dL_dmeans3D, float* dL_dscales, float* dL_drotations, VtgsBuffers* buf, void* stream) {
+    if (int e = check_cam(cam)) return e;
+    if (int e = check_buf(buf, N)) return e;
+    VTGS_REQUIRE(N >= 0, "num_gaussians < 0");
+    if (N > 0)
+        VTGS_REQUIRE(means3D && scales && rotations && dL_dout_color && dL_dmeans2D && dL_dcolors && dL_dopacity &&
+                         dL_dmeans3D && dL_dscales && dL_drotations,
+                     "pointer is NULL");
+    return launch_backward(cam, N, means3D, scales, rotations, opacities, colors, dL_dout_color, dL_dmeans2D, dL_dcolors,
+                           dL_dopacity, dL_dmeans3D, dL_dscales, dL_drotations, buf, (cudaStream_t)stream);
+}
+
+int vtgs_mark_visible(const VtgsCamera* cam, int64_t N, const float* means3D, uint8_t* present, void* stream) {
+    if (int e = check_cam(cam)) return e;
+    if (N > 0) VTGS_REQUIRE(means3D && present, "pointer is NULL");
+    return launch_mark_visible(cam, N, means3D, present, (cudaStream_t)stream);
+}
+
+int vtgs_export_sorted_keys(const VtgsCamera* cam, int64_t N, const VtgsBuffers* buf, uint64_t* keys_out,
+                            uint64_t keys_capacity, void* stream) {
+    (void)N;
+    if (int e = check_cam(cam)) return e;
+    VTGS_REQUIRE(buf && keys_out, "pointer is NULL");
+    return launch_export_keys(cam, buf, keys_out, keys_capacity, (cudaStream_t)stream);
+}
+
+int vtgs_export_geometry(int64_t N, const VtgsBuffers* buf, float* means2D, float* depths, float* conic_opacity, void* stream) {
+    VTGS_REQUIRE(buf != nullptr, "buffers is NULL");
+    return launch_export_geometry(N, buf, means2D, depths, conic_opacity, (cudaStream_t)stream);
+}
+
+static int check_fused(const VtgsCamera* cam, const VtgsParams* p, const VtgsPose* pose, const VtgsBuffers* buf) {
+    if (int e = check_cam(cam)) return e;
+    VTGS_REQUIRE(p && pose, "params / pose is NULL");
+    if (int e = check_buf(buf, p->num_gaussians)) return e;
+    VTGS_REQUIRE(p->num_gaussians >= 0, "num_gaussians < 0");
+    if (p->num_gaussians > 0)
+        VTGS_REQUIRE(p->means3D && p->rgb_colors && p->unnorm_rotations && p->logit_opacities && p->log_scales, "param pointer is NULL");
+    VTGS_REQUIRE(pose->cam_unnorm_rot && pose->cam_trans, "pose pointer is NULL");
+    if (p->log_scales_dim != 1) {
+        set_error("fused path supports isotropic Gaussians only (log_scales [N,1]); use vtgs_forward/backward for anisotropic");
+        return VTGS_E_UNSUPPORTED;
+    }
+    return VTGS_OK;
+}
+
+int vtgs_fused_forward(const VtgsCamera* cam, const VtgsParams* p, const VtgsPose* pose, float* out_image6, int32_t* radii,
+                       VtgsBuffers* buf, void* stream) {
+    if (int e = check_fused(cam, p, pose, buf)) return e;
+    VTGS_REQUIRE(out_image6 != nullptr, "out_image6 is NULL");
+    if (p->num_gaussians > 0) VTGS_REQUIRE(radii != nullptr, "radii is NULL");
+    if (int e = launch_pose_matrix(pose, buf->counters, (cudaStream_t)stream)) return e;
+    FrontEnd fe{};
+    fe.pose_Rt = buf->counters->pose_R;
+    for (int k = 0; k < 4; ++k) fe.depth_row[k] = pose->depth_row[k];
+    fe.log_scales_dim = p->log_scales_dim;
+    return launch_forward(cam, p->num_gaussians, true, fe, p->means3D, p->log_scales, p->unnorm_rotations, p->logit_opacities,
+                          p->rgb_colors, out_image6, nullptr, radii, buf, (cudaStream_t)stream);
+}
+
+int vtgs_fused_backward(const VtgsCamera* cam, const VtgsParams* p, const VtgsPose* pose, const float* dL_dimage4,
+                        int32_t accumulate, VtgsParamGrads* grads, VtgsBuffers* buf, void* stream) {
+    if (int e = check_fused(cam, p, pose, buf)) return e;
+    VTGS_REQUIRE(dL_dimage4 && grads, "pointer is NULL");
+    return launch_fused_backward(cam, p, pose, dL_dimage4, accumulate, grads, buf, (cudaStream_t)stream);
+}
+
+uint64_t vtgs_pose_scratch_floats(int64_t N) { return (uint64_t)((N + 255) / 256 + 1) * 12; }
+
+uint64_t vtgs_loss_scratch_floats(int32_t W, int32_t H, int32_t mode) {
+    (void)mode;
+    const uint64_t P = (uint64_t)W * H;
+    return ((P + 255) / 256 + 1) * 4;
+}
+
+int vtgs_loss(const VtgsCamera* cam, const VtgsLossConfig* cfg, const float* image6, const float* gt_rgb,
+              const float* gt_depth, float* dL_dimage4, float* loss_terms, float* scratch, void* stream) {
+    if (int e = check_cam(cam)) return e;
+    VTGS_REQUIRE(cfg && image6 && gt_rgb && gt_depth && dL_dimage4 && loss_terms && scratch, "pointer is NULL");
+    return launch_loss(cam, cfg, image6, gt_rgb, gt_depth, dL_dimage4, loss_terms, scratch, (cudaStream_t)stream);
+}
+
+int vtgs_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+              float beta2, float eps, int32_t step, const int32_t* step_dev, void* stream) {
+    VTGS_REQUIRE(n >= 0, "n < 0");
+    if (n > 0) VTGS_REQUIRE(param && grad && exp_avg && exp_avg_sq, "pointer is NULL");
+    VTGS_REQUIRE(step_dev != nullptr || step >= 1, "step must be >= 1");
+    return launch_adam(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step, step_dev, (cudaStream_t)stream);
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

@@ -1,0 +1,583 @@
+// backward.cu -- K6' backward blend and K7' backward preprocess (sm_100a).
+//
+// Replaces `_C.rasterize_gaussians_backward` of the reference's external rasteriser
+// (triggered by loss.backward() at reference src/vtgaussian_slam.py:1889,2686; upstream
+// BACKWARD::render / computeCov2DCUDA / preprocessCUDA) and,
+// in fused mode, the autograd chain the reference runs around it: get_depth_and_silhouette
+// (utils/slam_helpers.py:217-234), the activations (:127-160) and transform_to_frame
+// (:323-385) down to the Gaussian parameters and the 7 camera-pose numbers.
+//
+// K6' design: the upstream kernel issues 9-10 global float atomics per contributing
+// (pixel, Gaussian) pair.  Here a warp walks the survivors of its 8x4-pixel region in
+// lock-step (same ballot culling as the forward), reduces the per-pixel terms across the
+// warp with a transposed butterfly (~4 instructions per value instead of 10), adds the
+// warp total to a per-tile shared-memory accumulator, and the tile emits ONE vectorised
+// global reduction per (tile, Gaussian) pair at the end of each staged batch.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace vtgs {
+
+// Sum NV (<= 16) per-lane values across the warp.  On return lane L holds the warp total of
+// value (L >> 1) in v[0].  Each butterfly level halves the number of live values.
+template <int NV>
+__device__ __forceinline__ float warp_transpose_reduce(float (&v)[16], int lane) {
+    static_assert(NV <= 16, "at most 16 values");
+#pragma unroll
+    for (int k = NV; k < 16; ++k) v[k] = 0.0f;
+    {
+        const bool up = lane & 16;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float send = up ? v[i] : v[i + 8];
+            const float keep = up ? v[i + 8] : v[i];
+            v[i] = keep + __shfl_xor_sync(VTGS_FULL_MASK, send, 16);
+        }
+    }
+    {
+        const bool up = lane & 8;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float send = up ? v[i] : v[i + 4];
+            const float keep = up ? v[i + 4] : v[i];
+            v[i] = keep + __shfl_xor_sync(VTGS_FULL_MASK, send, 8);
+        }
+    }
+    {
+        const bool up = lane & 4;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const float send = up ? v[i] : v[i + 2];
+            const float keep = up ? v[i + 2] : v[i];
+            v[i] = keep + __shfl_xor_sync(VTGS_FULL_MASK, send, 4);
+        }
+    }
+    {
+        const bool up = lane & 2;
+        const float send = up ? v[0] : v[1];
+        const float keep = up ? v[1] : v[0];
+        v[0] = keep + __shfl_xor_sync(VTGS_FULL_MASK, send, 2);
+    }
+    v[0] += __shfl_xor_sync(VTGS_FULL_MASK, v[0], 1);
+    return v[0];
+}
+
+// =============================== K6': backward blend =======================================
+// grad_geom record per Gaussian (VTGS_GRAD_GEOM_FLOATS = 16):
+//   [0,1] dL/dmean2D (NDC-scaled)  [2,3,4] dL/dconic (xx, xy, yy)  [5] dL/dopacity
+//   [6..6+NCH) dL/dcolour  (API: r,g,b   fused: r,g,b,z)
+template <bool FUSED>
+__global__ void __launch_bounds__(256)
+blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __restrict__ ranges,
+                      const uint32_t* __restrict__ point_list, const GeomRecord* __restrict__ geom,
+                      const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
+                      const float* __restrict__ dL_dpix, float* __restrict__ grad_geom) {
+    constexpr int NCH = FUSED ? 4 : 3;
+    constexpr int NV = 6 + NCH;
+    constexpr int NVP = 13;                 // padded row of the shared accumulator (odd: no bank conflicts)
+    __shared__ float4 s_q0[256];
+    __shared__ float4 s_q1[256];
+    __shared__ float4 s_q2[256];
+    __shared__ uint32_t s_id[256];
+    __shared__ uint32_t s_mask[8][8];
+    __shared__ float s_acc[256 * NVP];
+    __shared__ uint32_t s_red[8];
+
+    const int tile = cam.row0 * cam.gx + blockIdx.x;
+    const int tile_x = tile % cam.gx, tile_y = tile / cam.gx;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int pix_x = tile_x * 16 + (warp & 1) * 8 + (lane & 7);
+    const int pix_y = tile_y * 16 + (warp >> 1) * 4 + (lane >> 3);
+    const bool inside = pix_x < cam.W && pix_y < cam.H;
+    const float pxf = (float)pix_x, pyf = (float)pix_y;
+    const float tox = (float)(tile_x * 16), toy = (float)(tile_y * 16);
+    const uint32_t rb = ranges[2 * tile], re = ranges[2 * tile + 1];
+    const size_t P = (size_t)cam.W * cam.H;
+    const size_t pid = (size_t)pix_y * cam.W + pix_x;
+
+    const float T_final = inside ? final_T[pid] : 0.0f;
+    const uint32_t last = inside ? n_contrib[pid] : 0u;
+    float dpix[NCH];
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) dpix[ch] = inside ? dL_dpix[ch * P + pid] : 0.0f;
+    const float bg_dot = cam.bg[0] * dpix[0] + cam.bg[1] * dpix[1] + cam.bg[2] * dpix[2];
+    const float ddelx_dx = 0.5f * cam.W, ddely_dy = 0.5f * cam.H;
+
+    // block-wide max of n_contrib: entries beyond it are never touched
+    uint32_t mx = last;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(VTGS_FULL_MASK, mx, o));
+    if (lane == 0) s_red[warp] = mx;
+    for (int k = tid; k < 256 * NVP; k += 256) s_acc[k] = 0.0f;
+    __syncthreads();
+    uint32_t todo = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) todo = max(todo, s_red[w]);
+    todo = min(todo, re - rb);
+    if (todo == 0) return;
+
+    float T = T_final;
+    float accum[NCH], lastc[NCH];
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) { accum[ch] = 0.0f; lastc[ch] = 0.0f; }
+    float last_alpha = 0.0f;
+
+    const int nb = (int)((todo + 255) / 256);
+    for (int b = nb - 1; b >= 0; --b) {
+        const uint32_t pos0 = (uint32_t)b * 256u;
+        const uint32_t pos = pos0 + tid;
+        uint32_t rmask = 0;
+        if (pos < todo) {
+            const uint32_t id = point_list[rb + pos];
+            const GeomRecord* rec = geom + id;
+            const float4 q0 = rec->q0, q1 = rec->q1, q2 = rec->q2, q3 = rec->q3;
+            s_q0[tid] = q0; s_q1[tid] = q1; s_q2[tid] = q2; s_id[tid] = id;
+            const float x0 = q0.x - q1.w - tox, x1 = q0.x + q1.w - tox;
+            const float y0 = q0.y - q3.y - toy, y1 = q0.y + q3.y - toy;
+            const uint32_t cm = ((x1 >= 0.0f && x0 <= 7.0f) ? 1u : 0u) | ((x1 >= 8.0f && x0 <= 15.0f) ? 2u : 0u);
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                if (y1 >= (float)(4 * r) && y0 <= (float)(4 * r + 3)) rmask |= cm << (2 * r);
+        }
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            const uint32_t m = __ballot_sync(VTGS_FULL_MASK, (rmask >> w) & 1u);
+            if (lane == 0) s_mask[w][warp] = m;
+        }
+        __syncthreads();
+
+#pragma unroll 1
+        for (int chunk = 7; chunk >= 0; --chunk) {
+            uint32_t m = s_mask[warp][chunk];
+            while (m) {
+                const int bit = 31 - __clz(m);
+                m &= ~(1u << bit);
+                const int j = chunk * 32 + bit;
+                const uint32_t pos1 = pos0 + (uint32_t)j + 1u;     // 1-based list position
+                const float4 q0 = s_q0[j];
+                const float4 q1 = s_q1[j];
+                const float dx = fsub(q0.x, pxf), dy = fsub(q0.y, pyf);
+                const float power = power_of(q1.x, q1.y, q1.z, dx, dy);
+                bool ok = pos1 <= last && power <= 0.0f && power >= q0.z;
+                float G = 0.0f, alpha = 0.0f;
+                if (ok) {
+                    G = vexpf(power);
+                    alpha = fminf(VTGS_ALPHA_MAX, fmul(q0.w, G));
+                    ok = alpha >= VTGS_ALPHA_MIN;
+                }
+                if (!__any_sync(VTGS_FULL_MASK, ok)) continue;
+                float v[16];
+#pragma unroll
+                for (int k = 0; k < NV; ++k) v[k] = 0.0f;
+                if (ok) {
+                    const float4 q2 = s_q2[j];
+                    const float col[4] = {q2.x, q2.y, q2.z, q2.w};
+                    const float one_m = 1.0f - alpha;
+                    T = __fdividef(T, one_m);
+                    const float dchannel_dcolor = alpha * T;
+                    float dL_dalpha = 0.0f;
+#pragma unroll
+                    for (int ch = 0; ch < NCH; ++ch) {
+                        accum[ch] = last_alpha * lastc[ch] + (1.0f - last_alpha) * accum[ch];
+                        lastc[ch] = col[ch];
+                        dL_dalpha += (col[ch] - accum[ch]) * dpix[ch];
+                        v[6 + ch] = dchannel_dcolor * dpix[ch];
+                    }
+                    dL_dalpha *= T;
+                    last_alpha = alpha;
+                    dL_dalpha += __fdividef(-T_final, one_m) * bg_dot;
+                    const float dL_dG = q0.w * dL_dalpha;
+                    const float gdx = G * dx, gdy = G * dy;
+                    const float dG_ddelx = -gdx * q1.x - gdy * q1.y;
+                    const float dG_ddely = -gdy * q1.z - gdx * q1.y;
+                    v[0] = dL_dG * dG_ddelx * ddelx_dx;
+                    v[1] = dL_dG * dG_ddely * ddely_dy;
+                    v[2] = -0.5f * gdx * dx * dL_dG;
+                    v[3] = -0.5f * gdx * dy * dL_dG;
+                    v[4] = -0.5f * gdy * dy * dL_dG;
+                    v[5] = G * dL_dalpha;
+                }
+                const float tot = warp_transpose_reduce<NV>(v, lane);
+                if ((lane & 1) == 0 && (lane >> 1) < NV) atomicAdd(&s_acc[j * NVP + (lane >> 1)], tot);
+            }
+        }
+        __syncthreads();
+        // flush: one vectorised global reduction per (tile, Gaussian) pair of this batch
+        if (pos < todo) {
+            float a[12];
+            bool any = false;
+#pragma unroll
+            for (int k = 0; k < 12; ++k) {
+                a[k] = k < NV ? s_acc[tid * NVP + k] : 0.0f;
+                any |= a[k] != 0.0f;
+                if (k < NV) s_acc[tid * NVP + k] = 0.0f;
+            }
+            if (any) {
+                float* dst = grad_geom + (size_t)s_id[tid] * VTGS_GRAD_GEOM_FLOATS;
+#pragma unroll
+                for (int k4 = 0; k4 < 3; ++k4) {
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * k4), "f"(a[4 * k4]),
+                                 "f"(a[4 * k4 + 1]), "f"(a[4 * k4 + 2]), "f"(a[4 * k4 + 3])
+                                 : "memory");
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---- shared pieces of K7' -------------------------------------------------------------------
+struct CovGrad {        // outputs of the conic -> cov2D -> {cov3D, mean} chain
+    float dmean[3];     // dL/d(p_view-frame input point), cov path + projection path
+    float dS[3][3];     // dL/dSigma as a full symmetric matrix (off-diagonals halved)
+};
+
+// Appendix A.6 (i)-(iii) for one visible Gaussian.  x,y,z: the point the rasteriser saw.
+__device__ __forceinline__ void cov2d_backward(const CamConst& cam, float x, float y, float z,
+                                               const float* S /*6*/, float gxx, float gxy, float gyy,
+                                               float g2x, float g2y, CovGrad& o) {
+    const float* V = cam.view;
+    const float tx = xform_row(V, 0, x, y, z), ty = xform_row(V, 1, x, y, z), tz = xform_row(V, 2, x, y, z);
+    const float txtz = tx / tz, tytz = ty / tz;
+    const float cx = fminf(cam.limx, fmaxf(-cam.limx, txtz)) * tz;
+    const float cy = fminf(cam.limy, fmaxf(-cam.limy, tytz)) * tz;
+    const float xmul = (txtz < -cam.limx || txtz > cam.limx) ? 0.0f : 1.0f;
+    const float ymul = (tytz < -cam.limy || tytz > cam.limy) ? 0.0f : 1.0f;
+    const float fx = cam.focal_x, fy = cam.focal_y;
+    const float itz = 1.0f / tz, itz2 = itz * itz, itz3 = itz2 * itz;
+    const float J00 = fx * itz, J02 = -(fx * cx) * itz2, J11 = fy * itz, J12 = -(fy * cy) * itz2;
+    float m0[3], m1[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        m0[k] = J02 * V[4 * k + 2] + J00 * V[4 * k + 0];
+        m1[k] = J12 * V[4 * k + 2] + J11 * V[4 * k + 1];
+    }
+    const float Sm[3][3] = {{S[0], S[1], S[2]}, {S[1], S[3], S[4]}, {S[2], S[4], S[5]}};
+    float Sm0[3], Sm1[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        Sm0[k] = Sm[k][0] * m0[0] + Sm[k][1] * m0[1] + Sm[k][2] * m0[2];
+        Sm1[k] = Sm[k][0] * m1[0] + Sm[k][1] * m1[1] + Sm[k][2] * m1[2];
+    }
+    const float a = m0[0] * Sm0[0] + m0[1] * Sm0[1] + m0[2] * Sm0[2] + VTGS_LOWPASS;
+    const float b = m1[0] * Sm0[0] + m1[1] * Sm0[1] + m1[2] * Sm0[2];
+    const float c = m1[0] * Sm1[0] + m1[1] * Sm1[1] + m1[2] * Sm1[2] + VTGS_LOWPASS;
+    const float denom = a * c - b * b;
+    const float d2inv = 1.0f / (denom * denom + 0.0000001f);
+    float dL_da = 0.f, dL_db = 0.f, dL_dc = 0.f;
+    if (d2inv != 0.0f) {
+        dL_da = d2inv * (-c * c * gxx + 2.0f * b * c * gxy + (denom - a * c) * gyy);
+        dL_dc = d2inv * (-a * a * gyy + 2.0f * a * b * gxy + (denom - a * c) * gxx);
+        dL_db = d2inv * 2.0f * (b * c * gxx - (denom + 2.0f * b * b) * gxy + a * b * gyy);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int l = 0; l < 3; ++l)
+            o.dS[k][l] = m0[k] * m0[l] * dL_da + 0.5f * (m0[k] * m1[l] + m0[l] * m1[k]) * dL_db + m1[k] * m1[l] * dL_dc;
+    float dJ00 = 0.f, dJ02 = 0.f, dJ11 = 0.f, dJ12 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float dm0 = 2.0f * Sm0[k] * dL_da + Sm1[k] * dL_db;
+        const float dm1 = 2.0f * Sm1[k] * dL_dc + Sm0[k] * dL_db;
+        dJ00 += dm0 * V[4 * k + 0];
+        dJ02 += dm0 * V[4 * k + 2];
+        dJ11 += dm1 * V[4 * k + 1];
+        dJ12 += dm1 * V[4 * k + 2];
+    }
+    const float dtx = xmul * (-fx * itz2) * dJ02;
+    const float dty = ymul * (-fy * itz2) * dJ12;
+    const float dtz = -fx * itz2 * dJ00 - fy * itz2 * dJ11 + (2.0f * fx * cx) * itz3 * dJ02 + (2.0f * fy * cy) * itz3 * dJ12;
+    const float* Pm = cam.proj;
+    const float hx = xform_row(Pm, 0, x, y, z), hy = xform_row(Pm, 1, x, y, z), hw = xform_row(Pm, 3, x, y, z);
+    const float mw = 1.0f / (hw + VTGS_EPS_W);
+    const float mul1 = hx * mw * mw, mul2 = hy * mw * mw;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        o.dmean[k] = V[4 * k + 0] * dtx + V[4 * k + 1] * dty + V[4 * k + 2] * dtz +
+                     (Pm[4 * k + 0] * mw - Pm[4 * k + 3] * mul1) * g2x + (Pm[4 * k + 1] * mw - Pm[4 * k + 3] * mul2) * g2y;
+    }
+}
+
+// Appendix A.6 (iv): dL/dSigma -> dL/dscale[3], dL/dq[4] (q as passed to the rasteriser).
+__device__ __forceinline__ void cov3d_backward(const float dS[3][3], const float* R, float mod,
+                                               float sx, float sy, float sz, float qr, float qx, float qy, float qz,
+                                               float* dscale, float* dq) {
+    const float sc[3] = {sx, sy, sz};
+    float D[3][3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float sk = mod * sc[k];
+        float Gr[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) Gr[r] = dS[r][0] * R[k] + dS[r][1] * R[3 + k] + dS[r][2] * R[6 + k];
+        const float rGr = R[k] * Gr[0] + R[3 + k] * Gr[1] + R[6 + k] * Gr[2];
+        dscale[k] = 2.0f * sk * rGr * mod;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) D[r][k] = 2.0f * sk * sk * Gr[r];
+    }
+    dq[0] = 2.0f * (qz * (D[1][0] - D[0][1]) + qy * (D[0][2] - D[2][0]) + qx * (D[2][1] - D[1][2]));
+    dq[1] = 2.0f * (qy * (D[0][1] + D[1][0]) + qz * (D[0][2] + D[2][0]) + qr * (D[2][1] - D[1][2])) - 4.0f * qx * (D[1][1] + D[2][2]);
+    dq[2] = 2.0f * (qx * (D[0][1] + D[1][0]) + qr * (D[0][2] - D[2][0]) + qz * (D[1][2] + D[2][1])) - 4.0f * qy * (D[0][0] + D[2][2]);
+    dq[3] = 2.0f * (qr * (D[1][0] - D[0][1]) + qx * (D[0][2] + D[2][0]) + qy * (D[1][2] + D[2][1])) - 4.0f * qz * (D[0][0] + D[1][1]);
+}
+
+// =============================== K7' (API mode) ==============================================
+__global__ void __launch_bounds__(256)
+preprocess_backward_kernel(const __grid_constant__ CamConst cam, int64_t N,
+                           const float* __restrict__ means3D, const float* __restrict__ scales,
+                           const float* __restrict__ rotations, const int32_t* __restrict__ radii_or_null,
+                           const GeomRecord* __restrict__ geom, float* __restrict__ grad_geom,
+                           float* __restrict__ dL_dmeans2D, float* __restrict__ dL_dcolors,
+                           float* __restrict__ dL_dopacity, float* __restrict__ dL_dmeans3D,
+                           float* __restrict__ dL_dscales, float* __restrict__ dL_drot) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= N) return;
+    float4* gg = reinterpret_cast<float4*>(grad_geom + (size_t)i * VTGS_GRAD_GEOM_FLOATS);
+    const float4 g0 = gg[0], g1 = gg[1], g2 = gg[2];
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    gg[0] = zero4; gg[1] = zero4; gg[2] = zero4;       // leave the scratch zeroed for the next backward
+    // visible <=> the forward wrote a record with a non-empty full rect; q1.w (hx) = -1e30 marks culled
+    // culled splats (and splats whose opacity can never reach alpha >= 1/255) carry hx = -1e30:
+    // nothing was blended from them, every gradient is exactly zero
+    const bool visible = geom[i].q1.w > -1e29f;
+    (void)radii_or_null;
+    dL_dmeans2D[3 * i] = g0.x; dL_dmeans2D[3 * i + 1] = g0.y; dL_dmeans2D[3 * i + 2] = 0.0f;
+    dL_dcolors[3 * i] = g1.z; dL_dcolors[3 * i + 1] = g1.w; dL_dcolors[3 * i + 2] = g2.x;
+    dL_dopacity[i] = g1.y;
+    float dmean[3] = {0.f, 0.f, 0.f}, dscale[3] = {0.f, 0.f, 0.f}, dq[4] = {0.f, 0.f, 0.f, 0.f};
+    if (visible) {
+        const float x = means3D[3 * i], y = means3D[3 * i + 1], z = means3D[3 * i + 2];
+        const float sx = scales[3 * i], sy = scales[3 * i + 1], sz = scales[3 * i + 2];
+        const float qr = rotations[4 * i], qx = rotations[4 * i + 1], qy = rotations[4 * i + 2], qz = rotations[4 * i + 3];
+        float R[9], S[6];
+        quat_to_R(qr, qx, qy, qz, R);
+        cov3d_from(sx, sy, sz, cam.scale_modifier, R, S);
+        CovGrad cg;
+        cov2d_backward(cam, x, y, z, S, g0.z, g0.w, g1.x, g0.x, g0.y, cg);
+        cov3d_backward(cg.dS, R, cam.scale_modifier, sx, sy, sz, qr, qx, qy, qz, dscale, dq);
+        dmean[0] = cg.dmean[0]; dmean[1] = cg.dmean[1]; dmean[2] = cg.dmean[2];
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { dL_dmeans3D[3 * i + k] = dmean[k]; dL_dscales[3 * i + k] = dscale[k]; }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) dL_drot[4 * i + k] = dq[k];
+}
+
+int launch_backward(const VtgsCamera* camera, int64_t N,
+                    const float* means3D, const float* scales, const float* rotations,
+                    const float* opacities, const float* colors, const float* dL_dout_color,
+                    float* dL_dmeans2D, float* dL_dcolors, float* dL_dopacity,
+                    float* dL_dmeans3D, float* dL_dscales, float* dL_drotations,
+                    VtgsBuffers* buf, cudaStream_t stream) {
+    (void)opacities; (void)colors;
+    const CamConst cam = make_cam_const(*camera);
+    const GeomRecord* geom = reinterpret_cast<const GeomRecord*>(buf->geom);
+    const int band_tiles = (cam.row1 - cam.row0) * cam.gx;
+    if (N <= 0) return VTGS_OK;
+    if (band_tiles > 0) {
+        blend_backward_kernel<false><<<band_tiles, 256, 0, stream>>>(cam, buf->tile_ranges, buf->point_list, geom, buf->final_T,
+                                                                      buf->n_contrib, dL_dout_color, buf->grad_geom);
+        VTGS_LAUNCH_CHECK();
+    }
+    preprocess_backward_kernel<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(cam, N, means3D, scales, rotations, nullptr, geom,
+                                                                               buf->grad_geom, dL_dmeans2D, dL_dcolors, dL_dopacity,
+                                                                               dL_dmeans3D, dL_dscales, dL_drotations);
+    VTGS_LAUNCH_CHECK();
+    return VTGS_OK;
+}
+
+// =============================== fused path ==================================================
+// Pose matrix of the frame (reference transform_to_frame, utils/slam_helpers.py:339-350 +
+// build_rotation, utils/slam_external.py:25-42): q = F.normalize(cam_unnorm_rot), then
+// build_rotation normalises once more.  Spec'd fp32 order, mirrored by the oracle.
+__global__ void pose_matrix_kernel(const float* __restrict__ q_un, const float* __restrict__ t, VtgsCounters* __restrict__ c) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const float u0 = q_un[0], u1 = q_un[1], u2 = q_un[2], u3 = q_un[3];
+    const float n1 = __fsqrt_rn(ffma(u3, u3, ffma(u2, u2, ffma(u1, u1, fmul(u0, u0)))));
+    const float d1 = fmaxf(n1, 1e-12f);
+    const float q0 = __fdiv_rn(u0, d1), q1 = __fdiv_rn(u1, d1), q2 = __fdiv_rn(u2, d1), q3 = __fdiv_rn(u3, d1);
+    const float n2 = __fsqrt_rn(ffma(q3, q3, ffma(q2, q2, ffma(q1, q1, fmul(q0, q0)))));
+    float R[9];
+    quat_to_R(__fdiv_rn(q0, n2), __fdiv_rn(q1, n2), __fdiv_rn(q2, n2), __fdiv_rn(q3, n2), R);
+    for (int k = 0; k < 9; ++k) c->pose_R[k] = R[k];
+    c->pose_t[0] = t[0]; c->pose_t[1] = t[1]; c->pose_t[2] = t[2];
+    c->pose_q[0] = q0; c->pose_q[1] = q1; c->pose_q[2] = q2; c->pose_q[3] = q3;
+    c->pose_qnorm[0] = n1; c->pose_qnorm[1] = n2;
+}
+
+int launch_pose_matrix(const VtgsPose* pose, VtgsCounters* counters, cudaStream_t stream) {
+    pose_matrix_kernel<<<1, 32, 0, stream>>>(pose->cam_unnorm_rot, pose->cam_trans, counters);
+    VTGS_LAUNCH_CHECK();
+    return VTGS_OK;
+}
+
+constexpr int POSE_TERMS = 12;       // sum g (3) and sum g p^T (9)
+
+// Fused K7': per-Gaussian parameter gradients + block partial sums of the pose terms.
+__global__ void __launch_bounds__(256)
+fused_preprocess_backward_kernel(const __grid_constant__ CamConst cam, int64_t N, VtgsParams prm,
+                                 const float* __restrict__ pose_Rt, float dr0, float dr1, float dr2,
+                                 const GeomRecord* __restrict__ geom, float* __restrict__ grad_geom,
+                                 VtgsParamGrads out, int accumulate, int want_pose) {
+    __shared__ float s_part[8][POSE_TERMS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t i = (int64_t)blockIdx.x * 256 + tid;
+    float pose_v[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) pose_v[k] = 0.0f;
+    if (i < N) {
+        float4* gg = reinterpret_cast<float4*>(grad_geom + (size_t)i * VTGS_GRAD_GEOM_FLOATS);
+        const float4 g0 = gg[0], g1 = gg[1], g2 = gg[2];
+        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        gg[0] = zero4; gg[1] = zero4; gg[2] = zero4;
+        const GeomRecord rec = geom[i];
+        const bool visible = rec.q1.w > -1e29f;
+        float dmeanw[3] = {0.f, 0.f, 0.f}, dls = 0.f, dlogit = 0.f, dqu[4] = {0.f, 0.f, 0.f, 0.f};
+        if (visible) {
+            float Rt[12];
+#pragma unroll
+            for (int k = 0; k < 12; ++k) Rt[k] = __ldg(pose_Rt + k);
+            const float px = prm.means3D[3 * i], py = prm.means3D[3 * i + 1], pz = prm.means3D[3 * i + 2];
+            const float x = fadd(ffma(Rt[2], pz, ffma(Rt[1], py, fmul(Rt[0], px))), Rt[9]);
+            const float y = fadd(ffma(Rt[5], pz, ffma(Rt[4], py, fmul(Rt[3], px))), Rt[10]);
+            const float z = fadd(ffma(Rt[8], pz, ffma(Rt[7], py, fmul(Rt[6], px))), Rt[11]);
+            const float s = vexpf(prm.log_scales[i]);
+            float u[4] = {prm.unnorm_rotations[4 * i], prm.unnorm_rotations[4 * i + 1], prm.unnorm_rotations[4 * i + 2], prm.unnorm_rotations[4 * i + 3]};
+            const float nrm = sqrtf(u[0] * u[0] + u[1] * u[1] + u[2] * u[2] + u[3] * u[3]);
+            const float d = fmaxf(nrm, 1e-12f);
+            const float q[4] = {u[0] / d, u[1] / d, u[2] / d, u[3] / d};
+            float R[9], S[6];
+            quat_to_R(q[0], q[1], q[2], q[3], R);
+            cov3d_from(s, s, s, cam.scale_modifier, R, S);
+            CovGrad cg;
+            cov2d_backward(cam, x, y, z, S, g0.z, g0.w, g1.x, g0.x, g0.y, cg);
+            float dscale[3], dq[4];
+            cov3d_backward(cg.dS, R, cam.scale_modifier, s, s, s, q[0], q[1], q[2], q[3], dscale, dq);
+            // chain through get_depth_and_silhouette: colour channel 3 is z_cam = depth_row . (p', 1)
+            const float dz = g2.y;
+            const float gm[3] = {cg.dmean[0] + dr0 * dz, cg.dmean[1] + dr1 * dz, cg.dmean[2] + dr2 * dz};
+            // p' = R p + t
+            dmeanw[0] = Rt[0] * gm[0] + Rt[3] * gm[1] + Rt[6] * gm[2];
+            dmeanw[1] = Rt[1] * gm[0] + Rt[4] * gm[1] + Rt[7] * gm[2];
+            dmeanw[2] = Rt[2] * gm[0] + Rt[5] * gm[1] + Rt[8] * gm[2];
+            dls = (dscale[0] + dscale[1] + dscale[2]) * s;            // d exp(ls)/d ls, tiled x3
+            const float o = rec.q0.w;
+            dlogit = g1.y * o * (1.0f - o);
+            // F.normalize backward
+            const float qd = q[0] * dq[0] + q[1] * dq[1] + q[2] * dq[2] + q[3] * dq[3];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) dqu[k] = nrm >= 1e-12f ? (dq[k] - q[k] * qd) / d : dq[k] / d;
+            pose_v[0] = gm[0]; pose_v[1] = gm[1]; pose_v[2] = gm[2];
+            pose_v[3] = gm[0] * px; pose_v[4] = gm[0] * py; pose_v[5] = gm[0] * pz;
+            pose_v[6] = gm[1] * px; pose_v[7] = gm[1] * py; pose_v[8] = gm[1] * pz;
+            pose_v[9] = gm[2] * px; pose_v[10] = gm[2] * py; pose_v[11] = gm[2] * pz;
+        }
+        if (accumulate) {
+            if (out.means3D) { out.means3D[3 * i] += dmeanw[0]; out.means3D[3 * i + 1] += dmeanw[1]; out.means3D[3 * i + 2] += dmeanw[2]; }
+            if (out.rgb_colors) { out.rgb_colors[3 * i] += g1.z; out.rgb_colors[3 * i + 1] += g1.w; out.rgb_colors[3 * i + 2] += g2.x; }
+            if (out.unnorm_rotations) for (int k = 0; k < 4; ++k) out.unnorm_rotations[4 * i + k] += dqu[k];
+            if (out.logit_opacities) out.logit_opacities[i] += dlogit;
+            if (out.log_scales) out.log_scales[i] += dls;
+            if (out.means2D) { out.means2D[3 * i] += g0.x; out.means2D[3 * i + 1] += g0.y; }
+        } else {
+            if (out.means3D) { out.means3D[3 * i] = dmeanw[0]; out.means3D[3 * i + 1] = dmeanw[1]; out.means3D[3 * i + 2] = dmeanw[2]; }
+            if (out.rgb_colors) { out.rgb_colors[3 * i] = g1.z; out.rgb_colors[3 * i + 1] = g1.w; out.rgb_colors[3 * i + 2] = g2.x; }
+            if (out.unnorm_rotations) for (int k = 0; k < 4; ++k) out.unnorm_rotations[4 * i + k] = dqu[k];
+            if (out.logit_opacities) out.logit_opacities[i] = dlogit;
+            if (out.log_scales) out.log_scales[i] = dls;
+            if (out.means2D) { out.means2D[3 * i] = g0.x; out.means2D[3 * i + 1] = g0.y; out.means2D[3 * i + 2] = 0.0f; }
+        }
+    }
+    if (!want_pose) return;
+    const float tot = warp_transpose_reduce<POSE_TERMS>(pose_v, lane);
+    if ((lane & 1) == 0 && (lane >> 1) < POSE_TERMS) s_part[warp][lane >> 1] = tot;
+    __syncthreads();
+    if (tid < POSE_TERMS) {
+        float s = 0.0f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += s_part[w][tid];
+        out.pose_scratch[(size_t)blockIdx.x * POSE_TERMS + tid] = s;
+    }
+}
+
+// Deterministic final reduction of the block partials (fixed order, fp64) and the chain
+// dL/dR, dL/dt -> cam_unnorm_rot, cam_trans through build_rotation and the two normalisations.
+__global__ void __launch_bounds__(256)
+pose_finalize_kernel(const float* __restrict__ partials, int nblocks, const VtgsCounters* __restrict__ c,
+                     float* __restrict__ d_rot, float* __restrict__ d_trans, int accumulate) {
+    __shared__ double s_sum[POSE_TERMS][32];
+    const int tid = threadIdx.x;
+    // 12 terms x 16 strided lanes, each sums its slice in index order; then a fixed tree
+    if (tid < POSE_TERMS * 16) {
+        const int term = tid / 16, l = tid % 16;
+        double acc = 0.0;
+        for (int b = l; b < nblocks; b += 16) acc += (double)partials[(size_t)b * POSE_TERMS + term];
+        s_sum[term][l] = acc;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double tot[POSE_TERMS];
+        for (int k = 0; k < POSE_TERMS; ++k) {
+            double a = 0.0;
+            for (int l = 0; l < 16; ++l) a += s_sum[k][l];
+            tot[k] = a;
+        }
+        // D[r][k] = dL/dR[r][k] = sum g_r p_k
+        const double D[3][3] = {{tot[3], tot[4], tot[5]}, {tot[6], tot[7], tot[8]}, {tot[9], tot[10], tot[11]}};
+        const double n1 = c->pose_qnorm[0], n2 = c->pose_qnorm[1];
+        const double q[4] = {c->pose_q[0], c->pose_q[1], c->pose_q[2], c->pose_q[3]};
+        const double qq[4] = {q[0] / n2, q[1] / n2, q[2] / n2, q[3] / n2};
+        const double qr = qq[0], qx = qq[1], qy = qq[2], qz = qq[3];
+        double dqq[4];
+        dqq[0] = 2.0 * (qz * (D[1][0] - D[0][1]) + qy * (D[0][2] - D[2][0]) + qx * (D[2][1] - D[1][2]));
+        dqq[1] = 2.0 * (qy * (D[0][1] + D[1][0]) + qz * (D[0][2] + D[2][0]) + qr * (D[2][1] - D[1][2])) - 4.0 * qx * (D[1][1] + D[2][2]);
+        dqq[2] = 2.0 * (qx * (D[0][1] + D[1][0]) + qr * (D[0][2] - D[2][0]) + qz * (D[1][2] + D[2][1])) - 4.0 * qy * (D[0][0] + D[2][2]);
+        dqq[3] = 2.0 * (qr * (D[1][0] - D[0][1]) + qx * (D[0][2] + D[2][0]) + qy * (D[1][2] + D[2][1])) - 4.0 * qz * (D[0][0] + D[1][1]);
+        // qq = q / |q|
+        double dot = qq[0] * dqq[0] + qq[1] * dqq[1] + qq[2] * dqq[2] + qq[3] * dqq[3];
+        double dq[4];
+        for (int k = 0; k < 4; ++k) dq[k] = (dqq[k] - qq[k] * dot) / n2;
+        // q = u / max(|u|, eps)
+        const double d1 = n1 > 1e-12 ? n1 : 1e-12;
+        dot = q[0] * dq[0] + q[1] * dq[1] + q[2] * dq[2] + q[3] * dq[3];
+        for (int k = 0; k < 4; ++k) {
+            const double du = n1 >= 1e-12 ? (dq[k] - q[k] * dot) / d1 : dq[k] / d1;
+            if (accumulate) d_rot[k] += (float)du; else d_rot[k] = (float)du;
+        }
+        for (int k = 0; k < 3; ++k) {
+            if (accumulate) d_trans[k] += (float)tot[k]; else d_trans[k] = (float)tot[k];
+        }
+    }
+}
+
+int launch_fused_backward(const VtgsCamera* camera, const VtgsParams* params, const VtgsPose* pose,
+                          const float* dL_dimage4, int accumulate, VtgsParamGrads* grads,
+                          VtgsBuffers* buf, cudaStream_t stream) {
+    const CamConst cam = make_cam_const(*camera);
+    const int64_t N = params->num_gaussians;
+    const GeomRecord* geom = reinterpret_cast<const GeomRecord*>(buf->geom);
+    const int band_tiles = (cam.row1 - cam.row0) * cam.gx;
+    const int want_pose = (grads->cam_unnorm_rot != nullptr && grads->cam_trans != nullptr) ? 1 : 0;
+    if (want_pose && grads->pose_scratch == nullptr) { set_error("pose gradients need pose_scratch"); return VTGS_E_INVALID; }
+    const int blocks = (int)((N + 255) / 256);
+    if (N > 0) {
+        if (band_tiles > 0) {
+            blend_backward_kernel<true><<<band_tiles, 256, 0, stream>>>(cam, buf->tile_ranges, buf->point_list, geom, buf->final_T,
+                                                                         buf->n_contrib, dL_dimage4, buf->grad_geom);
+            VTGS_LAUNCH_CHECK();
+        }
+        fused_preprocess_backward_kernel<<<blocks, 256, 0, stream>>>(cam, N, *params, buf->counters->pose_R, pose->depth_row[0],
+                                                                     pose->depth_row[1], pose->depth_row[2], geom, buf->grad_geom,
+                                                                     *grads, accumulate, want_pose);
+        VTGS_LAUNCH_CHECK();
+    }
+    if (want_pose) {
+        pose_finalize_kernel<<<1, 256, 0, stream>>>(grads->pose_scratch, N > 0 ? blocks : 0, buf->counters, grads->cam_unnorm_rot,
+                                                    grads->cam_trans, accumulate);
+        VTGS_LAUNCH_CHECK();
+    }
+    return VTGS_OK;
+}
+
+}  // namespace vtgs

@@ -1,0 +1,492 @@
+// forward.cu -- K1' preprocess, K2'-K5a' tile binning, K5' front-to-back blend (sm_100a).
+//
+// Replaces the forward half of the reference's external rasteriser
+// (`_C.rasterize_gaussians`, called at reference src/vtgaussian_slam.py:461,466,747):
+// upstream preprocessCUDA / InclusiveSum / duplicateWithKeys / DeviceRadixSort /
+// identifyTileRanges / renderCUDA.
+//
+// Design:
+//  * binning is an MSD radix sort on the 64-bit (tile | depth) key: the tile digit is a
+//    counting sort (per-tile histogram in preprocess, a one-block scan that also yields the
+//    tile ranges, an atomic-cursor scatter), the 32 depth bits (+ Gaussian id as the
+//    stable tie-break) are sorted per tile in shared memory.  The sorted order is
+//    (tile, depth bits, Gaussian index) -- exactly what the reference's stable LSD sort
+//    of its duplicateWithKeys output produces.
+//  * the blend kernel culls each staged batch against its eight 8x4-pixel warp regions
+//    with one ballot per region, so a warp only evaluates splats whose alpha >= 1/255
+//    ellipse can touch its pixels (view-tied splats are ~1 px wide: ~70% of the
+//    upstream pair tests disappear) while list positions (n_contrib) stay exact.
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace vtgs {
+
+// =============================== K1': preprocess =========================================
+// One thread per Gaussian.  [N,3] arrays are staged through shared memory so that global
+// loads are unit-stride; rotations are float4 loads when 16-byte aligned.
+template <bool FUSED>
+__global__ void __launch_bounds__(256)
+preprocess_kernel(const __grid_constant__ CamConst cam, int64_t N, FrontEnd fe,
+                  const float* __restrict__ means3D, const float* __restrict__ scales,
+                  const float* __restrict__ rotations, const float* __restrict__ opacities,
+                  const float* __restrict__ colors,
+                  GeomRecord* __restrict__ geom, int32_t* __restrict__ radii,
+                  uint32_t* __restrict__ tiles_touched, uint32_t* __restrict__ tile_counts) {
+    __shared__ float s_a[256 * 3];
+    __shared__ float s_b[256 * 3];
+    __shared__ float s_c[256 * 3];
+    const int64_t base = (int64_t)blockIdx.x * 256;
+    const int tid = threadIdx.x;
+    const int64_t i = base + tid;
+    const int64_t remain = N - base;
+    const int cnt3 = (int)(remain < 256 ? remain : 256) * 3;
+    for (int k = tid; k < cnt3; k += 256) {
+        s_a[k] = means3D[base * 3 + k];
+        s_c[k] = colors[base * 3 + k];
+        if (!FUSED || fe.log_scales_dim == 3) s_b[k] = scales[base * 3 + k];
+    }
+    __syncthreads();
+    if (i >= N) return;
+
+    float x = s_a[3 * tid], y = s_a[3 * tid + 1], z = s_a[3 * tid + 2];
+    float sx, sy, sz, qr, qx, qy, qz, op, c3;
+    {
+        float4 q;
+        if ((reinterpret_cast<uintptr_t>(rotations) & 15) == 0) q = reinterpret_cast<const float4*>(rotations)[i];
+        else q = make_float4(rotations[4 * i], rotations[4 * i + 1], rotations[4 * i + 2], rotations[4 * i + 3]);
+        qr = q.x; qx = q.y; qy = q.z; qz = q.w;
+    }
+    if (FUSED) {
+        // transform_to_frame + activations (reference utils/slam_helpers.py:323-385,127-160):
+        // p' = R p + t, scales = exp(log_scales), opacity = sigmoid(logit), q = normalize(q)
+        float Rt[12];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) Rt[k] = __ldg(fe.pose_Rt + k);
+        const float X = fadd(ffma(Rt[2], z, ffma(Rt[1], y, fmul(Rt[0], x))), Rt[9]);
+        const float Y = fadd(ffma(Rt[5], z, ffma(Rt[4], y, fmul(Rt[3], x))), Rt[10]);
+        const float Z = fadd(ffma(Rt[8], z, ffma(Rt[7], y, fmul(Rt[6], x))), Rt[11]);
+        x = X; y = Y; z = Z;
+        if (fe.log_scales_dim == 3) {
+            sx = vexpf(s_b[3 * tid]); sy = vexpf(s_b[3 * tid + 1]); sz = vexpf(s_b[3 * tid + 2]);
+        } else {
+            sx = sy = sz = vexpf(scales[i]);
+        }
+        const float nrm = __fsqrt_rn(ffma(qz, qz, ffma(qy, qy, ffma(qx, qx, fmul(qr, qr)))));
+        const float d = fmaxf(nrm, 1e-12f);
+        qr = __fdiv_rn(qr, d); qx = __fdiv_rn(qx, d); qy = __fdiv_rn(qy, d); qz = __fdiv_rn(qz, d);
+        op = __fdiv_rn(1.0f, fadd(1.0f, vexpf(-opacities[i])));
+        // get_depth_and_silhouette (reference utils/slam_helpers.py:217-234): z of w2c * p'
+        c3 = fadd(ffma(fe.depth_row[2], z, ffma(fe.depth_row[1], y, fmul(fe.depth_row[0], x))), fe.depth_row[3]);
+    } else {
+        sx = s_b[3 * tid]; sy = s_b[3 * tid + 1]; sz = s_b[3 * tid + 2];
+        op = opacities[i];
+        c3 = 0.0f;
+    }
+
+    SplatGeom g;
+    splat_geometry(cam, x, y, z, sx, sy, sz, qr, qx, qy, qz, g);
+    if (!FUSED) c3 = g.depth;
+
+    GeomRecord rec;
+    uint32_t tiles = 0;
+    if (g.radius > 0) {
+        const int miny = max(g.miny, cam.row0), maxy = min(g.maxy, cam.row1);
+        const int hgt = max(0, maxy - miny);
+        tiles = (uint32_t)((g.maxx - g.minx) * hgt);
+        float pthr, hx, hy;
+        cull_bounds(op, g.cov_a, g.cov_c, pthr, hx, hy);
+        rec.q0 = make_float4(g.px, g.py, pthr, op);
+        rec.q1 = make_float4(g.A, g.B, g.C, hx);
+        rec.q2 = make_float4(s_c[3 * tid], s_c[3 * tid + 1], s_c[3 * tid + 2], c3);
+        rec.q3 = make_float4(g.depth, hy, __uint_as_float((uint32_t)g.minx | ((uint32_t)miny << 16)),
+                             __uint_as_float((uint32_t)g.maxx | ((uint32_t)(hgt > 0 ? maxy : miny) << 16)));
+        for (int ty = miny; ty < maxy; ++ty)
+            for (int tx = g.minx; tx < g.maxx; ++tx) atomicAdd(&tile_counts[ty * cam.gx + tx], 1u);
+    } else {
+        rec.q0 = make_float4(0.f, 0.f, 1.0f, 0.f);
+        rec.q1 = make_float4(0.f, 0.f, 0.f, -1e30f);
+        rec.q2 = make_float4(0.f, 0.f, 0.f, 0.f);
+        rec.q3 = make_float4(g.depth, -1e30f, __uint_as_float(0u), __uint_as_float(0u));
+    }
+    geom[i] = rec;
+    radii[i] = g.radius;
+    tiles_touched[i] = tiles;
+}
+
+// =============================== K2'/K5a': tile scan = tile ranges =========================
+// One block.  Exclusive scan of the per-tile counts gives each tile's [begin, end) in the
+// sorted list directly (identifyTileRanges for free); counts are re-zeroed to serve as the
+// scatter cursors.  Empty tiles get (0,0) like the reference's memset.
+__global__ void __launch_bounds__(1024)
+tile_scan_kernel(uint32_t* __restrict__ tile_counts, uint32_t* __restrict__ ranges, int num_tiles,
+                 uint64_t capacity, VtgsCounters* __restrict__ counters) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    __shared__ uint32_t s_max[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    uint32_t vmax = 0;
+    __syncthreads();
+    for (int base = 0; base < num_tiles; base += 1024) {
+        const int t = base + tid;
+        const uint32_t c = t < num_tiles ? tile_counts[t] : 0u;
+        vmax = max(vmax, c);
+        uint32_t incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t n = __shfl_up_sync(VTGS_FULL_MASK, incl, o);
+            if (lane >= o) incl += n;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = s_warp[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t n = __shfl_up_sync(VTGS_FULL_MASK, w, o);
+                if (lane >= o) w += n;
+            }
+            s_warp[lane] = w;     // inclusive over warps
+        }
+        __syncthreads();
+        const uint32_t carry = s_carry;
+        const uint32_t excl = carry + (warp > 0 ? s_warp[warp - 1] : 0u) + incl - c;
+        if (t < num_tiles) {
+            uint64_t b = excl, e = (uint64_t)excl + c;
+            if (b > capacity) b = capacity;
+            if (e > capacity) e = capacity;
+            if (c == 0) { b = 0; e = 0; }
+            ranges[2 * t] = (uint32_t)b;
+            ranges[2 * t + 1] = (uint32_t)e;
+            tile_counts[t] = 0;
+        }
+        __syncthreads();
+        if (tid == 1023) s_carry = carry + s_warp[31];
+        __syncthreads();
+    }
+    vmax = max(vmax, __shfl_xor_sync(VTGS_FULL_MASK, vmax, 16));
+    vmax = max(vmax, __shfl_xor_sync(VTGS_FULL_MASK, vmax, 8));
+    vmax = max(vmax, __shfl_xor_sync(VTGS_FULL_MASK, vmax, 4));
+    vmax = max(vmax, __shfl_xor_sync(VTGS_FULL_MASK, vmax, 2));
+    vmax = max(vmax, __shfl_xor_sync(VTGS_FULL_MASK, vmax, 1));
+    if (lane == 0) s_max[warp] = vmax;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t m = 0;
+        for (int w = 0; w < 32; ++w) m = max(m, s_max[w]);
+        const uint32_t total = s_carry;
+        counters->num_rendered = total;
+        counters->overflow = (uint64_t)total > capacity ? 1u : 0u;
+        counters->max_tile_pairs = m;
+    }
+}
+
+// =============================== K3': scatter (duplicateWithKeys) ==========================
+// One thread per Gaussian: for every touched tile claim a slot in that tile's segment and
+// store (depth_bits << 32 | id).  Slot order inside a segment is arbitrary; the per-tile
+// sort on the composite key makes the final order deterministic.
+__global__ void __launch_bounds__(256)
+scatter_kernel(int64_t N, int gx, const GeomRecord* __restrict__ geom, const uint32_t* __restrict__ tiles_touched,
+               const uint32_t* __restrict__ ranges, uint32_t* __restrict__ tile_cursor,
+               uint64_t* __restrict__ pair_keys) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= N) return;
+    if (tiles_touched[i] == 0) return;
+    const float4 q3 = geom[i].q3;
+    const uint32_t rmin = __float_as_uint(q3.z), rmax = __float_as_uint(q3.w);
+    const int minx = rmin & 0xffff, miny = rmin >> 16, maxx = rmax & 0xffff, maxy = rmax >> 16;
+    const uint64_t key = ((uint64_t)__float_as_uint(q3.x) << 32) | (uint64_t)(uint32_t)i;
+    for (int ty = miny; ty < maxy; ++ty)
+        for (int tx = minx; tx < maxx; ++tx) {
+            const int t = ty * gx + tx;
+            const uint32_t pos = ranges[2 * t] + atomicAdd(&tile_cursor[t], 1u);
+            if (pos < ranges[2 * t + 1]) pair_keys[pos] = key;
+        }
+}
+
+// =============================== K4': per-tile sort ========================================
+// One block per tile.  Normalised bitonic network (every compare-exchange ascending, the
+// first sub-step of each merge mirrors the index) so that indices >= n act as +inf padding
+// without being stored.  Segments up to SORT_SMEM_ELEMS are sorted in shared memory;
+// longer ones in place in global memory (same network, block-local barriers).
+constexpr int SORT_SMEM_ELEMS = 4096;
+
+__device__ __forceinline__ void bitonic_network(uint64_t* __restrict__ s, int n, int npad) {
+    for (int k = 2; k <= npad; k <<= 1) {
+        // flip step
+        {
+            const int half = k >> 1;
+            for (int t = threadIdx.x; t < (npad >> 1); t += blockDim.x) {
+                const int blk = t / half, off = t - blk * half;
+                const int i = blk * k + off, p = blk * k + (k - 1 - off);
+                if (p < n) {
+                    const uint64_t a = s[i], b = s[p];
+                    if (a > b) { s[i] = b; s[p] = a; }
+                }
+            }
+            __syncthreads();
+        }
+        for (int j = k >> 2; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < (npad >> 1); t += blockDim.x) {
+                const int i = ((t / j) * (j << 1)) + (t % j), p = i + j;
+                if (p < n) {
+                    const uint64_t a = s[i], b = s[p];
+                    if (a > b) { s[i] = b; s[p] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+tile_sort_kernel(const uint32_t* __restrict__ ranges, int tile0, uint64_t* __restrict__ pair_keys,
+                 uint32_t* __restrict__ point_list) {
+    extern __shared__ __align__(16) uint64_t s_keys[];
+    const int tile = tile0 + blockIdx.x;
+    const uint32_t b = ranges[2 * tile], e = ranges[2 * tile + 1];
+    const int n = (int)(e - b);
+    if (n <= 0) return;
+    int npad = 2;
+    while (npad < n) npad <<= 1;
+    if (n <= SORT_SMEM_ELEMS) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) s_keys[i] = pair_keys[b + i];
+        __syncthreads();
+        bitonic_network(s_keys, n, npad);
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const uint64_t k = s_keys[i];
+            point_list[b + i] = (uint32_t)k;
+            pair_keys[b + i] = k;
+        }
+    } else {
+        __syncthreads();
+        bitonic_network(pair_keys + b, n, npad);
+        for (int i = threadIdx.x; i < n; i += blockDim.x) point_list[b + i] = (uint32_t)pair_keys[b + i];
+    }
+}
+
+// =============================== K5': forward blend ========================================
+// Block = one 16x16 tile, 8 warps; warp w owns the 8x4-pixel region (w&1, w>>1).
+// NCH_OUT planes: API mode 3 colours (+ depth plane), fused mode r,g,b,z,sil,z^2.
+template <bool FUSED>
+__global__ void __launch_bounds__(256)
+blend_forward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __restrict__ ranges,
+                     const uint32_t* __restrict__ point_list, const GeomRecord* __restrict__ geom,
+                     float* __restrict__ out_color, float* __restrict__ out_depth,
+                     float* __restrict__ final_T, uint32_t* __restrict__ n_contrib) {
+    __shared__ float4 s_q0[256];
+    __shared__ float4 s_q1[256];
+    __shared__ float4 s_q2[256];
+    __shared__ uint32_t s_mask[8][8];      // [region][chunk of 32 staged entries]
+
+    const int tile = cam.row0 * cam.gx + blockIdx.x;
+    const int tile_x = tile % cam.gx, tile_y = tile / cam.gx;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int pix_x = tile_x * 16 + (warp & 1) * 8 + (lane & 7);
+    const int pix_y = tile_y * 16 + (warp >> 1) * 4 + (lane >> 3);
+    const bool inside = pix_x < cam.W && pix_y < cam.H;
+    const float pxf = (float)pix_x, pyf = (float)pix_y;
+    const float tox = (float)(tile_x * 16), toy = (float)(tile_y * 16);
+
+    const uint32_t rb = ranges[2 * tile], re = ranges[2 * tile + 1];
+
+    float T = 1.0f;
+    float C0 = 0.f, C1 = 0.f, C2 = 0.f, C3 = 0.f, C4 = 0.f, C5 = 0.f;
+    uint32_t last = 0;
+    bool done = !inside;
+
+    for (uint32_t base = rb; base < re; base += 256) {
+        if (__syncthreads_and(done)) break;
+        const uint32_t idx = base + tid;
+        uint32_t rmask = 0;
+        if (idx < re) {
+            const uint32_t id = point_list[idx];
+            const GeomRecord* rec = geom + id;
+            const float4 q0 = rec->q0, q1 = rec->q1, q2 = rec->q2, q3 = rec->q3;
+            s_q0[tid] = q0; s_q1[tid] = q1; s_q2[tid] = q2;
+            const float x0 = q0.x - q1.w - tox, x1 = q0.x + q1.w - tox;
+            const float y0 = q0.y - q3.y - toy, y1 = q0.y + q3.y - toy;
+            const uint32_t cm = ((x1 >= 0.0f && x0 <= 7.0f) ? 1u : 0u) | ((x1 >= 8.0f && x0 <= 15.0f) ? 2u : 0u);
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                if (y1 >= (float)(4 * r) && y0 <= (float)(4 * r + 3)) rmask |= cm << (2 * r);
+        }
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            const uint32_t m = __ballot_sync(VTGS_FULL_MASK, (rmask >> w) & 1u);
+            if (lane == 0) s_mask[w][warp] = m;
+        }
+        __syncthreads();
+        const uint32_t pos0 = base - rb;
+#pragma unroll 1
+        for (int chunk = 0; chunk < 8; ++chunk) {
+            uint32_t m = s_mask[warp][chunk];
+            if (m == 0) continue;
+            if (__all_sync(VTGS_FULL_MASK, done)) break;
+            while (m) {
+                const int bit = __ffs(m) - 1;
+                m &= m - 1;
+                const int j = chunk * 32 + bit;
+                const float4 q0 = s_q0[j];
+                const float4 q1 = s_q1[j];
+                const float dx = fsub(q0.x, pxf), dy = fsub(q0.y, pyf);
+                const float power = power_of(q1.x, q1.y, q1.z, dx, dy);
+                if (!done && power <= 0.0f && power >= q0.z) {
+                    const float alpha = fminf(VTGS_ALPHA_MAX, fmul(q0.w, vexpf(power)));
+                    if (alpha >= VTGS_ALPHA_MIN) {
+                        const float test_T = fmul(T, fsub(1.0f, alpha));
+                        if (test_T < VTGS_T_MIN) {
+                            done = true;
+                        } else {
+                            const float4 q2 = s_q2[j];
+                            C0 = ffma(fmul(q2.x, alpha), T, C0);
+                            C1 = ffma(fmul(q2.y, alpha), T, C1);
+                            C2 = ffma(fmul(q2.z, alpha), T, C2);
+                            C3 = ffma(fmul(q2.w, alpha), T, C3);
+                            if (FUSED) {
+                                C4 = ffma(alpha, T, C4);                               // 1.0 * alpha * T
+                                C5 = ffma(fmul(fmul(q2.w, q2.w), alpha), T, C5);
+                            }
+                            T = test_T;
+                            last = pos0 + (uint32_t)j + 1u;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (inside) {
+        const size_t P = (size_t)cam.W * cam.H;
+        const size_t pid = (size_t)pix_y * cam.W + pix_x;
+        final_T[pid] = T;
+        n_contrib[pid] = last;
+        out_color[pid] = ffma(T, cam.bg[0], C0);
+        out_color[P + pid] = ffma(T, cam.bg[1], C1);
+        out_color[2 * P + pid] = ffma(T, cam.bg[2], C2);
+        if (FUSED) {
+            out_color[3 * P + pid] = C3;
+            out_color[4 * P + pid] = C4;
+            out_color[5 * P + pid] = C5;
+        } else {
+            out_depth[pid] = C3;
+        }
+    }
+}
+
+// Rows outside the band keep the background (multi-GPU tracking: each rank owns a band).
+__global__ void fill_outside_band_kernel(const __grid_constant__ CamConst cam, int planes,
+                                         float* __restrict__ out_color, float* __restrict__ out_depth,
+                                         float* __restrict__ final_T, uint32_t* __restrict__ n_contrib) {
+    const size_t P = (size_t)cam.W * cam.H;
+    const size_t pid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pid >= P) return;
+    const int y = (int)(pid / cam.W);
+    if (y >= cam.row0 * 16 && y < cam.row1 * 16) return;
+    final_T[pid] = 1.0f;
+    n_contrib[pid] = 0;
+    for (int ch = 0; ch < planes; ++ch) out_color[ch * P + pid] = ch < 3 ? cam.bg[ch] : 0.0f;
+    if (out_depth) out_depth[pid] = 0.0f;
+}
+
+// =============================== host orchestration ======================================
+int launch_forward(const VtgsCamera* camera, int64_t N, bool fused, const FrontEnd& fe,
+                   const float* means3D, const float* scales, const float* rotations,
+                   const float* opacities, const float* colors,
+                   float* out_color, float* out_depth, int32_t* radii, VtgsBuffers* buf,
+                   cudaStream_t stream) {
+    const CamConst cam = make_cam_const(*camera);
+    const int num_tiles = cam.gx * cam.gy;
+    if (cam.gx > 0xffff || cam.gy > 0xffff) { set_error("image too large for packed tile rects"); return VTGS_E_INVALID; }
+    GeomRecord* geom = reinterpret_cast<GeomRecord*>(buf->geom);
+    VTGS_CUDA_CHECK(cudaMemsetAsync(buf->tile_counts, 0, sizeof(uint32_t) * num_tiles, stream));
+    const int blocks = (int)((N + 255) / 256);
+    if (N > 0) {
+        if (fused)
+            preprocess_kernel<true><<<blocks, 256, 0, stream>>>(cam, N, fe, means3D, scales, rotations, opacities, colors,
+                                                                 geom, radii, buf->tiles_touched, buf->tile_counts);
+        else
+            preprocess_kernel<false><<<blocks, 256, 0, stream>>>(cam, N, fe, means3D, scales, rotations, opacities, colors,
+                                                                  geom, radii, buf->tiles_touched, buf->tile_counts);
+        VTGS_LAUNCH_CHECK();
+    }
+    tile_scan_kernel<<<1, 1024, 0, stream>>>(buf->tile_counts, buf->tile_ranges, num_tiles, buf->pair_capacity, buf->counters);
+    VTGS_LAUNCH_CHECK();
+    const int band_tiles = (cam.row1 - cam.row0) * cam.gx;
+    if (N > 0 && band_tiles > 0) {
+        scatter_kernel<<<blocks, 256, 0, stream>>>(N, cam.gx, geom, buf->tiles_touched, buf->tile_ranges, buf->tile_counts, buf->pair_keys);
+        VTGS_LAUNCH_CHECK();
+        static bool attr_set = false;
+        if (!attr_set) {
+            VTGS_CUDA_CHECK(cudaFuncSetAttribute(tile_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_SMEM_ELEMS * 8));
+            attr_set = true;
+        }
+        tile_sort_kernel<<<band_tiles, 256, SORT_SMEM_ELEMS * 8, stream>>>(buf->tile_ranges, cam.row0 * cam.gx, buf->pair_keys, buf->point_list);
+        VTGS_LAUNCH_CHECK();
+    }
+    if (band_tiles > 0) {
+        if (fused)
+            blend_forward_kernel<true><<<band_tiles, 256, 0, stream>>>(cam, buf->tile_ranges, buf->point_list, geom, out_color, out_depth, buf->final_T, buf->n_contrib);
+        else
+            blend_forward_kernel<false><<<band_tiles, 256, 0, stream>>>(cam, buf->tile_ranges, buf->point_list, geom, out_color, out_depth, buf->final_T, buf->n_contrib);
+        VTGS_LAUNCH_CHECK();
+    }
+    if (band_tiles < num_tiles) {
+        const size_t P = (size_t)cam.W * cam.H;
+        fill_outside_band_kernel<<<(unsigned)((P + 255) / 256), 256, 0, stream>>>(cam, fused ? 6 : 3, out_color, out_depth, buf->final_T, buf->n_contrib);
+        VTGS_LAUNCH_CHECK();
+    }
+    return VTGS_OK;
+}
+
+// ---- parity / debug exports ---------------------------------------------------------------
+__global__ void export_keys_kernel(const uint32_t* __restrict__ ranges, int num_tiles, const uint64_t* __restrict__ pair_keys,
+                                   uint64_t* __restrict__ out, uint64_t cap) {
+    const int tile = blockIdx.x;
+    if (tile >= num_tiles) return;
+    const uint32_t b = ranges[2 * tile], e = ranges[2 * tile + 1];
+    for (uint32_t i = b + threadIdx.x; i < e; i += blockDim.x)
+        if (i < cap) out[i] = ((uint64_t)tile << 32) | (pair_keys[i] >> 32);
+}
+
+int launch_export_keys(const VtgsCamera* camera, const VtgsBuffers* buf, uint64_t* out, uint64_t cap, cudaStream_t stream) {
+    const CamConst cam = make_cam_const(*camera);
+    const int num_tiles = cam.gx * cam.gy;
+    export_keys_kernel<<<num_tiles, 128, 0, stream>>>(buf->tile_ranges, num_tiles, buf->pair_keys, out, cap);
+    VTGS_LAUNCH_CHECK();
+    return VTGS_OK;
+}
+
+__global__ void export_geom_kernel(int64_t N, const GeomRecord* __restrict__ geom, float* means2D, float* depths, float* conic_opacity) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const GeomRecord r = geom[i];
+    if (means2D) { means2D[2 * i] = r.q0.x; means2D[2 * i + 1] = r.q0.y; }
+    if (depths) depths[i] = r.q3.x;
+    if (conic_opacity) { conic_opacity[4 * i] = r.q1.x; conic_opacity[4 * i + 1] = r.q1.y; conic_opacity[4 * i + 2] = r.q1.z; conic_opacity[4 * i + 3] = r.q0.w; }
+}
+
+int launch_export_geometry(int64_t N, const VtgsBuffers* buf, float* means2D, float* depths, float* conic_opacity, cudaStream_t stream) {
+    if (N <= 0) return VTGS_OK;
+    export_geom_kernel<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(N, reinterpret_cast<const GeomRecord*>(buf->geom), means2D, depths, conic_opacity);
+    VTGS_LAUNCH_CHECK();
+    return VTGS_OK;
+}
+
+__global__ void mark_visible_kernel(const __grid_constant__ CamConst cam, int64_t N, const float* __restrict__ means3D, uint8_t* __restrict__ present) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    present[i] = xform_row(cam.view, 2, means3D[3 * i], means3D[3 * i + 1], means3D[3 * i + 2]) > VTGS_NEAR_CULL ? 1 : 0;
+}
+
+int launch_mark_visible(const VtgsCamera* camera, int64_t N, const float* means3D, uint8_t* present, cudaStream_t stream) {
+    if (N <= 0) return VTGS_OK;
+    const CamConst cam = make_cam_const(*camera);
+    mark_visible_kernel<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(cam, N, means3D, present);
+    VTGS_LAUNCH_CHECK();
+    return VTGS_OK;
+}
+
+}  // namespace vtgs

@@ -1,0 +1,45 @@
+// kernels.h -- internal launch interface between the translation units of libvtgs_cuda.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/vtgs.h"
+
+namespace vtgs {
+
+// Front end of the fused path (transform_to_frame + activations); unused in API mode.
+struct FrontEnd {
+    const float* pose_Rt;     // device: R[9] row-major then t[3] (VtgsCounters.pose_R/pose_t)
+    float depth_row[4];
+    int log_scales_dim;
+};
+
+int launch_forward(const VtgsCamera* cam, int64_t N, bool fused, const FrontEnd& fe,
+                   const float* means3D, const float* scales, const float* rotations,
+                   const float* opacities, const float* colors,
+                   float* out_color, float* out_depth, int32_t* radii, VtgsBuffers* buf,
+                   cudaStream_t stream);
+int launch_export_keys(const VtgsCamera* cam, const VtgsBuffers* buf, uint64_t* out, uint64_t cap, cudaStream_t stream);
+int launch_export_geometry(int64_t N, const VtgsBuffers* buf, float* means2D, float* depths, float* conic_opacity, cudaStream_t stream);
+int launch_mark_visible(const VtgsCamera* cam, int64_t N, const float* means3D, uint8_t* present, cudaStream_t stream);
+
+// API-mode backward (K6 + K7).
+int launch_backward(const VtgsCamera* cam, int64_t N,
+                    const float* means3D, const float* scales, const float* rotations,
+                    const float* opacities, const float* colors, const float* dL_dout_color,
+                    float* dL_dmeans2D, float* dL_dcolors, float* dL_dopacity,
+                    float* dL_dmeans3D, float* dL_dscales, float* dL_drotations,
+                    VtgsBuffers* buf, cudaStream_t stream);
+
+// Fused path.
+int launch_pose_matrix(const VtgsPose* pose, VtgsCounters* counters, cudaStream_t stream);
+int launch_fused_backward(const VtgsCamera* cam, const VtgsParams* params, const VtgsPose* pose,
+                          const float* dL_dimage4, int accumulate, VtgsParamGrads* grads,
+                          VtgsBuffers* buf, cudaStream_t stream);
+int launch_loss(const VtgsCamera* cam, const VtgsLossConfig* cfg, const float* image6,
+                const float* gt_rgb, const float* gt_depth, float* dL_dimage4, float* loss_terms,
+                float* scratch, cudaStream_t stream);
+int launch_adam(float* param, const float* grad, float* m, float* v, int64_t n, float lr, float b1,
+                float b2, float eps, int step, const int32_t* step_dev, cudaStream_t stream);
+
+}  // namespace vtgs
