@@ -1,0 +1,210 @@
+"""-m gpu parity tests of the fused view-tied path (vtgs_fused_forward / vtgs_loss /
+vtgs_fused_backward / vtgs_adam) against the oracle + the reference-shaped host chain."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from helpers import oracle_camera, rel_err
+from vtgaussian_slam_b200 import slam_ops, synthetic
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _scene(W=300, H=170, n_edge=6000, opacity="trained", seed=0):
+    fr = synthetic.make_frame("replica", W, H, seed=seed)
+    p = synthetic.view_tied_gaussians(fr, n_edge=n_edge, opacity=opacity)
+    q, t = synthetic.perturbed_pose(seed=1)
+    q = q * 1.7         # un-normalised on purpose
+    return fr, p, q, t
+
+
+def _settings(fr, dev=DEV):
+    from gpu_helpers import settings_from
+    s = synthetic.setup_camera(fr["W"], fr["H"], fr["K"], np.eye(4))
+    return settings_from(s, torch.device(dev)), s
+
+
+def _oracle_fused(fr, p, q, t, depth_row=(0, 0, 1, 0), tile_rows=(0, 0)):
+    cam_o, _ = oracle_camera(fr["W"], fr["H"], fr["K"], tile_rows=tile_rows)
+    m, s, r, o, c6 = oracle.frontend(p["means3D"], p["rgb_colors"], p["unnorm_rotations"], p["logit_opacities"],
+                                     p["log_scales"], q, t, depth_row=depth_row)
+    orc = oracle.Oracle()
+    ref = orc.forward(cam_o, m, s, r, o, c6)
+    return orc, ref, (m, s, r, o, c6)
+
+
+def _gpu_params(p):
+    return {k: torch.tensor(v, device=DEV) for k, v in p.items()}
+
+
+@pytest.mark.parametrize("depth_row", [(0, 0, 1, 0), (0.02, -0.03, 0.99, 0.1)])
+def test_fused_forward_bit_exact(depth_row):
+    from vtgaussian_slam_b200.fused import FusedRenderer
+    fr, p, q, t = _scene()
+    _, ref, _ = _oracle_fused(fr, p, q, t, depth_row)
+    settings, _ = _settings(fr)
+    r = FusedRenderer(settings, p["means3D"].shape[0], device=DEV, depth_row=depth_row)
+    img, radii = r.forward(_gpu_params(p), torch.tensor(q, device=DEV), torch.tensor(t, device=DEV))
+    torch.cuda.synchronize()
+    overflow, R = r.overflowed()
+    assert not overflow and R == ref["R"]
+    assert np.array_equal(radii.cpu().numpy(), ref["radii"])
+    assert np.array_equal(r.ws.n_contrib.cpu().numpy().astype(np.uint32), ref["n_contrib"])
+    assert np.array_equal(r.ws.tile_ranges.cpu().numpy().astype(np.uint32), ref["ranges"])
+    assert np.array_equal(r.ws.point_list[:R].cpu().numpy().astype(np.uint32), ref["point_list"])
+    got = img.cpu().numpy()
+    assert np.abs(got - ref["color"]).max() <= 1e-4
+    assert np.array_equal(got, ref["color"]), "six planes are expected to be bit-identical to the oracle"
+
+
+def test_fused_equals_two_dropin_passes():
+    """One fused six-plane pass == the reference's two three-channel passes (get_loss :461,:466)."""
+    from diff_gaussian_rasterization import GaussianRasterizer
+    from vtgaussian_slam_b200.fused import FusedRenderer
+    fr, p, q, t = _scene(200, 120, n_edge=2000)
+    settings, _ = _settings(fr)
+    gp = _gpu_params(p)
+    params = dict(gp, cam_unnorm_rots=torch.tensor(q, device=DEV).reshape(1, 4, 1), cam_trans=torch.tensor(t, device=DEV).reshape(1, 3, 1))
+    tg = slam_ops.transform_to_frame(params, 0, gaussians_grad=False, camera_grad=False)
+    rv = slam_ops.transformed_params2rendervar(params, tg)
+    dv = slam_ops.transformed_params2depthplussilhouette(params, torch.eye(4, device=DEV), tg)
+    im, radius, _ = GaussianRasterizer(raster_settings=settings)(**rv)
+    ds, _, _ = GaussianRasterizer(raster_settings=settings)(**dv)
+    r = FusedRenderer(settings, p["means3D"].shape[0], device=DEV)
+    img, radii = r.forward(gp, torch.tensor(q, device=DEV), torch.tensor(t, device=DEV))
+    # activations differ in the last ulp (torch.exp / sigmoid vs the spec'd vexpf), so not bit-exact here
+    assert (im - img[:3]).abs().max().item() <= 1e-4
+    assert ((ds - img[3:]).abs() / (1 + ds.abs())).max().item() <= 1e-4
+    assert (radius != radii).float().mean().item() < 1e-3
+
+
+def test_tracking_loss_and_backward_parity():
+    from vtgaussian_slam_b200.fused import FusedRenderer
+    fr, p, q, t = _scene()
+    orc, ref, (m, s, rr, o, c6) = _oracle_fused(fr, p, q, t)
+    settings, _ = _settings(fr)
+    N = p["means3D"].shape[0]
+    r = FusedRenderer(settings, N, device=DEV)
+    gp = _gpu_params(p)
+    qd, td = torch.tensor(q, device=DEV), torch.tensor(t, device=DEV)
+    r.forward(gp, qd, td)
+    gt_rgb, gt_d = torch.tensor(fr["im"], device=DEV), torch.tensor(fr["depth"], device=DEV)
+    terms = r.tracking_loss(gt_rgb, gt_d, w_im=0.5, w_depth=0.025, use_sil_for_loss=True, sil_thres=0.99).cpu().numpy()
+
+    # reference-shaped loss on the oracle's planes (host logic of get_loss)
+    img = torch.tensor(ref["color"], requires_grad=True)
+    data = dict(im=torch.tensor(fr["im"]), depth=torch.tensor(fr["depth"]))
+    loss, wl = slam_ops._masks_and_losses(img[:3], img[3:], data, dict(im=0.5, depth=0.025), True, 0.99, True, False, True,
+                                          None, "tum", None, None, None, None, None)
+    loss.backward()
+    assert abs(terms[0] - loss.item()) <= 1e-4 * abs(loss.item())
+    assert abs(terms[1] - wl["im"].item()) <= 1e-4 * abs(wl["im"].item())
+    assert abs(terms[2] - wl["depth"].item()) <= 1e-4 * abs(wl["depth"].item())
+    dL6 = img.grad.numpy()
+    assert np.abs(dL6[4:]).max() == 0.0                       # silhouette / depth^2 carry no gradient
+    assert np.array_equal(r.dL_dimage4.cpu().numpy(), dL6[:4])
+
+    # oracle backward (6 channels) + the reference's autograd chain through the front end (CPU, fp64)
+    g = orc.backward(dL6)
+    P = {k: torch.tensor(v, dtype=torch.float64, requires_grad=True) for k, v in p.items()}
+    P["cam_unnorm_rots"] = torch.tensor(q, dtype=torch.float64).reshape(1, 4, 1).requires_grad_(True)
+    P["cam_trans"] = torch.tensor(t, dtype=torch.float64).reshape(1, 3, 1).requires_grad_(True)
+    tg = slam_ops.transform_to_frame(P, 0, gaussians_grad=True, camera_grad=True)
+    rv = slam_ops.transformed_params2rendervar(P, tg)
+    dsc = slam_ops.get_depth_and_silhouette(tg["means3D"], torch.eye(4, dtype=torch.float64))
+    outs = [rv["means3D"], rv["scales"], rv["rotations"], rv["opacities"][:, 0], rv["colors_precomp"], dsc]
+    gouts = [g["means3D"], g["scales"], g["rotations"], g["opacities"], g["colors"][:, :3], g["colors"][:, 3:]]
+    torch.autograd.backward(outs, [torch.tensor(x, dtype=torch.float64) for x in gouts])
+
+    pg = {k: torch.zeros_like(gp[k]) for k in gp}
+    dq, dt = torch.zeros(4, device=DEV), torch.zeros(3, device=DEV)
+    m2d = torch.zeros(N, 3, device=DEV)
+    r.backward(gp, qd, td, param_grads=pg, pose_grads=(dq, dt), means2D_grad=m2d)
+    torch.cuda.synchronize()
+    assert rel_err(dq.cpu().numpy(), P["cam_unnorm_rots"].grad.numpy().reshape(4)) <= 1e-3
+    assert rel_err(dt.cpu().numpy(), P["cam_trans"].grad.numpy().reshape(3)) <= 1e-3
+    assert rel_err(m2d.cpu().numpy(), g["means2D"]) <= 1e-3
+    for k in ("means3D", "rgb_colors", "logit_opacities", "log_scales"):
+        assert rel_err(pg[k].cpu().numpy(), P[k].grad.numpy()) <= 1e-3, k
+    floor = float(np.abs(P["log_scales"].grad.numpy()).max())
+    assert rel_err(pg["unnorm_rotations"].cpu().numpy(), P["unnorm_rotations"].grad.numpy(), floor=floor) <= 1e-3
+    # a second backward must give the same result (grad_geom scratch left zeroed)
+    dq2, dt2 = torch.zeros(4, device=DEV), torch.zeros(3, device=DEV)
+    r.backward(gp, qd, td, pose_grads=(dq2, dt2))
+    assert rel_err(dq2.cpu().numpy(), dq.cpu().numpy()) <= 1e-5 and rel_err(dt2.cpu().numpy(), dt.cpu().numpy()) <= 1e-5
+
+
+def test_adam_matches_torch():
+    from vtgaussian_slam_b200.fused import adam_step
+    g = torch.Generator().manual_seed(0)
+    p0 = torch.randn(1000, generator=g)
+    for eps in (1e-8, 1e-15):
+        ref = torch.nn.Parameter(p0.clone())
+        opt = torch.optim.Adam([ref], lr=2e-3, eps=eps)
+        p = p0.clone().to(DEV)
+        m, v = torch.zeros_like(p), torch.zeros_like(p)
+        step = torch.zeros(1, dtype=torch.int32, device=DEV)
+        for it in range(5):
+            grad = torch.randn(1000, generator=g)
+            ref.grad = grad.clone()
+            opt.step()
+            step.add_(1)
+            adam_step(p, grad.to(DEV), m, v, 2e-3, step_dev=step, eps=eps)
+        assert (p.cpu() - ref.detach()).abs().max().item() <= 2e-6
+
+
+def test_tracking_solver_converges_and_graph_matches_eager():
+    from vtgaussian_slam_b200.fused import TrackingSolver
+    fr, p, _, _ = _scene(240, 136, n_edge=0, opacity="trained")
+    settings, _ = _settings(fr)
+    q0, t0 = synthetic.perturbed_pose(seed=3, trans_sigma=0.01, rot_deg=0.4)
+    res = {}
+    for use_graph in (False, True):
+        ts = TrackingSolver(settings, _gpu_params(p), device=DEV, use_graph=use_graph, sil_thres=0.99)
+        ts.set_frame(torch.tensor(fr["im"]), torch.tensor(fr["depth"]), q0, t0)
+        losses = []
+        for it in range(30):
+            ts.step()
+            losses.append(ts.loss_terms()[0].item())
+        res[use_graph] = (losses, ts.cam_q.cpu().numpy(), ts.cam_t.cpu().numpy(), ts.best_loss.item())
+    l_e, q_e, t_e, b_e = res[False]
+    l_g, q_g, t_g, b_g = res[True]
+    assert l_e[-1] < 0.7 * l_e[0], l_e                      # pose refinement reduces the loss
+    assert np.allclose(l_e, l_g, rtol=1e-3)
+    assert np.allclose(q_e, q_g, atol=1e-5) and np.allclose(t_e, t_g, atol=1e-5)
+    assert b_e <= min(l_e) * (1 + 1e-6)
+    assert np.linalg.norm(t_e) < np.linalg.norm(t0)          # moved towards the true pose (identity)
+
+
+def test_get_loss_fused_equals_dropin():
+    fr, p, q, t = _scene(200, 120, n_edge=1500)
+    settings, _ = _settings(fr)
+    data = dict(cam=settings, im=torch.tensor(fr["im"], device=DEV), depth=torch.tensor(fr["depth"], device=DEV),
+                w2c=torch.eye(4, device=DEV))
+    out = {}
+    for backend in ("dropin", "fused"):
+        params = {k: torch.nn.Parameter(torch.tensor(v, device=DEV)) for k, v in p.items()}
+        params["cam_unnorm_rots"] = torch.nn.Parameter(torch.tensor(q, device=DEV).reshape(1, 4, 1).repeat(1, 1, 2).contiguous())
+        params["cam_trans"] = torch.nn.Parameter(torch.tensor(t, device=DEV).reshape(1, 3, 1).repeat(1, 1, 2).contiguous())
+        variables = dict(max_2D_radius=torch.zeros(p["means3D"].shape[0], device=DEV))
+        loss, variables, wl = slam_ops.get_loss(params, data, variables, 1, dict(im=0.5, depth=0.025), True, 0.99, True, False,
+                                                tracking=True, dataset_name="tum", backend=backend)
+        loss.backward()
+        out[backend] = (loss.item(), params["cam_unnorm_rots"].grad.cpu().numpy(), params["cam_trans"].grad.cpu().numpy(),
+                        variables["seen"].float().mean().item())
+        assert params["means3D"].grad is None
+        assert np.all(out[backend][1][..., 0] == 0)          # only the rendered frame's pose slice gets gradient
+    a, b = out["dropin"], out["fused"]
+    assert abs(a[0] - b[0]) <= 2e-3 * abs(a[0])
+    assert rel_err(b[1], a[1]) <= 2e-2 and rel_err(b[2], a[2]) <= 2e-2     # sum-of-signs loss: mask flips at ulp level
+    assert abs(a[3] - b[3]) < 1e-3
+    # mapping: Gaussian parameters receive gradients, pose does not
+    params = {k: torch.nn.Parameter(torch.tensor(v, device=DEV)) for k, v in p.items()}
+    params["cam_unnorm_rots"] = torch.nn.Parameter(torch.tensor(q, device=DEV).reshape(1, 4, 1).contiguous())
+    params["cam_trans"] = torch.nn.Parameter(torch.tensor(t, device=DEV).reshape(1, 3, 1).contiguous())
+    variables = dict(max_2D_radius=torch.zeros(p["means3D"].shape[0], device=DEV))
+    loss, _, _ = slam_ops.get_loss(params, data, variables, 0, dict(im=1.0, depth=1.0), False, 0.5, True, False, mapping=True)
+    loss.backward()
+    assert params["rgb_colors"].grad.abs().sum().item() > 0 and params["cam_trans"].grad is None

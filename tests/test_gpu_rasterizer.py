@@ -53,8 +53,12 @@ def _run_case(W, H, sc, K, bg=(0, 0, 0), grads=True, seed=0, sigma_mult=3.0, til
             g_ref = o.backward(dL)
             g = rasterizer.rasterize_backward(cam, ws, torch.tensor(dL, device="cuda:0"))
             names = ["means3D", "means2D", "colors", "opacities", "scales", "rotations"]
+            # dL/dq of an isotropic splat is analytically zero (Sigma = s^2 I is rotation invariant): both
+            # sides then hold cancellation noise, so rotations are compared on the scale s * |dL/ds|
+            rot_floor = float(np.abs(g_ref["scales"]).max() * np.abs(sc["scales"]).max())
             for name, t in zip(names, g):
-                e = rel_err(t.cpu().numpy().reshape(g_ref[name].shape), g_ref[name])
+                e = rel_err(t.cpu().numpy().reshape(g_ref[name].shape), g_ref[name],
+                            floor=max(rot_floor, 1e-6) if name == "rotations" else 1e-6)
                 assert e <= GRAD_RTOL, (name, e)
         return ref, got, bit_exact
     finally:

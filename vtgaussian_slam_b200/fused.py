@@ -1,0 +1,283 @@
+"""Fused view-tied render -> loss -> backward -> Adam iteration (the hot loops of
+reference src/vtgaussian_slam.py:1794-1891 (tracking) and :2525-2702 (mapping)).
+
+One six-plane pass replaces the two rasteriser passes of get_loss (:461,:466), the front end
+(transform_to_frame, the two render-variable builders) runs inside the preprocess kernel,
+the masked-L1 loss and its gradient are one kernel, the backward reduces straight to the
+7 pose numbers (tracking) and/or the Gaussian parameter gradients (mapping), and Adam is one
+kernel per tensor.  Nothing here synchronises with the host, so `TrackingSolver` /
+`MappingSolver` capture a whole iteration in a CUDA graph.
+
+All compute is in libvtgs_cuda.so (include/vtgs.h); no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .rasterizer import Workspace, _ptr, _require_cuda, _stream_ptr, camera_struct
+
+PARAM_KEYS = ("means3D", "rgb_colors", "unnorm_rotations", "logit_opacities", "log_scales")
+
+
+class FusedRenderer:
+    """Persistent buffers for rendering N view-tied Gaussians into a W x H frame.
+
+    pair_capacity bounds R = sum(tiles_touched); the library never reads R back.  Poll
+    `overflowed()` (one tiny D2H) when convenient -- e.g. once per frame -- and call
+    `reserve_pairs` to grow."""
+
+    def __init__(self, settings, num_gaussians, device="cuda:0", pair_capacity=None, tile_rows=(0, 0),
+                 depth_row=(0.0, 0.0, 1.0, 0.0)):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("FusedRenderer needs a CUDA device: vtgaussian_slam_b200 has no CPU fallback")
+        self.cam = camera_struct(settings, tile_rows=tile_rows)
+        self.W, self.H, self.N = self.cam.image_width, self.cam.image_height, int(num_gaussians)
+        if pair_capacity is None:
+            pair_capacity = int(self.N * 6) + 65536
+        self.ws = Workspace(self.device, self.W, self.H, self.N, pair_capacity)
+        self.ws.ensure_grad_geom()
+        self.depth_row = tuple(float(v) for v in depth_row)
+        L = _lib.lib()
+        f32 = dict(dtype=torch.float32, device=self.device)
+        self.image6 = torch.zeros((6, self.H, self.W), **f32)
+        self.radii = torch.zeros(max(self.N, 1), dtype=torch.int32, device=self.device)
+        self.dL_dimage4 = torch.zeros((4, self.H, self.W), **f32)
+        self.loss_terms = torch.zeros(8, **f32)
+        self._loss_scratch = torch.zeros(int(L.vtgs_loss_scratch_floats(self.W, self.H, 0)), **f32)
+        self._pose_scratch = torch.zeros(int(L.vtgs_pose_scratch_floats(self.N)), **f32)
+        self._bufs = self.ws.struct()
+
+    # -- helpers ---------------------------------------------------------------------------
+    def reserve_pairs(self, cap):
+        self.ws.reserve_pairs(cap)
+        self._bufs = self.ws.struct()
+
+    def overflowed(self):
+        R, overflow, _ = self.ws.read_counters()
+        return bool(overflow), R
+
+    def _params_struct(self, params):
+        p = _lib.VtgsParams()
+        for k in PARAM_KEYS:
+            t = params[k]
+            _require_cuda(k, t)
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                raise ValueError(f"params['{k}'] must be contiguous float32")
+            setattr(p, k, t.data_ptr())
+        ls = params["log_scales"]
+        p.log_scales_dim = 1 if ls.dim() == 1 else int(ls.shape[1])
+        p.num_gaussians = self.N
+        if params["means3D"].shape[0] != self.N:
+            raise ValueError("number of Gaussians differs from the renderer's")
+        return p
+
+    def _pose_struct(self, cam_q, cam_t):
+        for n, t, k in (("cam_q", cam_q, 4), ("cam_t", cam_t, 3)):
+            _require_cuda(n, t)
+            if t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != k:
+                raise ValueError(f"{n} must be a contiguous float32 tensor of {k} elements")
+        ps = _lib.VtgsPose()
+        ps.cam_unnorm_rot = cam_q.data_ptr()
+        ps.cam_trans = cam_t.data_ptr()
+        ps.depth_row[:] = self.depth_row
+        return ps
+
+    # -- the three stages ------------------------------------------------------------------
+    def forward(self, params, cam_q, cam_t):
+        """-> image6[6,H,W] = (r, g, b, depth, silhouette, depth^2), radii[N].  Buffers are reused."""
+        p, ps = self._params_struct(params), self._pose_struct(cam_q, cam_t)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().vtgs_fused_forward(C.byref(self.cam), C.byref(p), C.byref(ps), _ptr(self.image6),
+                                                     _ptr(self.radii), C.byref(self._bufs), _stream_ptr(self.device)))
+        return self.image6, self.radii[:self.N]
+
+    def tracking_loss(self, gt_rgb, gt_depth, w_im=0.5, w_depth=0.025, use_sil_for_loss=True, sil_thres=0.99,
+                      far_depth_thres=0.0, image6=None):
+        """Masked-L1 tracking loss (reference get_loss :513-605,:678-679) of the last forward.
+        -> loss_terms[8] (device): loss, w_im*im, w_depth*depth, mask count, ...; fills dL_dimage4."""
+        cfg = _lib.VtgsLossConfig(0, int(bool(use_sil_for_loss)), 0, 1, float(sil_thres), float(w_im), float(w_depth),
+                                  float(far_depth_thres))
+        img = self.image6 if image6 is None else image6
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().vtgs_loss(C.byref(self.cam), C.byref(cfg), _ptr(img), _ptr(gt_rgb), _ptr(gt_depth),
+                                            _ptr(self.dL_dimage4), _ptr(self.loss_terms), _ptr(self._loss_scratch),
+                                            _stream_ptr(self.device)))
+        return self.loss_terms
+
+    def backward(self, params, cam_q, cam_t, dL_dimage4=None, param_grads=None, pose_grads=None, means2D_grad=None,
+                 accumulate=False):
+        """param_grads: dict key -> tensor to receive dL/dparams[key] (any subset of PARAM_KEYS).
+        pose_grads: (d_cam_q[4], d_cam_t[3]) tensors or None."""
+        p, ps = self._params_struct(params), self._pose_struct(cam_q, cam_t)
+        g = _lib.VtgsParamGrads()
+        for k in PARAM_KEYS:
+            t = None if param_grads is None else param_grads.get(k)
+            if t is not None:
+                if t.shape != params[k].shape or t.dtype != torch.float32 or not t.is_contiguous():
+                    raise ValueError(f"gradient buffer for '{k}' must match the parameter")
+                setattr(g, k, t.data_ptr())
+        if means2D_grad is not None:
+            g.means2D = means2D_grad.data_ptr()
+        if pose_grads is not None:
+            g.cam_unnorm_rot, g.cam_trans = pose_grads[0].data_ptr(), pose_grads[1].data_ptr()
+            g.pose_scratch = self._pose_scratch.data_ptr()
+        dL = self.dL_dimage4 if dL_dimage4 is None else dL_dimage4
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().vtgs_fused_backward(C.byref(self.cam), C.byref(p), C.byref(ps), _ptr(dL), int(bool(accumulate)),
+                                                      C.byref(g), C.byref(self._bufs), _stream_ptr(self.device)))
+
+
+def adam_step(param, grad, exp_avg, exp_avg_sq, lr, step=None, step_dev=None, beta1=0.9, beta2=0.999, eps=1e-8):
+    """torch.optim.Adam's update of one tensor (reference initialize_optimizer,
+    src/vtgaussian_slam.py:180-187: eps 1e-8 tracking, 1e-15 mapping)."""
+    _require_cuda("param", param)
+    with torch.cuda.device(param.device):
+        _lib.check(_lib.lib().vtgs_adam(_ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), param.numel(), float(lr),
+                                        float(beta1), float(beta2), float(eps), int(step or 0), _ptr(step_dev),
+                                        _stream_ptr(param.device)))
+
+
+class TrackingSolver:
+    """The reference's per-frame tracking loop (src/vtgaussian_slam.py:1794-1970) for one frame:
+    num_iters x (get_loss(tracking=True) -> backward -> Adam on the 7 pose numbers), keeping
+    the best pose by loss.  Gaussians are frozen (their tracking LRs are 0, configs/replica/room0.py:78-86).
+
+    One iteration = 9 kernel launches, no host synchronisation; with use_graph the iteration is
+    captured once and replayed."""
+
+    LAUNCHES_PER_ITER = 14
+
+    def __init__(self, settings, params, device="cuda:0", lr_rot=4e-4, lr_trans=2e-3, w_im=0.5, w_depth=0.025,
+                 use_sil_for_loss=True, sil_thres=0.99, tile_rows=(0, 0), pair_capacity=None, use_graph=True,
+                 process_group=None):
+        self.device = torch.device(device)
+        self.params = {k: params[k].detach().to(self.device).float().contiguous() for k in PARAM_KEYS}
+        N = self.params["means3D"].shape[0]
+        self.r = FusedRenderer(settings, N, device=self.device, tile_rows=tile_rows, pair_capacity=pair_capacity)
+        self.cfg = dict(w_im=w_im, w_depth=w_depth, use_sil_for_loss=use_sil_for_loss, sil_thres=sil_thres)
+        self.lr_rot, self.lr_trans = lr_rot, lr_trans
+        f32 = dict(dtype=torch.float32, device=self.device)
+        self.cam_q = torch.tensor([1.0, 0, 0, 0], **f32)
+        self.cam_t = torch.zeros(3, **f32)
+        # gradient message of one iteration: d_q[4] d_t[3] pad loss_terms[8] -> 16 floats (all-reduced when sharded)
+        self.msg = torch.zeros(16, **f32)
+        self.d_q, self.d_t = self.msg[0:4], self.msg[4:7]
+        self.r.loss_terms = self.msg[8:16]          # the loss kernel writes straight into the message
+        self.m_q, self.v_q = torch.zeros(4, **f32), torch.zeros(4, **f32)
+        self.m_t, self.v_t = torch.zeros(3, **f32), torch.zeros(3, **f32)
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.best_loss = torch.full((1,), float("inf"), **f32)
+        self.best_q, self.best_t = self.cam_q.clone(), self.cam_t.clone()
+        self.gt_rgb = torch.zeros((3, self.r.H, self.r.W), **f32)
+        self.gt_depth = torch.zeros((1, self.r.H, self.r.W), **f32)
+        self.pg = process_group
+        self.use_graph = use_graph
+        self._graph = None
+
+    def set_frame(self, gt_rgb, gt_depth, cam_q, cam_t):
+        """New frame: targets, initial pose (e.g. constant-velocity propagated) and a fresh Adam
+        state -- the reference re-creates its optimiser every frame (:1678-1758)."""
+        self.gt_rgb.copy_(gt_rgb, non_blocking=True)
+        self.gt_depth.copy_(gt_depth.reshape(self.gt_depth.shape), non_blocking=True)
+        self.cam_q.copy_(torch.as_tensor(cam_q).reshape(4), non_blocking=True)
+        self.cam_t.copy_(torch.as_tensor(cam_t).reshape(3), non_blocking=True)
+        for t in (self.m_q, self.v_q, self.m_t, self.v_t):
+            t.zero_()
+        self.step_dev.zero_()
+        self.best_loss.fill_(float("inf"))
+
+    def _iteration(self):
+        r = self.r
+        r.forward(self.params, self.cam_q, self.cam_t)
+        r.tracking_loss(self.gt_rgb, self.gt_depth, **self.cfg)
+        r.backward(self.params, self.cam_q, self.cam_t, pose_grads=(self.d_q, self.d_t))
+        if self.pg is not None:
+            # tile-band sharding: every rank holds its band's partial sums; one 16-float all-reduce
+            torch.distributed.all_reduce(self.msg, group=self.pg)
+        loss = self.msg[8:9]
+        # keep the best candidate pose (reference :1961-1970), evaluated BEFORE the step like the reference
+        better = loss < self.best_loss
+        self.best_q.copy_(torch.where(better, self.cam_q, self.best_q))
+        self.best_t.copy_(torch.where(better, self.cam_t, self.best_t))
+        self.best_loss.copy_(torch.where(better, loss, self.best_loss))
+        self.step_dev.add_(1)
+        adam_step(self.cam_q, self.d_q, self.m_q, self.v_q, self.lr_rot, step_dev=self.step_dev)
+        adam_step(self.cam_t, self.d_t, self.m_t, self.v_t, self.lr_trans, step_dev=self.step_dev)
+
+    def step(self):
+        if not self.use_graph:
+            self._iteration()
+            return
+        if self._graph is None:
+            # warm-up on a side stream, then capture
+            s = torch.cuda.Stream(self.device)
+            s.wait_stream(torch.cuda.current_stream(self.device))
+            snap = [t.clone() for t in (self.cam_q, self.cam_t, self.m_q, self.v_q, self.m_t, self.v_t, self.step_dev,
+                                        self.best_loss, self.best_q, self.best_t)]
+            with torch.cuda.stream(s):
+                self._iteration()
+            torch.cuda.current_stream(self.device).wait_stream(s)
+            for t, v in zip((self.cam_q, self.cam_t, self.m_q, self.v_q, self.m_t, self.v_t, self.step_dev,
+                             self.best_loss, self.best_q, self.best_t), snap):
+                t.copy_(v)
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):
+                self._iteration()
+            for t, v in zip((self.cam_q, self.cam_t, self.m_q, self.v_q, self.m_t, self.v_t, self.step_dev,
+                             self.best_loss, self.best_q, self.best_t), snap):
+                t.copy_(v)
+        self._graph.replay()
+
+    def loss_terms(self):
+        return self.msg[8:16]
+
+
+class MappingSolver:
+    """The reference's mapping iteration (src/vtgaussian_slam.py:2525-2702) over a set of
+    keyframes with the semantics of its all-keyframes branch (:2609-2666): sum of the
+    per-keyframe losses, one backward, one Adam step over rgb / logit-opacity / log-scale
+    (mapping LRs, configs/replica/room0.py:99-107; means3D and rotations have LR 0).
+
+    `loss_fn(image6, kf) -> (loss, dL_dimage4)` supplies the mapping loss
+    (0.8 L1 + 0.2 (1-SSIM) + depth L1 mean, see slam_ops.mapping_loss_and_grad)."""
+
+    def __init__(self, settings, params, device="cuda:0", lrs=None, eps=1e-15, pair_capacity=None, process_group=None):
+        self.device = torch.device(device)
+        self.params = {k: params[k].detach().to(self.device).float().contiguous() for k in PARAM_KEYS}
+        N = self.params["means3D"].shape[0]
+        self.r = FusedRenderer(settings, N, device=self.device, pair_capacity=pair_capacity)
+        self.lrs = dict(rgb_colors=0.0025, logit_opacities=0.05, log_scales=0.005) if lrs is None else dict(lrs)
+        self.eps = eps
+        self.grads = {k: torch.zeros_like(self.params[k]) for k in self.lrs}
+        self.m = {k: torch.zeros_like(self.params[k]) for k in self.lrs}
+        self.v = {k: torch.zeros_like(self.params[k]) for k in self.lrs}
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.pg = process_group
+        self.total_loss = torch.zeros(1, dtype=torch.float32, device=self.device)
+
+    def iteration(self, keyframes, loss_fn):
+        """keyframes: list of dict(cam_q, cam_t, gt_rgb, gt_depth) owned by THIS rank."""
+        self.total_loss.zero_()
+        first = True
+        for kf in keyframes:
+            img, _ = self.r.forward(self.params, kf["cam_q"], kf["cam_t"])
+            loss, dL4 = loss_fn(img, kf)
+            self.total_loss += loss
+            self.r.backward(self.params, kf["cam_q"], kf["cam_t"], dL_dimage4=dL4, param_grads=self.grads, accumulate=not first)
+            first = False
+        if first:
+            for g in self.grads.values():
+                g.zero_()
+        if self.pg is not None:
+            # keyframe sharding: all-reduce (SUM) the Gaussian-parameter gradients over NVLink
+            for k in self.grads:
+                torch.distributed.all_reduce(self.grads[k], group=self.pg)
+            torch.distributed.all_reduce(self.total_loss, group=self.pg)
+        self.step_dev.add_(1)
+        for k, lr in self.lrs.items():
+            adam_step(self.params[k], self.grads[k], self.m[k], self.v[k], lr, step_dev=self.step_dev, eps=self.eps)
+        return self.total_loss

@@ -1,0 +1,381 @@
+"""Host-side mirror of the reference's operator interface around the rasteriser -- same
+names, argument meaning and error behaviour as the reference functions, device-agnostic
+(the reference hard-codes .cuda(); these follow the input tensors' device so the host logic
+is testable on CPU), with the rasteriser / fused kernels reached through the C ABI.
+
+    build_rotation                         reference utils/slam_external.py:25-42
+    calc_ssim                              utils/slam_external.py:54-97
+    l1_loss_v1, l1_loss_v1_mask            utils/slam_helpers.py:5-9
+    setup_camera                           utils/recon_helpers.py:4-27
+    transform_to_frame                     utils/slam_helpers.py:323-385
+    transformed_params2rendervar           utils/slam_helpers.py:127-160
+    get_depth_and_silhouette               utils/slam_helpers.py:217-234
+    transformed_params2depthplussilhouette utils/slam_helpers.py:255-287
+    initialize_optimizer                   src/vtgaussian_slam.py:180-187
+    get_loss                               src/vtgaussian_slam.py:407-689
+"""
+from __future__ import annotations
+
+from math import exp
+
+import torch
+import torch.nn.functional as F
+
+from .rasterizer import GaussianRasterizationSettings as Camera
+from .rasterizer import GaussianRasterizer as Renderer
+
+
+# ---------------------------------------------------------------------------- small ops
+def build_rotation(q):
+    norm = torch.sqrt(q[:, 0] * q[:, 0] + q[:, 1] * q[:, 1] + q[:, 2] * q[:, 2] + q[:, 3] * q[:, 3])
+    q = q / norm[:, None]
+    rot = torch.zeros((q.size(0), 3, 3), device=q.device, dtype=q.dtype)
+    r, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+    rot[:, 0, 0] = 1 - 2 * (y * y + z * z)
+    rot[:, 0, 1] = 2 * (x * y - r * z)
+    rot[:, 0, 2] = 2 * (x * z + r * y)
+    rot[:, 1, 0] = 2 * (x * y + r * z)
+    rot[:, 1, 1] = 1 - 2 * (x * x + z * z)
+    rot[:, 1, 2] = 2 * (y * z - r * x)
+    rot[:, 2, 0] = 2 * (x * z - r * y)
+    rot[:, 2, 1] = 2 * (y * z + r * x)
+    rot[:, 2, 2] = 1 - 2 * (x * x + y * y)
+    return rot
+
+
+def l1_loss_v1(x, y):
+    return torch.abs((x - y)).mean()
+
+
+def l1_loss_v1_mask(x, y, mask):
+    return (torch.abs((x - y)) * mask).mean()
+
+
+def quat_mult(q1, q2):
+    w1, x1, y1, z1 = q1.T
+    w2, x2, y2, z2 = q2.T
+    w = w1 * w2 - x1 * x2 - y1 * y2 - z1 * z2
+    x = w1 * x2 + x1 * w2 + y1 * z2 - z1 * y2
+    y = w1 * y2 - x1 * z2 + y1 * w2 + z1 * x2
+    z = w1 * z2 + x1 * y2 - y1 * x2 + z1 * w2
+    return torch.stack([w, x, y, z]).T
+
+
+def _gaussian_window(window_size, sigma):
+    g = torch.tensor([exp(-(x - window_size // 2) ** 2 / float(2 * sigma ** 2)) for x in range(window_size)])
+    return g / g.sum()
+
+
+def calc_ssim(img1, img2, window_size=11, size_average=True):
+    channel = img1.size(-3)
+    w1 = _gaussian_window(window_size, 1.5).unsqueeze(1)
+    window = w1.mm(w1.t()).float().unsqueeze(0).unsqueeze(0).expand(channel, 1, window_size, window_size).contiguous()
+    window = window.to(img1.device).type_as(img1)
+    pad = window_size // 2
+    mu1 = F.conv2d(img1, window, padding=pad, groups=channel)
+    mu2 = F.conv2d(img2, window, padding=pad, groups=channel)
+    mu1_sq, mu2_sq, mu1_mu2 = mu1.pow(2), mu2.pow(2), mu1 * mu2
+    sigma1_sq = F.conv2d(img1 * img1, window, padding=pad, groups=channel) - mu1_sq
+    sigma2_sq = F.conv2d(img2 * img2, window, padding=pad, groups=channel) - mu2_sq
+    sigma12 = F.conv2d(img1 * img2, window, padding=pad, groups=channel) - mu1_mu2
+    c1, c2 = 0.01 ** 2, 0.03 ** 2
+    ssim_map = ((2 * mu1_mu2 + c1) * (2 * sigma12 + c2)) / ((mu1_sq + mu2_sq + c1) * (sigma1_sq + sigma2_sq + c2))
+    if size_average:
+        return ssim_map.mean()
+    return ssim_map.mean(1).mean(1).mean(1)
+
+
+# ---------------------------------------------------------------------------- camera
+def setup_camera(w, h, k, w2c, near=0.01, far=100, device="cuda"):
+    fx, fy, cx, cy = k[0][0], k[1][1], k[0][2], k[1][2]
+    w2c = torch.tensor(w2c).to(device).float()
+    cam_center = torch.inverse(w2c)[:3, 3]
+    w2c = w2c.unsqueeze(0).transpose(1, 2)
+    opengl_proj = torch.tensor([[2 * fx / w, 0.0, -(w - 2 * cx) / w, 0.0],
+                                [0.0, 2 * fy / h, -(h - 2 * cy) / h, 0.0],
+                                [0.0, 0.0, far / (far - near), -(far * near) / (far - near)],
+                                [0.0, 0.0, 1.0, 0.0]]).to(device).float().unsqueeze(0).transpose(1, 2)
+    full_proj = w2c.bmm(opengl_proj)
+    return Camera(image_height=h, image_width=w, tanfovx=w / (2 * fx), tanfovy=h / (2 * fy),
+                  bg=torch.tensor([0, 0, 0], dtype=torch.float32, device=device), scale_modifier=1.0,
+                  viewmatrix=w2c, projmatrix=full_proj, sh_degree=0, campos=cam_center, prefiltered=False)
+
+
+# ---------------------------------------------------------------------------- render variables
+def transform_to_frame(params, time_idx, gaussians_grad, camera_grad, opt_cam_rot=None, opt_cam_trans=None, latest_w2c=None):
+    if camera_grad:
+        if opt_cam_rot is None and opt_cam_trans is None:
+            cam_rot = F.normalize(params['cam_unnorm_rots'][..., time_idx])
+            cam_tran = params['cam_trans'][..., time_idx]
+        else:
+            cam_rot = F.normalize(opt_cam_rot[None])
+            cam_tran = opt_cam_trans
+    else:
+        cam_rot = F.normalize(params['cam_unnorm_rots'][..., time_idx].detach())
+        cam_tran = params['cam_trans'][..., time_idx].detach()
+    dev = params['means3D'].device
+    rel_w2c = torch.eye(4, device=dev).float()
+    rel_w2c[:3, :3] = build_rotation(cam_rot)
+    rel_w2c[:3, 3] = cam_tran
+    if latest_w2c is not None:
+        rel_w2c = latest_w2c @ rel_w2c
+    transform_rots = params['log_scales'].shape[1] != 1     # anisotropic Gaussians are rotated too
+    if gaussians_grad:
+        pts, unnorm_rots = params['means3D'], params['unnorm_rotations']
+    else:
+        pts, unnorm_rots = params['means3D'].detach(), params['unnorm_rotations'].detach()
+    transformed_gaussians = {}
+    pts_ones = torch.ones(pts.shape[0], 1, device=dev).float()
+    pts4 = torch.cat((pts, pts_ones), dim=1)
+    transformed_gaussians['means3D'] = (rel_w2c @ pts4.T).T[:, :3]
+    if transform_rots:
+        transformed_gaussians['unnorm_rotations'] = quat_mult(cam_rot, F.normalize(unnorm_rots))
+    else:
+        transformed_gaussians['unnorm_rotations'] = unnorm_rots
+    return transformed_gaussians
+
+
+def _log_scales3(params):
+    if params['log_scales'].shape[1] == 1:
+        return torch.tile(params['log_scales'], (1, 3))
+    return params['log_scales']
+
+
+def transformed_params2rendervar(params, transformed_gaussians):
+    return {
+        'means3D': transformed_gaussians['means3D'],
+        'colors_precomp': params['rgb_colors'],
+        'rotations': F.normalize(transformed_gaussians['unnorm_rotations']),
+        'opacities': torch.sigmoid(params['logit_opacities']),
+        'scales': torch.exp(_log_scales3(params)),
+        'means2D': torch.zeros_like(params['means3D'], requires_grad=True) + 0,
+    }
+
+
+def get_depth_and_silhouette(pts_3D, w2c):
+    pts4 = torch.cat((pts_3D, torch.ones_like(pts_3D[:, :1])), dim=-1)
+    pts_in_cam = (w2c @ pts4.transpose(0, 1)).transpose(0, 1)
+    depth_z = pts_in_cam[:, 2].unsqueeze(-1)
+    depth_z_sq = torch.square(depth_z)
+    depth_silhouette = torch.zeros((pts_3D.shape[0], 3), device=pts_3D.device).float()
+    depth_silhouette[:, 0] = depth_z.squeeze(-1)
+    depth_silhouette[:, 1] = 1.0
+    depth_silhouette[:, 2] = depth_z_sq.squeeze(-1)
+    return depth_silhouette
+
+
+def transformed_params2depthplussilhouette(params, w2c, transformed_gaussians):
+    return {
+        'means3D': transformed_gaussians['means3D'],
+        'colors_precomp': get_depth_and_silhouette(transformed_gaussians['means3D'], w2c),
+        'rotations': F.normalize(transformed_gaussians['unnorm_rotations']),
+        'opacities': torch.sigmoid(params['logit_opacities']),
+        'scales': torch.exp(_log_scales3(params)),
+        'means2D': torch.zeros_like(params['means3D'], requires_grad=True) + 0,
+    }
+
+
+def initialize_optimizer(params, lrs_dict, tracking):
+    param_groups = [{'params': [v], 'name': k, 'lr': lrs_dict[k]} for k, v in params.items()]
+    if tracking:
+        return torch.optim.Adam(param_groups)
+    return torch.optim.Adam(param_groups, lr=0.0, eps=1e-15)
+
+
+# ---------------------------------------------------------------------------- the loss
+REPLICA_SIL_LADDER = [0.990, 0.993, 0.995, 0.997, 0.999]
+
+
+def _masks_and_losses(im, depth_sil, curr_data, loss_weights, use_sil_for_loss, sil_thres, use_l1,
+                      ignore_outlier_depth_loss, tracking, additional_mask, dataset_name, tracking_iteration,
+                      presence_sil_mask_mse_ls, sil_thres_ls, far_depth_filter_thres, vis_mask):
+    """The part of get_loss after the two renders (reference :467-612,:678-679), pure torch."""
+    losses = {}
+    depth = depth_sil[0, :, :].unsqueeze(0)
+    silhouette = depth_sil[1, :, :]
+    presence_sil_mask = None
+    if dataset_name == 'replica':
+        if tracking and use_sil_for_loss:
+            if tracking_iteration == 0 and presence_sil_mask_mse_ls is not None:
+                mse_ls = []
+                for thr in REPLICA_SIL_LADDER:          # :476-508 pick the threshold with the smallest masked MSE
+                    m = (silhouette > thr) & (curr_data['depth'] > 0)
+                    cm = torch.tile(m, (3, 1, 1)).detach()
+                    mse_ls.append(torch.mean((curr_data['im'] - im)[cm] ** 2).item())
+                min_mse = min(mse_ls)
+                presence_sil_mask_mse_ls.append(min_mse)
+                sil_thres_ls.append(REPLICA_SIL_LADDER[mse_ls.index(min_mse)])
+                presence_sil_mask = (silhouette > sil_thres_ls[-1])
+            elif sil_thres_ls:
+                presence_sil_mask = (silhouette > sil_thres_ls[-1])
+            else:
+                presence_sil_mask = (silhouette > sil_thres)
+    else:
+        presence_sil_mask = (silhouette > sil_thres)
+
+    depth_sq = depth_sil[2, :, :].unsqueeze(0)
+    uncertainty = (depth_sq - depth ** 2).detach()
+    nan_mask = (~torch.isnan(depth)) & (~torch.isnan(uncertainty))
+    if ignore_outlier_depth_loss:
+        depth_error = torch.abs(curr_data['depth'] - depth) * (curr_data['depth'] > 0)
+        mask = (depth_error < 50 * depth_error.median())
+        mask = mask & (curr_data['depth'] > 0)
+    else:
+        mask = (curr_data['depth'] > 0)
+    mask = mask & nan_mask
+    if tracking and use_sil_for_loss:
+        mask = mask & presence_sil_mask
+    if tracking and vis_mask is not None and dataset_name != 'replica':
+        mask = mask & vis_mask
+    if tracking and far_depth_filter_thres is not None and dataset_name not in ('replica', 'scannetpp'):
+        mask = mask & (curr_data['depth'] < far_depth_filter_thres)
+
+    if use_l1:
+        mask = mask.detach()
+        if tracking:
+            losses['depth'] = torch.abs(curr_data['depth'] - depth)[mask].sum()
+        else:
+            losses['depth'] = torch.abs(curr_data['depth'] - depth)[mask].mean()
+    if tracking and (use_sil_for_loss or ignore_outlier_depth_loss):
+        color_mask = torch.tile(mask, (3, 1, 1)).detach()
+        losses['im'] = torch.abs(curr_data['im'] - im)[color_mask].sum()
+    elif tracking:
+        losses['im'] = torch.abs(curr_data['im'] - im).sum()
+    else:
+        if additional_mask is None:
+            losses['im'] = 0.8 * l1_loss_v1(im, curr_data['im']) + 0.2 * (1.0 - calc_ssim(im, curr_data['im']))
+        else:
+            am = 10 * additional_mask.to(im.device).float() + 0.8 * torch.ones_like(additional_mask).to(im.device).float()
+            losses['im'] = l1_loss_v1_mask(im, curr_data['im'], am) + 0.2 * (1.0 - calc_ssim(im, curr_data['im']))
+    weighted_losses = {k: v * loss_weights[k] for k, v in losses.items()}
+    loss = sum(weighted_losses.values())
+    weighted_losses['loss'] = loss
+    return loss, weighted_losses
+
+
+class _FusedRender(torch.autograd.Function):
+    """im, depth_sil, radii = both rasteriser passes of get_loss as one fused six-plane pass,
+    differentiable w.r.t. the Gaussian parameters and the frame's pose slices."""
+
+    @staticmethod
+    def forward(ctx, renderer, means3D, rgb, unnorm_rot, logit_op, log_scales, cam_q, cam_t, want_gauss, want_pose):
+        params = dict(means3D=means3D.detach().contiguous(), rgb_colors=rgb.detach().contiguous(),
+                      unnorm_rotations=unnorm_rot.detach().contiguous(), logit_opacities=logit_op.detach().contiguous(),
+                      log_scales=log_scales.detach().contiguous())
+        q, t = cam_q.detach().contiguous().reshape(4), cam_t.detach().contiguous().reshape(3)
+        img, radii = renderer.forward(params, q, t)
+        ctx.renderer, ctx.params, ctx.q, ctx.t = renderer, params, q, t
+        ctx.want = (want_gauss, want_pose)
+        ctx.pose_shapes = (cam_q.shape, cam_t.shape)
+        out = img.clone()
+        means2D_grad = torch.zeros_like(params["means3D"])
+        ctx.means2D_grad = means2D_grad
+        radii = radii.clone()
+        ctx.mark_non_differentiable(radii)
+        return out[:3], out[3:6], radii, means2D_grad
+
+    @staticmethod
+    def backward(ctx, g_im, g_ds, _g_radii, _g_m2d):
+        r, params = ctx.renderer, ctx.params
+        H, W = r.H, r.W
+        dL4 = torch.zeros((4, H, W), dtype=torch.float32, device=g_im.device)
+        if g_im is not None:
+            dL4[:3] = g_im
+        if g_ds is not None:
+            if float(g_ds[1:].abs().max()) != 0.0:
+                raise NotImplementedError("the fused backward carries gradients for r,g,b and depth only "
+                                          "(the reference never differentiates silhouette / depth^2, SURVEY A.7)")
+            dL4[3] = g_ds[0]
+        want_gauss, want_pose = ctx.want
+        pg = {k: torch.zeros_like(params[k]) for k in params} if want_gauss else None
+        pose = (torch.zeros(4, device=g_im.device), torch.zeros(3, device=g_im.device)) if want_pose else None
+        r.backward(params, ctx.q, ctx.t, dL_dimage4=dL4, param_grads=pg, pose_grads=pose, means2D_grad=ctx.means2D_grad)
+        gq = pose[0].reshape(ctx.pose_shapes[0]) if want_pose else None
+        gt = pose[1].reshape(ctx.pose_shapes[1]) if want_pose else None
+        if want_gauss:
+            return (None, pg["means3D"], pg["rgb_colors"], pg["unnorm_rotations"], pg["logit_opacities"], pg["log_scales"],
+                    gq, gt, None, None)
+        return (None, None, None, None, None, None, gq, gt, None, None)
+
+
+_RENDERERS: dict = {}
+
+
+def _renderer_for(cam, n, device):
+    from .fused import FusedRenderer
+    key = (id(cam), n, str(device))
+    r = _RENDERERS.get(key)
+    if r is None:
+        if len(_RENDERERS) > 4:
+            _RENDERERS.clear()
+        r = _RENDERERS[key] = (FusedRenderer(cam, n, device=device), cam)
+    return r[0]
+
+
+def get_loss(params, curr_data, variables, iter_time_idx, loss_weights, use_sil_for_loss,
+             sil_thres, use_l1, ignore_outlier_depth_loss, tracking=False,
+             mapping=False, do_ba=False, plot_dir=None, visualize_tracking_loss=False,
+             tracking_iteration=None, additional_mask=None, dataset_name=None,
+             presence_sil_mask_mse_ls=None, sil_thres_ls=None, far_depth_filter_thres=None, vis_mask_thres=0.05,
+             vis_mask=None, backend="fused"):
+    """Compute loss for mapping and tracking -- signature and return values of the reference's
+    get_loss (src/vtgaussian_slam.py:407-689).  `backend="dropin"` follows the reference
+    literally (two Renderer calls); `backend="fused"` (default) renders the six planes in one
+    pass with the front end and the pose / parameter chain inside the CUDA kernels.  The
+    overlap-visibility mask the reference derives from neighbouring keyframes (:536-583) is
+    SLAM policy outside this path: pass it precomputed as `vis_mask`."""
+    for k, v in params.items():
+        if not isinstance(v, torch.Tensor):
+            params[k] = torch.tensor(v).float().contiguous()
+    gaussians_grad = not tracking
+    camera_grad = tracking or (mapping and do_ba)
+
+    if backend == "dropin":
+        transformed_gaussians = transform_to_frame(params, iter_time_idx, gaussians_grad=gaussians_grad, camera_grad=camera_grad)
+        rendervar = transformed_params2rendervar(params, transformed_gaussians)
+        depth_sil_rendervar = transformed_params2depthplussilhouette(params, curr_data['w2c'], transformed_gaussians)
+        rendervar['means2D'].retain_grad()
+        im, radius, _, = Renderer(raster_settings=curr_data['cam'])(**rendervar)
+        variables['means2D'] = rendervar['means2D']
+        depth_sil, _, _, = Renderer(raster_settings=curr_data['cam'])(**depth_sil_rendervar)
+    elif backend == "fused":
+        if params['log_scales'].shape[1] != 1:
+            raise NotImplementedError("fused backend: isotropic Gaussians only; use backend='dropin'")
+        dev = params['means3D'].device
+        r = _renderer_for(curr_data['cam'], params['means3D'].shape[0], dev)
+        w2c = torch.as_tensor(curr_data['w2c']).detach().float().cpu()
+        r.depth_row = tuple(float(v) for v in w2c[2])
+        cam_q = params['cam_unnorm_rots'][0, :, iter_time_idx]
+        cam_t = params['cam_trans'][0, :, iter_time_idx]
+        if not camera_grad:
+            cam_q, cam_t = cam_q.detach(), cam_t.detach()
+        g = (lambda t: t) if gaussians_grad else (lambda t: t.detach())
+        im, depth_sil, radius, means2D = _FusedRender.apply(
+            r, g(params['means3D']), g(params['rgb_colors']), g(params['unnorm_rotations']), g(params['logit_opacities']),
+            g(params['log_scales']), cam_q, cam_t, gaussians_grad, camera_grad)
+        variables['means2D'] = means2D          # .grad is not populated; the tensor itself receives dL/dmeans2D
+    else:
+        raise ValueError(f"unknown backend {backend!r}")
+
+    loss, weighted_losses = _masks_and_losses(
+        im, depth_sil, curr_data, loss_weights, use_sil_for_loss, sil_thres, use_l1, ignore_outlier_depth_loss, tracking,
+        additional_mask, dataset_name, tracking_iteration, presence_sil_mask_mse_ls, sil_thres_ls, far_depth_filter_thres,
+        vis_mask)
+
+    seen = radius > 0
+    variables['max_2D_radius'][seen] = torch.max(radius[seen], variables['max_2D_radius'][seen])
+    variables['seen'] = seen
+    if presence_sil_mask_mse_ls is not None:
+        return loss, variables, weighted_losses, presence_sil_mask_mse_ls, sil_thres_ls
+    return loss, variables, weighted_losses
+
+
+def mapping_loss_and_grad(image6, kf, w_im=1.0, w_depth=1.0):
+    """Mapping loss of get_loss (:597,:608: mean-L1 depth on depth>0, 0.8 L1 + 0.2 (1-SSIM) colour)
+    and its gradient w.r.t. the r,g,b,depth planes, for MappingSolver."""
+    img = image6.detach().clone().requires_grad_(True)
+    data = dict(im=kf["gt_rgb"], depth=kf["gt_depth"].reshape(1, *image6.shape[1:]))
+    loss, _ = _masks_and_losses(img[:3], img[3:6], data, dict(im=w_im, depth=w_depth), False, 0.5, True, False, False,
+                                None, None, None, None, None, None, None)
+    (g,) = torch.autograd.grad(loss, img)
+    return loss.detach(), g[:4].contiguous()
