@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py -- fwd+bwd render iterations/s of the VTGaussian-SLAM hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched with torchrun)
+    python bench.py --impl reference --steps K --warmup W    (CPU oracle port on the host cores)
+
+A "step" is one tracking iteration of BASELINE.json configs[1] (Replica room0-shaped 1200x680,
+~1.0 M view-tied Gaussians): fused six-plane render -> masked-L1 tracking loss -> backward to
+the 7 pose numbers -> Adam (reference src/vtgaussian_slam.py:1794-1891).  At N>1 the image is
+sharded by tile bands with one 16-float all-reduce per iteration ("strong" scaling).
+
+Prints ONE JSON line (rank 0).  `value` = iterations/s with everything resident in HBM (CUDA
+graph replay, CUDA-event timed, max over ranks); `e2e` = the same iteration through the
+reference-facing API (slam_ops.get_loss + backward + torch Adam) with the frame copied H2D
+from pinned memory and the loss read back D2H every step; `roofline` = the dominant kernel
+against the measured HBM peak; `cpu_baseline` = the oracle port on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "fwd+bwd render iters/s, Replica 1200x680 view-tied Gaussians"
+UNIT = "iters/s"
+LOSS_W = dict(im=0.5, depth=0.025)          # configs/replica/room0.py:74-77
+SIL_THRES = 0.99
+FP32_NOMINAL_TFLOPS = 74.4                  # 148 SM x 128 lanes x 2 x 1.965 GHz
+
+
+def build_workload(small=False, seed=0):
+    """configs[1]: one Replica-shaped frame, one Gaussian per pixel (816 000) + 200 000 edge-densified
+    Gaussians of the 2x grid, a mapped ('trained') section, pose perturbed by ~1 cm / 0.5 deg."""
+    from vtgaussian_slam_b200 import synthetic
+    if small:
+        fr = synthetic.make_frame("replica", 300, 170, seed=seed)
+        p = synthetic.view_tied_gaussians(fr, n_edge=12000, opacity="trained")
+    else:
+        fr = synthetic.make_frame("replica", seed=seed)
+        p = synthetic.view_tied_gaussians(fr, n_edge=200000, opacity="trained")
+    q, t = synthetic.perturbed_pose(seed=1, trans_sigma=0.01, rot_deg=0.5)
+    s = synthetic.setup_camera(fr["W"], fr["H"], fr["K"], np.eye(4))
+    name = "tracking_replica_%dx%d_N%d" % (fr["W"], fr["H"], p["means3D"].shape[0])
+    return dict(frame=fr, params=p, q=q, t=t, settings=s, name=name)
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_iteration(wl, tile_rows=(0, 0)):
+    """One tracking iteration of the oracle port: front end + six-plane forward + tracking loss +
+    backward (all host cores through OpenMP).  Returns (seconds, loss)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle                                         # the checker; timed here only as the CPU baseline
+    fr, p, s = wl["frame"], wl["params"], wl["settings"]
+    cam = oracle.make_camera(fr["W"], fr["H"], s["tanfovx"], s["tanfovy"], s["viewmatrix"], s["projmatrix"], tile_rows=tile_rows)
+    t0 = time.perf_counter()
+    m, sc, rot, op, c6 = oracle.frontend(p["means3D"], p["rgb_colors"], p["unnorm_rotations"], p["logit_opacities"],
+                                         p["log_scales"], wl["q"], wl["t"])
+    orc = oracle.Oracle()
+    out = orc.forward(cam, m, sc, rot, op, c6)
+    img = out["color"]
+    gd = fr["depth"][0]
+    mask = (gd > 0) & (img[4] > SIL_THRES) & ~np.isnan(img[3]) & ~np.isnan(img[5] - img[3] ** 2)
+    if tile_rows[1] > tile_rows[0]:
+        band = np.zeros_like(mask)
+        band[tile_rows[0] * 16:tile_rows[1] * 16] = True
+        mask &= band
+    dL = np.zeros((6,) + gd.shape, np.float32)
+    e_im = img[:3] - fr["im"]
+    e_d = img[3] - gd
+    dL[:3] = LOSS_W["im"] * np.sign(e_im) * mask
+    dL[3] = LOSS_W["depth"] * np.sign(e_d) * mask
+    loss = LOSS_W["im"] * np.abs(e_im)[:, mask].sum() + LOSS_W["depth"] * np.abs(e_d)[mask].sum()
+    orc.backward(dL)
+    return time.perf_counter() - t0, float(loss), out
+
+
+def run_reference_arm(args, wl):
+    cores = len(os.sched_getaffinity(0))
+    gy = (wl["frame"]["H"] + 15) // 16
+    # bounded sample: a centred band of tile rows sized so that W+K steps finish within a few minutes
+    t_full, _, _ = cpu_iteration(wl)
+    budget = 150.0
+    frac = min(1.0, budget / max(t_full * (args.steps + args.warmup), 1e-9))
+    rows = max(1, int(round(gy * frac)))
+    r0 = (gy - rows) // 2
+    band = (0, 0) if rows >= gy else (r0, r0 + rows)
+    for _ in range(args.warmup):
+        cpu_iteration(wl, band)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_iteration(wl, band)
+    dt = (time.perf_counter() - t0) / args.steps
+    work_frac = rows / gy
+    value = work_frac / dt            # iterations/s, extrapolated by tile rows when a band was sampled
+    sample = ("full iteration" if rows >= gy else f"{rows} of {gy} tile rows per step (value extrapolated by rows)") + \
+             f"; first full iteration took {t_full:.2f} s"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3 / work_frac, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": {"workload": wl["name"], "what": "CPU oracle port of the splatting path (reference rasteriser is an absent pip dependency)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def band_for_rank(gy, rank, world):
+    base, rem = divmod(gy, world)
+    r0 = rank * base + min(rank, rem)
+    return (r0, r0 + base + (1 if rank < rem else 0))
+
+
+def run_ours(args, wl):
+    import torch
+    import torch.distributed as dist
+    from vtgaussian_slam_b200 import _lib, slam_ops
+    from vtgaussian_slam_b200.fused import TrackingSolver
+    from vtgaussian_slam_b200.rasterizer import GaussianRasterizationSettings
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    pg = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        pg = dist.group.WORLD
+    fr, s = wl["frame"], wl["settings"]
+    W, H = fr["W"], fr["H"]
+    gy = (H + 15) // 16
+    settings = GaussianRasterizationSettings(
+        image_height=H, image_width=W, tanfovx=s["tanfovx"], tanfovy=s["tanfovy"], bg=torch.tensor(s["bg"], device=dev),
+        scale_modifier=1.0, viewmatrix=torch.tensor(s["viewmatrix"], device=dev), projmatrix=torch.tensor(s["projmatrix"], device=dev),
+        sh_degree=0, campos=torch.tensor(s["campos"], device=dev), prefiltered=False)
+    params = {k: torch.tensor(v, device=dev) for k, v in wl["params"].items()}
+    N = params["means3D"].shape[0]
+    band = band_for_rank(gy, rank, world) if world > 1 else (0, 0)
+    solver = TrackingSolver(settings, params, device=dev, w_im=LOSS_W["im"], w_depth=LOSS_W["depth"], sil_thres=SIL_THRES,
+                            tile_rows=band, use_graph=True, process_group=pg)
+    gt_rgb = torch.tensor(fr["im"]).pin_memory()
+    gt_depth = torch.tensor(fr["depth"]).pin_memory()
+    solver.set_frame(gt_rgb, gt_depth, wl["q"], wl["t"])
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    # ---- device-resident timed region: W warm-up + K timed graph replays ---------------------------
+    for _ in range(max(args.warmup, 3)):
+        solver.step()
+    overflow, R = solver.r.overflowed()
+    if overflow:
+        raise SystemExit(f"pair buffer overflow: R={R}")
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        solver.step()
+    e1.record()
+    sync_all()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = ms.item() / args.steps
+    loss_now = solver.loss_terms()[0].item()
+
+    # ---- per-kernel durations (eager, CUDA events around every launch of the library) --------------
+    solver.use_graph = False
+    _lib.profile_enable(True)
+    torch.cuda.synchronize(dev)
+    for _ in range(args.steps):
+        solver.step()
+    torch.cuda.synchronize(dev)
+    prof = _lib.profile_summary()
+    _lib.profile_enable(False)
+    launches_per_step = sum(n for n, _ in prof.values()) // args.steps
+    total_prof_ms = sum(t for _, t in prof.values())
+    S = int(solver.r.ws.n_contrib.to(torch.int64).sum().item())
+    _, R = solver.r.overflowed()
+    P = W * H
+    kbytes = {       # ALGORITHMIC bytes per launch (DESIGN.md "Kernels and their rooflines")
+        "preprocess_kernel": N * (12 + 4 + 16 + 4 + 12) + N * (64 + 4 + 4) + R * 4,
+        "scatter_kernel": N * (4 + 16) + R * (8 + 4),
+        "tile_sort_kernel": R * (8 + 8 + 4),
+        "blend_forward_kernel": R * 52 + P * (6 * 4 + 4 + 4),
+        "tracking_loss_kernel": P * (6 * 4 + 4 * 4 + 4 * 4),
+        "blend_backward_kernel": R * 52 + P * (4 * 4 + 4 + 4) + N * 48,
+        "fused_preprocess_backward_kernel": N * (48 + 12 + 4 + 16 + 4 + 64) + N * 48,
+    }
+    dom = max(prof.items(), key=lambda kv: kv[1][1])
+    dom_name, (dom_n, dom_ms) = dom
+    dom_s = dom_ms * 1e-3 / dom_n
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = kbytes.get(dom_name, 0) / dom_s / 1e9
+    hbm_floor_s = sum(kbytes.get(k, 0) for k in prof) / (hbm_peak * 1e9)
+    roofline = {
+        "bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+        "frac": achieved / hbm_peak, "traffic": None,
+        "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)",
+        "kernel_us": dom_s * 1e6, "kernel_share_of_step": dom_ms / total_prof_ms,
+        "note": "the blend kernels are FP32-issue bound (no dense contraction, tensor cores unused): see pair_tests_per_s",
+        "pair_tests_per_launch": S, "pair_tests_per_s": S / dom_s,
+        "iteration_hbm_floor_us": hbm_floor_s * 1e6, "iteration_hbm_frac": hbm_floor_s / (ms_per_step * 1e-3),
+        "per_kernel_us": {k: round(t * 1e3 / n, 2) for k, (n, t) in prof.items()},
+    }
+
+    # ---- e2e: the reference-facing API with host buffers ------------------------------------------
+    solver = None
+    torch.cuda.empty_cache()
+    P_ = {k: torch.nn.Parameter(v.clone()) for k, v in params.items()}
+    P_["cam_unnorm_rots"] = torch.nn.Parameter(torch.tensor(wl["q"], device=dev).reshape(1, 4, 1).contiguous())
+    P_["cam_trans"] = torch.nn.Parameter(torch.tensor(wl["t"], device=dev).reshape(1, 3, 1).contiguous())
+    lrs = dict(means3D=0.0, rgb_colors=0.0, unnorm_rotations=0.0, logit_opacities=0.0, log_scales=0.0,
+               cam_unnorm_rots=0.0004, cam_trans=0.002)                  # configs/replica/room0.py:78-86
+    opt = slam_ops.initialize_optimizer(P_, lrs, tracking=True)
+    variables = dict(max_2D_radius=torch.zeros(N, device=dev))
+    data = dict(cam=settings, im=torch.empty((3, H, W), device=dev), depth=torch.empty((1, H, W), device=dev),
+                w2c=torch.eye(4, device=dev))
+    loss_host = torch.zeros(1).pin_memory()
+
+    def e2e_step():
+        data["im"].copy_(gt_rgb, non_blocking=True)            # H2D of the step's inputs (pinned)
+        data["depth"].copy_(gt_depth, non_blocking=True)
+        loss, _, _ = slam_ops.get_loss(P_, data, variables, 0, LOSS_W, True, SIL_THRES, True, False, tracking=True,
+                                       dataset_name="tum", backend="fused")
+        loss.backward()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        loss_host.copy_(loss.detach().reshape(1), non_blocking=False)      # D2H of the step's result
+        return loss_host
+
+    e2e = None
+    if world == 1:
+        for _ in range(3):
+            e2e_step()
+        torch.cuda.synchronize(dev)
+        k2 = max(3, min(args.steps, 20))
+        e0.record()
+        for _ in range(k2):
+            e2e_step()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        e2e_ms = e0.elapsed_time(e1) / k2
+        e2e = {"value": 1e3 / e2e_ms, "unit": UNIT, "h2d_bytes_per_step": int(4 * 4 * P), "d2h_bytes_per_step": 4,
+               "ms_per_step": e2e_ms, "api": "slam_ops.get_loss(backend='fused') + loss.backward() + torch.optim.Adam.step()"}
+
+    # ---- CPU baseline (rank 0, N=1 only): the oracle port on a bounded sample ----------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        t_cpu, _, _ = cpu_iteration(wl)
+        cpu = {"value": 1.0 / t_cpu, "unit": UNIT, "cores": len(os.sched_getaffinity(0)), "kind": "port",
+               "sample": f"1 full iteration of the same workload on the host cores ({t_cpu:.2f} s)"}
+
+    if rank == 0:
+        working_set_mb = (N * (64 + 64 + 44) + R * 12 + P * (6 + 4 + 4 + 2) * 4) / 1e6
+        line = {
+            "metric": METRIC, "value": 1e3 / ms_per_step, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "config": {"workload": wl["name"], "gaussians": N, "pairs_R": R, "pair_tests_S": S,
+                       "iteration": "fused 6-plane render + masked-L1 tracking loss + backward to pose + Adam",
+                       "parallelism": f"tile-band x{world} + 16-float all-reduce" if world > 1 else "single GPU",
+                       "l2": f"working set {working_set_mb:.0f} MB per iteration > 126 MB L2 (no explicit flush)",
+                       "loss_after_run": loss_now},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
+            "launches_per_step": launches_per_step, "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--small", action="store_true", help="300x170 debug workload")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        run_reference_arm(args, build_workload(args.small))
+        return
+    run_ours(args, build_workload(args.small))
+
+
+if __name__ == "__main__":
+    main()

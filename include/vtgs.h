@@ -292,6 +292,15 @@ VTGS_API int vtgs_adam(float* param, const float* grad, float* exp_avg, float* e
               float lr, float beta1, float beta2, float eps, int32_t step,
               const int32_t* step_dev, void* stream);
 
+/*
+ * Optional per-kernel timing for bench.py's roofline: while enabled, every kernel launch of
+ * the library is bracketed by CUDA events on its launching stream.  vtgs_profile_summary
+ * synchronises those events and writes one line per kernel: "<name> <launches> <total_ms>".
+ * Not capturable in a CUDA graph; off by default (zero overhead).
+ */
+VTGS_API int vtgs_profile_enable(int32_t on);
+VTGS_API int vtgs_profile_summary(char* buf, uint64_t capacity);
+
 #ifdef __cplusplus
 }
 #endif

@@ -94,6 +94,8 @@ SYMBOLS = {
     "vtgs_pose_scratch_floats": (C.c_uint64, [C.c_int64]),
     "vtgs_fused_backward": (C.c_int, [C.POINTER(VtgsCamera), C.POINTER(VtgsParams), C.POINTER(VtgsPose), _P, C.c_int32,
                                       C.POINTER(VtgsParamGrads), C.POINTER(VtgsBuffers), _P]),
+    "vtgs_profile_enable": (C.c_int, [C.c_int32]),
+    "vtgs_profile_summary": (C.c_int, [C.c_char_p, C.c_uint64]),
     "vtgs_adam": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32, _P, _P]),
 }
 
@@ -141,3 +143,18 @@ def check(code: int):
         if code == -3:
             raise NotImplementedError(msg)
         raise VtgsError(f"vtgs error {code}: {msg}")
+
+
+def profile_enable(on: bool):
+    check(lib().vtgs_profile_enable(1 if on else 0))
+
+
+def profile_summary():
+    """-> {kernel name: (launches, total_ms)} of everything launched since profile_enable(True)."""
+    buf = C.create_string_buffer(1 << 16)
+    check(lib().vtgs_profile_summary(buf, len(buf)))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, n, ms = line.split()
+        out[name] = (int(n), float(ms))
+    return out

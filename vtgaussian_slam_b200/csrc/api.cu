@@ -3,6 +3,11 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -13,6 +18,27 @@ void set_error(const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+
+// ---- optional per-kernel event timing ----------------------------------------------------------
+struct ProfRec { const char* name; cudaEvent_t a, b; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+static std::mutex g_prof_mu;
+
+ProfScope::ProfScope(const char* name, cudaStream_t st) : slot(-1), stream(st) {
+    if (!g_prof_on) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    ProfRec r{name, nullptr, nullptr};
+    if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+    cudaEventRecord(r.a, st);
+    g_prof.push_back(r);
+    slot = (int)g_prof.size() - 1;
+}
+ProfScope::~ProfScope() {
+    if (slot < 0) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    cudaEventRecord(g_prof[slot].b, stream);
 }
 }  // namespace vtgs
 
@@ -176,6 +202,41 @@ int vtgs_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq
     if (n > 0) VTGS_REQUIRE(param && grad && exp_avg && exp_avg_sq, "pointer is NULL");
     VTGS_REQUIRE(step_dev != nullptr || step >= 1, "step must be >= 1");
     return launch_adam(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step, step_dev, (cudaStream_t)stream);
+}
+
+int vtgs_profile_enable(int32_t on) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (on) {
+        for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+        g_prof.clear();
+    }
+    g_prof_on = on != 0;
+    return VTGS_OK;
+}
+
+int vtgs_profile_summary(char* buf, uint64_t capacity) {
+    VTGS_REQUIRE(buf != nullptr && capacity > 0, "buffer is NULL");
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    std::map<std::string, std::pair<int, double>> agg;
+    std::vector<std::string> order;
+    for (auto& r : g_prof) {
+        if (cudaEventSynchronize(r.b) != cudaSuccess) continue;
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) continue;
+        if (!agg.count(r.name)) order.push_back(r.name);
+        auto& e = agg[r.name];
+        e.first += 1;
+        e.second += ms;
+    }
+    std::string out;
+    for (auto& n : order) {
+        char line[256];
+        snprintf(line, sizeof(line), "%s %d %.6f\n", n.c_str(), agg[n].first, agg[n].second);
+        out += line;
+    }
+    if (out.size() + 1 > capacity) { set_error("profile buffer too small"); return VTGS_E_INVALID; }
+    memcpy(buf, out.c_str(), out.size() + 1);
+    return VTGS_OK;
 }
 
 }  // extern "C"

@@ -376,13 +376,13 @@ int launch_backward(const VtgsCamera* camera, int64_t N,
     const int band_tiles = (cam.row1 - cam.row0) * cam.gx;
     if (N <= 0) return VTGS_OK;
     if (band_tiles > 0) {
-        blend_backward_kernel<false><<<band_tiles, 256, 0, stream>>>(cam, buf->tile_ranges, buf->point_list, geom, buf->final_T,
-                                                                      buf->n_contrib, dL_dout_color, buf->grad_geom);
+        { VTGS_PROF("blend_backward_kernel", stream); blend_backward_kernel<false><<<band_tiles, 256, 0, stream>>>(cam, buf->tile_ranges, buf->point_list, geom, buf->final_T,
+                                                                      buf->n_contrib, dL_dout_color, buf->grad_geom); }
         VTGS_LAUNCH_CHECK();
     }
-    preprocess_backward_kernel<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(cam, N, means3D, scales, rotations, nullptr, geom,
+    { VTGS_PROF("preprocess_backward_kernel", stream); preprocess_backward_kernel<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(cam, N, means3D, scales, rotations, nullptr, geom,
                                                                                buf->grad_geom, dL_dmeans2D, dL_dcolors, dL_dopacity,
-                                                                               dL_dmeans3D, dL_dscales, dL_drotations);
+                                                                               dL_dmeans3D, dL_dscales, dL_drotations); }
     VTGS_LAUNCH_CHECK();
     return VTGS_OK;
 }
@@ -407,7 +407,7 @@ __global__ void pose_matrix_kernel(const float* __restrict__ q_un, const float* 
 }
 
 int launch_pose_matrix(const VtgsPose* pose, VtgsCounters* counters, cudaStream_t stream) {
-    pose_matrix_kernel<<<1, 32, 0, stream>>>(pose->cam_unnorm_rot, pose->cam_trans, counters);
+    { VTGS_PROF("pose_matrix_kernel", stream); pose_matrix_kernel<<<1, 32, 0, stream>>>(pose->cam_unnorm_rot, pose->cam_trans, counters); }
     VTGS_LAUNCH_CHECK();
     return VTGS_OK;
 }
@@ -563,18 +563,18 @@ int launch_fused_backward(const VtgsCamera* camera, const VtgsParams* params, co
     const int blocks = (int)((N + 255) / 256);
     if (N > 0) {
         if (band_tiles > 0) {
-            blend_backward_kernel<true><<<band_tiles, 256, 0, stream>>>(cam, buf->tile_ranges, buf->point_list, geom, buf->final_T,
-                                                                         buf->n_contrib, dL_dimage4, buf->grad_geom);
+            { VTGS_PROF("blend_backward_kernel", stream); blend_backward_kernel<true><<<band_tiles, 256, 0, stream>>>(cam, buf->tile_ranges, buf->point_list, geom, buf->final_T,
+                                                                         buf->n_contrib, dL_dimage4, buf->grad_geom); }
             VTGS_LAUNCH_CHECK();
         }
-        fused_preprocess_backward_kernel<<<blocks, 256, 0, stream>>>(cam, N, *params, buf->counters->pose_R, pose->depth_row[0],
+        { VTGS_PROF("fused_preprocess_backward_kernel", stream); fused_preprocess_backward_kernel<<<blocks, 256, 0, stream>>>(cam, N, *params, buf->counters->pose_R, pose->depth_row[0],
                                                                      pose->depth_row[1], pose->depth_row[2], geom, buf->grad_geom,
-                                                                     *grads, accumulate, want_pose);
+                                                                     *grads, accumulate, want_pose); }
         VTGS_LAUNCH_CHECK();
     }
     if (want_pose) {
-        pose_finalize_kernel<<<1, 256, 0, stream>>>(grads->pose_scratch, N > 0 ? blocks : 0, buf->counters, grads->cam_unnorm_rot,
-                                                    grads->cam_trans, accumulate);
+        { VTGS_PROF("pose_finalize_kernel", stream); pose_finalize_kernel<<<1, 256, 0, stream>>>(grads->pose_scratch, N > 0 ? blocks : 0, buf->counters, grads->cam_unnorm_rot,
+                                                    grads->cam_trans, accumulate); }
         VTGS_LAUNCH_CHECK();
     }
     return VTGS_OK;

@@ -405,37 +405,35 @@ int launch_forward(const VtgsCamera* camera, int64_t N, bool fused, const FrontE
     const int blocks = (int)((N + 255) / 256);
     if (N > 0) {
         if (fused)
-            preprocess_kernel<true><<<blocks, 256, 0, stream>>>(cam, N, fe, means3D, scales, rotations, opacities, colors,
-                                                                 geom, radii, buf->tiles_touched, buf->tile_counts);
-        else
-            preprocess_kernel<false><<<blocks, 256, 0, stream>>>(cam, N, fe, means3D, scales, rotations, opacities, colors,
-                                                                  geom, radii, buf->tiles_touched, buf->tile_counts);
+            { VTGS_PROF("preprocess_kernel", stream); preprocess_kernel<true><<<blocks, 256, 0, stream>>>(cam, N, fe, means3D, scales, rotations, opacities, colors,
+                                                                 geom, radii, buf->tiles_touched, buf->tile_counts); }
+        else { VTGS_PROF("preprocess_kernel", stream); preprocess_kernel<false><<<blocks, 256, 0, stream>>>(cam, N, fe, means3D, scales, rotations, opacities, colors,
+                                                                  geom, radii, buf->tiles_touched, buf->tile_counts); }
         VTGS_LAUNCH_CHECK();
     }
-    tile_scan_kernel<<<1, 1024, 0, stream>>>(buf->tile_counts, buf->tile_ranges, num_tiles, buf->pair_capacity, buf->counters);
+    { VTGS_PROF("tile_scan_kernel", stream); tile_scan_kernel<<<1, 1024, 0, stream>>>(buf->tile_counts, buf->tile_ranges, num_tiles, buf->pair_capacity, buf->counters); }
     VTGS_LAUNCH_CHECK();
     const int band_tiles = (cam.row1 - cam.row0) * cam.gx;
     if (N > 0 && band_tiles > 0) {
-        scatter_kernel<<<blocks, 256, 0, stream>>>(N, cam.gx, geom, buf->tiles_touched, buf->tile_ranges, buf->tile_counts, buf->pair_keys);
+        { VTGS_PROF("scatter_kernel", stream); scatter_kernel<<<blocks, 256, 0, stream>>>(N, cam.gx, geom, buf->tiles_touched, buf->tile_ranges, buf->tile_counts, buf->pair_keys); }
         VTGS_LAUNCH_CHECK();
         static bool attr_set = false;
         if (!attr_set) {
             VTGS_CUDA_CHECK(cudaFuncSetAttribute(tile_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_SMEM_ELEMS * 8));
             attr_set = true;
         }
-        tile_sort_kernel<<<band_tiles, 256, SORT_SMEM_ELEMS * 8, stream>>>(buf->tile_ranges, cam.row0 * cam.gx, buf->pair_keys, buf->point_list);
+        { VTGS_PROF("tile_sort_kernel", stream); tile_sort_kernel<<<band_tiles, 256, SORT_SMEM_ELEMS * 8, stream>>>(buf->tile_ranges, cam.row0 * cam.gx, buf->pair_keys, buf->point_list); }
         VTGS_LAUNCH_CHECK();
     }
     if (band_tiles > 0) {
         if (fused)
-            blend_forward_kernel<true><<<band_tiles, 256, 0, stream>>>(cam, buf->tile_ranges, buf->point_list, geom, out_color, out_depth, buf->final_T, buf->n_contrib);
-        else
-            blend_forward_kernel<false><<<band_tiles, 256, 0, stream>>>(cam, buf->tile_ranges, buf->point_list, geom, out_color, out_depth, buf->final_T, buf->n_contrib);
+            { VTGS_PROF("blend_forward_kernel", stream); blend_forward_kernel<true><<<band_tiles, 256, 0, stream>>>(cam, buf->tile_ranges, buf->point_list, geom, out_color, out_depth, buf->final_T, buf->n_contrib); }
+        else { VTGS_PROF("blend_forward_kernel", stream); blend_forward_kernel<false><<<band_tiles, 256, 0, stream>>>(cam, buf->tile_ranges, buf->point_list, geom, out_color, out_depth, buf->final_T, buf->n_contrib); }
         VTGS_LAUNCH_CHECK();
     }
     if (band_tiles < num_tiles) {
         const size_t P = (size_t)cam.W * cam.H;
-        fill_outside_band_kernel<<<(unsigned)((P + 255) / 256), 256, 0, stream>>>(cam, fused ? 6 : 3, out_color, out_depth, buf->final_T, buf->n_contrib);
+        { VTGS_PROF("fill_outside_band_kernel", stream); fill_outside_band_kernel<<<(unsigned)((P + 255) / 256), 256, 0, stream>>>(cam, fused ? 6 : 3, out_color, out_depth, buf->final_T, buf->n_contrib); }
         VTGS_LAUNCH_CHECK();
     }
     return VTGS_OK;
@@ -454,7 +452,7 @@ __global__ void export_keys_kernel(const uint32_t* __restrict__ ranges, int num_
 int launch_export_keys(const VtgsCamera* camera, const VtgsBuffers* buf, uint64_t* out, uint64_t cap, cudaStream_t stream) {
     const CamConst cam = make_cam_const(*camera);
     const int num_tiles = cam.gx * cam.gy;
-    export_keys_kernel<<<num_tiles, 128, 0, stream>>>(buf->tile_ranges, num_tiles, buf->pair_keys, out, cap);
+    { VTGS_PROF("export_keys_kernel", stream); export_keys_kernel<<<num_tiles, 128, 0, stream>>>(buf->tile_ranges, num_tiles, buf->pair_keys, out, cap); }
     VTGS_LAUNCH_CHECK();
     return VTGS_OK;
 }
@@ -470,7 +468,7 @@ __global__ void export_geom_kernel(int64_t N, const GeomRecord* __restrict__ geo
 
 int launch_export_geometry(int64_t N, const VtgsBuffers* buf, float* means2D, float* depths, float* conic_opacity, cudaStream_t stream) {
     if (N <= 0) return VTGS_OK;
-    export_geom_kernel<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(N, reinterpret_cast<const GeomRecord*>(buf->geom), means2D, depths, conic_opacity);
+    { VTGS_PROF("export_geom_kernel", stream); export_geom_kernel<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(N, reinterpret_cast<const GeomRecord*>(buf->geom), means2D, depths, conic_opacity); }
     VTGS_LAUNCH_CHECK();
     return VTGS_OK;
 }
@@ -484,7 +482,7 @@ __global__ void mark_visible_kernel(const __grid_constant__ CamConst cam, int64_
 int launch_mark_visible(const VtgsCamera* camera, int64_t N, const float* means3D, uint8_t* present, cudaStream_t stream) {
     if (N <= 0) return VTGS_OK;
     const CamConst cam = make_cam_const(*camera);
-    mark_visible_kernel<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(cam, N, means3D, present);
+    { VTGS_PROF("mark_visible_kernel", stream); mark_visible_kernel<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(cam, N, means3D, present); }
     VTGS_LAUNCH_CHECK();
     return VTGS_OK;
 }

@@ -97,10 +97,10 @@ int launch_loss(const VtgsCamera* camera, const VtgsLossConfig* cfg, const float
     const size_t npx = band_pixels(cam);
     const int nblocks = (int)((npx + 255) / 256);
     if (nblocks > 0) {
-        tracking_loss_kernel<<<nblocks, 256, 0, stream>>>(cam, *cfg, image6, gt_rgb, gt_depth, dL_dimage4, scratch);
+        { VTGS_PROF("tracking_loss_kernel", stream); tracking_loss_kernel<<<nblocks, 256, 0, stream>>>(cam, *cfg, image6, gt_rgb, gt_depth, dL_dimage4, scratch); }
         VTGS_LAUNCH_CHECK();
     }
-    loss_finalize_kernel<<<1, 256, 0, stream>>>(scratch, nblocks, *cfg, loss_terms);
+    { VTGS_PROF("loss_finalize_kernel", stream); loss_finalize_kernel<<<1, 256, 0, stream>>>(scratch, nblocks, *cfg, loss_terms); }
     VTGS_LAUNCH_CHECK();
     return VTGS_OK;
 }
@@ -131,7 +131,7 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
 int launch_adam(float* param, const float* grad, float* m, float* v, int64_t n, float lr, float b1,
                 float b2, float eps, int step, const int32_t* step_dev, cudaStream_t stream) {
     if (n <= 0) return VTGS_OK;
-    adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(param, grad, m, v, n, lr, b1, b2, eps, step, step_dev);
+    { VTGS_PROF("adam_kernel", stream); adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(param, grad, m, v, n, lr, b1, b2, eps, step, step_dev); }
     VTGS_LAUNCH_CHECK();
     return VTGS_OK;
 }

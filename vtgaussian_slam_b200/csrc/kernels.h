@@ -7,6 +7,15 @@
 
 namespace vtgs {
 
+// RAII event bracket around one kernel launch (only when vtgs_profile_enable(1) was called).
+struct ProfScope {
+    ProfScope(const char* name, cudaStream_t stream);
+    ~ProfScope();
+    int slot;
+    cudaStream_t stream;
+};
+#define VTGS_PROF(name, stream) vtgs::ProfScope _prof_scope(name, stream)
+
 // Front end of the fused path (transform_to_frame + activations); unused in API mode.
 struct FrontEnd {
     const float* pose_Rt;     // device: R[9] row-major then t[3] (VtgsCounters.pose_R/pose_t)

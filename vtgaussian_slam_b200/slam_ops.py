@@ -114,7 +114,7 @@ def transform_to_frame(params, time_idx, gaussians_grad, camera_grad, opt_cam_ro
         cam_rot = F.normalize(params['cam_unnorm_rots'][..., time_idx].detach())
         cam_tran = params['cam_trans'][..., time_idx].detach()
     dev = params['means3D'].device
-    rel_w2c = torch.eye(4, device=dev).float()
+    rel_w2c = torch.eye(4, device=dev, dtype=params['means3D'].dtype)
     rel_w2c[:3, :3] = build_rotation(cam_rot)
     rel_w2c[:3, 3] = cam_tran
     if latest_w2c is not None:
@@ -125,7 +125,7 @@ def transform_to_frame(params, time_idx, gaussians_grad, camera_grad, opt_cam_ro
     else:
         pts, unnorm_rots = params['means3D'].detach(), params['unnorm_rotations'].detach()
     transformed_gaussians = {}
-    pts_ones = torch.ones(pts.shape[0], 1, device=dev).float()
+    pts_ones = torch.ones(pts.shape[0], 1, device=dev, dtype=pts.dtype)
     pts4 = torch.cat((pts, pts_ones), dim=1)
     transformed_gaussians['means3D'] = (rel_w2c @ pts4.T).T[:, :3]
     if transform_rots:
@@ -157,7 +157,7 @@ def get_depth_and_silhouette(pts_3D, w2c):
     pts_in_cam = (w2c @ pts4.transpose(0, 1)).transpose(0, 1)
     depth_z = pts_in_cam[:, 2].unsqueeze(-1)
     depth_z_sq = torch.square(depth_z)
-    depth_silhouette = torch.zeros((pts_3D.shape[0], 3), device=pts_3D.device).float()
+    depth_silhouette = torch.zeros((pts_3D.shape[0], 3), device=pts_3D.device, dtype=pts_3D.dtype)
     depth_silhouette[:, 0] = depth_z.squeeze(-1)
     depth_silhouette[:, 1] = 1.0
     depth_silhouette[:, 2] = depth_z_sq.squeeze(-1)
