@@ -24,6 +24,26 @@
 
 namespace vtgs {
 
+// Warp-collective walk over every lane's tile rect [minx,maxx) x [miny,maxy).  Each step all lanes
+// present their current tile (or none); lanes presenting the same tile are grouped with
+// match.any so that the callback can issue ONE atomic per distinct tile:
+//   f(tile, peers_mask, rank_in_group, is_leader).  Must be called by all 32 lanes.
+template <typename F>
+__device__ __forceinline__ void warp_tile_walk(int minx, int miny, int maxx, int maxy, int gx, F f) {
+    const int lane = threadIdx.x & 31;
+    int tx = minx, ty = miny;
+    bool have = (maxx > minx) && (maxy > miny);
+    while (__any_sync(VTGS_FULL_MASK, have)) {
+        const int tile = have ? ty * gx + tx : -1 - lane;      // distinct negative ids: never grouped
+        const uint32_t peers = __match_any_sync(VTGS_FULL_MASK, tile);
+        if (have) {
+            const int rank = __popc(peers & ((1u << lane) - 1u));
+            f(tile, peers, rank, rank == 0);
+            if (++tx >= maxx) { tx = minx; if (++ty >= maxy) have = false; }
+        }
+    }
+}
+
 // =============================== K1': preprocess =========================================
 // One thread per Gaussian.  [N,3] arrays are staged through shared memory so that global
 // loads are unit-stride; rotations are float4 loads when 16-byte aligned.
@@ -49,8 +69,8 @@ preprocess_kernel(const __grid_constant__ CamConst cam, int64_t N, FrontEnd fe,
         if (!FUSED || fe.log_scales_dim == 3) s_b[k] = scales[base * 3 + k];
     }
     __syncthreads();
-    if (i >= N) return;
-
+    int w_minx = 0, w_maxx = 0, w_miny = 0, w_maxy = 0;       // tile rect to count (empty when culled / out of range)
+    if (i < N) {
     float x = s_a[3 * tid], y = s_a[3 * tid + 1], z = s_a[3 * tid + 2];
     float sx, sy, sz, qr, qx, qy, qz, op, c3;
     {
@@ -103,8 +123,7 @@ preprocess_kernel(const __grid_constant__ CamConst cam, int64_t N, FrontEnd fe,
         rec.q2 = make_float4(s_c[3 * tid], s_c[3 * tid + 1], s_c[3 * tid + 2], c3);
         rec.q3 = make_float4(g.depth, hy, __uint_as_float((uint32_t)g.minx | ((uint32_t)miny << 16)),
                              __uint_as_float((uint32_t)g.maxx | ((uint32_t)(hgt > 0 ? maxy : miny) << 16)));
-        for (int ty = miny; ty < maxy; ++ty)
-            for (int tx = g.minx; tx < g.maxx; ++tx) atomicAdd(&tile_counts[ty * cam.gx + tx], 1u);
+        w_minx = g.minx; w_maxx = g.maxx; w_miny = miny; w_maxy = hgt > 0 ? maxy : miny;
     } else {
         rec.q0 = make_float4(0.f, 0.f, 1.0f, 0.f);
         rec.q1 = make_float4(0.f, 0.f, 0.f, -1e30f);
@@ -114,6 +133,12 @@ preprocess_kernel(const __grid_constant__ CamConst cam, int64_t N, FrontEnd fe,
     geom[i] = rec;
     radii[i] = g.radius;
     tiles_touched[i] = tiles;
+    }
+    // per-tile histogram, warp-aggregated: neighbouring Gaussians (neighbouring pixels of a view-tied
+    // section) touch the same tiles, so one atomic per distinct tile per warp step instead of one per lane
+    warp_tile_walk(w_minx, w_miny, w_maxx, w_maxy, cam.gx, [&](int tile, uint32_t peers, int /*rank*/, bool leader) {
+        if (leader) atomicAdd(&tile_counts[tile], (uint32_t)__popc(peers));
+    });
 }
 
 // =============================== K2'/K5a': tile scan = tile ranges =========================
@@ -193,18 +218,21 @@ scatter_kernel(int64_t N, int gx, const GeomRecord* __restrict__ geom, const uin
                const uint32_t* __restrict__ ranges, uint32_t* __restrict__ tile_cursor,
                uint64_t* __restrict__ pair_keys) {
     const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (i >= N) return;
-    if (tiles_touched[i] == 0) return;
-    const float4 q3 = geom[i].q3;
-    const uint32_t rmin = __float_as_uint(q3.z), rmax = __float_as_uint(q3.w);
-    const int minx = rmin & 0xffff, miny = rmin >> 16, maxx = rmax & 0xffff, maxy = rmax >> 16;
-    const uint64_t key = ((uint64_t)__float_as_uint(q3.x) << 32) | (uint64_t)(uint32_t)i;
-    for (int ty = miny; ty < maxy; ++ty)
-        for (int tx = minx; tx < maxx; ++tx) {
-            const int t = ty * gx + tx;
-            const uint32_t pos = ranges[2 * t] + atomicAdd(&tile_cursor[t], 1u);
-            if (pos < ranges[2 * t + 1]) pair_keys[pos] = key;
-        }
+    int minx = 0, miny = 0, maxx = 0, maxy = 0;
+    uint64_t key = 0;
+    if (i < N && tiles_touched[i] != 0) {
+        const float4 q3 = geom[i].q3;
+        const uint32_t rmin = __float_as_uint(q3.z), rmax = __float_as_uint(q3.w);
+        minx = rmin & 0xffff; miny = rmin >> 16; maxx = rmax & 0xffff; maxy = rmax >> 16;
+        key = ((uint64_t)__float_as_uint(q3.x) << 32) | (uint64_t)(uint32_t)i;
+    }
+    warp_tile_walk(minx, miny, maxx, maxy, gx, [&](int tile, uint32_t peers, int rank, bool leader) {
+        uint32_t base = 0;
+        if (leader) base = ranges[2 * tile] + atomicAdd(&tile_cursor[tile], (uint32_t)__popc(peers));
+        base = __shfl_sync(peers, base, __ffs(peers) - 1);
+        const uint32_t pos = base + (uint32_t)rank;
+        if (pos < ranges[2 * tile + 1]) pair_keys[pos] = key;
+    });
 }
 
 // =============================== K4': per-tile sort ========================================
@@ -215,13 +243,15 @@ scatter_kernel(int64_t N, int gx, const GeomRecord* __restrict__ geom, const uin
 constexpr int SORT_SMEM_ELEMS = 4096;
 
 __device__ __forceinline__ void bitonic_network(uint64_t* __restrict__ s, int n, int npad) {
-    for (int k = 2; k <= npad; k <<= 1) {
-        // flip step
+    const int pairs = npad >> 1;
+    for (int lk = 1; (1 << lk) <= npad; ++lk) {
+        const int k = 1 << lk;
+        // flip step: partner is the mirror inside the block of k
         {
-            const int half = k >> 1;
-            for (int t = threadIdx.x; t < (npad >> 1); t += blockDim.x) {
-                const int blk = t / half, off = t - blk * half;
-                const int i = blk * k + off, p = blk * k + (k - 1 - off);
+            const int lh = lk - 1, hm = (1 << lh) - 1;
+            for (int t = threadIdx.x; t < pairs; t += blockDim.x) {
+                const int blk = t >> lh, off = t & hm;
+                const int i = (blk << lk) + off, p = (blk << lk) + (k - 1 - off);
                 if (p < n) {
                     const uint64_t a = s[i], b = s[p];
                     if (a > b) { s[i] = b; s[p] = a; }
@@ -229,9 +259,10 @@ __device__ __forceinline__ void bitonic_network(uint64_t* __restrict__ s, int n,
             }
             __syncthreads();
         }
-        for (int j = k >> 2; j > 0; j >>= 1) {
-            for (int t = threadIdx.x; t < (npad >> 1); t += blockDim.x) {
-                const int i = ((t / j) * (j << 1)) + (t % j), p = i + j;
+        for (int lj = lk - 2; lj >= 0; --lj) {
+            const int j = 1 << lj;
+            for (int t = threadIdx.x; t < pairs; t += blockDim.x) {
+                const int i = ((t >> lj) << (lj + 1)) | (t & (j - 1)), p = i + j;
                 if (p < n) {
                     const uint64_t a = s[i], b = s[p];
                     if (a > b) { s[i] = b; s[p] = a; }

@@ -56,8 +56,10 @@ def _room_depth(W, H, K, boxes=True):
     """Analytic box room seen from inside (camera at the origin looking down +z) plus a few
     fronto-parallel slabs: returns depth[H,W] (metres, z-depth) and hit points[H,W,3]."""
     fx, fy, cx, cy = K[0, 0], K[1, 1], K[0, 2], K[1, 2]
-    x = (np.arange(W, dtype=np.float64) - cx) / fx
-    y = (np.arange(H, dtype=np.float64) - cy) / fy
+    # ray through pixel (x, y) in the rasteriser's convention: setup_camera's projection maps the
+    # camera-frame direction ((x - cx + 0.5)/fx, (y - cy + 0.5)/fy, 1) onto pixel centre (x, y)
+    x = (np.arange(W, dtype=np.float64) - cx + 0.5) / fx
+    y = (np.arange(H, dtype=np.float64) - cy + 0.5) / fy
     dx, dy = np.meshgrid(x, y)
     big = 1e9
     with np.errstate(divide="ignore", invalid="ignore"):
