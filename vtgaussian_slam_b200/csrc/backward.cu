@@ -13,7 +13,7 @@
 // warp with a transposed butterfly (~4 instructions per value instead of 10), adds the
 // warp total to a per-tile shared-memory accumulator, and the tile emits ONE vectorised
 // global reduction per (tile, Gaussian) pair at the end of each staged batch.
-#include "common.cuh"
+#include "blend_common.cuh"
 #include "kernels.h"
 
 namespace vtgs {
@@ -66,55 +66,63 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[16], int lane)
 // grad_geom record per Gaussian (VTGS_GRAD_GEOM_FLOATS = 16):
 //   [0,1] dL/dmean2D (NDC-scaled)  [2,3,4] dL/dconic (xx, xy, yy)  [5] dL/dopacity
 //   [6..6+NCH) dL/dcolour  (API: r,g,b   fused: r,g,b,z)
+//
+// Block = one 16x16 tile, 8 independent warps (no block barrier), warp w = 8x4-pixel region.
+// Each warp walks the tile list BACK TO FRONT in chunks of 32 (prefetched gathers), box-culls,
+// queues survivors in its private ring and processes full groups of 32:
+//   P1 lane = splat : 32x32 "may contribute" bit matrix, transposed to the pixel lanes;
+//   P2 lane = pixel : back-to-front over ITS OWN splats: recompute alpha, unwind T, run the
+//                     accum recursion, and leave (w = alpha*T, g0 = G*dL/dalpha) in the
+//                     (splat, pixel) cell of a warp-private shared matrix;
+//   P3 lane = splat : sum its row of cells against the pixels' dL/dpixel and coordinates: the
+//                     ten per-splat sums come out of plain per-lane FMAs, no shuffles;
+//   P4 lane = splat : three red.global.add.v4.f32 per (region, splat).
+// Upstream: 9-10 global float atomics per contributing (pixel, splat) pair.
 template <bool FUSED>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __restrict__ ranges,
                       const uint32_t* __restrict__ point_list, const GeomRecord* __restrict__ geom,
                       const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
                       const float* __restrict__ dL_dpix, float* __restrict__ grad_geom) {
     constexpr int NCH = FUSED ? 4 : 3;
-    constexpr int NV = 6 + NCH;
-    constexpr int NVP = 13;                 // padded row of the shared accumulator (odd: no bank conflicts)
-    __shared__ float4 s_q0[256];
-    __shared__ float4 s_q1[256];
-    __shared__ float4 s_q2[256];
-    __shared__ uint32_t s_id[256];
-    __shared__ uint32_t s_mask[8][8];
-    __shared__ float s_acc[256 * NVP];
-    __shared__ uint32_t s_red[8];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    struct WarpArea {
+        WarpQueue Q;
+        float2 cell[32][33];        // [splat of the group][pixel], padded row: (w, g0)
+        float4 dpix[32];            // dL/dpixel of the region's pixels (r,g,b,z)
+    };
+    WarpArea* areas = reinterpret_cast<WarpArea*>(smem_raw);
 
     const int tile = cam.row0 * cam.gx + blockIdx.x;
     const int tile_x = tile % cam.gx, tile_y = tile / cam.gx;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int pix_x = tile_x * 16 + (warp & 1) * 8 + (lane & 7);
-    const int pix_y = tile_y * 16 + (warp >> 1) * 4 + (lane >> 3);
+    WarpArea& A = areas[warp];
+    WarpQueue& Q = A.Q;
+    const int rx0 = tile_x * 16 + (warp & 1) * 8, ry0 = tile_y * 16 + (warp >> 1) * 4;
+    const int pix_x = rx0 + (lane & 7), pix_y = ry0 + (lane >> 3);
     const bool inside = pix_x < cam.W && pix_y < cam.H;
     const float pxf = (float)pix_x, pyf = (float)pix_y;
-    const float tox = (float)(tile_x * 16), toy = (float)(tile_y * 16);
+    const float x0f = (float)rx0, y0f = (float)ry0;
     const uint32_t rb = ranges[2 * tile], re = ranges[2 * tile + 1];
     const size_t P = (size_t)cam.W * cam.H;
     const size_t pid = (size_t)pix_y * cam.W + pix_x;
 
     const float T_final = inside ? final_T[pid] : 0.0f;
     const uint32_t last = inside ? n_contrib[pid] : 0u;
-    float dpix[NCH];
+    float dpix[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int ch = 0; ch < NCH; ++ch) dpix[ch] = inside ? dL_dpix[ch * P + pid] : 0.0f;
+    A.dpix[lane] = make_float4(dpix[0], dpix[1], dpix[2], dpix[3]);
     const float bg_dot = cam.bg[0] * dpix[0] + cam.bg[1] * dpix[1] + cam.bg[2] * dpix[2];
-    const float ddelx_dx = 0.5f * cam.W, ddely_dy = 0.5f * cam.H;
+    const float half_w = 0.5f * cam.W, half_h = 0.5f * cam.H;
 
-    // block-wide max of n_contrib: entries beyond it are never touched
-    uint32_t mx = last;
+    // entries beyond the region's largest n_contrib are never touched
+    uint32_t todo = last;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(VTGS_FULL_MASK, mx, o));
-    if (lane == 0) s_red[warp] = mx;
-    for (int k = tid; k < 256 * NVP; k += 256) s_acc[k] = 0.0f;
-    __syncthreads();
-    uint32_t todo = 0;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) todo = max(todo, s_red[w]);
+    for (int o = 16; o > 0; o >>= 1) todo = max(todo, __shfl_xor_sync(VTGS_FULL_MASK, todo, o));
     todo = min(todo, re - rb);
     if (todo == 0) return;
+    __syncwarp();
 
     float T = T_final;
     float accum[NCH], lastc[NCH];
@@ -122,108 +130,110 @@ blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __re
     for (int ch = 0; ch < NCH; ++ch) { accum[ch] = 0.0f; lastc[ch] = 0.0f; }
     float last_alpha = 0.0f;
 
-    const int nb = (int)((todo + 255) / 256);
-    for (int b = nb - 1; b >= 0; --b) {
-        const uint32_t pos0 = (uint32_t)b * 256u;
-        const uint32_t pos = pos0 + tid;
-        uint32_t rmask = 0;
-        if (pos < todo) {
-            const uint32_t id = point_list[rb + pos];
-            const GeomRecord* rec = geom + id;
-            const float4 q0 = rec->q0, q1 = rec->q1, q2 = rec->q2, q3 = rec->q3;
-            s_q0[tid] = q0; s_q1[tid] = q1; s_q2[tid] = q2; s_id[tid] = id;
-            const float x0 = q0.x - q1.w - tox, x1 = q0.x + q1.w - tox;
-            const float y0 = q0.y - q3.y - toy, y1 = q0.y + q3.y - toy;
-            const uint32_t cm = ((x1 >= 0.0f && x0 <= 7.0f) ? 1u : 0u) | ((x1 >= 8.0f && x0 <= 15.0f) ? 2u : 0u);
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
-                if (y1 >= (float)(4 * r) && y0 <= (float)(4 * r + 3)) rmask |= cm << (2 * r);
-        }
-#pragma unroll
-        for (int w = 0; w < 8; ++w) {
-            const uint32_t m = __ballot_sync(VTGS_FULL_MASK, (rmask >> w) & 1u);
-            if (lane == 0) s_mask[w][warp] = m;
-        }
-        __syncthreads();
-
-#pragma unroll 1
-        for (int chunk = 7; chunk >= 0; --chunk) {
-            uint32_t m = s_mask[warp][chunk];
-            while (m) {
-                const int bit = 31 - __clz(m);
-                m &= ~(1u << bit);
-                const int j = chunk * 32 + bit;
-                const uint32_t pos1 = pos0 + (uint32_t)j + 1u;     // 1-based list position
-                const float4 q0 = s_q0[j];
-                const float4 q1 = s_q1[j];
+    auto process_group = [&](uint32_t head, int n) {
+        const bool have = lane < n;
+        const int slot = (head + (have ? lane : 0)) & 63;
+        const float4 e0 = Q.q0[slot], e1 = Q.q1[slot];
+        uint32_t emask;
+        uint32_t m = p1_masks(have, e0, e1, x0f, y0f, lane, emask);                  // P1: lane = splat
+        // ---- P2: lane = pixel; ring order is back-to-front, so ascending bits = descending list position
+        while (m) {
+            const int e = __ffs(m) - 1;
+            m &= m - 1;
+            const int sl = (head + e) & 63;
+            float2 out = make_float2(0.0f, 0.0f);
+            if (Q.pos[sl] <= last) {
+                const float4 q0 = Q.q0[sl];
+                const float4 q1 = Q.q1[sl];
                 const float dx = fsub(q0.x, pxf), dy = fsub(q0.y, pyf);
                 const float power = power_of(q1.x, q1.y, q1.z, dx, dy);
-                bool ok = pos1 <= last && power <= 0.0f && power >= q0.z;
-                float G = 0.0f, alpha = 0.0f;
-                if (ok) {
-                    G = vexpf(power);
-                    alpha = fminf(VTGS_ALPHA_MAX, fmul(q0.w, G));
-                    ok = alpha >= VTGS_ALPHA_MIN;
-                }
-                if (!__any_sync(VTGS_FULL_MASK, ok)) continue;
-                float v[16];
-#pragma unroll
-                for (int k = 0; k < NV; ++k) v[k] = 0.0f;
-                if (ok) {
-                    const float4 q2 = s_q2[j];
+                const float G = vexpf(power);
+                const float alpha = fminf(VTGS_ALPHA_MAX, fmul(q0.w, G));
+                if (alpha >= VTGS_ALPHA_MIN) {
+                    const float4 q2 = Q.q2[sl];
                     const float col[4] = {q2.x, q2.y, q2.z, q2.w};
-                    const float one_m = 1.0f - alpha;
-                    T = __fdividef(T, one_m);
-                    const float dchannel_dcolor = alpha * T;
+                    const float inv = __fdividef(1.0f, 1.0f - alpha);
+                    T = T * inv;
                     float dL_dalpha = 0.0f;
 #pragma unroll
                     for (int ch = 0; ch < NCH; ++ch) {
                         accum[ch] = last_alpha * lastc[ch] + (1.0f - last_alpha) * accum[ch];
                         lastc[ch] = col[ch];
                         dL_dalpha += (col[ch] - accum[ch]) * dpix[ch];
-                        v[6 + ch] = dchannel_dcolor * dpix[ch];
                     }
                     dL_dalpha *= T;
                     last_alpha = alpha;
-                    dL_dalpha += __fdividef(-T_final, one_m) * bg_dot;
-                    const float dL_dG = q0.w * dL_dalpha;
-                    const float gdx = G * dx, gdy = G * dy;
-                    const float dG_ddelx = -gdx * q1.x - gdy * q1.y;
-                    const float dG_ddely = -gdy * q1.z - gdx * q1.y;
-                    v[0] = dL_dG * dG_ddelx * ddelx_dx;
-                    v[1] = dL_dG * dG_ddely * ddely_dy;
-                    v[2] = -0.5f * gdx * dx * dL_dG;
-                    v[3] = -0.5f * gdx * dy * dL_dG;
-                    v[4] = -0.5f * gdy * dy * dL_dG;
-                    v[5] = G * dL_dalpha;
-                }
-                const float tot = warp_transpose_reduce<NV>(v, lane);
-                if ((lane & 1) == 0 && (lane >> 1) < NV) atomicAdd(&s_acc[j * NVP + (lane >> 1)], tot);
-            }
-        }
-        __syncthreads();
-        // flush: one vectorised global reduction per (tile, Gaussian) pair of this batch
-        if (pos < todo) {
-            float a[12];
-            bool any = false;
-#pragma unroll
-            for (int k = 0; k < 12; ++k) {
-                a[k] = k < NV ? s_acc[tid * NVP + k] : 0.0f;
-                any |= a[k] != 0.0f;
-                if (k < NV) s_acc[tid * NVP + k] = 0.0f;
-            }
-            if (any) {
-                float* dst = grad_geom + (size_t)s_id[tid] * VTGS_GRAD_GEOM_FLOATS;
-#pragma unroll
-                for (int k4 = 0; k4 < 3; ++k4) {
-                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * k4), "f"(a[4 * k4]),
-                                 "f"(a[4 * k4 + 1]), "f"(a[4 * k4 + 2]), "f"(a[4 * k4 + 3])
-                                 : "memory");
+                    dL_dalpha -= T_final * inv * bg_dot;
+                    out = make_float2(alpha * T, G * dL_dalpha);
                 }
             }
+            A.cell[e][lane] = out;
         }
-        __syncthreads();
+        __syncwarp();
+        // ---- P3: lane = splat: reduce my row of cells
+        float s0 = 0.f, sx = 0.f, sy = 0.f, sxx = 0.f, sxy = 0.f, syy = 0.f;
+        float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
+        uint32_t pm = emask;
+        while (pm) {
+            const int p = __ffs(pm) - 1;
+            pm &= pm - 1;
+            const float2 cw = A.cell[lane][p];
+            const float4 dp = A.dpix[p];
+            const float dx = e0.x - (x0f + (float)(p & 7)), dy = e0.y - (y0f + (float)(p >> 3));
+            c0 = fmaf(cw.x, dp.x, c0); c1 = fmaf(cw.x, dp.y, c1); c2 = fmaf(cw.x, dp.z, c2);
+            if (NCH == 4) c3 = fmaf(cw.x, dp.w, c3);
+            const float g = cw.y, gx_ = g * dx, gy_ = g * dy;
+            s0 += g; sx += gx_; sy += gy_;
+            sxx = fmaf(gx_, dx, sxx); sxy = fmaf(gx_, dy, sxy); syy = fmaf(gy_, dy, syy);
+        }
+        // ---- P4: finalize (dL/dG * G = opacity * g0) and one vector reduction per (region, splat)
+        if (emask) {
+            const float o = e0.w, ca = e1.x, cb = e1.y, cc = e1.z;
+            const float v0 = -half_w * o * (ca * sx + cb * sy);
+            const float v1 = -half_h * o * (cc * sy + cb * sx);
+            const float v2 = -0.5f * o * sxx, v3 = -0.5f * o * sxy, v4 = -0.5f * o * syy;
+            float* dst = grad_geom + (size_t)Q.id[slot] * VTGS_GRAD_GEOM_FLOATS;
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v0), "f"(v1), "f"(v2), "f"(v3) : "memory");
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(v4), "f"(s0), "f"(c0), "f"(c1) : "memory");
+            if (NCH == 4) asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(dst + 8), "f"(c2), "f"(c3) : "memory");
+            else atomicAdd(dst + 8, c2);
+        }
+        __syncwarp();
+    };
+
+    const uint32_t gt = ~((2u << lane) - 1u);        // lanes above me
+    uint32_t head = 0, count = 0;
+    const int cmax = (int)((todo - 1) >> 5);
+    // software pipeline (descending chunks): ids two chunks ahead, records one chunk ahead
+    auto pos_of = [&](int c) { return (uint32_t)(c * 32 + lane); };
+    uint32_t id_next = pos_of(cmax) < todo ? point_list[rb + pos_of(cmax)] : 0u;
+    uint32_t id_next2 = (cmax >= 1) ? point_list[rb + pos_of(cmax - 1)] : 0u;
+    ChunkRegs nxt;
+    load_chunk(nxt, pos_of(cmax) < todo, geom, id_next);
+    for (int c = cmax; c >= 0; --c) {
+        const ChunkRegs cur = nxt;
+        const uint32_t cur_id = id_next;
+        const uint32_t p = pos_of(c);
+        const bool valid = p < todo;
+        id_next = id_next2;
+        id_next2 = (c >= 2) ? point_list[rb + pos_of(c - 2)] : 0u;
+        load_chunk(nxt, c >= 1, geom, id_next);
+        const bool keep = valid && region_hit(cur, x0f, y0f);
+        const uint32_t b = __ballot_sync(VTGS_FULL_MASK, keep);
+        if (b == 0) continue;
+        if (keep) {
+            const int sl = (head + count + __popc(b & gt)) & 63;      // higher list positions first
+            Q.q0[sl] = cur.q0; Q.q1[sl] = cur.q1; Q.q2[sl] = cur.q2; Q.pos[sl] = p + 1u; Q.id[sl] = cur_id;
+        }
+        count += __popc(b);
+        __syncwarp();
+        if (count >= 32) {
+            process_group(head, 32);
+            head = (head + 32) & 63;
+            count -= 32;
+        }
     }
+    if (count > 0) process_group(head, (int)count);
 }
 
 // ---- shared pieces of K7' -------------------------------------------------------------------
@@ -364,6 +374,18 @@ preprocess_backward_kernel(const __grid_constant__ CamConst cam, int64_t N,
     for (int k = 0; k < 4; ++k) dL_drot[4 * i + k] = dq[k];
 }
 
+// dynamic shared memory of blend_backward_kernel: 8 x (ring 3584 + cells 8448 + dpix 512) bytes
+constexpr int BWD_SMEM = 8 * (int)(sizeof(WarpQueue) + 32 * 33 * sizeof(float2) + 32 * sizeof(float4));
+static int ensure_bwd_smem() {
+    static bool done = false;
+    if (!done) {
+        VTGS_CUDA_CHECK(cudaFuncSetAttribute(blend_backward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
+        VTGS_CUDA_CHECK(cudaFuncSetAttribute(blend_backward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
+        done = true;
+    }
+    return VTGS_OK;
+}
+
 int launch_backward(const VtgsCamera* camera, int64_t N,
                     const float* means3D, const float* scales, const float* rotations,
                     const float* opacities, const float* colors, const float* dL_dout_color,
@@ -375,8 +397,9 @@ int launch_backward(const VtgsCamera* camera, int64_t N,
     const GeomRecord* geom = reinterpret_cast<const GeomRecord*>(buf->geom);
     const int band_tiles = (cam.row1 - cam.row0) * cam.gx;
     if (N <= 0) return VTGS_OK;
+    if (int e = ensure_bwd_smem()) return e;
     if (band_tiles > 0) {
-        { VTGS_PROF("blend_backward_kernel", stream); blend_backward_kernel<false><<<band_tiles, 256, 0, stream>>>(cam, buf->tile_ranges, buf->point_list, geom, buf->final_T,
+        { VTGS_PROF("blend_backward_kernel", stream); blend_backward_kernel<false><<<band_tiles, 256, BWD_SMEM, stream>>>(cam, buf->tile_ranges, buf->point_list, geom, buf->final_T,
                                                                       buf->n_contrib, dL_dout_color, buf->grad_geom); }
         VTGS_LAUNCH_CHECK();
     }
@@ -561,9 +584,10 @@ int launch_fused_backward(const VtgsCamera* camera, const VtgsParams* params, co
     const int want_pose = (grads->cam_unnorm_rot != nullptr && grads->cam_trans != nullptr) ? 1 : 0;
     if (want_pose && grads->pose_scratch == nullptr) { set_error("pose gradients need pose_scratch"); return VTGS_E_INVALID; }
     const int blocks = (int)((N + 255) / 256);
+    if (int e = ensure_bwd_smem()) return e;
     if (N > 0) {
         if (band_tiles > 0) {
-            { VTGS_PROF("blend_backward_kernel", stream); blend_backward_kernel<true><<<band_tiles, 256, 0, stream>>>(cam, buf->tile_ranges, buf->point_list, geom, buf->final_T,
+            { VTGS_PROF("blend_backward_kernel", stream); blend_backward_kernel<true><<<band_tiles, 256, BWD_SMEM, stream>>>(cam, buf->tile_ranges, buf->point_list, geom, buf->final_T,
                                                                          buf->n_contrib, dL_dimage4, buf->grad_geom); }
             VTGS_LAUNCH_CHECK();
         }

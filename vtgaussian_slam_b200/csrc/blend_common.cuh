@@ -1,0 +1,103 @@
+// blend_common.cuh -- staging, culling and the lane-transposed test phase shared by the
+// forward (K5') and backward (K6') blend kernels.
+//
+// Geometry of a tile block: 256 threads = 8 warps; warp w owns the 8x4-pixel region
+// (w & 1, w >> 1) of the 16x16 tile and lane l the pixel (l & 7, l >> 3) of that region.
+//
+// View-tied Gaussians are ~1 px wide: a splat listed for a tile touches ~30% of the tile's
+// eight regions and, inside a region it touches, ~25% of the 32 pixels.  Walking a tile
+// list with one pixel per lane and the SAME splat in every lane (the upstream scheme) leaves
+// 3/4 of the lanes idle in the expensive part (exp, blend / gradient terms).  The kernels here
+// instead work on groups of 32 surviving splats of a region in three lane roles:
+//   P1  lane = splat   : evaluate `power` for the 32 pixels (pixel coordinates are warp-uniform
+//                        immediates; per-splat terms factor out) -> a 32x32 bit matrix
+//                        "splat e may contribute to pixel p", transposed across the warp with a
+//                        5-step butterfly so that every pixel lane gets its own splat mask;
+//   P2  lane = pixel   : each lane walks ITS OWN mask in list order (different splats in
+//                        different lanes), so the expensive part runs max-popcount times per
+//                        group instead of once per splat;
+//   P3  lane = splat   : (backward only) gather the per-(splat,pixel) terms P2 left in shared
+//                        memory and reduce them per splat without any cross-lane shuffle.
+// List positions (n_contrib), the alpha / T tests and the blend order per pixel are exactly the
+// reference's, so every output is bit-identical to the one-splat-at-a-time formulation.
+#pragma once
+#include "common.cuh"
+
+namespace vtgs {
+
+// Per-warp ring of surviving splats (64 slots: < 32 pending + <= 32 appended per chunk).
+struct WarpQueue {
+    float4 q0[64];
+    float4 q1[64];
+    float4 q2[64];
+    uint32_t pos[64];      // 1-based position in the tile list (n_contrib semantics)
+    uint32_t id[64];       // Gaussian id (backward)
+};
+
+// Prefetched chunk of 32 list entries: one entry per lane.
+struct ChunkRegs {
+    float4 q0, q1, q2, q3;
+};
+
+__device__ __forceinline__ void load_chunk(ChunkRegs& r, bool valid, const GeomRecord* __restrict__ geom, uint32_t id) {
+    if (valid) {
+        const GeomRecord* rec = geom + id;
+        r.q0 = rec->q0; r.q1 = rec->q1; r.q2 = rec->q2; r.q3 = rec->q3;
+    }
+}
+
+// Bounding box of the alpha >= 1/255 ellipse against this warp's 8x4-pixel region.
+__device__ __forceinline__ bool region_hit(const ChunkRegs& r, float x0f, float y0f) {
+    return (r.q0.x + r.q1.w >= x0f) && (r.q0.x - r.q1.w <= x0f + 7.0f) &&
+           (r.q0.y + r.q3.y >= y0f) && (r.q0.y - r.q3.y <= y0f + 3.0f);
+}
+
+// 32x32 bit-matrix transpose across the warp: on entry lane e holds row e (bit p = column p),
+// on return lane p holds column p (bit e = row e).
+__device__ __forceinline__ uint32_t warp_transpose_bits(uint32_t x, int lane) {
+#define VTGS_TSTEP(s, lo)                                                              \
+    {                                                                                  \
+        const uint32_t y = __shfl_xor_sync(VTGS_FULL_MASK, x, s);                      \
+        x = (lane & s) ? ((x & ~(lo)) | ((y & ~(lo)) >> s)) : ((x & (lo)) | ((y & (lo)) << s)); \
+    }
+    VTGS_TSTEP(16, 0x0000FFFFu)
+    VTGS_TSTEP(8, 0x00FF00FFu)
+    VTGS_TSTEP(4, 0x0F0F0F0Fu)
+    VTGS_TSTEP(2, 0x33333333u)
+    VTGS_TSTEP(1, 0x55555555u)
+#undef VTGS_TSTEP
+    return x;
+}
+
+// P1: lane = splat (q0, q1 of this lane's splat; have == false for the tail of a partial group).
+// emask: pixels of the region this splat may contribute to (power in [pthr, 0], in the spec'd
+// arithmetic -- the same `power` P2 recomputes).  pmask (returned): for this lane AS A PIXEL, the
+// splats of the group that may contribute to it.
+__device__ __forceinline__ uint32_t p1_masks(bool have, const float4 q0, const float4 q1, float x0f, float y0f,
+                                             int lane, uint32_t& emask) {
+    float dx[8], u[8], v[8], dy[4], wq[4];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        dx[c] = fsub(q0.x, x0f + (float)c);
+        u[c] = fmul(q1.x, dx[c]);
+        v[c] = fmul(q1.y, dx[c]);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        dy[r] = fsub(q0.y, y0f + (float)r);
+        wq[r] = fmul(fmul(q1.z, dy[r]), dy[r]);
+    }
+    uint32_t em = 0;
+#pragma unroll
+    for (int p = 0; p < 32; ++p) {
+        const int c = p & 7, r = p >> 3;
+        const float q = ffma(u[c], dx[c], wq[r]);
+        const float pw = ffma(-0.5f, q, -fmul(v[c], dy[r]));
+        if (pw <= 0.0f && pw >= q0.z) em |= 1u << p;
+    }
+    em = have ? em : 0u;
+    emask = em;
+    return warp_transpose_bits(em, lane);
+}
+
+}  // namespace vtgs

@@ -19,7 +19,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 
-#include "common.cuh"
+#include "blend_common.cuh"
 #include "kernels.h"
 
 namespace vtgs {
@@ -300,95 +300,105 @@ tile_sort_kernel(const uint32_t* __restrict__ ranges, int tile0, uint64_t* __res
 }
 
 // =============================== K5': forward blend ========================================
-// Block = one 16x16 tile, 8 warps; warp w owns the 8x4-pixel region (w&1, w>>1).
-// NCH_OUT planes: API mode 3 colours (+ depth plane), fused mode r,g,b,z,sil,z^2.
+// Block = one 16x16 tile, 8 INDEPENDENT warps (no block barrier): warp w owns the 8x4-pixel region
+// (w&1, w>>1), walks the whole tile list in chunks of 32 (software-prefetched gathers of the 64-byte
+// records; the eight warps of a tile share them through L1), box-culls each chunk against its
+// region (lane = list entry), queues the survivors in a warp-private ring and blends them in full
+// groups of 32 with the lane-transposed scheme of blend_common.cuh.
+// Planes: API mode 3 colours (+ depth plane), fused mode r,g,b,z,sil,z^2.
 template <bool FUSED>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 blend_forward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __restrict__ ranges,
                      const uint32_t* __restrict__ point_list, const GeomRecord* __restrict__ geom,
                      float* __restrict__ out_color, float* __restrict__ out_depth,
                      float* __restrict__ final_T, uint32_t* __restrict__ n_contrib) {
-    __shared__ float4 s_q0[256];
-    __shared__ float4 s_q1[256];
-    __shared__ float4 s_q2[256];
-    __shared__ uint32_t s_mask[8][8];      // [region][chunk of 32 staged entries]
+    __shared__ WarpQueue Qs[8];
 
     const int tile = cam.row0 * cam.gx + blockIdx.x;
     const int tile_x = tile % cam.gx, tile_y = tile / cam.gx;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int pix_x = tile_x * 16 + (warp & 1) * 8 + (lane & 7);
-    const int pix_y = tile_y * 16 + (warp >> 1) * 4 + (lane >> 3);
+    WarpQueue& Q = Qs[warp];
+    const int rx0 = tile_x * 16 + (warp & 1) * 8, ry0 = tile_y * 16 + (warp >> 1) * 4;
+    const int pix_x = rx0 + (lane & 7), pix_y = ry0 + (lane >> 3);
     const bool inside = pix_x < cam.W && pix_y < cam.H;
     const float pxf = (float)pix_x, pyf = (float)pix_y;
-    const float tox = (float)(tile_x * 16), toy = (float)(tile_y * 16);
+    const float x0f = (float)rx0, y0f = (float)ry0;
+    const uint32_t lt = (1u << lane) - 1u;
 
     const uint32_t rb = ranges[2 * tile], re = ranges[2 * tile + 1];
+    const uint32_t len = re - rb;
+    const int nchunks = (int)((len + 31) >> 5);
 
     float T = 1.0f;
     float C0 = 0.f, C1 = 0.f, C2 = 0.f, C3 = 0.f, C4 = 0.f, C5 = 0.f;
     uint32_t last = 0;
     bool done = !inside;
 
-    for (uint32_t base = rb; base < re; base += 256) {
-        if (__syncthreads_and(done)) break;
-        const uint32_t idx = base + tid;
-        uint32_t rmask = 0;
-        if (idx < re) {
-            const uint32_t id = point_list[idx];
-            const GeomRecord* rec = geom + id;
-            const float4 q0 = rec->q0, q1 = rec->q1, q2 = rec->q2, q3 = rec->q3;
-            s_q0[tid] = q0; s_q1[tid] = q1; s_q2[tid] = q2;
-            const float x0 = q0.x - q1.w - tox, x1 = q0.x + q1.w - tox;
-            const float y0 = q0.y - q3.y - toy, y1 = q0.y + q3.y - toy;
-            const uint32_t cm = ((x1 >= 0.0f && x0 <= 7.0f) ? 1u : 0u) | ((x1 >= 8.0f && x0 <= 15.0f) ? 2u : 0u);
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
-                if (y1 >= (float)(4 * r) && y0 <= (float)(4 * r + 3)) rmask |= cm << (2 * r);
-        }
-#pragma unroll
-        for (int w = 0; w < 8; ++w) {
-            const uint32_t m = __ballot_sync(VTGS_FULL_MASK, (rmask >> w) & 1u);
-            if (lane == 0) s_mask[w][warp] = m;
-        }
-        __syncthreads();
-        const uint32_t pos0 = base - rb;
-#pragma unroll 1
-        for (int chunk = 0; chunk < 8; ++chunk) {
-            uint32_t m = s_mask[warp][chunk];
-            if (m == 0) continue;
-            if (__all_sync(VTGS_FULL_MASK, done)) break;
-            while (m) {
-                const int bit = __ffs(m) - 1;
-                m &= m - 1;
-                const int j = chunk * 32 + bit;
-                const float4 q0 = s_q0[j];
-                const float4 q1 = s_q1[j];
-                const float dx = fsub(q0.x, pxf), dy = fsub(q0.y, pyf);
-                const float power = power_of(q1.x, q1.y, q1.z, dx, dy);
-                if (!done && power <= 0.0f && power >= q0.z) {
-                    const float alpha = fminf(VTGS_ALPHA_MAX, fmul(q0.w, vexpf(power)));
-                    if (alpha >= VTGS_ALPHA_MIN) {
-                        const float test_T = fmul(T, fsub(1.0f, alpha));
-                        if (test_T < VTGS_T_MIN) {
-                            done = true;
-                        } else {
-                            const float4 q2 = s_q2[j];
-                            C0 = ffma(fmul(q2.x, alpha), T, C0);
-                            C1 = ffma(fmul(q2.y, alpha), T, C1);
-                            C2 = ffma(fmul(q2.z, alpha), T, C2);
-                            C3 = ffma(fmul(q2.w, alpha), T, C3);
-                            if (FUSED) {
-                                C4 = ffma(alpha, T, C4);                               // 1.0 * alpha * T
-                                C5 = ffma(fmul(fmul(q2.w, q2.w), alpha), T, C5);
-                            }
-                            T = test_T;
-                            last = pos0 + (uint32_t)j + 1u;
-                        }
-                    }
-                }
+    // blend one group of `n` (<= 32) queued splats starting at ring slot `head`
+    auto process_group = [&](uint32_t head, int n) {
+        const bool have = lane < n;
+        const int slot = (head + (have ? lane : 0)) & 63;
+        uint32_t emask;
+        uint32_t m = p1_masks(have, Q.q0[slot], Q.q1[slot], x0f, y0f, lane, emask);      // P1: lane = splat
+        if (done) m = 0;
+        while (m) {                                                                       // P2: lane = pixel
+            const int e = __ffs(m) - 1;
+            m &= m - 1;
+            const int sl = (head + e) & 63;
+            const float4 q0 = Q.q0[sl];
+            const float4 q1 = Q.q1[sl];
+            const float dx = fsub(q0.x, pxf), dy = fsub(q0.y, pyf);
+            const float power = power_of(q1.x, q1.y, q1.z, dx, dy);     // in [pthr, 0] by P1 (same arithmetic)
+            const float alpha = fminf(VTGS_ALPHA_MAX, fmul(q0.w, vexpf(power)));
+            if (alpha < VTGS_ALPHA_MIN) continue;
+            const float test_T = fmul(T, fsub(1.0f, alpha));
+            if (test_T < VTGS_T_MIN) { done = true; break; }
+            const float4 q2 = Q.q2[sl];
+            C0 = ffma(fmul(q2.x, alpha), T, C0);
+            C1 = ffma(fmul(q2.y, alpha), T, C1);
+            C2 = ffma(fmul(q2.z, alpha), T, C2);
+            C3 = ffma(fmul(q2.w, alpha), T, C3);
+            if (FUSED) {
+                C4 = ffma(alpha, T, C4);                               // 1.0 * alpha * T
+                C5 = ffma(fmul(fmul(q2.w, q2.w), alpha), T, C5);
             }
+            T = test_T;
+            last = Q.pos[sl];
+        }
+    };
+
+    uint32_t head = 0, count = 0;
+    // software pipeline: ids two chunks ahead, records one chunk ahead
+    uint32_t id_next = (uint32_t)lane < len ? point_list[rb + lane] : 0u;
+    uint32_t id_next2 = (uint32_t)(32 + lane) < len ? point_list[rb + 32 + lane] : 0u;
+    ChunkRegs nxt;
+    load_chunk(nxt, (uint32_t)lane < len, geom, id_next);
+    bool all_done = __all_sync(VTGS_FULL_MASK, done);
+    for (int c = 0; c < nchunks && !all_done; ++c) {
+        const ChunkRegs cur = nxt;
+        const uint32_t p = (uint32_t)(c * 32 + lane);
+        const bool valid = p < len;
+        id_next = id_next2;
+        id_next2 = (p + 64u) < len ? point_list[rb + p + 64u] : 0u;
+        load_chunk(nxt, (p + 32u) < len, geom, id_next);
+        const bool keep = valid && region_hit(cur, x0f, y0f);
+        const uint32_t b = __ballot_sync(VTGS_FULL_MASK, keep);
+        if (b == 0) continue;
+        if (keep) {
+            const int sl = (head + count + __popc(b & lt)) & 63;
+            Q.q0[sl] = cur.q0; Q.q1[sl] = cur.q1; Q.q2[sl] = cur.q2; Q.pos[sl] = p + 1u;
+        }
+        count += __popc(b);
+        __syncwarp();
+        if (count >= 32) {
+            process_group(head, 32);
+            head = (head + 32) & 63;
+            count -= 32;
+            all_done = __all_sync(VTGS_FULL_MASK, done);
         }
     }
+    if (count > 0 && !all_done) process_group(head, (int)count);
+
     if (inside) {
         const size_t P = (size_t)cam.W * cam.H;
         const size_t pid = (size_t)pix_y * cam.W + pix_x;
