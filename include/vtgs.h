@@ -293,6 +293,16 @@ VTGS_API int vtgs_adam(float* param, const float* grad, float* exp_avg, float* e
               const int32_t* step_dev, void* stream);
 
 /*
+ * Tracking pose update in one launch: the reference's `optimizer.step()` on the frame's pose slices
+ * (src/vtgaussian_slam.py:1890, Adam betas (0.9, 0.999)) plus its best-candidate bookkeeping (:1961-1970).
+ *   msg[16]        = {dL/dq[4], dL/dt[3], pad, loss_terms[8]}  (the all-reduced message of an iteration)
+ *   adam_state[14] = {m_q[4], v_q[4], m_t[3], v_t[3]};  *step_dev is incremented
+ *   best[8]        = {best_loss, best_q[4], best_t[3]}: pose BEFORE this step is kept if msg loss < best_loss
+ */
+VTGS_API int vtgs_tracking_update(float* cam_unnorm_rot, float* cam_trans, const float* msg, float* adam_state,
+                                  int32_t* step_dev, float* best, float lr_rot, float lr_trans, float eps, void* stream);
+
+/*
  * Optional per-kernel timing for bench.py's roofline: while enabled, every kernel launch of
  * the library is bracketed by CUDA events on its launching stream.  vtgs_profile_summary
  * synchronises those events and writes one line per kernel: "<name> <launches> <total_ms>".

@@ -204,6 +204,12 @@ int vtgs_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq
     return launch_adam(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step, step_dev, (cudaStream_t)stream);
 }
 
+int vtgs_tracking_update(float* cam_unnorm_rot, float* cam_trans, const float* msg, float* adam_state, int32_t* step_dev,
+                         float* best, float lr_rot, float lr_trans, float eps, void* stream) {
+    VTGS_REQUIRE(cam_unnorm_rot && cam_trans && msg && adam_state && step_dev && best, "pointer is NULL");
+    return launch_tracking_update(cam_unnorm_rot, cam_trans, msg, adam_state, step_dev, best, lr_rot, lr_trans, eps, (cudaStream_t)stream);
+}
+
 int vtgs_profile_enable(int32_t on) {
     std::lock_guard<std::mutex> lk(g_prof_mu);
     if (on) {

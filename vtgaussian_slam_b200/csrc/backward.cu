@@ -90,6 +90,7 @@ blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __re
         WarpQueue Q;
         float2 cell[32][33];        // [splat of the group][pixel], padded row: (w, g0)
         float4 dpix[32];            // dL/dpixel of the region's pixels (r,g,b,z)
+        float2 pxy[32];             // pixel centres of the region
     };
     WarpArea* areas = reinterpret_cast<WarpArea*>(smem_raw);
 
@@ -113,6 +114,7 @@ blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __re
 #pragma unroll
     for (int ch = 0; ch < NCH; ++ch) dpix[ch] = inside ? dL_dpix[ch * P + pid] : 0.0f;
     A.dpix[lane] = make_float4(dpix[0], dpix[1], dpix[2], dpix[3]);
+    A.pxy[lane] = make_float2(pxf, pyf);
     const float bg_dot = cam.bg[0] * dpix[0] + cam.bg[1] * dpix[1] + cam.bg[2] * dpix[2];
     const float half_w = 0.5f * cam.W, half_h = 0.5f * cam.H;
 
@@ -135,15 +137,15 @@ blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __re
         const int slot = (head + (have ? lane : 0)) & 63;
         const float4 e0 = Q.q0[slot], e1 = Q.q1[slot];
         uint32_t emask;
-        uint32_t m = p1_masks(have, e0, e1, x0f, y0f, lane, emask);                  // P1: lane = splat
+        uint32_t m = p1_masks(have, e0, e1, Q.pthr[slot], x0f, y0f, lane, emask);    // P1: lane = splat
         // ---- P2: lane = pixel; ring order is back-to-front, so ascending bits = descending list position
         while (m) {
             const int e = __ffs(m) - 1;
             m &= m - 1;
             const int sl = (head + e) & 63;
             float2 out = make_float2(0.0f, 0.0f);
-            if (Q.pos[sl] <= last) {
-                const float4 q0 = Q.q0[sl];
+            const float4 q0 = Q.q0[sl];
+            if (__float_as_uint(q0.z) <= last) {
                 const float4 q1 = Q.q1[sl];
                 const float dx = fsub(q0.x, pxf), dy = fsub(q0.y, pyf);
                 const float power = power_of(q1.x, q1.y, q1.z, dx, dy);
@@ -179,7 +181,8 @@ blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __re
             pm &= pm - 1;
             const float2 cw = A.cell[lane][p];
             const float4 dp = A.dpix[p];
-            const float dx = e0.x - (x0f + (float)(p & 7)), dy = e0.y - (y0f + (float)(p >> 3));
+            const float2 pc = A.pxy[p];
+            const float dx = e0.x - pc.x, dy = e0.y - pc.y;
             c0 = fmaf(cw.x, dp.x, c0); c1 = fmaf(cw.x, dp.y, c1); c2 = fmaf(cw.x, dp.z, c2);
             if (NCH == 4) c3 = fmaf(cw.x, dp.w, c3);
             const float g = cw.y, gx_ = g * dx, gy_ = g * dy;
@@ -223,7 +226,8 @@ blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __re
         if (b == 0) continue;
         if (keep) {
             const int sl = (head + count + __popc(b & gt)) & 63;      // higher list positions first
-            Q.q0[sl] = cur.q0; Q.q1[sl] = cur.q1; Q.q2[sl] = cur.q2; Q.pos[sl] = p + 1u; Q.id[sl] = cur_id;
+            queue_put(Q, sl, cur.q0, cur.q1, cur.q2, p + 1u);
+            Q.id[sl] = cur_id;
         }
         count += __popc(b);
         __syncwarp();
@@ -375,7 +379,7 @@ preprocess_backward_kernel(const __grid_constant__ CamConst cam, int64_t N,
 }
 
 // dynamic shared memory of blend_backward_kernel: 8 x (ring 3584 + cells 8448 + dpix 512) bytes
-constexpr int BWD_SMEM = 8 * (int)(sizeof(WarpQueue) + 32 * 33 * sizeof(float2) + 32 * sizeof(float4));
+constexpr int BWD_SMEM = 8 * (int)(sizeof(WarpQueue) + 32 * 33 * sizeof(float2) + 32 * sizeof(float4) + 32 * sizeof(float2));
 static int ensure_bwd_smem() {
     static bool done = false;
     if (!done) {
@@ -438,7 +442,7 @@ int launch_pose_matrix(const VtgsPose* pose, VtgsCounters* counters, cudaStream_
 constexpr int POSE_TERMS = 12;       // sum g (3) and sum g p^T (9)
 
 // Fused K7': per-Gaussian parameter gradients + block partial sums of the pose terms.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 fused_preprocess_backward_kernel(const __grid_constant__ CamConst cam, int64_t N, VtgsParams prm,
                                  const float* __restrict__ pose_Rt, float dr0, float dr1, float dr2,
                                  const GeomRecord* __restrict__ geom, float* __restrict__ grad_geom,
@@ -526,26 +530,29 @@ fused_preprocess_backward_kernel(const __grid_constant__ CamConst cam, int64_t N
 
 // Deterministic final reduction of the block partials (fixed order, fp64) and the chain
 // dL/dR, dL/dt -> cam_unnorm_rot, cam_trans through build_rotation and the two normalisations.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 pose_finalize_kernel(const float* __restrict__ partials, int nblocks, const VtgsCounters* __restrict__ c,
                      float* __restrict__ d_rot, float* __restrict__ d_trans, int accumulate) {
-    __shared__ double s_sum[POSE_TERMS][32];
+    constexpr int SLICES = 85;                    // 12 terms x 85 slices = 1020 threads, coalesced reads
+    __shared__ double s_sum[POSE_TERMS][SLICES];
+    __shared__ double s_tot[POSE_TERMS];
     const int tid = threadIdx.x;
-    // 12 terms x 16 strided lanes, each sums its slice in index order; then a fixed tree
-    if (tid < POSE_TERMS * 16) {
-        const int term = tid / 16, l = tid % 16;
+    if (tid < POSE_TERMS * SLICES) {
+        const int term = tid % POSE_TERMS, sl = tid / POSE_TERMS;
         double acc = 0.0;
-        for (int b = l; b < nblocks; b += 16) acc += (double)partials[(size_t)b * POSE_TERMS + term];
-        s_sum[term][l] = acc;
+        for (int b = sl; b < nblocks; b += SLICES) acc += (double)partials[(size_t)b * POSE_TERMS + term];
+        s_sum[term][sl] = acc;
+    }
+    __syncthreads();
+    if (tid < POSE_TERMS) {                       // fixed order: deterministic
+        double a = 0.0;
+        for (int l = 0; l < SLICES; ++l) a += s_sum[tid][l];
+        s_tot[tid] = a;
     }
     __syncthreads();
     if (tid == 0) {
         double tot[POSE_TERMS];
-        for (int k = 0; k < POSE_TERMS; ++k) {
-            double a = 0.0;
-            for (int l = 0; l < 16; ++l) a += s_sum[k][l];
-            tot[k] = a;
-        }
+        for (int k = 0; k < POSE_TERMS; ++k) tot[k] = s_tot[k];
         // D[r][k] = dL/dR[r][k] = sum g_r p_k
         const double D[3][3] = {{tot[3], tot[4], tot[5]}, {tot[6], tot[7], tot[8]}, {tot[9], tot[10], tot[11]}};
         const double n1 = c->pose_qnorm[0], n2 = c->pose_qnorm[1];
@@ -597,7 +604,7 @@ int launch_fused_backward(const VtgsCamera* camera, const VtgsParams* params, co
         VTGS_LAUNCH_CHECK();
     }
     if (want_pose) {
-        { VTGS_PROF("pose_finalize_kernel", stream); pose_finalize_kernel<<<1, 256, 0, stream>>>(grads->pose_scratch, N > 0 ? blocks : 0, buf->counters, grads->cam_unnorm_rot,
+        { VTGS_PROF("pose_finalize_kernel", stream); pose_finalize_kernel<<<1, 1024, 0, stream>>>(grads->pose_scratch, N > 0 ? blocks : 0, buf->counters, grads->cam_unnorm_rot,
                                                     grads->cam_trans, accumulate); }
         VTGS_LAUNCH_CHECK();
     }

@@ -27,12 +27,19 @@ namespace vtgs {
 
 // Per-warp ring of surviving splats (64 slots: < 32 pending + <= 32 appended per chunk).
 struct WarpQueue {
-    float4 q0[64];
-    float4 q1[64];
-    float4 q2[64];
-    uint32_t pos[64];      // 1-based position in the tile list (n_contrib semantics)
+    float4 q0[64];         // {px, py, bits(1-based position in the tile list), opacity}
+    float4 q1[64];         // {A, B, C, -}
+    float4 q2[64];         // colours
+    float pthr[64];        // conservative lower bound of power (read by P1 only)
     uint32_t id[64];       // Gaussian id (backward)
 };
+
+__device__ __forceinline__ void queue_put(WarpQueue& Q, int sl, const float4 q0, const float4 q1, const float4 q2, uint32_t pos1) {
+    Q.q0[sl] = make_float4(q0.x, q0.y, __uint_as_float(pos1), q0.w);
+    Q.q1[sl] = q1;
+    Q.q2[sl] = q2;
+    Q.pthr[sl] = q0.z;
+}
 
 // Prefetched chunk of 32 list entries: one entry per lane.
 struct ChunkRegs {
@@ -73,7 +80,7 @@ __device__ __forceinline__ uint32_t warp_transpose_bits(uint32_t x, int lane) {
 // emask: pixels of the region this splat may contribute to (power in [pthr, 0], in the spec'd
 // arithmetic -- the same `power` P2 recomputes).  pmask (returned): for this lane AS A PIXEL, the
 // splats of the group that may contribute to it.
-__device__ __forceinline__ uint32_t p1_masks(bool have, const float4 q0, const float4 q1, float x0f, float y0f,
+__device__ __forceinline__ uint32_t p1_masks(bool have, const float4 q0, const float4 q1, float pthr, float x0f, float y0f,
                                              int lane, uint32_t& emask) {
     float dx[8], u[8], v[8], dy[4], wq[4];
 #pragma unroll
@@ -93,7 +100,7 @@ __device__ __forceinline__ uint32_t p1_masks(bool have, const float4 q0, const f
         const int c = p & 7, r = p >> 3;
         const float q = ffma(u[c], dx[c], wq[r]);
         const float pw = ffma(-0.5f, q, -fmul(v[c], dy[r]));
-        if (pw <= 0.0f && pw >= q0.z) em |= 1u << p;
+        if (pw <= 0.0f && pw >= pthr) em |= 1u << p;
     }
     em = have ? em : 0u;
     emask = em;

@@ -339,7 +339,7 @@ blend_forward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __res
         const bool have = lane < n;
         const int slot = (head + (have ? lane : 0)) & 63;
         uint32_t emask;
-        uint32_t m = p1_masks(have, Q.q0[slot], Q.q1[slot], x0f, y0f, lane, emask);      // P1: lane = splat
+        uint32_t m = p1_masks(have, Q.q0[slot], Q.q1[slot], Q.pthr[slot], x0f, y0f, lane, emask);      // P1: lane = splat
         if (done) m = 0;
         while (m) {                                                                       // P2: lane = pixel
             const int e = __ffs(m) - 1;
@@ -363,7 +363,7 @@ blend_forward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __res
                 C5 = ffma(fmul(fmul(q2.w, q2.w), alpha), T, C5);
             }
             T = test_T;
-            last = Q.pos[sl];
+            last = __float_as_uint(q0.z);
         }
     };
 
@@ -386,7 +386,7 @@ blend_forward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __res
         if (b == 0) continue;
         if (keep) {
             const int sl = (head + count + __popc(b & lt)) & 63;
-            Q.q0[sl] = cur.q0; Q.q1[sl] = cur.q1; Q.q2[sl] = cur.q2; Q.pos[sl] = p + 1u;
+            queue_put(Q, sl, cur.q0, cur.q1, cur.q2, p + 1u);
         }
         count += __popc(b);
         __syncwarp();

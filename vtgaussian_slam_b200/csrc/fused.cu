@@ -53,22 +53,25 @@ tracking_loss_kernel(const __grid_constant__ CamConst cam, VtgsLossConfig cfg, c
     }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 loss_finalize_kernel(const float* __restrict__ partials, int nblocks, VtgsLossConfig cfg, float* __restrict__ loss_terms) {
-    __shared__ double s_sum[LOSS_TERMS][64];
+    __shared__ double s_sum[LOSS_TERMS][256];
+    __shared__ double s_tot[LOSS_TERMS];
     const int tid = threadIdx.x;
-    const int term = tid / 64, l = tid % 64;
+    const int term = tid & (LOSS_TERMS - 1), sl = tid >> 2;          // coalesced: consecutive threads, consecutive floats
     double acc = 0.0;
-    for (int b = l; b < nblocks; b += 64) acc += (double)partials[(size_t)b * LOSS_TERMS + term];
-    s_sum[term][l] = acc;
+    for (int b = sl; b < nblocks; b += 256) acc += (double)partials[(size_t)b * LOSS_TERMS + term];
+    s_sum[term][sl] = acc;
+    __syncthreads();
+    if (tid < LOSS_TERMS) {                                          // fixed order: deterministic
+        double a = 0.0;
+        for (int i = 0; i < 256; ++i) a += s_sum[tid][i];
+        s_tot[tid] = a;
+    }
     __syncthreads();
     if (tid == 0) {
         double tot[LOSS_TERMS];
-        for (int k = 0; k < LOSS_TERMS; ++k) {
-            double a = 0.0;
-            for (int i = 0; i < 64; ++i) a += s_sum[k][i];
-            tot[k] = a;
-        }
+        for (int k = 0; k < LOSS_TERMS; ++k) tot[k] = s_tot[k];
         const double wim = (double)cfg.w_im * tot[1], wd = (double)cfg.w_depth * tot[0];
         loss_terms[0] = (float)(wim + wd);
         loss_terms[1] = (float)wim;
@@ -100,7 +103,7 @@ int launch_loss(const VtgsCamera* camera, const VtgsLossConfig* cfg, const float
         { VTGS_PROF("tracking_loss_kernel", stream); tracking_loss_kernel<<<nblocks, 256, 0, stream>>>(cam, *cfg, image6, gt_rgb, gt_depth, dL_dimage4, scratch); }
         VTGS_LAUNCH_CHECK();
     }
-    { VTGS_PROF("loss_finalize_kernel", stream); loss_finalize_kernel<<<1, 256, 0, stream>>>(scratch, nblocks, *cfg, loss_terms); }
+    { VTGS_PROF("loss_finalize_kernel", stream); loss_finalize_kernel<<<1, 1024, 0, stream>>>(scratch, nblocks, *cfg, loss_terms); }
     VTGS_LAUNCH_CHECK();
     return VTGS_OK;
 }
@@ -126,6 +129,46 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
     m[i] = mi; v[i] = vi;
     const float denom = sqrtf(vi) / s_c[1] + eps;
     p[i] = p[i] - s_c[0] * (mi / denom);
+}
+
+// ---- tracking pose update: best-candidate bookkeeping + Adam on the 7 pose numbers, one launch ----
+// Reference src/vtgaussian_slam.py:1890 (optimizer.step) and :1961-1970 (keep the candidate pose with
+// the smallest loss; the loss of an iteration belongs to the pose BEFORE that iteration's step).
+__global__ void tracking_update_kernel(float* __restrict__ cam_q, float* __restrict__ cam_t, const float* __restrict__ msg,
+                                       float* __restrict__ adam, int32_t* __restrict__ step_dev, float* __restrict__ best,
+                                       float lr_rot, float lr_trans, float b1, float b2, float eps) {
+    const int k = threadIdx.x;           // 0..3 quaternion, 4..6 translation
+    __shared__ int s_step;
+    __shared__ bool s_better;
+    if (k == 0) {
+        s_step = *step_dev + 1;
+        *step_dev = s_step;
+        const float loss = msg[8];
+        s_better = loss < best[0];
+        if (s_better) best[0] = loss;
+    }
+    __syncthreads();
+    if (k >= 7) return;
+    float* p = k < 4 ? cam_q + k : cam_t + (k - 4);
+    if (s_better) best[1 + k] = *p;
+    const float g = msg[k];
+    float* m = adam + (k < 4 ? k : 8 + (k - 4));
+    float* v = adam + (k < 4 ? 4 + k : 11 + (k - 4));
+    const double bc1 = 1.0 - pow((double)b1, (double)s_step);
+    const double bc2 = 1.0 - pow((double)b2, (double)s_step);
+    const float step_size = (float)((double)(k < 4 ? lr_rot : lr_trans) / bc1);
+    const float mi = *m + (1.0f - b1) * (g - *m);
+    const float vi = b2 * *v + (1.0f - b2) * g * g;
+    *m = mi; *v = vi;
+    const float denom = sqrtf(vi) / (float)sqrt(bc2) + eps;
+    *p = *p - step_size * (mi / denom);
+}
+
+int launch_tracking_update(float* cam_q, float* cam_t, const float* msg, float* adam, int32_t* step_dev, float* best,
+                           float lr_rot, float lr_trans, float eps, cudaStream_t stream) {
+    { VTGS_PROF("tracking_update_kernel", stream); tracking_update_kernel<<<1, 32, 0, stream>>>(cam_q, cam_t, msg, adam, step_dev, best, lr_rot, lr_trans, 0.9f, 0.999f, eps); }
+    VTGS_LAUNCH_CHECK();
+    return VTGS_OK;
 }
 
 int launch_adam(float* param, const float* grad, float* m, float* v, int64_t n, float lr, float b1,

@@ -48,6 +48,8 @@ int launch_fused_backward(const VtgsCamera* cam, const VtgsParams* params, const
 int launch_loss(const VtgsCamera* cam, const VtgsLossConfig* cfg, const float* image6,
                 const float* gt_rgb, const float* gt_depth, float* dL_dimage4, float* loss_terms,
                 float* scratch, cudaStream_t stream);
+int launch_tracking_update(float* cam_q, float* cam_t, const float* msg, float* adam, int32_t* step_dev, float* best,
+                           float lr_rot, float lr_trans, float eps, cudaStream_t stream);
 int launch_adam(float* param, const float* grad, float* m, float* v, int64_t n, float lr, float b1,
                 float b2, float eps, int step, const int32_t* step_dev, cudaStream_t stream);
 

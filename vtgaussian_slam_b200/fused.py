@@ -167,11 +167,11 @@ class TrackingSolver:
         self.msg = torch.zeros(16, **f32)
         self.d_q, self.d_t = self.msg[0:4], self.msg[4:7]
         self.r.loss_terms = self.msg[8:16]          # the loss kernel writes straight into the message
-        self.m_q, self.v_q = torch.zeros(4, **f32), torch.zeros(4, **f32)
-        self.m_t, self.v_t = torch.zeros(3, **f32), torch.zeros(3, **f32)
+        self.adam = torch.zeros(14, **f32)                 # m_q[4] v_q[4] m_t[3] v_t[3]
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
-        self.best_loss = torch.full((1,), float("inf"), **f32)
-        self.best_q, self.best_t = self.cam_q.clone(), self.cam_t.clone()
+        self.best = torch.zeros(8, **f32)                  # best_loss, best_q[4], best_t[3]
+        self.best[0] = float("inf")
+        self.best_loss, self.best_q, self.best_t = self.best[0:1], self.best[1:5], self.best[5:8]
         self.gt_rgb = torch.zeros((3, self.r.H, self.r.W), **f32)
         self.gt_depth = torch.zeros((1, self.r.H, self.r.W), **f32)
         self.pg = process_group
@@ -185,10 +185,10 @@ class TrackingSolver:
         self.gt_depth.copy_(gt_depth.reshape(self.gt_depth.shape), non_blocking=True)
         self.cam_q.copy_(torch.as_tensor(cam_q).reshape(4), non_blocking=True)
         self.cam_t.copy_(torch.as_tensor(cam_t).reshape(3), non_blocking=True)
-        for t in (self.m_q, self.v_q, self.m_t, self.v_t):
-            t.zero_()
+        self.adam.zero_()
         self.step_dev.zero_()
-        self.best_loss.fill_(float("inf"))
+        self.best.zero_()
+        self.best[0] = float("inf")
 
     def _iteration(self):
         r = self.r
@@ -198,15 +198,11 @@ class TrackingSolver:
         if self.pg is not None:
             # tile-band sharding: every rank holds its band's partial sums; one 16-float all-reduce
             torch.distributed.all_reduce(self.msg, group=self.pg)
-        loss = self.msg[8:9]
-        # keep the best candidate pose (reference :1961-1970), evaluated BEFORE the step like the reference
-        better = loss < self.best_loss
-        self.best_q.copy_(torch.where(better, self.cam_q, self.best_q))
-        self.best_t.copy_(torch.where(better, self.cam_t, self.best_t))
-        self.best_loss.copy_(torch.where(better, loss, self.best_loss))
-        self.step_dev.add_(1)
-        adam_step(self.cam_q, self.d_q, self.m_q, self.v_q, self.lr_rot, step_dev=self.step_dev)
-        adam_step(self.cam_t, self.d_t, self.m_t, self.v_t, self.lr_trans, step_dev=self.step_dev)
+        # best-candidate bookkeeping (reference :1961-1970) + Adam on the 7 pose numbers, one launch
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().vtgs_tracking_update(_ptr(self.cam_q), _ptr(self.cam_t), _ptr(self.msg), _ptr(self.adam),
+                                                       _ptr(self.step_dev), _ptr(self.best), float(self.lr_rot),
+                                                       float(self.lr_trans), 1e-8, _stream_ptr(self.device)))
 
     def step(self):
         if not self.use_graph:
@@ -216,19 +212,17 @@ class TrackingSolver:
             # warm-up on a side stream, then capture
             s = torch.cuda.Stream(self.device)
             s.wait_stream(torch.cuda.current_stream(self.device))
-            snap = [t.clone() for t in (self.cam_q, self.cam_t, self.m_q, self.v_q, self.m_t, self.v_t, self.step_dev,
-                                        self.best_loss, self.best_q, self.best_t)]
+            state = (self.cam_q, self.cam_t, self.adam, self.step_dev, self.best)
+            snap = [t.clone() for t in state]
             with torch.cuda.stream(s):
                 self._iteration()
             torch.cuda.current_stream(self.device).wait_stream(s)
-            for t, v in zip((self.cam_q, self.cam_t, self.m_q, self.v_q, self.m_t, self.v_t, self.step_dev,
-                             self.best_loss, self.best_q, self.best_t), snap):
+            for t, v in zip(state, snap):
                 t.copy_(v)
             self._graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self._graph):
                 self._iteration()
-            for t, v in zip((self.cam_q, self.cam_t, self.m_q, self.v_q, self.m_t, self.v_t, self.step_dev,
-                             self.best_loss, self.best_q, self.best_t), snap):
+            for t, v in zip(state, snap):
                 t.copy_(v)
         self._graph.replay()
 
