@@ -138,38 +138,40 @@ blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __re
         const float4 e0 = Q.q0[slot], e1 = Q.q1[slot];
         uint32_t emask;
         uint32_t m = p1_masks(have, e0, e1, Q.pthr[slot], x0f, y0f, lane, emask);    // P1: lane = splat
-        // ---- P2: lane = pixel; ring order is back-to-front, so ascending bits = descending list position
-        while (m) {
-            const int e = __ffs(m) - 1;
-            m &= m - 1;
-            const int sl = (head + e) & 63;
-            float2 out = make_float2(0.0f, 0.0f);
-            const float4 q0 = Q.q0[sl];
-            if (__float_as_uint(q0.z) <= last) {
-                const float4 q1 = Q.q1[sl];
-                const float dx = fsub(q0.x, pxf), dy = fsub(q0.y, pyf);
-                const float power = power_of(q1.x, q1.y, q1.z, dx, dy);
-                const float G = vexpf(power);
-                const float alpha = fminf(VTGS_ALPHA_MAX, fmul(q0.w, G));
-                if (alpha >= VTGS_ALPHA_MIN) {
-                    const float4 q2 = Q.q2[sl];
-                    const float col[4] = {q2.x, q2.y, q2.z, q2.w};
-                    const float inv = __fdividef(1.0f, 1.0f - alpha);
-                    T = T * inv;
-                    float dL_dalpha = 0.0f;
+        // ---- P2: lane = pixel; ring order is back-to-front, so ascending bits = descending list position.
+        // Two splats per trip: loads / power / exp are independent, the T / accum recursion is ordered.
+        auto back_one = [&](const float4 q0, const float G, const int sl) -> float2 {
+            const float alpha = fminf(VTGS_ALPHA_MAX, fmul(q0.w, G));
+            if (__float_as_uint(q0.z) > last || alpha < VTGS_ALPHA_MIN) return make_float2(0.0f, 0.0f);
+            const float4 q2 = Q.q2[sl];
+            const float col[4] = {q2.x, q2.y, q2.z, q2.w};
+            const float inv = __fdividef(1.0f, 1.0f - alpha);
+            T = T * inv;
+            float dL_dalpha = 0.0f;
 #pragma unroll
-                    for (int ch = 0; ch < NCH; ++ch) {
-                        accum[ch] = last_alpha * lastc[ch] + (1.0f - last_alpha) * accum[ch];
-                        lastc[ch] = col[ch];
-                        dL_dalpha += (col[ch] - accum[ch]) * dpix[ch];
-                    }
-                    dL_dalpha *= T;
-                    last_alpha = alpha;
-                    dL_dalpha -= T_final * inv * bg_dot;
-                    out = make_float2(alpha * T, G * dL_dalpha);
-                }
+            for (int ch = 0; ch < NCH; ++ch) {
+                accum[ch] = last_alpha * lastc[ch] + (1.0f - last_alpha) * accum[ch];
+                lastc[ch] = col[ch];
+                dL_dalpha += (col[ch] - accum[ch]) * dpix[ch];
             }
-            A.cell[e][lane] = out;
+            dL_dalpha *= T;
+            last_alpha = alpha;
+            dL_dalpha -= T_final * inv * bg_dot;
+            return make_float2(alpha * T, G * dL_dalpha);
+        };
+        while (m) {
+            const int ea = __ffs(m) - 1;
+            m &= m - 1;
+            const bool two = m != 0;
+            const int eb = two ? __ffs(m) - 1 : ea;
+            m &= m - 1;
+            const int sa = (head + ea) & 63, sb = (head + eb) & 63;
+            const float4 a0 = Q.q0[sa], a1 = Q.q1[sa];
+            const float4 b0 = Q.q0[sb], b1 = Q.q1[sb];
+            const float Ga = vexpf(power_of(a1.x, a1.y, a1.z, fsub(a0.x, pxf), fsub(a0.y, pyf)));
+            const float Gb = vexpf(power_of(b1.x, b1.y, b1.z, fsub(b0.x, pxf), fsub(b0.y, pyf)));
+            A.cell[ea][lane] = back_one(a0, Ga, sa);
+            if (two) A.cell[eb][lane] = back_one(b0, Gb, sb);
         }
         __syncwarp();
         // ---- P3: lane = splat: reduce my row of cells

@@ -341,18 +341,12 @@ blend_forward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __res
         uint32_t emask;
         uint32_t m = p1_masks(have, Q.q0[slot], Q.q1[slot], Q.pthr[slot], x0f, y0f, lane, emask);      // P1: lane = splat
         if (done) m = 0;
-        while (m) {                                                                       // P2: lane = pixel
-            const int e = __ffs(m) - 1;
-            m &= m - 1;
-            const int sl = (head + e) & 63;
-            const float4 q0 = Q.q0[sl];
-            const float4 q1 = Q.q1[sl];
-            const float dx = fsub(q0.x, pxf), dy = fsub(q0.y, pyf);
-            const float power = power_of(q1.x, q1.y, q1.z, dx, dy);     // in [pthr, 0] by P1 (same arithmetic)
-            const float alpha = fminf(VTGS_ALPHA_MAX, fmul(q0.w, vexpf(power)));
-            if (alpha < VTGS_ALPHA_MIN) continue;
+        // P2: lane = pixel.  Two splats per trip: their loads / power / exp are independent, only the
+        // T and colour updates are ordered.
+        auto blend_one = [&](const float4 q0, const float alpha, const int sl) -> bool {
+            if (alpha < VTGS_ALPHA_MIN) return true;
             const float test_T = fmul(T, fsub(1.0f, alpha));
-            if (test_T < VTGS_T_MIN) { done = true; break; }
+            if (test_T < VTGS_T_MIN) { done = true; return false; }
             const float4 q2 = Q.q2[sl];
             C0 = ffma(fmul(q2.x, alpha), T, C0);
             C1 = ffma(fmul(q2.y, alpha), T, C1);
@@ -364,6 +358,24 @@ blend_forward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __res
             }
             T = test_T;
             last = __float_as_uint(q0.z);
+            return true;
+        };
+        while (m) {
+            const int ea = __ffs(m) - 1;
+            m &= m - 1;
+            const bool two = m != 0;
+            const int eb = two ? __ffs(m) - 1 : ea;
+            m &= m - 1;                                   // no-op when m == 0
+            const int sa = (head + ea) & 63, sb = (head + eb) & 63;
+            const float4 a0 = Q.q0[sa], a1 = Q.q1[sa];
+            const float4 b0 = Q.q0[sb], b1 = Q.q1[sb];
+            // power is in [pthr, 0] by P1 (same arithmetic)
+            const float pa = power_of(a1.x, a1.y, a1.z, fsub(a0.x, pxf), fsub(a0.y, pyf));
+            const float pb = power_of(b1.x, b1.y, b1.z, fsub(b0.x, pxf), fsub(b0.y, pyf));
+            const float alpha_a = fminf(VTGS_ALPHA_MAX, fmul(a0.w, vexpf(pa)));
+            const float alpha_b = fminf(VTGS_ALPHA_MAX, fmul(b0.w, vexpf(pb)));
+            if (!blend_one(a0, alpha_a, sa)) break;
+            if (two && !blend_one(b0, alpha_b, sb)) break;
         }
     };
 
