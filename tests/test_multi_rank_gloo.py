@@ -1,0 +1,104 @@
+"""CPU, world_size 2 over gloo: the host-side logic of the two sharding modes.
+
+* tracking (tile-row bands): every rank evaluates ONLY its band (oracle with tile_row_begin/end),
+  the 16-float message (pose-gradient partials + loss terms) is all-reduced, and the result must
+  equal the single-rank full-image evaluation -- the property the GPU path relies on
+  (fused.TrackingSolver(process_group=...), bench.py --gpus N).
+* mapping (keyframe shards): per-keyframe parameter gradients all-reduced == sum over keyframes.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _tracking_terms(tile_rows, q, t):
+    """Loss terms and dL/d(cam-frame means) sums of one band through the oracle."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle
+    from helpers import oracle_camera
+    from vtgaussian_slam_b200 import synthetic
+    fr = synthetic.make_frame("replica", 160, 96, seed=0)
+    p = synthetic.view_tied_gaussians(fr, opacity="trained")
+    cam, _ = oracle_camera(fr["W"], fr["H"], fr["K"], tile_rows=tile_rows)
+    m, s, r, o, c6 = oracle.frontend(p["means3D"], p["rgb_colors"], p["unnorm_rotations"], p["logit_opacities"], p["log_scales"], q, t)
+    orc = oracle.Oracle()
+    out = orc.forward(cam, m, s, r, o, c6)
+    img, gd = out["color"], fr["depth"][0]
+    mask = (gd > 0) & (img[4] > 0.99)
+    if tile_rows[1] > tile_rows[0]:
+        band = np.zeros_like(mask)
+        band[tile_rows[0] * 16:tile_rows[1] * 16] = True
+        mask &= band
+    dL = np.zeros((6,) + gd.shape, np.float32)
+    dL[:3] = 0.5 * np.sign(img[:3] - fr["im"]) * mask
+    dL[3] = 0.025 * np.sign(img[3] - gd) * mask
+    loss_im = 0.5 * np.abs(img[:3] - fr["im"])[:, mask].sum()
+    loss_d = 0.025 * np.abs(img[3] - gd)[mask].sum()
+    g = orc.backward(dL)
+    gm = g["means3D"].astype(np.float64)
+    gm[:, 2] += g["colors"][:, 3]                      # depth channel chains into z (depth_row = 0,0,1,0)
+    msg = np.zeros(16)
+    msg[0:3] = gm.sum(0)                               # dL/dt
+    msg[3:12] = (gm[:, :, None] * p["means3D"][:, None, :].astype(np.float64)).sum(0).reshape(-1)   # dL/dR
+    msg[12], msg[13], msg[14] = loss_im + loss_d, loss_im, loss_d
+    msg[15] = mask.sum()
+    return msg, (fr["H"] + 15) // 16
+
+
+def _worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    import bench
+    q, t = np.array([0.9999, 0.005, -0.003, 0.002], np.float32), np.array([0.01, -0.004, 0.006], np.float32)
+    _, gy = _tracking_terms((0, 1), q, t)
+    band = bench.band_for_rank(gy, rank, world)
+    msg, _ = _tracking_terms(band, q, t)
+    tmsg = torch.tensor(msg)
+    dist.all_reduce(tmsg)                              # the one collective of a tracking iteration
+    # mapping: keyframe k -> rank k % world; gradient all-reduce == sum over keyframes
+    kf_grads = [torch.full((5,), float(k + 1)) for k in range(4)]
+    mine = sum(kf_grads[k] for k in range(4) if k % world == rank)
+    dist.all_reduce(mine)
+    if rank == 0:
+        ret["msg"] = tmsg.numpy().copy()
+        ret["map"] = mine.numpy().copy()
+        ret["band0"] = band
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_band_partition_covers_all_rows():
+    sys.path.insert(0, ROOT)
+    import bench
+    for gy in (43, 30, 73, 7):
+        for world in (1, 2, 4, 8):
+            bands = [bench.band_for_rank(gy, r, world) for r in range(world)]
+            assert bands[0][0] == 0 and bands[-1][1] == gy
+            assert all(bands[i][1] == bands[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in bands]
+            assert max(sizes) - min(sizes) <= 1
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_gloo_allreduce_equals_single_rank():
+    port = 29500 + (os.getpid() % 2000)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(2, port, ret), nprocs=2, join=True)
+    q, t = np.array([0.9999, 0.005, -0.003, 0.002], np.float32), np.array([0.01, -0.004, 0.006], np.float32)
+    full, _ = _tracking_terms((0, 0), q, t)
+    got = ret["msg"]
+    assert got[15] == full[15]                                         # mask counts add up exactly
+    np.testing.assert_allclose(got[12:15], full[12:15], rtol=1e-6)     # loss terms
+    scale = np.abs(full[:12]).max()
+    assert np.abs(got[:12] - full[:12]).max() <= 1e-5 * scale          # pose-gradient partial sums
+    np.testing.assert_allclose(ret["map"], np.full(5, 10.0))

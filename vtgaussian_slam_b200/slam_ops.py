@@ -298,6 +298,37 @@ class _FusedRender(torch.autograd.Function):
         return (None, None, None, None, None, None, gq, gt, None, None)
 
 
+class _FusedTrackingLoss(torch.autograd.Function):
+    """loss, loss_terms, radii = get_loss(tracking=True) in three library calls: fused six-plane render,
+    masked-L1 tracking loss + dL/dplanes (vtgs_loss), and -- in backward -- the reduction straight to the
+    frame's 7 pose numbers (vtgs_fused_backward).  Gaussians are frozen in tracking (their LRs are 0 and
+    transform_to_frame detaches them, reference :432-436)."""
+
+    @staticmethod
+    def forward(ctx, renderer, params, cam_q, cam_t, gt_rgb, gt_depth, cfg, thres_fn):
+        p = {k: params[k].detach().contiguous() for k in ("means3D", "rgb_colors", "unnorm_rotations", "logit_opacities", "log_scales")}
+        q, t = cam_q.detach().contiguous().reshape(4), cam_t.detach().contiguous().reshape(3)
+        img, radii = renderer.forward(p, q, t)
+        cfg = dict(cfg)
+        if thres_fn is not None:
+            cfg["sil_thres"] = thres_fn(img)
+        terms = renderer.tracking_loss(gt_rgb.contiguous(), gt_depth.contiguous(), **cfg).clone()
+        ctx.renderer, ctx.p, ctx.q, ctx.t = renderer, p, q, t
+        ctx.pose_shapes = (cam_q.shape, cam_t.shape)
+        ctx.dL4 = renderer.dL_dimage4          # valid until the renderer's next loss call
+        radii = radii.clone()
+        ctx.mark_non_differentiable(radii, terms)
+        return terms[0].clone(), terms, radii
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_terms, _g_radii):
+        dq = torch.zeros(4, dtype=torch.float32, device=g_loss.device)
+        dt = torch.zeros(3, dtype=torch.float32, device=g_loss.device)
+        ctx.renderer.backward(ctx.p, ctx.q, ctx.t, dL_dimage4=ctx.dL4, pose_grads=(dq, dt))
+        return (None, None, (dq * g_loss).reshape(ctx.pose_shapes[0]), (dt * g_loss).reshape(ctx.pose_shapes[1]),
+                None, None, None, None)
+
+
 _RENDERERS: dict = {}
 
 
@@ -349,6 +380,38 @@ def get_loss(params, curr_data, variables, iter_time_idx, loss_weights, use_sil_
         cam_t = params['cam_trans'][0, :, iter_time_idx]
         if not camera_grad:
             cam_q, cam_t = cam_q.detach(), cam_t.detach()
+        fused_loss_ok = (tracking and use_l1 and not ignore_outlier_depth_loss and vis_mask is None and additional_mask is None
+                         and set(loss_weights) == {'im', 'depth'})
+        if fused_loss_ok:
+            # whole tracking loss on the device: no boolean-index gathers, no host synchronisation
+            thres, thres_fn = sil_thres, None
+            far = 0.0
+            if dataset_name == 'replica' and use_sil_for_loss:
+                if tracking_iteration == 0 and presence_sil_mask_mse_ls is not None:
+                    def thres_fn(img6):                      # :476-508 threshold ladder on the rendered planes
+                        mse_ls = []
+                        for thr in REPLICA_SIL_LADDER:
+                            m = (img6[4] > thr) & (curr_data['depth'][0] > 0)
+                            d2 = ((curr_data['im'] - img6[:3]) ** 2) * m
+                            mse_ls.append((d2.sum() / (3 * m.sum())).item())
+                        presence_sil_mask_mse_ls.append(min(mse_ls))
+                        sil_thres_ls.append(REPLICA_SIL_LADDER[mse_ls.index(min(mse_ls))])
+                        return sil_thres_ls[-1]
+                elif sil_thres_ls:
+                    thres = sil_thres_ls[-1]
+            elif far_depth_filter_thres is not None and dataset_name != 'scannetpp':
+                far = float(far_depth_filter_thres)
+            cfg = dict(w_im=float(loss_weights['im']), w_depth=float(loss_weights['depth']),
+                       use_sil_for_loss=bool(use_sil_for_loss), sil_thres=float(thres), far_depth_thres=far)
+            loss, terms, radius = _FusedTrackingLoss.apply(r, params, cam_q, cam_t, curr_data['im'], curr_data['depth'], cfg, thres_fn)
+            weighted_losses = {'depth': terms[2], 'im': terms[1], 'loss': loss}
+            seen = radius > 0
+            variables['max_2D_radius'] = torch.where(seen, torch.max(radius.to(variables['max_2D_radius'].dtype),
+                                                                     variables['max_2D_radius']), variables['max_2D_radius'])
+            variables['seen'] = seen
+            if presence_sil_mask_mse_ls is not None:
+                return loss, variables, weighted_losses, presence_sil_mask_mse_ls, sil_thres_ls
+            return loss, variables, weighted_losses
         g = (lambda t: t) if gaussians_grad else (lambda t: t.detach())
         im, depth_sil, radius, means2D = _FusedRender.apply(
             r, g(params['means3D']), g(params['rgb_colors']), g(params['unnorm_rotations']), g(params['logit_opacities']),
@@ -362,8 +425,10 @@ def get_loss(params, curr_data, variables, iter_time_idx, loss_weights, use_sil_
         additional_mask, dataset_name, tracking_iteration, presence_sil_mask_mse_ls, sil_thres_ls, far_depth_filter_thres,
         vis_mask)
 
+    # reference :681-683 (max_2D_radius[seen] = max(radius[seen], max_2D_radius[seen])) without the boolean-index sync
     seen = radius > 0
-    variables['max_2D_radius'][seen] = torch.max(radius[seen], variables['max_2D_radius'][seen])
+    variables['max_2D_radius'] = torch.where(seen, torch.max(radius.to(variables['max_2D_radius'].dtype),
+                                                             variables['max_2D_radius']), variables['max_2D_radius'])
     variables['seen'] = seen
     if presence_sil_mask_mse_ls is not None:
         return loss, variables, weighted_losses, presence_sil_mask_mse_ls, sil_thres_ls
