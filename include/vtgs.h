@@ -236,7 +236,7 @@ VTGS_API int vtgs_fused_forward(const VtgsCamera* cam, const VtgsParams* params,
  * dL/d(image6) in place of autograd.
  *   mode 0: tracking   losses = sum|d|[mask] (depth), sum|rgb diff|[mask] (im)
  *   mode 1: mapping    losses = mean|d|[depth>0] (depth), 0.8*L1mean + 0.2*(1-SSIM) (im)
- * loss_terms[8] = {loss, w_im*im, w_depth*depth, mask_count, l1_im, ssim, 0, 0}.
+ * loss_terms[8] = {loss, w_im*im, w_depth*depth, mask_count, l1_im, ssim, depth_l1_mean, 0}.
  */
 typedef struct VtgsLossConfig {
     int32_t mode;                   /* 0 tracking, 1 mapping                              */
@@ -291,6 +291,14 @@ VTGS_API int vtgs_fused_backward(const VtgsCamera* cam, const VtgsParams* params
 VTGS_API int vtgs_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
               float lr, float beta1, float beta2, float eps, int32_t step,
               const int32_t* step_dev, void* stream);
+
+/*
+ * Re-tie a section's view-tied Gaussians to its optimised pose (reference src/vtgaussian_slam.py:2706-2727):
+ * means3D[i] <- inv([R(q)|t]) * (w2c_old * means3D[i]) for i in [0, n).  w2c_old: 12 HOST floats (rows of the 3x4
+ * matrix the section was tied to); q = cam_unnorm_rot[4], t = cam_trans[3] on the DEVICE (the just-stepped pose).
+ */
+VTGS_API int vtgs_retie(float* means3D, int64_t n, const float* w2c_old, const float* cam_unnorm_rot,
+                        const float* cam_trans, void* stream);
 
 /*
  * Tracking pose update in one launch: the reference's `optimizer.step()` on the frame's pose slices

@@ -215,3 +215,70 @@ def test_get_loss_fused_equals_dropin():
     loss, _, _ = slam_ops.get_loss(params, data, variables, 0, dict(im=1.0, depth=1.0), False, 0.5, True, False, mapping=True)
     loss.backward()
     assert params["rgb_colors"].grad.abs().sum().item() > 0 and params["cam_trans"].grad is None
+
+
+def test_mapping_loss_kernels_match_torch_autograd():
+    """vtgs_loss mode 1 (SSIM forward/backward kernels) against the reference-shaped torch loss
+    (0.8 L1 + 0.2 (1 - calc_ssim) + mean depth L1) and its autograd gradient."""
+    from vtgaussian_slam_b200.fused import FusedRenderer
+    fr, p, q, t = _scene(203, 117, n_edge=1500)             # ragged: not multiples of 16
+    settings, _ = _settings(fr)
+    r = FusedRenderer(settings, p["means3D"].shape[0], device=DEV)
+    gp = _gpu_params(p)
+    img, _ = r.forward(gp, torch.tensor(q, device=DEV), torch.tensor(t, device=DEV))
+    gt_rgb, gt_d = torch.tensor(fr["im"], device=DEV), torch.tensor(fr["depth"], device=DEV)
+    gt_d[0, 10:20, 30:50] = 0.0                              # invalid depth region
+    terms = r.mapping_loss(gt_rgb, gt_d, w_im=1.0, w_depth=1.0).cpu().numpy()
+    loss_ref, g_ref = slam_ops.mapping_loss_and_grad(img, dict(gt_rgb=gt_rgb, gt_depth=gt_d))
+    assert abs(terms[0] - loss_ref.item()) <= 2e-5 * abs(loss_ref.item())
+    ssim_ref = slam_ops.calc_ssim(img[:3], gt_rgb).item()
+    assert abs(terms[5] - ssim_ref) <= 2e-5
+    got = r.dL_dimage4
+    scale = g_ref.abs().amax(dim=(1, 2), keepdim=True)
+    assert ((got - g_ref).abs() / scale).max().item() <= 2e-3
+
+
+def test_mapping_solver_matches_torch_adam_and_retie():
+    from vtgaussian_slam_b200.fused import MappingSolver, retie
+    fr, p, q, t = _scene(160, 96, n_edge=800)
+    settings, _ = _settings(fr)
+    gp = _gpu_params(p)
+    ms = MappingSolver(settings, {k: v.clone() for k, v in gp.items()}, device=DEV)    # the solver updates its tensors in place
+    kfs = []
+    for k in range(2):
+        qk, tk = synthetic.perturbed_pose(seed=10 + k, trans_sigma=0.01, rot_deg=0.3)
+        kfs.append(dict(cam_q=torch.tensor(qk, device=DEV), cam_t=torch.tensor(tk, device=DEV),
+                        gt_rgb=torch.tensor(fr["im"], device=DEV), gt_depth=torch.tensor(fr["depth"], device=DEV)))
+    # reference: the host mirror of get_loss (drop-in backend, torch autograd) summed over keyframes + torch Adam
+    P = {k: torch.nn.Parameter(v.clone()) for k, v in gp.items()}
+    lrs = dict(means3D=0.0, rgb_colors=0.0025, unnorm_rotations=0.0, logit_opacities=0.05, log_scales=0.005)
+    opt = torch.optim.Adam([{'params': [v], 'lr': lrs[k]} for k, v in P.items()], lr=0.0, eps=1e-15)
+    for it in range(2):
+        total = 0
+        for kf in kfs:
+            params = dict(P, cam_unnorm_rots=kf["cam_q"].reshape(1, 4, 1), cam_trans=kf["cam_t"].reshape(1, 3, 1))
+            data = dict(cam=settings, im=kf["gt_rgb"], depth=kf["gt_depth"], w2c=torch.eye(4, device=DEV))
+            variables = dict(max_2D_radius=torch.zeros(P["means3D"].shape[0], device=DEV))
+            loss, _, _ = slam_ops.get_loss(params, data, variables, 0, dict(im=1.0, depth=1.0), False, 0.5, True, False,
+                                           mapping=True, backend="dropin")
+            total = total + loss
+        opt.zero_grad()
+        total.backward()
+        opt.step()
+        got = ms.iteration(kfs)
+        assert abs(got.item() - total.item()) <= 1e-3 * abs(total.item())
+    for k in ("rgb_colors", "logit_opacities", "log_scales"):
+        d_ref = (P[k].detach() - gp[k])
+        d_got = (ms.params[k] - gp[k])
+        assert (d_got - d_ref).abs().max().item() <= 0.05 * d_ref.abs().max().item() + 1e-7, k     # Adam normalises: sign-level agreement
+        assert (torch.sign(d_got) != torch.sign(d_ref)).float().mean().item() < 0.02, k
+    # re-tie (reference :2706-2727)
+    pts = gp["means3D"][-500:].clone()
+    w2c_old = np.eye(4, dtype=np.float32); w2c_old[:3, 3] = [0.02, -0.01, 0.03]
+    qn, tn = synthetic.perturbed_pose(seed=5, trans_sigma=0.02, rot_deg=1.0)
+    qn = (qn * 1.3).astype(np.float32)
+    out = retie(pts.clone(), w2c_old, torch.tensor(qn, device=DEV), torch.tensor(tn, device=DEV)).cpu().numpy()
+    R = slam_ops.build_rotation(torch.nn.functional.normalize(torch.tensor(qn)[None]))[0].numpy()
+    cam = pts.cpu().numpy() @ w2c_old[:3, :3].T + w2c_old[:3, 3]
+    want = (cam - tn) @ R                                   # R^T (p - t)
+    assert np.abs(out - want).max() <= 1e-5

@@ -94,6 +94,7 @@ SYMBOLS = {
     "vtgs_pose_scratch_floats": (C.c_uint64, [C.c_int64]),
     "vtgs_fused_backward": (C.c_int, [C.POINTER(VtgsCamera), C.POINTER(VtgsParams), C.POINTER(VtgsPose), _P, C.c_int32,
                                       C.POINTER(VtgsParamGrads), C.POINTER(VtgsBuffers), _P]),
+    "vtgs_retie": (C.c_int, [_P, C.c_int64, C.POINTER(C.c_float * 12), _P, _P, _P]),
     "vtgs_tracking_update": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_float, C.c_float, C.c_float, _P]),
     "vtgs_profile_enable": (C.c_int, [C.c_int32]),
     "vtgs_profile_summary": (C.c_int, [C.c_char_p, C.c_uint64]),

@@ -184,9 +184,15 @@ int vtgs_fused_backward(const VtgsCamera* cam, const VtgsParams* p, const VtgsPo
 uint64_t vtgs_pose_scratch_floats(int64_t N) { return (uint64_t)((N + 255) / 256 + 1) * 12; }
 
 uint64_t vtgs_loss_scratch_floats(int32_t W, int32_t H, int32_t mode) {
-    (void)mode;
     const uint64_t P = (uint64_t)W * H;
+    if (mode == 1) return 9 * P + ((uint64_t)((W + 15) / 16) * ((H + 15) / 16) * 3 + 1) * 4;
     return ((P + 255) / 256 + 1) * 4;
+}
+
+int vtgs_retie(float* means3D, int64_t n, const float* w2c_old, const float* cam_unnorm_rot, const float* cam_trans, void* stream) {
+    VTGS_REQUIRE(n >= 0, "n < 0");
+    VTGS_REQUIRE(w2c_old && cam_unnorm_rot && cam_trans && (n == 0 || means3D), "pointer is NULL");
+    return launch_retie(means3D, n, w2c_old, cam_unnorm_rot, cam_trans, (cudaStream_t)stream);
 }
 
 int vtgs_loss(const VtgsCamera* cam, const VtgsLossConfig* cfg, const float* image6, const float* gt_rgb,

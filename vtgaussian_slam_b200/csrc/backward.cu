@@ -460,19 +460,25 @@ fused_preprocess_backward_kernel(const __grid_constant__ CamConst cam, int64_t N
         const float4 g0 = gg[0], g1 = gg[1], g2 = gg[2];
         const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
         gg[0] = zero4; gg[1] = zero4; gg[2] = zero4;
-        const GeomRecord rec = geom[i];
-        const bool visible = rec.q1.w > -1e29f;
+        // every load is issued before the first use: one memory round trip per thread
+        const float rec_hx = geom[i].q1.w, rec_op = geom[i].q0.w;
+        const float px = prm.means3D[3 * i], py = prm.means3D[3 * i + 1], pz = prm.means3D[3 * i + 2];
+        const float ls = prm.log_scales[i];
+        const float4 uq = (reinterpret_cast<uintptr_t>(prm.unnorm_rotations) & 15) == 0
+                              ? reinterpret_cast<const float4*>(prm.unnorm_rotations)[i]
+                              : make_float4(prm.unnorm_rotations[4 * i], prm.unnorm_rotations[4 * i + 1],
+                                            prm.unnorm_rotations[4 * i + 2], prm.unnorm_rotations[4 * i + 3]);
+        float Rt[12];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) Rt[k] = __ldg(pose_Rt + k);
+        const bool visible = rec_hx > -1e29f;
         float dmeanw[3] = {0.f, 0.f, 0.f}, dls = 0.f, dlogit = 0.f, dqu[4] = {0.f, 0.f, 0.f, 0.f};
         if (visible) {
-            float Rt[12];
-#pragma unroll
-            for (int k = 0; k < 12; ++k) Rt[k] = __ldg(pose_Rt + k);
-            const float px = prm.means3D[3 * i], py = prm.means3D[3 * i + 1], pz = prm.means3D[3 * i + 2];
             const float x = fadd(ffma(Rt[2], pz, ffma(Rt[1], py, fmul(Rt[0], px))), Rt[9]);
             const float y = fadd(ffma(Rt[5], pz, ffma(Rt[4], py, fmul(Rt[3], px))), Rt[10]);
             const float z = fadd(ffma(Rt[8], pz, ffma(Rt[7], py, fmul(Rt[6], px))), Rt[11]);
-            const float s = vexpf(prm.log_scales[i]);
-            float u[4] = {prm.unnorm_rotations[4 * i], prm.unnorm_rotations[4 * i + 1], prm.unnorm_rotations[4 * i + 2], prm.unnorm_rotations[4 * i + 3]};
+            const float s = vexpf(ls);
+            float u[4] = {uq.x, uq.y, uq.z, uq.w};
             const float nrm = sqrtf(u[0] * u[0] + u[1] * u[1] + u[2] * u[2] + u[3] * u[3]);
             const float d = fmaxf(nrm, 1e-12f);
             const float q[4] = {u[0] / d, u[1] / d, u[2] / d, u[3] / d};
@@ -491,7 +497,7 @@ fused_preprocess_backward_kernel(const __grid_constant__ CamConst cam, int64_t N
             dmeanw[1] = Rt[1] * gm[0] + Rt[4] * gm[1] + Rt[7] * gm[2];
             dmeanw[2] = Rt[2] * gm[0] + Rt[5] * gm[1] + Rt[8] * gm[2];
             dls = (dscale[0] + dscale[1] + dscale[2]) * s;            // d exp(ls)/d ls, tiled x3
-            const float o = rec.q0.w;
+            const float o = rec_op;
             dlogit = g1.y * o * (1.0f - o);
             // F.normalize backward
             const float qd = q[0] * dq[0] + q[1] * dq[1] + q[2] * dq[2] + q[3] * dq[3];

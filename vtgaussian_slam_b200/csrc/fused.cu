@@ -82,6 +82,226 @@ loss_finalize_kernel(const float* __restrict__ partials, int nblocks, VtgsLossCo
     }
 }
 
+// =============================== mapping loss (mode 1) =========================================
+// Reference get_loss, mapping branch (src/vtgaussian_slam.py:597,608): depth = mean |gt - d| over
+// (gt > 0 & ~nan); im = 0.8 * mean|im - gt| + 0.2 * (1 - SSIM), SSIM = calc_ssim
+// (utils/slam_external.py:54-97: 11x11 Gaussian window sigma 1.5, zero padding, c1 = 0.01^2, c2 = 0.03^2).
+// Three kernels: stats + SSIM forward (per 16x16 tile and channel, separable window in shared memory,
+// also emits the three derivative maps), a deterministic finalize, and the SSIM backward that
+// convolves the derivative maps and assembles dL/d(r,g,b,depth).
+constexpr int SSIM_R = 5;                 // window radius
+constexpr int SSIM_T = 16;                // output tile
+constexpr int SSIM_H = SSIM_T + 2 * SSIM_R;
+constexpr int MAP_TERMS = 4;              // per-block partials: rgb L1 sum, depth L1 sum, mask count, ssim sum
+
+struct SsimWindow { float g[2 * SSIM_R + 1]; };
+
+static SsimWindow make_window() {
+    SsimWindow w;
+    float sum = 0.f;
+    for (int k = 0; k <= 2 * SSIM_R; ++k) {
+        w.g[k] = (float)exp(-(double)((k - SSIM_R) * (k - SSIM_R)) / (2.0 * 1.5 * 1.5));
+        sum += w.g[k];
+    }
+    for (int k = 0; k <= 2 * SSIM_R; ++k) w.g[k] /= sum;
+    return w;
+}
+
+// grid (tiles_x, tiles_y, 3 channels); block 16x16.
+__global__ void __launch_bounds__(256)
+ssim_forward_kernel(int W, int H, const SsimWindow win, const float* __restrict__ image6, const float* __restrict__ gt_rgb,
+                    const float* __restrict__ gt_depth, float* __restrict__ maps /* [3 ch][3 maps][P] */,
+                    float* __restrict__ partials) {
+    __shared__ float sx[SSIM_H][SSIM_H + 1], sy[SSIM_H][SSIM_H + 1];
+    __shared__ float hb[5][SSIM_H][SSIM_T + 1];
+    __shared__ float s_part[8][MAP_TERMS];
+    const int ch = blockIdx.z;
+    const size_t P = (size_t)W * H;
+    const float* X = image6 + (size_t)ch * P;
+    const float* Y = gt_rgb + (size_t)ch * P;
+    const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * SSIM_T + tx;
+    const int ox = blockIdx.x * SSIM_T - SSIM_R, oy = blockIdx.y * SSIM_T - SSIM_R;
+    for (int k = tid; k < SSIM_H * SSIM_H; k += 256) {
+        const int r = k / SSIM_H, c = k % SSIM_H;
+        const int gx = ox + c, gy = oy + r;
+        const bool in = gx >= 0 && gx < W && gy >= 0 && gy < H;          // zero padding
+        sx[r][c] = in ? X[(size_t)gy * W + gx] : 0.0f;
+        sy[r][c] = in ? Y[(size_t)gy * W + gx] : 0.0f;
+    }
+    __syncthreads();
+    // horizontal pass: 26 rows x 16 columns of the five fields
+    for (int k = tid; k < SSIM_H * SSIM_T; k += 256) {
+        const int r = k / SSIM_T, c = k % SSIM_T;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f;
+#pragma unroll
+        for (int j = 0; j <= 2 * SSIM_R; ++j) {
+            const float x = sx[r][c + j], y = sy[r][c + j], g = win.g[j];
+            a0 = fmaf(g, x, a0); a1 = fmaf(g, y, a1); a2 = fmaf(g, x * x, a2); a3 = fmaf(g, y * y, a3); a4 = fmaf(g, x * y, a4);
+        }
+        hb[0][r][c] = a0; hb[1][r][c] = a1; hb[2][r][c] = a2; hb[3][r][c] = a3; hb[4][r][c] = a4;
+    }
+    __syncthreads();
+    const int px = blockIdx.x * SSIM_T + tx, py = blockIdx.y * SSIM_T + ty;
+    float l1 = 0.f, ld = 0.f, cnt = 0.f, ss = 0.f;
+    if (px < W && py < H) {
+        float m1 = 0.f, m2 = 0.f, X2 = 0.f, Y2 = 0.f, XY = 0.f;
+#pragma unroll
+        for (int j = 0; j <= 2 * SSIM_R; ++j) {
+            const float g = win.g[j];
+            m1 = fmaf(g, hb[0][ty + j][tx], m1); m2 = fmaf(g, hb[1][ty + j][tx], m2);
+            X2 = fmaf(g, hb[2][ty + j][tx], X2); Y2 = fmaf(g, hb[3][ty + j][tx], Y2); XY = fmaf(g, hb[4][ty + j][tx], XY);
+        }
+        const float c1 = 0.0001f, c2 = 0.0009f;
+        const float s11 = X2 - m1 * m1, s22 = Y2 - m2 * m2, s12 = XY - m1 * m2;
+        const float A1 = 2.f * m1 * m2 + c1, A2 = 2.f * s12 + c2, B1 = m1 * m1 + m2 * m2 + c1, B2 = s11 + s22 + c2;
+        const float inv = 1.0f / (B1 * B2);
+        const float S = A1 * A2 * inv;
+        ss = S;
+        const size_t pid = (size_t)py * W + px;
+        float* mp = maps + (size_t)ch * 3 * P;
+        mp[pid] = (2.f * m2 * (A2 - A1) - 2.f * m1 * S * (B2 - B1)) * inv;      // dS/dmu1 (X2, XY held)
+        mp[P + pid] = -S / B2;                                                 // dS/dconv(x^2)
+        mp[2 * P + pid] = 2.f * A1 * inv;                                      // dS/dconv(xy)
+        l1 = fabsf(sx[ty + SSIM_R][tx + SSIM_R] - sy[ty + SSIM_R][tx + SSIM_R]);
+        if (ch == 0) {
+            const float d = image6[3 * P + pid], dsq = image6[5 * P + pid], gd = gt_depth[pid];
+            const float unc = dsq - d * d;
+            if (gd > 0.0f && !(d != d) && !(unc != unc)) { ld = fabsf(gd - d); cnt = 1.0f; }
+        }
+    }
+    l1 = warp_sum(l1); ld = warp_sum(ld); cnt = warp_sum(cnt); ss = warp_sum(ss);
+    const int lane = tid & 31, warp = tid >> 5;
+    if (lane == 0) { s_part[warp][0] = l1; s_part[warp][1] = ld; s_part[warp][2] = cnt; s_part[warp][3] = ss; }
+    __syncthreads();
+    if (tid < MAP_TERMS) {
+        float a = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) a += s_part[w][tid];
+        const size_t b = ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+        partials[b * MAP_TERMS + tid] = a;
+    }
+}
+
+__global__ void __launch_bounds__(1024)
+mapping_finalize_kernel(const float* __restrict__ partials, int nblocks, int W, int H, VtgsLossConfig cfg, float* __restrict__ loss_terms) {
+    __shared__ double s_sum[MAP_TERMS][256];
+    __shared__ double s_tot[MAP_TERMS];
+    const int tid = threadIdx.x;
+    const int term = tid & (MAP_TERMS - 1), sl = tid >> 2;
+    double acc = 0.0;
+    for (int b = sl; b < nblocks; b += 256) acc += (double)partials[(size_t)b * MAP_TERMS + term];
+    s_sum[term][sl] = acc;
+    __syncthreads();
+    if (tid < MAP_TERMS) {
+        double a = 0.0;
+        for (int i = 0; i < 256; ++i) a += s_sum[tid][i];
+        s_tot[tid] = a;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const double n3 = 3.0 * (double)W * (double)H;
+        const double l1_mean = s_tot[0] / n3, ssim = s_tot[3] / n3;
+        const double cnt = s_tot[2];
+        const double depth_mean = cnt > 0.0 ? s_tot[1] / cnt : 0.0 / 0.0;      // torch: mean of an empty selection is nan
+        const double im = 0.8 * l1_mean + 0.2 * (1.0 - ssim);
+        loss_terms[0] = (float)((double)cfg.w_im * im + (double)cfg.w_depth * depth_mean);
+        loss_terms[1] = (float)((double)cfg.w_im * im);
+        loss_terms[2] = (float)((double)cfg.w_depth * depth_mean);
+        loss_terms[3] = (float)cnt;
+        loss_terms[4] = (float)l1_mean;
+        loss_terms[5] = (float)ssim;
+        loss_terms[6] = (float)depth_mean;
+        loss_terms[7] = 0.0f;
+    }
+}
+
+// dL/dx = conv(gS * a) + 2 x conv(gS * b) + y conv(gS * c), gS = -0.2 w_im / (3P); plus the L1 terms.
+__global__ void __launch_bounds__(256)
+ssim_backward_kernel(int W, int H, const SsimWindow win, VtgsLossConfig cfg, const float* __restrict__ image6,
+                     const float* __restrict__ gt_rgb, const float* __restrict__ gt_depth, const float* __restrict__ maps,
+                     const float* __restrict__ loss_terms, float* __restrict__ dL_dimage4) {
+    __shared__ float sm[3][SSIM_H][SSIM_H + 1];
+    __shared__ float hb[3][SSIM_H][SSIM_T + 1];
+    const int ch = blockIdx.z;
+    const size_t P = (size_t)W * H;
+    const float* mp = maps + (size_t)ch * 3 * P;
+    const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * SSIM_T + tx;
+    const int ox = blockIdx.x * SSIM_T - SSIM_R, oy = blockIdx.y * SSIM_T - SSIM_R;
+    for (int k = tid; k < SSIM_H * SSIM_H; k += 256) {
+        const int r = k / SSIM_H, c = k % SSIM_H;
+        const int gx = ox + c, gy = oy + r;
+        const bool in = gx >= 0 && gx < W && gy >= 0 && gy < H;
+        const size_t pid = (size_t)gy * W + gx;
+        sm[0][r][c] = in ? mp[pid] : 0.0f;
+        sm[1][r][c] = in ? mp[P + pid] : 0.0f;
+        sm[2][r][c] = in ? mp[2 * P + pid] : 0.0f;
+    }
+    __syncthreads();
+    for (int k = tid; k < SSIM_H * SSIM_T; k += 256) {
+        const int r = k / SSIM_T, c = k % SSIM_T;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll
+        for (int j = 0; j <= 2 * SSIM_R; ++j) {
+            const float g = win.g[j];
+            a0 = fmaf(g, sm[0][r][c + j], a0); a1 = fmaf(g, sm[1][r][c + j], a1); a2 = fmaf(g, sm[2][r][c + j], a2);
+        }
+        hb[0][r][c] = a0; hb[1][r][c] = a1; hb[2][r][c] = a2;
+    }
+    __syncthreads();
+    const int px = blockIdx.x * SSIM_T + tx, py = blockIdx.y * SSIM_T + ty;
+    if (px >= W || py >= H) return;
+    float ca = 0.f, cb = 0.f, cc = 0.f;
+#pragma unroll
+    for (int j = 0; j <= 2 * SSIM_R; ++j) {
+        const float g = win.g[j];
+        ca = fmaf(g, hb[0][ty + j][tx], ca); cb = fmaf(g, hb[1][ty + j][tx], cb); cc = fmaf(g, hb[2][ty + j][tx], cc);
+    }
+    const size_t pid = (size_t)py * W + px;
+    const float x = image6[(size_t)ch * P + pid], y = gt_rgb[(size_t)ch * P + pid];
+    const float n3 = 3.0f * (float)W * (float)H;
+    const float dssim = ca + 2.0f * x * cb + y * cc;
+    dL_dimage4[(size_t)ch * P + pid] = cfg.w_im * (0.8f * sgn(x - y) - 0.2f * dssim) / n3;
+    if (ch == 0) {
+        const float d = image6[3 * P + pid], dsq = image6[5 * P + pid], gd = gt_depth[pid];
+        const float unc = dsq - d * d;
+        const bool mask = gd > 0.0f && !(d != d) && !(unc != unc);
+        const float cnt = loss_terms[3];
+        dL_dimage4[3 * P + pid] = mask ? cfg.w_depth * sgn(d - gd) / cnt : 0.0f;
+    }
+}
+
+// ---- re-tie a section's Gaussians to its optimised pose (reference src/vtgaussian_slam.py:2706-2727) ----
+// pts <- inv([R(q)|t]) * (w2c_old * pts), q/t read from the device (the pose the optimiser just updated).
+struct Mat34 { float m[12]; };
+__global__ void __launch_bounds__(256)
+retie_kernel(float* __restrict__ means3D, int64_t n, const Mat34 old, const float* __restrict__ q_un, const float* __restrict__ t) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const float u0 = q_un[0], u1 = q_un[1], u2 = q_un[2], u3 = q_un[3];
+    const float n1 = fmaxf(sqrtf(u0 * u0 + u1 * u1 + u2 * u2 + u3 * u3), 1e-12f);
+    float q0 = u0 / n1, q1 = u1 / n1, q2 = u2 / n1, q3 = u3 / n1;
+    const float n2 = sqrtf(q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3);
+    q0 /= n2; q1 /= n2; q2 /= n2; q3 /= n2;
+    float R[9];
+    quat_to_R(q0, q1, q2, q3, R);
+    const float x = means3D[3 * i], y = means3D[3 * i + 1], z = means3D[3 * i + 2];
+    const float cx = old.m[0] * x + old.m[1] * y + old.m[2] * z + old.m[3] - t[0];
+    const float cy = old.m[4] * x + old.m[5] * y + old.m[6] * z + old.m[7] - t[1];
+    const float cz = old.m[8] * x + old.m[9] * y + old.m[10] * z + old.m[11] - t[2];
+    means3D[3 * i] = R[0] * cx + R[3] * cy + R[6] * cz;          // R^T (p_cam - t)
+    means3D[3 * i + 1] = R[1] * cx + R[4] * cy + R[7] * cz;
+    means3D[3 * i + 2] = R[2] * cx + R[5] * cy + R[8] * cz;
+}
+
+int launch_retie(float* means3D, int64_t n, const float* w2c_old_rowmajor12, const float* q_un, const float* t, cudaStream_t stream) {
+    if (n <= 0) return VTGS_OK;
+    Mat34 m;
+    for (int k = 0; k < 12; ++k) m.m[k] = w2c_old_rowmajor12[k];
+    { VTGS_PROF("retie_kernel", stream); retie_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(means3D, n, m, q_un, t); }
+    VTGS_LAUNCH_CHECK();
+    return VTGS_OK;
+}
+
 static inline size_t band_pixels(const CamConst& cam) {
     const size_t P = (size_t)cam.W * cam.H;
     const size_t b = (size_t)cam.row0 * 16 * cam.W;
@@ -96,7 +316,23 @@ int launch_loss(const VtgsCamera* camera, const VtgsLossConfig* cfg, const float
     const CamConst cam = make_cam_const(*camera);
     if (cfg->ignore_outlier_depth) { set_error("ignore_outlier_depth_loss (median mask) is not fused"); return VTGS_E_UNSUPPORTED; }
     if (!cfg->use_l1) { set_error("use_l1 = False is not supported"); return VTGS_E_UNSUPPORTED; }
-    if (cfg->mode != 0) { set_error("mapping loss (SSIM) is computed on the host side in this build"); return VTGS_E_UNSUPPORTED; }
+    if (cfg->mode == 1) {
+        if (cam.row0 != 0 || cam.row1 != cam.gy) { set_error("mapping loss is not band-sharded"); return VTGS_E_INVALID; }
+        static const SsimWindow win = make_window();
+        const size_t P = (size_t)cam.W * cam.H;
+        const dim3 grid((cam.W + SSIM_T - 1) / SSIM_T, (cam.H + SSIM_T - 1) / SSIM_T, 3), block(SSIM_T, SSIM_T);
+        const int nb = (int)(grid.x * grid.y * grid.z);
+        float* maps = scratch;                      // 9 P floats
+        float* partials = scratch + 9 * P;          // nb * 4
+        { VTGS_PROF("ssim_forward_kernel", stream); ssim_forward_kernel<<<grid, block, 0, stream>>>(cam.W, cam.H, win, image6, gt_rgb, gt_depth, maps, partials); }
+        VTGS_LAUNCH_CHECK();
+        { VTGS_PROF("mapping_finalize_kernel", stream); mapping_finalize_kernel<<<1, 1024, 0, stream>>>(partials, nb, cam.W, cam.H, *cfg, loss_terms); }
+        VTGS_LAUNCH_CHECK();
+        { VTGS_PROF("ssim_backward_kernel", stream); ssim_backward_kernel<<<grid, block, 0, stream>>>(cam.W, cam.H, win, *cfg, image6, gt_rgb, gt_depth, maps, loss_terms, dL_dimage4); }
+        VTGS_LAUNCH_CHECK();
+        return VTGS_OK;
+    }
+    if (cfg->mode != 0) { set_error("unknown loss mode"); return VTGS_E_INVALID; }
     const size_t npx = band_pixels(cam);
     const int nblocks = (int)((npx + 255) / 256);
     if (nblocks > 0) {

@@ -50,6 +50,7 @@ int launch_loss(const VtgsCamera* cam, const VtgsLossConfig* cfg, const float* i
                 float* scratch, cudaStream_t stream);
 int launch_tracking_update(float* cam_q, float* cam_t, const float* msg, float* adam, int32_t* step_dev, float* best,
                            float lr_rot, float lr_trans, float eps, cudaStream_t stream);
+int launch_retie(float* means3D, int64_t n, const float* w2c_old_rowmajor12, const float* q_un, const float* t, cudaStream_t stream);
 int launch_adam(float* param, const float* grad, float* m, float* v, int64_t n, float lr, float b1,
                 float b2, float eps, int step, const int32_t* step_dev, cudaStream_t stream);
 

@@ -49,6 +49,7 @@ class FusedRenderer:
         self.loss_terms = torch.zeros(8, **f32)
         self._loss_scratch = torch.zeros(int(L.vtgs_loss_scratch_floats(self.W, self.H, 0)), **f32)
         self._pose_scratch = torch.zeros(int(L.vtgs_pose_scratch_floats(self.N)), **f32)
+        self._map_scratch = None
         self._bufs = self.ws.struct()
 
     # -- helpers ---------------------------------------------------------------------------
@@ -108,6 +109,21 @@ class FusedRenderer:
                                             _stream_ptr(self.device)))
         return self.loss_terms
 
+    def mapping_loss(self, gt_rgb, gt_depth, w_im=1.0, w_depth=1.0, image6=None):
+        """Mapping loss of get_loss (reference :597,:608): w_depth * mean|gt-d|[gt>0] + w_im * (0.8 L1mean +
+        0.2 (1 - SSIM)) of the last forward, SSIM forward+backward in hand-written kernels.
+        -> loss_terms[8] (device): loss, w_im*im, w_depth*depth, mask count, L1 mean, SSIM, depth L1 mean; fills dL_dimage4."""
+        if self._map_scratch is None:
+            n = int(_lib.lib().vtgs_loss_scratch_floats(self.W, self.H, 1))
+            self._map_scratch = torch.zeros(n, dtype=torch.float32, device=self.device)
+        cfg = _lib.VtgsLossConfig(1, 0, 0, 1, 0.0, float(w_im), float(w_depth), 0.0)
+        img = self.image6 if image6 is None else image6
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().vtgs_loss(C.byref(self.cam), C.byref(cfg), _ptr(img), _ptr(gt_rgb), _ptr(gt_depth),
+                                            _ptr(self.dL_dimage4), _ptr(self.loss_terms), _ptr(self._map_scratch),
+                                            _stream_ptr(self.device)))
+        return self.loss_terms
+
     def backward(self, params, cam_q, cam_t, dL_dimage4=None, param_grads=None, pose_grads=None, means2D_grad=None,
                  accumulate=False):
         """param_grads: dict key -> tensor to receive dL/dparams[key] (any subset of PARAM_KEYS).
@@ -129,6 +145,21 @@ class FusedRenderer:
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().vtgs_fused_backward(C.byref(self.cam), C.byref(p), C.byref(ps), _ptr(dL), int(bool(accumulate)),
                                                       C.byref(g), C.byref(self._bufs), _stream_ptr(self.device)))
+
+
+def retie(means3D, w2c_old, cam_q, cam_t):
+    """In place: means3D <- inv([R(cam_q)|cam_t]) (w2c_old means3D) -- the reference's re-tie of a section's newest
+    Gaussians to the pose the mapping step just optimised (src/vtgaussian_slam.py:2706-2727).  `means3D` may be a
+    contiguous row slice (e.g. params['means3D'][-num_gs_curr:])."""
+    _require_cuda("means3D", means3D)
+    if not means3D.is_contiguous() or means3D.dtype != torch.float32:
+        raise ValueError("means3D must be a contiguous float32 tensor (a row slice is fine)")
+    m = torch.as_tensor(w2c_old).detach().float().cpu().reshape(4, 4)[:3].reshape(-1).tolist()
+    arr = (C.c_float * 12)(*m)
+    with torch.cuda.device(means3D.device):
+        _lib.check(_lib.lib().vtgs_retie(_ptr(means3D), means3D.shape[0], C.byref(arr), _ptr(cam_q), _ptr(cam_t),
+                                         _stream_ptr(means3D.device)))
+    return means3D
 
 
 def adam_step(param, grad, exp_avg, exp_avg_sq, lr, step=None, step_dev=None, beta1=0.9, beta2=0.999, eps=1e-8):
@@ -236,8 +267,10 @@ class MappingSolver:
     per-keyframe losses, one backward, one Adam step over rgb / logit-opacity / log-scale
     (mapping LRs, configs/replica/room0.py:99-107; means3D and rotations have LR 0).
 
-    `loss_fn(image6, kf) -> (loss, dL_dimage4)` supplies the mapping loss
-    (0.8 L1 + 0.2 (1-SSIM) + depth L1 mean, see slam_ops.mapping_loss_and_grad)."""
+    Parameters that are already contiguous float32 CUDA tensors are updated IN PLACE (no copy is made).
+    The mapping loss (0.8 L1 + 0.2 (1-SSIM) + depth L1 mean) runs in the library's SSIM kernels; an optional
+    `loss_fn(image6, kf) -> (loss, dL_dimage4)` can replace it (e.g. slam_ops.mapping_loss_and_grad, the
+    torch-autograd restatement used to check it)."""
 
     def __init__(self, settings, params, device="cuda:0", lrs=None, eps=1e-15, pair_capacity=None, process_group=None):
         self.device = torch.device(device)
@@ -253,13 +286,17 @@ class MappingSolver:
         self.pg = process_group
         self.total_loss = torch.zeros(1, dtype=torch.float32, device=self.device)
 
-    def iteration(self, keyframes, loss_fn):
-        """keyframes: list of dict(cam_q, cam_t, gt_rgb, gt_depth) owned by THIS rank."""
+    def iteration(self, keyframes, loss_fn=None, w_im=1.0, w_depth=1.0):
+        """keyframes: list of dict(cam_q, cam_t, gt_rgb, gt_depth) owned by THIS rank.  loss_fn=None uses the
+        fused mapping loss kernels (FusedRenderer.mapping_loss)."""
         self.total_loss.zero_()
         first = True
         for kf in keyframes:
             img, _ = self.r.forward(self.params, kf["cam_q"], kf["cam_t"])
-            loss, dL4 = loss_fn(img, kf)
+            if loss_fn is None:
+                loss, dL4 = self.r.mapping_loss(kf["gt_rgb"], kf["gt_depth"], w_im=w_im, w_depth=w_depth)[0:1], None
+            else:
+                loss, dL4 = loss_fn(img, kf)
             self.total_loss += loss
             self.r.backward(self.params, kf["cam_q"], kf["cam_t"], dL_dimage4=dL4, param_grads=self.grads, accumulate=not first)
             first = False

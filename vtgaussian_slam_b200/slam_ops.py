@@ -329,6 +329,40 @@ class _FusedTrackingLoss(torch.autograd.Function):
                 None, None, None, None)
 
 
+class _FusedMappingLoss(torch.autograd.Function):
+    """loss, loss_terms, radii = get_loss(mapping=True) on the device: fused six-plane render, the mapping loss
+    with its SSIM forward/backward kernels, and the backward to the Gaussian parameters (and the pose if do_ba)."""
+
+    @staticmethod
+    def forward(ctx, renderer, means3D, rgb, unnorm_rot, logit_op, log_scales, cam_q, cam_t, gt_rgb, gt_depth, w_im, w_depth,
+                want_pose):
+        p = dict(means3D=means3D.detach().contiguous(), rgb_colors=rgb.detach().contiguous(),
+                 unnorm_rotations=unnorm_rot.detach().contiguous(), logit_opacities=logit_op.detach().contiguous(),
+                 log_scales=log_scales.detach().contiguous())
+        q, t = cam_q.detach().contiguous().reshape(4), cam_t.detach().contiguous().reshape(3)
+        _, radii = renderer.forward(p, q, t)
+        terms = renderer.mapping_loss(gt_rgb.contiguous(), gt_depth.contiguous(), w_im=w_im, w_depth=w_depth).clone()
+        ctx.renderer, ctx.p, ctx.q, ctx.t, ctx.want_pose = renderer, p, q, t, want_pose
+        ctx.pose_shapes = (cam_q.shape, cam_t.shape)
+        ctx.means2D_grad = torch.zeros_like(p["means3D"])
+        radii = radii.clone()
+        ctx.mark_non_differentiable(radii, terms)
+        return terms[0].clone(), terms, radii, ctx.means2D_grad
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_terms, _g_radii, _g_m2d):
+        p = ctx.p
+        pg = {k: torch.zeros_like(v) for k, v in p.items()}
+        pose = None
+        if ctx.want_pose:
+            pose = (torch.zeros(4, dtype=torch.float32, device=g_loss.device), torch.zeros(3, dtype=torch.float32, device=g_loss.device))
+        ctx.renderer.backward(p, ctx.q, ctx.t, param_grads=pg, pose_grads=pose, means2D_grad=ctx.means2D_grad)
+        gq = (pose[0] * g_loss).reshape(ctx.pose_shapes[0]) if pose else None
+        gt = (pose[1] * g_loss).reshape(ctx.pose_shapes[1]) if pose else None
+        return (None, pg["means3D"] * g_loss, pg["rgb_colors"] * g_loss, pg["unnorm_rotations"] * g_loss,
+                pg["logit_opacities"] * g_loss, pg["log_scales"] * g_loss, gq, gt, None, None, None, None, None)
+
+
 _RENDERERS: dict = {}
 
 
@@ -411,6 +445,20 @@ def get_loss(params, curr_data, variables, iter_time_idx, loss_weights, use_sil_
             variables['seen'] = seen
             if presence_sil_mask_mse_ls is not None:
                 return loss, variables, weighted_losses, presence_sil_mask_mse_ls, sil_thres_ls
+            return loss, variables, weighted_losses
+        fused_map_ok = (mapping and not tracking and use_l1 and not ignore_outlier_depth_loss and additional_mask is None
+                        and set(loss_weights) == {'im', 'depth'})
+        if fused_map_ok:
+            loss, terms, radius, means2D = _FusedMappingLoss.apply(
+                r, params['means3D'], params['rgb_colors'], params['unnorm_rotations'], params['logit_opacities'],
+                params['log_scales'], cam_q, cam_t, curr_data['im'], curr_data['depth'], float(loss_weights['im']),
+                float(loss_weights['depth']), camera_grad)
+            variables['means2D'] = means2D
+            weighted_losses = {'depth': terms[2], 'im': terms[1], 'loss': loss}
+            seen = radius > 0
+            variables['max_2D_radius'] = torch.where(seen, torch.max(radius.to(variables['max_2D_radius'].dtype),
+                                                                     variables['max_2D_radius']), variables['max_2D_radius'])
+            variables['seen'] = seen
             return loss, variables, weighted_losses
         g = (lambda t: t) if gaussians_grad else (lambda t: t.detach())
         im, depth_sil, radius, means2D = _FusedRender.apply(
