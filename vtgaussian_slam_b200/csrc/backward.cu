@@ -99,8 +99,8 @@ blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __re
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     WarpArea& A = areas[warp];
     WarpQueue& Q = A.Q;
-    const int rx0 = tile_x * 16 + (warp & 1) * 8, ry0 = tile_y * 16 + (warp >> 1) * 4;
-    const int pix_x = rx0 + (lane & 7), pix_y = ry0 + (lane >> 3);
+    const int rx0 = tile_x * 16 + (warp % REGIONS_X) * REGION_W, ry0 = tile_y * 16 + (warp / REGIONS_X) * REGION_H;
+    const int pix_x = rx0 + (lane % REGION_W), pix_y = ry0 + (lane / REGION_W);
     const bool inside = pix_x < cam.W && pix_y < cam.H;
     const float pxf = (float)pix_x, pyf = (float)pix_y;
     const float x0f = (float)rx0, y0f = (float)ry0;
@@ -254,13 +254,14 @@ __device__ __forceinline__ void cov2d_backward(const CamConst& cam, float x, flo
                                                float g2x, float g2y, CovGrad& o) {
     const float* V = cam.view;
     const float tx = xform_row(V, 0, x, y, z), ty = xform_row(V, 1, x, y, z), tz = xform_row(V, 2, x, y, z);
-    const float txtz = tx / tz, tytz = ty / tz;
+    const float itz = __fdividef(1.0f, tz);
+    const float txtz = tx * itz, tytz = ty * itz;
     const float cx = fminf(cam.limx, fmaxf(-cam.limx, txtz)) * tz;
     const float cy = fminf(cam.limy, fmaxf(-cam.limy, tytz)) * tz;
     const float xmul = (txtz < -cam.limx || txtz > cam.limx) ? 0.0f : 1.0f;
     const float ymul = (tytz < -cam.limy || tytz > cam.limy) ? 0.0f : 1.0f;
     const float fx = cam.focal_x, fy = cam.focal_y;
-    const float itz = 1.0f / tz, itz2 = itz * itz, itz3 = itz2 * itz;
+    const float itz2 = itz * itz, itz3 = itz2 * itz;
     const float J00 = fx * itz, J02 = -(fx * cx) * itz2, J11 = fy * itz, J12 = -(fy * cy) * itz2;
     float m0[3], m1[3];
 #pragma unroll
@@ -279,7 +280,7 @@ __device__ __forceinline__ void cov2d_backward(const CamConst& cam, float x, flo
     const float b = m1[0] * Sm0[0] + m1[1] * Sm0[1] + m1[2] * Sm0[2];
     const float c = m1[0] * Sm1[0] + m1[1] * Sm1[1] + m1[2] * Sm1[2] + VTGS_LOWPASS;
     const float denom = a * c - b * b;
-    const float d2inv = 1.0f / (denom * denom + 0.0000001f);
+    const float d2inv = __fdividef(1.0f, denom * denom + 0.0000001f);
     float dL_da = 0.f, dL_db = 0.f, dL_dc = 0.f;
     if (d2inv != 0.0f) {
         dL_da = d2inv * (-c * c * gxx + 2.0f * b * c * gxy + (denom - a * c) * gyy);
@@ -306,7 +307,7 @@ __device__ __forceinline__ void cov2d_backward(const CamConst& cam, float x, flo
     const float dtz = -fx * itz2 * dJ00 - fy * itz2 * dJ11 + (2.0f * fx * cx) * itz3 * dJ02 + (2.0f * fy * cy) * itz3 * dJ12;
     const float* Pm = cam.proj;
     const float hx = xform_row(Pm, 0, x, y, z), hy = xform_row(Pm, 1, x, y, z), hw = xform_row(Pm, 3, x, y, z);
-    const float mw = 1.0f / (hw + VTGS_EPS_W);
+    const float mw = __fdividef(1.0f, hw + VTGS_EPS_W);
     const float mul1 = hx * mw * mw, mul2 = hy * mw * mw;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -471,7 +472,11 @@ fused_preprocess_backward_kernel(const __grid_constant__ CamConst cam, int64_t N
         float Rt[12];
 #pragma unroll
         for (int k = 0; k < 12; ++k) Rt[k] = __ldg(pose_Rt + k);
-        const bool visible = rec_hx > -1e29f;
+        // culled splats, and splats no pixel blended (all sums exactly zero), have zero gradients: every
+        // term below is linear in g0..g2
+        const bool any_grad = (g0.x != 0.f) | (g0.y != 0.f) | (g0.z != 0.f) | (g0.w != 0.f) | (g1.x != 0.f) | (g1.y != 0.f) |
+                              (g1.z != 0.f) | (g1.w != 0.f) | (g2.x != 0.f) | (g2.y != 0.f);
+        const bool visible = rec_hx > -1e29f && any_grad;
         float dmeanw[3] = {0.f, 0.f, 0.f}, dls = 0.f, dlogit = 0.f, dqu[4] = {0.f, 0.f, 0.f, 0.f};
         if (visible) {
             const float x = fadd(ffma(Rt[2], pz, ffma(Rt[1], py, fmul(Rt[0], px))), Rt[9]);
@@ -480,8 +485,8 @@ fused_preprocess_backward_kernel(const __grid_constant__ CamConst cam, int64_t N
             const float s = vexpf(ls);
             float u[4] = {uq.x, uq.y, uq.z, uq.w};
             const float nrm = sqrtf(u[0] * u[0] + u[1] * u[1] + u[2] * u[2] + u[3] * u[3]);
-            const float d = fmaxf(nrm, 1e-12f);
-            const float q[4] = {u[0] / d, u[1] / d, u[2] / d, u[3] / d};
+            const float d = fmaxf(nrm, 1e-12f), id_ = __fdividef(1.0f, d);
+            const float q[4] = {u[0] * id_, u[1] * id_, u[2] * id_, u[3] * id_};
             float R[9], S[6];
             quat_to_R(q[0], q[1], q[2], q[3], R);
             cov3d_from(s, s, s, cam.scale_modifier, R, S);
@@ -502,7 +507,7 @@ fused_preprocess_backward_kernel(const __grid_constant__ CamConst cam, int64_t N
             // F.normalize backward
             const float qd = q[0] * dq[0] + q[1] * dq[1] + q[2] * dq[2] + q[3] * dq[3];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) dqu[k] = nrm >= 1e-12f ? (dq[k] - q[k] * qd) / d : dq[k] / d;
+            for (int k = 0; k < 4; ++k) dqu[k] = nrm >= 1e-12f ? (dq[k] - q[k] * qd) * id_ : dq[k] * id_;
             pose_v[0] = gm[0]; pose_v[1] = gm[1]; pose_v[2] = gm[2];
             pose_v[3] = gm[0] * px; pose_v[4] = gm[0] * py; pose_v[5] = gm[0] * pz;
             pose_v[6] = gm[1] * px; pose_v[7] = gm[1] * py; pose_v[8] = gm[1] * pz;

@@ -53,10 +53,20 @@ __device__ __forceinline__ void load_chunk(ChunkRegs& r, bool valid, const GeomR
     }
 }
 
-// Bounding box of the alpha >= 1/255 ellipse against this warp's 8x4-pixel region.
+// Shape of a warp's pixel region: REGION_W x REGION_H = 32 pixels, lane l = pixel (l % REGION_W, l / REGION_W).
+// A 16x16 tile holds (16 / REGION_W) x (16 / REGION_H) = 8 regions, one per warp.
+#ifndef VTGS_REGION_W
+#define VTGS_REGION_W 8
+#endif
+constexpr int REGION_W = VTGS_REGION_W;
+constexpr int REGION_H = 32 / REGION_W;
+constexpr int REGIONS_X = 16 / REGION_W;
+static_assert(REGION_W * REGION_H == 32 && 16 % REGION_W == 0 && 16 % REGION_H == 0, "region must tile 16x16 with 32 pixels");
+
+// Bounding box of the alpha >= 1/255 ellipse against this warp's pixel region.
 __device__ __forceinline__ bool region_hit(const ChunkRegs& r, float x0f, float y0f) {
-    return (r.q0.x + r.q1.w >= x0f) && (r.q0.x - r.q1.w <= x0f + 7.0f) &&
-           (r.q0.y + r.q3.y >= y0f) && (r.q0.y - r.q3.y <= y0f + 3.0f);
+    return (r.q0.x + r.q1.w >= x0f) && (r.q0.x - r.q1.w <= x0f + (float)(REGION_W - 1)) &&
+           (r.q0.y + r.q3.y >= y0f) && (r.q0.y - r.q3.y <= y0f + (float)(REGION_H - 1));
 }
 
 // 32x32 bit-matrix transpose across the warp: on entry lane e holds row e (bit p = column p),
@@ -82,22 +92,22 @@ __device__ __forceinline__ uint32_t warp_transpose_bits(uint32_t x, int lane) {
 // splats of the group that may contribute to it.
 __device__ __forceinline__ uint32_t p1_masks(bool have, const float4 q0, const float4 q1, float pthr, float x0f, float y0f,
                                              int lane, uint32_t& emask) {
-    float dx[8], u[8], v[8], dy[4], wq[4];
+    float dx[REGION_W], u[REGION_W], v[REGION_W], dy[REGION_H], wq[REGION_H];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
+    for (int c = 0; c < REGION_W; ++c) {
         dx[c] = fsub(q0.x, x0f + (float)c);
         u[c] = fmul(q1.x, dx[c]);
         v[c] = fmul(q1.y, dx[c]);
     }
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
+    for (int r = 0; r < REGION_H; ++r) {
         dy[r] = fsub(q0.y, y0f + (float)r);
         wq[r] = fmul(fmul(q1.z, dy[r]), dy[r]);
     }
     uint32_t em = 0;
 #pragma unroll
     for (int p = 0; p < 32; ++p) {
-        const int c = p & 7, r = p >> 3;
+        const int c = p % REGION_W, r = p / REGION_W;
         const float q = ffma(u[c], dx[c], wq[r]);
         const float pw = ffma(-0.5f, q, -fmul(v[c], dy[r]));
         if (pw <= 0.0f && pw >= pthr) em |= 1u << p;

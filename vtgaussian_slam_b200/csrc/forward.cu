@@ -273,6 +273,76 @@ __device__ __forceinline__ void bitonic_network(uint64_t* __restrict__ s, int n,
     }
 }
 
+// Register-resident bitonic sort of up to 256*E keys by one 256-thread block: thread t holds the E
+// consecutive elements [t*E, t*E+E).  Exchange distance j < E stays inside a thread, E <= j < 32E is
+// a warp shuffle, only the three largest distances go through shared memory (6 barriers-pairs for
+// 1024 keys instead of 55).  Unused slots hold ~0 (sorts last).
+template <int E>
+__device__ __forceinline__ void bitonic_regs(uint64_t (&v)[E], uint64_t* __restrict__ s_x, int tid, int npad) {
+    for (int k = 2; k <= npad; k <<= 1) {
+        const bool asc_t = ((tid * E) & k) == 0;                         // direction of this thread's run when k >= E
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j < E) {
+#pragma unroll
+                for (int jj = E / 2; jj >= 1; jj >>= 1) {               // compile-time distance: registers stay registers
+                    if (j != jj) continue;
+#pragma unroll
+                    for (int e = 0; e < E; ++e) {
+                        if ((e & jj) == 0) {
+                            const bool asc = k >= E ? asc_t : ((e & k) == 0);
+                            const uint64_t a = v[e], b = v[e | jj];
+                            const bool sw = (a > b) == asc;
+                            v[e] = sw ? b : a;
+                            v[e | jj] = sw ? a : b;
+                        }
+                    }
+                }
+            } else if (j < 32 * E) {
+                const int tm = j / E;                                   // lane bit
+                const bool lower = (tid & tm) == 0;
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const uint64_t o = __shfl_xor_sync(VTGS_FULL_MASK, v[e], tm);
+                    const bool take_min = lower == asc_t;
+                    v[e] = ((o < v[e]) == take_min) ? o : v[e];
+                }
+            } else {
+                const int tm = j / E;                                   // warp bit
+                const bool lower = (tid & tm) == 0;
+                __syncthreads();
+#pragma unroll
+                for (int e = 0; e < E; ++e) s_x[e * 256 + tid] = v[e];   // [e][tid]: conflict-free
+                __syncthreads();
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const uint64_t o = s_x[e * 256 + (tid ^ tm)];
+                    const bool take_min = lower == asc_t;
+                    v[e] = ((o < v[e]) == take_min) ? o : v[e];
+                }
+            }
+        }
+    }
+}
+
+template <int E>
+__device__ __forceinline__ void sort_segment_regs(uint64_t* __restrict__ s_x, uint64_t* __restrict__ keys, uint32_t* __restrict__ ids,
+                                                  int n, int tid) {
+    uint64_t v[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const int i = tid * E + e;
+        v[e] = i < n ? keys[i] : ~0ull;
+    }
+    int npad = 2 * E;                       // at least one cross-thread stage keeps the code uniform
+    while (npad < n) npad <<= 1;
+    bitonic_regs<E>(v, s_x, tid, npad);
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const int i = tid * E + e;
+        if (i < n) { keys[i] = v[e]; ids[i] = (uint32_t)v[e]; }
+    }
+}
+
 __global__ void __launch_bounds__(256)
 tile_sort_kernel(const uint32_t* __restrict__ ranges, int tile0, uint64_t* __restrict__ pair_keys,
                  uint32_t* __restrict__ point_list) {
@@ -281,6 +351,9 @@ tile_sort_kernel(const uint32_t* __restrict__ ranges, int tile0, uint64_t* __res
     const uint32_t b = ranges[2 * tile], e = ranges[2 * tile + 1];
     const int n = (int)(e - b);
     if (n <= 0) return;
+    if (n <= 512) { sort_segment_regs<2>(s_keys, pair_keys + b, point_list + b, n, threadIdx.x); return; }
+    if (n <= 1024) { sort_segment_regs<4>(s_keys, pair_keys + b, point_list + b, n, threadIdx.x); return; }
+    if (n <= 2048) { sort_segment_regs<8>(s_keys, pair_keys + b, point_list + b, n, threadIdx.x); return; }
     int npad = 2;
     while (npad < n) npad <<= 1;
     if (n <= SORT_SMEM_ELEMS) {
@@ -318,8 +391,8 @@ blend_forward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __res
     const int tile_x = tile % cam.gx, tile_y = tile / cam.gx;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     WarpQueue& Q = Qs[warp];
-    const int rx0 = tile_x * 16 + (warp & 1) * 8, ry0 = tile_y * 16 + (warp >> 1) * 4;
-    const int pix_x = rx0 + (lane & 7), pix_y = ry0 + (lane >> 3);
+    const int rx0 = tile_x * 16 + (warp % REGIONS_X) * REGION_W, ry0 = tile_y * 16 + (warp / REGIONS_X) * REGION_H;
+    const int pix_x = rx0 + (lane % REGION_W), pix_y = ry0 + (lane / REGION_W);
     const bool inside = pix_x < cam.W && pix_y < cam.H;
     const float pxf = (float)pix_x, pyf = (float)pix_y;
     const float x0f = (float)rx0, y0f = (float)ry0;
