@@ -271,21 +271,39 @@ def run_ours(args, wl):
                cam_unnorm_rots=0.0004, cam_trans=0.002)                  # configs/replica/room0.py:78-86
     opt = slam_ops.initialize_optimizer(P_, lrs, tracking=True)
     variables = dict(max_2D_radius=torch.zeros(N, device=dev))
-    data = dict(cam=settings, im=torch.empty((3, H, W), device=dev), depth=torch.empty((1, H, W), device=dev),
-                w2c=torch.eye(4, device=dev))
+    # double-buffered frame upload: the H2D copy of step k+1's inputs runs on a copy stream while step k computes
+    # (every step's inputs are still copied from pinned host memory inside the timed region)
+    bufs = [dict(im=torch.empty((3, H, W), device=dev), depth=torch.empty((1, H, W), device=dev), ev=torch.cuda.Event())
+            for _ in range(2)]
+    copy_stream = torch.cuda.Stream(dev)
+    w2c_eye = torch.eye(4, device=dev)
     loss_host = torch.zeros(1).pin_memory()
+    state = {"k": 0}
+
+    def upload(slot):
+        b = bufs[slot]
+        with torch.cuda.stream(copy_stream):
+            b["im"].copy_(gt_rgb, non_blocking=True)           # H2D of a step's inputs (pinned)
+            b["depth"].copy_(gt_depth, non_blocking=True)
+            b["ev"].record(copy_stream)
 
     def e2e_step():
-        data["im"].copy_(gt_rgb, non_blocking=True)            # H2D of the step's inputs (pinned)
-        data["depth"].copy_(gt_depth, non_blocking=True)
+        k = state["k"]
+        cur = bufs[k & 1]
+        torch.cuda.current_stream(dev).wait_event(cur["ev"])   # this step's inputs have landed
+        copy_stream.wait_stream(torch.cuda.current_stream(dev))  # the other buffer's previous consumer is queued before the copy
+        data = dict(cam=settings, im=cur["im"], depth=cur["depth"], w2c=w2c_eye)
         loss, _, _ = slam_ops.get_loss(P_, data, variables, 0, LOSS_W, True, SIL_THRES, True, False, tracking=True,
                                        dataset_name="tum", backend="fused")
+        upload((k + 1) & 1)                                    # prefetch the next step's inputs
         loss.backward()
         opt.step()
         opt.zero_grad(set_to_none=True)
         loss_host.copy_(loss.detach().reshape(1), non_blocking=False)      # D2H of the step's result
+        state["k"] = k + 1
         return loss_host
 
+    upload(0)
     e2e = None
     if world == 1:
         for _ in range(3):

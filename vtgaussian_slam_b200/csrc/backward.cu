@@ -13,6 +13,8 @@
 // warp with a transposed butterfly (~4 instructions per value instead of 10), adds the
 // warp total to a per-tile shared-memory accumulator, and the tile emits ONE vectorised
 // global reduction per (tile, Gaussian) pair at the end of each staged batch.
+#include <algorithm>
+
 #include "blend_common.cuh"
 #include "kernels.h"
 
@@ -445,45 +447,68 @@ int launch_pose_matrix(const VtgsPose* pose, VtgsCounters* counters, cudaStream_
 constexpr int POSE_TERMS = 12;       // sum g (3) and sum g p^T (9)
 
 // Fused K7': per-Gaussian parameter gradients + block partial sums of the pose terms.
-__global__ void __launch_bounds__(256, 4)
+// Persistent grid-stride kernel: every thread keeps the loads of its NEXT Gaussian in flight while it
+// works on the current one (the kernel is otherwise pure memory latency: ~190 B per Gaussian, a
+// ~700-instruction dependent chain only for the Gaussians that received gradient), accumulates the 12
+// pose terms in registers across its Gaussians and reduces them once at the end.
+struct K7Item {
+    float4 g0, g1, g2, uq;
+    float hx, op, px, py, pz, ls;
+};
+
+__device__ __forceinline__ void k7_load(K7Item& it, int64_t i, const VtgsParams& prm, const GeomRecord* __restrict__ geom,
+                                        const float* __restrict__ grad_geom, bool rot_aligned) {
+    const float4* gg = reinterpret_cast<const float4*>(grad_geom + (size_t)i * VTGS_GRAD_GEOM_FLOATS);
+    it.g0 = gg[0]; it.g1 = gg[1]; it.g2 = gg[2];
+    it.hx = geom[i].q1.w; it.op = geom[i].q0.w;
+    it.px = prm.means3D[3 * i]; it.py = prm.means3D[3 * i + 1]; it.pz = prm.means3D[3 * i + 2];
+    it.ls = prm.log_scales[i];
+    it.uq = rot_aligned ? reinterpret_cast<const float4*>(prm.unnorm_rotations)[i]
+                        : make_float4(prm.unnorm_rotations[4 * i], prm.unnorm_rotations[4 * i + 1],
+                                      prm.unnorm_rotations[4 * i + 2], prm.unnorm_rotations[4 * i + 3]);
+}
+
+__global__ void __launch_bounds__(256, 2)
 fused_preprocess_backward_kernel(const __grid_constant__ CamConst cam, int64_t N, VtgsParams prm,
                                  const float* __restrict__ pose_Rt, float dr0, float dr1, float dr2,
                                  const GeomRecord* __restrict__ geom, float* __restrict__ grad_geom,
                                  VtgsParamGrads out, int accumulate, int want_pose) {
     __shared__ float s_part[8][POSE_TERMS];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t i = (int64_t)blockIdx.x * 256 + tid;
+    const int64_t stride = (int64_t)gridDim.x * 256;
+    const bool rot_aligned = (reinterpret_cast<uintptr_t>(prm.unnorm_rotations) & 15) == 0;
+    float Rt[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) Rt[k] = __ldg(pose_Rt + k);
     float pose_v[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) pose_v[k] = 0.0f;
-    if (i < N) {
-        float4* gg = reinterpret_cast<float4*>(grad_geom + (size_t)i * VTGS_GRAD_GEOM_FLOATS);
-        const float4 g0 = gg[0], g1 = gg[1], g2 = gg[2];
-        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        gg[0] = zero4; gg[1] = zero4; gg[2] = zero4;
-        // every load is issued before the first use: one memory round trip per thread
-        const float rec_hx = geom[i].q1.w, rec_op = geom[i].q0.w;
-        const float px = prm.means3D[3 * i], py = prm.means3D[3 * i + 1], pz = prm.means3D[3 * i + 2];
-        const float ls = prm.log_scales[i];
-        const float4 uq = (reinterpret_cast<uintptr_t>(prm.unnorm_rotations) & 15) == 0
-                              ? reinterpret_cast<const float4*>(prm.unnorm_rotations)[i]
-                              : make_float4(prm.unnorm_rotations[4 * i], prm.unnorm_rotations[4 * i + 1],
-                                            prm.unnorm_rotations[4 * i + 2], prm.unnorm_rotations[4 * i + 3]);
-        float Rt[12];
-#pragma unroll
-        for (int k = 0; k < 12; ++k) Rt[k] = __ldg(pose_Rt + k);
+
+    int64_t i = (int64_t)blockIdx.x * 256 + tid;
+    K7Item nxt;
+    if (i < N) k7_load(nxt, i, prm, geom, grad_geom, rot_aligned);
+    for (; i < N; i += stride) {
+        const K7Item it = nxt;
+        if (i + stride < N) k7_load(nxt, i + stride, prm, geom, grad_geom, rot_aligned);
+        const float4 g0 = it.g0, g1 = it.g1, g2 = it.g2;
         // culled splats, and splats no pixel blended (all sums exactly zero), have zero gradients: every
         // term below is linear in g0..g2
         const bool any_grad = (g0.x != 0.f) | (g0.y != 0.f) | (g0.z != 0.f) | (g0.w != 0.f) | (g1.x != 0.f) | (g1.y != 0.f) |
                               (g1.z != 0.f) | (g1.w != 0.f) | (g2.x != 0.f) | (g2.y != 0.f);
-        const bool visible = rec_hx > -1e29f && any_grad;
+        if (any_grad) {                                   // leave the scratch zeroed for the next backward
+            float4* gg = reinterpret_cast<float4*>(grad_geom + (size_t)i * VTGS_GRAD_GEOM_FLOATS);
+            const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            gg[0] = zero4; gg[1] = zero4; gg[2] = zero4;
+        }
+        const bool visible = it.hx > -1e29f && any_grad;
         float dmeanw[3] = {0.f, 0.f, 0.f}, dls = 0.f, dlogit = 0.f, dqu[4] = {0.f, 0.f, 0.f, 0.f};
         if (visible) {
+            const float px = it.px, py = it.py, pz = it.pz;
             const float x = fadd(ffma(Rt[2], pz, ffma(Rt[1], py, fmul(Rt[0], px))), Rt[9]);
             const float y = fadd(ffma(Rt[5], pz, ffma(Rt[4], py, fmul(Rt[3], px))), Rt[10]);
             const float z = fadd(ffma(Rt[8], pz, ffma(Rt[7], py, fmul(Rt[6], px))), Rt[11]);
-            const float s = vexpf(ls);
-            float u[4] = {uq.x, uq.y, uq.z, uq.w};
+            const float s = vexpf(it.ls);
+            const float u[4] = {it.uq.x, it.uq.y, it.uq.z, it.uq.w};
             const float nrm = sqrtf(u[0] * u[0] + u[1] * u[1] + u[2] * u[2] + u[3] * u[3]);
             const float d = fmaxf(nrm, 1e-12f), id_ = __fdividef(1.0f, d);
             const float q[4] = {u[0] * id_, u[1] * id_, u[2] * id_, u[3] * id_};
@@ -502,16 +527,16 @@ fused_preprocess_backward_kernel(const __grid_constant__ CamConst cam, int64_t N
             dmeanw[1] = Rt[1] * gm[0] + Rt[4] * gm[1] + Rt[7] * gm[2];
             dmeanw[2] = Rt[2] * gm[0] + Rt[5] * gm[1] + Rt[8] * gm[2];
             dls = (dscale[0] + dscale[1] + dscale[2]) * s;            // d exp(ls)/d ls, tiled x3
-            const float o = rec_op;
+            const float o = it.op;
             dlogit = g1.y * o * (1.0f - o);
             // F.normalize backward
             const float qd = q[0] * dq[0] + q[1] * dq[1] + q[2] * dq[2] + q[3] * dq[3];
 #pragma unroll
             for (int k = 0; k < 4; ++k) dqu[k] = nrm >= 1e-12f ? (dq[k] - q[k] * qd) * id_ : dq[k] * id_;
-            pose_v[0] = gm[0]; pose_v[1] = gm[1]; pose_v[2] = gm[2];
-            pose_v[3] = gm[0] * px; pose_v[4] = gm[0] * py; pose_v[5] = gm[0] * pz;
-            pose_v[6] = gm[1] * px; pose_v[7] = gm[1] * py; pose_v[8] = gm[1] * pz;
-            pose_v[9] = gm[2] * px; pose_v[10] = gm[2] * py; pose_v[11] = gm[2] * pz;
+            pose_v[0] += gm[0]; pose_v[1] += gm[1]; pose_v[2] += gm[2];
+            pose_v[3] += gm[0] * px; pose_v[4] += gm[0] * py; pose_v[5] += gm[0] * pz;
+            pose_v[6] += gm[1] * px; pose_v[7] += gm[1] * py; pose_v[8] += gm[1] * pz;
+            pose_v[9] += gm[2] * px; pose_v[10] += gm[2] * py; pose_v[11] += gm[2] * pz;
         }
         if (accumulate) {
             if (out.means3D) { out.means3D[3 * i] += dmeanw[0]; out.means3D[3 * i + 1] += dmeanw[1]; out.means3D[3 * i + 2] += dmeanw[2]; }
@@ -603,7 +628,8 @@ int launch_fused_backward(const VtgsCamera* camera, const VtgsParams* params, co
     const int band_tiles = (cam.row1 - cam.row0) * cam.gx;
     const int want_pose = (grads->cam_unnorm_rot != nullptr && grads->cam_trans != nullptr) ? 1 : 0;
     if (want_pose && grads->pose_scratch == nullptr) { set_error("pose gradients need pose_scratch"); return VTGS_E_INVALID; }
-    const int blocks = (int)((N + 255) / 256);
+    // persistent K7' grid: 148 SMs x 2 resident blocks x 2 waves (fixed, so the partial-sum layout is deterministic)
+    const int blocks = (int)std::min<int64_t>((N + 255) / 256, 148 * 4);
     if (int e = ensure_bwd_smem()) return e;
     if (N > 0) {
         if (band_tiles > 0) {
