@@ -45,100 +45,110 @@ __device__ __forceinline__ void warp_tile_walk(int minx, int miny, int maxx, int
 }
 
 // =============================== K1': preprocess =========================================
-// One thread per Gaussian.  [N,3] arrays are staged through shared memory so that global
-// loads are unit-stride; rotations are float4 loads when 16-byte aligned.
+// Persistent grid-stride kernel, one Gaussian per thread per trip; the loads of the NEXT Gaussian are
+// in flight while the current one is projected (the math is ~1000 instructions of IEEE div / sqrt /
+// fp64 ndc2Pix per Gaussian, the loads ~48 B, the stores one 64-byte record).
+struct K1Item {
+    float x, y, z, c0, c1, c2, s0, s1, s2, op;
+    float4 q;
+};
+
 template <bool FUSED>
-__global__ void __launch_bounds__(256)
+__device__ __forceinline__ void k1_load(K1Item& it, int64_t i, int ls_dim, bool rot_aligned,
+                                        const float* __restrict__ means3D, const float* __restrict__ scales,
+                                        const float* __restrict__ rotations, const float* __restrict__ opacities,
+                                        const float* __restrict__ colors) {
+    it.x = means3D[3 * i]; it.y = means3D[3 * i + 1]; it.z = means3D[3 * i + 2];
+    it.c0 = colors[3 * i]; it.c1 = colors[3 * i + 1]; it.c2 = colors[3 * i + 2];
+    if (FUSED && ls_dim == 1) { it.s0 = scales[i]; it.s1 = it.s0; it.s2 = it.s0; }
+    else { it.s0 = scales[3 * i]; it.s1 = scales[3 * i + 1]; it.s2 = scales[3 * i + 2]; }
+    it.op = opacities[i];
+    it.q = rot_aligned ? reinterpret_cast<const float4*>(rotations)[i]
+                       : make_float4(rotations[4 * i], rotations[4 * i + 1], rotations[4 * i + 2], rotations[4 * i + 3]);
+}
+
+template <bool FUSED>
+__global__ void __launch_bounds__(256, 3)
 preprocess_kernel(const __grid_constant__ CamConst cam, int64_t N, FrontEnd fe,
                   const float* __restrict__ means3D, const float* __restrict__ scales,
                   const float* __restrict__ rotations, const float* __restrict__ opacities,
                   const float* __restrict__ colors,
                   GeomRecord* __restrict__ geom, int32_t* __restrict__ radii,
                   uint32_t* __restrict__ tiles_touched, uint32_t* __restrict__ tile_counts) {
-    __shared__ float s_a[256 * 3];
-    __shared__ float s_b[256 * 3];
-    __shared__ float s_c[256 * 3];
-    const int64_t base = (int64_t)blockIdx.x * 256;
     const int tid = threadIdx.x;
-    const int64_t i = base + tid;
-    const int64_t remain = N - base;
-    const int cnt3 = (int)(remain < 256 ? remain : 256) * 3;
-    for (int k = tid; k < cnt3; k += 256) {
-        s_a[k] = means3D[base * 3 + k];
-        s_c[k] = colors[base * 3 + k];
-        if (!FUSED || fe.log_scales_dim == 3) s_b[k] = scales[base * 3 + k];
-    }
-    __syncthreads();
-    int w_minx = 0, w_maxx = 0, w_miny = 0, w_maxy = 0;       // tile rect to count (empty when culled / out of range)
-    if (i < N) {
-    float x = s_a[3 * tid], y = s_a[3 * tid + 1], z = s_a[3 * tid + 2];
-    float sx, sy, sz, qr, qx, qy, qz, op, c3;
-    {
-        float4 q;
-        if ((reinterpret_cast<uintptr_t>(rotations) & 15) == 0) q = reinterpret_cast<const float4*>(rotations)[i];
-        else q = make_float4(rotations[4 * i], rotations[4 * i + 1], rotations[4 * i + 2], rotations[4 * i + 3]);
-        qr = q.x; qx = q.y; qy = q.z; qz = q.w;
-    }
+    const int64_t stride = (int64_t)gridDim.x * 256;
+    const bool rot_aligned = (reinterpret_cast<uintptr_t>(rotations) & 15) == 0;
+    float Rt[12];
     if (FUSED) {
-        // transform_to_frame + activations (reference utils/slam_helpers.py:323-385,127-160):
-        // p' = R p + t, scales = exp(log_scales), opacity = sigmoid(logit), q = normalize(q)
-        float Rt[12];
 #pragma unroll
         for (int k = 0; k < 12; ++k) Rt[k] = __ldg(fe.pose_Rt + k);
-        const float X = fadd(ffma(Rt[2], z, ffma(Rt[1], y, fmul(Rt[0], x))), Rt[9]);
-        const float Y = fadd(ffma(Rt[5], z, ffma(Rt[4], y, fmul(Rt[3], x))), Rt[10]);
-        const float Z = fadd(ffma(Rt[8], z, ffma(Rt[7], y, fmul(Rt[6], x))), Rt[11]);
-        x = X; y = Y; z = Z;
-        if (fe.log_scales_dim == 3) {
-            sx = vexpf(s_b[3 * tid]); sy = vexpf(s_b[3 * tid + 1]); sz = vexpf(s_b[3 * tid + 2]);
-        } else {
-            sx = sy = sz = vexpf(scales[i]);
+    }
+    int64_t i = (int64_t)blockIdx.x * 256 + tid;
+    K1Item nxt;
+    if (i < N) k1_load<FUSED>(nxt, i, fe.log_scales_dim, rot_aligned, means3D, scales, rotations, opacities, colors);
+    // whole warps loop together (the tile walk below is warp-collective)
+    for (int64_t wbase = i - (tid & 31); wbase < N; wbase += stride, i += stride) {
+        int w_minx = 0, w_maxx = 0, w_miny = 0, w_maxy = 0;       // tile rect to count (empty when culled / out of range)
+        if (i < N) {
+            const K1Item it = nxt;
+            if (i + stride < N) k1_load<FUSED>(nxt, i + stride, fe.log_scales_dim, rot_aligned, means3D, scales, rotations, opacities, colors);
+            float x = it.x, y = it.y, z = it.z;
+            float sx, sy, sz, qr = it.q.x, qx = it.q.y, qy = it.q.z, qz = it.q.w, op, c3;
+            if (FUSED) {
+                // transform_to_frame + activations (reference utils/slam_helpers.py:323-385,127-160):
+                // p' = R p + t, scales = exp(log_scales), opacity = sigmoid(logit), q = normalize(q)
+                const float X = fadd(ffma(Rt[2], z, ffma(Rt[1], y, fmul(Rt[0], x))), Rt[9]);
+                const float Y = fadd(ffma(Rt[5], z, ffma(Rt[4], y, fmul(Rt[3], x))), Rt[10]);
+                const float Z = fadd(ffma(Rt[8], z, ffma(Rt[7], y, fmul(Rt[6], x))), Rt[11]);
+                x = X; y = Y; z = Z;
+                if (fe.log_scales_dim == 3) { sx = vexpf(it.s0); sy = vexpf(it.s1); sz = vexpf(it.s2); }
+                else { sx = sy = sz = vexpf(it.s0); }
+                const float nrm = __fsqrt_rn(ffma(qz, qz, ffma(qy, qy, ffma(qx, qx, fmul(qr, qr)))));
+                const float d = fmaxf(nrm, 1e-12f);
+                qr = __fdiv_rn(qr, d); qx = __fdiv_rn(qx, d); qy = __fdiv_rn(qy, d); qz = __fdiv_rn(qz, d);
+                op = __fdiv_rn(1.0f, fadd(1.0f, vexpf(-it.op)));
+                // get_depth_and_silhouette (reference utils/slam_helpers.py:217-234): z of w2c * p'
+                c3 = fadd(ffma(fe.depth_row[2], z, ffma(fe.depth_row[1], y, fmul(fe.depth_row[0], x))), fe.depth_row[3]);
+            } else {
+                sx = it.s0; sy = it.s1; sz = it.s2;
+                op = it.op;
+                c3 = 0.0f;
+            }
+
+            SplatGeom g;
+            splat_geometry(cam, x, y, z, sx, sy, sz, qr, qx, qy, qz, g);
+            if (!FUSED) c3 = g.depth;
+
+            GeomRecord rec;
+            uint32_t tiles = 0;
+            if (g.radius > 0) {
+                const int miny = max(g.miny, cam.row0), maxy = min(g.maxy, cam.row1);
+                const int hgt = max(0, maxy - miny);
+                tiles = (uint32_t)((g.maxx - g.minx) * hgt);
+                float pthr, hx, hy;
+                cull_bounds(op, g.cov_a, g.cov_c, pthr, hx, hy);
+                rec.q0 = make_float4(g.px, g.py, pthr, op);
+                rec.q1 = make_float4(g.A, g.B, g.C, hx);
+                rec.q2 = make_float4(it.c0, it.c1, it.c2, c3);
+                rec.q3 = make_float4(g.depth, hy, __uint_as_float((uint32_t)g.minx | ((uint32_t)miny << 16)),
+                                     __uint_as_float((uint32_t)g.maxx | ((uint32_t)(hgt > 0 ? maxy : miny) << 16)));
+                w_minx = g.minx; w_maxx = g.maxx; w_miny = miny; w_maxy = hgt > 0 ? maxy : miny;
+            } else {
+                rec.q0 = make_float4(0.f, 0.f, 1.0f, 0.f);
+                rec.q1 = make_float4(0.f, 0.f, 0.f, -1e30f);
+                rec.q2 = make_float4(0.f, 0.f, 0.f, 0.f);
+                rec.q3 = make_float4(g.depth, -1e30f, __uint_as_float(0u), __uint_as_float(0u));
+            }
+            geom[i] = rec;
+            radii[i] = g.radius;
+            tiles_touched[i] = tiles;
         }
-        const float nrm = __fsqrt_rn(ffma(qz, qz, ffma(qy, qy, ffma(qx, qx, fmul(qr, qr)))));
-        const float d = fmaxf(nrm, 1e-12f);
-        qr = __fdiv_rn(qr, d); qx = __fdiv_rn(qx, d); qy = __fdiv_rn(qy, d); qz = __fdiv_rn(qz, d);
-        op = __fdiv_rn(1.0f, fadd(1.0f, vexpf(-opacities[i])));
-        // get_depth_and_silhouette (reference utils/slam_helpers.py:217-234): z of w2c * p'
-        c3 = fadd(ffma(fe.depth_row[2], z, ffma(fe.depth_row[1], y, fmul(fe.depth_row[0], x))), fe.depth_row[3]);
-    } else {
-        sx = s_b[3 * tid]; sy = s_b[3 * tid + 1]; sz = s_b[3 * tid + 2];
-        op = opacities[i];
-        c3 = 0.0f;
+        // per-tile histogram, warp-aggregated: neighbouring Gaussians (neighbouring pixels of a view-tied
+        // section) touch the same tiles, so one atomic per distinct tile per warp step instead of one per lane
+        warp_tile_walk(w_minx, w_miny, w_maxx, w_maxy, cam.gx, [&](int tile, uint32_t peers, int /*rank*/, bool leader) {
+            if (leader) atomicAdd(&tile_counts[tile], (uint32_t)__popc(peers));
+        });
     }
-
-    SplatGeom g;
-    splat_geometry(cam, x, y, z, sx, sy, sz, qr, qx, qy, qz, g);
-    if (!FUSED) c3 = g.depth;
-
-    GeomRecord rec;
-    uint32_t tiles = 0;
-    if (g.radius > 0) {
-        const int miny = max(g.miny, cam.row0), maxy = min(g.maxy, cam.row1);
-        const int hgt = max(0, maxy - miny);
-        tiles = (uint32_t)((g.maxx - g.minx) * hgt);
-        float pthr, hx, hy;
-        cull_bounds(op, g.cov_a, g.cov_c, pthr, hx, hy);
-        rec.q0 = make_float4(g.px, g.py, pthr, op);
-        rec.q1 = make_float4(g.A, g.B, g.C, hx);
-        rec.q2 = make_float4(s_c[3 * tid], s_c[3 * tid + 1], s_c[3 * tid + 2], c3);
-        rec.q3 = make_float4(g.depth, hy, __uint_as_float((uint32_t)g.minx | ((uint32_t)miny << 16)),
-                             __uint_as_float((uint32_t)g.maxx | ((uint32_t)(hgt > 0 ? maxy : miny) << 16)));
-        w_minx = g.minx; w_maxx = g.maxx; w_miny = miny; w_maxy = hgt > 0 ? maxy : miny;
-    } else {
-        rec.q0 = make_float4(0.f, 0.f, 1.0f, 0.f);
-        rec.q1 = make_float4(0.f, 0.f, 0.f, -1e30f);
-        rec.q2 = make_float4(0.f, 0.f, 0.f, 0.f);
-        rec.q3 = make_float4(g.depth, -1e30f, __uint_as_float(0u), __uint_as_float(0u));
-    }
-    geom[i] = rec;
-    radii[i] = g.radius;
-    tiles_touched[i] = tiles;
-    }
-    // per-tile histogram, warp-aggregated: neighbouring Gaussians (neighbouring pixels of a view-tied
-    // section) touch the same tiles, so one atomic per distinct tile per warp step instead of one per lane
-    warp_tile_walk(w_minx, w_miny, w_maxx, w_maxy, cam.gx, [&](int tile, uint32_t peers, int /*rank*/, bool leader) {
-        if (leader) atomicAdd(&tile_counts[tile], (uint32_t)__popc(peers));
-    });
 }
 
 // =============================== K2'/K5a': tile scan = tile ranges =========================
@@ -529,11 +539,12 @@ int launch_forward(const VtgsCamera* camera, int64_t N, bool fused, const FrontE
     GeomRecord* geom = reinterpret_cast<GeomRecord*>(buf->geom);
     VTGS_CUDA_CHECK(cudaMemsetAsync(buf->tile_counts, 0, sizeof(uint32_t) * num_tiles, stream));
     const int blocks = (int)((N + 255) / 256);
+    const int k1_blocks = blocks < 148 * 6 ? blocks : 148 * 6;          // persistent: 3 resident blocks per SM x 2 waves
     if (N > 0) {
         if (fused)
-            { VTGS_PROF("preprocess_kernel", stream); preprocess_kernel<true><<<blocks, 256, 0, stream>>>(cam, N, fe, means3D, scales, rotations, opacities, colors,
+            { VTGS_PROF("preprocess_kernel", stream); preprocess_kernel<true><<<k1_blocks, 256, 0, stream>>>(cam, N, fe, means3D, scales, rotations, opacities, colors,
                                                                  geom, radii, buf->tiles_touched, buf->tile_counts); }
-        else { VTGS_PROF("preprocess_kernel", stream); preprocess_kernel<false><<<blocks, 256, 0, stream>>>(cam, N, fe, means3D, scales, rotations, opacities, colors,
+        else { VTGS_PROF("preprocess_kernel", stream); preprocess_kernel<false><<<k1_blocks, 256, 0, stream>>>(cam, N, fe, means3D, scales, rotations, opacities, colors,
                                                                   geom, radii, buf->tiles_touched, buf->tile_counts); }
         VTGS_LAUNCH_CHECK();
     }
