@@ -345,6 +345,59 @@ def run_ours(args, wl):
         dist.destroy_process_group()
 
 
+def run_mapping(args, wl):
+    """configs[2]-shaped side benchmark (NOT the driver's default line): keyframe-sharded mapping.  Every rank
+    renders ONE keyframe of the same section per step (fused six-plane render, SSIM mapping loss, backward to
+    the Gaussian parameters), the parameter gradients are all-reduced (NCCL) and a replicated Adam step follows.
+    value = keyframe fwd+bwd iterations/s over all ranks ("weak" scaling: one keyframe per GPU)."""
+    import torch
+    import torch.distributed as dist
+    from vtgaussian_slam_b200 import synthetic
+    from vtgaussian_slam_b200.fused import MappingSolver
+    from vtgaussian_slam_b200.rasterizer import GaussianRasterizationSettings
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    pg = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        pg = dist.group.WORLD
+    fr, s = wl["frame"], wl["settings"]
+    W, H = fr["W"], fr["H"]
+    settings = GaussianRasterizationSettings(
+        image_height=H, image_width=W, tanfovx=s["tanfovx"], tanfovy=s["tanfovy"], bg=torch.tensor(s["bg"], device=dev),
+        scale_modifier=1.0, viewmatrix=torch.tensor(s["viewmatrix"], device=dev), projmatrix=torch.tensor(s["projmatrix"], device=dev),
+        sh_degree=0, campos=torch.tensor(s["campos"], device=dev), prefiltered=False)
+    params = {k: torch.tensor(v, device=dev) for k, v in wl["params"].items()}
+    ms = MappingSolver(settings, params, device=dev, process_group=pg)
+    q, t = synthetic.perturbed_pose(seed=100 + rank, trans_sigma=0.02, rot_deg=1.0)       # keyframe of this rank
+    kf = [dict(cam_q=torch.tensor(q, device=dev), cam_t=torch.tensor(t, device=dev),
+               gt_rgb=torch.tensor(fr["im"], device=dev), gt_depth=torch.tensor(fr["depth"], device=dev))]
+    for _ in range(max(args.warmup, 3)):
+        ms.iteration(kf)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        ms.iteration(kf)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms_t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        msps = ms_t.item() / args.steps
+        print(json.dumps({"metric": METRIC + " (mapping, keyframe-sharded)", "value": world * 1e3 / msps, "unit": UNIT, "n_gpus": world,
+                          "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": msps, "higher_is_better": True,
+                          "scaling": "weak", "dtype": "fp32", "data": "synthetic",
+                          "config": {"workload": wl["name"].replace("tracking", "mapping"), "keyframes_per_step": world,
+                                     "collective": "all-reduce(SUM) of dL/d{rgb, logit_opacity, log_scale} = 5 N fp32 + loss"}}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -353,12 +406,17 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--small", action="store_true", help="300x170 debug workload")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--mode", default="tracking", choices=["tracking", "mapping"],
+                    help="tracking = configs[1] (the driver's line); mapping = keyframe-sharded side benchmark")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     if args.impl == "reference":
         if rank != 0:
             return
         run_reference_arm(args, build_workload(args.small))
+        return
+    if args.mode == "mapping":
+        run_mapping(args, build_workload(args.small))
         return
     run_ours(args, build_workload(args.small))
 

@@ -568,7 +568,7 @@ int launch_forward(const VtgsCamera* camera, int64_t N, bool fused, const FrontE
         else { VTGS_PROF("blend_forward_kernel", stream); blend_forward_kernel<false><<<band_tiles, 256, 0, stream>>>(cam, buf->tile_ranges, buf->point_list, geom, out_color, out_depth, buf->final_T, buf->n_contrib); }
         VTGS_LAUNCH_CHECK();
     }
-    if (band_tiles < num_tiles) {
+    if (band_tiles < num_tiles && !fused) {       // API mode returns complete planes; the fused solvers only ever read their band
         const size_t P = (size_t)cam.W * cam.H;
         { VTGS_PROF("fill_outside_band_kernel", stream); fill_outside_band_kernel<<<(unsigned)((P + 255) / 256), 256, 0, stream>>>(cam, fused ? 6 : 3, out_color, out_depth, buf->final_T, buf->n_contrib); }
         VTGS_LAUNCH_CHECK();

@@ -279,12 +279,18 @@ class MappingSolver:
         self.r = FusedRenderer(settings, N, device=self.device, pair_capacity=pair_capacity)
         self.lrs = dict(rgb_colors=0.0025, logit_opacities=0.05, log_scales=0.005) if lrs is None else dict(lrs)
         self.eps = eps
-        self.grads = {k: torch.zeros_like(self.params[k]) for k in self.lrs}
+        # one flat gradient message (all learnable parameter gradients + the loss): a single all-reduce per step
+        sizes = {k: self.params[k].numel() for k in self.lrs}
+        self.flat = torch.zeros(sum(sizes.values()) + 1, dtype=torch.float32, device=self.device)
+        self.grads, off = {}, 0
+        for k, n in sizes.items():
+            self.grads[k] = self.flat[off:off + n].view(self.params[k].shape)
+            off += n
         self.m = {k: torch.zeros_like(self.params[k]) for k in self.lrs}
         self.v = {k: torch.zeros_like(self.params[k]) for k in self.lrs}
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.pg = process_group
-        self.total_loss = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self.total_loss = self.flat[-1:]
 
     def iteration(self, keyframes, loss_fn=None, w_im=1.0, w_depth=1.0):
         """keyframes: list of dict(cam_q, cam_t, gt_rgb, gt_depth) owned by THIS rank.  loss_fn=None uses the
@@ -304,10 +310,8 @@ class MappingSolver:
             for g in self.grads.values():
                 g.zero_()
         if self.pg is not None:
-            # keyframe sharding: all-reduce (SUM) the Gaussian-parameter gradients over NVLink
-            for k in self.grads:
-                torch.distributed.all_reduce(self.grads[k], group=self.pg)
-            torch.distributed.all_reduce(self.total_loss, group=self.pg)
+            # keyframe sharding: ONE all-reduce (SUM) of the flat gradient message over NVLink (5 N fp32 + loss)
+            torch.distributed.all_reduce(self.flat, group=self.pg)
         self.step_dev.add_(1)
         for k, lr in self.lrs.items():
             adam_step(self.params[k], self.grads[k], self.m[k], self.v[k], lr, step_dev=self.step_dev, eps=self.eps)
