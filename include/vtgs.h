@@ -114,8 +114,12 @@ typedef struct VtgsBuffers {
     uint32_t*     point_list;     /* [pair_capacity] sorted Gaussian ids                   */
     float*        final_T;        /* [H*W]                                                 */
     uint32_t*     n_contrib;      /* [H*W]                                                 */
-    float*        grad_geom;      /* [N][VTGS_GRAD_GEOM_FLOATS] scratch of backward        */
+    float*        grad_geom;      /* [N][VTGS_GRAD_GEOM_FLOATS] scratch of backward; must be zero on
+                                     entry to a backward and is left zeroed by it          */
     VtgsCounters* counters;       /* 1                                                     */
+    void*         region_pairs;   /* [8 * pair_capacity] uint32x2 {Gaussian id, 1-based position in the tile
+                                     list}: per-tile, per-8x4-pixel-region lists built by the sort kernel  */
+    uint32_t*     region_cnt;     /* [tiles][8] length of each region list                 */
     uint64_t      pair_capacity;
 } VtgsBuffers;
 
@@ -133,6 +137,8 @@ typedef struct VtgsWorkspaceSizes {
     uint64_t n_contrib_bytes;
     uint64_t grad_geom_bytes;
     uint64_t counters_bytes;
+    uint64_t region_pairs_bytes;
+    uint64_t region_cnt_bytes;
     uint32_t tiles_x;
     uint32_t tiles_y;
 } VtgsWorkspaceSizes;

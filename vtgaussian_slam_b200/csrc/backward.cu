@@ -69,9 +69,9 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[16], int lane)
 //   [0,1] dL/dmean2D (NDC-scaled)  [2,3,4] dL/dconic (xx, xy, yy)  [5] dL/dopacity
 //   [6..6+NCH) dL/dcolour  (API: r,g,b   fused: r,g,b,z)
 //
-// Block = one 16x16 tile, 8 independent warps (no block barrier), warp w = 8x4-pixel region.
-// Each warp walks the tile list BACK TO FRONT in chunks of 32 (prefetched gathers), box-culls,
-// queues survivors in its private ring and processes full groups of 32:
+// Block = one 16x16 tile, 8 independent warps (no block barrier), warp w = pixel region w.
+// Each warp walks ITS REGION'S LIST (built by the sort kernel) BACK TO FRONT in groups of 32
+// (prefetched gathers of the 64-byte records):
 //   P1 lane = splat : 32x32 "may contribute" bit matrix, transposed to the pixel lanes;
 //   P2 lane = pixel : back-to-front over ITS OWN splats: recompute alpha, unwind T, run the
 //                     accum recursion, and leave (w = alpha*T, g0 = G*dL/dalpha) in the
@@ -83,13 +83,14 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[16], int lane)
 template <bool FUSED>
 __global__ void __launch_bounds__(256, 2)
 blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __restrict__ ranges,
-                      const uint32_t* __restrict__ point_list, const GeomRecord* __restrict__ geom,
+                      const uint2* __restrict__ region_pairs, const uint32_t* __restrict__ region_cnt,
+                      const GeomRecord* __restrict__ geom,
                       const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
                       const float* __restrict__ dL_dpix, float* __restrict__ grad_geom) {
     constexpr int NCH = FUSED ? 4 : 3;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     struct WarpArea {
-        WarpQueue Q;
+        GroupSmem G;
         float2 cell[32][33];        // [splat of the group][pixel], padded row: (w, g0)
         float4 dpix[32];            // dL/dpixel of the region's pixels (r,g,b,z)
         float2 pxy[32];             // pixel centres of the region
@@ -100,13 +101,15 @@ blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __re
     const int tile_x = tile % cam.gx, tile_y = tile / cam.gx;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     WarpArea& A = areas[warp];
-    WarpQueue& Q = A.Q;
+    GroupSmem& G = A.G;
     const int rx0 = tile_x * 16 + (warp % REGIONS_X) * REGION_W, ry0 = tile_y * 16 + (warp / REGIONS_X) * REGION_H;
     const int pix_x = rx0 + (lane % REGION_W), pix_y = ry0 + (lane / REGION_W);
     const bool inside = pix_x < cam.W && pix_y < cam.H;
     const float pxf = (float)pix_x, pyf = (float)pix_y;
     const float x0f = (float)rx0, y0f = (float)ry0;
     const uint32_t rb = ranges[2 * tile], re = ranges[2 * tile + 1];
+    const int n = (int)region_cnt[(size_t)tile * 8 + warp];
+    const uint2* __restrict__ list = region_pairs + (size_t)8 * rb + (size_t)warp * (re - rb);
     const size_t P = (size_t)cam.W * cam.H;
     const size_t pid = (size_t)pix_y * cam.W + pix_x;
 
@@ -124,9 +127,7 @@ blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __re
     uint32_t todo = last;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) todo = max(todo, __shfl_xor_sync(VTGS_FULL_MASK, todo, o));
-    todo = min(todo, re - rb);
-    if (todo == 0) return;
-    __syncwarp();
+    if (todo == 0 || n == 0) return;
 
     float T = T_final;
     float accum[NCH], lastc[NCH];
@@ -134,18 +135,37 @@ blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __re
     for (int ch = 0; ch < NCH; ++ch) { accum[ch] = 0.0f; lastc[ch] = 0.0f; }
     float last_alpha = 0.0f;
 
-    auto process_group = [&](uint32_t head, int n) {
-        const bool have = lane < n;
-        const int slot = (head + (have ? lane : 0)) & 63;
-        const float4 e0 = Q.q0[slot], e1 = Q.q1[slot];
+    // group g (counted from the END of the list) holds list indices n-1-32g-l for lane l: ascending lane =
+    // descending list position
+    const int ngroups = (n + 31) >> 5;
+    auto idx_of = [&](int g) { return n - 1 - (g * 32 + lane); };
+    uint2 ent_next = idx_of(0) >= 0 ? list[idx_of(0)] : make_uint2(0u, 0u);
+    uint2 ent_next2 = idx_of(1) >= 0 ? list[idx_of(1)] : make_uint2(0u, 0u);
+    SplatRegs nxt;
+    // a group whose every position lies beyond `todo` is skipped without touching its records
+    bool nxt_live = __any_sync(VTGS_FULL_MASK, idx_of(0) >= 0 && ent_next.y <= todo);
+    if (nxt_live) load_splat(nxt, idx_of(0) >= 0, geom, ent_next);
+    for (int g = 0; g < ngroups; ++g) {
+        const SplatRegs cur = nxt;
+        const uint2 cur_ent = ent_next;
+        const bool cur_live = nxt_live;
+        const bool have = idx_of(g) >= 0;
+        ent_next = ent_next2;
+        ent_next2 = idx_of(g + 2) >= 0 ? list[idx_of(g + 2)] : make_uint2(0u, 0u);
+        nxt_live = __any_sync(VTGS_FULL_MASK, idx_of(g + 1) >= 0 && ent_next.y <= todo);
+        if (nxt_live) load_splat(nxt, idx_of(g + 1) >= 0, geom, ent_next);
+        if (!cur_live) continue;
+        __syncwarp();                                   // previous group's P3 reads are complete
+        if (have) { G.a[lane] = cur.a; G.b[lane] = cur.b; G.c[lane] = cur.c; }
+        __syncwarp();
         uint32_t emask;
-        uint32_t m = p1_masks(have, e0, e1, Q.pthr[slot], x0f, y0f, lane, emask);    // P1: lane = splat
-        // ---- P2: lane = pixel; ring order is back-to-front, so ascending bits = descending list position.
-        // Two splats per trip: loads / power / exp are independent, the T / accum recursion is ordered.
-        auto back_one = [&](const float4 q0, const float G, const int sl) -> float2 {
-            const float alpha = fminf(VTGS_ALPHA_MAX, fmul(q0.w, G));
+        uint32_t m = p1_masks(have, cur.a, cur.b, x0f, y0f, lane, emask);          // P1: lane = splat
+        // ---- P2: lane = pixel; ascending bits = descending list position.  Two splats per trip: loads /
+        // power / exp are independent, the T / accum recursion is ordered.
+        auto back_one = [&](const float4 q0, const float Gv, const int e) -> float2 {
+            const float alpha = fminf(VTGS_ALPHA_MAX, fmul(q0.w, Gv));
             if (__float_as_uint(q0.z) > last || alpha < VTGS_ALPHA_MIN) return make_float2(0.0f, 0.0f);
-            const float4 q2 = Q.q2[sl];
+            const float4 q2 = G.c[e];
             const float col[4] = {q2.x, q2.y, q2.z, q2.w};
             const float inv = __fdividef(1.0f, 1.0f - alpha);
             T = T * inv;
@@ -159,7 +179,7 @@ blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __re
             dL_dalpha *= T;
             last_alpha = alpha;
             dL_dalpha -= T_final * inv * bg_dot;
-            return make_float2(alpha * T, G * dL_dalpha);
+            return make_float2(alpha * T, Gv * dL_dalpha);
         };
         while (m) {
             const int ea = __ffs(m) - 1;
@@ -167,13 +187,12 @@ blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __re
             const bool two = m != 0;
             const int eb = two ? __ffs(m) - 1 : ea;
             m &= m - 1;
-            const int sa = (head + ea) & 63, sb = (head + eb) & 63;
-            const float4 a0 = Q.q0[sa], a1 = Q.q1[sa];
-            const float4 b0 = Q.q0[sb], b1 = Q.q1[sb];
+            const float4 a0 = G.a[ea], a1 = G.b[ea];
+            const float4 b0 = G.a[eb], b1 = G.b[eb];
             const float Ga = vexpf(power_of(a1.x, a1.y, a1.z, fsub(a0.x, pxf), fsub(a0.y, pyf)));
             const float Gb = vexpf(power_of(b1.x, b1.y, b1.z, fsub(b0.x, pxf), fsub(b0.y, pyf)));
-            A.cell[ea][lane] = back_one(a0, Ga, sa);
-            if (two) A.cell[eb][lane] = back_one(b0, Gb, sb);
+            A.cell[ea][lane] = back_one(a0, Ga, ea);
+            if (two) A.cell[eb][lane] = back_one(b0, Gb, eb);
         }
         __syncwarp();
         // ---- P3: lane = splat: reduce my row of cells
@@ -186,62 +205,26 @@ blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __re
             const float2 cw = A.cell[lane][p];
             const float4 dp = A.dpix[p];
             const float2 pc = A.pxy[p];
-            const float dx = e0.x - pc.x, dy = e0.y - pc.y;
+            const float dx = cur.a.x - pc.x, dy = cur.a.y - pc.y;
             c0 = fmaf(cw.x, dp.x, c0); c1 = fmaf(cw.x, dp.y, c1); c2 = fmaf(cw.x, dp.z, c2);
             if (NCH == 4) c3 = fmaf(cw.x, dp.w, c3);
-            const float g = cw.y, gx_ = g * dx, gy_ = g * dy;
-            s0 += g; sx += gx_; sy += gy_;
+            const float gg = cw.y, gx_ = gg * dx, gy_ = gg * dy;
+            s0 += gg; sx += gx_; sy += gy_;
             sxx = fmaf(gx_, dx, sxx); sxy = fmaf(gx_, dy, sxy); syy = fmaf(gy_, dy, syy);
         }
         // ---- P4: finalize (dL/dG * G = opacity * g0) and one vector reduction per (region, splat)
         if (emask) {
-            const float o = e0.w, ca = e1.x, cb = e1.y, cc = e1.z;
+            const float o = cur.a.w, ca = cur.b.x, cb = cur.b.y, cc = cur.b.z;
             const float v0 = -half_w * o * (ca * sx + cb * sy);
             const float v1 = -half_h * o * (cc * sy + cb * sx);
             const float v2 = -0.5f * o * sxx, v3 = -0.5f * o * sxy, v4 = -0.5f * o * syy;
-            float* dst = grad_geom + (size_t)Q.id[slot] * VTGS_GRAD_GEOM_FLOATS;
+            float* dst = grad_geom + (size_t)cur_ent.x * VTGS_GRAD_GEOM_FLOATS;
             asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v0), "f"(v1), "f"(v2), "f"(v3) : "memory");
             asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(v4), "f"(s0), "f"(c0), "f"(c1) : "memory");
             if (NCH == 4) asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(dst + 8), "f"(c2), "f"(c3) : "memory");
             else atomicAdd(dst + 8, c2);
         }
-        __syncwarp();
-    };
-
-    const uint32_t gt = ~((2u << lane) - 1u);        // lanes above me
-    uint32_t head = 0, count = 0;
-    const int cmax = (int)((todo - 1) >> 5);
-    // software pipeline (descending chunks): ids two chunks ahead, records one chunk ahead
-    auto pos_of = [&](int c) { return (uint32_t)(c * 32 + lane); };
-    uint32_t id_next = pos_of(cmax) < todo ? point_list[rb + pos_of(cmax)] : 0u;
-    uint32_t id_next2 = (cmax >= 1) ? point_list[rb + pos_of(cmax - 1)] : 0u;
-    ChunkRegs nxt;
-    load_chunk(nxt, pos_of(cmax) < todo, geom, id_next);
-    for (int c = cmax; c >= 0; --c) {
-        const ChunkRegs cur = nxt;
-        const uint32_t cur_id = id_next;
-        const uint32_t p = pos_of(c);
-        const bool valid = p < todo;
-        id_next = id_next2;
-        id_next2 = (c >= 2) ? point_list[rb + pos_of(c - 2)] : 0u;
-        load_chunk(nxt, c >= 1, geom, id_next);
-        const bool keep = valid && region_hit(cur, x0f, y0f);
-        const uint32_t b = __ballot_sync(VTGS_FULL_MASK, keep);
-        if (b == 0) continue;
-        if (keep) {
-            const int sl = (head + count + __popc(b & gt)) & 63;      // higher list positions first
-            queue_put(Q, sl, cur.q0, cur.q1, cur.q2, p + 1u);
-            Q.id[sl] = cur_id;
-        }
-        count += __popc(b);
-        __syncwarp();
-        if (count >= 32) {
-            process_group(head, 32);
-            head = (head + 32) & 63;
-            count -= 32;
-        }
     }
-    if (count > 0) process_group(head, (int)count);
 }
 
 // ---- shared pieces of K7' -------------------------------------------------------------------
@@ -359,7 +342,7 @@ preprocess_backward_kernel(const __grid_constant__ CamConst cam, int64_t N,
     // visible <=> the forward wrote a record with a non-empty full rect; q1.w (hx) = -1e30 marks culled
     // culled splats (and splats whose opacity can never reach alpha >= 1/255) carry hx = -1e30:
     // nothing was blended from them, every gradient is exactly zero
-    const bool visible = geom[i].q1.w > -1e29f;
+    const bool visible = geom[i].q0.z > -1e29f;
     (void)radii_or_null;
     dL_dmeans2D[3 * i] = g0.x; dL_dmeans2D[3 * i + 1] = g0.y; dL_dmeans2D[3 * i + 2] = 0.0f;
     dL_dcolors[3 * i] = g1.z; dL_dcolors[3 * i + 1] = g1.w; dL_dcolors[3 * i + 2] = g2.x;
@@ -383,8 +366,8 @@ preprocess_backward_kernel(const __grid_constant__ CamConst cam, int64_t N,
     for (int k = 0; k < 4; ++k) dL_drot[4 * i + k] = dq[k];
 }
 
-// dynamic shared memory of blend_backward_kernel: 8 x (ring 3584 + cells 8448 + dpix 512) bytes
-constexpr int BWD_SMEM = 8 * (int)(sizeof(WarpQueue) + 32 * 33 * sizeof(float2) + 32 * sizeof(float4) + 32 * sizeof(float2));
+// dynamic shared memory of blend_backward_kernel: 8 x (group 1536 + cells 8448 + dpix 512 + pxy 256) bytes
+constexpr int BWD_SMEM = 8 * (int)(sizeof(GroupSmem) + 32 * 33 * sizeof(float2) + 32 * sizeof(float4) + 32 * sizeof(float2));
 static int ensure_bwd_smem() {
     static bool done = false;
     if (!done) {
@@ -408,7 +391,7 @@ int launch_backward(const VtgsCamera* camera, int64_t N,
     if (N <= 0) return VTGS_OK;
     if (int e = ensure_bwd_smem()) return e;
     if (band_tiles > 0) {
-        { VTGS_PROF("blend_backward_kernel", stream); blend_backward_kernel<false><<<band_tiles, 256, BWD_SMEM, stream>>>(cam, buf->tile_ranges, buf->point_list, geom, buf->final_T,
+        { VTGS_PROF("blend_backward_kernel", stream); blend_backward_kernel<false><<<band_tiles, 256, BWD_SMEM, stream>>>(cam, buf->tile_ranges, reinterpret_cast<const uint2*>(buf->region_pairs), buf->region_cnt, geom, buf->final_T,
                                                                       buf->n_contrib, dL_dout_color, buf->grad_geom); }
         VTGS_LAUNCH_CHECK();
     }
@@ -460,7 +443,7 @@ __device__ __forceinline__ void k7_load(K7Item& it, int64_t i, const VtgsParams&
                                         const float* __restrict__ grad_geom, bool rot_aligned) {
     const float4* gg = reinterpret_cast<const float4*>(grad_geom + (size_t)i * VTGS_GRAD_GEOM_FLOATS);
     it.g0 = gg[0]; it.g1 = gg[1]; it.g2 = gg[2];
-    it.hx = geom[i].q1.w; it.op = geom[i].q0.w;
+    it.hx = geom[i].q0.z; it.op = geom[i].q1.w;
     it.px = prm.means3D[3 * i]; it.py = prm.means3D[3 * i + 1]; it.pz = prm.means3D[3 * i + 2];
     it.ls = prm.log_scales[i];
     it.uq = rot_aligned ? reinterpret_cast<const float4*>(prm.unnorm_rotations)[i]
@@ -633,7 +616,7 @@ int launch_fused_backward(const VtgsCamera* camera, const VtgsParams* params, co
     if (int e = ensure_bwd_smem()) return e;
     if (N > 0) {
         if (band_tiles > 0) {
-            { VTGS_PROF("blend_backward_kernel", stream); blend_backward_kernel<true><<<band_tiles, 256, BWD_SMEM, stream>>>(cam, buf->tile_ranges, buf->point_list, geom, buf->final_T,
+            { VTGS_PROF("blend_backward_kernel", stream); blend_backward_kernel<true><<<band_tiles, 256, BWD_SMEM, stream>>>(cam, buf->tile_ranges, reinterpret_cast<const uint2*>(buf->region_pairs), buf->region_cnt, geom, buf->final_T,
                                                                          buf->n_contrib, dL_dimage4, buf->grad_geom); }
             VTGS_LAUNCH_CHECK();
         }

@@ -1,4 +1,4 @@
-// blend_common.cuh -- staging, culling and the lane-transposed test phase shared by the
+// blend_common.cuh -- region lists and the lane-transposed test phase shared by the
 // forward (K5') and backward (K6') blend kernels.
 //
 // Geometry of a tile block: 256 threads = 8 warps; warp w owns the 8x4-pixel region
@@ -25,31 +25,28 @@
 
 namespace vtgs {
 
-// Per-warp ring of surviving splats (64 slots: < 32 pending + <= 32 appended per chunk).
-struct WarpQueue {
-    float4 q0[64];         // {px, py, bits(1-based position in the tile list), opacity}
-    float4 q1[64];         // {A, B, C, -}
-    float4 q2[64];         // colours
-    float pthr[64];        // conservative lower bound of power (read by P1 only)
-    uint32_t id[64];       // Gaussian id (backward)
+// One group of 32 splats staged for P2 (pixel lanes pick arbitrary splats of the group).
+struct GroupSmem {
+    float4 a[32];          // {px, py, bits(1-based position in the tile list), opacity}
+    float4 b[32];          // {A, B, C, pthr}
+    float4 c[32];          // colours
 };
 
-__device__ __forceinline__ void queue_put(WarpQueue& Q, int sl, const float4 q0, const float4 q1, const float4 q2, uint32_t pos1) {
-    Q.q0[sl] = make_float4(q0.x, q0.y, __uint_as_float(pos1), q0.w);
-    Q.q1[sl] = q1;
-    Q.q2[sl] = q2;
-    Q.pthr[sl] = q0.z;
-}
-
-// Prefetched chunk of 32 list entries: one entry per lane.
-struct ChunkRegs {
-    float4 q0, q1, q2, q3;
+// One entry of a region list, as registers of the lane that owns it in P1.
+struct SplatRegs {
+    float4 a, b, c;        // same packing as GroupSmem
 };
 
-__device__ __forceinline__ void load_chunk(ChunkRegs& r, bool valid, const GeomRecord* __restrict__ geom, uint32_t id) {
+// Region-list entry -> splat registers (gather of the 64-byte record; the 8 warps of a tile and the
+// neighbouring tiles share these lines through L1 / L2).
+__device__ __forceinline__ void load_splat(SplatRegs& r, bool valid, const GeomRecord* __restrict__ geom, uint2 ent) {
     if (valid) {
-        const GeomRecord* rec = geom + id;
-        r.q0 = rec->q0; r.q1 = rec->q1; r.q2 = rec->q2; r.q3 = rec->q3;
+        const GeomRecord* rec = geom + ent.x;
+        const float4 q0 = rec->q0, q1 = rec->q1;
+        r.c = rec->q2;
+        const float pthr = rec->q3.y;
+        r.a = make_float4(q0.x, q0.y, __uint_as_float(ent.y), q1.w);
+        r.b = make_float4(q1.x, q1.y, q1.z, pthr);
     }
 }
 
@@ -63,10 +60,19 @@ constexpr int REGION_H = 32 / REGION_W;
 constexpr int REGIONS_X = 16 / REGION_W;
 static_assert(REGION_W * REGION_H == 32 && 16 % REGION_W == 0 && 16 % REGION_H == 0, "region must tile 16x16 with 32 pixels");
 
-// Bounding box of the alpha >= 1/255 ellipse against this warp's pixel region.
-__device__ __forceinline__ bool region_hit(const ChunkRegs& r, float x0f, float y0f) {
-    return (r.q0.x + r.q1.w >= x0f) && (r.q0.x - r.q1.w <= x0f + (float)(REGION_W - 1)) &&
-           (r.q0.y + r.q3.y >= y0f) && (r.q0.y - r.q3.y <= y0f + (float)(REGION_H - 1));
+// Which of the tile's 8 regions the box of a splat's alpha >= 1/255 ellipse touches (bit r = region r).
+// tox, toy: pixel origin of the tile.
+__device__ __forceinline__ uint32_t region_mask(const float4 q0, float tox, float toy) {
+    const float x0 = q0.x - q0.z - tox, x1 = q0.x + q0.z - tox;
+    const float y0 = q0.y - q0.w - toy, y1 = q0.y + q0.w - toy;
+    uint32_t cm = 0, rmask = 0;
+#pragma unroll
+    for (int c = 0; c < REGIONS_X; ++c)
+        if (x1 >= (float)(c * REGION_W) && x0 <= (float)(c * REGION_W + REGION_W - 1)) cm |= 1u << c;
+#pragma unroll
+    for (int r = 0; r < 16 / REGION_H; ++r)
+        if (y1 >= (float)(r * REGION_H) && y0 <= (float)(r * REGION_H + REGION_H - 1)) rmask |= cm << (r * REGIONS_X);
+    return rmask;
 }
 
 // 32x32 bit-matrix transpose across the warp: on entry lane e holds row e (bit p = column p),
@@ -90,8 +96,9 @@ __device__ __forceinline__ uint32_t warp_transpose_bits(uint32_t x, int lane) {
 // emask: pixels of the region this splat may contribute to (power in [pthr, 0], in the spec'd
 // arithmetic -- the same `power` P2 recomputes).  pmask (returned): for this lane AS A PIXEL, the
 // splats of the group that may contribute to it.
-__device__ __forceinline__ uint32_t p1_masks(bool have, const float4 q0, const float4 q1, float pthr, float x0f, float y0f,
+__device__ __forceinline__ uint32_t p1_masks(bool have, const float4 q0, const float4 q1, float x0f, float y0f,
                                              int lane, uint32_t& emask) {
+    const float pthr = q1.w;
     float dx[REGION_W], u[REGION_W], v[REGION_W], dy[REGION_H], wq[REGION_H];
 #pragma unroll
     for (int c = 0; c < REGION_W; ++c) {

@@ -29,10 +29,12 @@ void set_error(const char* fmt, ...);
 #define VTGS_LAUNCH_CHECK() VTGS_CUDA_CHECK(cudaGetLastError())
 
 // ---- packed per-Gaussian render record (VTGS_GEOM_RECORD_BYTES = 64) ---------------------
-//   q0 = {px, py, pthr, opacity}     pthr: conservative lower bound of `power` for alpha >= 1/255
-//   q1 = {A, B, C, hx}               conic, half-extent of the alpha >= 1/255 ellipse in x
+//   q0 = {px, py, hx, hy}            pixel centre and the half extents of the alpha >= 1/255 ellipse's box
+//   q1 = {A, B, C, opacity}          conic and opacity
 //   q2 = {c0, c1, c2, c3}            colours; c3 = view depth (API mode) / z channel (fused mode)
-//   q3 = {depth, hy, rect_min, rect_max}   rect packed as x | y << 16 (band-clipped in y)
+//   q3 = {depth, pthr, rect_min, rect_max}   pthr: conservative lower bound of `power` for alpha >= 1/255;
+//                                    rect packed as x | y << 16 (band-clipped in y)
+// Culled splats carry hx = hy = -1e30 and pthr = 1 (never pass any test).
 struct __align__(16) GeomRecord {
     float4 q0, q1, q2, q3;
 };

@@ -127,17 +127,17 @@ preprocess_kernel(const __grid_constant__ CamConst cam, int64_t N, FrontEnd fe,
                 tiles = (uint32_t)((g.maxx - g.minx) * hgt);
                 float pthr, hx, hy;
                 cull_bounds(op, g.cov_a, g.cov_c, pthr, hx, hy);
-                rec.q0 = make_float4(g.px, g.py, pthr, op);
-                rec.q1 = make_float4(g.A, g.B, g.C, hx);
+                rec.q0 = make_float4(g.px, g.py, hx, hy);
+                rec.q1 = make_float4(g.A, g.B, g.C, op);
                 rec.q2 = make_float4(it.c0, it.c1, it.c2, c3);
-                rec.q3 = make_float4(g.depth, hy, __uint_as_float((uint32_t)g.minx | ((uint32_t)miny << 16)),
+                rec.q3 = make_float4(g.depth, pthr, __uint_as_float((uint32_t)g.minx | ((uint32_t)miny << 16)),
                                      __uint_as_float((uint32_t)g.maxx | ((uint32_t)(hgt > 0 ? maxy : miny) << 16)));
                 w_minx = g.minx; w_maxx = g.maxx; w_miny = miny; w_maxy = hgt > 0 ? maxy : miny;
             } else {
-                rec.q0 = make_float4(0.f, 0.f, 1.0f, 0.f);
-                rec.q1 = make_float4(0.f, 0.f, 0.f, -1e30f);
+                rec.q0 = make_float4(0.f, 0.f, -1e30f, -1e30f);
+                rec.q1 = make_float4(0.f, 0.f, 0.f, 0.f);
                 rec.q2 = make_float4(0.f, 0.f, 0.f, 0.f);
-                rec.q3 = make_float4(g.depth, -1e30f, __uint_as_float(0u), __uint_as_float(0u));
+                rec.q3 = make_float4(g.depth, 1.0f, __uint_as_float(0u), __uint_as_float(0u));
             }
             geom[i] = rec;
             radii[i] = g.radius;
@@ -353,146 +353,187 @@ __device__ __forceinline__ void sort_segment_regs(uint64_t* __restrict__ s_x, ui
     }
 }
 
+// After a tile's list is sorted: per-region lists.  Every (sorted) entry is tested once against the
+// tile's 8 warp regions (box of its alpha >= 1/255 ellipse) and appended, in list order, to the list of
+// every region it may touch as (Gaussian id, 1-based position in the tile list).  The blend kernels then
+// walk only their own region's list: the culling is done once per (tile, splat) here instead of once per
+// (warp, splat) in each of the two blend kernels.
+// Arena: region r of a tile with list [rb, re) owns slots [8 rb + r (re - rb), 8 rb + (r + 1)(re - rb)).
+__device__ __forceinline__ void build_region_lists(const uint32_t* __restrict__ ids, int n, uint32_t rb, int tile, float tox, float toy,
+                                                   const GeomRecord* __restrict__ geom, uint2* __restrict__ region_pairs,
+                                                   uint32_t* __restrict__ region_cnt, uint32_t* s_cnt /* [8][8] */, uint32_t* s_base /* [8] */) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < 8) s_base[tid] = 0;
+    __syncthreads();                                   // also orders the sorted ids written by other threads
+    const uint32_t lt = (1u << lane) - 1u;
+    for (int base = 0; base < n; base += 256) {
+        const int i = base + tid;
+        uint32_t rmask = 0, id = 0;
+        if (i < n) {
+            id = ids[i];
+            rmask = region_mask(geom[id].q0, tox, toy);
+        }
+        uint32_t bal[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            bal[r] = __ballot_sync(VTGS_FULL_MASK, (rmask >> r) & 1u);
+            if (lane == 0) s_cnt[r * 8 + warp] = __popc(bal[r]);
+        }
+        __syncthreads();
+        uint32_t pre = 0, tot = 0;
+        if (lane < 8) {
+#pragma unroll
+            for (int w = 0; w < 8; ++w) {
+                const uint32_t c = s_cnt[lane * 8 + w];
+                if (w < warp) pre += c;
+                tot += c;
+            }
+            pre += s_base[lane];
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const uint32_t p = __shfl_sync(VTGS_FULL_MASK, pre, r);
+            if ((rmask >> r) & 1u)
+                region_pairs[(size_t)8 * rb + (size_t)r * n + p + __popc(bal[r] & lt)] = make_uint2(id, (uint32_t)i + 1u);
+        }
+        __syncthreads();
+        if (warp == 0 && lane < 8) s_base[lane] += tot;
+        __syncthreads();
+    }
+    if (tid < 8) region_cnt[(size_t)tile * 8 + tid] = s_base[tid];
+}
+
 __global__ void __launch_bounds__(256)
-tile_sort_kernel(const uint32_t* __restrict__ ranges, int tile0, uint64_t* __restrict__ pair_keys,
-                 uint32_t* __restrict__ point_list) {
+tile_sort_kernel(const __grid_constant__ CamConst cam, const uint32_t* __restrict__ ranges, int tile0,
+                 uint64_t* __restrict__ pair_keys, uint32_t* __restrict__ point_list, const GeomRecord* __restrict__ geom,
+                 uint2* __restrict__ region_pairs, uint32_t* __restrict__ region_cnt) {
     extern __shared__ __align__(16) uint64_t s_keys[];
+    __shared__ uint32_t s_cnt[64];
+    __shared__ uint32_t s_base[8];
     const int tile = tile0 + blockIdx.x;
     const uint32_t b = ranges[2 * tile], e = ranges[2 * tile + 1];
     const int n = (int)(e - b);
-    if (n <= 0) return;
-    if (n <= 512) { sort_segment_regs<2>(s_keys, pair_keys + b, point_list + b, n, threadIdx.x); return; }
-    if (n <= 1024) { sort_segment_regs<4>(s_keys, pair_keys + b, point_list + b, n, threadIdx.x); return; }
-    if (n <= 2048) { sort_segment_regs<8>(s_keys, pair_keys + b, point_list + b, n, threadIdx.x); return; }
-    int npad = 2;
-    while (npad < n) npad <<= 1;
-    if (n <= SORT_SMEM_ELEMS) {
-        for (int i = threadIdx.x; i < n; i += blockDim.x) s_keys[i] = pair_keys[b + i];
-        __syncthreads();
-        bitonic_network(s_keys, n, npad);
-        for (int i = threadIdx.x; i < n; i += blockDim.x) {
-            const uint64_t k = s_keys[i];
-            point_list[b + i] = (uint32_t)k;
-            pair_keys[b + i] = k;
-        }
-    } else {
-        __syncthreads();
-        bitonic_network(pair_keys + b, n, npad);
-        for (int i = threadIdx.x; i < n; i += blockDim.x) point_list[b + i] = (uint32_t)pair_keys[b + i];
+    if (n <= 0) {
+        if (threadIdx.x < 8) region_cnt[(size_t)tile * 8 + threadIdx.x] = 0;
+        return;
     }
+    if (n <= 512) sort_segment_regs<2>(s_keys, pair_keys + b, point_list + b, n, threadIdx.x);
+    else if (n <= 1024) sort_segment_regs<4>(s_keys, pair_keys + b, point_list + b, n, threadIdx.x);
+    else if (n <= 2048) sort_segment_regs<8>(s_keys, pair_keys + b, point_list + b, n, threadIdx.x);
+    else {
+        int npad = 2;
+        while (npad < n) npad <<= 1;
+        if (n <= SORT_SMEM_ELEMS) {
+            for (int i = threadIdx.x; i < n; i += blockDim.x) s_keys[i] = pair_keys[b + i];
+            __syncthreads();
+            bitonic_network(s_keys, n, npad);
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                const uint64_t k = s_keys[i];
+                point_list[b + i] = (uint32_t)k;
+                pair_keys[b + i] = k;
+            }
+        } else {
+            __syncthreads();
+            bitonic_network(pair_keys + b, n, npad);
+            for (int i = threadIdx.x; i < n; i += blockDim.x) point_list[b + i] = (uint32_t)pair_keys[b + i];
+        }
+    }
+    const int tile_x = tile % cam.gx, tile_y = tile / cam.gx;
+    build_region_lists(point_list + b, n, b, tile, (float)(tile_x * 16), (float)(tile_y * 16), geom, region_pairs, region_cnt, s_cnt, s_base);
 }
 
 // =============================== K5': forward blend ========================================
-// Block = one 16x16 tile, 8 INDEPENDENT warps (no block barrier): warp w owns the 8x4-pixel region
-// (w&1, w>>1), walks the whole tile list in chunks of 32 (software-prefetched gathers of the 64-byte
-// records; the eight warps of a tile share them through L1), box-culls each chunk against its
-// region (lane = list entry), queues the survivors in a warp-private ring and blends them in full
-// groups of 32 with the lane-transposed scheme of blend_common.cuh.
+// Block = one 16x16 tile, 8 INDEPENDENT warps (no block barrier): warp w owns pixel region w and walks
+// that region's list (built by the sort kernel) in groups of 32 splats -- software-prefetched gathers of
+// the 64-byte records, lane-transposed blending (blend_common.cuh): P1 lane = splat from registers,
+// P2 lane = pixel from the group staged in shared memory.
 // Planes: API mode 3 colours (+ depth plane), fused mode r,g,b,z,sil,z^2.
 template <bool FUSED>
 __global__ void __launch_bounds__(256, 3)
 blend_forward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __restrict__ ranges,
-                     const uint32_t* __restrict__ point_list, const GeomRecord* __restrict__ geom,
+                     const uint2* __restrict__ region_pairs, const uint32_t* __restrict__ region_cnt,
+                     const GeomRecord* __restrict__ geom,
                      float* __restrict__ out_color, float* __restrict__ out_depth,
                      float* __restrict__ final_T, uint32_t* __restrict__ n_contrib) {
-    __shared__ WarpQueue Qs[8];
+    __shared__ GroupSmem Gs[8];
 
     const int tile = cam.row0 * cam.gx + blockIdx.x;
     const int tile_x = tile % cam.gx, tile_y = tile / cam.gx;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    WarpQueue& Q = Qs[warp];
+    GroupSmem& G = Gs[warp];
     const int rx0 = tile_x * 16 + (warp % REGIONS_X) * REGION_W, ry0 = tile_y * 16 + (warp / REGIONS_X) * REGION_H;
     const int pix_x = rx0 + (lane % REGION_W), pix_y = ry0 + (lane / REGION_W);
     const bool inside = pix_x < cam.W && pix_y < cam.H;
     const float pxf = (float)pix_x, pyf = (float)pix_y;
     const float x0f = (float)rx0, y0f = (float)ry0;
-    const uint32_t lt = (1u << lane) - 1u;
 
     const uint32_t rb = ranges[2 * tile], re = ranges[2 * tile + 1];
-    const uint32_t len = re - rb;
-    const int nchunks = (int)((len + 31) >> 5);
+    const int n = (int)region_cnt[(size_t)tile * 8 + warp];
+    const uint2* __restrict__ list = region_pairs + (size_t)8 * rb + (size_t)warp * (re - rb);
+    const int ngroups = (n + 31) >> 5;
 
     float T = 1.0f;
     float C0 = 0.f, C1 = 0.f, C2 = 0.f, C3 = 0.f, C4 = 0.f, C5 = 0.f;
     uint32_t last = 0;
     bool done = !inside;
 
-    // blend one group of `n` (<= 32) queued splats starting at ring slot `head`
-    auto process_group = [&](uint32_t head, int n) {
-        const bool have = lane < n;
-        const int slot = (head + (have ? lane : 0)) & 63;
+    auto blend_one = [&](const float4 a, const float alpha, const int e) -> bool {
+        if (alpha < VTGS_ALPHA_MIN) return true;
+        const float test_T = fmul(T, fsub(1.0f, alpha));
+        if (test_T < VTGS_T_MIN) { done = true; return false; }
+        const float4 q2 = G.c[e];
+        C0 = ffma(fmul(q2.x, alpha), T, C0);
+        C1 = ffma(fmul(q2.y, alpha), T, C1);
+        C2 = ffma(fmul(q2.z, alpha), T, C2);
+        C3 = ffma(fmul(q2.w, alpha), T, C3);
+        if (FUSED) {
+            C4 = ffma(alpha, T, C4);                               // 1.0 * alpha * T
+            C5 = ffma(fmul(fmul(q2.w, q2.w), alpha), T, C5);
+        }
+        T = test_T;
+        last = __float_as_uint(a.z);
+        return true;
+    };
+
+    // software pipeline: list entries two groups ahead, records one group ahead
+    uint2 ent_next = lane < n ? list[lane] : make_uint2(0u, 0u);
+    uint2 ent_next2 = (32 + lane) < n ? list[32 + lane] : make_uint2(0u, 0u);
+    SplatRegs nxt;
+    load_splat(nxt, lane < n, geom, ent_next);
+    bool all_done = __all_sync(VTGS_FULL_MASK, done);
+    for (int g = 0; g < ngroups && !all_done; ++g) {
+        const SplatRegs cur = nxt;
+        const int k = g * 32 + lane;
+        const bool have = k < n;
+        ent_next = ent_next2;
+        ent_next2 = (k + 64) < n ? list[k + 64] : make_uint2(0u, 0u);
+        load_splat(nxt, (k + 32) < n, geom, ent_next);
+        __syncwarp();                                   // the previous group's P2 reads are complete
+        if (have) { G.a[lane] = cur.a; G.b[lane] = cur.b; G.c[lane] = cur.c; }
+        __syncwarp();
         uint32_t emask;
-        uint32_t m = p1_masks(have, Q.q0[slot], Q.q1[slot], Q.pthr[slot], x0f, y0f, lane, emask);      // P1: lane = splat
+        uint32_t m = p1_masks(have, cur.a, cur.b, x0f, y0f, lane, emask);       // P1: lane = splat
         if (done) m = 0;
-        // P2: lane = pixel.  Two splats per trip: their loads / power / exp are independent, only the
-        // T and colour updates are ordered.
-        auto blend_one = [&](const float4 q0, const float alpha, const int sl) -> bool {
-            if (alpha < VTGS_ALPHA_MIN) return true;
-            const float test_T = fmul(T, fsub(1.0f, alpha));
-            if (test_T < VTGS_T_MIN) { done = true; return false; }
-            const float4 q2 = Q.q2[sl];
-            C0 = ffma(fmul(q2.x, alpha), T, C0);
-            C1 = ffma(fmul(q2.y, alpha), T, C1);
-            C2 = ffma(fmul(q2.z, alpha), T, C2);
-            C3 = ffma(fmul(q2.w, alpha), T, C3);
-            if (FUSED) {
-                C4 = ffma(alpha, T, C4);                               // 1.0 * alpha * T
-                C5 = ffma(fmul(fmul(q2.w, q2.w), alpha), T, C5);
-            }
-            T = test_T;
-            last = __float_as_uint(q0.z);
-            return true;
-        };
+        // P2: lane = pixel.  Two splats per trip: loads / power / exp are independent, only the T and
+        // colour updates are ordered.
         while (m) {
             const int ea = __ffs(m) - 1;
             m &= m - 1;
             const bool two = m != 0;
             const int eb = two ? __ffs(m) - 1 : ea;
             m &= m - 1;                                   // no-op when m == 0
-            const int sa = (head + ea) & 63, sb = (head + eb) & 63;
-            const float4 a0 = Q.q0[sa], a1 = Q.q1[sa];
-            const float4 b0 = Q.q0[sb], b1 = Q.q1[sb];
+            const float4 a0 = G.a[ea], a1 = G.b[ea];
+            const float4 b0 = G.a[eb], b1 = G.b[eb];
             // power is in [pthr, 0] by P1 (same arithmetic)
             const float pa = power_of(a1.x, a1.y, a1.z, fsub(a0.x, pxf), fsub(a0.y, pyf));
             const float pb = power_of(b1.x, b1.y, b1.z, fsub(b0.x, pxf), fsub(b0.y, pyf));
             const float alpha_a = fminf(VTGS_ALPHA_MAX, fmul(a0.w, vexpf(pa)));
             const float alpha_b = fminf(VTGS_ALPHA_MAX, fmul(b0.w, vexpf(pb)));
-            if (!blend_one(a0, alpha_a, sa)) break;
-            if (two && !blend_one(b0, alpha_b, sb)) break;
+            if (!blend_one(a0, alpha_a, ea)) break;
+            if (two && !blend_one(b0, alpha_b, eb)) break;
         }
-    };
-
-    uint32_t head = 0, count = 0;
-    // software pipeline: ids two chunks ahead, records one chunk ahead
-    uint32_t id_next = (uint32_t)lane < len ? point_list[rb + lane] : 0u;
-    uint32_t id_next2 = (uint32_t)(32 + lane) < len ? point_list[rb + 32 + lane] : 0u;
-    ChunkRegs nxt;
-    load_chunk(nxt, (uint32_t)lane < len, geom, id_next);
-    bool all_done = __all_sync(VTGS_FULL_MASK, done);
-    for (int c = 0; c < nchunks && !all_done; ++c) {
-        const ChunkRegs cur = nxt;
-        const uint32_t p = (uint32_t)(c * 32 + lane);
-        const bool valid = p < len;
-        id_next = id_next2;
-        id_next2 = (p + 64u) < len ? point_list[rb + p + 64u] : 0u;
-        load_chunk(nxt, (p + 32u) < len, geom, id_next);
-        const bool keep = valid && region_hit(cur, x0f, y0f);
-        const uint32_t b = __ballot_sync(VTGS_FULL_MASK, keep);
-        if (b == 0) continue;
-        if (keep) {
-            const int sl = (head + count + __popc(b & lt)) & 63;
-            queue_put(Q, sl, cur.q0, cur.q1, cur.q2, p + 1u);
-        }
-        count += __popc(b);
-        __syncwarp();
-        if (count >= 32) {
-            process_group(head, 32);
-            head = (head + 32) & 63;
-            count -= 32;
-            all_done = __all_sync(VTGS_FULL_MASK, done);
-        }
+        all_done = __all_sync(VTGS_FULL_MASK, done);
     }
-    if (count > 0 && !all_done) process_group(head, (int)count);
 
     if (inside) {
         const size_t P = (size_t)cam.W * cam.H;
@@ -559,13 +600,14 @@ int launch_forward(const VtgsCamera* camera, int64_t N, bool fused, const FrontE
             VTGS_CUDA_CHECK(cudaFuncSetAttribute(tile_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_SMEM_ELEMS * 8));
             attr_set = true;
         }
-        { VTGS_PROF("tile_sort_kernel", stream); tile_sort_kernel<<<band_tiles, 256, SORT_SMEM_ELEMS * 8, stream>>>(buf->tile_ranges, cam.row0 * cam.gx, buf->pair_keys, buf->point_list); }
+        { VTGS_PROF("tile_sort_kernel", stream); tile_sort_kernel<<<band_tiles, 256, SORT_SMEM_ELEMS * 8, stream>>>(cam, buf->tile_ranges, cam.row0 * cam.gx, buf->pair_keys, buf->point_list, geom, reinterpret_cast<uint2*>(buf->region_pairs), buf->region_cnt); }
         VTGS_LAUNCH_CHECK();
     }
+    if (N <= 0) VTGS_CUDA_CHECK(cudaMemsetAsync(buf->region_cnt, 0, sizeof(uint32_t) * 8 * num_tiles, stream));
     if (band_tiles > 0) {
         if (fused)
-            { VTGS_PROF("blend_forward_kernel", stream); blend_forward_kernel<true><<<band_tiles, 256, 0, stream>>>(cam, buf->tile_ranges, buf->point_list, geom, out_color, out_depth, buf->final_T, buf->n_contrib); }
-        else { VTGS_PROF("blend_forward_kernel", stream); blend_forward_kernel<false><<<band_tiles, 256, 0, stream>>>(cam, buf->tile_ranges, buf->point_list, geom, out_color, out_depth, buf->final_T, buf->n_contrib); }
+            { VTGS_PROF("blend_forward_kernel", stream); blend_forward_kernel<true><<<band_tiles, 256, 0, stream>>>(cam, buf->tile_ranges, reinterpret_cast<const uint2*>(buf->region_pairs), buf->region_cnt, geom, out_color, out_depth, buf->final_T, buf->n_contrib); }
+        else { VTGS_PROF("blend_forward_kernel", stream); blend_forward_kernel<false><<<band_tiles, 256, 0, stream>>>(cam, buf->tile_ranges, reinterpret_cast<const uint2*>(buf->region_pairs), buf->region_cnt, geom, out_color, out_depth, buf->final_T, buf->n_contrib); }
         VTGS_LAUNCH_CHECK();
     }
     if (band_tiles < num_tiles && !fused) {       // API mode returns complete planes; the fused solvers only ever read their band
@@ -600,7 +642,7 @@ __global__ void export_geom_kernel(int64_t N, const GeomRecord* __restrict__ geo
     const GeomRecord r = geom[i];
     if (means2D) { means2D[2 * i] = r.q0.x; means2D[2 * i + 1] = r.q0.y; }
     if (depths) depths[i] = r.q3.x;
-    if (conic_opacity) { conic_opacity[4 * i] = r.q1.x; conic_opacity[4 * i + 1] = r.q1.y; conic_opacity[4 * i + 2] = r.q1.z; conic_opacity[4 * i + 3] = r.q0.w; }
+    if (conic_opacity) { conic_opacity[4 * i] = r.q1.x; conic_opacity[4 * i + 1] = r.q1.y; conic_opacity[4 * i + 2] = r.q1.z; conic_opacity[4 * i + 3] = r.q1.w; }
 }
 
 int launch_export_geometry(int64_t N, const VtgsBuffers* buf, float* means2D, float* depths, float* conic_opacity, cudaStream_t stream) {

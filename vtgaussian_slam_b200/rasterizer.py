@@ -110,6 +110,8 @@ class Workspace:
         self.n_contrib = torch.empty((self.H, self.W), dtype=torch.int32, device=device)
         self.grad_geom = None
         self.counters = torch.zeros(sz.counters_bytes // 4, dtype=torch.int32, device=device)
+        self.region_cnt = torch.zeros(sz.region_cnt_bytes // 4, dtype=torch.int32, device=device)
+        self.region_pairs = None
         self.pair_capacity = 0
         self.pair_keys = self.point_list = None
         self.reserve_pairs(pair_capacity)
@@ -119,6 +121,7 @@ class Workspace:
         if cap > self.pair_capacity:
             self.pair_keys = torch.empty(cap, dtype=torch.int64, device=self.device)
             self.point_list = torch.empty(cap, dtype=torch.int32, device=self.device)
+            self.region_pairs = torch.empty((8 * cap, 2), dtype=torch.int32, device=self.device)
             self.pair_capacity = cap
 
     def ensure_grad_geom(self):
@@ -138,6 +141,8 @@ class Workspace:
         b.n_contrib = self.n_contrib.data_ptr()
         b.grad_geom = self.ensure_grad_geom().data_ptr()
         b.counters = self.counters.data_ptr()
+        b.region_pairs = self.region_pairs.data_ptr()
+        b.region_cnt = self.region_cnt.data_ptr()
         b.pair_capacity = self.pair_capacity
         return b
 
