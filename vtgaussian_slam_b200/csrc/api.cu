@@ -167,9 +167,12 @@ int vtgs_fused_forward(const VtgsCamera* cam, const VtgsParams* p, const VtgsPos
     if (int e = check_fused(cam, p, pose, buf)) return e;
     VTGS_REQUIRE(out_image6 != nullptr, "out_image6 is NULL");
     if (p->num_gaussians > 0) VTGS_REQUIRE(radii != nullptr, "radii is NULL");
-    if (int e = launch_pose_matrix(pose, buf->counters, (cudaStream_t)stream)) return e;
     FrontEnd fe{};
-    fe.pose_Rt = buf->counters->pose_R;
+    fe.cam_unnorm_rot = pose->cam_unnorm_rot;
+    fe.cam_trans = pose->cam_trans;
+    fe.counters = buf->counters;
+    if (p->num_gaussians <= 0)          // nothing to preprocess: still publish the pose for the backward
+        if (int e = launch_pose_matrix(pose, buf->counters, (cudaStream_t)stream)) return e;
     for (int k = 0; k < 4; ++k) fe.depth_row[k] = pose->depth_row[k];
     fe.log_scales_dim = p->log_scales_dim;
     return launch_forward(cam, p->num_gaussians, true, fe, p->means3D, p->log_scales, p->unnorm_rotations, p->logit_opacities,

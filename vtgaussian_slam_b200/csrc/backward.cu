@@ -408,17 +408,12 @@ int launch_backward(const VtgsCamera* camera, int64_t N,
 // build_rotation normalises once more.  Spec'd fp32 order, mirrored by the oracle.
 __global__ void pose_matrix_kernel(const float* __restrict__ q_un, const float* __restrict__ t, VtgsCounters* __restrict__ c) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    const float u0 = q_un[0], u1 = q_un[1], u2 = q_un[2], u3 = q_un[3];
-    const float n1 = __fsqrt_rn(ffma(u3, u3, ffma(u2, u2, ffma(u1, u1, fmul(u0, u0)))));
-    const float d1 = fmaxf(n1, 1e-12f);
-    const float q0 = __fdiv_rn(u0, d1), q1 = __fdiv_rn(u1, d1), q2 = __fdiv_rn(u2, d1), q3 = __fdiv_rn(u3, d1);
-    const float n2 = __fsqrt_rn(ffma(q3, q3, ffma(q2, q2, ffma(q1, q1, fmul(q0, q0)))));
-    float R[9];
-    quat_to_R(__fdiv_rn(q0, n2), __fdiv_rn(q1, n2), __fdiv_rn(q2, n2), __fdiv_rn(q3, n2), R);
-    for (int k = 0; k < 9; ++k) c->pose_R[k] = R[k];
-    c->pose_t[0] = t[0]; c->pose_t[1] = t[1]; c->pose_t[2] = t[2];
-    c->pose_q[0] = q0; c->pose_q[1] = q1; c->pose_q[2] = q2; c->pose_q[3] = q3;
-    c->pose_qnorm[0] = n1; c->pose_qnorm[1] = n2;
+    float Rt[12], qn[4], nrm2[2];
+    pose_from_quat(q_un, t, Rt, qn, nrm2);
+    for (int k = 0; k < 9; ++k) c->pose_R[k] = Rt[k];
+    for (int k = 0; k < 3; ++k) c->pose_t[k] = Rt[9 + k];
+    for (int k = 0; k < 4; ++k) c->pose_q[k] = qn[k];
+    c->pose_qnorm[0] = nrm2[0]; c->pose_qnorm[1] = nrm2[1];
 }
 
 int launch_pose_matrix(const VtgsPose* pose, VtgsCounters* counters, cudaStream_t stream) {
@@ -428,6 +423,56 @@ int launch_pose_matrix(const VtgsPose* pose, VtgsCounters* counters, cudaStream_
 }
 
 constexpr int POSE_TERMS = 12;       // sum g (3) and sum g p^T (9)
+
+// Deterministic final reduction of the block partials (fixed slice order, fp64) and the chain
+// dL/dR, dL/dt -> cam_unnorm_rot, cam_trans through build_rotation and the two normalisations.
+// Executed by the K7' block that finishes last (256 threads): no extra launch.
+__device__ __forceinline__ void pose_finalize_block(const float* __restrict__ partials, int nblocks,
+                                                    const VtgsCounters* __restrict__ c, float* __restrict__ d_rot,
+                                                    float* __restrict__ d_trans, int accumulate, double (*s_sum)[21]) {
+    constexpr int SLICES = 21;                    // 12 terms x 21 slices = 252 threads, coalesced reads
+    const int tid = threadIdx.x;
+    if (tid < POSE_TERMS * SLICES) {
+        const int term = tid % POSE_TERMS, sl = tid / POSE_TERMS;
+        double acc = 0.0;
+        for (int b = sl; b < nblocks; b += SLICES) acc += (double)__ldcg(&partials[(size_t)b * POSE_TERMS + term]);
+        s_sum[term][sl] = acc;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double tot[POSE_TERMS];
+        for (int k = 0; k < POSE_TERMS; ++k) {
+            double a = 0.0;
+            for (int l = 0; l < SLICES; ++l) a += s_sum[k][l];
+            tot[k] = a;
+        }
+        // D[r][k] = dL/dR[r][k] = sum g_r p_k
+        const double D[3][3] = {{tot[3], tot[4], tot[5]}, {tot[6], tot[7], tot[8]}, {tot[9], tot[10], tot[11]}};
+        const double n1 = c->pose_qnorm[0], n2 = c->pose_qnorm[1];
+        const double q[4] = {c->pose_q[0], c->pose_q[1], c->pose_q[2], c->pose_q[3]};
+        const double qq[4] = {q[0] / n2, q[1] / n2, q[2] / n2, q[3] / n2};
+        const double qr = qq[0], qx = qq[1], qy = qq[2], qz = qq[3];
+        double dqq[4];
+        dqq[0] = 2.0 * (qz * (D[1][0] - D[0][1]) + qy * (D[0][2] - D[2][0]) + qx * (D[2][1] - D[1][2]));
+        dqq[1] = 2.0 * (qy * (D[0][1] + D[1][0]) + qz * (D[0][2] + D[2][0]) + qr * (D[2][1] - D[1][2])) - 4.0 * qx * (D[1][1] + D[2][2]);
+        dqq[2] = 2.0 * (qx * (D[0][1] + D[1][0]) + qr * (D[0][2] - D[2][0]) + qz * (D[1][2] + D[2][1])) - 4.0 * qy * (D[0][0] + D[2][2]);
+        dqq[3] = 2.0 * (qr * (D[1][0] - D[0][1]) + qx * (D[0][2] + D[2][0]) + qy * (D[1][2] + D[2][1])) - 4.0 * qz * (D[0][0] + D[1][1]);
+        // qq = q / |q|
+        double dot = qq[0] * dqq[0] + qq[1] * dqq[1] + qq[2] * dqq[2] + qq[3] * dqq[3];
+        double dq[4];
+        for (int k = 0; k < 4; ++k) dq[k] = (dqq[k] - qq[k] * dot) / n2;
+        // q = u / max(|u|, eps)
+        const double d1 = n1 > 1e-12 ? n1 : 1e-12;
+        dot = q[0] * dq[0] + q[1] * dq[1] + q[2] * dq[2] + q[3] * dq[3];
+        for (int k = 0; k < 4; ++k) {
+            const double du = n1 >= 1e-12 ? (dq[k] - q[k] * dot) / d1 : dq[k] / d1;
+            if (accumulate) d_rot[k] += (float)du; else d_rot[k] = (float)du;
+        }
+        for (int k = 0; k < 3; ++k) {
+            if (accumulate) d_trans[k] += (float)tot[k]; else d_trans[k] = (float)tot[k];
+        }
+    }
+}
 
 // Fused K7': per-Gaussian parameter gradients + block partial sums of the pose terms.
 // Persistent grid-stride kernel: every thread keeps the loads of its NEXT Gaussian in flight while it
@@ -455,8 +500,11 @@ __global__ void __launch_bounds__(256, 2)
 fused_preprocess_backward_kernel(const __grid_constant__ CamConst cam, int64_t N, VtgsParams prm,
                                  const float* __restrict__ pose_Rt, float dr0, float dr1, float dr2,
                                  const GeomRecord* __restrict__ geom, float* __restrict__ grad_geom,
-                                 VtgsParamGrads out, int accumulate, int want_pose) {
+                                 VtgsParamGrads out, int accumulate, int want_pose,
+                                 const VtgsCounters* __restrict__ counters, unsigned int* __restrict__ ticket) {
     __shared__ float s_part[8][POSE_TERMS];
+    __shared__ double s_sum[POSE_TERMS][21];
+    __shared__ bool s_last;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t stride = (int64_t)gridDim.x * 256;
     const bool rot_aligned = (reinterpret_cast<uintptr_t>(prm.unnorm_rotations) & 15) == 0;
@@ -546,60 +594,15 @@ fused_preprocess_backward_kernel(const __grid_constant__ CamConst cam, int64_t N
 #pragma unroll
         for (int w = 0; w < 8; ++w) s += s_part[w][tid];
         out.pose_scratch[(size_t)blockIdx.x * POSE_TERMS + tid] = s;
-    }
-}
-
-// Deterministic final reduction of the block partials (fixed order, fp64) and the chain
-// dL/dR, dL/dt -> cam_unnorm_rot, cam_trans through build_rotation and the two normalisations.
-__global__ void __launch_bounds__(1024)
-pose_finalize_kernel(const float* __restrict__ partials, int nblocks, const VtgsCounters* __restrict__ c,
-                     float* __restrict__ d_rot, float* __restrict__ d_trans, int accumulate) {
-    constexpr int SLICES = 85;                    // 12 terms x 85 slices = 1020 threads, coalesced reads
-    __shared__ double s_sum[POSE_TERMS][SLICES];
-    __shared__ double s_tot[POSE_TERMS];
-    const int tid = threadIdx.x;
-    if (tid < POSE_TERMS * SLICES) {
-        const int term = tid % POSE_TERMS, sl = tid / POSE_TERMS;
-        double acc = 0.0;
-        for (int b = sl; b < nblocks; b += SLICES) acc += (double)partials[(size_t)b * POSE_TERMS + term];
-        s_sum[term][sl] = acc;
+        __threadfence();
     }
     __syncthreads();
-    if (tid < POSE_TERMS) {                       // fixed order: deterministic
-        double a = 0.0;
-        for (int l = 0; l < SLICES; ++l) a += s_sum[tid][l];
-        s_tot[tid] = a;
-    }
+    if (tid == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
     __syncthreads();
-    if (tid == 0) {
-        double tot[POSE_TERMS];
-        for (int k = 0; k < POSE_TERMS; ++k) tot[k] = s_tot[k];
-        // D[r][k] = dL/dR[r][k] = sum g_r p_k
-        const double D[3][3] = {{tot[3], tot[4], tot[5]}, {tot[6], tot[7], tot[8]}, {tot[9], tot[10], tot[11]}};
-        const double n1 = c->pose_qnorm[0], n2 = c->pose_qnorm[1];
-        const double q[4] = {c->pose_q[0], c->pose_q[1], c->pose_q[2], c->pose_q[3]};
-        const double qq[4] = {q[0] / n2, q[1] / n2, q[2] / n2, q[3] / n2};
-        const double qr = qq[0], qx = qq[1], qy = qq[2], qz = qq[3];
-        double dqq[4];
-        dqq[0] = 2.0 * (qz * (D[1][0] - D[0][1]) + qy * (D[0][2] - D[2][0]) + qx * (D[2][1] - D[1][2]));
-        dqq[1] = 2.0 * (qy * (D[0][1] + D[1][0]) + qz * (D[0][2] + D[2][0]) + qr * (D[2][1] - D[1][2])) - 4.0 * qx * (D[1][1] + D[2][2]);
-        dqq[2] = 2.0 * (qx * (D[0][1] + D[1][0]) + qr * (D[0][2] - D[2][0]) + qz * (D[1][2] + D[2][1])) - 4.0 * qy * (D[0][0] + D[2][2]);
-        dqq[3] = 2.0 * (qr * (D[1][0] - D[0][1]) + qx * (D[0][2] + D[2][0]) + qy * (D[1][2] + D[2][1])) - 4.0 * qz * (D[0][0] + D[1][1]);
-        // qq = q / |q|
-        double dot = qq[0] * dqq[0] + qq[1] * dqq[1] + qq[2] * dqq[2] + qq[3] * dqq[3];
-        double dq[4];
-        for (int k = 0; k < 4; ++k) dq[k] = (dqq[k] - qq[k] * dot) / n2;
-        // q = u / max(|u|, eps)
-        const double d1 = n1 > 1e-12 ? n1 : 1e-12;
-        dot = q[0] * dq[0] + q[1] * dq[1] + q[2] * dq[2] + q[3] * dq[3];
-        for (int k = 0; k < 4; ++k) {
-            const double du = n1 >= 1e-12 ? (dq[k] - q[k] * dot) / d1 : dq[k] / d1;
-            if (accumulate) d_rot[k] += (float)du; else d_rot[k] = (float)du;
-        }
-        for (int k = 0; k < 3; ++k) {
-            if (accumulate) d_trans[k] += (float)tot[k]; else d_trans[k] = (float)tot[k];
-        }
-    }
+    if (!s_last) return;
+    __threadfence();
+    pose_finalize_block(out.pose_scratch, (int)gridDim.x, counters, out.cam_unnorm_rot, out.cam_trans, accumulate, s_sum);
+    if (tid == 0) *ticket = 0u;
 }
 
 int launch_fused_backward(const VtgsCamera* camera, const VtgsParams* params, const VtgsPose* pose,
@@ -620,15 +623,14 @@ int launch_fused_backward(const VtgsCamera* camera, const VtgsParams* params, co
                                                                          buf->n_contrib, dL_dimage4, buf->grad_geom); }
             VTGS_LAUNCH_CHECK();
         }
+        unsigned int* ticket = reinterpret_cast<unsigned int*>(grads->pose_scratch ? grads->pose_scratch + (size_t)blocks * POSE_TERMS : nullptr);
         { VTGS_PROF("fused_preprocess_backward_kernel", stream); fused_preprocess_backward_kernel<<<blocks, 256, 0, stream>>>(cam, N, *params, buf->counters->pose_R, pose->depth_row[0],
                                                                      pose->depth_row[1], pose->depth_row[2], geom, buf->grad_geom,
-                                                                     *grads, accumulate, want_pose); }
+                                                                     *grads, accumulate, want_pose, buf->counters, ticket); }
         VTGS_LAUNCH_CHECK();
-    }
-    if (want_pose) {
-        { VTGS_PROF("pose_finalize_kernel", stream); pose_finalize_kernel<<<1, 1024, 0, stream>>>(grads->pose_scratch, N > 0 ? blocks : 0, buf->counters, grads->cam_unnorm_rot,
-                                                    grads->cam_trans, accumulate); }
-        VTGS_LAUNCH_CHECK();
+    } else if (want_pose && !accumulate) {
+        VTGS_CUDA_CHECK(cudaMemsetAsync(grads->cam_unnorm_rot, 0, 4 * sizeof(float), stream));
+        VTGS_CUDA_CHECK(cudaMemsetAsync(grads->cam_trans, 0, 3 * sizeof(float), stream));
     }
     return VTGS_OK;
 }

@@ -236,6 +236,22 @@ __device__ __forceinline__ void cull_bounds(float opacity, float cov_a, float co
     if (!(hx == hx) || !(hy == hy)) { hx = 1e30f; hy = 1e30f; }
 }
 
+// Pose of the frame (reference transform_to_frame, utils/slam_helpers.py:339-350 + build_rotation,
+// utils/slam_external.py:25-42): q = F.normalize(cam_unnorm_rot), then build_rotation normalises once
+// more.  Spec'd fp32 order, mirrored by the oracle (vtgso_pose_matrix).  Rt = R (row-major 9) then t (3).
+__device__ __forceinline__ void pose_from_quat(const float* __restrict__ q_un, const float* __restrict__ t,
+                                               float* Rt, float* q_norm1 /*4*/, float* norms /*2*/) {
+    const float u0 = q_un[0], u1 = q_un[1], u2 = q_un[2], u3 = q_un[3];
+    const float n1 = __fsqrt_rn(ffma(u3, u3, ffma(u2, u2, ffma(u1, u1, fmul(u0, u0)))));
+    const float d1 = fmaxf(n1, 1e-12f);
+    const float q0 = __fdiv_rn(u0, d1), q1 = __fdiv_rn(u1, d1), q2 = __fdiv_rn(u2, d1), q3 = __fdiv_rn(u3, d1);
+    const float n2 = __fsqrt_rn(ffma(q3, q3, ffma(q2, q2, ffma(q1, q1, fmul(q0, q0)))));
+    quat_to_R(__fdiv_rn(q0, n2), __fdiv_rn(q1, n2), __fdiv_rn(q2, n2), __fdiv_rn(q3, n2), Rt);
+    Rt[9] = t[0]; Rt[10] = t[1]; Rt[11] = t[2];
+    q_norm1[0] = q0; q_norm1[1] = q1; q_norm1[2] = q2; q_norm1[3] = q3;
+    norms[0] = n1; norms[1] = n2;
+}
+
 template <typename T>
 __device__ __forceinline__ T warp_sum(T v) {
 #pragma unroll

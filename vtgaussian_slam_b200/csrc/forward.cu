@@ -80,8 +80,19 @@ preprocess_kernel(const __grid_constant__ CamConst cam, int64_t N, FrontEnd fe,
     const bool rot_aligned = (reinterpret_cast<uintptr_t>(rotations) & 15) == 0;
     float Rt[12];
     if (FUSED) {
+        // every thread derives the pose matrix itself (a few dozen instructions, once per persistent thread);
+        // thread 0 publishes it for the backward (K7' and the pose chain)
+        float qn[4], nrm2[2];
+        pose_from_quat(fe.cam_unnorm_rot, fe.cam_trans, Rt, qn, nrm2);
+        if (blockIdx.x == 0 && tid == 0) {
 #pragma unroll
-        for (int k = 0; k < 12; ++k) Rt[k] = __ldg(fe.pose_Rt + k);
+            for (int k = 0; k < 9; ++k) fe.counters->pose_R[k] = Rt[k];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) fe.counters->pose_t[k] = Rt[9 + k];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) fe.counters->pose_q[k] = qn[k];
+            fe.counters->pose_qnorm[0] = nrm2[0]; fe.counters->pose_qnorm[1] = nrm2[1];
+        }
     }
     int64_t i = (int64_t)blockIdx.x * 256 + tid;
     K1Item nxt;

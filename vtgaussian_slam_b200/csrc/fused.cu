@@ -7,22 +7,31 @@
 
 namespace vtgs {
 
+constexpr int LOSS_PX_PER_THREAD = 4;  // 1024 pixels per block: 4x fewer partials for the in-kernel final reduction
 constexpr int LOSS_TERMS = 4;      // per-block partials: depth L1, rgb L1, mask count, spare
 
 __device__ __forceinline__ float sgn(float v) { return v > 0.0f ? 1.0f : (v < 0.0f ? -1.0f : 0.0f); }
 
 // Tracking loss (mode 0): sums of masked absolute differences; dL/dplane = w * sign * mask.
+// The block that finishes last performs the final reduction of the per-block partials (fixed slice order,
+// fp64: deterministic regardless of which block is last) -- no second launch.  `ticket` must be zero on
+// entry and is reset by the last block.
 __global__ void __launch_bounds__(256)
 tracking_loss_kernel(const __grid_constant__ CamConst cam, VtgsLossConfig cfg, const float* __restrict__ image6,
                      const float* __restrict__ gt_rgb, const float* __restrict__ gt_depth,
-                     float* __restrict__ dL_dimage4, float* __restrict__ partials) {
+                     float* __restrict__ dL_dimage4, float* __restrict__ partials, unsigned int* __restrict__ ticket,
+                     float* __restrict__ loss_terms) {
     __shared__ float s_part[8][LOSS_TERMS];
+    __shared__ double s_sum[LOSS_TERMS][64];
+    __shared__ bool s_last;
     const size_t P = (size_t)cam.W * cam.H;
     const size_t row_begin = (size_t)cam.row0 * 16 * cam.W;
     const size_t row_end = min(P, (size_t)cam.row1 * 16 * cam.W);
-    const size_t pid = row_begin + (size_t)blockIdx.x * 256 + threadIdx.x;
     float ld = 0.f, li = 0.f, cnt = 0.f;
-    if (pid < row_end) {
+#pragma unroll
+    for (int rep = 0; rep < LOSS_PX_PER_THREAD; ++rep) {
+        const size_t pid = row_begin + ((size_t)blockIdx.x * LOSS_PX_PER_THREAD + rep) * 256 + threadIdx.x;
+        if (pid >= row_end) break;
         const float r = image6[pid], g = image6[P + pid], b = image6[2 * P + pid];
         const float d = image6[3 * P + pid], sil = image6[4 * P + pid], dsq = image6[5 * P + pid];
         const float gd = gt_depth[pid];
@@ -34,44 +43,42 @@ tracking_loss_kernel(const __grid_constant__ CamConst cam, VtgsLossConfig cfg, c
         const bool mask_im = cfg.use_sil_for_loss ? mask : true;
         const float er = r - gt_rgb[pid], eg = g - gt_rgb[P + pid], eb = b - gt_rgb[2 * P + pid];
         const float ed = d - gd;
-        if (mask) { ld = fabsf(ed); cnt = 1.0f; }
-        if (mask_im) li = fabsf(er) + fabsf(eg) + fabsf(eb);
+        if (mask) { ld += fabsf(ed); cnt += 1.0f; }
+        if (mask_im) li += fabsf(er) + fabsf(eg) + fabsf(eb);
         dL_dimage4[pid] = mask_im ? cfg.w_im * sgn(er) : 0.0f;
         dL_dimage4[P + pid] = mask_im ? cfg.w_im * sgn(eg) : 0.0f;
         dL_dimage4[2 * P + pid] = mask_im ? cfg.w_im * sgn(eb) : 0.0f;
         dL_dimage4[3 * P + pid] = mask ? cfg.w_depth * sgn(ed) : 0.0f;
     }
     ld = warp_sum(ld); li = warp_sum(li); cnt = warp_sum(cnt);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (lane == 0) { s_part[warp][0] = ld; s_part[warp][1] = li; s_part[warp][2] = cnt; s_part[warp][3] = 0.f; }
     __syncthreads();
-    if (threadIdx.x < LOSS_TERMS) {
+    if (tid < LOSS_TERMS) {
         float s = 0.f;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) s += s_part[w][threadIdx.x];
-        partials[(size_t)blockIdx.x * LOSS_TERMS + threadIdx.x] = s;
+        for (int w = 0; w < 8; ++w) s += s_part[w][tid];
+        partials[(size_t)blockIdx.x * LOSS_TERMS + tid] = s;
+        __threadfence();
     }
-}
-
-__global__ void __launch_bounds__(1024)
-loss_finalize_kernel(const float* __restrict__ partials, int nblocks, VtgsLossConfig cfg, float* __restrict__ loss_terms) {
-    __shared__ double s_sum[LOSS_TERMS][256];
-    __shared__ double s_tot[LOSS_TERMS];
-    const int tid = threadIdx.x;
-    const int term = tid & (LOSS_TERMS - 1), sl = tid >> 2;          // coalesced: consecutive threads, consecutive floats
-    double acc = 0.0;
-    for (int b = sl; b < nblocks; b += 256) acc += (double)partials[(size_t)b * LOSS_TERMS + term];
-    s_sum[term][sl] = acc;
     __syncthreads();
-    if (tid < LOSS_TERMS) {                                          // fixed order: deterministic
-        double a = 0.0;
-        for (int i = 0; i < 256; ++i) a += s_sum[tid][i];
-        s_tot[tid] = a;
-    }
+    if (tid == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const int nblocks = gridDim.x;
+    const int term = tid & (LOSS_TERMS - 1), sl = tid >> 2;           // 64 slices, coalesced
+    double acc = 0.0;
+    for (int b = sl; b < nblocks; b += 64) acc += (double)__ldcg(&partials[(size_t)b * LOSS_TERMS + term]);
+    s_sum[term][sl] = acc;
     __syncthreads();
     if (tid == 0) {
         double tot[LOSS_TERMS];
-        for (int k = 0; k < LOSS_TERMS; ++k) tot[k] = s_tot[k];
+        for (int k = 0; k < LOSS_TERMS; ++k) {
+            double a = 0.0;
+            for (int i = 0; i < 64; ++i) a += s_sum[k][i];
+            tot[k] = a;
+        }
         const double wim = (double)cfg.w_im * tot[1], wd = (double)cfg.w_depth * tot[0];
         loss_terms[0] = (float)(wim + wd);
         loss_terms[1] = (float)wim;
@@ -79,6 +86,7 @@ loss_finalize_kernel(const float* __restrict__ partials, int nblocks, VtgsLossCo
         loss_terms[3] = (float)tot[2];
         loss_terms[4] = (float)tot[1];
         loss_terms[5] = 0.0f; loss_terms[6] = 0.0f; loss_terms[7] = 0.0f;
+        *ticket = 0u;
     }
 }
 
@@ -334,13 +342,14 @@ int launch_loss(const VtgsCamera* camera, const VtgsLossConfig* cfg, const float
     }
     if (cfg->mode != 0) { set_error("unknown loss mode"); return VTGS_E_INVALID; }
     const size_t npx = band_pixels(cam);
-    const int nblocks = (int)((npx + 255) / 256);
+    const int nblocks = (int)((npx + 256 * LOSS_PX_PER_THREAD - 1) / (256 * LOSS_PX_PER_THREAD));
     if (nblocks > 0) {
-        { VTGS_PROF("tracking_loss_kernel", stream); tracking_loss_kernel<<<nblocks, 256, 0, stream>>>(cam, *cfg, image6, gt_rgb, gt_depth, dL_dimage4, scratch); }
+        unsigned int* ticket = reinterpret_cast<unsigned int*>(scratch + (size_t)nblocks * LOSS_TERMS);
+        { VTGS_PROF("tracking_loss_kernel", stream); tracking_loss_kernel<<<nblocks, 256, 0, stream>>>(cam, *cfg, image6, gt_rgb, gt_depth, dL_dimage4, scratch, ticket, loss_terms); }
         VTGS_LAUNCH_CHECK();
+    } else {
+        VTGS_CUDA_CHECK(cudaMemsetAsync(loss_terms, 0, 8 * sizeof(float), stream));
     }
-    { VTGS_PROF("loss_finalize_kernel", stream); loss_finalize_kernel<<<1, 1024, 0, stream>>>(scratch, nblocks, *cfg, loss_terms); }
-    VTGS_LAUNCH_CHECK();
     return VTGS_OK;
 }
 

@@ -18,7 +18,9 @@ struct ProfScope {
 
 // Front end of the fused path (transform_to_frame + activations); unused in API mode.
 struct FrontEnd {
-    const float* pose_Rt;     // device: R[9] row-major then t[3] (VtgsCounters.pose_R/pose_t)
+    const float* cam_unnorm_rot;   // device [4]: the frame's un-normalised pose quaternion
+    const float* cam_trans;        // device [3]
+    VtgsCounters* counters;        // device: receives pose_R / pose_t / pose_q / pose_qnorm for the backward
     float depth_row[4];
     int log_scales_dim;
 };

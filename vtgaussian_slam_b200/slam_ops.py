@@ -364,6 +364,20 @@ class _FusedMappingLoss(torch.autograd.Function):
 
 
 _RENDERERS: dict = {}
+_DEPTH_ROWS: dict = {}
+
+
+def _depth_row_of(w2c):
+    """Third row of curr_data['w2c'] as host floats (get_depth_and_silhouette's z).  The device->host read is
+    cached per tensor (the reference keeps one first-frame w2c for the whole run, src/vtgaussian_slam.py:209)."""
+    key = (id(w2c), getattr(w2c, "_version", 0))
+    hit = _DEPTH_ROWS.get(key)
+    if hit is None:
+        if len(_DEPTH_ROWS) > 64:
+            _DEPTH_ROWS.clear()
+        row = tuple(float(v) for v in torch.as_tensor(w2c).detach().float().cpu()[2])
+        hit = _DEPTH_ROWS[key] = (row, w2c)          # keep the tensor alive so its id stays unique
+    return hit[0]
 
 
 def _renderer_for(cam, n, device):
@@ -408,8 +422,7 @@ def get_loss(params, curr_data, variables, iter_time_idx, loss_weights, use_sil_
             raise NotImplementedError("fused backend: isotropic Gaussians only; use backend='dropin'")
         dev = params['means3D'].device
         r = _renderer_for(curr_data['cam'], params['means3D'].shape[0], dev)
-        w2c = torch.as_tensor(curr_data['w2c']).detach().float().cpu()
-        r.depth_row = tuple(float(v) for v in w2c[2])
+        r.depth_row = _depth_row_of(curr_data['w2c'])
         cam_q = params['cam_unnorm_rots'][0, :, iter_time_idx]
         cam_t = params['cam_trans'][0, :, iter_time_idx]
         if not camera_grad:
