@@ -120,6 +120,11 @@ typedef struct VtgsBuffers {
     void*         region_pairs;   /* [8 * pair_capacity] uint32x2 {Gaussian id, 1-based position in the tile
                                      list}: per-tile, per-8x4-pixel-region lists built by the sort kernel  */
     uint32_t*     region_cnt;     /* [tiles][8] length of each region list                 */
+    uint32_t*     region_masks;   /* [8 * (pair_capacity + 32 tiles)] per (region, group of 32 splats, pixel
+                                     lane): bit e = splat e of the group was blended into that pixel.  Written
+                                     by the forward blend, consumed by the backward blend               */
+    uint32_t*     region_done;    /* [tiles][8] groups of each region list the forward walked before every
+                                     pixel of the region had saturated                                   */
     uint64_t      pair_capacity;
 } VtgsBuffers;
 
@@ -139,6 +144,8 @@ typedef struct VtgsWorkspaceSizes {
     uint64_t counters_bytes;
     uint64_t region_pairs_bytes;
     uint64_t region_cnt_bytes;
+    uint64_t region_masks_bytes;
+    uint64_t region_done_bytes;
     uint32_t tiles_x;
     uint32_t tiles_y;
 } VtgsWorkspaceSizes;

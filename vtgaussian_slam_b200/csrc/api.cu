@@ -62,7 +62,7 @@ static int check_cam(const VtgsCamera* cam) {
 
 static int check_buf(const VtgsBuffers* b, int64_t N) {
     VTGS_REQUIRE(b != nullptr, "buffers is NULL");
-    VTGS_REQUIRE(b->tile_counts && b->tile_ranges && b->final_T && b->n_contrib && b->counters && b->region_cnt, "workspace pointer is NULL");
+    VTGS_REQUIRE(b->tile_counts && b->tile_ranges && b->final_T && b->n_contrib && b->counters && b->region_cnt && b->region_masks && b->region_done, "workspace pointer is NULL");
     if (N > 0) VTGS_REQUIRE(b->geom && b->tiles_touched && b->grad_geom, "per-Gaussian workspace pointer is NULL");
     VTGS_REQUIRE(b->pair_capacity == 0 || (b->pair_keys && b->point_list && b->region_pairs), "pair workspace pointer is NULL");
     VTGS_REQUIRE(b->pair_capacity < 0xffffffffull, "pair_capacity must fit 32 bits");
@@ -95,6 +95,8 @@ int vtgs_workspace_query(int32_t W, int32_t H, int64_t N, uint64_t pair_capacity
     s->counters_bytes = sizeof(VtgsCounters);
     s->region_pairs_bytes = (pair_capacity > 0 ? pair_capacity : 1) * 8 * 8;
     s->region_cnt_bytes = gx * gy * 8 * 4;
+    s->region_masks_bytes = ((pair_capacity > 0 ? pair_capacity : 1) + 32 * gx * gy) * 8 * 4;
+    s->region_done_bytes = gx * gy * 8 * 4;
     s->tiles_x = (uint32_t)gx;
     s->tiles_y = (uint32_t)gy;
     return VTGS_OK;

@@ -70,23 +70,24 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[16], int lane)
 //   [6..6+NCH) dL/dcolour  (API: r,g,b   fused: r,g,b,z)
 //
 // Block = one 16x16 tile, 8 independent warps (no block barrier), warp w = pixel region w.
-// Each warp walks ITS REGION'S LIST (built by the sort kernel) BACK TO FRONT in groups of 32
-// (prefetched gathers of the 64-byte records):
-//   P1 lane = splat : 32x32 "may contribute" bit matrix, transposed to the pixel lanes;
-//   P2 lane = pixel : back-to-front over ITS OWN splats: recompute alpha, unwind T, run the
-//                     accum recursion, and leave (w = alpha*T, g0 = G*dL/dalpha) in the
+// Each warp walks ITS REGION'S LIST (built by the sort kernel) BACK TO FRONT in the forward's groups of 32
+// (prefetched gathers of the 64-byte records).  The forward blend left, per group and pixel lane, the mask
+// of splats it actually blended, so nothing is re-tested here:
+//   P2 lane = pixel : back-to-front over the splats ITS pixel blended: recompute G and alpha, unwind T,
+//                     run the accum recursion, and leave (w = alpha*T, g0 = G*dL/dalpha) in the
 //                     (splat, pixel) cell of a warp-private shared matrix;
-//   P3 lane = splat : sum its row of cells against the pixels' dL/dpixel and coordinates: the
-//                     ten per-splat sums come out of plain per-lane FMAs, no shuffles;
+//   P3 lane = splat : (pixel masks transposed across the warp) sum its row of cells against the pixels'
+//                     dL/dpixel and coordinates: the ten per-splat sums are plain per-lane FMAs;
 //   P4 lane = splat : three red.global.add.v4.f32 per (region, splat).
+// Groups in which no pixel of the region blended anything are skipped before their records are fetched.
 // Upstream: 9-10 global float atomics per contributing (pixel, splat) pair.
 template <bool FUSED>
 __global__ void __launch_bounds__(256, 2)
 blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __restrict__ ranges,
                       const uint2* __restrict__ region_pairs, const uint32_t* __restrict__ region_cnt,
+                      const uint32_t* __restrict__ region_masks, const uint32_t* __restrict__ region_done,
                       const GeomRecord* __restrict__ geom,
-                      const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
-                      const float* __restrict__ dL_dpix, float* __restrict__ grad_geom) {
+                      const float* __restrict__ final_T, const float* __restrict__ dL_dpix, float* __restrict__ grad_geom) {
     constexpr int NCH = FUSED ? 4 : 3;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     struct WarpArea {
@@ -106,15 +107,16 @@ blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __re
     const int pix_x = rx0 + (lane % REGION_W), pix_y = ry0 + (lane / REGION_W);
     const bool inside = pix_x < cam.W && pix_y < cam.H;
     const float pxf = (float)pix_x, pyf = (float)pix_y;
-    const float x0f = (float)rx0, y0f = (float)ry0;
     const uint32_t rb = ranges[2 * tile], re = ranges[2 * tile + 1];
     const int n = (int)region_cnt[(size_t)tile * 8 + warp];
+    const int gdone = (int)region_done[(size_t)tile * 8 + warp];      // groups the forward walked
+    if (n == 0 || gdone == 0) return;
     const uint2* __restrict__ list = region_pairs + (size_t)8 * rb + (size_t)warp * (re - rb);
+    const uint32_t* __restrict__ masks = region_masks + mask_arena_base(rb, re, tile, warp);
     const size_t P = (size_t)cam.W * cam.H;
     const size_t pid = (size_t)pix_y * cam.W + pix_x;
 
     const float T_final = inside ? final_T[pid] : 0.0f;
-    const uint32_t last = inside ? n_contrib[pid] : 0u;
     float dpix[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int ch = 0; ch < NCH; ++ch) dpix[ch] = inside ? dL_dpix[ch * P + pid] : 0.0f;
@@ -123,48 +125,48 @@ blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __re
     const float bg_dot = cam.bg[0] * dpix[0] + cam.bg[1] * dpix[1] + cam.bg[2] * dpix[2];
     const float half_w = 0.5f * cam.W, half_h = 0.5f * cam.H;
 
-    // entries beyond the region's largest n_contrib are never touched
-    uint32_t todo = last;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) todo = max(todo, __shfl_xor_sync(VTGS_FULL_MASK, todo, o));
-    if (todo == 0 || n == 0) return;
-
     float T = T_final;
     float accum[NCH], lastc[NCH];
 #pragma unroll
     for (int ch = 0; ch < NCH; ++ch) { accum[ch] = 0.0f; lastc[ch] = 0.0f; }
     float last_alpha = 0.0f;
 
-    // group g (counted from the END of the list) holds list indices n-1-32g-l for lane l: ascending lane =
-    // descending list position
-    const int ngroups = (n + 31) >> 5;
-    auto idx_of = [&](int g) { return n - 1 - (g * 32 + lane); };
-    uint2 ent_next = idx_of(0) >= 0 ? list[idx_of(0)] : make_uint2(0u, 0u);
-    uint2 ent_next2 = idx_of(1) >= 0 ? list[idx_of(1)] : make_uint2(0u, 0u);
+    // software pipeline over the forward's groups, last to first: masks two groups ahead, list entries and
+    // records one group ahead (only for groups with at least one blended splat)
+    auto mask_of = [&](int g) { return g >= 0 ? masks[g * 32 + lane] : 0u; };
+    int g = gdone - 1;
+    uint32_t m_next = mask_of(g), m_next2 = mask_of(g - 1);
+    bool nxt_live = __any_sync(VTGS_FULL_MASK, m_next != 0u);
+    uint2 ent_next = make_uint2(0u, 0u);
     SplatRegs nxt;
-    // a group whose every position lies beyond `todo` is skipped without touching its records
-    bool nxt_live = __any_sync(VTGS_FULL_MASK, idx_of(0) >= 0 && ent_next.y <= todo);
-    if (nxt_live) load_splat(nxt, idx_of(0) >= 0, geom, ent_next);
-    for (int g = 0; g < ngroups; ++g) {
+    if (nxt_live) {
+        const bool v = g * 32 + lane < n;
+        if (v) ent_next = list[g * 32 + lane];
+        load_splat(nxt, v, geom, ent_next);
+    }
+    for (; g >= 0; --g) {
         const SplatRegs cur = nxt;
         const uint2 cur_ent = ent_next;
         const bool cur_live = nxt_live;
-        const bool have = idx_of(g) >= 0;
-        ent_next = ent_next2;
-        ent_next2 = idx_of(g + 2) >= 0 ? list[idx_of(g + 2)] : make_uint2(0u, 0u);
-        nxt_live = __any_sync(VTGS_FULL_MASK, idx_of(g + 1) >= 0 && ent_next.y <= todo);
-        if (nxt_live) load_splat(nxt, idx_of(g + 1) >= 0, geom, ent_next);
+        uint32_t m = m_next;
+        m_next = m_next2;
+        m_next2 = mask_of(g - 2);
+        nxt_live = __any_sync(VTGS_FULL_MASK, m_next != 0u);
+        if (nxt_live) {
+            const bool v = (g - 1) * 32 + lane < n;
+            if (v) ent_next = list[(g - 1) * 32 + lane];
+            load_splat(nxt, v, geom, ent_next);
+        }
         if (!cur_live) continue;
+        const bool have = g * 32 + lane < n;
         __syncwarp();                                   // previous group's P3 reads are complete
         if (have) { G.a[lane] = cur.a; G.b[lane] = cur.b; G.c[lane] = cur.c; }
         __syncwarp();
-        uint32_t emask;
-        uint32_t m = p1_masks(have, cur.a, cur.b, x0f, y0f, lane, emask);          // P1: lane = splat
-        // ---- P2: lane = pixel; ascending bits = descending list position.  Two splats per trip: loads /
+        const uint32_t emask = warp_transpose_bits(m, lane);      // lane = splat: the pixels that blended it
+        // ---- P2: lane = pixel; descending bits = descending list position.  Two splats per trip: loads /
         // power / exp are independent, the T / accum recursion is ordered.
         auto back_one = [&](const float4 q0, const float Gv, const int e) -> float2 {
             const float alpha = fminf(VTGS_ALPHA_MAX, fmul(q0.w, Gv));
-            if (__float_as_uint(q0.z) > last || alpha < VTGS_ALPHA_MIN) return make_float2(0.0f, 0.0f);
             const float4 q2 = G.c[e];
             const float col[4] = {q2.x, q2.y, q2.z, q2.w};
             const float inv = __fdividef(1.0f, 1.0f - alpha);
@@ -182,11 +184,11 @@ blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __re
             return make_float2(alpha * T, Gv * dL_dalpha);
         };
         while (m) {
-            const int ea = __ffs(m) - 1;
-            m &= m - 1;
+            const int ea = 31 - __clz(m);
+            m &= ~(1u << ea);
             const bool two = m != 0;
-            const int eb = two ? __ffs(m) - 1 : ea;
-            m &= m - 1;
+            const int eb = two ? 31 - __clz(m) : ea;
+            m &= ~(1u << eb);
             const float4 a0 = G.a[ea], a1 = G.b[ea];
             const float4 b0 = G.a[eb], b1 = G.b[eb];
             const float Ga = vexpf(power_of(a1.x, a1.y, a1.z, fsub(a0.x, pxf), fsub(a0.y, pyf)));
@@ -391,8 +393,8 @@ int launch_backward(const VtgsCamera* camera, int64_t N,
     if (N <= 0) return VTGS_OK;
     if (int e = ensure_bwd_smem()) return e;
     if (band_tiles > 0) {
-        { VTGS_PROF("blend_backward_kernel", stream); blend_backward_kernel<false><<<band_tiles, 256, BWD_SMEM, stream>>>(cam, buf->tile_ranges, reinterpret_cast<const uint2*>(buf->region_pairs), buf->region_cnt, geom, buf->final_T,
-                                                                      buf->n_contrib, dL_dout_color, buf->grad_geom); }
+        { VTGS_PROF("blend_backward_kernel", stream); blend_backward_kernel<false><<<band_tiles, 256, BWD_SMEM, stream>>>(cam, buf->tile_ranges, reinterpret_cast<const uint2*>(buf->region_pairs), buf->region_cnt, buf->region_masks, buf->region_done, geom, buf->final_T,
+                                                                      dL_dout_color, buf->grad_geom); }
         VTGS_LAUNCH_CHECK();
     }
     { VTGS_PROF("preprocess_backward_kernel", stream); preprocess_backward_kernel<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(cam, N, means3D, scales, rotations, nullptr, geom,
@@ -619,8 +621,8 @@ int launch_fused_backward(const VtgsCamera* camera, const VtgsParams* params, co
     if (int e = ensure_bwd_smem()) return e;
     if (N > 0) {
         if (band_tiles > 0) {
-            { VTGS_PROF("blend_backward_kernel", stream); blend_backward_kernel<true><<<band_tiles, 256, BWD_SMEM, stream>>>(cam, buf->tile_ranges, reinterpret_cast<const uint2*>(buf->region_pairs), buf->region_cnt, geom, buf->final_T,
-                                                                         buf->n_contrib, dL_dimage4, buf->grad_geom); }
+            { VTGS_PROF("blend_backward_kernel", stream); blend_backward_kernel<true><<<band_tiles, 256, BWD_SMEM, stream>>>(cam, buf->tile_ranges, reinterpret_cast<const uint2*>(buf->region_pairs), buf->region_cnt, buf->region_masks, buf->region_done, geom, buf->final_T,
+                                                                         dL_dimage4, buf->grad_geom); }
             VTGS_LAUNCH_CHECK();
         }
         unsigned int* ticket = reinterpret_cast<unsigned int*>(grads->pose_scratch ? grads->pose_scratch + (size_t)blocks * POSE_TERMS : nullptr);

@@ -75,6 +75,12 @@ __device__ __forceinline__ uint32_t region_mask(const float4 q0, float tox, floa
     return rmask;
 }
 
+// Offset of a region's applied-contribution masks: one 32-bit word per (group of 32 splats, pixel lane).  A
+// region list is shorter than its tile list (re - rb) but its last group is padded to 32, hence the +32.
+__device__ __forceinline__ size_t mask_arena_base(uint32_t rb, uint32_t re, int tile, int warp) {
+    return (size_t)8 * ((size_t)rb + (size_t)32 * tile) + (size_t)warp * ((size_t)(re - rb) + 32);
+}
+
 // 32x32 bit-matrix transpose across the warp: on entry lane e holds row e (bit p = column p),
 // on return lane p holds column p (bit e = row e).
 __device__ __forceinline__ uint32_t warp_transpose_bits(uint32_t x, int lane) {

@@ -463,6 +463,7 @@ template <bool FUSED>
 __global__ void __launch_bounds__(256, 3)
 blend_forward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __restrict__ ranges,
                      const uint2* __restrict__ region_pairs, const uint32_t* __restrict__ region_cnt,
+                     uint32_t* __restrict__ region_masks, uint32_t* __restrict__ region_done,
                      const GeomRecord* __restrict__ geom,
                      float* __restrict__ out_color, float* __restrict__ out_depth,
                      float* __restrict__ final_T, uint32_t* __restrict__ n_contrib) {
@@ -481,11 +482,12 @@ blend_forward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __res
     const uint32_t rb = ranges[2 * tile], re = ranges[2 * tile + 1];
     const int n = (int)region_cnt[(size_t)tile * 8 + warp];
     const uint2* __restrict__ list = region_pairs + (size_t)8 * rb + (size_t)warp * (re - rb);
+    uint32_t* __restrict__ masks = region_masks + mask_arena_base(rb, re, tile, warp);
     const int ngroups = (n + 31) >> 5;
 
     float T = 1.0f;
     float C0 = 0.f, C1 = 0.f, C2 = 0.f, C3 = 0.f, C4 = 0.f, C5 = 0.f;
-    uint32_t last = 0;
+    uint32_t last = 0, applied = 0;
     bool done = !inside;
 
     auto blend_one = [&](const float4 a, const float alpha, const int e) -> bool {
@@ -503,6 +505,7 @@ blend_forward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __res
         }
         T = test_T;
         last = __float_as_uint(a.z);
+        applied |= 1u << e;
         return true;
     };
 
@@ -512,7 +515,8 @@ blend_forward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __res
     SplatRegs nxt;
     load_splat(nxt, lane < n, geom, ent_next);
     bool all_done = __all_sync(VTGS_FULL_MASK, done);
-    for (int g = 0; g < ngroups && !all_done; ++g) {
+    int g = 0;
+    for (; g < ngroups && !all_done; ++g) {
         const SplatRegs cur = nxt;
         const int k = g * 32 + lane;
         const bool have = k < n;
@@ -543,8 +547,11 @@ blend_forward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __res
             if (!blend_one(a0, alpha_a, ea)) break;
             if (two && !blend_one(b0, alpha_b, eb)) break;
         }
+        masks[g * 32 + lane] = applied;                 // which splats of this group each pixel blended (for K6')
+        applied = 0;
         all_done = __all_sync(VTGS_FULL_MASK, done);
     }
+    if (lane == 0) region_done[(size_t)tile * 8 + warp] = (uint32_t)g;
 
     if (inside) {
         const size_t P = (size_t)cam.W * cam.H;
@@ -617,8 +624,8 @@ int launch_forward(const VtgsCamera* camera, int64_t N, bool fused, const FrontE
     if (N <= 0) VTGS_CUDA_CHECK(cudaMemsetAsync(buf->region_cnt, 0, sizeof(uint32_t) * 8 * num_tiles, stream));
     if (band_tiles > 0) {
         if (fused)
-            { VTGS_PROF("blend_forward_kernel", stream); blend_forward_kernel<true><<<band_tiles, 256, 0, stream>>>(cam, buf->tile_ranges, reinterpret_cast<const uint2*>(buf->region_pairs), buf->region_cnt, geom, out_color, out_depth, buf->final_T, buf->n_contrib); }
-        else { VTGS_PROF("blend_forward_kernel", stream); blend_forward_kernel<false><<<band_tiles, 256, 0, stream>>>(cam, buf->tile_ranges, reinterpret_cast<const uint2*>(buf->region_pairs), buf->region_cnt, geom, out_color, out_depth, buf->final_T, buf->n_contrib); }
+            { VTGS_PROF("blend_forward_kernel", stream); blend_forward_kernel<true><<<band_tiles, 256, 0, stream>>>(cam, buf->tile_ranges, reinterpret_cast<const uint2*>(buf->region_pairs), buf->region_cnt, buf->region_masks, buf->region_done, geom, out_color, out_depth, buf->final_T, buf->n_contrib); }
+        else { VTGS_PROF("blend_forward_kernel", stream); blend_forward_kernel<false><<<band_tiles, 256, 0, stream>>>(cam, buf->tile_ranges, reinterpret_cast<const uint2*>(buf->region_pairs), buf->region_cnt, buf->region_masks, buf->region_done, geom, out_color, out_depth, buf->final_T, buf->n_contrib); }
         VTGS_LAUNCH_CHECK();
     }
     if (band_tiles < num_tiles && !fused) {       // API mode returns complete planes; the fused solvers only ever read their band

@@ -111,7 +111,9 @@ class Workspace:
         self.grad_geom = None
         self.counters = torch.zeros(sz.counters_bytes // 4, dtype=torch.int32, device=device)
         self.region_cnt = torch.zeros(sz.region_cnt_bytes // 4, dtype=torch.int32, device=device)
-        self.region_pairs = None
+        self.region_done = torch.zeros(sz.region_done_bytes // 4, dtype=torch.int32, device=device)
+        self.region_pairs = self.region_masks = None
+        self._num_tiles = sz.tiles_x * sz.tiles_y
         self.pair_capacity = 0
         self.pair_keys = self.point_list = None
         self.reserve_pairs(pair_capacity)
@@ -122,6 +124,7 @@ class Workspace:
             self.pair_keys = torch.empty(cap, dtype=torch.int64, device=self.device)
             self.point_list = torch.empty(cap, dtype=torch.int32, device=self.device)
             self.region_pairs = torch.empty((8 * cap, 2), dtype=torch.int32, device=self.device)
+            self.region_masks = torch.empty(8 * (cap + 32 * self._num_tiles), dtype=torch.int32, device=self.device)
             self.pair_capacity = cap
 
     def ensure_grad_geom(self):
@@ -143,6 +146,8 @@ class Workspace:
         b.counters = self.counters.data_ptr()
         b.region_pairs = self.region_pairs.data_ptr()
         b.region_cnt = self.region_cnt.data_ptr()
+        b.region_masks = self.region_masks.data_ptr()
+        b.region_done = self.region_done.data_ptr()
         b.pair_capacity = self.pair_capacity
         return b
 
