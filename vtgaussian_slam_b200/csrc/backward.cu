@@ -81,8 +81,9 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[16], int lane)
 //   P4 lane = splat : three red.global.add.v4.f32 per (region, splat).
 // Groups in which no pixel of the region blended anything are skipped before their records are fetched.
 // Upstream: 9-10 global float atomics per contributing (pixel, splat) pair.
+constexpr int BWD_WARPS = 4;          // warps (regions) per block: a tile is covered by 8 / BWD_WARPS blocks
 template <bool FUSED>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(32 * BWD_WARPS, 20 / BWD_WARPS)
 blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __restrict__ ranges,
                       const uint2* __restrict__ region_pairs, const uint32_t* __restrict__ region_cnt,
                       const uint32_t* __restrict__ region_masks, const uint32_t* __restrict__ region_done,
@@ -98,10 +99,12 @@ blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __re
     };
     WarpArea* areas = reinterpret_cast<WarpArea*>(smem_raw);
 
-    const int tile = cam.row0 * cam.gx + blockIdx.x;
+    constexpr int BPT = 8 / BWD_WARPS;                                  // blocks per tile
+    const int tile = cam.row0 * cam.gx + blockIdx.x / BPT;
     const int tile_x = tile % cam.gx, tile_y = tile / cam.gx;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    WarpArea& A = areas[warp];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = (blockIdx.x % BPT) * BWD_WARPS + (tid >> 5);       // region index inside the tile
+    WarpArea& A = areas[tid >> 5];
     GroupSmem& G = A.G;
     const int rx0 = tile_x * 16 + (warp % REGIONS_X) * REGION_W, ry0 = tile_y * 16 + (warp / REGIONS_X) * REGION_H;
     const int pix_x = rx0 + (lane % REGION_W), pix_y = ry0 + (lane / REGION_W);
@@ -369,7 +372,7 @@ preprocess_backward_kernel(const __grid_constant__ CamConst cam, int64_t N,
 }
 
 // dynamic shared memory of blend_backward_kernel: 8 x (group 1536 + cells 8448 + dpix 512 + pxy 256) bytes
-constexpr int BWD_SMEM = 8 * (int)(sizeof(GroupSmem) + 32 * 33 * sizeof(float2) + 32 * sizeof(float4) + 32 * sizeof(float2));
+constexpr int BWD_SMEM = BWD_WARPS * (int)(sizeof(GroupSmem) + 32 * 33 * sizeof(float2) + 32 * sizeof(float4) + 32 * sizeof(float2));
 static int ensure_bwd_smem() {
     static bool done = false;
     if (!done) {
@@ -393,7 +396,7 @@ int launch_backward(const VtgsCamera* camera, int64_t N,
     if (N <= 0) return VTGS_OK;
     if (int e = ensure_bwd_smem()) return e;
     if (band_tiles > 0) {
-        { VTGS_PROF("blend_backward_kernel", stream); blend_backward_kernel<false><<<band_tiles, 256, BWD_SMEM, stream>>>(cam, buf->tile_ranges, reinterpret_cast<const uint2*>(buf->region_pairs), buf->region_cnt, buf->region_masks, buf->region_done, geom, buf->final_T,
+        { VTGS_PROF("blend_backward_kernel", stream); blend_backward_kernel<false><<<band_tiles * (8 / BWD_WARPS), 32 * BWD_WARPS, BWD_SMEM, stream>>>(cam, buf->tile_ranges, reinterpret_cast<const uint2*>(buf->region_pairs), buf->region_cnt, buf->region_masks, buf->region_done, geom, buf->final_T,
                                                                       dL_dout_color, buf->grad_geom); }
         VTGS_LAUNCH_CHECK();
     }
@@ -621,7 +624,7 @@ int launch_fused_backward(const VtgsCamera* camera, const VtgsParams* params, co
     if (int e = ensure_bwd_smem()) return e;
     if (N > 0) {
         if (band_tiles > 0) {
-            { VTGS_PROF("blend_backward_kernel", stream); blend_backward_kernel<true><<<band_tiles, 256, BWD_SMEM, stream>>>(cam, buf->tile_ranges, reinterpret_cast<const uint2*>(buf->region_pairs), buf->region_cnt, buf->region_masks, buf->region_done, geom, buf->final_T,
+            { VTGS_PROF("blend_backward_kernel", stream); blend_backward_kernel<true><<<band_tiles * (8 / BWD_WARPS), 32 * BWD_WARPS, BWD_SMEM, stream>>>(cam, buf->tile_ranges, reinterpret_cast<const uint2*>(buf->region_pairs), buf->region_cnt, buf->region_masks, buf->region_done, geom, buf->final_T,
                                                                          dL_dimage4, buf->grad_geom); }
             VTGS_LAUNCH_CHECK();
         }
