@@ -153,6 +153,22 @@ def band_for_rank(gy, rank, world):
     return (r0, r0 + base + (1 if rank < rem else 0))
 
 
+def balanced_bands(row_work, world):
+    """Contiguous tile-row bands of near-equal work: row_work[r] = cost proxy of tile row r (sum of n_contrib).
+    Deterministic, covers [0, rows) exactly, every band non-empty (rows >= world)."""
+    w = np.asarray(row_work, dtype=np.float64) + 1e-9
+    rows = len(w)
+    cum = np.concatenate([[0.0], np.cumsum(w)])
+    cuts = [0]
+    for k in range(1, world):
+        target = cum[-1] * k / world
+        c = int(np.searchsorted(cum, target))
+        c = min(max(c, cuts[-1] + 1), rows - (world - k))
+        cuts.append(c)
+    cuts.append(rows)
+    return [(cuts[k], cuts[k + 1]) for k in range(world)]
+
+
 def run_ours(args, wl):
     import torch
     import torch.distributed as dist
@@ -180,7 +196,20 @@ def run_ours(args, wl):
         sh_degree=0, campos=torch.tensor(s["campos"], device=dev), prefiltered=False)
     params = {k: torch.tensor(v, device=dev) for k, v in wl["params"].items()}
     N = params["means3D"].shape[0]
-    band = band_for_rank(gy, rank, world) if world > 1 else (0, 0)
+    band = (0, 0)
+    if world > 1:
+        # one full-frame render per rank (identical on every rank, once per FRAME, outside the timed iterations)
+        # measures the work of every tile row; bands are cut to equal work instead of equal rows
+        from vtgaussian_slam_b200.fused import FusedRenderer
+        probe = FusedRenderer(settings, N, device=dev)
+        probe.forward(params, torch.tensor(wl["q"], device=dev), torch.tensor(wl["t"], device=dev))
+        nc = probe.ws.n_contrib.to(torch.float64)
+        pad = torch.zeros((gy * 16, nc.shape[1]), dtype=torch.float64, device=dev)
+        pad[:H] = nc
+        row_work = pad.reshape(gy, 16, -1).sum(dim=(1, 2)).cpu().numpy()
+        band = balanced_bands(row_work, world)[rank]
+        del probe, nc, pad
+        torch.cuda.empty_cache()
     solver = TrackingSolver(settings, params, device=dev, w_im=LOSS_W["im"], w_depth=LOSS_W["depth"], sil_thres=SIL_THRES,
                             tile_rows=band, use_graph=True, process_group=pg)
     gt_rgb = torch.tensor(fr["im"]).pin_memory()

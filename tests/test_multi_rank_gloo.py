@@ -88,6 +88,22 @@ def test_band_partition_covers_all_rows():
             assert max(sizes) - min(sizes) <= 1
 
 
+def test_balanced_bands_properties():
+    sys.path.insert(0, ROOT)
+    import bench
+    rng = np.random.default_rng(0)
+    for rows in (43, 30, 73, 8):
+        for world in (1, 2, 4, 8):
+            w = rng.uniform(0.2, 3.0, rows)
+            bands = bench.balanced_bands(w, world)
+            assert bands[0][0] == 0 and bands[-1][1] == rows and len(bands) == world
+            assert all(b > a for a, b in bands) and all(bands[i][1] == bands[i + 1][0] for i in range(world - 1))
+            loads = [w[a:b].sum() for a, b in bands]
+            if rows >= 4 * world:
+                assert max(loads) <= w.sum() / world + w.max() + 1e-9        # within one row of the ideal share
+    assert bench.balanced_bands(np.zeros(8), 8) == [(i, i + 1) for i in range(8)]
+
+
 @pytest.mark.timeout(300)
 def test_two_rank_gloo_allreduce_equals_single_rank():
     port = 29500 + (os.getpid() % 2000)

@@ -490,7 +490,15 @@ struct K7Item {
 };
 
 __device__ __forceinline__ void k7_load(K7Item& it, int64_t i, const VtgsParams& prm, const GeomRecord* __restrict__ geom,
-                                        const float* __restrict__ grad_geom, bool rot_aligned) {
+                                        const float* __restrict__ grad_geom, bool rot_aligned, const uint32_t* __restrict__ tiles_touched) {
+    // a Gaussian with no tile in this rank's band (tile-band sharding) or culled received no gradient here:
+    // 4 bytes decide that instead of ~190
+    if (tiles_touched[i] == 0u) {
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        it.g0 = z4; it.g1 = z4; it.g2 = z4; it.uq = z4;
+        it.hx = -1e30f; it.op = 0.f; it.px = 0.f; it.py = 0.f; it.pz = 0.f; it.ls = 0.f;
+        return;
+    }
     const float4* gg = reinterpret_cast<const float4*>(grad_geom + (size_t)i * VTGS_GRAD_GEOM_FLOATS);
     it.g0 = gg[0]; it.g1 = gg[1]; it.g2 = gg[2];
     it.hx = geom[i].q0.z; it.op = geom[i].q1.w;
@@ -506,7 +514,8 @@ fused_preprocess_backward_kernel(const __grid_constant__ CamConst cam, int64_t N
                                  const float* __restrict__ pose_Rt, float dr0, float dr1, float dr2,
                                  const GeomRecord* __restrict__ geom, float* __restrict__ grad_geom,
                                  VtgsParamGrads out, int accumulate, int want_pose,
-                                 const VtgsCounters* __restrict__ counters, unsigned int* __restrict__ ticket) {
+                                 const VtgsCounters* __restrict__ counters, unsigned int* __restrict__ ticket,
+                                 const uint32_t* __restrict__ tiles_touched) {
     __shared__ float s_part[8][POSE_TERMS];
     __shared__ double s_sum[POSE_TERMS][21];
     __shared__ bool s_last;
@@ -522,10 +531,10 @@ fused_preprocess_backward_kernel(const __grid_constant__ CamConst cam, int64_t N
 
     int64_t i = (int64_t)blockIdx.x * 256 + tid;
     K7Item nxt;
-    if (i < N) k7_load(nxt, i, prm, geom, grad_geom, rot_aligned);
+    if (i < N) k7_load(nxt, i, prm, geom, grad_geom, rot_aligned, tiles_touched);
     for (; i < N; i += stride) {
         const K7Item it = nxt;
-        if (i + stride < N) k7_load(nxt, i + stride, prm, geom, grad_geom, rot_aligned);
+        if (i + stride < N) k7_load(nxt, i + stride, prm, geom, grad_geom, rot_aligned, tiles_touched);
         const float4 g0 = it.g0, g1 = it.g1, g2 = it.g2;
         // culled splats, and splats no pixel blended (all sums exactly zero), have zero gradients: every
         // term below is linear in g0..g2
@@ -631,7 +640,7 @@ int launch_fused_backward(const VtgsCamera* camera, const VtgsParams* params, co
         unsigned int* ticket = reinterpret_cast<unsigned int*>(grads->pose_scratch ? grads->pose_scratch + (size_t)blocks * POSE_TERMS : nullptr);
         { VTGS_PROF("fused_preprocess_backward_kernel", stream); fused_preprocess_backward_kernel<<<blocks, 256, 0, stream>>>(cam, N, *params, buf->counters->pose_R, pose->depth_row[0],
                                                                      pose->depth_row[1], pose->depth_row[2], geom, buf->grad_geom,
-                                                                     *grads, accumulate, want_pose, buf->counters, ticket); }
+                                                                     *grads, accumulate, want_pose, buf->counters, ticket, buf->tiles_touched); }
         VTGS_LAUNCH_CHECK();
     } else if (want_pose && !accumulate) {
         VTGS_CUDA_CHECK(cudaMemsetAsync(grads->cam_unnorm_rot, 0, 4 * sizeof(float), stream));
