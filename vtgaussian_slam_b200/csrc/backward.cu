@@ -169,7 +169,7 @@ blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __re
         // ---- P2: lane = pixel; descending bits = descending list position.  Two splats per trip: loads /
         // power / exp are independent, the T / accum recursion is ordered.
         auto back_one = [&](const float4 q0, const float Gv, const int e) -> float2 {
-            const float alpha = fminf(VTGS_ALPHA_MAX, fmul(q0.w, Gv));
+            const float alpha = fminf(VTGS_ALPHA_MAX, q0.w * Gv);
             const float4 q2 = G.c[e];
             const float col[4] = {q2.x, q2.y, q2.z, q2.w};
             const float inv = __fdividef(1.0f, 1.0f - alpha);
@@ -194,8 +194,11 @@ blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __re
             m &= ~(1u << eb);
             const float4 a0 = G.a[ea], a1 = G.b[ea];
             const float4 b0 = G.a[eb], b1 = G.b[eb];
-            const float Ga = vexpf(power_of(a1.x, a1.y, a1.z, fsub(a0.x, pxf), fsub(a0.y, pyf)));
-            const float Gb = vexpf(power_of(b1.x, b1.y, b1.z, fsub(b0.x, pxf), fsub(b0.y, pyf)));
+            // no decision depends on G any more (the forward's masks fix which splats were blended), so the
+            // backward may use the hardware exp2 and free contraction: gradients are judged to 1e-3 relative
+            const float dxa = a0.x - pxf, dya = a0.y - pyf, dxb = b0.x - pxf, dyb = b0.y - pyf;
+            const float Ga = __expf(-0.5f * (a1.x * dxa * dxa + a1.z * dya * dya) - a1.y * dxa * dya);
+            const float Gb = __expf(-0.5f * (b1.x * dxb * dxb + b1.z * dyb * dyb) - b1.y * dxb * dyb);
             A.cell[ea][lane] = back_one(a0, Ga, ea);
             if (two) A.cell[eb][lane] = back_one(b0, Gb, eb);
         }
@@ -493,7 +496,7 @@ __device__ __forceinline__ void k7_load(K7Item& it, int64_t i, const VtgsParams&
                                         const float* __restrict__ grad_geom, bool rot_aligned, const uint32_t* __restrict__ tiles_touched) {
     // a Gaussian with no tile in this rank's band (tile-band sharding) or culled received no gradient here:
     // 4 bytes decide that instead of ~190
-    if (tiles_touched[i] == 0u) {
+    if (tiles_touched != nullptr && tiles_touched[i] == 0u) {
         const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
         it.g0 = z4; it.g1 = z4; it.g2 = z4; it.uq = z4;
         it.hx = -1e30f; it.op = 0.f; it.px = 0.f; it.py = 0.f; it.pz = 0.f; it.ls = 0.f;
@@ -640,7 +643,8 @@ int launch_fused_backward(const VtgsCamera* camera, const VtgsParams* params, co
         unsigned int* ticket = reinterpret_cast<unsigned int*>(grads->pose_scratch ? grads->pose_scratch + (size_t)blocks * POSE_TERMS : nullptr);
         { VTGS_PROF("fused_preprocess_backward_kernel", stream); fused_preprocess_backward_kernel<<<blocks, 256, 0, stream>>>(cam, N, *params, buf->counters->pose_R, pose->depth_row[0],
                                                                      pose->depth_row[1], pose->depth_row[2], geom, buf->grad_geom,
-                                                                     *grads, accumulate, want_pose, buf->counters, ticket, buf->tiles_touched); }
+                                                                     *grads, accumulate, want_pose, buf->counters, ticket,
+                                                                     band_tiles < cam.gx * cam.gy ? buf->tiles_touched : nullptr); }
         VTGS_LAUNCH_CHECK();
     } else if (want_pose && !accumulate) {
         VTGS_CUDA_CHECK(cudaMemsetAsync(grads->cam_unnorm_rot, 0, 4 * sizeof(float), stream));
