@@ -282,3 +282,30 @@ def test_mapping_solver_matches_torch_adam_and_retie():
     cam = pts.cpu().numpy() @ w2c_old[:3, :3].T + w2c_old[:3, 3]
     want = (cam - tn) @ R                                   # R^T (p - t)
     assert np.abs(out - want).max() <= 1e-5
+
+
+def test_get_loss_summed_over_keyframes_before_one_backward():
+    """The reference's all-keyframes mapping branch (src/vtgaussian_slam.py:2609-2666): several get_loss calls,
+    then ONE backward.  Each call must keep its own render state until the backward runs."""
+    fr, p, q, t = _scene(160, 96, n_edge=500)
+    settings, _ = _settings(fr)
+    data = dict(cam=settings, im=torch.tensor(fr["im"], device=DEV), depth=torch.tensor(fr["depth"], device=DEV),
+                w2c=torch.eye(4, device=DEV))
+    poses = [synthetic.perturbed_pose(seed=20 + k, trans_sigma=0.01, rot_deg=0.3) for k in range(3)]
+    grads = {}
+    for backend in ("dropin", "fused"):
+        P = {k: torch.nn.Parameter(torch.tensor(v, device=DEV)) for k, v in p.items()}
+        P["cam_unnorm_rots"] = torch.nn.Parameter(torch.tensor(np.stack([a for a, _ in poses], 1), device=DEV).reshape(1, 4, 3).contiguous())
+        P["cam_trans"] = torch.nn.Parameter(torch.tensor(np.stack([b for _, b in poses], 1), device=DEV).reshape(1, 3, 3).contiguous())
+        total = 0
+        for k in range(3):
+            variables = dict(max_2D_radius=torch.zeros(p["means3D"].shape[0], device=DEV))
+            loss, _, _ = slam_ops.get_loss(P, data, variables, k, dict(im=1.0, depth=1.0), False, 0.5, True, False,
+                                           mapping=True, backend=backend)
+            total = total + loss
+        total.backward()
+        grads[backend] = (total.item(), P["rgb_colors"].grad.clone(), P["log_scales"].grad.clone())
+    a, b = grads["dropin"], grads["fused"]
+    assert abs(a[0] - b[0]) <= 1e-3 * abs(a[0])
+    for ga, gb in zip(a[1:], b[1:]):
+        assert ((ga - gb).abs().max() / ga.abs().max()).item() <= 2e-2

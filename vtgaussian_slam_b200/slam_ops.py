@@ -264,6 +264,7 @@ class _FusedRender(torch.autograd.Function):
                       log_scales=log_scales.detach().contiguous())
         q, t = cam_q.detach().contiguous().reshape(4), cam_t.detach().contiguous().reshape(3)
         img, radii = renderer.forward(params, q, t)
+        renderer.pending_backward = any(ctx.needs_input_grad)
         ctx.renderer, ctx.params, ctx.q, ctx.t = renderer, params, q, t
         ctx.want = (want_gauss, want_pose)
         ctx.pose_shapes = (cam_q.shape, cam_t.shape)
@@ -290,6 +291,7 @@ class _FusedRender(torch.autograd.Function):
         pg = {k: torch.zeros_like(params[k]) for k in params} if want_gauss else None
         pose = (torch.zeros(4, device=g_im.device), torch.zeros(3, device=g_im.device)) if want_pose else None
         r.backward(params, ctx.q, ctx.t, dL_dimage4=dL4, param_grads=pg, pose_grads=pose, means2D_grad=ctx.means2D_grad)
+        r.pending_backward = False
         gq = pose[0].reshape(ctx.pose_shapes[0]) if want_pose else None
         gt = pose[1].reshape(ctx.pose_shapes[1]) if want_pose else None
         if want_gauss:
@@ -313,6 +315,7 @@ class _FusedTrackingLoss(torch.autograd.Function):
         if thres_fn is not None:
             cfg["sil_thres"] = thres_fn(img)
         terms = renderer.tracking_loss(gt_rgb.contiguous(), gt_depth.contiguous(), **cfg).clone()
+        renderer.pending_backward = any(ctx.needs_input_grad)
         ctx.renderer, ctx.p, ctx.q, ctx.t = renderer, p, q, t
         ctx.pose_shapes = (cam_q.shape, cam_t.shape)
         ctx.dL4 = renderer.dL_dimage4          # valid until the renderer's next loss call
@@ -325,6 +328,7 @@ class _FusedTrackingLoss(torch.autograd.Function):
         dq = torch.zeros(4, dtype=torch.float32, device=g_loss.device)
         dt = torch.zeros(3, dtype=torch.float32, device=g_loss.device)
         ctx.renderer.backward(ctx.p, ctx.q, ctx.t, dL_dimage4=ctx.dL4, pose_grads=(dq, dt))
+        ctx.renderer.pending_backward = False
         return (None, None, (dq * g_loss).reshape(ctx.pose_shapes[0]), (dt * g_loss).reshape(ctx.pose_shapes[1]),
                 None, None, None, None)
 
@@ -342,6 +346,7 @@ class _FusedMappingLoss(torch.autograd.Function):
         q, t = cam_q.detach().contiguous().reshape(4), cam_t.detach().contiguous().reshape(3)
         _, radii = renderer.forward(p, q, t)
         terms = renderer.mapping_loss(gt_rgb.contiguous(), gt_depth.contiguous(), w_im=w_im, w_depth=w_depth).clone()
+        renderer.pending_backward = any(ctx.needs_input_grad)
         ctx.renderer, ctx.p, ctx.q, ctx.t, ctx.want_pose = renderer, p, q, t, want_pose
         ctx.pose_shapes = (cam_q.shape, cam_t.shape)
         ctx.means2D_grad = torch.zeros_like(p["means3D"])
@@ -357,6 +362,7 @@ class _FusedMappingLoss(torch.autograd.Function):
         if ctx.want_pose:
             pose = (torch.zeros(4, dtype=torch.float32, device=g_loss.device), torch.zeros(3, dtype=torch.float32, device=g_loss.device))
         ctx.renderer.backward(p, ctx.q, ctx.t, param_grads=pg, pose_grads=pose, means2D_grad=ctx.means2D_grad)
+        ctx.renderer.pending_backward = False
         gq = (pose[0] * g_loss).reshape(ctx.pose_shapes[0]) if pose else None
         gt = (pose[1] * g_loss).reshape(ctx.pose_shapes[1]) if pose else None
         return (None, pg["means3D"] * g_loss, pg["rgb_colors"] * g_loss, pg["unnorm_rotations"] * g_loss,
@@ -381,14 +387,22 @@ def _depth_row_of(w2c):
 
 
 def _renderer_for(cam, n, device):
+    """A FusedRenderer for (camera, N) whose buffers are free: a renderer that still holds the state of a forward
+    whose backward has not run yet (e.g. the reference's all-keyframes mapping branch sums several get_loss calls
+    before one backward, src/vtgaussian_slam.py:2609-2666) is never handed out again."""
     from .fused import FusedRenderer
     key = (id(cam), n, str(device))
-    r = _RENDERERS.get(key)
-    if r is None:
+    pool = _RENDERERS.get(key)
+    if pool is None:
         if len(_RENDERERS) > 4:
             _RENDERERS.clear()
-        r = _RENDERERS[key] = (FusedRenderer(cam, n, device=device), cam)
-    return r[0]
+        pool = _RENDERERS[key] = ([], cam)
+    for r in pool[0]:
+        if not getattr(r, "pending_backward", False):
+            return r
+    r = FusedRenderer(cam, n, device=device)
+    pool[0].append(r)
+    return r
 
 
 def get_loss(params, curr_data, variables, iter_time_idx, loss_weights, use_sil_for_loss,
