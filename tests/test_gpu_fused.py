@@ -309,3 +309,38 @@ def test_get_loss_summed_over_keyframes_before_one_backward():
     assert abs(a[0] - b[0]) <= 1e-3 * abs(a[0])
     for ga, gb in zip(a[1:], b[1:]):
         assert ((ga - gb).abs().max() / ga.abs().max()).item() <= 2e-2
+
+
+def test_tile_band_shards_sum_to_the_full_frame():
+    """Tile-band sharding of tracking (bench.py --gpus N): every band rendered and back-propagated on its own
+    (here sequentially on one GPU) -- band rows bit-identical to the oracle, pose-gradient partials and loss terms
+    sum to the full-frame values."""
+    from vtgaussian_slam_b200.fused import FusedRenderer
+    fr, p, q, t = _scene(192, 112, n_edge=1500)             # 7 tile rows
+    settings, _ = _settings(fr)
+    gp = _gpu_params(p)
+    qd, td = torch.tensor(q, device=DEV), torch.tensor(t, device=DEV)
+    gt_rgb, gt_d = torch.tensor(fr["im"], device=DEV), torch.tensor(fr["depth"], device=DEV)
+    N = p["means3D"].shape[0]
+
+    def run(tile_rows):
+        r = FusedRenderer(settings, N, device=DEV, tile_rows=tile_rows)
+        img, radii = r.forward(gp, qd, td)
+        terms = r.tracking_loss(gt_rgb, gt_d, sil_thres=0.99).clone()
+        dq, dt = torch.zeros(4, device=DEV), torch.zeros(3, device=DEV)
+        r.backward(gp, qd, td, pose_grads=(dq, dt))
+        return img.clone(), radii.clone(), terms.double(), torch.cat([dq, dt]).double()
+
+    full = run((0, 0))
+    bands = [(0, 3), (3, 5), (5, 7)]
+    parts = [run(b) for b in bands]
+    _, ref, _ = _oracle_fused(fr, p, q, t)
+    for (r0, r1), part in zip(bands, parts):
+        ys = slice(r0 * 16, r1 * 16)
+        assert np.array_equal(part[0][:, ys].cpu().numpy(), ref["color"][:, ys])
+        assert torch.equal(part[1], full[1])                                   # radii do not depend on the band
+    terms = sum(pt[2] for pt in parts)
+    assert terms[3].item() == full[2][3].item()                                # mask counts add up exactly
+    assert ((terms[:3] - full[2][:3]).abs() / full[2][:3].abs()).max().item() <= 1e-5
+    g = sum(pt[3] for pt in parts)
+    assert ((g - full[3]).abs().max() / full[3].abs().max()).item() <= 1e-4
