@@ -262,7 +262,7 @@ def run_ours(args, wl):
     kbytes = {       # ALGORITHMIC bytes per launch (DESIGN.md "Kernels and their rooflines")
         "preprocess_kernel": N * (12 + 4 + 16 + 4 + 12) + N * (64 + 4 + 4) + R * 4,
         "scatter_kernel": N * (4 + 16) + R * (8 + 4),
-        "tile_sort_kernel": R * (8 + 8 + 4),
+        "tile_sort_kernel": R * (8 + 8 + 4) + R * 32 + int(2.3 * R) * 8,
         "blend_forward_kernel": R * 52 + P * (6 * 4 + 4 + 4),
         "tracking_loss_kernel": P * (6 * 4 + 4 * 4 + 4 * 4),
         "blend_backward_kernel": R * 52 + P * (4 * 4 + 4 + 4) + N * 48,
@@ -281,7 +281,11 @@ def run_ours(args, wl):
     hbm_floor_s = sum(kbytes.get(k, 0) for k in prof) / (hbm_peak * 1e9)
     roofline = {
         "bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-        "frac": achieved / hbm_peak, "traffic": None,
+        "frac": achieved / hbm_peak,
+        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel per launch, from the ncu --set full capture of
+        # the same workload committed under profiles/r01_kernels_ncu_full.txt (only valid for the full C2 workload at N=1)
+        "traffic": (241.2e6 if (dom_name == "blend_backward_kernel" and world == 1 and not args.small) else None),
+        "traffic_unit": "bytes/launch",
         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)",
         "kernel_us": dom_s * 1e6, "kernel_share_of_step": dom_ms / total_prof_ms,
         "note": "the blend kernels are FP32-issue bound (no dense contraction, tensor cores unused): see pair_tests_per_s",
@@ -346,7 +350,7 @@ def run_ours(args, wl):
         torch.cuda.synchronize(dev)
         e2e_ms = e0.elapsed_time(e1) / k2
         e2e = {"value": 1e3 / e2e_ms, "unit": UNIT, "h2d_bytes_per_step": int(4 * 4 * P), "d2h_bytes_per_step": 4,
-               "ms_per_step": e2e_ms, "api": "slam_ops.get_loss(backend='fused') + loss.backward() + torch.optim.Adam.step()"}
+               "ms_per_step": e2e_ms, "api": "slam_ops.get_loss(backend='fused') + loss.backward() + torch.optim.Adam.step(); frame upload double-buffered on a copy stream"}
 
     # ---- CPU baseline (rank 0, N=1 only): the oracle port on a bounded sample ----------------------
     cpu = None
