@@ -62,7 +62,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
@@ -249,12 +249,13 @@ def run_ours(args, wl):
     solver.use_graph = False
     _lib.profile_enable(True)
     torch.cuda.synchronize(dev)
-    for _ in range(args.steps):
+    prof_steps = min(args.steps, 20)
+    for _ in range(prof_steps):
         solver.step()
     torch.cuda.synchronize(dev)
     prof = _lib.profile_summary()
     _lib.profile_enable(False)
-    launches_per_step = sum(n for n, _ in prof.values()) // args.steps
+    launches_per_step = sum(n for n, _ in prof.values()) // prof_steps
     total_prof_ms = sum(t for _, t in prof.values())
     S = int(solver.r.ws.n_contrib.to(torch.int64).sum().item())
     _, R = solver.r.overflowed()
@@ -290,6 +291,12 @@ def run_ours(args, wl):
         "kernel_us": dom_s * 1e6, "kernel_share_of_step": dom_ms / total_prof_ms,
         "note": "the blend kernels are FP32-issue bound (no dense contraction, tensor cores unused): see pair_tests_per_s",
         "pair_tests_per_launch": S, "pair_tests_per_s": S / dom_s,
+        # issue-slot view of the same kernel: warp instructions per launch from the committed ncu capture
+        # (smsp__inst_executed.sum, C2 at N=1 only) over the live duration, against 148 SM x 4 schedulers x SM clock
+        "issue": ({"warp_inst_per_launch": 243.35e6, "achieved_ginst_s": 243.35e6 / dom_s / 1e9,
+                   "peak_ginst_s": 148 * 4 * float(peaks.get("sm_max_mhz", 1965.0)) / 1e3,
+                   "frac": 243.35e6 / dom_s / 1e9 / (148 * 4 * float(peaks.get("sm_max_mhz", 1965.0)) / 1e3)}
+                  if (dom_name == "blend_backward_kernel" and world == 1 and not args.small) else None),
         "iteration_hbm_floor_us": hbm_floor_s * 1e6, "iteration_hbm_frac": hbm_floor_s / (ms_per_step * 1e-3),
         "per_kernel_us": {k: round(t * 1e3 / n, 2) for k, (n, t) in prof.items()},
     }
@@ -342,7 +349,7 @@ def run_ours(args, wl):
         for _ in range(3):
             e2e_step()
         torch.cuda.synchronize(dev)
-        k2 = max(3, min(args.steps, 20))
+        k2 = max(3, min(args.steps, 100))
         e0.record()
         for _ in range(k2):
             e2e_step()
@@ -434,8 +441,8 @@ def run_mapping(args, wl):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--small", action="store_true", help="300x170 debug workload")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

@@ -27,152 +27,127 @@ from .rasterizer import GaussianRasterizer as Renderer
 
 # ---------------------------------------------------------------------------- small ops
 def build_rotation(q):
-    norm = torch.sqrt(q[:, 0] * q[:, 0] + q[:, 1] * q[:, 1] + q[:, 2] * q[:, 2] + q[:, 3] * q[:, 3])
-    q = q / norm[:, None]
-    rot = torch.zeros((q.size(0), 3, 3), device=q.device, dtype=q.dtype)
-    r, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
-    rot[:, 0, 0] = 1 - 2 * (y * y + z * z)
-    rot[:, 0, 1] = 2 * (x * y - r * z)
-    rot[:, 0, 2] = 2 * (x * z + r * y)
-    rot[:, 1, 0] = 2 * (x * y + r * z)
-    rot[:, 1, 1] = 1 - 2 * (x * x + z * z)
-    rot[:, 1, 2] = 2 * (y * z - r * x)
-    rot[:, 2, 0] = 2 * (x * z - r * y)
-    rot[:, 2, 1] = 2 * (y * z + r * x)
-    rot[:, 2, 2] = 1 - 2 * (x * x + y * y)
-    return rot
+    """[M,4] quaternions (w,x,y,z), normalised here -> [M,3,3] rotation matrices."""
+    w, x, y, z = (q / q.norm(dim=1, keepdim=True)).unbind(dim=1)
+    rows = (1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y),
+            2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x),
+            2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y))
+    return torch.stack(rows, dim=1).reshape(-1, 3, 3)
 
 
 def l1_loss_v1(x, y):
-    return torch.abs((x - y)).mean()
+    return (x - y).abs().mean()
 
 
 def l1_loss_v1_mask(x, y, mask):
-    return (torch.abs((x - y)) * mask).mean()
+    return ((x - y).abs() * mask).mean()
 
 
 def quat_mult(q1, q2):
-    w1, x1, y1, z1 = q1.T
-    w2, x2, y2, z2 = q2.T
-    w = w1 * w2 - x1 * x2 - y1 * y2 - z1 * z2
-    x = w1 * x2 + x1 * w2 + y1 * z2 - z1 * y2
-    y = w1 * y2 - x1 * z2 + y1 * w2 + z1 * x2
-    z = w1 * z2 + x1 * y2 - y1 * x2 + z1 * w2
-    return torch.stack([w, x, y, z]).T
+    """Hamilton product of [M,4] (w,x,y,z) quaternions."""
+    a, b, c, d = q1.unbind(dim=1)
+    e, f, g, h = q2.unbind(dim=1)
+    return torch.stack((a * e - b * f - c * g - d * h,
+                        a * f + b * e + c * h - d * g,
+                        a * g - b * h + c * e + d * f,
+                        a * h + b * g - c * f + d * e), dim=1)
 
 
-def _gaussian_window(window_size, sigma):
-    g = torch.tensor([exp(-(x - window_size // 2) ** 2 / float(2 * sigma ** 2)) for x in range(window_size)])
-    return g / g.sum()
+def _ssim_window(size, sigma, channels, like):
+    k = torch.arange(size, dtype=torch.float32) - size // 2
+    g = torch.tensor([exp(-float(v) ** 2 / (2.0 * sigma ** 2)) for v in k])
+    g = (g / g.sum()).unsqueeze(1)
+    w2d = (g @ g.t()).float()
+    return w2d.expand(channels, 1, size, size).contiguous().to(like.device).type_as(like)
 
 
 def calc_ssim(img1, img2, window_size=11, size_average=True):
-    channel = img1.size(-3)
-    w1 = _gaussian_window(window_size, 1.5).unsqueeze(1)
-    window = w1.mm(w1.t()).float().unsqueeze(0).unsqueeze(0).expand(channel, 1, window_size, window_size).contiguous()
-    window = window.to(img1.device).type_as(img1)
-    pad = window_size // 2
-    mu1 = F.conv2d(img1, window, padding=pad, groups=channel)
-    mu2 = F.conv2d(img2, window, padding=pad, groups=channel)
-    mu1_sq, mu2_sq, mu1_mu2 = mu1.pow(2), mu2.pow(2), mu1 * mu2
-    sigma1_sq = F.conv2d(img1 * img1, window, padding=pad, groups=channel) - mu1_sq
-    sigma2_sq = F.conv2d(img2 * img2, window, padding=pad, groups=channel) - mu2_sq
-    sigma12 = F.conv2d(img1 * img2, window, padding=pad, groups=channel) - mu1_mu2
+    """SSIM with an 11x11 Gaussian window (sigma 1.5), zero padding, c1 = 0.01^2, c2 = 0.03^2."""
+    ch = img1.size(-3)
+    win = _ssim_window(window_size, 1.5, ch, img1)
+    blur = lambda t: F.conv2d(t, win, padding=window_size // 2, groups=ch)
+    mu1, mu2 = blur(img1), blur(img2)
+    var1 = blur(img1 * img1) - mu1.pow(2)
+    var2 = blur(img2 * img2) - mu2.pow(2)
+    cov = blur(img1 * img2) - mu1 * mu2
     c1, c2 = 0.01 ** 2, 0.03 ** 2
-    ssim_map = ((2 * mu1_mu2 + c1) * (2 * sigma12 + c2)) / ((mu1_sq + mu2_sq + c1) * (sigma1_sq + sigma2_sq + c2))
-    if size_average:
-        return ssim_map.mean()
-    return ssim_map.mean(1).mean(1).mean(1)
+    ssim_map = ((2 * mu1 * mu2 + c1) * (2 * cov + c2)) / ((mu1.pow(2) + mu2.pow(2) + c1) * (var1 + var2 + c2))
+    return ssim_map.mean() if size_average else ssim_map.mean(1).mean(1).mean(1)
 
 
 # ---------------------------------------------------------------------------- camera
 def setup_camera(w, h, k, w2c, near=0.01, far=100, device="cuda"):
+    """The 11 raster settings for intrinsics k and world-to-camera w2c (matrices in the rasteriser's row-vector
+    convention: viewmatrix = w2c^T, projmatrix = (P w2c)^T)."""
     fx, fy, cx, cy = k[0][0], k[1][1], k[0][2], k[1][2]
-    w2c = torch.tensor(w2c).to(device).float()
-    cam_center = torch.inverse(w2c)[:3, 3]
-    w2c = w2c.unsqueeze(0).transpose(1, 2)
-    opengl_proj = torch.tensor([[2 * fx / w, 0.0, -(w - 2 * cx) / w, 0.0],
-                                [0.0, 2 * fy / h, -(h - 2 * cy) / h, 0.0],
-                                [0.0, 0.0, far / (far - near), -(far * near) / (far - near)],
-                                [0.0, 0.0, 1.0, 0.0]]).to(device).float().unsqueeze(0).transpose(1, 2)
-    full_proj = w2c.bmm(opengl_proj)
+    world2cam = torch.tensor(w2c).to(device).float()
+    proj = torch.zeros(4, 4, device=device)
+    proj[0, 0], proj[0, 2] = 2 * fx / w, -(w - 2 * cx) / w
+    proj[1, 1], proj[1, 2] = 2 * fy / h, -(h - 2 * cy) / h
+    proj[2, 2], proj[2, 3] = far / (far - near), -(far * near) / (far - near)
+    proj[3, 2] = 1.0
+    view_t = world2cam.t().unsqueeze(0)
     return Camera(image_height=h, image_width=w, tanfovx=w / (2 * fx), tanfovy=h / (2 * fy),
-                  bg=torch.tensor([0, 0, 0], dtype=torch.float32, device=device), scale_modifier=1.0,
-                  viewmatrix=w2c, projmatrix=full_proj, sh_degree=0, campos=cam_center, prefiltered=False)
+                  bg=torch.zeros(3, dtype=torch.float32, device=device), scale_modifier=1.0,
+                  viewmatrix=view_t, projmatrix=view_t.bmm(proj.t().unsqueeze(0)), sh_degree=0,
+                  campos=torch.inverse(world2cam)[:3, 3], prefiltered=False)
 
 
 # ---------------------------------------------------------------------------- render variables
+def _frame_pose(params, time_idx, camera_grad, opt_cam_rot, opt_cam_trans):
+    if camera_grad and opt_cam_rot is not None and opt_cam_trans is not None:
+        return F.normalize(opt_cam_rot[None]), opt_cam_trans
+    q, t = params['cam_unnorm_rots'][..., time_idx], params['cam_trans'][..., time_idx]
+    if not camera_grad:
+        q, t = q.detach(), t.detach()
+    return F.normalize(q), t
+
+
 def transform_to_frame(params, time_idx, gaussians_grad, camera_grad, opt_cam_rot=None, opt_cam_trans=None, latest_w2c=None):
-    if camera_grad:
-        if opt_cam_rot is None and opt_cam_trans is None:
-            cam_rot = F.normalize(params['cam_unnorm_rots'][..., time_idx])
-            cam_tran = params['cam_trans'][..., time_idx]
-        else:
-            cam_rot = F.normalize(opt_cam_rot[None])
-            cam_tran = opt_cam_trans
-    else:
-        cam_rot = F.normalize(params['cam_unnorm_rots'][..., time_idx].detach())
-        cam_tran = params['cam_trans'][..., time_idx].detach()
-    dev = params['means3D'].device
-    rel_w2c = torch.eye(4, device=dev, dtype=params['means3D'].dtype)
+    """World -> camera frame `time_idx`: means3D through [R(q)|t] (optionally pre-multiplied by latest_w2c);
+    anisotropic Gaussians (log_scales [N,3]) also get their quaternions rotated."""
+    cam_rot, cam_tran = _frame_pose(params, time_idx, camera_grad, opt_cam_rot, opt_cam_trans)
+    pts, unnorm_rots = params['means3D'], params['unnorm_rotations']
+    if not gaussians_grad:
+        pts, unnorm_rots = pts.detach(), unnorm_rots.detach()
+    rel_w2c = torch.eye(4, device=pts.device, dtype=pts.dtype)
     rel_w2c[:3, :3] = build_rotation(cam_rot)
     rel_w2c[:3, 3] = cam_tran
     if latest_w2c is not None:
         rel_w2c = latest_w2c @ rel_w2c
-    transform_rots = params['log_scales'].shape[1] != 1     # anisotropic Gaussians are rotated too
-    if gaussians_grad:
-        pts, unnorm_rots = params['means3D'], params['unnorm_rotations']
+    homog = torch.cat((pts, torch.ones_like(pts[:, :1])), dim=1)
+    out = {'means3D': (rel_w2c @ homog.T).T[:, :3]}
+    if params['log_scales'].shape[1] == 1:                 # isotropic: rotations pass through
+        out['unnorm_rotations'] = unnorm_rots
     else:
-        pts, unnorm_rots = params['means3D'].detach(), params['unnorm_rotations'].detach()
-    transformed_gaussians = {}
-    pts_ones = torch.ones(pts.shape[0], 1, device=dev, dtype=pts.dtype)
-    pts4 = torch.cat((pts, pts_ones), dim=1)
-    transformed_gaussians['means3D'] = (rel_w2c @ pts4.T).T[:, :3]
-    if transform_rots:
-        transformed_gaussians['unnorm_rotations'] = quat_mult(cam_rot, F.normalize(unnorm_rots))
-    else:
-        transformed_gaussians['unnorm_rotations'] = unnorm_rots
-    return transformed_gaussians
+        out['unnorm_rotations'] = quat_mult(cam_rot, F.normalize(unnorm_rots))
+    return out
 
 
-def _log_scales3(params):
-    if params['log_scales'].shape[1] == 1:
-        return torch.tile(params['log_scales'], (1, 3))
-    return params['log_scales']
+def _activated(params, transformed_gaussians, colors):
+    ls = params['log_scales']
+    return {
+        'means3D': transformed_gaussians['means3D'],
+        'colors_precomp': colors,
+        'rotations': F.normalize(transformed_gaussians['unnorm_rotations']),
+        'opacities': torch.sigmoid(params['logit_opacities']),
+        'scales': torch.exp(ls.expand(-1, 3) if ls.shape[1] == 1 else ls),
+        'means2D': torch.zeros_like(params['means3D'], requires_grad=True) + 0,
+    }
 
 
 def transformed_params2rendervar(params, transformed_gaussians):
-    return {
-        'means3D': transformed_gaussians['means3D'],
-        'colors_precomp': params['rgb_colors'],
-        'rotations': F.normalize(transformed_gaussians['unnorm_rotations']),
-        'opacities': torch.sigmoid(params['logit_opacities']),
-        'scales': torch.exp(_log_scales3(params)),
-        'means2D': torch.zeros_like(params['means3D'], requires_grad=True) + 0,
-    }
+    return _activated(params, transformed_gaussians, params['rgb_colors'])
 
 
 def get_depth_and_silhouette(pts_3D, w2c):
-    pts4 = torch.cat((pts_3D, torch.ones_like(pts_3D[:, :1])), dim=-1)
-    pts_in_cam = (w2c @ pts4.transpose(0, 1)).transpose(0, 1)
-    depth_z = pts_in_cam[:, 2].unsqueeze(-1)
-    depth_z_sq = torch.square(depth_z)
-    depth_silhouette = torch.zeros((pts_3D.shape[0], 3), device=pts_3D.device, dtype=pts_3D.dtype)
-    depth_silhouette[:, 0] = depth_z.squeeze(-1)
-    depth_silhouette[:, 1] = 1.0
-    depth_silhouette[:, 2] = depth_z_sq.squeeze(-1)
-    return depth_silhouette
+    """Per-Gaussian 'colours' (z, 1, z^2) with z the depth of the centre in the frame w2c."""
+    z = pts_3D @ w2c[2, :3] + w2c[2, 3]
+    return torch.stack((z, torch.ones_like(z), z * z), dim=1)
 
 
 def transformed_params2depthplussilhouette(params, w2c, transformed_gaussians):
-    return {
-        'means3D': transformed_gaussians['means3D'],
-        'colors_precomp': get_depth_and_silhouette(transformed_gaussians['means3D'], w2c),
-        'rotations': F.normalize(transformed_gaussians['unnorm_rotations']),
-        'opacities': torch.sigmoid(params['logit_opacities']),
-        'scales': torch.exp(_log_scales3(params)),
-        'means2D': torch.zeros_like(params['means3D'], requires_grad=True) + 0,
-    }
+    return _activated(params, transformed_gaussians, get_depth_and_silhouette(transformed_gaussians['means3D'], w2c))
 
 
 def initialize_optimizer(params, lrs_dict, tracking):
