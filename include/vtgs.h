@@ -110,7 +110,7 @@ typedef struct VtgsBuffers {
     uint32_t*     tiles_touched;  /* [N]                                                   */
     uint32_t*     tile_counts;    /* [tiles]  scratch (zeroed by forward)                  */
     uint32_t*     tile_ranges;    /* [tiles][2] = {begin, end} into point_list             */
-    uint64_t*     pair_keys;      /* [pair_capacity] (depth_bits<<32 | gaussian id)        */
+    uint64_t*     pair_keys;      /* [pair_capacity] depth_bits<<32 | gaussian id<<8 | region mask */
     uint32_t*     point_list;     /* [pair_capacity] sorted Gaussian ids                   */
     float*        final_T;        /* [H*W]                                                 */
     uint32_t*     n_contrib;      /* [H*W]                                                 */

@@ -38,12 +38,12 @@ def _check_binning(r, N):
     nz = lens > 0
     starts = rng[nz, 0]
     assert torch.equal(starts, torch.cumsum(lens[nz], 0) - lens[nz])          # ranges partition [0, R) in tile order
-    keys = ws.pair_keys[:R]                                                     # (depth_bits << 32 | id), per-tile segments
+    keys = ws.pair_keys[:R]                                                     # (depth_bits << 32 | id << 8 | region mask), per-tile segments
     inc = keys[1:] > keys[:-1]
     boundary = torch.zeros(R - 1, dtype=torch.bool, device=keys.device)
     boundary[(rng[nz, 1][:-1] - 1).clamp(min=0)] = True                         # last element of every non-empty tile
     assert bool((inc | boundary).all().item()), "keys must be strictly increasing inside every tile"
-    assert torch.equal(ws.point_list[:R].to(torch.int64), keys & 0xFFFFFFFF)
+    assert torch.equal(ws.point_list[:R].to(torch.int64), (keys & 0xFFFFFFFF) >> 8)       # low word = id << 8 | region mask
     # n_contrib never exceeds its tile's list length
     H, W = r.H, r.W
     gy, gx = (H + 15) // 16, (W + 15) // 16

@@ -241,18 +241,24 @@ scatter_kernel(int64_t N, int gx, const GeomRecord* __restrict__ geom, const uin
     const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
     int minx = 0, miny = 0, maxx = 0, maxy = 0;
     uint64_t key = 0;
+    float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (i < N && tiles_touched[i] != 0) {
         const float4 q3 = geom[i].q3;
+        q0 = geom[i].q0;
         const uint32_t rmin = __float_as_uint(q3.z), rmax = __float_as_uint(q3.w);
         minx = rmin & 0xffff; miny = rmin >> 16; maxx = rmax & 0xffff; maxy = rmax >> 16;
-        key = ((uint64_t)__float_as_uint(q3.x) << 32) | (uint64_t)(uint32_t)i;
+        key = ((uint64_t)__float_as_uint(q3.x) << 32) | ((uint64_t)(uint32_t)i << 8);
     }
     warp_tile_walk(minx, miny, maxx, maxy, gx, [&](int tile, uint32_t peers, int rank, bool leader) {
         uint32_t base = 0;
         if (leader) base = ranges[2 * tile] + atomicAdd(&tile_cursor[tile], (uint32_t)__popc(peers));
         base = __shfl_sync(peers, base, __ffs(peers) - 1);
         const uint32_t pos = base + (uint32_t)rank;
-        if (pos < ranges[2 * tile + 1]) pair_keys[pos] = key;
+        // low 8 bits: which of this tile's 8 warp regions the splat's alpha >= 1/255 box touches (ids are unique, so
+        // these bits never decide the order; the sort kernel reads them back instead of gathering the record again)
+        const int tx = tile % gx, ty = tile / gx;
+        const uint32_t rmask = region_mask(q0, (float)(tx * 16), (float)(ty * 16));
+        if (pos < ranges[2 * tile + 1]) pair_keys[pos] = key | rmask;
     });
 }
 
@@ -360,7 +366,7 @@ __device__ __forceinline__ void sort_segment_regs(uint64_t* __restrict__ s_x, ui
 #pragma unroll
     for (int e = 0; e < E; ++e) {
         const int i = tid * E + e;
-        if (i < n) { keys[i] = v[e]; ids[i] = (uint32_t)v[e]; }
+        if (i < n) { keys[i] = v[e]; ids[i] = (uint32_t)v[e] >> 8; }
     }
 }
 
@@ -370,8 +376,8 @@ __device__ __forceinline__ void sort_segment_regs(uint64_t* __restrict__ s_x, ui
 // walk only their own region's list: the culling is done once per (tile, splat) here instead of once per
 // (warp, splat) in each of the two blend kernels.
 // Arena: region r of a tile with list [rb, re) owns slots [8 rb + r (re - rb), 8 rb + (r + 1)(re - rb)).
-__device__ __forceinline__ void build_region_lists(const uint32_t* __restrict__ ids, int n, uint32_t rb, int tile, float tox, float toy,
-                                                   const GeomRecord* __restrict__ geom, uint2* __restrict__ region_pairs,
+__device__ __forceinline__ void build_region_lists(const uint64_t* __restrict__ keys, int n, uint32_t rb, int tile,
+                                                   uint2* __restrict__ region_pairs,
                                                    uint32_t* __restrict__ region_cnt, uint32_t* s_cnt /* [8][8] */, uint32_t* s_base /* [8] */) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid < 8) s_base[tid] = 0;
@@ -381,8 +387,9 @@ __device__ __forceinline__ void build_region_lists(const uint32_t* __restrict__ 
         const int i = base + tid;
         uint32_t rmask = 0, id = 0;
         if (i < n) {
-            id = ids[i];
-            rmask = region_mask(geom[id].q0, tox, toy);
+            const uint32_t lo = (uint32_t)keys[i];          // (id << 8) | region mask, written by the scatter kernel
+            id = lo >> 8;
+            rmask = lo & 0xffu;
         }
         uint32_t bal[8];
 #pragma unroll
@@ -440,17 +447,16 @@ tile_sort_kernel(const __grid_constant__ CamConst cam, const uint32_t* __restric
             bitonic_network(s_keys, n, npad);
             for (int i = threadIdx.x; i < n; i += blockDim.x) {
                 const uint64_t k = s_keys[i];
-                point_list[b + i] = (uint32_t)k;
+                point_list[b + i] = (uint32_t)k >> 8;
                 pair_keys[b + i] = k;
             }
         } else {
             __syncthreads();
             bitonic_network(pair_keys + b, n, npad);
-            for (int i = threadIdx.x; i < n; i += blockDim.x) point_list[b + i] = (uint32_t)pair_keys[b + i];
+            for (int i = threadIdx.x; i < n; i += blockDim.x) point_list[b + i] = (uint32_t)pair_keys[b + i] >> 8;
         }
     }
-    const int tile_x = tile % cam.gx, tile_y = tile / cam.gx;
-    build_region_lists(point_list + b, n, b, tile, (float)(tile_x * 16), (float)(tile_y * 16), geom, region_pairs, region_cnt, s_cnt, s_base);
+    build_region_lists(pair_keys + b, n, b, tile, region_pairs, region_cnt, s_cnt, s_base);
 }
 
 // =============================== K5': forward blend ========================================
@@ -595,6 +601,7 @@ int launch_forward(const VtgsCamera* camera, int64_t N, bool fused, const FrontE
     const CamConst cam = make_cam_const(*camera);
     const int num_tiles = cam.gx * cam.gy;
     if (cam.gx > 0xffff || cam.gy > 0xffff) { set_error("image too large for packed tile rects"); return VTGS_E_INVALID; }
+    if (N >= (int64_t)1 << 24) { set_error("at most 2^24 - 1 Gaussians per render (24-bit id in the sort key)"); return VTGS_E_UNSUPPORTED; }
     GeomRecord* geom = reinterpret_cast<GeomRecord*>(buf->geom);
     VTGS_CUDA_CHECK(cudaMemsetAsync(buf->tile_counts, 0, sizeof(uint32_t) * num_tiles, stream));
     const int blocks = (int)((N + 255) / 256);
