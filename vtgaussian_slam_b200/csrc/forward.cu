@@ -18,6 +18,7 @@
 //    upstream pair tests disappear) while list positions (n_contrib) stay exact.
 #include <stdarg.h>
 #include <stdio.h>
+#include <string.h>
 
 #include "blend_common.cuh"
 #include "kernels.h"
@@ -459,6 +460,9 @@ tile_sort_kernel(const __grid_constant__ CamConst cam, const uint32_t* __restric
     build_region_lists(pair_keys + b, n, b, tile, region_pairs, region_cnt, s_cnt, s_base);
 }
 
+#ifdef VTGS_STATS
+__device__ unsigned long long vtgs_stats[8];
+#endif
 // =============================== K5': forward blend ========================================
 // Block = one 16x16 tile, 8 INDEPENDENT warps (no block barrier): warp w owns pixel region w and walks
 // that region's list (built by the sort kernel) in groups of 32 splats -- software-prefetched gathers of
@@ -495,6 +499,9 @@ blend_forward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __res
     float C0 = 0.f, C1 = 0.f, C2 = 0.f, C3 = 0.f, C4 = 0.f, C5 = 0.f;
     uint32_t last = 0, applied = 0;
     bool done = !inside;
+#ifdef VTGS_STATS
+    int st_c2 = 0, st_c4 = 0;
+#endif
 
     auto blend_one = [&](const float4 a, const float alpha, const int e) -> bool {
         if (alpha < VTGS_ALPHA_MIN) return true;
@@ -554,6 +561,25 @@ blend_forward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __res
             if (two && !blend_one(b0, alpha_b, eb)) break;
         }
         masks[g * 32 + lane] = applied;                 // which splats of this group each pixel blended (for K6')
+#ifdef VTGS_STATS
+        {
+            const int c = __popc(applied);
+            st_c2 += c; st_c4 += c;
+            auto wmax = [&](int v) { for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(VTGS_FULL_MASK, v, o)); return v; };
+            auto wsum = [&](int v) { for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(VTGS_FULL_MASK, v, o); return v; };
+            const int mx1 = wmax(c), tot = wsum(c);
+            int mx2 = 0, mx4 = 0;
+            if ((g & 1) == 1) { mx2 = wmax(st_c2); st_c2 = 0; }
+            if ((g & 3) == 3) { mx4 = wmax(st_c4); st_c4 = 0; }
+            if (lane == 0) {
+                atomicAdd(&vtgs_stats[0], (unsigned long long)tot);
+                atomicAdd(&vtgs_stats[1], (unsigned long long)mx1);
+                atomicAdd(&vtgs_stats[2], (unsigned long long)mx2);
+                atomicAdd(&vtgs_stats[3], (unsigned long long)mx4);
+                atomicAdd(&vtgs_stats[4], 1ull);
+            }
+        }
+#endif
         applied = 0;
         all_done = __all_sync(VTGS_FULL_MASK, done);
     }
@@ -635,6 +661,17 @@ int launch_forward(const VtgsCamera* camera, int64_t N, bool fused, const FrontE
         else { VTGS_PROF("blend_forward_kernel", stream); blend_forward_kernel<false><<<band_tiles, 256, 0, stream>>>(cam, buf->tile_ranges, reinterpret_cast<const uint2*>(buf->region_pairs), buf->region_cnt, buf->region_masks, buf->region_done, geom, out_color, out_depth, buf->final_T, buf->n_contrib); }
         VTGS_LAUNCH_CHECK();
     }
+#ifdef VTGS_STATS
+    {
+        unsigned long long h[8];
+        cudaStreamSynchronize(stream);
+        cudaMemcpyFromSymbol(h, vtgs_stats, sizeof(h));
+        fprintf(stderr, "[stats] contributions %llu  sum_max(SG1) %llu  sum_max(SG2) %llu  sum_max(SG4) %llu  groups %llu  -> lane efficiency SG1 %.3f SG2 %.3f SG4 %.3f\n",
+                h[0], h[1], h[2], h[3], h[4], h[0] / (32.0 * h[1]), h[0] / (32.0 * h[2]), h[0] / (32.0 * h[3]));
+        memset(h, 0, sizeof(h));
+        cudaMemcpyToSymbol(vtgs_stats, h, sizeof(h));
+    }
+#endif
     if (band_tiles < num_tiles && !fused) {       // API mode returns complete planes; the fused solvers only ever read their band
         const size_t P = (size_t)cam.W * cam.H;
         { VTGS_PROF("fill_outside_band_kernel", stream); fill_outside_band_kernel<<<(unsigned)((P + 255) / 256), 256, 0, stream>>>(cam, fused ? 6 : 3, out_color, out_depth, buf->final_T, buf->n_contrib); }

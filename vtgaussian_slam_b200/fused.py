@@ -260,6 +260,19 @@ class TrackingSolver:
     def loss_terms(self):
         return self.msg[8:16]
 
+    def check(self, grow=True):
+        """One blocking read of the device counters (call once per frame, not per iteration): raises if the pair
+        buffers overflowed (R > pair_capacity: that iteration's render was truncated); with grow=True the buffers
+        are first enlarged so that the next frame fits."""
+        overflow, R = self.r.overflowed()
+        if overflow:
+            if grow:
+                self.r.reserve_pairs(int(R * 1.5) + 65536)
+                self._graph = None          # buffer addresses changed: re-capture
+            raise _lib.VtgsError(f"pair buffer overflow: R = {R} > capacity; buffers "
+                                 f"{'were grown -- re-run the frame' if grow else 'unchanged'}")
+        return R
+
 
 class MappingSolver:
     """The reference's mapping iteration (src/vtgaussian_slam.py:2525-2702) over a set of
