@@ -154,3 +154,24 @@ def test_autograd_module_matches_oracle_and_rejects_cpu():
     with pytest.raises(RuntimeError):
         rend(means3D=t["means3D"].cpu(), means2D=m2d.cpu(), opacities=op.cpu(), colors_precomp=t["colors"].cpu(),
              scales=t["scales"].cpu(), rotations=t["rotations"].cpu())
+
+
+def test_giant_offscreen_and_degenerate_splats():
+    """Robustness of the binning: splats larger than the image (every tile, all 8 regions), splats far off screen
+    (saturating float->int casts in getRect), needle-thin and tiny splats, zero / >1 opacities, huge depth spread."""
+    W, H = 150, 90
+    K, sc = synthetic.random_scene(600, W, H, seed=21, anisotropic=True, scale_px=(0.2, 3.0))
+    f = K[0, 0]
+    sc["scales"][:20] *= 200.0                                   # giants: radius >> image
+    sc["scales"][20:40, 0] *= 1e-4                               # needles
+    sc["scales"][40:60] *= 1e-3                                  # sub-pixel
+    sc["means3D"][60:80, 0] = 1e6                                # far off screen (x), in front of the camera
+    sc["means3D"][80:90, 2] = 1e4                                # very far
+    sc["means3D"][90:100, 2] = 0.2000001                         # just beyond the near cull
+    sc["opacities"][100:110] = 0.0
+    sc["opacities"][110:120] = 1.5                               # > 1 (clamped to 0.99 by the blend)
+    sc["opacities"][120:130] = 1.0 / 255.0                       # exactly the alpha threshold
+    ref, got, bit_exact = _run_case(W, H, sc, K, seed=21)
+    assert bit_exact
+    gx, gy = (W + 15) // 16, (H + 15) // 16
+    assert ref["tiles_touched"].max() == gx * gy                 # at least one giant covers every tile
