@@ -239,7 +239,9 @@ typedef struct VtgsPose {
  *   out_image7[7,H,W] = {r, g, b, depth, silhouette, depth^2, <unused>}: channel order
  *   is im[0..2] then depth_sil[0..2] of the reference.  Only 6 planes are written.
  *   radii[N] as the RGB pass would return them.
- *   With a tile-row band (VtgsCamera.tile_row_begin/end) only the band's rows of the planes are written.
+ *   With a tile-row band (VtgsCamera.tile_row_begin/end) only the band's rows of the planes are written and
+ *   radii[i] is only guaranteed for Gaussians that touch the band (others may be reported as 0: they are
+ *   rejected by a cheap conservative bound before the full projection).
  */
 VTGS_API int vtgs_fused_forward(const VtgsCamera* cam, const VtgsParams* params, const VtgsPose* pose,
                        float* out_image6, int32_t* radii, VtgsBuffers* buf, void* stream);

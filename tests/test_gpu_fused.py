@@ -338,7 +338,8 @@ def test_tile_band_shards_sum_to_the_full_frame():
     for (r0, r1), part in zip(bands, parts):
         ys = slice(r0 * 16, r1 * 16)
         assert np.array_equal(part[0][:, ys].cpu().numpy(), ref["color"][:, ys])
-        assert torch.equal(part[1], full[1])                                   # radii do not depend on the band
+        same_or_skipped = (part[1] == full[1]) | (part[1] == 0)                  # radii: full value, or 0 when the
+        assert bool(same_or_skipped.all().item())                                #        splat cannot reach the band
     terms = sum(pt[2] for pt in parts)
     assert terms[3].item() == full[2][3].item()                                # mask counts add up exactly
     assert ((terms[:3] - full[2][:3]).abs() / full[2][:3].abs()).max().item() <= 1e-5

@@ -79,6 +79,7 @@ preprocess_kernel(const __grid_constant__ CamConst cam, int64_t N, FrontEnd fe,
     const int tid = threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * 256;
     const bool rot_aligned = (reinterpret_cast<uintptr_t>(rotations) & 15) == 0;
+    const bool band_active = cam.row0 > 0 || cam.row1 < cam.gy;
     float Rt[12];
     if (FUSED) {
         // every thread derives the pose matrix itself (a few dozen instructions, once per persistent thread);
@@ -128,7 +129,25 @@ preprocess_kernel(const __grid_constant__ CamConst cam, int64_t N, FrontEnd fe,
             }
 
             SplatGeom g;
-            splat_geometry(cam, x, y, z, sx, sy, sz, qr, qx, qy, qz, g);
+            bool outside_band = false;
+            if (FUSED && band_active) {
+                // Tile-band sharding: a conservative bound of the splat's screen-space extent decides in ~40
+                // instructions that it cannot reach this rank's rows, skipping the ~900-instruction projection.
+                // (radius <= sigma_mult * sqrt(trace(cov2D)), trace <= s^2 (|J0|^2 + |J1|^2) + 2 * lowpass with the
+                // clamped Jacobian; 1 % + 3 px of slack cover the approximate arithmetic and the ceil.)
+                const float tz_ = xform_row(cam.view, 2, x, y, z);
+                if (tz_ > VTGS_NEAR_CULL) {
+                    const float hy_ = xform_row(cam.proj, 1, x, y, z), hw_ = xform_row(cam.proj, 3, x, y, z);
+                    const float py_ = ((__fdividef(hy_, hw_ + VTGS_EPS_W) + 1.0f) * (float)cam.H - 1.0f) * 0.5f;
+                    const float smax = fmaxf(sx, fmaxf(sy, sz)) * cam.scale_modifier, itz = __fdividef(1.0f, tz_);
+                    const float tr = smax * smax * itz * itz * (cam.focal_x * cam.focal_x * (1.0f + cam.limx * cam.limx) +
+                                                                 cam.focal_y * cam.focal_y * (1.0f + cam.limy * cam.limy)) + 2.0f * VTGS_LOWPASS;
+                    const float rb = cam.sigma_mult * sqrtf(tr) * 1.01f + 3.0f;
+                    outside_band = (py_ - rb > (float)(cam.row1 * 16)) || (py_ + rb + 16.0f < (float)(cam.row0 * 16));
+                }
+            }
+            if (outside_band) { g.radius = 0; g.depth = 0.0f; }
+            else splat_geometry(cam, x, y, z, sx, sy, sz, qr, qx, qy, qz, g);
             if (!FUSED) c3 = g.depth;
 
             GeomRecord rec;
