@@ -1,0 +1,73 @@
+"""CPU: host-side pieces of the compact SLAM loop (pose algebra, posed synthetic frames)."""
+import numpy as np
+
+from vtgaussian_slam_b200 import synthetic
+from vtgaussian_slam_b200.slam_loop import matrix_from_quat, propagate_pose, quat_from_matrix, ate_rmse
+
+
+def _rand_rot(rng):
+    q = rng.normal(size=4)
+    return matrix_from_quat(q, np.zeros(3))[:3, :3]
+
+
+def test_quaternion_matrix_round_trip():
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        R = _rand_rot(rng)
+        q = quat_from_matrix(R)
+        assert abs(np.linalg.norm(q) - 1) < 1e-12 and q[0] >= 0
+        assert np.allclose(matrix_from_quat(q, np.zeros(3))[:3, :3], R, atol=1e-12)
+    # the trace <= 0 branches (rotations by ~pi about each axis)
+    for ax in range(3):
+        R = -np.eye(3)
+        R[ax, ax] = 1.0
+        assert np.allclose(matrix_from_quat(quat_from_matrix(R), np.zeros(3))[:3, :3], R, atol=1e-12)
+
+
+def test_constant_velocity_propagation_is_exact_for_a_constant_twist():
+    rng = np.random.default_rng(1)
+    D = np.eye(4)
+    D[:3, :3] = _rand_rot(rng)
+    D[:3, 3] = rng.normal(0, 0.1, 3)
+    c0 = np.eye(4)
+    c0[:3, :3] = _rand_rot(rng)
+    c1, c2 = D @ c0, D @ D @ c0                       # c2w[t] = D c2w[t-1]
+    pred = propagate_pose(np.linalg.inv(c1), np.linalg.inv(c0))
+    assert np.allclose(np.linalg.inv(pred), c2, atol=1e-10)
+
+
+def test_trajectory_starts_at_identity_with_the_requested_step():
+    T = synthetic.trajectory(40, step_m=0.01, step_deg=0.3)
+    assert np.allclose(T[0], np.eye(4))
+    step = np.linalg.norm(np.diff(T[:, :3, 3], axis=0), axis=1)
+    assert 0.002 < step.mean() < 0.03
+    for M in T:
+        assert np.allclose(M[:3, :3] @ M[:3, :3].T, np.eye(3), atol=1e-12)
+    assert ate_rmse(T, T) == 0.0
+
+
+def test_posed_frame_hit_points_reproject_to_their_pixels():
+    W, H, K = synthetic.intrinsics("tum_fr1", 80, 60)
+    c2w = synthetic.trajectory(30, 0.02, 1.0)[17]
+    depth, pts = synthetic._room_depth(W, H, K, c2w=c2w)
+    w2c = np.linalg.inv(c2w)
+    cam = pts.reshape(-1, 3) @ w2c[:3, :3].T + w2c[:3, 3]
+    assert np.allclose(cam[:, 2], depth.reshape(-1), atol=1e-9)
+    u = cam[:, 0] / cam[:, 2] * K[0, 0] + K[0, 2] - 0.5
+    v = cam[:, 1] / cam[:, 2] * K[1, 1] + K[1, 2] - 0.5
+    xg, yg = np.meshgrid(np.arange(W), np.arange(H))
+    assert np.allclose(u, xg.reshape(-1), atol=1e-6) and np.allclose(v, yg.reshape(-1), atol=1e-6)
+    # every hit lies on the room's surfaces or on a slab
+    x, y, z = pts[..., 0], pts[..., 1], pts[..., 2]
+    on_wall = (np.isclose(x, synthetic.ROOM["x"][0]) | np.isclose(x, synthetic.ROOM["x"][1]) | np.isclose(y, synthetic.ROOM["y"][0]) |
+               np.isclose(y, synthetic.ROOM["y"][1]) | np.isclose(z, synthetic.ROOM["z"][0]) | np.isclose(z, synthetic.ROOM["z"][1]))
+    on_slab = np.zeros_like(on_wall)
+    for s in synthetic.SLABS:
+        on_slab |= np.isclose(z, s[4])
+    assert bool((on_wall | on_slab).all())
+
+
+def test_identity_pose_frame_equals_the_unposed_frame():
+    a = synthetic.make_frame("tum_fr1", 64, 48, seed=5)
+    b = synthetic.make_frame("tum_fr1", 64, 48, seed=5, c2w=np.eye(4))
+    assert np.array_equal(a["depth"], b["depth"]) and np.array_equal(a["im"], b["im"])

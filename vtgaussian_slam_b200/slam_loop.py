@@ -1,0 +1,209 @@
+"""A compact view-tied SLAM loop over the fused solvers: the caller side of the hot path (SURVEY.md 8(f) rows
+N1/N2 in embryo, BASELINE config "TUM fr1_desk-shaped full tracking+mapping loop over synthetic frames").
+
+What it mirrors of the reference's `rgbd_slam` (src/vtgaussian_slam.py:1574-2876), and what it leaves out:
+
+  * sections ("base frames", :1620-1760): every `baseframe_every` frames a new set of view-tied Gaussians is
+    built from that frame's RGB-D at its tracked pose -- `section_from_frame` follows get_pointcloud (:76-128:
+    one Gaussian per valid pixel at ((x-cx+0.5)/fx z, (y-cy+0.5)/fy z, z), z = 1.005 depth, isotropic
+    scale z / ((fx+fy)/2)) and initialize_params (:132-177: identity quaternions, logit opacity 0);
+  * pose initialisation (:817-885): constant velocity, init_c2w = c2w[t-1] inv(c2w[t-2]) c2w[t-1];
+  * tracking (:1794-1970): `track_iters` x (render -> masked L1 -> backward to the pose -> Adam), best pose by
+    loss kept -- TrackingSolver, one CUDA graph replay per iteration;
+  * mapping (:2525-2702): `map_iters` x (sum of keyframe losses -> backward -> Adam over rgb / opacity / scale of
+    the current section) over the section's most recent keyframes -- MappingSolver.
+  Left out (not on the hot path, SURVEY.md 8 "out of scope" / later rows): edge-mask densification on the 2x grid,
+  cross-section overlap selection and the frozen-section loss, silhouette-driven Gaussian addition, checkpoints.
+
+Everything on the device runs through the CUDA library; there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import time
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from .fused import MappingSolver, TrackingSolver
+from .rasterizer import GaussianRasterizationSettings
+from . import synthetic
+
+
+@dataclass
+class LoopConfig:
+    track_iters: int = 40                 # configs/replica/room0.py:62 uses 60 (BASELINE quotes 40); fr1_config.py:63 uses 200
+    map_iters: int = 15                   # room0.py:89 100, fr1_config.py:80 30
+    baseframe_every: int = 10             # fr1_config.py:36 30
+    map_every: int = 5
+    keyframes_per_map: int = 4
+    lr_rot: float = 4e-4                  # room0.py:78-86
+    lr_trans: float = 2e-3
+    track_w_im: float = 0.5
+    track_w_depth: float = 1.0            # fr1_config.py:66 (Replica: 0.025... see DESIGN.md)
+    sil_thres: float = 0.99
+    map_w_im: float = 1.0
+    map_w_depth: float = 1.0
+    map_lrs: dict = field(default_factory=lambda: dict(rgb_colors=0.0025, logit_opacities=0.05, log_scales=0.005))
+    use_graph: bool = True
+
+
+def quat_from_matrix(R):
+    """Unit quaternion (w, x, y, z) of a 3x3 rotation (numerically safe branch selection)."""
+    R = np.asarray(R, np.float64)
+    tr = np.trace(R)
+    if tr > 0:
+        s = np.sqrt(tr + 1.0) * 2
+        q = [0.25 * s, (R[2, 1] - R[1, 2]) / s, (R[0, 2] - R[2, 0]) / s, (R[1, 0] - R[0, 1]) / s]
+    else:
+        i = int(np.argmax(np.diag(R)))
+        j, k = (i + 1) % 3, (i + 2) % 3
+        s = np.sqrt(1.0 + R[i, i] - R[j, j] - R[k, k]) * 2
+        q = [0.0] * 4
+        q[0] = (R[k, j] - R[j, k]) / s
+        q[1 + i] = 0.25 * s
+        q[1 + j] = (R[j, i] + R[i, j]) / s
+        q[1 + k] = (R[k, i] + R[i, k]) / s
+    q = np.asarray(q)
+    return q / np.linalg.norm(q) * (1.0 if q[0] >= 0 else -1.0)
+
+
+def matrix_from_quat(q, t):
+    """4x4 [R(q/|q|) | t] (the reference's build_rotation, utils/slam_external.py:25-42)."""
+    w, x, y, z = np.asarray(q, np.float64) / np.linalg.norm(q)
+    R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                  [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                  [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+    M = np.eye(4)
+    M[:3, :3] = R
+    M[:3, 3] = np.asarray(t, np.float64)
+    return M
+
+
+def propagate_pose(w2c_prev1, w2c_prev2):
+    """Constant-velocity initial guess (reference initialize_camera_pose, :838-875)."""
+    c1, c2 = np.linalg.inv(w2c_prev1), np.linalg.inv(w2c_prev2)
+    return np.linalg.inv(c1 @ np.linalg.inv(c2) @ c1)
+
+
+def section_from_frame(rgb, depth, K, c2w, device, factor=1.005):
+    """View-tied Gaussians of one RGB-D frame in the world frame (reference get_pointcloud + initialize_params).
+    rgb[3,H,W], depth[1,H,W] CUDA tensors; pixels with depth <= 0 are dropped."""
+    H, W = depth.shape[-2:]
+    fx, fy, cx, cy = float(K[0][0]), float(K[1][1]), float(K[0][2]), float(K[1][2])
+    f32 = dict(dtype=torch.float32, device=device)
+    xx = ((torch.arange(W, **f32) - cx + 0.5) / fx).repeat(H)
+    yy = ((torch.arange(H, **f32) - cy + 0.5) / fy).repeat_interleave(W)
+    z = depth.reshape(-1).to(**f32) * factor
+    keep = z > 0
+    pts = torch.stack((xx * z, yy * z, z), -1)
+    M = torch.as_tensor(np.asarray(c2w, np.float32), device=device)
+    pts = pts @ M[:3, :3].T + M[:3, 3]
+    cols = rgb.to(**f32).reshape(3, -1).T
+    scale = z / ((fx + fy) / 2.0)
+    n = int(keep.sum().item())
+    rots = torch.zeros((n, 4), **f32)
+    rots[:, 0] = 1.0
+    return dict(means3D=pts[keep].contiguous(), rgb_colors=cols[keep].contiguous(), unnorm_rotations=rots,
+                logit_opacities=torch.zeros((n, 1), **f32), log_scales=torch.log(scale[keep])[:, None].contiguous())
+
+
+def ate_rmse(est_c2w, gt_c2w):
+    """Translation RMSE between two trajectories that share their first pose (no alignment: both are relative to frame 0)."""
+    e = np.asarray(est_c2w)[:, :3, 3] - np.asarray(gt_c2w)[:, :3, 3]
+    return float(np.sqrt((e ** 2).sum(-1).mean()))
+
+
+class ViewTiedSLAM:
+    """frames: dicts with 'im'[3,H,W], 'depth'[1,H,W] (numpy or tensors), optional 'c2w' ground truth."""
+
+    def __init__(self, W, H, K, cfg: LoopConfig | None = None, device="cuda:0"):
+        self.W, self.H, self.K = int(W), int(H), np.asarray(K, np.float64)
+        self.cfg = cfg or LoopConfig()
+        self.device = torch.device(device)
+        s = synthetic.setup_camera(self.W, self.H, self.K, np.eye(4))
+        t = lambda a: torch.as_tensor(a, dtype=torch.float32, device=self.device)
+        self.settings = GaussianRasterizationSettings(
+            image_height=s["image_height"], image_width=s["image_width"], tanfovx=s["tanfovx"], tanfovy=s["tanfovy"],
+            bg=t(s["bg"]), scale_modifier=s["scale_modifier"], viewmatrix=t(s["viewmatrix"]), projmatrix=t(s["projmatrix"]),
+            sh_degree=0, campos=t(s["campos"]), prefiltered=False)
+        self.w2c = []                      # estimated poses, one 4x4 per frame
+        self.sections = []                 # dict(params, base, keyframes=[(idx, rgb, depth)])
+        self.tracker = None
+        self.mapper = None
+        self.stats = dict(track_iters=0, map_iters=0, track_s=0.0, map_s=0.0, track_loss=[])
+
+    # -- sections -------------------------------------------------------------------------------------------
+    def _new_section(self, idx, rgb, depth):
+        c2w = np.linalg.inv(self.w2c[idx])
+        params = section_from_frame(rgb, depth, self.K, c2w, self.device)
+        sec = dict(params=params, base=idx, keyframes=[])
+        self.sections.append(sec)
+        c = self.cfg
+        # the solvers alias `params` (contiguous float32 CUDA tensors are used in place): mapping updates are
+        # seen by the tracker without a copy
+        self.mapper = MappingSolver(self.settings, params, device=self.device, lrs=c.map_lrs)
+        self.tracker = TrackingSolver(self.settings, self.mapper.params, device=self.device, lr_rot=c.lr_rot,
+                                      lr_trans=c.lr_trans, w_im=c.track_w_im, w_depth=c.track_w_depth,
+                                      sil_thres=c.sil_thres, use_graph=c.use_graph)
+        return sec
+
+    def _keyframe(self, sec, idx, rgb, depth):
+        sec["keyframes"].append((idx, rgb, depth))
+
+    def _map(self, sec):
+        c = self.cfg
+        kfs = []
+        chosen = [sec["keyframes"][0]] + sec["keyframes"][1:][-(c.keyframes_per_map - 1):] if c.keyframes_per_map > 1 else sec["keyframes"][-1:]
+        for idx, rgb, depth in chosen:
+            M = self.w2c[idx]
+            kfs.append(dict(cam_q=torch.as_tensor(quat_from_matrix(M[:3, :3]), dtype=torch.float32, device=self.device),
+                            cam_t=torch.as_tensor(M[:3, 3], dtype=torch.float32, device=self.device),
+                            gt_rgb=rgb, gt_depth=depth))
+        t0 = time.perf_counter()
+        for _ in range(c.map_iters):
+            self.mapper.iteration(kfs, w_im=c.map_w_im, w_depth=c.map_w_depth)
+        torch.cuda.synchronize(self.device)
+        self.stats["map_s"] += time.perf_counter() - t0
+        self.stats["map_iters"] += c.map_iters * len(kfs)
+
+    # -- tracking -------------------------------------------------------------------------------------------
+    def _track(self, idx, rgb, depth):
+        c = self.cfg
+        init = propagate_pose(self.w2c[idx - 1], self.w2c[idx - 2]) if idx >= 2 else self.w2c[idx - 1].copy()
+        tr = self.tracker
+        tr.set_frame(rgb, depth, quat_from_matrix(init[:3, :3]).astype(np.float32), init[:3, 3].astype(np.float32))
+        t0 = time.perf_counter()
+        for _ in range(c.track_iters + 1):          # the +1 evaluates (and books) the pose of the last Adam step
+            tr.step()
+        best = tr.best.cpu().numpy()                # one read per frame (synchronises)
+        self.stats["track_s"] += time.perf_counter() - t0
+        self.stats["track_iters"] += c.track_iters + 1
+        tr.check()
+        self.stats["track_loss"].append(float(best[0]))
+        return matrix_from_quat(best[1:5], best[5:8])
+
+    # -- driver ---------------------------------------------------------------------------------------------
+    def process(self, frame):
+        idx = len(self.w2c)
+        rgb = torch.as_tensor(frame["im"], dtype=torch.float32).to(self.device, non_blocking=True).contiguous()
+        depth = torch.as_tensor(frame["depth"], dtype=torch.float32).to(self.device, non_blocking=True).reshape(1, self.H, self.W).contiguous()
+        c = self.cfg
+        if idx == 0:
+            self.w2c.append(np.eye(4))
+        else:
+            self.w2c.append(self._track(idx, rgb, depth))
+        if idx % c.baseframe_every == 0:
+            sec = self._new_section(idx, rgb, depth)
+            self._keyframe(sec, idx, rgb, depth)
+            self._map(sec)
+        elif idx % c.map_every == 0:
+            sec = self.sections[-1]
+            self._keyframe(sec, idx, rgb, depth)
+            self._map(sec)
+        return self.w2c[-1]
+
+    def run(self, frames):
+        for fr in frames:
+            self.process(fr)
+        return np.stack([np.linalg.inv(m) for m in self.w2c])

@@ -52,27 +52,41 @@ def setup_camera(w, h, k, w2c, near=0.01, far=100.0, bg=(0.0, 0.0, 0.0)):
                 projmatrix=full_proj.reshape(1, 4, 4), sh_degree=0, campos=cam_center, prefiltered=False)
 
 
-def _room_depth(W, H, K, boxes=True):
-    """Analytic box room seen from inside (camera at the origin looking down +z) plus a few
-    fronto-parallel slabs: returns depth[H,W] (metres, z-depth) and hit points[H,W,3]."""
+ROOM = dict(x=(-2.7, 3.1), y=(-1.5, 1.3), z=(-1.6, 4.2))                   # axis-aligned box room (metres, world frame)
+SLABS = [(-1.6, -0.4, 0.1, 1.3, 2.4), (0.5, 1.7, 0.4, 1.3, 3.0), (-0.3, 0.35, -0.2, 0.5, 1.7)]   # (x0, x1, y0, y1, z) rectangles
+
+
+def _room_depth(W, H, K, boxes=True, c2w=None):
+    """Analytic box room seen from inside plus a few slabs parallel to the world xy-plane, ray-cast from the camera
+    `c2w` (4x4 camera-to-world, default: at the origin looking down +z): returns the z-depth[H,W] in the camera
+    frame (metres) and the WORLD hit points[H,W,3]."""
     fx, fy, cx, cy = K[0, 0], K[1, 1], K[0, 2], K[1, 2]
     # ray through pixel (x, y) in the rasteriser's convention: setup_camera's projection maps the
     # camera-frame direction ((x - cx + 0.5)/fx, (y - cy + 0.5)/fy, 1) onto pixel centre (x, y)
     x = (np.arange(W, dtype=np.float64) - cx + 0.5) / fx
     y = (np.arange(H, dtype=np.float64) - cy + 0.5) / fy
     dx, dy = np.meshgrid(x, y)
+    if c2w is None:
+        o = np.zeros(3)
+        d = (dx, dy, np.ones_like(dx))
+    else:
+        c2w = np.asarray(c2w, np.float64)
+        o, R = c2w[:3, 3], c2w[:3, :3]
+        d = tuple(R[i, 0] * dx + R[i, 1] * dy + R[i, 2] for i in range(3))
     big = 1e9
+    # the camera-frame direction has z = 1, so the ray parameter t IS the z-depth
+    t = np.full((H, W), big)
     with np.errstate(divide="ignore", invalid="ignore"):
-        t = np.full((H, W), 4.2)                                   # back wall z = 4.2
-        t = np.minimum(t, np.where(dx > 0, 3.1 / dx, big))          # right wall x = 3.1
-        t = np.minimum(t, np.where(dx < 0, -2.7 / dx, big))         # left wall x = -2.7
-        t = np.minimum(t, np.where(dy > 0, 1.3 / dy, big))          # floor y = 1.3
-        t = np.minimum(t, np.where(dy < 0, -1.5 / dy, big))         # ceiling y = -1.5
-    if boxes:
-        for (x0, x1, y0, y1, z0) in [(-1.6, -0.4, 0.1, 1.3, 2.4), (0.5, 1.7, 0.4, 1.3, 3.0), (-0.3, 0.35, -0.2, 0.5, 1.7)]:
-            inside = (dx * z0 > x0) & (dx * z0 < x1) & (dy * z0 > y0) & (dy * z0 < y1)
-            t = np.where(inside & (z0 < t), z0, t)
-    pts = np.stack([dx * t, dy * t, t], -1)
+        for axis, (lo, hi) in zip(range(3), (ROOM["x"], ROOM["y"], ROOM["z"])):
+            t = np.minimum(t, np.where(d[axis] > 0, (hi - o[axis]) / d[axis], big))
+            t = np.minimum(t, np.where(d[axis] < 0, (lo - o[axis]) / d[axis], big))
+        if boxes:
+            for (x0, x1, y0, y1, z0) in SLABS:
+                ts = np.where(np.abs(d[2]) > 1e-12, (z0 - o[2]) / d[2], big)
+                hx, hy = o[0] + d[0] * ts, o[1] + d[1] * ts
+                hit = (ts > 0) & (hx > x0) & (hx < x1) & (hy > y0) & (hy < y1) & (ts < t)
+                t = np.where(hit, ts, t)
+    pts = np.stack([o[0] + d[0] * t, o[1] + d[1] * t, o[2] + d[2] * t], -1)
     return t, pts
 
 
@@ -85,13 +99,55 @@ def _texture(pts):
     return np.clip(np.stack([r + chk, g - chk, b + 0.5 * chk], 0), 0.0, 1.0)
 
 
-def make_frame(shape="replica", width=None, height=None, seed=0):
-    """-> dict(W,H,K, im[3,H,W] float32 in [0,1], depth[1,H,W] float32 metres)."""
+def make_frame(shape="replica", width=None, height=None, seed=0, c2w=None):
+    """-> dict(W,H,K, im[3,H,W] float32 in [0,1], depth[1,H,W] float32 metres[, c2w]) seen from camera pose c2w."""
     W, H, K = intrinsics(shape, width, height)
-    depth, pts = _room_depth(W, H, K)
+    depth, pts = _room_depth(W, H, K, c2w=c2w)
     rng = np.random.default_rng(seed)
     im = _texture(pts) + rng.normal(0, 0.004, (3, H, W))
-    return dict(W=W, H=H, K=K, im=np.clip(im, 0, 1).astype(np.float32), depth=depth[None].astype(np.float32))
+    fr = dict(W=W, H=H, K=K, im=np.clip(im, 0, 1).astype(np.float32), depth=depth[None].astype(np.float32))
+    if c2w is not None:
+        fr["c2w"] = np.asarray(c2w, np.float64)
+    return fr
+
+
+def trajectory(num_frames, step_m=0.01, step_deg=0.3, seed=3):
+    """A smooth hand-held-like camera path inside the room: c2w[num_frames,4,4], frame 0 = identity (dataset poses
+    are relative to the first frame, reference datasets/gradslam_datasets/basedataset.py:288-292).  Consecutive
+    frames are ~step_m apart and ~step_deg rotated; the path is a sum of slow sinusoids, so constant-velocity
+    propagation is a good but not exact initial guess."""
+    rng = np.random.default_rng(seed)
+    ph = rng.uniform(0, 2 * np.pi, 6)
+    s = np.arange(num_frames, dtype=np.float64)
+    span = max(num_frames - 1, 1)
+    # amplitudes chosen so that the mean per-frame step is ~step_m / ~step_deg regardless of the length
+    A_t = step_m * span / 4.0
+    A_r = np.deg2rad(step_deg) * span / 4.0
+    A_t, A_r = min(A_t, 0.6), min(A_r, np.deg2rad(20.0))
+    w = 2 * np.pi / max(span, 8) * np.array([1.0, 0.7, 1.3, 0.9, 1.1, 0.6])
+    if A_t < step_m * span / 4.0:                  # long sequences: keep the per-frame step by cycling faster
+        w = w * (step_m * span / 4.0) / A_t
+    tr = np.stack([A_t * (np.sin(w[0] * s + ph[0]) - np.sin(ph[0])),
+                   0.4 * A_t * (np.sin(w[1] * s + ph[1]) - np.sin(ph[1])),
+                   0.7 * A_t * (np.sin(w[2] * s + ph[2]) - np.sin(ph[2]))], -1)
+    ang = np.stack([0.5 * A_r * (np.sin(w[3] * s + ph[3]) - np.sin(ph[3])),
+                    A_r * (np.sin(w[4] * s + ph[4]) - np.sin(ph[4])),
+                    0.3 * A_r * (np.sin(w[5] * s + ph[5]) - np.sin(ph[5]))], -1)
+    out = np.tile(np.eye(4), (num_frames, 1, 1))
+    for i in range(num_frames):
+        ax, ay, az = ang[i]
+        Rx = np.array([[1, 0, 0], [0, np.cos(ax), -np.sin(ax)], [0, np.sin(ax), np.cos(ax)]])
+        Ry = np.array([[np.cos(ay), 0, np.sin(ay)], [0, 1, 0], [-np.sin(ay), 0, np.cos(ay)]])
+        Rz = np.array([[np.cos(az), -np.sin(az), 0], [np.sin(az), np.cos(az), 0], [0, 0, 1]])
+        out[i, :3, :3] = Rz @ Ry @ Rx
+        out[i, :3, 3] = tr[i]
+    return out
+
+
+def make_sequence(shape="tum_fr1", num_frames=8, width=None, height=None, step_m=0.01, step_deg=0.3, seed=0):
+    """-> list of frames (make_frame dicts carrying their ground-truth 'c2w') along `trajectory`."""
+    poses = trajectory(num_frames, step_m, step_deg, seed=seed + 3)
+    return [make_frame(shape, width, height, seed=seed + i, c2w=poses[i]) for i in range(num_frames)]
 
 
 def view_tied_gaussians(frame, n_target=None, n_edge=0, opacity="fresh", seed=2, color_noise=0.02):
