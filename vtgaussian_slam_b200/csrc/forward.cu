@@ -116,23 +116,15 @@ preprocess_kernel(const __grid_constant__ CamConst cam, int64_t N, FrontEnd fe,
                 x = X; y = Y; z = Z;
                 if (fe.log_scales_dim == 3) { sx = vexpf(it.s0); sy = vexpf(it.s1); sz = vexpf(it.s2); }
                 else { sx = sy = sz = vexpf(it.s0); }
-                const float nrm = __fsqrt_rn(ffma(qz, qz, ffma(qy, qy, ffma(qx, qx, fmul(qr, qr)))));
-                const float d = fmaxf(nrm, 1e-12f);
-                qr = __fdiv_rn(qr, d); qx = __fdiv_rn(qx, d); qy = __fdiv_rn(qy, d); qz = __fdiv_rn(qz, d);
-                op = __fdiv_rn(1.0f, fadd(1.0f, vexpf(-it.op)));
-                // get_depth_and_silhouette (reference utils/slam_helpers.py:217-234): z of w2c * p'
-                c3 = fadd(ffma(fe.depth_row[2], z, ffma(fe.depth_row[1], y, fmul(fe.depth_row[0], x))), fe.depth_row[3]);
             } else {
                 sx = it.s0; sy = it.s1; sz = it.s2;
-                op = it.op;
-                c3 = 0.0f;
             }
-
             SplatGeom g;
             bool outside_band = false;
             if (FUSED && band_active) {
                 // Tile-band sharding: a conservative bound of the splat's screen-space extent decides in ~40
-                // instructions that it cannot reach this rank's rows, skipping the ~900-instruction projection.
+                // instructions that it cannot reach this rank's rows, skipping the activations and the
+                // ~900-instruction projection, and the 64-byte record (nothing reads it when tiles_touched = 0).
                 // (radius <= sigma_mult * sqrt(trace(cov2D)), trace <= s^2 (|J0|^2 + |J1|^2) + 2 * lowpass with the
                 // clamped Jacobian; 1 % + 3 px of slack cover the approximate arithmetic and the ceil.)
                 const float tz_ = xform_row(cam.view, 2, x, y, z);
@@ -146,8 +138,22 @@ preprocess_kernel(const __grid_constant__ CamConst cam, int64_t N, FrontEnd fe,
                     outside_band = (py_ - rb > (float)(cam.row1 * 16)) || (py_ + rb + 16.0f < (float)(cam.row0 * 16));
                 }
             }
-            if (outside_band) { g.radius = 0; g.depth = 0.0f; }
-            else splat_geometry(cam, x, y, z, sx, sy, sz, qr, qx, qy, qz, g);
+            if (outside_band) {
+                radii[i] = 0;
+                tiles_touched[i] = 0;
+            } else {
+            if (FUSED) {
+                const float nrm = __fsqrt_rn(ffma(qz, qz, ffma(qy, qy, ffma(qx, qx, fmul(qr, qr)))));
+                const float d = fmaxf(nrm, 1e-12f);
+                qr = __fdiv_rn(qr, d); qx = __fdiv_rn(qx, d); qy = __fdiv_rn(qy, d); qz = __fdiv_rn(qz, d);
+                op = __fdiv_rn(1.0f, fadd(1.0f, vexpf(-it.op)));
+                // get_depth_and_silhouette (reference utils/slam_helpers.py:217-234): z of w2c * p'
+                c3 = fadd(ffma(fe.depth_row[2], z, ffma(fe.depth_row[1], y, fmul(fe.depth_row[0], x))), fe.depth_row[3]);
+            } else {
+                op = it.op;
+                c3 = 0.0f;
+            }
+            splat_geometry(cam, x, y, z, sx, sy, sz, qr, qx, qy, qz, g);
             if (!FUSED) c3 = g.depth;
 
             GeomRecord rec;
@@ -173,6 +179,7 @@ preprocess_kernel(const __grid_constant__ CamConst cam, int64_t N, FrontEnd fe,
             geom[i] = rec;
             radii[i] = g.radius;
             tiles_touched[i] = tiles;
+            }
         }
         // per-tile histogram, warp-aggregated: neighbouring Gaussians (neighbouring pixels of a view-tied
         // section) touch the same tiles, so one atomic per distinct tile per warp step instead of one per lane
