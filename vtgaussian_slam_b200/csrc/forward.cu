@@ -397,6 +397,141 @@ __device__ __forceinline__ void sort_segment_regs(uint64_t* __restrict__ s_x, ui
     }
 }
 
+// Stable LSD radix sort of a tile's segment (256 < n <= SORT_SMEM_ELEMS) on the DEPTH word of the keys, 8 bits per
+// pass, only over the bits in which the tile's depths actually differ (a tile sees a narrow depth range: usually
+// 3 passes).  Warp w owns the contiguous chunk [32 E w, 32 E (w + 1)), element (round e, lane l) = chunk + 32 e + l,
+// so that (warp, round, lane) order IS list order: ranks come from __match_any_sync inside a round, running
+// per-warp digit counters across rounds and one block scan over (digit, warp) per pass -- ~1/5 of the bitonic
+// network's instructions.  The scatter's slot order is arbitrary, so equal depths (rare) would come out in arbitrary
+// order: a tile that holds any tie re-sorts its (already depth-ordered) keys with the full 64-bit network.
+template <int E>
+__device__ __forceinline__ void sort_segment_radix(uint64_t* __restrict__ s_keys, uint32_t (*__restrict__ wh)[256],
+                                                   uint32_t* __restrict__ s_red, const uint64_t* __restrict__ keys_in, int n, int tid) {
+    const int lane = tid & 31, warp = tid >> 5;
+    const uint32_t lt = (1u << lane) - 1u;
+    const int cbase = warp * 32 * E + lane;
+    uint64_t v[E];
+    uint32_t dmin = 0xffffffffu, dmax = 0u;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const int i = cbase + 32 * e;
+        v[e] = ~0ull;
+        if (i < n) {
+            v[e] = keys_in[i];
+            const uint32_t hi = (uint32_t)(v[e] >> 32);
+            dmin = min(dmin, hi);
+            dmax = max(dmax, hi);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        dmin = min(dmin, __shfl_xor_sync(VTGS_FULL_MASK, dmin, o));
+        dmax = max(dmax, __shfl_xor_sync(VTGS_FULL_MASK, dmax, o));
+    }
+    if (lane == 0) { s_red[warp] = dmin; s_red[8 + warp] = dmax; }
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { dmin = min(dmin, s_red[w]); dmax = max(dmax, s_red[8 + w]); }
+    const int hb = 32 - __clz((int)(dmin ^ dmax));            // low bits in which the depths differ (0: all equal)
+    __syncthreads();                                           // s_red is reused by the scans below
+    for (int shift = 0; shift < hb; shift += 8) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) wh[warp][lane + 32 * k] = 0u;
+        __syncwarp();
+        uint32_t off[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const bool valid = cbase + 32 * e < n;
+            const uint32_t vm = __ballot_sync(VTGS_FULL_MASK, valid);
+            uint32_t d = 0u, peers = 0u, prev = 0u;
+            if (valid) {
+                d = (uint32_t)(v[e] >> (32 + shift)) & 0xffu;
+                peers = __match_any_sync(vm, d);
+                prev = wh[warp][d];
+            }
+            __syncwarp();
+            const uint32_t rank = __popc(peers & lt);
+            if (valid && rank == 0u) wh[warp][d] = prev + (uint32_t)__popc(peers);
+            __syncwarp();
+            off[e] = prev + rank;
+        }
+        __syncthreads();
+        {   // exclusive scan over (digit, warp): thread b owns digit b
+            uint32_t run = 0u;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) { const uint32_t c = wh[w][tid]; wh[w][tid] = run; run += c; }
+            uint32_t incl = run;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(VTGS_FULL_MASK, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if (lane == 31) s_red[warp] = incl;
+            __syncthreads();
+            uint32_t dbase = incl - run;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) if (w < warp) dbase += s_red[w];
+#pragma unroll
+            for (int w = 0; w < 8; ++w) wh[w][tid] += dbase;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < E; ++e)
+            if (cbase + 32 * e < n) s_keys[wh[warp][(uint32_t)(v[e] >> (32 + shift)) & 0xffu] + off[e]] = v[e];
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < E; ++e)
+            if (cbase + 32 * e < n) v[e] = s_keys[cbase + 32 * e];
+    }
+    if (hb == 0) {
+#pragma unroll
+        for (int e = 0; e < E; ++e)
+            if (cbase + 32 * e < n) s_keys[cbase + 32 * e] = v[e];
+        __syncthreads();
+    }
+    // Equal depths: with ~10^3 floats from a narrow range per tile a coincidence somewhere is likely (birthday
+    // bound), but runs are short.  Every member of a run finds its place by counting the run's smaller ids
+    // (low words: id << 8 | mask, ids are unique); runs longer than TIE_RUN_MAX fall back to the 64-bit network.
+    constexpr int TIE_RUN_MAX = 48;
+    bool moved = false, too_long = false;
+    int newpos[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const int i = cbase + 32 * e;
+        newpos[e] = i;
+        if (i < n) {
+            const uint32_t hi = (uint32_t)(v[e] >> 32), lo = (uint32_t)v[e];
+            int shiftpos = 0, steps = 0;
+            for (int j = i - 1; j >= 0; --j) {
+                const uint64_t o = s_keys[j];
+                if ((uint32_t)(o >> 32) != hi) break;
+                if ((uint32_t)o > lo) --shiftpos;
+                if (++steps > TIE_RUN_MAX) { too_long = true; break; }
+            }
+            for (int j = i + 1; j < n; ++j) {
+                const uint64_t o = s_keys[j];
+                if ((uint32_t)(o >> 32) != hi) break;
+                if ((uint32_t)o < lo) ++shiftpos;
+                if (++steps > TIE_RUN_MAX) { too_long = true; break; }
+            }
+            newpos[e] = i + shiftpos;
+            moved |= shiftpos != 0;
+        }
+    }
+    const bool any_long = __syncthreads_or(too_long) != 0;        // (a barrier: every read of s_keys above is done)
+    const bool any_moved = __syncthreads_or(moved) != 0;
+    if (any_long) {
+        int npad = 2;
+        while (npad < n) npad <<= 1;
+        bitonic_network(s_keys, n, npad);
+    } else if (any_moved) {
+#pragma unroll
+        for (int e = 0; e < E; ++e)
+            if (cbase + 32 * e < n && newpos[e] != cbase + 32 * e) s_keys[newpos[e]] = v[e];
+        __syncthreads();
+    }
+}
+
 // After a tile's list is sorted: per-region lists.  Every (sorted) entry is tested once against the
 // tile's 8 warp regions (box of its alpha >= 1/255 ellipse) and appended, in list order, to the list of
 // every region it may touch as (Gaussian id, 1-based position in the tile list).  The blend kernels then
@@ -453,6 +588,7 @@ tile_sort_kernel(const __grid_constant__ CamConst cam, const uint32_t* __restric
                  uint64_t* __restrict__ pair_keys, uint32_t* __restrict__ point_list, const GeomRecord* __restrict__ geom,
                  uint2* __restrict__ region_pairs, uint32_t* __restrict__ region_cnt) {
     extern __shared__ __align__(16) uint64_t s_keys[];
+    __shared__ uint32_t s_wh[8][256];
     __shared__ uint32_t s_cnt[64];
     __shared__ uint32_t s_base[8];
     const int tile = tile0 + blockIdx.x;
@@ -462,10 +598,23 @@ tile_sort_kernel(const __grid_constant__ CamConst cam, const uint32_t* __restric
         if (threadIdx.x < 8) region_cnt[(size_t)tile * 8 + threadIdx.x] = 0;
         return;
     }
-    if (n <= 512) sort_segment_regs<2>(s_keys, pair_keys + b, point_list + b, n, threadIdx.x);
-    else if (n <= 1024) sort_segment_regs<4>(s_keys, pair_keys + b, point_list + b, n, threadIdx.x);
-    else if (n <= 2048) sort_segment_regs<8>(s_keys, pair_keys + b, point_list + b, n, threadIdx.x);
-    else {
+    const uint64_t* sorted = pair_keys + b;
+    if (n <= 256) sort_segment_regs<2>(s_keys, pair_keys + b, point_list + b, n, threadIdx.x);
+    else if (n <= 2048) {
+        const uint64_t* in = pair_keys + b;
+        const int tid = threadIdx.x;
+        if (n <= 512) sort_segment_radix<2>(s_keys, s_wh, s_cnt, in, n, tid);
+        else if (n <= 768) sort_segment_radix<3>(s_keys, s_wh, s_cnt, in, n, tid);
+        else if (n <= 1024) sort_segment_radix<4>(s_keys, s_wh, s_cnt, in, n, tid);
+        else if (n <= 1536) sort_segment_radix<6>(s_keys, s_wh, s_cnt, in, n, tid);
+        else sort_segment_radix<8>(s_keys, s_wh, s_cnt, in, n, tid);
+        for (int i = tid; i < n; i += 256) {
+            const uint64_t k = s_keys[i];
+            pair_keys[b + i] = k;
+            point_list[b + i] = (uint32_t)k >> 8;
+        }
+        sorted = s_keys;
+    } else {
         int npad = 2;
         while (npad < n) npad <<= 1;
         if (n <= SORT_SMEM_ELEMS) {
@@ -477,13 +626,14 @@ tile_sort_kernel(const __grid_constant__ CamConst cam, const uint32_t* __restric
                 point_list[b + i] = (uint32_t)k >> 8;
                 pair_keys[b + i] = k;
             }
+            sorted = s_keys;
         } else {
             __syncthreads();
             bitonic_network(pair_keys + b, n, npad);
             for (int i = threadIdx.x; i < n; i += blockDim.x) point_list[b + i] = (uint32_t)pair_keys[b + i] >> 8;
         }
     }
-    build_region_lists(pair_keys + b, n, b, tile, region_pairs, region_cnt, s_cnt, s_base);
+    build_region_lists(sorted, n, b, tile, region_pairs, region_cnt, s_cnt, s_base);
 }
 
 #ifdef VTGS_STATS
@@ -666,9 +816,12 @@ int launch_forward(const VtgsCamera* camera, int64_t N, bool fused, const FrontE
                                                                   geom, radii, buf->tiles_touched, buf->tile_counts); }
         VTGS_LAUNCH_CHECK();
     }
-    { VTGS_PROF("tile_scan_kernel", stream); tile_scan_kernel<<<1, 1024, 0, stream>>>(buf->tile_counts, buf->tile_ranges, num_tiles, buf->pair_capacity, buf->counters); }
-    VTGS_LAUNCH_CHECK();
+    // only the band's tiles hold counts (tile-band sharding: K1' clips every rect to the band); the fused solvers never
+    // look at another tile's range, so they scan the band alone -- API mode keeps (0,0) ranges for the other tiles
     const int band_tiles = (cam.row1 - cam.row0) * cam.gx;
+    const int scan0 = fused ? cam.row0 * cam.gx : 0, scan_n = fused ? band_tiles : num_tiles;
+    { VTGS_PROF("tile_scan_kernel", stream); tile_scan_kernel<<<1, 1024, 0, stream>>>(buf->tile_counts + scan0, buf->tile_ranges + 2 * (size_t)scan0, scan_n, buf->pair_capacity, buf->counters); }
+    VTGS_LAUNCH_CHECK();
     if (N > 0 && band_tiles > 0) {
         { VTGS_PROF("scatter_kernel", stream); scatter_kernel<<<blocks, 256, 0, stream>>>(N, cam.gx, geom, buf->tiles_touched, buf->tile_ranges, buf->tile_counts, buf->pair_keys); }
         VTGS_LAUNCH_CHECK();

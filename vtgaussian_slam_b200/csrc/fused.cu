@@ -354,14 +354,25 @@ int launch_loss(const VtgsCamera* camera, const VtgsLossConfig* cfg, const float
 }
 
 // ---- Adam -----------------------------------------------------------------------------------
+// beta^t by repeated squaring in fp64: a dozen DMULs (pow() is microseconds of serial fp64 on this part,
+// paid as a prologue by every block).
+__device__ __forceinline__ double ipow(double b, int t) {
+    double r = 1.0;
+    for (int e = t; e > 0; e >>= 1) {
+        if (e & 1) r *= b;
+        b *= b;
+    }
+    return r;
+}
+
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,
             float lr, float b1, float b2, float eps, int step, const int32_t* __restrict__ step_dev) {
     __shared__ float s_c[2];
     if (threadIdx.x == 0) {
         const int t = step_dev ? *step_dev : step;
-        const double bc1 = 1.0 - pow((double)b1, (double)t);
-        const double bc2 = 1.0 - pow((double)b2, (double)t);
+        const double bc1 = 1.0 - ipow((double)b1, t);
+        const double bc2 = 1.0 - ipow((double)b2, t);
         s_c[0] = (float)((double)lr / bc1);
         s_c[1] = (float)sqrt(bc2);
     }
@@ -399,8 +410,7 @@ __global__ void tracking_update_kernel(float* __restrict__ cam_q, float* __restr
     const float g = msg[k];
     float* m = adam + (k < 4 ? k : 8 + (k - 4));
     float* v = adam + (k < 4 ? 4 + k : 11 + (k - 4));
-    const double bc1 = 1.0 - pow((double)b1, (double)s_step);
-    const double bc2 = 1.0 - pow((double)b2, (double)s_step);
+    const double bc1 = 1.0 - ipow((double)b1, s_step), bc2 = 1.0 - ipow((double)b2, s_step);
     const float step_size = (float)((double)(k < 4 ? lr_rot : lr_trans) / bc1);
     const float mi = *m + (1.0f - b1) * (g - *m);
     const float vi = b2 * *v + (1.0f - b2) * g * g;
