@@ -294,7 +294,7 @@ scatter_kernel(int64_t N, int gx, const GeomRecord* __restrict__ geom, const uin
 // first sub-step of each merge mirrors the index) so that indices >= n act as +inf padding
 // without being stored.  Segments up to SORT_SMEM_ELEMS are sorted in shared memory;
 // longer ones in place in global memory (same network, block-local barriers).
-constexpr int SORT_SMEM_ELEMS = 4096;
+constexpr int SORT_SMEM_ELEMS = 2048;
 
 __device__ __forceinline__ void bitonic_network(uint64_t* __restrict__ s, int n, int npad) {
     const int pairs = npad >> 1;
@@ -583,7 +583,7 @@ __device__ __forceinline__ void build_region_lists(const uint64_t* __restrict__ 
     if (tid < 8) region_cnt[(size_t)tile * 8 + tid] = s_base[tid];
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 tile_sort_kernel(const __grid_constant__ CamConst cam, const uint32_t* __restrict__ ranges, int tile0,
                  uint64_t* __restrict__ pair_keys, uint32_t* __restrict__ point_list, const GeomRecord* __restrict__ geom,
                  uint2* __restrict__ region_pairs, uint32_t* __restrict__ region_cnt) {
