@@ -493,7 +493,8 @@ struct K7Item {
 };
 
 __device__ __forceinline__ void k7_load(K7Item& it, int64_t i, const VtgsParams& prm, const GeomRecord* __restrict__ geom,
-                                        const float* __restrict__ grad_geom, bool rot_aligned, const uint32_t* __restrict__ tiles_touched) {
+                                        const float* __restrict__ grad_geom, bool rot_aligned, const uint32_t* __restrict__ tiles_touched,
+                                        bool want_op) {
     // a Gaussian with no tile in this rank's band (tile-band sharding) or culled received no gradient here:
     // 4 bytes decide that instead of ~190
     if (tiles_touched != nullptr && tiles_touched[i] == 0u) {
@@ -504,7 +505,9 @@ __device__ __forceinline__ void k7_load(K7Item& it, int64_t i, const VtgsParams&
     }
     const float4* gg = reinterpret_cast<const float4*>(grad_geom + (size_t)i * VTGS_GRAD_GEOM_FLOATS);
     it.g0 = gg[0]; it.g1 = gg[1]; it.g2 = gg[2];
-    it.hx = geom[i].q0.z; it.op = geom[i].q1.w;
+    // a culled splat is in no list, so its sums are zero: only dL/dlogit needs the record (the activated opacity)
+    it.hx = 0.0f;
+    it.op = want_op ? geom[i].q1.w : 0.0f;
     it.px = prm.means3D[3 * i]; it.py = prm.means3D[3 * i + 1]; it.pz = prm.means3D[3 * i + 2];
     it.ls = prm.log_scales[i];
     it.uq = rot_aligned ? reinterpret_cast<const float4*>(prm.unnorm_rotations)[i]
@@ -512,6 +515,8 @@ __device__ __forceinline__ void k7_load(K7Item& it, int64_t i, const VtgsParams&
                                       prm.unnorm_rotations[4 * i + 2], prm.unnorm_rotations[4 * i + 3]);
 }
 
+// SHAPE = false (tracking: no dL/dlog_scale, dL/dquaternion wanted) drops the cov3D chain at compile time.
+template <bool SHAPE>
 __global__ void __launch_bounds__(256, 2)
 fused_preprocess_backward_kernel(const __grid_constant__ CamConst cam, int64_t N, VtgsParams prm,
                                  const float* __restrict__ pose_Rt, float dr0, float dr1, float dr2,
@@ -532,12 +537,13 @@ fused_preprocess_backward_kernel(const __grid_constant__ CamConst cam, int64_t N
 #pragma unroll
     for (int k = 0; k < 16; ++k) pose_v[k] = 0.0f;
 
+    const bool want_op = out.logit_opacities != nullptr;
     int64_t i = (int64_t)blockIdx.x * 256 + tid;
     K7Item nxt;
-    if (i < N) k7_load(nxt, i, prm, geom, grad_geom, rot_aligned, tiles_touched);
+    if (i < N) k7_load(nxt, i, prm, geom, grad_geom, rot_aligned, tiles_touched, want_op);
     for (; i < N; i += stride) {
         const K7Item it = nxt;
-        if (i + stride < N) k7_load(nxt, i + stride, prm, geom, grad_geom, rot_aligned, tiles_touched);
+        if (i + stride < N) k7_load(nxt, i + stride, prm, geom, grad_geom, rot_aligned, tiles_touched, want_op);
         const float4 g0 = it.g0, g1 = it.g1, g2 = it.g2;
         // culled splats, and splats no pixel blended (all sums exactly zero), have zero gradients: every
         // term below is linear in g0..g2
@@ -565,8 +571,8 @@ fused_preprocess_backward_kernel(const __grid_constant__ CamConst cam, int64_t N
             cov3d_from(s, s, s, cam.scale_modifier, R, S);
             CovGrad cg;
             cov2d_backward(cam, x, y, z, S, g0.z, g0.w, g1.x, g0.x, g0.y, cg);
-            float dscale[3], dq[4];
-            cov3d_backward(cg.dS, R, cam.scale_modifier, s, s, s, q[0], q[1], q[2], q[3], dscale, dq);
+            float dscale[3] = {0.f, 0.f, 0.f}, dq[4] = {0.f, 0.f, 0.f, 0.f};
+            if (SHAPE) cov3d_backward(cg.dS, R, cam.scale_modifier, s, s, s, q[0], q[1], q[2], q[3], dscale, dq);
             // chain through get_depth_and_silhouette: colour channel 3 is z_cam = depth_row . (p', 1)
             const float dz = g2.y;
             const float gm[3] = {cg.dmean[0] + dr0 * dz, cg.dmean[1] + dr1 * dz, cg.dmean[2] + dr2 * dz};
@@ -641,10 +647,18 @@ int launch_fused_backward(const VtgsCamera* camera, const VtgsParams* params, co
             VTGS_LAUNCH_CHECK();
         }
         unsigned int* ticket = reinterpret_cast<unsigned int*>(grads->pose_scratch ? grads->pose_scratch + (size_t)blocks * POSE_TERMS : nullptr);
-        { VTGS_PROF("fused_preprocess_backward_kernel", stream); fused_preprocess_backward_kernel<<<blocks, 256, 0, stream>>>(cam, N, *params, buf->counters->pose_R, pose->depth_row[0],
-                                                                     pose->depth_row[1], pose->depth_row[2], geom, buf->grad_geom,
-                                                                     *grads, accumulate, want_pose, buf->counters, ticket,
-                                                                     band_tiles < cam.gx * cam.gy ? buf->tiles_touched : nullptr); }
+        const uint32_t* band_touch = band_tiles < cam.gx * cam.gy ? buf->tiles_touched : nullptr;
+        if (grads->log_scales != nullptr || grads->unnorm_rotations != nullptr) {
+            VTGS_PROF("fused_preprocess_backward_kernel", stream);
+            fused_preprocess_backward_kernel<true><<<blocks, 256, 0, stream>>>(cam, N, *params, buf->counters->pose_R, pose->depth_row[0], pose->depth_row[1],
+                                                                               pose->depth_row[2], geom, buf->grad_geom, *grads, accumulate, want_pose,
+                                                                               buf->counters, ticket, band_touch);
+        } else {
+            VTGS_PROF("fused_preprocess_backward_kernel", stream);
+            fused_preprocess_backward_kernel<false><<<blocks, 256, 0, stream>>>(cam, N, *params, buf->counters->pose_R, pose->depth_row[0], pose->depth_row[1],
+                                                                                pose->depth_row[2], geom, buf->grad_geom, *grads, accumulate, want_pose,
+                                                                                buf->counters, ticket, band_touch);
+        }
         VTGS_LAUNCH_CHECK();
     } else if (want_pose && !accumulate) {
         VTGS_CUDA_CHECK(cudaMemsetAsync(grads->cam_unnorm_rot, 0, 4 * sizeof(float), stream));

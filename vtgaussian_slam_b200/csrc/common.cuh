@@ -36,7 +36,7 @@ void set_error(const char* fmt, ...);
 //                                    rect packed as x | y << 16 (band-clipped in y)
 // Culled splats carry hx = hy = -1e30 and pthr = 1 (never pass any test).
 struct __align__(16) GeomRecord {
-    float4 q0, q1, q2, q3;
+    float4 q0, q3, q1, q2;          // memory order: {q0, q3} (what the scatter reads) share one 32-byte sector
 };
 static_assert(sizeof(GeomRecord) == VTGS_GEOM_RECORD_BYTES, "record size");
 

@@ -145,7 +145,9 @@ preprocess_kernel(const __grid_constant__ CamConst cam, int64_t N, FrontEnd fe,
             if (FUSED) {
                 const float nrm = __fsqrt_rn(ffma(qz, qz, ffma(qy, qy, ffma(qx, qx, fmul(qr, qr)))));
                 const float d = fmaxf(nrm, 1e-12f);
-                qr = __fdiv_rn(qr, d); qx = __fdiv_rn(qx, d); qy = __fdiv_rn(qy, d); qz = __fdiv_rn(qz, d);
+                if (d != 1.0f) {         // x / 1 = x: view-tied Gaussians keep the unit quaternion they were created with
+                    qr = __fdiv_rn(qr, d); qx = __fdiv_rn(qx, d); qy = __fdiv_rn(qy, d); qz = __fdiv_rn(qz, d);
+                }
                 op = __fdiv_rn(1.0f, fadd(1.0f, vexpf(-it.op)));
                 // get_depth_and_silhouette (reference utils/slam_helpers.py:217-234): z of w2c * p'
                 c3 = fadd(ffma(fe.depth_row[2], z, ffma(fe.depth_row[1], y, fmul(fe.depth_row[0], x))), fe.depth_row[3]);

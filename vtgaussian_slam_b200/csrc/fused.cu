@@ -28,20 +28,34 @@ tracking_loss_kernel(const __grid_constant__ CamConst cam, VtgsLossConfig cfg, c
     const size_t row_begin = (size_t)cam.row0 * 16 * cam.W;
     const size_t row_end = min(P, (size_t)cam.row1 * 16 * cam.W);
     float ld = 0.f, li = 0.f, cnt = 0.f;
+    // all of a thread's loads are issued before the first dependent use (10 planes x LOSS_PX_PER_THREAD pixels in flight)
+    float in[LOSS_PX_PER_THREAD][10];
+    const size_t pid0 = row_begin + (size_t)blockIdx.x * LOSS_PX_PER_THREAD * 256 + threadIdx.x;
 #pragma unroll
     for (int rep = 0; rep < LOSS_PX_PER_THREAD; ++rep) {
-        const size_t pid = row_begin + ((size_t)blockIdx.x * LOSS_PX_PER_THREAD + rep) * 256 + threadIdx.x;
+        const size_t pid = pid0 + (size_t)rep * 256;
+        if (pid < row_end) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) in[rep][k] = __ldcs(image6 + (size_t)k * P + pid);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) in[rep][6 + k] = __ldg(gt_rgb + (size_t)k * P + pid);
+            in[rep][9] = __ldg(gt_depth + pid);
+        }
+    }
+#pragma unroll
+    for (int rep = 0; rep < LOSS_PX_PER_THREAD; ++rep) {
+        const size_t pid = pid0 + (size_t)rep * 256;
         if (pid >= row_end) break;
-        const float r = image6[pid], g = image6[P + pid], b = image6[2 * P + pid];
-        const float d = image6[3 * P + pid], sil = image6[4 * P + pid], dsq = image6[5 * P + pid];
-        const float gd = gt_depth[pid];
+        const float r = in[rep][0], g = in[rep][1], b = in[rep][2];
+        const float d = in[rep][3], sil = in[rep][4], dsq = in[rep][5];
+        const float gd = in[rep][9];
         const float unc = dsq - d * d;
         bool mask = gd > 0.0f && !(d != d) && !(unc != unc);
         if (cfg.use_sil_for_loss) mask = mask && sil > cfg.sil_thres;
         if (cfg.far_depth_thres > 0.0f) mask = mask && gd < cfg.far_depth_thres;
         // reference :600-605: the colour term is masked only with use_sil_for_loss / outlier masks
         const bool mask_im = cfg.use_sil_for_loss ? mask : true;
-        const float er = r - gt_rgb[pid], eg = g - gt_rgb[P + pid], eb = b - gt_rgb[2 * P + pid];
+        const float er = r - in[rep][6], eg = g - in[rep][7], eb = b - in[rep][8];
         const float ed = d - gd;
         if (mask) { ld += fabsf(ed); cnt += 1.0f; }
         if (mask_im) li += fabsf(er) + fabsf(eg) + fabsf(eb);
