@@ -85,6 +85,22 @@ def test_long_tile_lists_take_the_global_sort_path():
     assert (ref["ranges"][:, 1] - ref["ranges"][:, 0]).max() > 4096
 
 
+@pytest.mark.parametrize("n,quantum", [(1500, 2e-3), (7000, 1e-3), (3000, 0.5)])
+def test_short_and_long_equal_depth_runs(n, quantum):
+    # per-tile radix sort on the depth bits + repair of equal-depth runs by Gaussian index: short runs (local
+    # repair) in the shared-memory (n <= 2048) and the streaming (n > 2048) variants, and runs far beyond the
+    # repair limit (re-sorted by the 64-bit network)
+    W, H = 16, 16
+    K, sc = synthetic.random_scene(n, W, H, seed=6, anisotropic=False, scale_px=(0.3, 1.0), opacity_range=(0.02, 0.2))
+    z_old = sc["means3D"][:, 2].copy()
+    z_new = np.maximum(np.round(z_old / quantum) * quantum, quantum).astype(np.float32)
+    sc["means3D"] *= (z_new / z_old)[:, None]                       # same pixel, quantised depth
+    vis = z_new > 0.2
+    assert len(np.unique(z_new[vis])) < vis.sum()                   # there are exact ties
+    ref, got, bit_exact = _run_case(W, H, sc, K, seed=6)
+    assert bit_exact
+
+
 def test_saturation_and_equal_depth_ties():
     W, H = 48, 48
     K, sc = synthetic.random_scene(6000, W, H, seed=5, anisotropic=False, opacity_range=(0.6, 1.0), scale_px=(2.0, 6.0))

@@ -294,8 +294,7 @@ scatter_kernel(int64_t N, int gx, const GeomRecord* __restrict__ geom, const uin
 // =============================== K4': per-tile sort ========================================
 // One block per tile.  Normalised bitonic network (every compare-exchange ascending, the
 // first sub-step of each merge mirrors the index) so that indices >= n act as +inf padding
-// without being stored.  Segments up to SORT_SMEM_ELEMS are sorted in shared memory;
-// longer ones in place in global memory (same network, block-local barriers).
+// without being stored.  It serves the tie fall-back of the radix sorts below (shared or global memory).
 constexpr int SORT_SMEM_ELEMS = 2048;
 
 __device__ __forceinline__ void bitonic_network(uint64_t* __restrict__ s, int n, int npad) {
@@ -534,6 +533,129 @@ __device__ __forceinline__ void sort_segment_radix(uint64_t* __restrict__ s_keys
     }
 }
 
+// The same radix sort for long segments (n > SORT_SMEM_ELEMS: several overlapping sections in one view): keys
+// stream from / to global memory (L1 / L2 resident: a tile's segment is a few tens of KB), ping-ponging between the
+// segment and `scratch` (the tile's still unused slice of the region-list arena, 8 n entries).  Nothing is held in
+// registers, so any n works: every pass reads its keys twice (count, then rank + scatter).
+__device__ __noinline__ void sort_segment_radix_long(uint64_t* keys, uint64_t* scratch, uint32_t (*wh)[256], uint32_t* s_red,
+                                                     int n, int tid) {
+    const int lane = tid & 31, warp = tid >> 5;
+    const uint32_t lt = (1u << lane) - 1u;
+    const int chunk = ((n + 255) >> 8) << 5;                 // keys per warp (a multiple of 32), list order = (warp, round, lane)
+    const int wbeg = min(n, warp * chunk), wend = min(n, wbeg + chunk);
+    uint32_t dmin = 0xffffffffu, dmax = 0u;
+    for (int i = tid; i < n; i += 256) {
+        const uint32_t hi = (uint32_t)(keys[i] >> 32);
+        dmin = min(dmin, hi);
+        dmax = max(dmax, hi);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        dmin = min(dmin, __shfl_xor_sync(VTGS_FULL_MASK, dmin, o));
+        dmax = max(dmax, __shfl_xor_sync(VTGS_FULL_MASK, dmax, o));
+    }
+    if (lane == 0) { s_red[warp] = dmin; s_red[8 + warp] = dmax; }
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { dmin = min(dmin, s_red[w]); dmax = max(dmax, s_red[8 + w]); }
+    const int hb = 32 - __clz((int)(dmin ^ dmax));
+    __syncthreads();
+    uint64_t* src = keys;
+    uint64_t* dst = scratch;
+    for (int shift = 0; shift < hb; shift += 8) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) wh[warp][lane + 32 * k] = 0u;
+        __syncwarp();
+        for (int base = wbeg; base < wend; base += 32) {
+            const bool valid = base + lane < wend;
+            const uint32_t vm = __ballot_sync(VTGS_FULL_MASK, valid);
+            if (valid) {
+                const uint32_t d = (uint32_t)(src[base + lane] >> (32 + shift)) & 0xffu;
+                const uint32_t peers = __match_any_sync(vm, d);
+                if ((peers & lt) == 0u) wh[warp][d] += (uint32_t)__popc(peers);       // one lane per distinct digit
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+        {
+            uint32_t run = 0u;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) { const uint32_t c = wh[w][tid]; wh[w][tid] = run; run += c; }
+            uint32_t incl = run;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(VTGS_FULL_MASK, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if (lane == 31) s_red[warp] = incl;
+            __syncthreads();
+            uint32_t dbase = incl - run;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) if (w < warp) dbase += s_red[w];
+#pragma unroll
+            for (int w = 0; w < 8; ++w) wh[w][tid] += dbase;
+        }
+        __syncthreads();
+        for (int base = wbeg; base < wend; base += 32) {
+            const bool valid = base + lane < wend;
+            const uint32_t vm = __ballot_sync(VTGS_FULL_MASK, valid);
+            uint64_t k = 0ull;
+            uint32_t d = 0u, peers = 0u, prev = 0u;
+            if (valid) {
+                k = src[base + lane];
+                d = (uint32_t)(k >> (32 + shift)) & 0xffu;
+                peers = __match_any_sync(vm, d);
+                prev = wh[warp][d];
+            }
+            __syncwarp();
+            if (valid) {
+                const uint32_t rank = __popc(peers & lt);
+                if (rank == 0u) wh[warp][d] = prev + (uint32_t)__popc(peers);
+                dst[prev + rank] = k;
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+        uint64_t* t = src; src = dst; dst = t;
+    }
+    if (src != keys) {
+        for (int i = tid; i < n; i += 256) keys[i] = src[i];
+        __syncthreads();
+    }
+    // equal-depth runs: order by id (see sort_segment_radix); the repaired list is assembled in `scratch`
+    constexpr int TIE_RUN_MAX = 48;
+    bool moved = false, too_long = false;
+    for (int i = tid; i < n; i += 256) {
+        const uint64_t k = keys[i];
+        const uint32_t hi = (uint32_t)(k >> 32), lo = (uint32_t)k;
+        int shiftpos = 0, steps = 0;
+        for (int j = i - 1; j >= 0; --j) {
+            const uint64_t o = keys[j];
+            if ((uint32_t)(o >> 32) != hi) break;
+            if ((uint32_t)o > lo) --shiftpos;
+            if (++steps > TIE_RUN_MAX) { too_long = true; break; }
+        }
+        for (int j = i + 1; j < n; ++j) {
+            const uint64_t o = keys[j];
+            if ((uint32_t)(o >> 32) != hi) break;
+            if ((uint32_t)o < lo) ++shiftpos;
+            if (++steps > TIE_RUN_MAX) { too_long = true; break; }
+        }
+        scratch[i + shiftpos] = k;
+        moved |= shiftpos != 0;
+    }
+    const bool any_long = __syncthreads_or(too_long) != 0;
+    const bool any_moved = __syncthreads_or(moved) != 0;
+    if (any_long) {
+        int npad = 2;
+        while (npad < n) npad <<= 1;
+        bitonic_network(keys, n, npad);
+    } else if (any_moved) {
+        for (int i = tid; i < n; i += 256) keys[i] = scratch[i];
+        __syncthreads();
+    }
+}
+
 // After a tile's list is sorted: per-region lists.  Every (sorted) entry is tested once against the
 // tile's 8 warp regions (box of its alpha >= 1/255 ellipse) and appended, in list order, to the list of
 // every region it may touch as (Gaussian id, 1-based position in the tile list).  The blend kernels then
@@ -617,23 +739,8 @@ tile_sort_kernel(const __grid_constant__ CamConst cam, const uint32_t* __restric
         }
         sorted = s_keys;
     } else {
-        int npad = 2;
-        while (npad < n) npad <<= 1;
-        if (n <= SORT_SMEM_ELEMS) {
-            for (int i = threadIdx.x; i < n; i += blockDim.x) s_keys[i] = pair_keys[b + i];
-            __syncthreads();
-            bitonic_network(s_keys, n, npad);
-            for (int i = threadIdx.x; i < n; i += blockDim.x) {
-                const uint64_t k = s_keys[i];
-                point_list[b + i] = (uint32_t)k >> 8;
-                pair_keys[b + i] = k;
-            }
-            sorted = s_keys;
-        } else {
-            __syncthreads();
-            bitonic_network(pair_keys + b, n, npad);
-            for (int i = threadIdx.x; i < n; i += blockDim.x) point_list[b + i] = (uint32_t)pair_keys[b + i] >> 8;
-        }
+        sort_segment_radix_long(pair_keys + b, reinterpret_cast<uint64_t*>(region_pairs + (size_t)8 * b), s_wh, s_cnt, n, threadIdx.x);
+        for (int i = threadIdx.x; i < n; i += 256) point_list[b + i] = (uint32_t)pair_keys[b + i] >> 8;
     }
     build_region_lists(sorted, n, b, tile, region_pairs, region_cnt, s_cnt, s_base);
 }
