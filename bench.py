@@ -39,6 +39,17 @@ def build_workload(small=False, seed=0):
     """configs[1]: one Replica-shaped frame, one Gaussian per pixel (816 000) + 200 000 edge-densified
     Gaussians of the 2x grid, a mapped ('trained') section, pose perturbed by ~1 cm / 0.5 deg."""
     from vtgaussian_slam_b200 import synthetic
+    if small == "c5":
+        # configs[4] shape (side benchmark, --workload c5): ScanNet++-sized view of four overlapping view-tied sections
+        from vtgaussian_slam_b200.slam_loop import quat_from_matrix
+        frames, poses, p = synthetic.multi_section_scene("scannetpp", sections=4, spacing_m=0.3, seed=seed)
+        fr = frames[-1]
+        w2c = np.linalg.inv(poses[-1])
+        q = quat_from_matrix(w2c[:3, :3]).astype(np.float32)
+        t = (w2c[:3, 3] + np.random.default_rng(1).normal(0, 0.01, 3)).astype(np.float32)
+        s = synthetic.setup_camera(fr["W"], fr["H"], fr["K"], np.eye(4))
+        name = "tracking_scannetpp_%dx%d_N%d_4sections" % (fr["W"], fr["H"], p["means3D"].shape[0])
+        return dict(frame=fr, params=p, q=q, t=t, settings=s, name=name)
     if small:
         fr = synthetic.make_frame("replica", 300, 170, seed=seed)
         p = synthetic.view_tied_gaussians(fr, n_edge=12000, opacity="trained")
@@ -517,20 +528,25 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--small", action="store_true", help="300x170 debug workload")
+    ap.add_argument("--workload", choices=["c2", "c5"], default="c2",
+                    help="c2 (default, the headline): Replica 1200x680, ~1 M Gaussians; c5 (side benchmark): ScanNet++-shaped 1752x1168, ~8 M Gaussians in 4 sections")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--mode", default="tracking", choices=["tracking", "mapping"],
                     help="tracking = configs[1] (the driver's line); mapping = keyframe-sharded side benchmark")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
+    wl_key = "c5" if args.workload == "c5" else args.small
+    if args.workload == "c5":
+        args.small = True          # (only gates the C2-specific ncu traffic figure)
     if args.impl == "reference":
         if rank != 0:
             return
-        run_reference_arm(args, build_workload(args.small))
+        run_reference_arm(args, build_workload(wl_key))
         return
     if args.mode == "mapping":
-        run_mapping(args, build_workload(args.small))
+        run_mapping(args, build_workload(wl_key))
         return
-    run_ours(args, build_workload(args.small))
+    run_ours(args, build_workload(wl_key))
 
 
 if __name__ == "__main__":

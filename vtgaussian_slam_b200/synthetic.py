@@ -213,6 +213,39 @@ def view_tied_gaussians(frame, n_target=None, n_edge=0, opacity="fresh", seed=2,
                 log_scales=np.log(scale)[:, None].astype(np.float32))
 
 
+def section_gaussians(frame, c2w=None, opacity="trained", seed=2, color_noise=0.02, factor=1.005):
+    """View-tied Gaussians of one posed frame in the WORLD frame, built from the frame's own depth image the way
+    the reference does at a section start (get_pointcloud + initialize_params, src/vtgaussian_slam.py:76-177):
+    numpy twin of slam_loop.section_from_frame."""
+    W, H, K = frame["W"], frame["H"], frame["K"]
+    fx, fy, cx, cy = K[0, 0], K[1, 1], K[0, 2], K[1, 2]
+    c2w = np.eye(4) if c2w is None else np.asarray(c2w, np.float64)
+    rng = np.random.default_rng(seed)
+    z = frame["depth"].reshape(-1).astype(np.float64) * factor
+    xx = np.tile((np.arange(W) - cx + 0.5) / fx, H)
+    yy = np.repeat((np.arange(H) - cy + 0.5) / fy, W)
+    pts = np.stack([xx * z, yy * z, z], -1) @ c2w[:3, :3].T + c2w[:3, 3]
+    keep = z > 0
+    n = int(keep.sum())
+    cols = frame["im"].reshape(3, -1).T[keep] + rng.normal(0, color_noise, (n, 3))
+    logit = np.zeros((n, 1)) if opacity == "fresh" else rng.uniform(0.0, 4.0, (n, 1))
+    rots = np.tile(np.array([1.0, 0, 0, 0]), (n, 1))
+    scale = z[keep] / ((fx + fy) / 2.0)
+    return dict(means3D=pts[keep].astype(np.float32), rgb_colors=cols.astype(np.float32), unnorm_rotations=rots.astype(np.float32),
+                logit_opacities=logit.astype(np.float32), log_scales=np.log(scale)[:, None].astype(np.float32))
+
+
+def multi_section_scene(shape="scannetpp", sections=4, spacing_m=0.35, width=None, height=None, seed=0, opacity="trained"):
+    """BASELINE config 5 shape: `sections` overlapping view-tied sections created from poses ~spacing_m apart along
+    `trajectory`, concatenated (the reference concatenates the selected sections' params before rendering,
+    src/vtgaussian_slam.py:2734).  Returns (frames, poses[c2w], params) -- all sections in the world frame."""
+    poses = trajectory(sections, step_m=spacing_m, step_deg=4.0, seed=seed + 3)
+    frames = [make_frame(shape, width, height, seed=seed + i, c2w=poses[i]) for i in range(sections)]
+    parts = [section_gaussians(frames[i], poses[i], opacity=opacity, seed=seed + 10 + i) for i in range(sections)]
+    params = {k: np.concatenate([p[k] for p in parts], 0) for k in parts[0]}
+    return frames, poses, params
+
+
 def perturbed_pose(seed=1, trans_sigma=0.01, rot_deg=0.5):
     """Small camera perturbation (tracking start): -> (cam_unnorm_rot[4], cam_trans[3])."""
     rng = np.random.default_rng(seed)
