@@ -112,9 +112,12 @@ tracking_loss_kernel(const __grid_constant__ CamConst cam, VtgsLossConfig cfg, c
 // also emits the three derivative maps), a deterministic finalize, and the SSIM backward that
 // convolves the derivative maps and assembles dL/d(r,g,b,depth).
 constexpr int SSIM_R = 5;                 // window radius
-constexpr int SSIM_T = 16;                // output tile
+constexpr int SSIM_T = 32;                // output tile edge: 32 x 32 pixels per block of 256 threads
 constexpr int SSIM_H = SSIM_T + 2 * SSIM_R;
+constexpr int SSIM_HS = 8;                // horizontal pass: one thread filters a strip of 8 outputs of one row
+constexpr int SSIM_VS = 4;                // vertical pass: one thread filters 4 outputs of one column
 constexpr int MAP_TERMS = 4;              // per-block partials: rgb L1 sum, depth L1 sum, mask count, ssim sum
+static_assert(SSIM_H * (SSIM_T / SSIM_HS) <= 256 && SSIM_T * (SSIM_T / SSIM_VS) == 256, "SSIM strip decomposition");
 
 struct SsimWindow { float g[2 * SSIM_R + 1]; };
 
@@ -129,7 +132,10 @@ static SsimWindow make_window() {
     return w;
 }
 
-// grid (tiles_x, tiles_y, 3 channels); block 16x16.
+// grid (ceil(W/32), ceil(H/32), 3 channels); block 256.  Separable 11-tap window over a 42 x 42 halo in shared
+// memory; both passes are register-tiled (a thread slides the window over a strip it holds in registers: 18 loads
+// feed 8 outputs horizontally, 14 loads feed 4 outputs vertically), which is what bounds this kernel -- shared
+// memory loads, not FMAs or HBM.
 __global__ void __launch_bounds__(256)
 ssim_forward_kernel(int W, int H, const SsimWindow win, const float* __restrict__ image6, const float* __restrict__ gt_rgb,
                     const float* __restrict__ gt_depth, float* __restrict__ maps /* [3 ch][3 maps][P] */,
@@ -141,7 +147,7 @@ ssim_forward_kernel(int W, int H, const SsimWindow win, const float* __restrict_
     const size_t P = (size_t)W * H;
     const float* X = image6 + (size_t)ch * P;
     const float* Y = gt_rgb + (size_t)ch * P;
-    const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * SSIM_T + tx;
+    const int tid = threadIdx.x;
     const int ox = blockIdx.x * SSIM_T - SSIM_R, oy = blockIdx.y * SSIM_T - SSIM_R;
     for (int k = tid; k < SSIM_H * SSIM_H; k += 256) {
         const int r = k / SSIM_H, c = k % SSIM_H;
@@ -151,44 +157,64 @@ ssim_forward_kernel(int W, int H, const SsimWindow win, const float* __restrict_
         sy[r][c] = in ? Y[(size_t)gy * W + gx] : 0.0f;
     }
     __syncthreads();
-    // horizontal pass: 26 rows x 16 columns of the five fields
-    for (int k = tid; k < SSIM_H * SSIM_T; k += 256) {
-        const int r = k / SSIM_T, c = k % SSIM_T;
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f;
+    // horizontal pass: 42 rows x 32 columns of the five fields, strips of 8 columns
+    if (tid < SSIM_H * (SSIM_T / SSIM_HS)) {
+        const int r = tid / (SSIM_T / SSIM_HS), c0 = (tid % (SSIM_T / SSIM_HS)) * SSIM_HS;
+        float xv[SSIM_HS + 2 * SSIM_R], yv[SSIM_HS + 2 * SSIM_R];
 #pragma unroll
-        for (int j = 0; j <= 2 * SSIM_R; ++j) {
-            const float x = sx[r][c + j], y = sy[r][c + j], g = win.g[j];
-            a0 = fmaf(g, x, a0); a1 = fmaf(g, y, a1); a2 = fmaf(g, x * x, a2); a3 = fmaf(g, y * y, a3); a4 = fmaf(g, x * y, a4);
+        for (int i = 0; i < SSIM_HS + 2 * SSIM_R; ++i) { xv[i] = sx[r][c0 + i]; yv[i] = sy[r][c0 + i]; }
+#pragma unroll
+        for (int o = 0; o < SSIM_HS; ++o) {
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f;
+#pragma unroll
+            for (int j = 0; j <= 2 * SSIM_R; ++j) {
+                const float x = xv[o + j], y = yv[o + j], g = win.g[j];
+                a0 = fmaf(g, x, a0); a1 = fmaf(g, y, a1); a2 = fmaf(g, x * x, a2); a3 = fmaf(g, y * y, a3); a4 = fmaf(g, x * y, a4);
+            }
+            hb[0][r][c0 + o] = a0; hb[1][r][c0 + o] = a1; hb[2][r][c0 + o] = a2; hb[3][r][c0 + o] = a3; hb[4][r][c0 + o] = a4;
         }
-        hb[0][r][c] = a0; hb[1][r][c] = a1; hb[2][r][c] = a2; hb[3][r][c] = a3; hb[4][r][c] = a4;
     }
     __syncthreads();
-    const int px = blockIdx.x * SSIM_T + tx, py = blockIdx.y * SSIM_T + ty;
-    float l1 = 0.f, ld = 0.f, cnt = 0.f, ss = 0.f;
-    if (px < W && py < H) {
-        float m1 = 0.f, m2 = 0.f, X2 = 0.f, Y2 = 0.f, XY = 0.f;
+    // vertical pass: thread = (group of 4 rows, column)
+    const int tx = tid & 31, ty0 = (tid >> 5) * SSIM_VS;
+    float f[5][SSIM_VS];
 #pragma unroll
-        for (int j = 0; j <= 2 * SSIM_R; ++j) {
-            const float g = win.g[j];
-            m1 = fmaf(g, hb[0][ty + j][tx], m1); m2 = fmaf(g, hb[1][ty + j][tx], m2);
-            X2 = fmaf(g, hb[2][ty + j][tx], X2); Y2 = fmaf(g, hb[3][ty + j][tx], Y2); XY = fmaf(g, hb[4][ty + j][tx], XY);
+    for (int k = 0; k < 5; ++k) {
+        float v[SSIM_VS + 2 * SSIM_R];
+#pragma unroll
+        for (int i = 0; i < SSIM_VS + 2 * SSIM_R; ++i) v[i] = hb[k][ty0 + i][tx];
+#pragma unroll
+        for (int o = 0; o < SSIM_VS; ++o) {
+            float a = 0.f;
+#pragma unroll
+            for (int j = 0; j <= 2 * SSIM_R; ++j) a = fmaf(win.g[j], v[o + j], a);
+            f[k][o] = a;
         }
-        const float c1 = 0.0001f, c2 = 0.0009f;
-        const float s11 = X2 - m1 * m1, s22 = Y2 - m2 * m2, s12 = XY - m1 * m2;
-        const float A1 = 2.f * m1 * m2 + c1, A2 = 2.f * s12 + c2, B1 = m1 * m1 + m2 * m2 + c1, B2 = s11 + s22 + c2;
-        const float inv = 1.0f / (B1 * B2);
-        const float S = A1 * A2 * inv;
-        ss = S;
-        const size_t pid = (size_t)py * W + px;
-        float* mp = maps + (size_t)ch * 3 * P;
-        mp[pid] = (2.f * m2 * (A2 - A1) - 2.f * m1 * S * (B2 - B1)) * inv;      // dS/dmu1 (X2, XY held)
-        mp[P + pid] = -S / B2;                                                 // dS/dconv(x^2)
-        mp[2 * P + pid] = 2.f * A1 * inv;                                      // dS/dconv(xy)
-        l1 = fabsf(sx[ty + SSIM_R][tx + SSIM_R] - sy[ty + SSIM_R][tx + SSIM_R]);
-        if (ch == 0) {
-            const float d = image6[3 * P + pid], dsq = image6[5 * P + pid], gd = gt_depth[pid];
-            const float unc = dsq - d * d;
-            if (gd > 0.0f && !(d != d) && !(unc != unc)) { ld = fabsf(gd - d); cnt = 1.0f; }
+    }
+    const int px = blockIdx.x * SSIM_T + tx;
+    float l1 = 0.f, ld = 0.f, cnt = 0.f, ss = 0.f;
+#pragma unroll
+    for (int o = 0; o < SSIM_VS; ++o) {
+        const int ty = ty0 + o, py = blockIdx.y * SSIM_T + ty;
+        if (px < W && py < H) {
+            const float m1 = f[0][o], m2 = f[1][o], X2 = f[2][o], Y2 = f[3][o], XY = f[4][o];
+            const float c1 = 0.0001f, c2 = 0.0009f;
+            const float s11 = X2 - m1 * m1, s22 = Y2 - m2 * m2, s12 = XY - m1 * m2;
+            const float A1 = 2.f * m1 * m2 + c1, A2 = 2.f * s12 + c2, B1 = m1 * m1 + m2 * m2 + c1, B2 = s11 + s22 + c2;
+            const float inv = 1.0f / (B1 * B2);
+            const float S = A1 * A2 * inv;
+            ss += S;
+            const size_t pid = (size_t)py * W + px;
+            float* mp = maps + (size_t)ch * 3 * P;
+            mp[pid] = (2.f * m2 * (A2 - A1) - 2.f * m1 * S * (B2 - B1)) * inv;      // dS/dmu1 (X2, XY held)
+            mp[P + pid] = -S / B2;                                                 // dS/dconv(x^2)
+            mp[2 * P + pid] = 2.f * A1 * inv;                                      // dS/dconv(xy)
+            l1 += fabsf(sx[ty + SSIM_R][tx + SSIM_R] - sy[ty + SSIM_R][tx + SSIM_R]);
+            if (ch == 0) {
+                const float d = image6[3 * P + pid], dsq = image6[5 * P + pid], gd = gt_depth[pid];
+                const float unc = dsq - d * d;
+                if (gd > 0.0f && !(d != d) && !(unc != unc)) { ld += fabsf(gd - d); cnt += 1.0f; }
+            }
         }
     }
     l1 = warp_sum(l1); ld = warp_sum(ld); cnt = warp_sum(cnt); ss = warp_sum(ss);
@@ -238,6 +264,7 @@ mapping_finalize_kernel(const float* __restrict__ partials, int nblocks, int W, 
 }
 
 // dL/dx = conv(gS * a) + 2 x conv(gS * b) + y conv(gS * c), gS = -0.2 w_im / (3P); plus the L1 terms.
+// Same tiling as the forward: 32 x 32 outputs per block, register-tiled separable passes.
 __global__ void __launch_bounds__(256)
 ssim_backward_kernel(int W, int H, const SsimWindow win, VtgsLossConfig cfg, const float* __restrict__ image6,
                      const float* __restrict__ gt_rgb, const float* __restrict__ gt_depth, const float* __restrict__ maps,
@@ -247,7 +274,7 @@ ssim_backward_kernel(int W, int H, const SsimWindow win, VtgsLossConfig cfg, con
     const int ch = blockIdx.z;
     const size_t P = (size_t)W * H;
     const float* mp = maps + (size_t)ch * 3 * P;
-    const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * SSIM_T + tx;
+    const int tid = threadIdx.x;
     const int ox = blockIdx.x * SSIM_T - SSIM_R, oy = blockIdx.y * SSIM_T - SSIM_R;
     for (int k = tid; k < SSIM_H * SSIM_H; k += 256) {
         const int r = k / SSIM_H, c = k % SSIM_H;
@@ -259,36 +286,56 @@ ssim_backward_kernel(int W, int H, const SsimWindow win, VtgsLossConfig cfg, con
         sm[2][r][c] = in ? mp[2 * P + pid] : 0.0f;
     }
     __syncthreads();
-    for (int k = tid; k < SSIM_H * SSIM_T; k += 256) {
-        const int r = k / SSIM_T, c = k % SSIM_T;
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    if (tid < SSIM_H * (SSIM_T / SSIM_HS)) {
+        const int r = tid / (SSIM_T / SSIM_HS), c0 = (tid % (SSIM_T / SSIM_HS)) * SSIM_HS;
 #pragma unroll
-        for (int j = 0; j <= 2 * SSIM_R; ++j) {
-            const float g = win.g[j];
-            a0 = fmaf(g, sm[0][r][c + j], a0); a1 = fmaf(g, sm[1][r][c + j], a1); a2 = fmaf(g, sm[2][r][c + j], a2);
+        for (int k = 0; k < 3; ++k) {
+            float v[SSIM_HS + 2 * SSIM_R];
+#pragma unroll
+            for (int i = 0; i < SSIM_HS + 2 * SSIM_R; ++i) v[i] = sm[k][r][c0 + i];
+#pragma unroll
+            for (int o = 0; o < SSIM_HS; ++o) {
+                float a = 0.f;
+#pragma unroll
+                for (int j = 0; j <= 2 * SSIM_R; ++j) a = fmaf(win.g[j], v[o + j], a);
+                hb[k][r][c0 + o] = a;
+            }
         }
-        hb[0][r][c] = a0; hb[1][r][c] = a1; hb[2][r][c] = a2;
     }
     __syncthreads();
-    const int px = blockIdx.x * SSIM_T + tx, py = blockIdx.y * SSIM_T + ty;
-    if (px >= W || py >= H) return;
-    float ca = 0.f, cb = 0.f, cc = 0.f;
+    const int tx = tid & 31, ty0 = (tid >> 5) * SSIM_VS;
+    float f[3][SSIM_VS];
 #pragma unroll
-    for (int j = 0; j <= 2 * SSIM_R; ++j) {
-        const float g = win.g[j];
-        ca = fmaf(g, hb[0][ty + j][tx], ca); cb = fmaf(g, hb[1][ty + j][tx], cb); cc = fmaf(g, hb[2][ty + j][tx], cc);
+    for (int k = 0; k < 3; ++k) {
+        float v[SSIM_VS + 2 * SSIM_R];
+#pragma unroll
+        for (int i = 0; i < SSIM_VS + 2 * SSIM_R; ++i) v[i] = hb[k][ty0 + i][tx];
+#pragma unroll
+        for (int o = 0; o < SSIM_VS; ++o) {
+            float a = 0.f;
+#pragma unroll
+            for (int j = 0; j <= 2 * SSIM_R; ++j) a = fmaf(win.g[j], v[o + j], a);
+            f[k][o] = a;
+        }
     }
-    const size_t pid = (size_t)py * W + px;
-    const float x = image6[(size_t)ch * P + pid], y = gt_rgb[(size_t)ch * P + pid];
+    const int px = blockIdx.x * SSIM_T + tx;
+    if (px >= W) return;
     const float n3 = 3.0f * (float)W * (float)H;
-    const float dssim = ca + 2.0f * x * cb + y * cc;
-    dL_dimage4[(size_t)ch * P + pid] = cfg.w_im * (0.8f * sgn(x - y) - 0.2f * dssim) / n3;
-    if (ch == 0) {
-        const float d = image6[3 * P + pid], dsq = image6[5 * P + pid], gd = gt_depth[pid];
-        const float unc = dsq - d * d;
-        const bool mask = gd > 0.0f && !(d != d) && !(unc != unc);
-        const float cnt = loss_terms[3];
-        dL_dimage4[3 * P + pid] = mask ? cfg.w_depth * sgn(d - gd) / cnt : 0.0f;
+#pragma unroll
+    for (int o = 0; o < SSIM_VS; ++o) {
+        const int py = blockIdx.y * SSIM_T + ty0 + o;
+        if (py >= H) break;
+        const size_t pid = (size_t)py * W + px;
+        const float x = image6[(size_t)ch * P + pid], y = gt_rgb[(size_t)ch * P + pid];
+        const float dssim = f[0][o] + 2.0f * x * f[1][o] + y * f[2][o];
+        dL_dimage4[(size_t)ch * P + pid] = cfg.w_im * (0.8f * sgn(x - y) - 0.2f * dssim) / n3;
+        if (ch == 0) {
+            const float d = image6[3 * P + pid], dsq = image6[5 * P + pid], gd = gt_depth[pid];
+            const float unc = dsq - d * d;
+            const bool mask = gd > 0.0f && !(d != d) && !(unc != unc);
+            const float cnt = loss_terms[3];
+            dL_dimage4[3 * P + pid] = mask ? cfg.w_depth * sgn(d - gd) / cnt : 0.0f;
+        }
     }
 }
 
@@ -342,7 +389,7 @@ int launch_loss(const VtgsCamera* camera, const VtgsLossConfig* cfg, const float
         if (cam.row0 != 0 || cam.row1 != cam.gy) { set_error("mapping loss is not band-sharded"); return VTGS_E_INVALID; }
         static const SsimWindow win = make_window();
         const size_t P = (size_t)cam.W * cam.H;
-        const dim3 grid((cam.W + SSIM_T - 1) / SSIM_T, (cam.H + SSIM_T - 1) / SSIM_T, 3), block(SSIM_T, SSIM_T);
+        const dim3 grid((cam.W + SSIM_T - 1) / SSIM_T, (cam.H + SSIM_T - 1) / SSIM_T, 3), block(256);
         const int nb = (int)(grid.x * grid.y * grid.z);
         float* maps = scratch;                      // 9 P floats
         float* partials = scratch + 9 * P;          // nb * 4
