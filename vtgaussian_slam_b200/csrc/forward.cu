@@ -28,7 +28,7 @@ namespace vtgs {
 // Warp-collective walk over every lane's tile rect [minx,maxx) x [miny,maxy).  Each step all lanes
 // present their current tile (or none); lanes presenting the same tile are grouped with
 // match.any so that the callback can issue ONE atomic per distinct tile:
-//   f(tile, peers_mask, rank_in_group, is_leader).  Must be called by all 32 lanes.
+//   f(tile, tile_x, tile_y, peers_mask, rank_in_group, is_leader).  Must be called by all 32 lanes.
 template <typename F>
 __device__ __forceinline__ void warp_tile_walk(int minx, int miny, int maxx, int maxy, int gx, F f) {
     const int lane = threadIdx.x & 31;
@@ -39,7 +39,7 @@ __device__ __forceinline__ void warp_tile_walk(int minx, int miny, int maxx, int
         const uint32_t peers = __match_any_sync(VTGS_FULL_MASK, tile);
         if (have) {
             const int rank = __popc(peers & ((1u << lane) - 1u));
-            f(tile, peers, rank, rank == 0);
+            f(tile, tx, ty, peers, rank, rank == 0);
             if (++tx >= maxx) { tx = minx; if (++ty >= maxy) have = false; }
         }
     }
@@ -185,7 +185,7 @@ preprocess_kernel(const __grid_constant__ CamConst cam, int64_t N, FrontEnd fe,
         }
         // per-tile histogram, warp-aggregated: neighbouring Gaussians (neighbouring pixels of a view-tied
         // section) touch the same tiles, so one atomic per distinct tile per warp step instead of one per lane
-        warp_tile_walk(w_minx, w_miny, w_maxx, w_maxy, cam.gx, [&](int tile, uint32_t peers, int /*rank*/, bool leader) {
+        warp_tile_walk(w_minx, w_miny, w_maxx, w_maxy, cam.gx, [&](int tile, int /*tx*/, int /*ty*/, uint32_t peers, int /*rank*/, bool leader) {
             if (leader) atomicAdd(&tile_counts[tile], (uint32_t)__popc(peers));
         });
     }
@@ -278,14 +278,13 @@ scatter_kernel(int64_t N, int gx, const GeomRecord* __restrict__ geom, const uin
         minx = rmin & 0xffff; miny = rmin >> 16; maxx = rmax & 0xffff; maxy = rmax >> 16;
         key = ((uint64_t)__float_as_uint(q3.x) << 32) | ((uint64_t)(uint32_t)i << 8);
     }
-    warp_tile_walk(minx, miny, maxx, maxy, gx, [&](int tile, uint32_t peers, int rank, bool leader) {
+    warp_tile_walk(minx, miny, maxx, maxy, gx, [&](int tile, int tx, int ty, uint32_t peers, int rank, bool leader) {
         uint32_t base = 0;
         if (leader) base = ranges[2 * tile] + atomicAdd(&tile_cursor[tile], (uint32_t)__popc(peers));
         base = __shfl_sync(peers, base, __ffs(peers) - 1);
         const uint32_t pos = base + (uint32_t)rank;
         // low 8 bits: which of this tile's 8 warp regions the splat's alpha >= 1/255 box touches (ids are unique, so
         // these bits never decide the order; the sort kernel reads them back instead of gathering the record again)
-        const int tx = tile % gx, ty = tile / gx;
         const uint32_t rmask = region_mask(q0, (float)(tx * 16), (float)(ty * 16));
         if (pos < ranges[2 * tile + 1]) pair_keys[pos] = key | rmask;
     });
