@@ -257,12 +257,17 @@ VTGS_API int vtgs_fused_forward(const VtgsCamera* cam, const VtgsParams* params,
 typedef struct VtgsLossConfig {
     int32_t mode;                   /* 0 tracking, 1 mapping                              */
     int32_t use_sil_for_loss;
-    int32_t ignore_outlier_depth;   /* median-based mask: NOT fused (returns UNSUPPORTED) */
+    int32_t ignore_outlier_depth;   /* tracking: also mask |gt - d| (gt > 0) >= 50 * its median over the frame
+                                       (reference src/vtgaussian_slam.py:525-528; exact lower median as
+                                       torch.median, four 8-bit radix-select passes on the device).  Whole frame
+                                       only: UNSUPPORTED together with a tile-row band                       */
     int32_t use_l1;
     float   sil_thres;
     float   w_im;
     float   w_depth;
     float   far_depth_thres;        /* <= 0: disabled                                     */
+    const uint8_t* pixel_mask;      /* optional [H,W] bytes, tracking: pixels with 0 are masked out (the reference's
+                                       overlap-visibility mask, :536-583, computed by the caller); NULL: none */
 } VtgsLossConfig;
 
 VTGS_API int vtgs_loss(const VtgsCamera* cam, const VtgsLossConfig* cfg,

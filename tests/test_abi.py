@@ -36,7 +36,7 @@ def test_struct_layouts_match_the_header(L):
     assert C.sizeof(_lib.VtgsBuffers) == 8 * 15
     assert C.sizeof(_lib.VtgsParams) == 8 * 5 + 8 + 8
     assert C.sizeof(_lib.VtgsPose) == 16 + 16
-    assert C.sizeof(_lib.VtgsLossConfig) == 32
+    assert C.sizeof(_lib.VtgsLossConfig) == 32 + 8
     assert C.sizeof(_lib.VtgsParamGrads) == 72
 
 

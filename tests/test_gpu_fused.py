@@ -217,6 +217,68 @@ def test_get_loss_fused_equals_dropin():
     assert params["rgb_colors"].grad.abs().sum().item() > 0 and params["cam_trans"].grad is None
 
 
+@pytest.mark.parametrize("use_sil", [True, False])
+def test_outlier_median_and_visibility_masks_match_the_torch_path(use_sil):
+    """ignore_outlier_depth_loss (depth error < 50 x its frame median, reference :525-528: exact lower median by radix
+    select on the device) and the overlap-visibility mask, against the reference-shaped torch masks on the same render."""
+    from vtgaussian_slam_b200.fused import FusedRenderer
+    fr, p, q, t = _scene(200, 120, n_edge=1500)
+    settings, _ = _settings(fr)
+    rng = np.random.default_rng(3)
+    gt_depth = fr["depth"].copy()
+    gt_depth[0, 20:40, 30:90] *= 3.0                  # gross outliers: error >> 50 x median
+    gt_depth[0, 60:75, 100:160] = 0.0                 # invalid depth
+    vis = (rng.uniform(size=gt_depth.shape[1:]) > 0.2)
+    data = dict(cam=settings, im=torch.tensor(fr["im"], device=DEV), depth=torch.tensor(gt_depth, device=DEV),
+                w2c=torch.eye(4, device=DEV))
+    vis_t = torch.tensor(vis, device=DEV)
+
+    # the median itself, bit-exact against torch.median on the fused render's depth plane
+    gp = {k: torch.tensor(v, device=DEV) for k, v in p.items()}
+    r = FusedRenderer(settings, p["means3D"].shape[0], device=DEV)
+    img, _ = r.forward(gp, torch.tensor(q, device=DEV), torch.tensor(t, device=DEV))
+    terms = r.tracking_loss(data["im"], data["depth"], w_im=0.5, w_depth=1.0, use_sil_for_loss=use_sil, sil_thres=0.99,
+                            ignore_outlier_depth_loss=True, pixel_mask=vis_t).clone()
+    derr = torch.abs(data["depth"] - img[3:4]) * (data["depth"] > 0)
+    med = derr.median()
+    mask = (derr < 50 * med) & (data["depth"] > 0) & vis_t[None]
+    if use_sil:
+        mask = mask & (img[4:5] > 0.99)
+    assert int(terms[3].item()) == int(mask.sum().item())                       # identical mask => identical median
+    assert 0 < int(mask.sum().item()) < mask.numel() - 60 * 20
+    ld = torch.abs(data["depth"] - img[3:4])[mask].sum().item()
+    li = torch.abs(data["im"] - img[:3])[mask.expand(3, -1, -1)].sum().item()
+    assert abs(terms[2].item() - 1.0 * ld) <= 1e-4 * ld and abs(terms[1].item() - 0.5 * li) <= 1e-4 * li
+    dL = r.dL_dimage4
+    assert float(dL[3][~mask[0]].abs().max().item()) == 0.0 and float(dL[:3][:, ~mask[0]].abs().max().item()) == 0.0
+
+    # through get_loss: fused loss == two drop-in passes + torch masks (last-ulp front-end differences only)
+    out = {}
+    for backend in ("dropin", "fused"):
+        params = {k: torch.nn.Parameter(torch.tensor(v, device=DEV)) for k, v in p.items()}
+        params["cam_unnorm_rots"] = torch.nn.Parameter(torch.tensor(q, device=DEV).reshape(1, 4, 1).contiguous())
+        params["cam_trans"] = torch.nn.Parameter(torch.tensor(t, device=DEV).reshape(1, 3, 1).contiguous())
+        variables = dict(max_2D_radius=torch.zeros(p["means3D"].shape[0], device=DEV))
+        loss, variables, wl = slam_ops.get_loss(params, data, variables, 0, dict(im=0.5, depth=1.0), use_sil, 0.99, True, True,
+                                                tracking=True, dataset_name="scannetpp", vis_mask=vis_t[None], backend=backend)
+        loss.backward()
+        out[backend] = (loss.item(), params["cam_unnorm_rots"].grad.cpu().numpy(), params["cam_trans"].grad.cpu().numpy())
+    a, b = out["dropin"], out["fused"]
+    assert abs(a[0] - b[0]) <= 2e-3 * abs(a[0])
+    assert rel_err(b[1], a[1]) <= 2e-2 and rel_err(b[2], a[2]) <= 2e-2
+
+
+def test_outlier_median_is_rejected_with_a_tile_band():
+    from vtgaussian_slam_b200.fused import FusedRenderer
+    fr, p, q, t = _scene(200, 120, n_edge=500)
+    settings, _ = _settings(fr)
+    gp = {k: torch.tensor(v, device=DEV) for k, v in p.items()}
+    r = FusedRenderer(settings, p["means3D"].shape[0], device=DEV, tile_rows=(0, 4))
+    r.forward(gp, torch.tensor(q, device=DEV), torch.tensor(t, device=DEV))
+    with pytest.raises(NotImplementedError):            # VTGS_E_UNSUPPORTED
+        r.tracking_loss(torch.tensor(fr["im"], device=DEV), torch.tensor(fr["depth"], device=DEV), ignore_outlier_depth_loss=True)
+
+
 def test_mapping_loss_kernels_match_torch_autograd():
     """vtgs_loss mode 1 (SSIM forward/backward kernels) against the reference-shaped torch loss
     (0.8 L1 + 0.2 (1 - calc_ssim) + mean depth L1) and its autograd gradient."""

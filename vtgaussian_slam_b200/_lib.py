@@ -68,7 +68,7 @@ class VtgsLossConfig(C.Structure):
     _fields_ = [
         ("mode", C.c_int32), ("use_sil_for_loss", C.c_int32), ("ignore_outlier_depth", C.c_int32),
         ("use_l1", C.c_int32), ("sil_thres", C.c_float), ("w_im", C.c_float), ("w_depth", C.c_float),
-        ("far_depth_thres", C.c_float),
+        ("far_depth_thres", C.c_float), ("pixel_mask", C.c_void_p),
     ]
 
 

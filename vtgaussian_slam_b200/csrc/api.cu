@@ -193,7 +193,7 @@ uint64_t vtgs_pose_scratch_floats(int64_t N) { return (uint64_t)((N + 255) / 256
 uint64_t vtgs_loss_scratch_floats(int32_t W, int32_t H, int32_t mode) {
     const uint64_t P = (uint64_t)W * H;
     if (mode == 1) return 9 * P + ((uint64_t)((W + 15) / 16) * ((H + 15) / 16) * 3 + 1) * 4;
-    return ((P + 255) / 256 + 1) * 4;
+    return ((P + 255) / 256 + 1) * 4 + 512;      /* + the radix-select state of the outlier median */
 }
 
 int vtgs_retie(float* means3D, int64_t n, const float* w2c_old, const float* cam_unnorm_rot, const float* cam_trans, void* stream) {

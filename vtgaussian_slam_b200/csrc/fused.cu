@@ -2,6 +2,7 @@
 // the tracking / mapping loss of get_loss (reference src/vtgaussian_slam.py:513-612,678-679)
 // with its gradient w.r.t. the rendered planes, and the Adam update
 // (torch.optim.Adam as configured at src/vtgaussian_slam.py:180-187).
+#include <algorithm>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -12,6 +13,60 @@ constexpr int LOSS_TERMS = 4;      // per-block partials: depth L1, rgb L1, mask
 
 __device__ __forceinline__ float sgn(float v) { return v > 0.0f ? 1.0f : (v < 0.0f ? -1.0f : 0.0f); }
 
+// ---- exact median of depth_error = |gt - d| * (gt > 0) over the frame (reference :525-527, torch.median = the
+// LOWER median, element (P - 1) / 2 of the sorted values) by radix select: four passes, each a 256-bin histogram of
+// the next byte of the float bits (non-negative floats order like their bit patterns; NaN sorts last and, as in
+// torch, makes the median NaN) among the values matching the prefix selected so far; the block that finishes last
+// picks the bin holding the target rank.  state: hist[256], prefix, rank, nan_count, ticket, result bits.
+constexpr int MEDIAN_STATE_WORDS = 264;
+__global__ void __launch_bounds__(256)
+median_pass_kernel(const float* __restrict__ depth_plane, const float* __restrict__ gt_depth, size_t P, int pass,
+                   unsigned int* __restrict__ st) {
+    __shared__ unsigned int sh[256];
+    __shared__ bool s_last;
+    const int tid = threadIdx.x;
+    sh[tid] = 0u;
+    __syncthreads();
+    const unsigned int prefix = __ldcg(st + 256);
+    unsigned int nan_local = 0u;
+    for (size_t i = (size_t)blockIdx.x * 256 + tid; i < P; i += (size_t)gridDim.x * 256) {
+        const float gd = gt_depth[i], d = depth_plane[i];
+        const float e = fabsf(gd - d) * (gd > 0.0f ? 1.0f : 0.0f);
+        unsigned int key = __float_as_uint(e);
+        if (e != e) { key = 0xffffffffu; if (pass == 0) ++nan_local; }
+        if (pass == 0 || (key >> (32 - 8 * pass)) == prefix) atomicAdd(&sh[(key >> (24 - 8 * pass)) & 0xffu], 1u);
+    }
+    __syncthreads();
+    if (sh[tid]) atomicAdd(st + tid, sh[tid]);
+    if (nan_local) atomicAdd(st + 258, nan_local);
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(st + 259, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    sh[tid] = __ldcg(st + tid);
+    st[tid] = 0u;                                        // clean histogram for the next pass / call
+    __syncthreads();
+    if (tid == 0) {
+        unsigned int rank = pass == 0 ? (unsigned int)((P - 1) / 2) : __ldcg(st + 257);
+        unsigned int cum = 0u;
+        int b = 0;
+        for (; b < 255; ++b) {
+            if (rank < cum + sh[b]) break;
+            cum += sh[b];
+        }
+        const unsigned int np = (prefix << 8) | (unsigned int)b;
+        st[256] = pass == 3 ? 0u : np;
+        st[257] = rank - cum;
+        if (pass == 3) {
+            st[260] = __ldcg(st + 258) > 0u ? 0x7fc00000u : np;
+            st[258] = 0u;
+        }
+        st[259] = 0u;
+    }
+}
+
 // Tracking loss (mode 0): sums of masked absolute differences; dL/dplane = w * sign * mask.
 // The block that finishes last performs the final reduction of the per-block partials (fixed slice order,
 // fp64: deterministic regardless of which block is last) -- no second launch.  `ticket` must be zero on
@@ -20,13 +75,15 @@ __global__ void __launch_bounds__(256)
 tracking_loss_kernel(const __grid_constant__ CamConst cam, VtgsLossConfig cfg, const float* __restrict__ image6,
                      const float* __restrict__ gt_rgb, const float* __restrict__ gt_depth,
                      float* __restrict__ dL_dimage4, float* __restrict__ partials, unsigned int* __restrict__ ticket,
-                     float* __restrict__ loss_terms) {
+                     float* __restrict__ loss_terms, const unsigned int* __restrict__ median_state) {
     __shared__ float s_part[8][LOSS_TERMS];
     __shared__ double s_sum[LOSS_TERMS][64];
     __shared__ bool s_last;
     const size_t P = (size_t)cam.W * cam.H;
     const size_t row_begin = (size_t)cam.row0 * 16 * cam.W;
     const size_t row_end = min(P, (size_t)cam.row1 * 16 * cam.W);
+    // outlier mask: depth_error < 50 * median(depth_error) (NaN median: nothing passes)
+    const float outlier_thr = median_state ? 50.0f * __uint_as_float(__ldcg(median_state + 260)) : 0.0f;
     float ld = 0.f, li = 0.f, cnt = 0.f;
     // all of a thread's loads are issued before the first dependent use (10 planes x LOSS_PX_PER_THREAD pixels in flight)
     float in[LOSS_PX_PER_THREAD][10];
@@ -53,8 +110,10 @@ tracking_loss_kernel(const __grid_constant__ CamConst cam, VtgsLossConfig cfg, c
         bool mask = gd > 0.0f && !(d != d) && !(unc != unc);
         if (cfg.use_sil_for_loss) mask = mask && sil > cfg.sil_thres;
         if (cfg.far_depth_thres > 0.0f) mask = mask && gd < cfg.far_depth_thres;
+        if (median_state) mask = mask && (fabsf(gd - d) * (gd > 0.0f ? 1.0f : 0.0f) < outlier_thr);
+        if (cfg.pixel_mask) mask = mask && cfg.pixel_mask[pid] != 0;
         // reference :600-605: the colour term is masked only with use_sil_for_loss / outlier masks
-        const bool mask_im = cfg.use_sil_for_loss ? mask : true;
+        const bool mask_im = (cfg.use_sil_for_loss || cfg.ignore_outlier_depth) ? mask : true;
         const float er = r - in[rep][6], eg = g - in[rep][7], eb = b - in[rep][8];
         const float ed = d - gd;
         if (mask) { ld += fabsf(ed); cnt += 1.0f; }
@@ -383,7 +442,10 @@ int launch_loss(const VtgsCamera* camera, const VtgsLossConfig* cfg, const float
                 const float* gt_rgb, const float* gt_depth, float* dL_dimage4, float* loss_terms,
                 float* scratch, cudaStream_t stream) {
     const CamConst cam = make_cam_const(*camera);
-    if (cfg->ignore_outlier_depth) { set_error("ignore_outlier_depth_loss (median mask) is not fused"); return VTGS_E_UNSUPPORTED; }
+    if (cfg->ignore_outlier_depth && (cfg->mode != 0 || cam.row0 != 0 || cam.row1 != cam.gy)) {
+        set_error("ignore_outlier_depth_loss (frame-wide median mask) is fused for whole-frame tracking only");
+        return VTGS_E_UNSUPPORTED;
+    }
     if (!cfg->use_l1) { set_error("use_l1 = False is not supported"); return VTGS_E_UNSUPPORTED; }
     if (cfg->mode == 1) {
         if (cam.row0 != 0 || cam.row1 != cam.gy) { set_error("mapping loss is not band-sharded"); return VTGS_E_INVALID; }
@@ -406,7 +468,19 @@ int launch_loss(const VtgsCamera* camera, const VtgsLossConfig* cfg, const float
     const int nblocks = (int)((npx + 256 * LOSS_PX_PER_THREAD - 1) / (256 * LOSS_PX_PER_THREAD));
     if (nblocks > 0) {
         unsigned int* ticket = reinterpret_cast<unsigned int*>(scratch + (size_t)nblocks * LOSS_TERMS);
-        { VTGS_PROF("tracking_loss_kernel", stream); tracking_loss_kernel<<<nblocks, 256, 0, stream>>>(cam, *cfg, image6, gt_rgb, gt_depth, dL_dimage4, scratch, ticket, loss_terms); }
+        unsigned int* median_state = nullptr;
+        if (cfg->ignore_outlier_depth) {
+            median_state = ticket + 16;
+            const size_t P = (size_t)cam.W * cam.H;
+            const int mb = (int)std::min<size_t>((P + 1023) / 1024, 148 * 4);
+            VTGS_CUDA_CHECK(cudaMemsetAsync(median_state, 0, MEDIAN_STATE_WORDS * sizeof(unsigned int), stream));
+            for (int pass = 0; pass < 4; ++pass) {
+                VTGS_PROF("median_pass_kernel", stream);
+                median_pass_kernel<<<mb, 256, 0, stream>>>(image6 + 3 * P, gt_depth, P, pass, median_state);
+            }
+            VTGS_LAUNCH_CHECK();
+        }
+        { VTGS_PROF("tracking_loss_kernel", stream); tracking_loss_kernel<<<nblocks, 256, 0, stream>>>(cam, *cfg, image6, gt_rgb, gt_depth, dL_dimage4, scratch, ticket, loss_terms, median_state); }
         VTGS_LAUNCH_CHECK();
     } else {
         VTGS_CUDA_CHECK(cudaMemsetAsync(loss_terms, 0, 8 * sizeof(float), stream));

@@ -97,11 +97,19 @@ class FusedRenderer:
         return self.image6, self.radii[:self.N]
 
     def tracking_loss(self, gt_rgb, gt_depth, w_im=0.5, w_depth=0.025, use_sil_for_loss=True, sil_thres=0.99,
-                      far_depth_thres=0.0, image6=None):
+                      far_depth_thres=0.0, image6=None, ignore_outlier_depth_loss=False, pixel_mask=None):
         """Masked-L1 tracking loss (reference get_loss :513-605,:678-679) of the last forward.
+        ignore_outlier_depth_loss: also drop pixels whose depth error is >= 50x its frame median (:525-528);
+        pixel_mask: optional [H,W] uint8 / bool CUDA tensor, 0 = masked out (the overlap-visibility mask, :536-583).
         -> loss_terms[8] (device): loss, w_im*im, w_depth*depth, mask count, ...; fills dL_dimage4."""
-        cfg = _lib.VtgsLossConfig(0, int(bool(use_sil_for_loss)), 0, 1, float(sil_thres), float(w_im), float(w_depth),
-                                  float(far_depth_thres))
+        pm = None
+        if pixel_mask is not None:
+            _require_cuda("pixel_mask", pixel_mask)
+            pm = pixel_mask.reshape(self.H, self.W)
+            pm = (pm if pm.dtype == torch.uint8 else pm.to(torch.uint8)).contiguous()
+            self._pixel_mask = pm               # keep alive until the kernel has run
+        cfg = _lib.VtgsLossConfig(0, int(bool(use_sil_for_loss)), int(bool(ignore_outlier_depth_loss)), 1, float(sil_thres),
+                                  float(w_im), float(w_depth), float(far_depth_thres), _ptr(pm))
         img = self.image6 if image6 is None else image6
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().vtgs_loss(C.byref(self.cam), C.byref(cfg), _ptr(img), _ptr(gt_rgb), _ptr(gt_depth),
@@ -184,12 +192,13 @@ class TrackingSolver:
 
     def __init__(self, settings, params, device="cuda:0", lr_rot=4e-4, lr_trans=2e-3, w_im=0.5, w_depth=0.025,
                  use_sil_for_loss=True, sil_thres=0.99, tile_rows=(0, 0), pair_capacity=None, use_graph=True,
-                 process_group=None):
+                 process_group=None, ignore_outlier_depth_loss=False, far_depth_thres=0.0):
         self.device = torch.device(device)
         self.params = {k: params[k].detach().to(self.device).float().contiguous() for k in PARAM_KEYS}
         N = self.params["means3D"].shape[0]
         self.r = FusedRenderer(settings, N, device=self.device, tile_rows=tile_rows, pair_capacity=pair_capacity)
-        self.cfg = dict(w_im=w_im, w_depth=w_depth, use_sil_for_loss=use_sil_for_loss, sil_thres=sil_thres)
+        self.cfg = dict(w_im=w_im, w_depth=w_depth, use_sil_for_loss=use_sil_for_loss, sil_thres=sil_thres,
+                        ignore_outlier_depth_loss=ignore_outlier_depth_loss, far_depth_thres=far_depth_thres)
         self.lr_rot, self.lr_trans = lr_rot, lr_trans
         f32 = dict(dtype=torch.float32, device=self.device)
         self.cam_q = torch.tensor([1.0, 0, 0, 0], **f32)

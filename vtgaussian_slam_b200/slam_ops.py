@@ -416,8 +416,7 @@ def get_loss(params, curr_data, variables, iter_time_idx, loss_weights, use_sil_
         cam_t = params['cam_trans'][0, :, iter_time_idx]
         if not camera_grad:
             cam_q, cam_t = cam_q.detach(), cam_t.detach()
-        fused_loss_ok = (tracking and use_l1 and not ignore_outlier_depth_loss and vis_mask is None and additional_mask is None
-                         and set(loss_weights) == {'im', 'depth'})
+        fused_loss_ok = (tracking and use_l1 and additional_mask is None and set(loss_weights) == {'im', 'depth'})
         if fused_loss_ok:
             # whole tracking loss on the device: no boolean-index gathers, no host synchronisation
             thres, thres_fn = sil_thres, None
@@ -438,7 +437,10 @@ def get_loss(params, curr_data, variables, iter_time_idx, loss_weights, use_sil_
             elif far_depth_filter_thres is not None and dataset_name != 'scannetpp':
                 far = float(far_depth_filter_thres)
             cfg = dict(w_im=float(loss_weights['im']), w_depth=float(loss_weights['depth']),
-                       use_sil_for_loss=bool(use_sil_for_loss), sil_thres=float(thres), far_depth_thres=far)
+                       use_sil_for_loss=bool(use_sil_for_loss), sil_thres=float(thres), far_depth_thres=far,
+                       ignore_outlier_depth_loss=bool(ignore_outlier_depth_loss),
+                       pixel_mask=(None if (vis_mask is None or dataset_name == 'replica')
+                                   else vis_mask.reshape(curr_data['depth'].shape[-2:])))
             loss, terms, radius = _FusedTrackingLoss.apply(r, params, cam_q, cam_t, curr_data['im'], curr_data['depth'], cfg, thres_fn)
             weighted_losses = {'depth': terms[2], 'im': terms[1], 'loss': loss}
             seen = radius > 0
