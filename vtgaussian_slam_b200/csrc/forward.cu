@@ -671,49 +671,34 @@ __device__ __noinline__ void sort_segment_radix_long(uint64_t* keys, uint64_t* s
 // walk only their own region's list: the culling is done once per (tile, splat) here instead of once per
 // (warp, splat) in each of the two blend kernels.
 // Arena: region r of a tile with list [rb, re) owns slots [8 rb + r (re - rb), 8 rb + (r + 1)(re - rb)).
-__device__ __forceinline__ void build_region_lists(const uint64_t* __restrict__ keys, int n, uint32_t rb, int tile,
-                                                   uint2* __restrict__ region_pairs,
-                                                   uint32_t* __restrict__ region_cnt, uint32_t* s_cnt /* [8][8] */, uint32_t* s_base /* [8] */) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid < 8) s_base[tid] = 0;
-    __syncthreads();                                   // also orders the sorted ids written by other threads
+__device__ __forceinline__ void build_region_lists(const uint64_t* keys, int n, uint32_t rb, int tile,
+                                                   uint2* __restrict__ region_pairs, uint32_t* __restrict__ region_cnt) {
+    // warp r compacts region r's entries of the whole (sorted) list: ballot + prefix popcount keep the list order,
+    // the running base lives in a register -- no shared counters, no block barriers between chunks
+    const int tid = threadIdx.x, lane = tid & 31, r = tid >> 5;
     const uint32_t lt = (1u << lane) - 1u;
-    for (int base = 0; base < n; base += 256) {
-        const int i = base + tid;
-        uint32_t rmask = 0, id = 0;
-        if (i < n) {
-            const uint32_t lo = (uint32_t)keys[i];          // (id << 8) | region mask, written by the scatter kernel
-            id = lo >> 8;
-            rmask = lo & 0xffu;
-        }
-        uint32_t bal[8];
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            bal[r] = __ballot_sync(VTGS_FULL_MASK, (rmask >> r) & 1u);
-            if (lane == 0) s_cnt[r * 8 + warp] = __popc(bal[r]);
-        }
-        __syncthreads();
-        uint32_t pre = 0, tot = 0;
-        if (lane < 8) {
-#pragma unroll
-            for (int w = 0; w < 8; ++w) {
-                const uint32_t c = s_cnt[lane * 8 + w];
-                if (w < warp) pre += c;
-                tot += c;
-            }
-            pre += s_base[lane];
-        }
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            const uint32_t p = __shfl_sync(VTGS_FULL_MASK, pre, r);
-            if ((rmask >> r) & 1u)
-                region_pairs[(size_t)8 * rb + (size_t)r * n + p + __popc(bal[r] & lt)] = make_uint2(id, (uint32_t)i + 1u);
-        }
-        __syncthreads();
-        if (warp == 0 && lane < 8) s_base[lane] += tot;
-        __syncthreads();
+    __syncthreads();                                   // the sorted keys written by other threads are visible
+    uint2* __restrict__ out = region_pairs + (size_t)8 * rb + (size_t)r * n;
+    uint32_t base = 0u;
+    int i0 = 0;
+    for (; i0 + 64 <= n; i0 += 64) {                   // two chunks per trip: independent loads
+        const uint32_t lo0 = (uint32_t)keys[i0 + lane], lo1 = (uint32_t)keys[i0 + 32 + lane];
+        const bool h0 = (lo0 >> r) & 1u, h1 = (lo1 >> r) & 1u;
+        const uint32_t b0 = __ballot_sync(VTGS_FULL_MASK, h0), b1 = __ballot_sync(VTGS_FULL_MASK, h1);
+        const uint32_t base1 = base + (uint32_t)__popc(b0);
+        if (h0) out[base + __popc(b0 & lt)] = make_uint2(lo0 >> 8, (uint32_t)(i0 + lane) + 1u);
+        if (h1) out[base1 + __popc(b1 & lt)] = make_uint2(lo1 >> 8, (uint32_t)(i0 + 32 + lane) + 1u);
+        base = base1 + (uint32_t)__popc(b1);
     }
-    if (tid < 8) region_cnt[(size_t)tile * 8 + tid] = s_base[tid];
+    for (; i0 < n; i0 += 32) {
+        const int i = i0 + lane;
+        const uint32_t lo = i < n ? (uint32_t)keys[i] : 0u;
+        const bool h = (lo >> r) & 1u;
+        const uint32_t bal = __ballot_sync(VTGS_FULL_MASK, h);
+        if (h) out[base + __popc(bal & lt)] = make_uint2(lo >> 8, (uint32_t)i + 1u);
+        base += (uint32_t)__popc(bal);
+    }
+    if (lane == 0) region_cnt[(size_t)tile * 8 + r] = base;
 }
 
 __global__ void __launch_bounds__(256, 4)
@@ -723,7 +708,6 @@ tile_sort_kernel(const __grid_constant__ CamConst cam, const uint32_t* __restric
     extern __shared__ __align__(16) uint64_t s_keys[];
     __shared__ uint32_t s_wh[8][256];
     __shared__ uint32_t s_cnt[64];
-    __shared__ uint32_t s_base[8];
     const int tile = tile0 + blockIdx.x;
     const uint32_t b = ranges[2 * tile], e = ranges[2 * tile + 1];
     const int n = (int)(e - b);
@@ -751,7 +735,7 @@ tile_sort_kernel(const __grid_constant__ CamConst cam, const uint32_t* __restric
         sort_segment_radix_long(pair_keys + b, reinterpret_cast<uint64_t*>(region_pairs + (size_t)8 * b), s_wh, s_cnt, n, threadIdx.x);
         for (int i = threadIdx.x; i < n; i += 256) point_list[b + i] = (uint32_t)pair_keys[b + i] >> 8;
     }
-    build_region_lists(sorted, n, b, tile, region_pairs, region_cnt, s_cnt, s_base);
+    build_region_lists(sorted, n, b, tile, region_pairs, region_cnt);
 }
 
 #ifdef VTGS_STATS
