@@ -781,7 +781,9 @@ blend_forward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __res
     int st_c2 = 0, st_c4 = 0;
 #endif
 
-    auto blend_one = [&](const float4 a, const float alpha, const int e) -> bool {
+    // zz: the splat's z^2 (fused planes), staged once per splat in the slot of GroupSmem.b that P2 does not read;
+    // bit: the splat's bit in the group (isolated from the walk mask, no variable shift)
+    auto blend_one = [&](const float4 a, const float alpha, const int e, const float zz, const uint32_t bit) -> bool {
         if (alpha < VTGS_ALPHA_MIN) return true;
         const float test_T = fmul(T, fsub(1.0f, alpha));
         if (test_T < VTGS_T_MIN) { done = true; return false; }
@@ -792,11 +794,11 @@ blend_forward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __res
         C3 = ffma(fmul(q2.w, alpha), T, C3);
         if (FUSED) {
             C4 = ffma(alpha, T, C4);                               // 1.0 * alpha * T
-            C5 = ffma(fmul(fmul(q2.w, q2.w), alpha), T, C5);
+            C5 = ffma(fmul(zz, alpha), T, C5);
         }
         T = test_T;
         last = __float_as_uint(a.z);
-        applied |= 1u << e;
+        applied |= bit;
         return true;
     };
 
@@ -815,7 +817,11 @@ blend_forward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __res
         ent_next2 = (k + 64) < n ? list[k + 64] : make_uint2(0u, 0u);
         load_splat(nxt, (k + 32) < n, geom, ent_next);
         __syncwarp();                                   // the previous group's P2 reads are complete
-        if (have) { G.a[lane] = cur.a; G.b[lane] = cur.b; G.c[lane] = cur.c; }
+        if (have) {
+            G.a[lane] = cur.a;
+            G.b[lane] = make_float4(cur.b.x, cur.b.y, cur.b.z, FUSED ? fmul(cur.c.w, cur.c.w) : 0.0f);     // .w: z^2 (pthr stays in registers for P1)
+            G.c[lane] = cur.c;
+        }
         __syncwarp();
         uint32_t emask;
         uint32_t m = p1_masks(have, cur.a, cur.b, x0f, y0f, lane, emask);       // P1: lane = splat
@@ -824,10 +830,12 @@ blend_forward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __res
         // colour updates are ordered.
         while (m) {
             const int ea = __ffs(m) - 1;
-            m &= m - 1;
+            const uint32_t bit_a = m & (0u - m);
+            m ^= bit_a;
             const bool two = m != 0;
             const int eb = two ? __ffs(m) - 1 : ea;
-            m &= m - 1;                                   // no-op when m == 0
+            const uint32_t bit_b = m & (0u - m);          // 0 when m == 0
+            m ^= bit_b;
             const float4 a0 = G.a[ea], a1 = G.b[ea];
             const float4 b0 = G.a[eb], b1 = G.b[eb];
             // power is in [pthr, 0] by P1 (same arithmetic)
@@ -835,8 +843,8 @@ blend_forward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __res
             const float pb = power_of(b1.x, b1.y, b1.z, fsub(b0.x, pxf), fsub(b0.y, pyf));
             const float alpha_a = fminf(VTGS_ALPHA_MAX, fmul(a0.w, vexpf(pa)));
             const float alpha_b = fminf(VTGS_ALPHA_MAX, fmul(b0.w, vexpf(pb)));
-            if (!blend_one(a0, alpha_a, ea)) break;
-            if (two && !blend_one(b0, alpha_b, eb)) break;
+            if (!blend_one(a0, alpha_a, ea, a1.w, bit_a)) break;
+            if (two && !blend_one(b0, alpha_b, eb, b1.w, bit_b)) break;
         }
         masks[g * 32 + lane] = applied;                 // which splats of this group each pixel blended (for K6')
 #ifdef VTGS_STATS
