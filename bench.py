@@ -454,9 +454,15 @@ def run_ours(args, wl):
     # ---- CPU baseline (rank 0, N=1 only): the oracle port on a bounded sample ----------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        t_cpu, _, _ = cpu_iteration(wl)
+        # bounded sample: one warm-up iteration, then whole iterations of the same workload for ~12 s (at most 16)
+        cpu_iteration(wl)
+        times = []
+        while sum(times) < 12.0 and len(times) < 16:
+            times.append(cpu_iteration(wl)[0])
+        t_cpu = sum(times) / len(times)
         cpu = {"value": 1.0 / t_cpu, "unit": UNIT, "cores": len(os.sched_getaffinity(0)), "kind": "port",
-               "sample": f"1 full iteration of the same workload on the host cores ({t_cpu:.2f} s)"}
+               "sample": f"{len(times)} full iterations of the same workload on the host cores after one warm-up "
+                         f"({sum(times):.1f} s, {t_cpu:.2f} s each)"}
 
     if rank == 0:
         working_set_mb = (N * (64 + 64 + 44) + R * 12 + P * (6 + 4 + 4 + 2) * 4) / 1e6
