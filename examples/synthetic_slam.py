@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--map-every", type=int, default=5)
     ap.add_argument("--step-m", type=float, default=0.01)
     ap.add_argument("--step-deg", type=float, default=0.3)
+    ap.add_argument("--track-sections", type=int, default=1, help="track against the newest k sections")
     ap.add_argument("--no-graph", action="store_true")
     a = ap.parse_args()
 
@@ -36,7 +37,7 @@ def main():
     W, H, K = synthetic.intrinsics(a.shape, a.width, a.height)
     poses = synthetic.trajectory(a.frames, a.step_m, a.step_deg)
     cfg = LoopConfig(track_iters=a.track_iters, map_iters=a.map_iters, baseframe_every=a.baseframe_every,
-                     map_every=a.map_every, use_graph=not a.no_graph)
+                     map_every=a.map_every, use_graph=not a.no_graph, track_sections=a.track_sections)
     slam = ViewTiedSLAM(W, H, K, cfg)
     t0 = time.perf_counter()
     gen = 0.0

@@ -4,7 +4,7 @@ import pytest
 import torch
 
 from vtgaussian_slam_b200 import synthetic
-from vtgaussian_slam_b200.slam_loop import LoopConfig, ViewTiedSLAM, ate_rmse, section_from_frame
+from vtgaussian_slam_b200.slam_loop import LoopConfig, SectionStore, ViewTiedSLAM, ate_rmse, section_from_frame
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -35,3 +35,39 @@ def test_loop_tracks_a_synthetic_sequence(use_graph):
     still = ate_rmse(np.tile(np.eye(4), (n, 1, 1)), poses)
     assert len(slam.sections) == 3 and slam.stats["track_iters"] == (n - 1) * 61
     assert err < 0.2 * still and err < 0.01, (err, still)
+
+
+def test_section_store_views_alias_the_arena_and_survive_growth():
+    st = SectionStore(10, DEV)
+    mk = lambda n, v: {k: torch.full((n, c), float(v), device=DEV) for k, c in SectionStore.KEYS.items()}
+    a = st.append(mk(6, 1.0))
+    b = st.append(mk(7, 2.0))                      # 13 > 10: the arena grows, rows are preserved
+    c = st.append(mk(3, 3.0))
+    assert (a, b, c) == (0, 1, 2) and len(st) == 3 and st.num_gaussians == 16 and st.capacity >= 16
+    for k, v in st.rows(0).items():
+        assert v.shape[0] == 6 and float(v.min()) == 1.0 and float(v.max()) == 1.0 and v.is_contiguous()
+    both = st.rows(1, 2)
+    assert both["means3D"].shape == (10, 3) and float(both["means3D"][:7].max()) == 2.0 and float(both["means3D"][7:].min()) == 3.0
+    st.rows(2)["rgb_colors"].fill_(9.0)            # a view writes through to the arena
+    assert float(st.rows(1, 2)["rgb_colors"][7:].min()) == 9.0
+    assert st.rows(1)["unnorm_rotations"].data_ptr() % 16 == 0
+
+
+def test_loop_tracks_against_two_consecutive_sections():
+    n = 11
+    W, H, K = synthetic.intrinsics("tum_fr1", 320, 240)
+    poses = synthetic.trajectory(n, step_m=0.01, step_deg=0.3)
+    cfg = LoopConfig(track_iters=50, map_iters=8, baseframe_every=4, map_every=2, track_sections=2)
+    slam = ViewTiedSLAM(W, H, K, cfg, device=DEV)
+    for i in range(n):
+        slam.process(synthetic.make_frame("tum_fr1", 320, 240, seed=i, c2w=poses[i]))
+    assert len(slam.store) == 3 and slam.tracker.params["means3D"].shape[0] == 2 * 320 * 240
+    # the tracker's parameters ARE the arena rows the mapper optimises (no copies)
+    assert slam.tracker.params["rgb_colors"].data_ptr() == slam.store.rows(1, 2)["rgb_colors"].data_ptr()
+    assert slam.mapper.params["rgb_colors"].data_ptr() == slam.store.rows(2)["rgb_colors"].data_ptr()
+    est = np.stack([np.linalg.inv(m) for m in slam.w2c])
+    err = ate_rmse(est, poses)
+    still = ate_rmse(np.tile(np.eye(4), (n, 1, 1)), poses)
+    # two overlapping sections are displaced against each other by the pose error of the newer one's base frame, so the
+    # optimum is a compromise: tracking still follows the camera, but less tightly than against the newest section alone
+    assert err < 0.6 * still, (err, still)

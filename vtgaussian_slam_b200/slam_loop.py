@@ -37,6 +37,8 @@ class LoopConfig:
     baseframe_every: int = 10             # fr1_config.py:36 30
     map_every: int = 5
     keyframes_per_map: int = 4
+    track_sections: int = 1               # track against the newest k sections (consecutive rows of the SectionStore);
+                                          # k > 1 renders overlapping sections together and tracks less tightly
     lr_rot: float = 4e-4                  # room0.py:78-86
     lr_trans: float = 2e-3
     track_w_im: float = 0.5
@@ -108,6 +110,54 @@ def section_from_frame(rgb, depth, K, c2w, device, factor=1.005):
                 logit_opacities=torch.zeros((n, 1), **f32), log_scales=torch.log(scale[keep])[:, None].contiguous())
 
 
+class SectionStore:
+    """Device arena of view-tied sections: one SoA buffer per parameter, every section a contiguous row range.
+    Consecutive sections are therefore rendered, tracked against and optimised IN PLACE through row-slice views --
+    the reference concatenates the selected sections' tensors on every iteration and splits them back afterwards
+    (src/vtgaussian_slam.py:2734, :2832-2839)."""
+
+    KEYS = dict(means3D=3, rgb_colors=3, unnorm_rotations=4, logit_opacities=1, log_scales=1)
+
+    def __init__(self, capacity, device="cuda:0"):
+        self.device = torch.device(device)
+        self.capacity = int(capacity)
+        self.buf = {k: torch.empty((self.capacity, c), dtype=torch.float32, device=self.device) for k, c in self.KEYS.items()}
+        self.offsets = [0]                 # section i owns rows [offsets[i], offsets[i + 1])
+
+    def __len__(self):
+        return len(self.offsets) - 1
+
+    @property
+    def num_gaussians(self):
+        return self.offsets[-1]
+
+    def _grow(self, need):
+        cap = max(need, 2 * self.capacity)
+        for k, c in self.KEYS.items():
+            nb = torch.empty((cap, c), dtype=torch.float32, device=self.device)
+            nb[:self.offsets[-1]] = self.buf[k][:self.offsets[-1]]
+            self.buf[k] = nb
+        self.capacity = cap
+
+    def append(self, params):
+        """Copy a section's parameters to the end of the arena -> its index.  (Views handed out before a growth of
+        the arena keep pointing at the old storage: take them again after appending.)"""
+        n = int(params["means3D"].shape[0])
+        a = self.offsets[-1]
+        if a + n > self.capacity:
+            self._grow(a + n)
+        for k in self.KEYS:
+            self.buf[k][a:a + n] = params[k].to(self.device, torch.float32).reshape(n, self.KEYS[k])
+        self.offsets.append(a + n)
+        return len(self) - 1
+
+    def rows(self, first, last=None):
+        """Contiguous row-slice views (no copy) of sections first..last inclusive."""
+        last = first if last is None else last
+        a, b = self.offsets[first], self.offsets[last + 1]
+        return {k: v[a:b] for k, v in self.buf.items()}
+
+
 def ate_rmse(est_c2w, gt_c2w):
     """Translation RMSE between two trajectories that share their first pose (no alignment: both are relative to frame 0)."""
     e = np.asarray(est_c2w)[:, :3, 3] - np.asarray(gt_c2w)[:, :3, 3]
@@ -128,7 +178,8 @@ class ViewTiedSLAM:
             bg=t(s["bg"]), scale_modifier=s["scale_modifier"], viewmatrix=t(s["viewmatrix"]), projmatrix=t(s["projmatrix"]),
             sh_degree=0, campos=t(s["campos"]), prefiltered=False)
         self.w2c = []                      # estimated poses, one 4x4 per frame
-        self.sections = []                 # dict(params, base, keyframes=[(idx, rgb, depth)])
+        self.sections = []                 # dict(params (arena views), index, base, keyframes=[(idx, rgb, depth)])
+        self.store = None                  # SectionStore, created with the first section
         self.tracker = None
         self.mapper = None
         self.stats = dict(track_iters=0, map_iters=0, track_s=0.0, map_s=0.0, track_loss=[])
@@ -136,14 +187,21 @@ class ViewTiedSLAM:
     # -- sections -------------------------------------------------------------------------------------------
     def _new_section(self, idx, rgb, depth):
         c2w = np.linalg.inv(self.w2c[idx])
-        params = section_from_frame(rgb, depth, self.K, c2w, self.device)
-        sec = dict(params=params, base=idx, keyframes=[])
+        fresh = section_from_frame(rgb, depth, self.K, c2w, self.device)
+        if self.store is None:
+            self.store = SectionStore(4 * fresh["means3D"].shape[0], self.device)
+        k = self.store.append(fresh)
+        sec = dict(params=self.store.rows(k), index=k, base=idx, keyframes=[])
         self.sections.append(sec)
+        for s_ in self.sections:                         # the arena may have moved: refresh every view
+            s_["params"] = self.store.rows(s_["index"])
         c = self.cfg
-        # the solvers alias `params` (contiguous float32 CUDA tensors are used in place): mapping updates are
-        # seen by the tracker without a copy
-        self.mapper = MappingSolver(self.settings, params, device=self.device, lrs=c.map_lrs)
-        self.tracker = TrackingSolver(self.settings, self.mapper.params, device=self.device, lr_rot=c.lr_rot,
+        # the solvers alias the arena rows (contiguous float32 CUDA row slices are used in place): mapping updates the
+        # newest section where it lives, and the tracker -- over the newest `track_sections` consecutive sections --
+        # sees them without a copy
+        self.mapper = MappingSolver(self.settings, sec["params"], device=self.device, lrs=c.map_lrs)
+        first = max(0, k - max(1, c.track_sections) + 1)
+        self.tracker = TrackingSolver(self.settings, self.store.rows(first, k), device=self.device, lr_rot=c.lr_rot,
                                       lr_trans=c.lr_trans, w_im=c.track_w_im, w_depth=c.track_w_depth,
                                       sil_thres=c.sil_thres, use_graph=c.use_graph)
         return sec
