@@ -77,6 +77,22 @@ def test_random_scene_parity(seed, aniso, n, W, H, bg):
     assert bit_exact, "forward planes are expected to be bit-identical to the oracle"
 
 
+@pytest.mark.parametrize("seed", list(range(10, 22)))
+def test_seed_sweep_small_scenes(seed):
+    """A dozen more random scenes of varying shape (odd image sizes, mixed iso/anisotropic, scales from sub-pixel to a
+    third of the image, opaque to nearly transparent): the forward must stay bit-identical, gradients within 1e-3."""
+    rng = np.random.default_rng(seed)
+    W, H = int(rng.integers(17, 150)), int(rng.integers(17, 110))
+    n = int(rng.integers(50, 4000))
+    lo = float(rng.choice([0.2, 0.5, 2.0]))
+    hi = lo * float(rng.choice([2.0, 8.0, 30.0]))
+    K, sc = synthetic.random_scene(n, W, H, seed=seed, anisotropic=bool(seed % 2), scale_px=(lo, min(hi, W / 3)),
+                                   opacity_range=(0.01, 1.0) if seed % 3 else (0.5, 1.0))
+    bg = (0, 0, 0) if seed % 4 else (0.3, 0.1, 0.7)
+    _, _, bit_exact = _run_case(W, H, sc, K, bg=bg, seed=seed)
+    assert bit_exact
+
+
 def test_long_tile_lists_take_the_global_sort_path():
     # one 16x16 tile with > 4096 entries: the per-tile sort leaves shared memory
     W, H = 16, 16
