@@ -505,11 +505,18 @@ __device__ __forceinline__ void sort_segment_radix(uint64_t* __restrict__ s_keys
     constexpr int TIE_RUN_MAX = 48;
     bool moved = false, too_long = false;
     int newpos[E];
+    // the list is depth-sorted: equal depths TIE_RUN_MAX apart mean a longer run -- one load decides it for everyone
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const int i = cbase + 32 * e;
+        if (i < n && i >= TIE_RUN_MAX) too_long |= (uint32_t)(s_keys[i - TIE_RUN_MAX] >> 32) == (uint32_t)(v[e] >> 32);
+    }
+    const bool any_long = __syncthreads_or(too_long) != 0;
 #pragma unroll
     for (int e = 0; e < E; ++e) {
         const int i = cbase + 32 * e;
         newpos[e] = i;
-        if (i < n) {
+        if (i < n && !any_long) {
             const uint32_t hi = (uint32_t)(v[e] >> 32), lo = (uint32_t)v[e];
             int shiftpos = 0, steps = 0;
             for (int j = i - 1; j >= 0; --j) {
@@ -528,12 +535,22 @@ __device__ __forceinline__ void sort_segment_radix(uint64_t* __restrict__ s_keys
             moved |= shiftpos != 0;
         }
     }
-    const bool any_long = __syncthreads_or(too_long) != 0;        // (a barrier: every read of s_keys above is done)
-    const bool any_moved = __syncthreads_or(moved) != 0;
+    const bool any_moved = __syncthreads_or(moved) != 0;          // (a barrier: every read of s_keys above is done)
     if (any_long) {
-        int npad = 2;
+        // long runs (e.g. a fronto-parallel wall seen from the pose its quantised depths were measured at): full
+        // 64-bit sort of the tile with the register / shuffle bitonic network (3x cheaper than the shared-memory one)
+        constexpr int E2 = E <= 2 ? 2 : (E <= 4 ? 4 : 8);
+        uint64_t w[E2];
+#pragma unroll
+        for (int e = 0; e < E2; ++e) w[e] = tid * E2 + e < n ? s_keys[tid * E2 + e] : ~0ull;
+        int npad = 2 * E2;
         while (npad < n) npad <<= 1;
-        bitonic_network(s_keys, n, npad);
+        bitonic_regs<E2>(w, s_keys, tid, npad);          // s_keys doubles as the exchange buffer (barriers inside)
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < E2; ++e)
+            if (tid * E2 + e < n) s_keys[tid * E2 + e] = w[e];
+        __syncthreads();
     } else if (any_moved) {
 #pragma unroll
         for (int e = 0; e < E; ++e)
@@ -634,7 +651,10 @@ __device__ __noinline__ void sort_segment_radix_long(uint64_t* keys, uint64_t* s
     // equal-depth runs: order by id (see sort_segment_radix); the repaired list is assembled in `scratch`
     constexpr int TIE_RUN_MAX = 48;
     bool moved = false, too_long = false;
-    for (int i = tid; i < n; i += 256) {
+    for (int i = tid + TIE_RUN_MAX; i < n; i += 256)
+        too_long |= (uint32_t)(keys[i - TIE_RUN_MAX] >> 32) == (uint32_t)(keys[i] >> 32);
+    const bool any_long = __syncthreads_or(too_long) != 0;
+    for (int i = tid; i < n && !any_long; i += 256) {
         const uint64_t k = keys[i];
         const uint32_t hi = (uint32_t)(k >> 32), lo = (uint32_t)k;
         int shiftpos = 0, steps = 0;
@@ -653,7 +673,6 @@ __device__ __noinline__ void sort_segment_radix_long(uint64_t* keys, uint64_t* s
         scratch[i + shiftpos] = k;
         moved |= shiftpos != 0;
     }
-    const bool any_long = __syncthreads_or(too_long) != 0;
     const bool any_moved = __syncthreads_or(moved) != 0;
     if (any_long) {
         int npad = 2;

@@ -502,7 +502,7 @@ __device__ __forceinline__ double ipow(double b, int t) {
 
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,
-            float lr, float b1, float b2, float eps, int step, const int32_t* __restrict__ step_dev) {
+            float lr, float b1, float b2, float eps, int step, const int32_t* __restrict__ step_dev, int vec4) {
     __shared__ float s_c[2];
     if (threadIdx.x == 0) {
         const int t = step_dev ? *step_dev : step;
@@ -512,14 +512,27 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
         s_c[1] = (float)sqrt(bc2);
     }
     __syncthreads();
+    const float step_size = s_c[0], bc2s = s_c[1];
+    auto upd = [&](float& pi, const float gi, float& mi_, float& vi_) {
+        const float mi = mi_ + (1.0f - b1) * (gi - mi_);            // exp_avg.lerp_(grad, 1 - beta1)
+        const float vi = b2 * vi_ + (1.0f - b2) * gi * gi;          // exp_avg_sq.mul_(b2).addcmul_(g, g, 1 - b2)
+        mi_ = mi; vi_ = vi;
+        const float denom = sqrtf(vi) / bc2s + eps;
+        pi = pi - step_size * (mi / denom);
+    };
     const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (vec4) {                                                      // four elements per thread, 16-byte accesses
+        if (4 * i >= n) return;
+        float4 p4 = reinterpret_cast<float4*>(p)[i], m4 = reinterpret_cast<float4*>(m)[i], v4 = reinterpret_cast<float4*>(v)[i];
+        const float4 g4 = reinterpret_cast<const float4*>(g)[i];
+        upd(p4.x, g4.x, m4.x, v4.x); upd(p4.y, g4.y, m4.y, v4.y); upd(p4.z, g4.z, m4.z, v4.z); upd(p4.w, g4.w, m4.w, v4.w);
+        reinterpret_cast<float4*>(p)[i] = p4; reinterpret_cast<float4*>(m)[i] = m4; reinterpret_cast<float4*>(v)[i] = v4;
+        return;
+    }
     if (i >= n) return;
-    const float gi = g[i];
-    const float mi = m[i] + (1.0f - b1) * (gi - m[i]);          // exp_avg.lerp_(grad, 1 - beta1)
-    const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;         // exp_avg_sq.mul_(b2).addcmul_(g, g, 1 - b2)
-    m[i] = mi; v[i] = vi;
-    const float denom = sqrtf(vi) / s_c[1] + eps;
-    p[i] = p[i] - s_c[0] * (mi / denom);
+    float pi = p[i], mi = m[i], vi = v[i];
+    upd(pi, g[i], mi, vi);
+    p[i] = pi; m[i] = mi; v[i] = vi;
 }
 
 // ---- tracking pose update: best-candidate bookkeeping + Adam on the 7 pose numbers, one launch ----
@@ -564,7 +577,9 @@ int launch_tracking_update(float* cam_q, float* cam_t, const float* msg, float* 
 int launch_adam(float* param, const float* grad, float* m, float* v, int64_t n, float lr, float b1,
                 float b2, float eps, int step, const int32_t* step_dev, cudaStream_t stream) {
     if (n <= 0) return VTGS_OK;
-    { VTGS_PROF("adam_kernel", stream); adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(param, grad, m, v, n, lr, b1, b2, eps, step, step_dev); }
+    const bool vec4 = (n % 4 == 0) && (((uintptr_t)param | (uintptr_t)grad | (uintptr_t)m | (uintptr_t)v) & 15) == 0;
+    const int64_t threads = vec4 ? n / 4 : n;
+    { VTGS_PROF("adam_kernel", stream); adam_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(param, grad, m, v, n, lr, b1, b2, eps, step, step_dev, vec4 ? 1 : 0); }
     VTGS_LAUNCH_CHECK();
     return VTGS_OK;
 }
