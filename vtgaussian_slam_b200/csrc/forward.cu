@@ -187,15 +187,18 @@ preprocess_kernel(const __grid_constant__ CamConst cam, int64_t N, FrontEnd fe,
         // section) touch the same tiles, so one atomic per distinct tile per warp step instead of one per lane
         {
             // lanes with the SAME rect (one match per Gaussian, not per walk step) elect a leader that adds the group's
-            // size to every tile of the rect; culled lanes get distinct signatures and an empty rect
+            // size to every tile of the rect
             const bool have = (w_maxx > w_minx) && (w_maxy > w_miny);
-            const uint32_t sig_lo = have ? ((uint32_t)w_minx | ((uint32_t)w_miny << 16)) : 0xffff0000u | (uint32_t)(tid & 31);
-            const uint32_t sig_hi = have ? ((uint32_t)w_maxx | ((uint32_t)w_maxy << 16)) : 0u;
-            const uint32_t peers = __match_any_sync(VTGS_FULL_MASK, ((unsigned long long)sig_hi << 32) | sig_lo);
-            if (have && (peers & ((1u << (tid & 31)) - 1u)) == 0u) {
-                const uint32_t cnt = (uint32_t)__popc(peers);
-                for (int ty = w_miny; ty < w_maxy; ++ty)
-                    for (int tx = w_minx; tx < w_maxx; ++tx) atomicAdd(&tile_counts[ty * cam.gx + tx], cnt);
+            if (__any_sync(VTGS_FULL_MASK, have)) {          // (a warp of culled / out-of-band splats skips the match)
+                // lanes without a rect share one signature (they never act on it): the match costs per DISTINCT value
+                const uint32_t sig_lo = have ? ((uint32_t)w_minx | ((uint32_t)w_miny << 16)) : 0xffffffffu;
+                const uint32_t sig_hi = have ? ((uint32_t)w_maxx | ((uint32_t)w_maxy << 16)) : 0xffffffffu;
+                const uint32_t peers = __match_any_sync(VTGS_FULL_MASK, ((unsigned long long)sig_hi << 32) | sig_lo);
+                if (have && (peers & ((1u << (tid & 31)) - 1u)) == 0u) {
+                    const uint32_t cnt = (uint32_t)__popc(peers);
+                    for (int ty = w_miny; ty < w_maxy; ++ty)
+                        for (int tx = w_minx; tx < w_maxx; ++tx) atomicAdd(&tile_counts[ty * cam.gx + tx], cnt);
+                }
             }
         }
     }
