@@ -54,18 +54,24 @@ struct K1Item {
     float4 q;
 };
 
+__device__ __forceinline__ void k1_load_rest(K1Item& it, int64_t i, bool rot_aligned, const float* __restrict__ rotations,
+                                             const float* __restrict__ opacities, const float* __restrict__ colors) {
+    it.c0 = colors[3 * i]; it.c1 = colors[3 * i + 1]; it.c2 = colors[3 * i + 2];
+    it.op = opacities[i];
+    it.q = rot_aligned ? reinterpret_cast<const float4*>(rotations)[i]
+                       : make_float4(rotations[4 * i], rotations[4 * i + 1], rotations[4 * i + 2], rotations[4 * i + 3]);
+}
+
 template <bool FUSED>
 __device__ __forceinline__ void k1_load(K1Item& it, int64_t i, int ls_dim, bool rot_aligned,
                                         const float* __restrict__ means3D, const float* __restrict__ scales,
                                         const float* __restrict__ rotations, const float* __restrict__ opacities,
-                                        const float* __restrict__ colors) {
+                                        const float* __restrict__ colors, bool position_only = false) {
     it.x = means3D[3 * i]; it.y = means3D[3 * i + 1]; it.z = means3D[3 * i + 2];
-    it.c0 = colors[3 * i]; it.c1 = colors[3 * i + 1]; it.c2 = colors[3 * i + 2];
     if (FUSED && ls_dim == 1) { it.s0 = scales[i]; it.s1 = it.s0; it.s2 = it.s0; }
     else { it.s0 = scales[3 * i]; it.s1 = scales[3 * i + 1]; it.s2 = scales[3 * i + 2]; }
-    it.op = opacities[i];
-    it.q = rot_aligned ? reinterpret_cast<const float4*>(rotations)[i]
-                       : make_float4(rotations[4 * i], rotations[4 * i + 1], rotations[4 * i + 2], rotations[4 * i + 3]);
+    if (position_only) return;          // tile-band mode: the other 32 bytes are fetched only for splats that reach the band
+    k1_load_rest(it, i, rot_aligned, rotations, opacities, colors);
 }
 
 template <bool FUSED>
@@ -98,13 +104,14 @@ preprocess_kernel(const __grid_constant__ CamConst cam, int64_t N, FrontEnd fe,
     }
     int64_t i = (int64_t)blockIdx.x * 256 + tid;
     K1Item nxt;
-    if (i < N) k1_load<FUSED>(nxt, i, fe.log_scales_dim, rot_aligned, means3D, scales, rotations, opacities, colors);
+    const bool lite = FUSED && band_active && (cam.row1 - cam.row0) * 5 < cam.gy * 2;      // narrow bands: most splats are rejected
+    if (i < N) k1_load<FUSED>(nxt, i, fe.log_scales_dim, rot_aligned, means3D, scales, rotations, opacities, colors, lite);
     // whole warps loop together (the tile walk below is warp-collective)
     for (int64_t wbase = i - (tid & 31); wbase < N; wbase += stride, i += stride) {
         int w_minx = 0, w_maxx = 0, w_miny = 0, w_maxy = 0;       // tile rect to count (empty when culled / out of range)
         if (i < N) {
-            const K1Item it = nxt;
-            if (i + stride < N) k1_load<FUSED>(nxt, i + stride, fe.log_scales_dim, rot_aligned, means3D, scales, rotations, opacities, colors);
+            K1Item it = nxt;
+            if (i + stride < N) k1_load<FUSED>(nxt, i + stride, fe.log_scales_dim, rot_aligned, means3D, scales, rotations, opacities, colors, lite);
             float x = it.x, y = it.y, z = it.z;
             float sx, sy, sz, qr = it.q.x, qx = it.q.y, qy = it.q.z, qz = it.q.w, op, c3;
             if (FUSED) {
@@ -142,6 +149,10 @@ preprocess_kernel(const __grid_constant__ CamConst cam, int64_t N, FrontEnd fe,
                 radii[i] = 0;
                 tiles_touched[i] = 0;
             } else {
+            if (lite) {                                   // (band mode) now that the splat is known to matter
+                k1_load_rest(it, i, rot_aligned, rotations, opacities, colors);
+                qr = it.q.x; qx = it.q.y; qy = it.q.z; qz = it.q.w;
+            }
             if (FUSED) {
                 const float nrm = __fsqrt_rn(ffma(qz, qz, ffma(qy, qy, ffma(qx, qx, fmul(qr, qr)))));
                 const float d = fmaxf(nrm, 1e-12f);
