@@ -85,8 +85,10 @@ __device__ __forceinline__ float ffma(float a, float b, float c) { return __fmaf
 
 // exp(x): Cody-Waite reduction + Cephes degree-5 polynomial, scaling by exponent add.
 // Bit-identical to vexpf() of the CPU oracle.
+// CLAMP = false: the caller guarantees x in [-87, 88] (the clamp is then the identity; same bits).
+template <bool CLAMP = true>
 __device__ __forceinline__ float vexpf(float x) {
-    x = fminf(fmaxf(x, -87.0f), 88.0f);
+    if (CLAMP) x = fminf(fmaxf(x, -87.0f), 88.0f);
     const float t = ffma(x, 1.44269504088896341f, 12582912.0f);
     const float n = fsub(t, 12582912.0f);
     float r = ffma(n, -0.693145751953125f, x);
@@ -100,8 +102,9 @@ __device__ __forceinline__ float vexpf(float x) {
     const float r2 = fmul(r, r);
     float e = ffma(p, r2, r);
     e = fadd(e, 1.0f);
-    const int ni = __float2int_rz(n);
-    return __uint_as_float(__float_as_uint(e) + ((uint32_t)ni << 23));
+    // n (|n| <= 128) sits in the low mantissa bits of t = 1.5 * 2^23 + n, whose other low 22 bits are zero:
+    // bits(t) << 23 == (int)n << 23 (mod 2^32) -- the exponent add without a float -> int conversion
+    return __uint_as_float(__float_as_uint(e) + (__float_as_uint(t) << 23));
 }
 
 __device__ __forceinline__ float xform_row(const float* __restrict__ m, int r, float x, float y, float z) {

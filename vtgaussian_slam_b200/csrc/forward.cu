@@ -874,8 +874,9 @@ blend_forward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __res
             // power is in [pthr, 0] by P1 (same arithmetic)
             const float pa = power_of(a1.x, a1.y, a1.z, fsub(a0.x, pxf), fsub(a0.y, pyf));
             const float pb = power_of(b1.x, b1.y, b1.z, fsub(b0.x, pxf), fsub(b0.y, pyf));
-            const float alpha_a = fminf(VTGS_ALPHA_MAX, fmul(a0.w, vexpf(pa)));
-            const float alpha_b = fminf(VTGS_ALPHA_MAX, fmul(b0.w, vexpf(pb)));
+            // fused mode: opacity = sigmoid(.) < 1, so pthr >= log(1/255) - 1e-3 and power in [-5.6, 0]: no clamp needed
+            const float alpha_a = fminf(VTGS_ALPHA_MAX, fmul(a0.w, vexpf<!FUSED>(pa)));
+            const float alpha_b = fminf(VTGS_ALPHA_MAX, fmul(b0.w, vexpf<!FUSED>(pb)));
             if (!blend_one(a0, alpha_a, ea, a1.w, bit_a)) break;
             if (two && !blend_one(b0, alpha_b, eb, b1.w, bit_b)) break;
         }
