@@ -81,7 +81,7 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[16], int lane)
 //   P4 lane = splat : three red.global.add.v4.f32 per (region, splat).
 // Groups in which no pixel of the region blended anything are skipped before their records are fetched.
 // Upstream: 9-10 global float atomics per contributing (pixel, splat) pair.
-constexpr int BWD_WARPS = 4;          // warps (regions) per block: a tile is covered by 8 / BWD_WARPS blocks
+constexpr int BWD_WARPS = 2;          // warps (regions) per block: a tile is covered by 8 / BWD_WARPS blocks
 template <bool FUSED>
 __global__ void __launch_bounds__(32 * BWD_WARPS, 20 / BWD_WARPS)
 blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __restrict__ ranges,

@@ -74,7 +74,8 @@ __device__ __forceinline__ void k1_load(K1Item& it, int64_t i, int ls_dim, bool 
     k1_load_rest(it, i, rot_aligned, rotations, opacities, colors);
 }
 
-template <bool FUSED>
+// LITE (fused, narrow tile bands: most splats are rejected): only position and scale are fetched before the band test.
+template <bool FUSED, bool LITE = false>
 __global__ void __launch_bounds__(256, 3)
 preprocess_kernel(const __grid_constant__ CamConst cam, int64_t N, FrontEnd fe,
                   const float* __restrict__ means3D, const float* __restrict__ scales,
@@ -104,7 +105,7 @@ preprocess_kernel(const __grid_constant__ CamConst cam, int64_t N, FrontEnd fe,
     }
     int64_t i = (int64_t)blockIdx.x * 256 + tid;
     K1Item nxt;
-    const bool lite = FUSED && band_active && (cam.row1 - cam.row0) * 5 < cam.gy * 2;      // narrow bands: most splats are rejected
+    constexpr bool lite = LITE;
     if (i < N) k1_load<FUSED>(nxt, i, fe.log_scales_dim, rot_aligned, means3D, scales, rotations, opacities, colors, lite);
     // whole warps loop together (the tile walk below is warp-collective)
     for (int64_t wbase = i - (tid & 31); wbase < N; wbase += stride, i += stride) {
@@ -780,20 +781,23 @@ __device__ unsigned long long vtgs_stats[8];
 // the 64-byte records, lane-transposed blending (blend_common.cuh): P1 lane = splat from registers,
 // P2 lane = pixel from the group staged in shared memory.
 // Planes: API mode 3 colours (+ depth plane), fused mode r,g,b,z,sil,z^2.
+constexpr int FWD_WARPS = 4;          // warps (regions) per block: a tile is covered by 8 / FWD_WARPS blocks
 template <bool FUSED>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(32 * FWD_WARPS, 24 / FWD_WARPS)
 blend_forward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __restrict__ ranges,
                      const uint2* __restrict__ region_pairs, const uint32_t* __restrict__ region_cnt,
                      uint32_t* __restrict__ region_masks, uint32_t* __restrict__ region_done,
                      const GeomRecord* __restrict__ geom,
                      float* __restrict__ out_color, float* __restrict__ out_depth,
                      float* __restrict__ final_T, uint32_t* __restrict__ n_contrib) {
-    __shared__ GroupSmem Gs[8];
+    __shared__ GroupSmem Gs[FWD_WARPS];
 
-    const int tile = cam.row0 * cam.gx + blockIdx.x;
+    constexpr int BPT = 8 / FWD_WARPS;                                  // blocks per tile
+    const int tile = cam.row0 * cam.gx + blockIdx.x / BPT;
     const int tile_x = tile % cam.gx, tile_y = tile / cam.gx;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    GroupSmem& G = Gs[warp];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = (blockIdx.x % BPT) * FWD_WARPS + (tid >> 5);       // region index inside the tile
+    GroupSmem& G = Gs[tid >> 5];
     const int rx0 = tile_x * 16 + (warp % REGIONS_X) * REGION_W, ry0 = tile_y * 16 + (warp / REGIONS_X) * REGION_H;
     const int pix_x = rx0 + (lane % REGION_W), pix_y = ry0 + (lane / REGION_W);
     const bool inside = pix_x < cam.W && pix_y < cam.H;
@@ -953,7 +957,11 @@ int launch_forward(const VtgsCamera* camera, int64_t N, bool fused, const FrontE
     const int blocks = (int)((N + 255) / 256);
     const int k1_blocks = blocks < 148 * 6 ? blocks : 148 * 6;          // persistent: 3 resident blocks per SM x 2 waves
     if (N > 0) {
-        if (fused)
+        const bool narrow_band = (cam.row1 - cam.row0) * 5 < cam.gy * 2;
+        if (fused && narrow_band)
+            { VTGS_PROF("preprocess_kernel", stream); preprocess_kernel<true, true><<<k1_blocks, 256, 0, stream>>>(cam, N, fe, means3D, scales, rotations, opacities, colors,
+                                                                 geom, radii, buf->tiles_touched, buf->tile_counts); }
+        else if (fused)
             { VTGS_PROF("preprocess_kernel", stream); preprocess_kernel<true><<<k1_blocks, 256, 0, stream>>>(cam, N, fe, means3D, scales, rotations, opacities, colors,
                                                                  geom, radii, buf->tiles_touched, buf->tile_counts); }
         else { VTGS_PROF("preprocess_kernel", stream); preprocess_kernel<false><<<k1_blocks, 256, 0, stream>>>(cam, N, fe, means3D, scales, rotations, opacities, colors,
@@ -980,8 +988,8 @@ int launch_forward(const VtgsCamera* camera, int64_t N, bool fused, const FrontE
     if (N <= 0) VTGS_CUDA_CHECK(cudaMemsetAsync(buf->region_cnt, 0, sizeof(uint32_t) * 8 * num_tiles, stream));
     if (band_tiles > 0) {
         if (fused)
-            { VTGS_PROF("blend_forward_kernel", stream); blend_forward_kernel<true><<<band_tiles, 256, 0, stream>>>(cam, buf->tile_ranges, reinterpret_cast<const uint2*>(buf->region_pairs), buf->region_cnt, buf->region_masks, buf->region_done, geom, out_color, out_depth, buf->final_T, buf->n_contrib); }
-        else { VTGS_PROF("blend_forward_kernel", stream); blend_forward_kernel<false><<<band_tiles, 256, 0, stream>>>(cam, buf->tile_ranges, reinterpret_cast<const uint2*>(buf->region_pairs), buf->region_cnt, buf->region_masks, buf->region_done, geom, out_color, out_depth, buf->final_T, buf->n_contrib); }
+            { VTGS_PROF("blend_forward_kernel", stream); blend_forward_kernel<true><<<band_tiles * (8 / FWD_WARPS), 32 * FWD_WARPS, 0, stream>>>(cam, buf->tile_ranges, reinterpret_cast<const uint2*>(buf->region_pairs), buf->region_cnt, buf->region_masks, buf->region_done, geom, out_color, out_depth, buf->final_T, buf->n_contrib); }
+        else { VTGS_PROF("blend_forward_kernel", stream); blend_forward_kernel<false><<<band_tiles * (8 / FWD_WARPS), 32 * FWD_WARPS, 0, stream>>>(cam, buf->tile_ranges, reinterpret_cast<const uint2*>(buf->region_pairs), buf->region_cnt, buf->region_masks, buf->region_done, geom, out_color, out_depth, buf->final_T, buf->n_contrib); }
         VTGS_LAUNCH_CHECK();
     }
 #ifdef VTGS_STATS
