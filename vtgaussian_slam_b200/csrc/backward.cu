@@ -126,6 +126,7 @@ blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __re
     A.dpix[lane] = make_float4(dpix[0], dpix[1], dpix[2], dpix[3]);
     A.pxy[lane] = make_float2(pxf, pyf);
     const float bg_dot = cam.bg[0] * dpix[0] + cam.bg[1] * dpix[1] + cam.bg[2] * dpix[2];
+    const bool has_bg = cam.bg[0] != 0.0f || cam.bg[1] != 0.0f || cam.bg[2] != 0.0f;
     const float half_w = 0.5f * cam.W, half_h = 0.5f * cam.H;
 
     float T = T_final;
@@ -183,7 +184,7 @@ blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __re
             }
             dL_dalpha *= T;
             last_alpha = alpha;
-            dL_dalpha -= T_final * inv * bg_dot;
+            if (has_bg) dL_dalpha -= T_final * inv * bg_dot;      // (warp-uniform: the reference renders on black)
             return make_float2(alpha * T, Gv * dL_dalpha);
         };
         while (m) {
