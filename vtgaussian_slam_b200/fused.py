@@ -188,7 +188,7 @@ class TrackingSolver:
     One iteration = 9 kernel launches, no host synchronisation; with use_graph the iteration is
     captured once and replayed."""
 
-    LAUNCHES_PER_ITER = 14
+    LAUNCHES_PER_ITER = 9          # K1', scan, scatter, sort, K5', loss, K6', K7', update (+4 median passes with ignore_outlier_depth_loss)
 
     def __init__(self, settings, params, device="cuda:0", lr_rot=4e-4, lr_trans=2e-3, w_im=0.5, w_depth=0.025,
                  use_sil_for_loss=True, sil_thres=0.99, tile_rows=(0, 0), pair_capacity=None, use_graph=True,
