@@ -173,7 +173,7 @@ blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __re
             const float alpha = fminf(VTGS_ALPHA_MAX, q0.w * Gv);
             const float4 q2 = G.c[e];
             const float col[4] = {q2.x, q2.y, q2.z, q2.w};
-            const float inv = __fdividef(1.0f, 1.0f - alpha);
+            const float inv = rcp_approx(1.0f - alpha);             // 1 - alpha in [0.01, 1]
             T = T * inv;
             float dL_dalpha = 0.0f;
 #pragma unroll
@@ -198,8 +198,9 @@ blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __re
             // no decision depends on G any more (the forward's masks fix which splats were blended), so the
             // backward may use the hardware exp2 and free contraction: gradients are judged to 1e-3 relative
             const float dxa = a0.x - pxf, dya = a0.y - pyf, dxb = b0.x - pxf, dyb = b0.y - pyf;
-            const float Ga = __expf(-0.5f * (a1.x * dxa * dxa + a1.z * dya * dya) - a1.y * dxa * dya);
-            const float Gb = __expf(-0.5f * (b1.x * dxb * dxb + b1.z * dyb * dyb) - b1.y * dxb * dyb);
+            // (power is in [pthr, 0], |pthr| a few units: the forward blended these pairs)
+            const float Ga = ex2_approx(1.44269504f * (-0.5f * (a1.x * dxa * dxa + a1.z * dya * dya) - a1.y * dxa * dya));
+            const float Gb = ex2_approx(1.44269504f * (-0.5f * (b1.x * dxb * dxb + b1.z * dyb * dyb) - b1.y * dxb * dyb));
             A.cell[ea][lane] = back_one(a0, Ga, ea);
             if (two) A.cell[eb][lane] = back_one(b0, Gb, eb);
         }

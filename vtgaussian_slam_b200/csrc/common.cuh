@@ -107,6 +107,19 @@ __device__ __forceinline__ float vexpf(float x) {
     return __uint_as_float(__float_as_uint(e) + (__float_as_uint(t) << 23));
 }
 
+// Bare MUFU approximations for arguments known to be far from the denormal / overflow guards that __expf and
+// __fdividef wrap around them (3 and 5 extra instructions): gradients only (judged to 1e-3), never decisions.
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 __device__ __forceinline__ float xform_row(const float* __restrict__ m, int r, float x, float y, float z) {
     return fadd(ffma(m[8 + r], z, ffma(m[4 + r], y, fmul(m[r], x))), m[12 + r]);
 }
