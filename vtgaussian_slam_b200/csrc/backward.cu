@@ -188,10 +188,10 @@ blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __re
             return make_float2(alpha * T, Gv * dL_dalpha);
         };
         while (m) {
-            const int ea = 31 - __clz(m);
-            m &= ~(1u << ea);
+            const int ea = msb_index(m);
+            m ^= 1u << ea;
             const bool two = m != 0;
-            const int eb = two ? 31 - __clz(m) : ea;
+            const int eb = two ? msb_index(m) : ea;
             m &= ~(1u << eb);
             const float4 a0 = G.a[ea], a1 = G.b[ea];
             const float4 b0 = G.a[eb], b1 = G.b[eb];

@@ -120,6 +120,13 @@ __device__ __forceinline__ float rcp_approx(float x) {
     return y;
 }
 
+// index of the most significant set bit (x != 0): one FLO instead of 31 - (31 - FLO)
+__device__ __forceinline__ int msb_index(uint32_t x) {
+    int r;
+    asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(x));
+    return r;
+}
+
 __device__ __forceinline__ float xform_row(const float* __restrict__ m, int r, float x, float y, float z) {
     return fadd(ffma(m[8 + r], z, ffma(m[4 + r], y, fmul(m[r], x))), m[12 + r]);
 }
