@@ -296,7 +296,7 @@ def run_ours(args, wl):
         "frac": achieved / hbm_peak,
         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel per launch, from the ncu --set full capture of
         # the same workload committed under profiles/r01_kernels_ncu_full.txt (only valid for the full C2 workload at N=1)
-        "traffic": (241.2e6 if (dom_name == "blend_backward_kernel" and world == 1 and not args.small) else None),
+        "traffic": (242.1e6 if (dom_name == "blend_backward_kernel" and world == 1 and not args.small) else None),
         "traffic_unit": "bytes/launch",
         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)",
         "kernel_us": dom_s * 1e6, "kernel_share_of_step": dom_ms / total_prof_ms,
@@ -304,9 +304,9 @@ def run_ours(args, wl):
         "pair_tests_per_launch": S, "pair_tests_per_s": S / dom_s,
         # issue-slot view of the same kernel: warp instructions per launch from the committed ncu capture
         # (smsp__inst_executed.sum, C2 at N=1 only) over the live duration, against 148 SM x 4 schedulers x SM clock
-        "issue": ({"warp_inst_per_launch": 243.35e6, "achieved_ginst_s": 243.35e6 / dom_s / 1e9,
+        "issue": ({"warp_inst_per_launch": 218.38e6, "achieved_ginst_s": 218.38e6 / dom_s / 1e9,
                    "peak_ginst_s": 148 * 4 * float(peaks.get("sm_max_mhz", 1965.0)) / 1e3,
-                   "frac": 243.35e6 / dom_s / 1e9 / (148 * 4 * float(peaks.get("sm_max_mhz", 1965.0)) / 1e3)}
+                   "frac": 218.38e6 / dom_s / 1e9 / (148 * 4 * float(peaks.get("sm_max_mhz", 1965.0)) / 1e3)}
                   if (dom_name == "blend_backward_kernel" and world == 1 and not args.small) else None),
         "iteration_hbm_floor_us": hbm_floor_s * 1e6, "iteration_hbm_frac": hbm_floor_s / (ms_per_step * 1e-3),
         "per_kernel_us": {k: round(t * 1e3 / n, 2) for k, (n, t) in prof.items()},
