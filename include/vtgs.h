@@ -159,7 +159,10 @@ VTGS_API int vtgs_workspace_query(int32_t image_width, int32_t image_height, int
                          uint64_t pair_capacity, VtgsWorkspaceSizes* sizes);
 
 /*
- * Forward: replaces _C.rasterize_gaussians (K1..K5 of SURVEY.md section 2.3).
+ * Forward: replaces _C.rasterize_gaussians (K1..K5 of SURVEY.md section 2.3), the call behind the reference's
+ * `Renderer(raster_settings=curr_data['cam'])(**rendervar)` (src/vtgaussian_slam.py:461, :466, :747;
+ * utils/eval_helpers.py:240, :247, :431, :443, :728, :733; settings built at utils/recon_helpers.py:14-26).
+ * num_gaussians < 2^24 (24-bit Gaussian id in the sort key): VTGS_E_UNSUPPORTED beyond.
  *   means3D[N,3] scales[N,3] rotations[N,4] opacities[N] colors[N,3]  ->
  *   out_color[3,H,W]  out_depth[H,W]  radii[N]
  * Colours are precomputed (the reference never passes SHs: sh_degree = 0).
@@ -171,7 +174,8 @@ VTGS_API int vtgs_forward(const VtgsCamera* cam, int64_t num_gaussians,
                  VtgsBuffers* buf, void* stream);
 
 /*
- * Backward: replaces _C.rasterize_gaussians_backward (K6, K7).
+ * Backward: replaces _C.rasterize_gaussians_backward (K6, K7), reached from the reference's `loss.backward()`
+ * (src/vtgaussian_slam.py:1889 tracking, :2686 mapping) through the rasteriser's autograd Function.
  *   dL_dout_color[3,H,W] + the forward's inputs and buffers ->
  *   dL_dmeans2D[N,3] (z = 0), dL_dcolors[N,3], dL_dopacity[N], dL_dmeans3D[N,3],
  *   dL_dscales[N,3], dL_drotations[N,4].  No gradient flows through out_depth or radii
@@ -185,7 +189,8 @@ VTGS_API int vtgs_backward(const VtgsCamera* cam, int64_t num_gaussians,
                   float* dL_dmeans3D, float* dL_dscales, float* dL_drotations,
                   VtgsBuffers* buf, void* stream);
 
-/* Replaces _C.mark_visible: present[i] = (p_view.z > near cull). */
+/* Replaces _C.mark_visible (upstream GaussianRasterizer.markVisible; not called by the reference, kept for the
+ * drop-in surface): present[i] = (p_view.z > near cull). */
 VTGS_API int vtgs_mark_visible(const VtgsCamera* cam, int64_t num_gaussians, const float* means3D,
                       uint8_t* present, void* stream);
 
