@@ -41,6 +41,7 @@ def main():
 
     import torch
     from vtgaussian_slam_b200 import synthetic
+    from vtgaussian_slam_b200.metrics import ate_after_alignment
     from vtgaussian_slam_b200.slam_loop import LoopConfig, ViewTiedSLAM, ate_rmse
 
     from vtgaussian_slam_b200 import frames
@@ -71,6 +72,7 @@ def main():
         source=a.source, shape=a.shape if a.source == "synthetic" else a.sequence, W=W, H=H, frames=n, sections=len(slam.sections),
         gaussians_per_section=int(slam.sections[-1]["params"]["means3D"].shape[0]),
         ate_rmse_m=ate_rmse(est, poses), ate_rmse_if_not_tracking_m=ate_rmse(still, poses),
+        ate_mean_after_alignment_m=ate_after_alignment(list(poses), list(est)),        # the reference's evaluate_ate
         track_iters=st["track_iters"], track_iters_per_s=st["track_iters"] / max(st["track_s"], 1e-9),
         map_keyframe_iters=st["map_iters"], map_keyframe_iters_per_s=st["map_iters"] / max(st["map_s"], 1e-9),
         frames_per_s=n / wall, wall_s=wall)))
