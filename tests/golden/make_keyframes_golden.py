@@ -1,0 +1,54 @@
+"""Golden vectors for vtgaussian_slam_b200.keyframes from the reference's utils/keyframe_selection.py.
+
+    python tests/golden/make_keyframes_golden.py        # build container only (needs /root/reference)
+
+The reference module imports on CPU but calls `.cuda()` at run time: Tensor.cuda is made the identity and
+torch.cuda.empty_cache a no-op for the duration of the calls (nothing else is changed)."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, "/root/reference")
+
+
+def scene(seed):
+    from vtgaussian_slam_b200 import synthetic
+    W, H, K = synthetic.intrinsics("tum_fr1", 160, 120)
+    poses = synthetic.trajectory(12, step_m=0.12, step_deg=6.0, seed=seed)
+    fr = synthetic.make_frame("tum_fr1", 160, 120, seed=seed, c2w=poses[5])
+    depth = fr["depth"].copy()
+    depth[0, :10, :30] = 0.0                                  # some invalid depth
+    return depth, K.astype(np.float32), poses
+
+
+if __name__ == "__main__":
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    torch.cuda.empty_cache = lambda: None
+    from utils.keyframe_selection import get_pointcloud, keyframe_selection_overlap
+    out = {}
+    for case, seed in enumerate((0, 1, 2)):
+        depth, K, poses = scene(seed)
+        gt_depth = torch.tensor(depth)
+        intr = torch.tensor(K)
+        w2c = torch.tensor(np.linalg.inv(poses[5]), dtype=torch.float32)
+        kfs = [dict(id=i, est_w2c=torch.tensor(np.linalg.inv(poses[i]), dtype=torch.float32)) for i in range(12) if i != 5]
+        torch.manual_seed(100 + seed)
+        ranked = keyframe_selection_overlap(gt_depth, w2c, intr, [dict(k) for k in kfs], 4, pixels=400, edge_value=8, save_percent=True)
+        torch.manual_seed(100 + seed)
+        chosen = keyframe_selection_overlap(gt_depth, w2c, intr, [dict(k) for k in kfs], 4, pixels=400, edge_value=8)
+        out[f"c{case}.depth"], out[f"c{case}.K"], out[f"c{case}.poses"] = depth, K, poses
+        out[f"c{case}.ranked_ids"] = np.array([r["id"] for r in ranked])
+        out[f"c{case}.ranked_frac"] = np.array([float(r["percent_inside"]) for r in ranked], np.float32)
+        out[f"c{case}.chosen"] = np.array(chosen)
+        # get_pointcloud on explicit samples, with repeats and an invalid-depth pixel
+        idx = torch.tensor([[40, 50], [40, 50], [5, 5], [100, 20], [60, 150], [100, 20], [77, 33]])
+        out[f"c{case}.samples"] = idx.numpy()
+        out[f"c{case}.pts"] = get_pointcloud(gt_depth, intr, w2c, idx).numpy()
+    np.savez_compressed(os.path.join(HERE, "keyframes_golden.npz"), **out)
+    for c in range(3):
+        print(out[f"c{c}.chosen"], out[f"c{c}.ranked_frac"][:5], out[f"c{c}.pts"].shape)

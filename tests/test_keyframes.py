@@ -1,0 +1,47 @@
+"""CPU: vtgaussian_slam_b200.keyframes against the reference's keyframe_selection_overlap / get_pointcloud
+(golden vectors: tests/golden/make_keyframes_golden.py)."""
+import os
+
+import numpy as np
+import torch
+
+from vtgaussian_slam_b200 import keyframes
+
+G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "keyframes_golden.npz"))
+
+
+def _case(c):
+    depth, K, poses = torch.tensor(G[f"c{c}.depth"]), torch.tensor(G[f"c{c}.K"]), G[f"c{c}.poses"]
+    w2c = torch.tensor(np.linalg.inv(poses[5]), dtype=torch.float32)
+    kfs = [dict(id=i, est_w2c=torch.tensor(np.linalg.inv(poses[i]), dtype=torch.float32)) for i in range(12) if i != 5]
+    return depth, K, w2c, kfs
+
+
+def test_selection_and_ranking_match_the_reference():
+    for c, seed in enumerate((0, 1, 2)):
+        depth, K, w2c, kfs = _case(c)
+        torch.manual_seed(100 + seed)
+        ranked = keyframes.keyframe_selection_overlap(depth, w2c, K, kfs, 4, pixels=400, edge_value=8, save_percent=True)
+        assert [r["id"] for r in ranked] == list(G[f"c{c}.ranked_ids"])                 # including the order of ties
+        assert np.allclose([float(r["percent_inside"]) for r in ranked], G[f"c{c}.ranked_frac"], atol=1e-7)
+        torch.manual_seed(100 + seed)
+        assert keyframes.keyframe_selection_overlap(depth, w2c, K, kfs, 4, pixels=400, edge_value=8) == list(G[f"c{c}.chosen"])
+    assert keyframes.keyframe_selection_overlap(depth, w2c, K, [], 4) == []
+
+
+def test_backprojection_drops_coincident_points_like_the_reference():
+    for c in range(3):
+        depth, K, w2c, _ = _case(c)
+        pts = keyframes.backproject_samples(depth, K, w2c, torch.tensor(G[f"c{c}.samples"]))
+        assert pts.shape == G[f"c{c}.pts"].shape                     # repeated samples removed each other, so did the zero-depth pixel
+        assert np.allclose(pts.numpy(), G[f"c{c}.pts"], atol=1e-6)
+
+
+def test_a_generator_makes_the_sampling_reproducible_without_touching_global_state():
+    depth, K, w2c, kfs = _case(0)
+    g1, g2 = torch.Generator().manual_seed(7), torch.Generator().manual_seed(7)
+    a = keyframes.keyframe_selection_overlap(depth, w2c, K, kfs, 3, pixels=300, edge_value=8, generator=g1)
+    b = keyframes.keyframe_selection_overlap(depth, w2c, K, kfs, 3, pixels=300, edge_value=8, generator=g2)
+    assert a == b and len(a) == 3
+    far = [dict(est_w2c=torch.tensor(np.diag([-1.0, 1.0, -1.0, 1.0]), dtype=torch.float32))]      # looks the other way
+    assert keyframes.keyframe_selection_overlap(depth, w2c, K, far, 3, pixels=300, edge_value=8) == []

@@ -1,0 +1,62 @@
+"""Overlap-based keyframe selection (utils/keyframe_selection.py:10-120), batched and
+device-agnostic: the current frame's sampled pixels are back-projected once and tested against ALL keyframes in one
+batched projection on whatever device the inputs live on -- the reference loops over keyframes in Python and moves
+every keyframe's tensors to the GPU and back on each call (:68-71, :108-112).
+
+Semantics kept exactly (including two quirks):
+  * pixels are sampled WITH replacement from the valid-depth pixels (`torch.randint`), and `get_pointcloud` then drops
+    every point whose coordinates, rounded to 1e-4 and made absolute, coincide with another point's or with the origin
+    (:29-37) -- so repeated samples remove each other;
+  * a point counts as inside a keyframe when its projection is more than `edge` pixels from every border and its
+    depth (+1e-5) is positive; keyframes are ranked by that fraction (stable, descending), those with fraction 0 are
+    dropped, the first k ids are returned.
+"""
+from __future__ import annotations
+
+import torch
+
+
+def backproject_samples(depth, intrinsics, w2c, sampled_indices):
+    """World points of the sampled (row, col) pixels of depth[1,H,W] (reference get_pointcloud of this module: no
+    half-pixel offset here, unlike the section builder), minus coincident points."""
+    fx, fy, cx, cy = intrinsics[0][0], intrinsics[1][1], intrinsics[0][2], intrinsics[1][2]
+    rows, cols = sampled_indices[:, 0], sampled_indices[:, 1]
+    z = depth[0, rows, cols]
+    cam = torch.stack(((cols - cx) / fx * z, (rows - cy) / fy * z, z), dim=-1)
+    hom = torch.cat([cam, torch.ones_like(cam[:, :1])], dim=1)
+    pts = (torch.inverse(w2c) @ hom.T).T[:, :3]
+    keyed = torch.cat([torch.abs(torch.round(pts, decimals=4)), torch.zeros((1, 3), dtype=pts.dtype, device=pts.device)], dim=0)
+    _, inverse, counts = keyed.unique(dim=0, return_inverse=True, return_counts=True)
+    duplicated = torch.isin(inverse, torch.where(counts.gt(1))[0])[:pts.shape[0]]
+    return pts[~duplicated]
+
+
+def overlap_fractions(pts, intrinsics, keyframe_w2c, width, height, edge=20):
+    """Fraction of `pts` that projects inside each keyframe: keyframe_w2c[Kf,4,4] -> [Kf]."""
+    hom = torch.cat([pts, torch.ones_like(pts[:, :1])], dim=1)                       # [n, 4]
+    cam = (keyframe_w2c @ hom.T).transpose(1, 2)[..., :3]                             # [Kf, n, 3]
+    proj = cam @ intrinsics.T                                                         # [Kf, n, 3]
+    zed = proj[..., 2:] + 1e-5
+    uv = proj[..., :2] / zed
+    inside = (uv[..., 0] < width - edge) & (uv[..., 0] > edge) & (uv[..., 1] < height - edge) & (uv[..., 1] > edge) & (zed[..., 0] > 0)
+    return inside.sum(dim=1) / max(pts.shape[0], 1) if pts.shape[0] else torch.full((keyframe_w2c.shape[0],), float("nan"), device=pts.device)
+
+
+def keyframe_selection_overlap(gt_depth, w2c, intrinsics, keyframe_list, k, pixels=1600, edge_value=20, save_percent=False,
+                               generator=None):
+    """Signature and results of the reference's keyframe_selection_overlap; `keyframe_list[i]['est_w2c']` is the only
+    field read.  `generator` (optional) seeds the pixel sampling; by default torch's global generator is used, like
+    the reference."""
+    width, height = gt_depth.shape[2], gt_depth.shape[1]
+    valid = torch.stack(torch.where(gt_depth[0] > 0), dim=1)
+    pick = torch.randint(valid.shape[0], (pixels,), generator=generator)
+    pts = backproject_samples(gt_depth, intrinsics, w2c, valid[pick.to(valid.device)])
+    if not keyframe_list:
+        return []
+    stack = torch.stack([kf["est_w2c"].to(pts.device) for kf in keyframe_list])
+    frac = overlap_fractions(pts, intrinsics[:3, :3].to(pts.device), stack, width, height, edge_value)
+    order = torch.sort(frac, descending=True, stable=True).indices.tolist()
+    ranked = [{"id": i, "percent_inside": frac[i]} for i in order]
+    if save_percent:
+        return ranked
+    return [r["id"] for r in ranked if r["percent_inside"] > 0.0][:k]
