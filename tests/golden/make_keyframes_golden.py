@@ -52,3 +52,42 @@ if __name__ == "__main__":
     np.savez_compressed(os.path.join(HERE, "keyframes_golden.npz"), **out)
     for c in range(3):
         print(out[f"c{c}.chosen"], out[f"c{c}.ranked_frac"][:5], out[f"c{c}.pts"].shape)
+
+
+def vis_mask_goldens():
+    """get_vis_mask (src/vtgaussian_slam.py:376-404) and the nested get_pointcloud_forvismask (:538-556): that module
+    cannot be imported (rasteriser, open3d ... absent), so the two function definitions are compiled from its source."""
+    import ast
+    import torch.nn.functional as F
+    from vtgaussian_slam_b200 import synthetic
+    tree = ast.parse(open("/root/reference/src/vtgaussian_slam.py").read())
+    want = {}
+    for node in ast.walk(tree):
+        if isinstance(node, ast.FunctionDef) and node.name in ("get_vis_mask", "get_pointcloud_forvismask") and node.name not in want:
+            want[node.name] = node
+    ns = {"torch": torch, "F": F}
+    exec(compile(ast.Module(body=list(want.values()), type_ignores=[]), "vtgaussian_slam.py", "exec"), ns)
+    out = {}
+    W, H, K = synthetic.intrinsics("tum_fr1", 96, 72)
+    poses = synthetic.trajectory(8, step_m=0.25, step_deg=9.0, seed=4)
+    cur = synthetic.make_frame("tum_fr1", 96, 72, seed=0, c2w=poses[2])
+    gt_depth = torch.tensor(cur["depth"])
+    gt_depth[0, 60:, 80:] = 0.0
+    intr = torch.tensor(K.astype(np.float32))
+    curr_w2c = torch.tensor(np.linalg.inv(poses[2]), dtype=torch.float32)
+    idx = torch.stack(torch.where(gt_depth[0] >= 0), dim=1)
+    pts = ns["get_pointcloud_forvismask"](gt_depth, intr, curr_w2c, idx)
+    out["vis.depth"], out["vis.K"], out["vis.poses"], out["vis.pts"] = gt_depth.numpy(), intr.numpy(), poses, pts.numpy()
+    for j, k in enumerate((0, 4, 7)):
+        other = synthetic.make_frame("tum_fr1", 96, 72, seed=1 + k, c2w=poses[k])
+        od = torch.tensor(other["depth"])
+        out[f"vis.other{j}"] = od.numpy()
+        out[f"vis.mask{j}"] = ns["get_vis_mask"](torch.tensor(np.linalg.inv(poses[k]), dtype=torch.float32), pts.clone(), intr, od, 0.05, 72, 96).numpy()
+    return out
+
+
+if __name__ == "__main__":
+    g = dict(np.load(os.path.join(HERE, "keyframes_golden.npz")))
+    g.update(vis_mask_goldens())
+    np.savez_compressed(os.path.join(HERE, "keyframes_golden.npz"), **g)
+    print({k: float(v.mean()) for k, v in g.items() if k.startswith("vis.mask")})

@@ -268,6 +268,36 @@ def test_outlier_median_and_visibility_masks_match_the_torch_path(use_sil):
     assert rel_err(b[1], a[1]) <= 2e-2 and rel_err(b[2], a[2]) <= 2e-2
 
 
+def test_get_loss_builds_the_visibility_mask_from_the_overlap_arguments():
+    """The reference's own get_loss arguments (curr_w2c, overlap_w2c, overlap_gtdepth, ...) give the same loss as
+    passing the mask keyframes.tracking_vis_mask computes from them."""
+    from vtgaussian_slam_b200 import keyframes
+    fr, p, q, t = _scene(200, 120, n_edge=1500)
+    settings, _ = _settings(fr)
+    K = torch.tensor(fr["K"], dtype=torch.float32, device=DEV)
+    poses = synthetic.trajectory(6, step_m=0.2, step_deg=8.0, seed=2)
+    others = [synthetic.make_frame("replica", 200, 120, seed=5 + k, c2w=poses[k]) for k in (1, 3, 5)]
+    ov = [(torch.tensor(np.linalg.inv(poses[k]), dtype=torch.float32, device=DEV), torch.tensor(o["depth"], device=DEV))
+          for k, o in zip((1, 3, 5), others)]
+    data = dict(cam=settings, im=torch.tensor(fr["im"], device=DEV), depth=torch.tensor(fr["depth"], device=DEV),
+                w2c=torch.eye(4, device=DEV), intrinsics=K)
+    curr_w2c = torch.eye(4, device=DEV)
+    mask = keyframes.tracking_vis_mask(data["depth"], K, curr_w2c, ov, 0.05)
+    assert 0.05 < float(mask.float().mean()) < 0.999
+    losses = []
+    for kw in (dict(vis_mask=mask),
+               dict(curr_w2c=curr_w2c, overlap_w2c=ov[0][0], overlap_gtdepth=ov[0][1], overlap_mid_w2c=ov[1][0],
+                    overlap_mid_gtdepth=ov[1][1], overlap_last_w2c=ov[2][0], overlap_last_gtdepth=ov[2][1])):
+        params = {k: torch.nn.Parameter(torch.tensor(v, device=DEV)) for k, v in p.items()}
+        params["cam_unnorm_rots"] = torch.nn.Parameter(torch.tensor(q, device=DEV).reshape(1, 4, 1).contiguous())
+        params["cam_trans"] = torch.nn.Parameter(torch.tensor(t, device=DEV).reshape(1, 3, 1).contiguous())
+        variables = dict(max_2D_radius=torch.zeros(p["means3D"].shape[0], device=DEV))
+        loss, _, wl = slam_ops.get_loss(params, data, variables, 0, dict(im=0.5, depth=1.0), True, 0.99, True, False,
+                                        tracking=True, dataset_name="scannetpp", **kw)
+        losses.append(loss.item())
+    assert losses[0] == losses[1] and losses[0] > 0
+
+
 def test_outlier_median_is_rejected_with_a_tile_band():
     from vtgaussian_slam_b200.fused import FusedRenderer
     fr, p, q, t = _scene(200, 120, n_edge=500)

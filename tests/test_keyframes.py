@@ -45,3 +45,23 @@ def test_a_generator_makes_the_sampling_reproducible_without_touching_global_sta
     assert a == b and len(a) == 3
     far = [dict(est_w2c=torch.tensor(np.diag([-1.0, 1.0, -1.0, 1.0]), dtype=torch.float32))]      # looks the other way
     assert keyframes.keyframe_selection_overlap(depth, w2c, K, far, 3, pixels=300, edge_value=8) == []
+
+
+def test_visibility_mask_matches_the_reference():
+    depth, K, poses = torch.tensor(G["vis.depth"]), torch.tensor(G["vis.K"]), G["vis.poses"]
+    curr_w2c = torch.tensor(np.linalg.inv(poses[2]), dtype=torch.float32)
+    pts = keyframes.frame_points(depth, K, curr_w2c)
+    assert np.allclose(pts.numpy(), G["vis.pts"], atol=1e-6)
+    overlaps = []
+    for j, k in enumerate((0, 4, 7)):
+        w2c = torch.tensor(np.linalg.inv(poses[k]), dtype=torch.float32)
+        od = torch.tensor(G[f"vis.other{j}"])
+        m = keyframes.get_vis_mask(w2c, pts, K, od, 0.05, 72, 96)
+        ref = G[f"vis.mask{j}"]
+        assert m.shape == ref.shape and m.dtype == torch.bool
+        assert (m.numpy() != ref).mean() < 2e-4          # knife-edge pixels of the float comparison at most
+        overlaps.append((w2c, od))
+    both = keyframes.tracking_vis_mask(depth, K, curr_w2c, overlaps, 0.05)
+    assert both.shape == (1, 72, 96)
+    assert ((both[0].numpy()) != (G["vis.mask0"] | G["vis.mask1"] | G["vis.mask2"])).mean() < 5e-4
+    assert 0.3 < float(both.float().mean()) < 1.0

@@ -60,3 +60,44 @@ def keyframe_selection_overlap(gt_depth, w2c, intrinsics, keyframe_list, k, pixe
     if save_percent:
         return ranked
     return [r["id"] for r in ranked if r["percent_inside"] > 0.0][:k]
+
+
+# ---- overlap-visibility mask of the tracking loss (reference src/vtgaussian_slam.py:376-404, :536-583) --------------
+def frame_points(gt_depth, intrinsics, w2c):
+    """World points of EVERY pixel of gt_depth[1,H,W] in row-major order (the reference's get_pointcloud_forvismask,
+    :538-556: `depth >= 0` keeps all pixels; pixel centres without the half-pixel offset)."""
+    H, W = gt_depth.shape[1], gt_depth.shape[2]
+    fx, fy, cx, cy = intrinsics[0][0], intrinsics[1][1], intrinsics[0][2], intrinsics[1][2]
+    rows = torch.arange(H, device=gt_depth.device).repeat_interleave(W)
+    cols = torch.arange(W, device=gt_depth.device).repeat(H)
+    z = gt_depth[0].reshape(-1)
+    cam = torch.stack(((cols - cx) / fx * z, (rows - cy) / fy * z, z), dim=-1)
+    hom = torch.cat([cam, torch.ones_like(cam[:, :1])], dim=1)
+    return (torch.inverse(w2c) @ hom.T).T[:, :3]
+
+
+def get_vis_mask(overlap_w2c, pts, intrinsics, overlap_gtdepth, vis_mask_thres, height, width):
+    """mask[H,W]: pixel i of the current frame (its world point pts[i]) is seen by the overlapping keyframe when
+    the keyframe's depth, bilinearly sampled (zeros outside, align_corners) at the projection, agrees with the
+    projected depth to within vis_mask_thres x the smaller of the two (reference get_vis_mask)."""
+    hom = torch.cat([pts, torch.ones_like(pts[:, :1])], dim=1)
+    cam = (overlap_w2c @ hom.T).T[:, :3]
+    proj = (intrinsics @ cam.T).T
+    z = proj[:, 2] + 1e-5
+    u, v = proj[:, 0] / z, proj[:, 1] / z
+    grid = torch.stack((u / (width - 1) * 2.0 - 1.0, v / (height - 1) * 2.0 - 1.0), dim=-1).reshape(1, 1, -1, 2)
+    seen = torch.nn.functional.grid_sample(overlap_gtdepth.to(grid.device).reshape(1, 1, height, width), grid,
+                                           padding_mode="zeros", align_corners=True).reshape(-1)
+    return (torch.abs(seen - z) < vis_mask_thres * torch.minimum(seen, z)).reshape(overlap_gtdepth.shape[1:])
+
+
+def tracking_vis_mask(gt_depth, intrinsics, curr_w2c, overlaps, vis_mask_thres=0.05):
+    """OR of get_vis_mask over the overlapping keyframes [(w2c, gt_depth), ...] (one for TUM, first / mid / last for
+    ScanNet(++), reference :563-574) -> bool[1,H,W], ready for slam_ops.get_loss(vis_mask=...) /
+    FusedRenderer.tracking_loss(pixel_mask=...)."""
+    H, W = gt_depth.shape[1], gt_depth.shape[2]
+    pts = frame_points(gt_depth, intrinsics, curr_w2c)
+    out = torch.zeros((H, W), dtype=torch.bool, device=gt_depth.device)
+    for w2c, depth in overlaps:
+        out |= get_vis_mask(w2c, pts, intrinsics, depth, vis_mask_thres, H, W)
+    return out[None]

@@ -385,13 +385,24 @@ def get_loss(params, curr_data, variables, iter_time_idx, loss_weights, use_sil_
              mapping=False, do_ba=False, plot_dir=None, visualize_tracking_loss=False,
              tracking_iteration=None, additional_mask=None, dataset_name=None,
              presence_sil_mask_mse_ls=None, sil_thres_ls=None, far_depth_filter_thres=None, vis_mask_thres=0.05,
-             vis_mask=None, backend="fused"):
+             curr_w2c=None, overlap_w2c=None, overlap_gtdepth=None, overlap_last_w2c=None, overlap_last_gtdepth=None,
+             overlap_mid_w2c=None, overlap_mid_gtdepth=None, vis_mask=None, backend="fused"):
     """Compute loss for mapping and tracking -- signature and return values of the reference's
     get_loss (src/vtgaussian_slam.py:407-689).  `backend="dropin"` follows the reference
     literally (two Renderer calls); `backend="fused"` (default) renders the six planes in one
     pass with the front end and the pose / parameter chain inside the CUDA kernels.  The
     overlap-visibility mask the reference derives from neighbouring keyframes (:536-583) is
-    SLAM policy outside this path: pass it precomputed as `vis_mask`."""
+    SLAM policy outside this path: pass it precomputed as `vis_mask`, or pass the reference's own
+    `curr_w2c` / `overlap_*` arguments and it is computed here (keyframes.tracking_vis_mask: one keyframe for
+    TUM, first | mid | last for ScanNet(++), none for Replica -- reference :536-583)."""
+    if vis_mask is None and tracking and overlap_w2c is not None and dataset_name != 'replica':
+        from .keyframes import tracking_vis_mask
+        overlaps = [(overlap_w2c, overlap_gtdepth)]
+        if dataset_name in ('scannet', 'scannetpp'):
+            overlaps += [(overlap_mid_w2c, overlap_mid_gtdepth), (overlap_last_w2c, overlap_last_gtdepth)]
+        dev_ = curr_data['depth'].device
+        overlaps = [(w.to(dev_), d.to(dev_)) for w, d in overlaps]
+        vis_mask = tracking_vis_mask(curr_data['depth'], curr_data['intrinsics'].to(dev_), curr_w2c.to(dev_), overlaps, vis_mask_thres)
     for k, v in params.items():
         if not isinstance(v, torch.Tensor):
             params[k] = torch.tensor(v).float().contiguous()
