@@ -71,3 +71,27 @@ def test_identity_pose_frame_equals_the_unposed_frame():
     a = synthetic.make_frame("tum_fr1", 64, 48, seed=5)
     b = synthetic.make_frame("tum_fr1", 64, 48, seed=5, c2w=np.eye(4))
     assert np.array_equal(a["depth"], b["depth"]) and np.array_equal(a["im"], b["im"])
+
+
+def test_params_ls_round_trip_in_the_reference_layout(tmp_path):
+    import torch
+    from vtgaussian_slam_b200.slam_loop import SectionStore, export_params_ls, import_params_ls
+    rng = np.random.default_rng(0)
+    st = SectionStore(8, "cpu")
+    secs = []
+    for n in (5, 9, 3):
+        p = {k: torch.tensor(rng.normal(size=(n, c)).astype(np.float32)) for k, c in SectionStore.KEYS.items()}
+        secs.append(p)
+        st.append(p)
+    traj = [np.linalg.inv(M) for M in synthetic.trajectory(7, 0.05, 2.0)]
+    path = export_params_ls(str(tmp_path / "params_ls.npy"), st, traj)
+    raw = np.load(path, allow_pickle=True)                         # what the reference's eval code does
+    assert raw.shape == (3,) and set(raw[0]) == set(SectionStore.KEYS) | {"cam_unnorm_rots", "cam_trans"}
+    assert tuple(raw[1]["cam_unnorm_rots"].shape) == (1, 4, 7) and tuple(raw[1]["cam_trans"].shape) == (1, 3, 7)
+    assert isinstance(raw[2]["means3D"], torch.Tensor) and raw[2]["means3D"].shape == (3, 3)
+    st2, traj2 = import_params_ls(path)
+    assert len(st2) == 3 and st2.num_gaussians == 17
+    for k in range(3):
+        for name in SectionStore.KEYS:
+            assert torch.equal(st2.rows(k)[name], secs[k][name])
+    assert len(traj2) == 7 and all(np.allclose(a, b, atol=1e-6) for a, b in zip(traj, traj2))

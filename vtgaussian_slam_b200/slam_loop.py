@@ -265,3 +265,49 @@ class ViewTiedSLAM:
         for fr in frames:
             self.process(fr)
         return np.stack([np.linalg.inv(m) for m in self.w2c])
+
+
+# ---- results in the reference's on-disk form (src/vtgaussian_slam.py:2868-2876: np.save of the list of per-section
+# parameter dicts, an object array of CPU tensors) -- so the reference's evaluation scripts can read a run of this loop
+def export_params_ls(path, store, w2c_list):
+    """Write `params_ls.npy`: one dict per section with the five Gaussian tensors plus the whole estimated
+    trajectory as cam_unnorm_rots[1,4,T] / cam_trans[1,3,T] (relative w2c per frame, as initialize_params lays
+    them out, :166-170)."""
+    T = len(w2c_list)
+    rots = torch.zeros((1, 4, T), dtype=torch.float32)
+    trans = torch.zeros((1, 3, T), dtype=torch.float32)
+    for i, M in enumerate(w2c_list):
+        M = np.asarray(M, np.float64)
+        rots[0, :, i] = torch.as_tensor(quat_from_matrix(M[:3, :3]), dtype=torch.float32)
+        trans[0, :, i] = torch.as_tensor(M[:3, 3], dtype=torch.float32)
+    out = []
+    for k in range(len(store)):
+        d = {name: t.detach().cpu().clone() for name, t in store.rows(k).items()}
+        d["cam_unnorm_rots"], d["cam_trans"] = rots.clone(), trans.clone()
+        out.append(d)
+    np.save(path, np.array(out, dtype=object), allow_pickle=True)
+    return path
+
+
+def import_params_ls(path, device="cpu"):
+    """Read a `params_ls.npy` (this loop's or the reference's) -> (SectionStore, list of 4x4 w2c of the trajectory
+    stored with the LAST section)."""
+    sections = list(np.load(path, allow_pickle=True))
+    if not sections:
+        raise ValueError(f"{path}: no sections")
+    as_t = lambda v: v if isinstance(v, torch.Tensor) else torch.as_tensor(np.asarray(v))
+    total = sum(int(as_t(s["means3D"]).shape[0]) for s in sections)
+    store = SectionStore(max(total, 1), device)
+    for s in sections:
+        p = {k: as_t(s[k]).float() for k in SectionStore.KEYS}
+        if p["log_scales"].dim() == 1:
+            p["log_scales"] = p["log_scales"][:, None]
+        if p["log_scales"].shape[1] != 1:
+            raise NotImplementedError("anisotropic sections (log_scales [N,3]) are not stored by SectionStore")
+        if p["logit_opacities"].dim() == 1:
+            p["logit_opacities"] = p["logit_opacities"][:, None]
+        store.append(p)
+    last = sections[-1]
+    rots, trans = as_t(last["cam_unnorm_rots"]).float(), as_t(last["cam_trans"]).float()
+    w2c = [matrix_from_quat(rots[0, :, i].numpy(), trans[0, :, i].numpy()) for i in range(rots.shape[-1])]
+    return store, w2c
