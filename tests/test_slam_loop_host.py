@@ -95,3 +95,26 @@ def test_params_ls_round_trip_in_the_reference_layout(tmp_path):
         for name in SectionStore.KEYS:
             assert torch.equal(st2.rows(k)[name], secs[k][name])
     assert len(traj2) == 7 and all(np.allclose(a, b, atol=1e-6) for a, b in zip(traj, traj2))
+
+
+def test_section_builders_match_the_reference_point_clouds():
+    """section_from_frame / geometric_edge_mask / densified_section (run on the CPU device here: plain torch ops, the same
+    on CUDA) against get_pointcloud + geometric_edge_mask of the reference, called as initialize_params_base_timestep does."""
+    import os
+    import torch
+    from vtgaussian_slam_b200.slam_loop import densified_section, geometric_edge_mask, section_from_frame
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "section_golden.npz"))
+    im, depth, im2, depth2 = (torch.tensor(G[k]) for k in ("im", "depth", "im2", "depth2"))
+    edge = geometric_edge_mask((im.permute(1, 2, 0) * 255).numpy(), dilate=True, rgb=True)
+    assert np.array_equal(edge, G["edge_mask"]) and 0.01 < (edge > 0).mean() < 0.9
+    n0 = int(G["n_base"])
+    base = section_from_frame(im, depth, G["K"], G["pose"], "cpu")
+    assert base["means3D"].shape[0] == n0 == int((G["depth"] > 0).sum())
+    sec = densified_section(im, depth, G["K"], im2, depth2, G["K2"], G["pose"], edge, "cpu")
+    assert sec["means3D"].shape == G["means3D"].shape and sec["means3D"].shape[0] > n0
+    assert np.allclose(sec["means3D"].numpy(), G["means3D"], atol=3e-6)
+    assert np.array_equal(sec["rgb_colors"].numpy(), G["rgb"])
+    assert np.allclose(sec["log_scales"][:, 0].numpy(), G["log_scales"], atol=2e-6)
+    # the dense Gaussians are half as wide as their neighbours of the base grid
+    assert float(sec["log_scales"][n0:].mean()) < float(sec["log_scales"][:n0].mean()) - 0.4      # (~log 2, edges sit at other depths)
+    assert float(sec["logit_opacities"].abs().max()) == 0.0 and float((sec["unnorm_rotations"][:, 0] - 1).abs().max()) == 0.0

@@ -88,9 +88,37 @@ def propagate_pose(w2c_prev1, w2c_prev2):
     return np.linalg.inv(c1 @ np.linalg.inv(c2) @ c1)
 
 
-def section_from_frame(rgb, depth, K, c2w, device, factor=1.005):
+def geometric_edge_mask(image_hwc, dilate=True, rgb=True):
+    """uint8[H,W] edge mask (255 on edges) of an HxWx3 image in 0..255: Canny (50 / 200, aperture 3, L2 gradient) on
+    the grey image cast to uint8, optionally dilated 3x3 -- the reference's densification mask
+    (src/vtgaussian_slam.py:1022-1041, computed once from the first frame, :1287-1289)."""
+    import cv2
+    grey = cv2.cvtColor(np.asarray(image_hwc), cv2.COLOR_RGB2GRAY if rgb else cv2.COLOR_BGR2GRAY)
+    if grey.dtype != np.uint8:
+        grey = grey.astype(np.uint8)
+    edges = cv2.Canny(grey, threshold1=50, threshold2=200, apertureSize=3, L2gradient=True)
+    return cv2.dilate(edges, np.ones((3, 3), np.uint8), iterations=1) if dilate else edges
+
+
+def densified_section(rgb, depth, K, rgb_dense, depth_dense, K_dense, c2w, edge_mask, device, factor=1.005):
+    """A section as the reference builds it at a base frame when a densification dataset is configured
+    (initialize_params_base_timestep, :285-345): every valid pixel of the tracking-resolution frame, followed by the
+    pixels of the denser frame (the same view at 2x resolution) that lie on `edge_mask` (any resolution: resized
+    with nearest neighbour to the dense grid) and have valid depth.  The dense Gaussians are half as wide
+    (scale = z / f of the dense intrinsics)."""
+    import cv2
+    Hd, Wd = depth_dense.shape[-2:]
+    m = cv2.resize(np.asarray(edge_mask), (Wd, Hd), interpolation=cv2.INTER_NEAREST).astype(np.bool_)
+    base = section_from_frame(rgb, depth, K, c2w, device, factor)
+    dense = section_from_frame(rgb_dense, depth_dense, K_dense, c2w, device, factor,
+                               pixel_mask=torch.as_tensor(m.reshape(-1), device=device))
+    return {k: torch.cat((base[k], dense[k]), dim=0).contiguous() for k in base}
+
+
+def section_from_frame(rgb, depth, K, c2w, device, factor=1.005, pixel_mask=None):
     """View-tied Gaussians of one RGB-D frame in the world frame (reference get_pointcloud + initialize_params).
-    rgb[3,H,W], depth[1,H,W] CUDA tensors; pixels with depth <= 0 are dropped."""
+    rgb[3,H,W], depth[1,H,W] tensors; pixels with depth <= 0 (and, if given, outside the flat bool `pixel_mask`)
+    are dropped."""
     H, W = depth.shape[-2:]
     fx, fy, cx, cy = float(K[0][0]), float(K[1][1]), float(K[0][2]), float(K[1][2])
     f32 = dict(dtype=torch.float32, device=device)
@@ -98,6 +126,8 @@ def section_from_frame(rgb, depth, K, c2w, device, factor=1.005):
     yy = ((torch.arange(H, **f32) - cy + 0.5) / fy).repeat_interleave(W)
     z = depth.reshape(-1).to(**f32) * factor
     keep = z > 0
+    if pixel_mask is not None:
+        keep = keep & pixel_mask.reshape(-1).to(device)
     pts = torch.stack((xx * z, yy * z, z), -1)
     M = torch.as_tensor(np.asarray(c2w, np.float32), device=device)
     pts = pts @ M[:3, :3].T + M[:3, 3]
