@@ -21,7 +21,7 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--source", default="synthetic", choices=["synthetic", "replica", "tum"])
+    ap.add_argument("--source", default="synthetic", choices=["synthetic", "replica", "tum", "scannetpp"])
     ap.add_argument("--basedir", default=None)
     ap.add_argument("--sequence", default=None)
     ap.add_argument("--camera-yaml", default=None, help="yaml with a camera_params block (reference configs/data/*.yaml)")
@@ -47,6 +47,9 @@ def main():
     from vtgaussian_slam_b200 import frames
     if a.source == "synthetic":
         src = frames.SyntheticSource(a.shape, a.frames, a.width, a.height, a.step_m, a.step_deg)
+    elif a.source == "scannetpp":
+        src = frames.ScannetPPSource(a.basedir, a.sequence, desired_height=a.height or 584, desired_width=a.width or 876,
+                                     end=a.frames if a.frames > 0 else -1)         # tracking resolution of configs/scannetpp/*.py
     else:
         import yaml
         with open(a.camera_yaml) as f:

@@ -74,6 +74,28 @@ def write_fixture():
     for name, lines in (("rgb.txt", rgb_l), ("depth.txt", dep_l), ("groundtruth.txt", gt_l)):
         with open(os.path.join(tdir, name), "w") as f:
             f.write("\n".join(lines) + "\n")
+    # ---- ScanNet++ DSLR layout: 5 training + 2 test images, OpenGL-convention c2w in a nerfstudio transforms file
+    import json
+    sdir = os.path.join(FIX, "scannetpp", "scene0", "dslr")
+    for d in ("undistorted_images", "undistorted_depths", "nerfstudio"):
+        os.makedirs(os.path.join(sdir, d), exist_ok=True)
+    flip = np.diag([1.0, -1.0, -1.0, 1.0])
+    names = [f"DSC{100 + i:05d}.JPG" for i in range(7)]
+    metas = []
+    sp = synthetic.trajectory(7, step_m=0.05, step_deg=2.0, seed=8)
+    for i, nme in enumerate(names):
+        fr = synthetic.make_frame("scannetpp", 72, 48, seed=20 + i, c2w=sp[i])
+        Image.fromarray((fr["im"].transpose(1, 2, 0) * 255 + 0.5).astype(np.uint8)).save(os.path.join(sdir, "undistorted_images", nme), quality=95)
+        Image.fromarray(np.clip(fr["depth"][0] * 1000.0 + 0.5, 0, 65535).astype(np.uint16)).save(
+            os.path.join(sdir, "undistorted_depths", nme.replace(".JPG", ".png")))
+        gl = flip @ (world @ sp[i]) @ flip                     # OpenCV c2w -> OpenGL c2w (P is its own inverse)
+        metas.append(dict(file_path=nme, transform_matrix=gl.tolist(), is_bad=bool(i == 3)))
+    Ws, Hs, Ks = synthetic.intrinsics("scannetpp", 72, 48)
+    with open(os.path.join(sdir, "nerfstudio", "transforms_undistorted.json"), "w") as f:
+        json.dump(dict(w=72, h=48, fl_x=float(Ks[0, 0]), fl_y=float(Ks[1, 1]), cx=float(Ks[0, 2]), cy=float(Ks[1, 2]),
+                       frames=[metas[i] for i in (4, 0, 2, 1, 3)], test_frames=[metas[6], metas[5]]), f)
+    with open(os.path.join(sdir, "train_test_lists.json"), "w") as f:
+        json.dump(dict(train=[names[i] for i in range(5)], test=[names[5], names[6]]), f)
 
 
 def shim_missing_modules():
@@ -130,7 +152,7 @@ def reference_outputs():
         return m
     for n in ("geometryutils", "datautils", "basedataset"):
         load(n)
-    replica, tum = load("replica"), load("tum")
+    replica, tum, spp = load("replica"), load("tum"), load("scannetpp")
     out = {}
     cases = [
         ("replica_native", replica.ReplicaDataset, dict(dataset_name="replica", camera_params=REPLICA_CAM), os.path.join(FIX, "replica"), "room0", dict(desired_height=48, desired_width=64)),
@@ -138,8 +160,14 @@ def reference_outputs():
         ("tum_native", tum.TUMDataset, dict(dataset_name="tum", camera_params=TUM_CAM), os.path.join(FIX, "tum"), "fr1", dict(desired_height=48, desired_width=64)),
         ("tum_resized", tum.TUMDataset, dict(dataset_name="tum", camera_params=TUM_CAM), os.path.join(FIX, "tum"), "fr1", dict(desired_height=24, desired_width=32, start=1)),
     ]
-    for tag, cls, cfg, basedir, seq, kw in cases:
-        ds = cls(cfg, basedir, seq, device="cpu", **{"stride": 1, **kw})
+    spp_cases = [
+        ("scannetpp_train", dict(desired_height=48, desired_width=72)),
+        ("scannetpp_train_nobad", dict(desired_height=24, desired_width=36, ignore_bad=True, start=1)),
+        ("scannetpp_test", dict(desired_height=48, desired_width=72, use_train_split=False)),
+    ]
+    datasets = [(tag, cls(cfg, basedir, seq, device="cpu", **{"stride": 1, **kw})) for tag, cls, cfg, basedir, seq, kw in cases]
+    datasets += [(tag, spp.ScannetPPDataset(os.path.join(FIX, "scannetpp"), "scene0", device="cpu", **{"stride": 1, **kw})) for tag, kw in spp_cases]
+    for tag, ds in datasets:
         ims, deps, Ks, Ps = [], [], [], []
         for i in range(len(ds)):
             color, depth, intr, pose = ds[i]

@@ -22,6 +22,11 @@ CASES = {
                                                     start=1, end=6, stride=2),
     "tum_native": lambda: frames.TumSource(TUM_CAM, os.path.join(FIX, "tum"), "fr1", desired_height=48, desired_width=64),
     "tum_resized": lambda: frames.TumSource(TUM_CAM, os.path.join(FIX, "tum"), "fr1", desired_height=24, desired_width=32, start=1),
+    "scannetpp_train": lambda: frames.ScannetPPSource(os.path.join(FIX, "scannetpp"), "scene0", desired_height=48, desired_width=72),
+    "scannetpp_train_nobad": lambda: frames.ScannetPPSource(os.path.join(FIX, "scannetpp"), "scene0", desired_height=24, desired_width=36,
+                                                            ignore_bad=True, start=1),
+    "scannetpp_test": lambda: frames.ScannetPPSource(os.path.join(FIX, "scannetpp"), "scene0", desired_height=48, desired_width=72,
+                                                     use_train_split=False),
 }
 
 

@@ -17,6 +17,9 @@ Reference behaviour mirrored (datasets/gradslam_datasets/):
   * replica.py:44-66         results/frame*.jpg, results/depth*.png in natural order, traj.txt = one row-major c2w per line
   * tum.py:44-160            rgb.txt / depth.txt / groundtruth.txt, nearest-timestamp association within 0.08 s, frames
                              at least 1/32 s apart, pose rows (tx ty tz qx qy qz qw)
+  * scannetpp.py:18-135      dslr/train_test_lists.json + dslr/nerfstudio/transforms_undistorted.json (intrinsics and
+                             per-image OpenGL c2w, converted with P c2w P^T, P = diag(1,-1,-1,1)), undistorted_images /
+                             undistorted_depths (mm); the test split is prefixed with the first training frame
 `FrameSource.prefetch` decodes ahead on a worker thread and (on CUDA) stages through pinned memory on a copy stream,
 which is what removes the reference's per-iteration synchronous image decode from the mapping loop (:2583).
 """
@@ -247,6 +250,54 @@ class TumSource(FrameSource):
             M[:3, 3] = vec[k, :3]
             out.append(M)
         return out
+
+
+class ScannetPPSource(FrameSource):
+    """ScanNet++ DSLR layout (scannetpp.py): camera parameters come from the sequence's own metadata."""
+
+    def __init__(self, basedir, sequence, ignore_bad=False, use_train_split=True, desired_height=1168, desired_width=1752, **kw):
+        import json
+        self.folder = os.path.join(basedir, sequence)
+        with open(os.path.join(self.folder, "dslr", "train_test_lists.json")) as f:
+            split = json.load(f)
+        with open(os.path.join(self.folder, "dslr", "nerfstudio", "transforms_undistorted.json")) as f:
+            meta = json.load(f)
+        self._train_names = split["train"]
+        self._names = split["train"] if use_train_split else split["test"]
+        self._frames = meta["frames"] if use_train_split else meta["test_frames"]
+        self._train_frames = meta["frames"]
+        self._ignore_bad, self._use_train = ignore_bad, use_train_split
+        cam = dict(png_depth_scale=1000.0, image_height=meta["h"], image_width=meta["w"], fx=meta["fl_x"], fy=meta["fl_y"],
+                   cx=meta["cx"], cy=meta["cy"])
+        self._listing = None
+        super().__init__(cam, desired_height=desired_height, desired_width=desired_width, **kw)
+
+    def _list(self):
+        if self._listing is not None:
+            return self._listing
+        base = os.path.join(self.folder, "dslr")
+        flip = np.diag([1.0, -1.0, -1.0, 1.0]).astype(np.float32)
+        by_name = {fr["file_path"]: fr for fr in self._frames}
+        entries = []
+        if not self._use_train:                        # evaluation split: anchored on the first training frame
+            first = self._train_names[0]
+            entries.append((first, {fr["file_path"]: fr for fr in self._train_frames}[first]))
+        for name in self._names:
+            fr = by_name[name]
+            if self._ignore_bad and fr["is_bad"]:
+                continue
+            entries.append((name, fr))
+        colour = [os.path.join(base, "undistorted_images", n) for n, _ in entries]
+        depth = [os.path.join(base, "undistorted_depths", n.replace(".JPG", ".png")) for n, _ in entries]
+        poses = [flip @ np.asarray(fr["transform_matrix"], np.float32) @ flip.T for _, fr in entries]
+        self._listing = (colour, depth, poses)
+        return self._listing
+
+    def _paths(self):
+        return self._list()[0], self._list()[1]
+
+    def _poses(self, n):
+        return self._list()[2]
 
 
 class SyntheticSource(FrameSource):
