@@ -86,8 +86,38 @@ def vis_mask_goldens():
     return out
 
 
+def visbased_goldens():
+    """keyframe_selection_overlap_visbased (utils/keyframe_selection.py:121-229), the variant the main loop uses."""
+    import contextlib
+    import io
+    from utils.keyframe_selection import keyframe_selection_overlap_visbased
+    from vtgaussian_slam_b200 import synthetic
+    out = {}
+    W, H, K = synthetic.intrinsics("tum_fr1", 80, 60)
+    poses = synthetic.trajectory(10, step_m=0.15, step_deg=7.0, seed=12)
+    cur = synthetic.make_frame("tum_fr1", 80, 60, seed=0, c2w=poses[4])
+    gt_depth = torch.tensor(cur["depth"])
+    gt_depth[0, 50:, :20] = 0.0
+    intr = torch.tensor(K.astype(np.float32))
+    w2c = torch.tensor(np.linalg.inv(poses[4]), dtype=torch.float32)
+    ids = [i for i in range(10) if i != 4]
+    depths = [synthetic.make_frame("tum_fr1", 80, 60, seed=30 + i, c2w=poses[i])["depth"] for i in ids]
+    mk = lambda: [dict(est_w2c=torch.tensor(np.linalg.inv(poses[i]), dtype=torch.float32), depth=torch.tensor(d)) for i, d in zip(ids, depths)]
+    with contextlib.redirect_stdout(io.StringIO()):                # the reference prints its ranking
+        ranked = keyframe_selection_overlap_visbased(gt_depth, w2c, intr, mk(), 3, edge_value=6, save_percent=True, kf_depth_thresh=0.02)
+        sel, early = keyframe_selection_overlap_visbased(gt_depth, w2c, intr, mk(), 3, edge_value=6, kf_depth_thresh=0.02, earliest_thres=0.3)
+        sel2, early2 = keyframe_selection_overlap_visbased(gt_depth, w2c, intr, mk(), 3, edge_value=6, kf_depth_thresh=0.02, earliest_thres=0.99)
+    out["vb.depth"], out["vb.K"], out["vb.poses"], out["vb.kf_depths"] = gt_depth.numpy(), intr.numpy(), poses, np.stack(depths)
+    out["vb.ranked_ids"] = np.array([r["id"] for r in ranked])
+    out["vb.ranked_frac"] = np.array([float(r["percent_inside"]) for r in ranked], np.float32)
+    out["vb.sel"], out["vb.early"], out["vb.sel2"], out["vb.early2"] = np.array(sel), np.array(early), np.array(sel2), np.array(early2)
+    return out
+
+
 if __name__ == "__main__":
     g = dict(np.load(os.path.join(HERE, "keyframes_golden.npz")))
     g.update(vis_mask_goldens())
+    g.update(visbased_goldens())
+    print({k: v for k, v in g.items() if k in ("vb.sel", "vb.early", "vb.early2", "vb.ranked_frac")})
     np.savez_compressed(os.path.join(HERE, "keyframes_golden.npz"), **g)
     print({k: float(v.mean()) for k, v in g.items() if k.startswith("vis.mask")})

@@ -65,3 +65,24 @@ def test_visibility_mask_matches_the_reference():
     assert both.shape == (1, 72, 96)
     assert ((both[0].numpy()) != (G["vis.mask0"] | G["vis.mask1"] | G["vis.mask2"])).mean() < 5e-4
     assert 0.3 < float(both.float().mean()) < 1.0
+
+
+def test_visibility_based_selection_matches_the_reference():
+    depth, K, poses = torch.tensor(G["vb.depth"]), torch.tensor(G["vb.K"]), G["vb.poses"]
+    w2c = torch.tensor(np.linalg.inv(poses[4]), dtype=torch.float32)
+    ids = [i for i in range(10) if i != 4]
+    kfs = [dict(est_w2c=torch.tensor(np.linalg.inv(poses[i]), dtype=torch.float32), depth=torch.tensor(d)) for i, d in zip(ids, G["vb.kf_depths"])]
+    ranked = keyframes.keyframe_selection_overlap_visbased(depth, w2c, K, kfs, 3, edge_value=6, save_percent=True, kf_depth_thresh=0.02)
+    assert [r["id"] for r in ranked] == list(G["vb.ranked_ids"])
+    assert np.allclose([float(r["percent_inside"]) for r in ranked], G["vb.ranked_frac"], atol=3e-4)      # knife-edge pixels of the depth test
+    sel, early = keyframes.keyframe_selection_overlap_visbased(depth, w2c, K, kfs, 3, edge_value=6, kf_depth_thresh=0.02, earliest_thres=0.3)
+    assert sel == list(G["vb.sel"]) and early == list(G["vb.early"])
+    sel2, early2 = keyframes.keyframe_selection_overlap_visbased(depth, w2c, K, kfs, 3, edge_value=6, kf_depth_thresh=0.02, earliest_thres=0.99)
+    assert sel2 == list(G["vb.sel2"]) and early2 == list(G["vb.early2"]) == sel2                          # nothing above the threshold
+    # chunking over keyframes does not change the result
+    pts = keyframes.backproject_samples(depth, K, w2c, torch.stack(torch.where(depth[0] > 0), dim=1))
+    stack = torch.stack([k["est_w2c"] for k in kfs])
+    deps = torch.stack([k["depth"] for k in kfs])
+    a = keyframes.overlap_fractions_visible(pts, K, stack, deps, 80, 60, 6, 0.02, chunk=2)
+    b = keyframes.overlap_fractions_visible(pts, K, stack, deps, 80, 60, 6, 0.02, chunk=64)
+    assert torch.equal(a, b)

@@ -101,3 +101,49 @@ def tracking_vis_mask(gt_depth, intrinsics, curr_w2c, overlaps, vis_mask_thres=0
     for w2c, depth in overlaps:
         out |= get_vis_mask(w2c, pts, intrinsics, depth, vis_mask_thres, H, W)
     return out[None]
+
+
+def overlap_fractions_visible(pts, intrinsics, keyframe_w2c, keyframe_depth, width, height, edge=20, kf_depth_thresh=0.01,
+                              chunk=8):
+    """Like overlap_fractions, with the keyframe's own depth map deciding visibility (reference
+    keyframe_selection_overlap_visbased, utils/keyframe_selection.py:121-229): a point counts when it projects
+    inside the margins AND the keyframe's depth sampled there agrees with its projected depth to within
+    kf_depth_thresh x the smaller of the two.  keyframe_depth[Kf,1,H,W]; keyframes are processed `chunk` at a time."""
+    hom = torch.cat([pts, torch.ones_like(pts[:, :1])], dim=1)
+    out = []
+    for a in range(0, keyframe_w2c.shape[0], chunk):
+        w2c, dep = keyframe_w2c[a:a + chunk], keyframe_depth[a:a + chunk].to(pts.device)
+        cam = (w2c @ hom.T).transpose(1, 2)[..., :3]
+        proj = cam @ intrinsics.T
+        z = proj[..., 2] + 1e-5
+        u, v = proj[..., 0] / z, proj[..., 1] / z
+        inside = (u < width - edge) & (u > edge) & (v < height - edge) & (v > edge) & (z > 0)
+        grid = torch.stack((u / (width - 1) * 2.0 - 1.0, v / (height - 1) * 2.0 - 1.0), dim=-1)[:, None]        # [c, 1, n, 2]
+        seen = torch.nn.functional.grid_sample(dep.reshape(-1, 1, height, width), grid, padding_mode="zeros",
+                                               align_corners=True)[:, 0, 0]
+        visible = torch.abs(seen - z) < kf_depth_thresh * torch.minimum(seen, z)
+        out.append((inside & visible).sum(dim=1) / max(pts.shape[0], 1))
+    return torch.cat(out) if out else torch.zeros(0, device=pts.device)
+
+
+def keyframe_selection_overlap_visbased(gt_depth, w2c, intrinsics, keyframe_list, k, pixels=1600, edge_value=20,
+                                        save_percent=False, kf_depth_thresh=0.01, earliest_thres=0.5):
+    """Signature and results of the reference's function of the same name (the variant its main loop imports): every
+    valid-depth pixel is used (`pixels` is ignored, as upstream), keyframes need 'est_w2c' and 'depth';
+    -> (ids of the k best-overlapping keyframes, [the LOWEST-ranked keyframe whose overlap still exceeds
+    earliest_thres] or, if none does, the first list again)."""
+    width, height = gt_depth.shape[2], gt_depth.shape[1]
+    valid = torch.stack(torch.where(gt_depth[0] > 0), dim=1)
+    pts = backproject_samples(gt_depth, intrinsics, w2c, valid)
+    if not keyframe_list:
+        return [] if save_percent else ([], [])
+    stack = torch.stack([kf["est_w2c"].to(pts.device) for kf in keyframe_list])
+    depths = torch.stack([kf["depth"].reshape(1, height, width) for kf in keyframe_list])
+    frac = overlap_fractions_visible(pts, intrinsics[:3, :3].to(pts.device), stack, depths, width, height, edge_value, kf_depth_thresh)
+    order = torch.sort(frac, descending=True, stable=True).indices.tolist()
+    ranked = [{"id": i, "percent_inside": frac[i]} for i in order]
+    if save_percent:
+        return ranked
+    selected = [r["id"] for r in ranked if r["percent_inside"] > 0.0][:k]
+    earliest = [r["id"] for r in ranked if r["percent_inside"] > earliest_thres][-1:]
+    return selected, (earliest if earliest else selected)
