@@ -312,6 +312,14 @@ def run_ours(args, wl):
         "per_kernel_us": {k: round(t * 1e3 / n, 2) for k, (n, t) in prof.items()},
     }
 
+    if args.kernels_only:
+        if rank == 0:
+            print(json.dumps({"value": 1e3 / ms_per_step, "ms_per_step": ms_per_step, "per_kernel_us": roofline["per_kernel_us"],
+                              "lib": os.environ.get("VTGS_LIB_PATH", "default")}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
     # ---- e2e (a): the repo's own tracking API with host buffers, at N GPUs ---------------------------
     # TrackingSolver.step() (graph replay; band-sharded + all-reduce at N > 1); every step uploads its frame from
     # pinned host memory on a copy stream (double-buffered staging, then a device copy into the solver's target
@@ -567,6 +575,7 @@ def main():
     ap.add_argument("--workload", choices=["c2", "c5"], default="c2",
                     help="c2 (default, the headline): Replica 1200x680, ~1 M Gaussians; c5 (side benchmark): ScanNet++-shaped 1752x1168, ~8 M Gaussians in 4 sections")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--kernels-only", action="store_true", help="kernel experiments: device-timed value + per-kernel durations only")
     ap.add_argument("--keyframes", type=int, default=8, help="--mode mapping: keyframes per mapping iteration (configs[2]: 8)")
     ap.add_argument("--mode", default="tracking", choices=["tracking", "mapping"],
                     help="tracking = configs[1] (the driver's line); mapping = keyframe-sharded side benchmark")

@@ -7,7 +7,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libvtgs_cuda.so")
+# VTGS_LIB_PATH: load another build of the same library (kernel experiments: csrc/Makefile OUT= / EXTRA=)
+LIB_PATH = os.environ.get("VTGS_LIB_PATH") or os.path.join(_HERE, "lib", "libvtgs_cuda.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 GEOM_RECORD_BYTES = 64

@@ -7,13 +7,9 @@
 // (utils/slam_helpers.py:217-234), the activations (:127-160) and transform_to_frame
 // (:323-385) down to the Gaussian parameters and the 7 camera-pose numbers.
 //
-// K6' design: the upstream kernel issues 9-10 global float atomics per contributing
-// (pixel, Gaussian) pair.  Here a warp walks the survivors of its 8x4-pixel region in
-// lock-step (same ballot culling as the forward), reduces the per-pixel terms across the
-// warp with a transposed butterfly (~4 instructions per value instead of 10), adds the
-// warp total to a per-tile shared-memory accumulator, and the tile emits ONE vectorised
-// global reduction per (tile, Gaussian) pair at the end of each staged batch.
+// K6' design: see the comment above blend_backward_kernel.
 #include <algorithm>
+#include <atomic>
 
 #include "blend_common.cuh"
 #include "kernels.h"
@@ -82,7 +78,10 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[16], int lane)
 // Groups in which no pixel of the region blended anything are skipped before their records are fetched.
 // Upstream: 9-10 global float atomics per contributing (pixel, splat) pair.
 constexpr int BWD_WARPS = 2;          // warps (regions) per block: a tile is covered by 8 / BWD_WARPS blocks
-template <bool FUSED>
+// BG:   the background is not black (one more term in dL/dalpha); the reference always renders on black.
+// LITE: the caller wants no colour / opacity gradients (tracking: only the pose gradient is formed, from the
+//       mean2D / conic / depth-channel sums) -- P3 drops the r,g,b and opacity sums.
+template <bool FUSED, bool BG, bool LITE>
 __global__ void __launch_bounds__(32 * BWD_WARPS, 20 / BWD_WARPS)
 blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __restrict__ ranges,
                       const uint2* __restrict__ region_pairs, const uint32_t* __restrict__ region_cnt,
@@ -125,15 +124,13 @@ blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __re
     for (int ch = 0; ch < NCH; ++ch) dpix[ch] = inside ? dL_dpix[ch * P + pid] : 0.0f;
     A.dpix[lane] = make_float4(dpix[0], dpix[1], dpix[2], dpix[3]);
     A.pxy[lane] = make_float2(pxf, pyf);
-    const float bg_dot = cam.bg[0] * dpix[0] + cam.bg[1] * dpix[1] + cam.bg[2] * dpix[2];
-    const bool has_bg = cam.bg[0] != 0.0f || cam.bg[1] != 0.0f || cam.bg[2] != 0.0f;
+    const float bg_dot = BG ? cam.bg[0] * dpix[0] + cam.bg[1] * dpix[1] + cam.bg[2] * dpix[2] : 0.0f;
     const float half_w = 0.5f * cam.W, half_h = 0.5f * cam.H;
 
+    // per-pixel recursion state: upstream's accum[ch] / last_color[ch] only ever enter dL/dalpha through their dot
+    // product with dL/dpixel, and the recursion is linear -- carry the two scalars instead of 2 x NCH values
     float T = T_final;
-    float accum[NCH], lastc[NCH];
-#pragma unroll
-    for (int ch = 0; ch < NCH; ++ch) { accum[ch] = 0.0f; lastc[ch] = 0.0f; }
-    float last_alpha = 0.0f;
+    float acc_dot = 0.0f, last_dot = 0.0f, last_alpha = 0.0f;
 
     // software pipeline over the forward's groups, last to first: masks two groups ahead, list entries and
     // records one group ahead (only for groups with at least one blended splat)
@@ -175,16 +172,13 @@ blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __re
             const float col[4] = {q2.x, q2.y, q2.z, q2.w};
             const float inv = rcp_approx(1.0f - alpha);             // 1 - alpha in [0.01, 1]
             T = T * inv;
-            float dL_dalpha = 0.0f;
-#pragma unroll
-            for (int ch = 0; ch < NCH; ++ch) {
-                accum[ch] = last_alpha * lastc[ch] + (1.0f - last_alpha) * accum[ch];
-                lastc[ch] = col[ch];
-                dL_dalpha += (col[ch] - accum[ch]) * dpix[ch];
-            }
-            dL_dalpha *= T;
+            float cdot = col[0] * dpix[0] + col[1] * dpix[1] + col[2] * dpix[2];
+            if (NCH == 4) cdot += col[3] * dpix[3];
+            acc_dot = last_alpha * last_dot + (1.0f - last_alpha) * acc_dot;
+            last_dot = cdot;
+            float dL_dalpha = (cdot - acc_dot) * T;
             last_alpha = alpha;
-            if (has_bg) dL_dalpha -= T_final * inv * bg_dot;      // (warp-uniform: the reference renders on black)
+            if (BG) dL_dalpha -= T_final * inv * bg_dot;
             return make_float2(alpha * T, Gv * dL_dalpha);
         };
         while (m) {
@@ -216,10 +210,11 @@ blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __re
             const float4 dp = A.dpix[p];
             const float2 pc = A.pxy[p];
             const float dx = cur.a.x - pc.x, dy = cur.a.y - pc.y;
-            c0 = fmaf(cw.x, dp.x, c0); c1 = fmaf(cw.x, dp.y, c1); c2 = fmaf(cw.x, dp.z, c2);
+            if (!LITE) { c0 = fmaf(cw.x, dp.x, c0); c1 = fmaf(cw.x, dp.y, c1); c2 = fmaf(cw.x, dp.z, c2); }
             if (NCH == 4) c3 = fmaf(cw.x, dp.w, c3);
             const float gg = cw.y, gx_ = gg * dx, gy_ = gg * dy;
-            s0 += gg; sx += gx_; sy += gy_;
+            if (!LITE) s0 += gg;
+            sx += gx_; sy += gy_;
             sxx = fmaf(gx_, dx, sxx); sxy = fmaf(gx_, dy, sxy); syy = fmaf(gy_, dy, syy);
         }
         // ---- P4: finalize (dL/dG * G = opacity * g0) and one vector reduction per (region, splat)
@@ -230,9 +225,14 @@ blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __re
             const float v2 = -0.5f * o * sxx, v3 = -0.5f * o * sxy, v4 = -0.5f * o * syy;
             float* dst = grad_geom + (size_t)cur_ent.x * VTGS_GRAD_GEOM_FLOATS;
             asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v0), "f"(v1), "f"(v2), "f"(v3) : "memory");
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(v4), "f"(s0), "f"(c0), "f"(c1) : "memory");
-            if (NCH == 4) asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(dst + 8), "f"(c2), "f"(c3) : "memory");
-            else atomicAdd(dst + 8, c2);
+            if (LITE) {                 // slots 5..8 (opacity, r, g, b) stay zero
+                atomicAdd(dst + 4, v4);
+                if (NCH == 4) atomicAdd(dst + 9, c3);
+            } else {
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(v4), "f"(s0), "f"(c0), "f"(c1) : "memory");
+                if (NCH == 4) asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(dst + 8), "f"(c2), "f"(c3) : "memory");
+                else atomicAdd(dst + 8, c2);
+            }
         }
     }
 }
@@ -376,15 +376,22 @@ preprocess_backward_kernel(const __grid_constant__ CamConst cam, int64_t N,
     for (int k = 0; k < 4; ++k) dL_drot[4 * i + k] = dq[k];
 }
 
-// dynamic shared memory of blend_backward_kernel: 8 x (group 1536 + cells 8448 + dpix 512 + pxy 256) bytes
+// dynamic shared memory of blend_backward_kernel
+// per warp: group 1536 + cells 8448 + dpix 512 + pxy 256 bytes
 constexpr int BWD_SMEM = BWD_WARPS * (int)(sizeof(GroupSmem) + 32 * 33 * sizeof(float2) + 32 * sizeof(float4) + 32 * sizeof(float2));
-static int ensure_bwd_smem() {
-    static bool done = false;
-    if (!done) {
-        VTGS_CUDA_CHECK(cudaFuncSetAttribute(blend_backward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
-        VTGS_CUDA_CHECK(cudaFuncSetAttribute(blend_backward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
-        done = true;
+template <bool FUSED, bool BG, bool LITE>
+static int launch_blend_backward(int blocks, cudaStream_t stream, const CamConst& cam, const VtgsBuffers* buf, const GeomRecord* geom,
+                                 const float* dL_dpix) {
+    static std::atomic<uint64_t> done{0};
+    if (first_call_on_device(done)) {
+        VTGS_CUDA_CHECK(cudaFuncSetAttribute(blend_backward_kernel<FUSED, BG, LITE>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
+        VTGS_CUDA_CHECK(cudaFuncSetAttribute(blend_backward_kernel<FUSED, BG, LITE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     }
+    VTGS_PROF("blend_backward_kernel", stream);
+    blend_backward_kernel<FUSED, BG, LITE><<<blocks, 32 * BWD_WARPS, BWD_SMEM, stream>>>(
+        cam, buf->tile_ranges, reinterpret_cast<const uint2*>(buf->region_pairs), buf->region_cnt, buf->region_masks, buf->region_done,
+        geom, buf->final_T, dL_dpix, buf->grad_geom);
+    VTGS_LAUNCH_CHECK();
     return VTGS_OK;
 }
 
@@ -399,11 +406,11 @@ int launch_backward(const VtgsCamera* camera, int64_t N,
     const GeomRecord* geom = reinterpret_cast<const GeomRecord*>(buf->geom);
     const int band_tiles = (cam.row1 - cam.row0) * cam.gx;
     if (N <= 0) return VTGS_OK;
-    if (int e = ensure_bwd_smem()) return e;
     if (band_tiles > 0) {
-        { VTGS_PROF("blend_backward_kernel", stream); blend_backward_kernel<false><<<band_tiles * (8 / BWD_WARPS), 32 * BWD_WARPS, BWD_SMEM, stream>>>(cam, buf->tile_ranges, reinterpret_cast<const uint2*>(buf->region_pairs), buf->region_cnt, buf->region_masks, buf->region_done, geom, buf->final_T,
-                                                                      dL_dout_color, buf->grad_geom); }
-        VTGS_LAUNCH_CHECK();
+        const bool has_bg = cam.bg[0] != 0.0f || cam.bg[1] != 0.0f || cam.bg[2] != 0.0f;
+        const int blocks = band_tiles * (8 / BWD_WARPS);
+        if (int e = has_bg ? launch_blend_backward<false, true, false>(blocks, stream, cam, buf, geom, dL_dout_color)
+                           : launch_blend_backward<false, false, false>(blocks, stream, cam, buf, geom, dL_dout_color)) return e;
     }
     { VTGS_PROF("preprocess_backward_kernel", stream); preprocess_backward_kernel<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(cam, N, means3D, scales, rotations, nullptr, geom,
                                                                                buf->grad_geom, dL_dmeans2D, dL_dcolors, dL_dopacity,
@@ -641,12 +648,18 @@ int launch_fused_backward(const VtgsCamera* camera, const VtgsParams* params, co
     if (want_pose && grads->pose_scratch == nullptr) { set_error("pose gradients need pose_scratch"); return VTGS_E_INVALID; }
     // persistent K7' grid: 148 SMs x 2 resident blocks x 2 waves (fixed, so the partial-sum layout is deterministic)
     const int blocks = (int)std::min<int64_t>((N + 255) / 256, 148 * 4);
-    if (int e = ensure_bwd_smem()) return e;
     if (N > 0) {
         if (band_tiles > 0) {
-            { VTGS_PROF("blend_backward_kernel", stream); blend_backward_kernel<true><<<band_tiles * (8 / BWD_WARPS), 32 * BWD_WARPS, BWD_SMEM, stream>>>(cam, buf->tile_ranges, reinterpret_cast<const uint2*>(buf->region_pairs), buf->region_cnt, buf->region_masks, buf->region_done, geom, buf->final_T,
-                                                                         dL_dimage4, buf->grad_geom); }
-            VTGS_LAUNCH_CHECK();
+            const bool has_bg = cam.bg[0] != 0.0f || cam.bg[1] != 0.0f || cam.bg[2] != 0.0f;
+            // tracking asks for the pose gradient only: no colour / opacity sums are formed (K7' never reads them then)
+            const bool lite = grads->rgb_colors == nullptr && grads->logit_opacities == nullptr;
+            const int bblocks = band_tiles * (8 / BWD_WARPS);
+            int e;
+            if (has_bg) e = lite ? launch_blend_backward<true, true, true>(bblocks, stream, cam, buf, geom, dL_dimage4)
+                                 : launch_blend_backward<true, true, false>(bblocks, stream, cam, buf, geom, dL_dimage4);
+            else e = lite ? launch_blend_backward<true, false, true>(bblocks, stream, cam, buf, geom, dL_dimage4)
+                          : launch_blend_backward<true, false, false>(bblocks, stream, cam, buf, geom, dL_dimage4);
+            if (e) return e;
         }
         unsigned int* ticket = reinterpret_cast<unsigned int*>(grads->pose_scratch ? grads->pose_scratch + (size_t)blocks * POSE_TERMS : nullptr);
         const uint32_t* band_touch = band_tiles < cam.gx * cam.gy ? buf->tiles_touched : nullptr;

@@ -28,6 +28,16 @@ void set_error(const char* fmt, ...);
     } while (0)
 #define VTGS_LAUNCH_CHECK() VTGS_CUDA_CHECK(cudaGetLastError())
 
+// One-time kernel attribute setup PER DEVICE (a process may drive several GPUs): true for the first caller on the
+// current device.  `mask` is a function-local static std::atomic<uint64_t>.
+template <typename AtomicU64>
+inline bool first_call_on_device(AtomicU64& mask) {
+    int d = 0;
+    cudaGetDevice(&d);
+    const uint64_t bit = 1ull << (d & 63);
+    return (mask.fetch_or(bit) & bit) == 0;
+}
+
 // ---- packed per-Gaussian render record (VTGS_GEOM_RECORD_BYTES = 64) ---------------------
 //   q0 = {px, py, hx, hy}            pixel centre and the half extents of the alpha >= 1/255 ellipse's box
 //   q1 = {A, B, C, opacity}          conic and opacity
@@ -117,6 +127,12 @@ __device__ __forceinline__ float ex2_approx(float x) {
 __device__ __forceinline__ float rcp_approx(float x) {
     float y;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
 

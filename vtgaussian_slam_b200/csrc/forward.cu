@@ -20,6 +20,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
+
 #include "blend_common.cuh"
 #include "kernels.h"
 
@@ -772,32 +774,48 @@ tile_sort_kernel(const __grid_constant__ CamConst cam, const uint32_t* __restric
     build_region_lists(sorted, n, b, tile, region_pairs, region_cnt);
 }
 
-#ifdef VTGS_STATS
-__device__ unsigned long long vtgs_stats[8];
-#endif
 // =============================== K5': forward blend ========================================
-// Block = one 16x16 tile, 8 INDEPENDENT warps (no block barrier): warp w owns pixel region w and walks
-// that region's list (built by the sort kernel) in groups of 32 splats -- software-prefetched gathers of
-// the 64-byte records, lane-transposed blending (blend_common.cuh): P1 lane = splat from registers,
-// P2 lane = pixel from the group staged in shared memory.
+// Block = FWD_WARPS INDEPENDENT warps (no block barrier); a warp owns one 8x4-pixel region of a tile and walks that
+// region's list (built by the sort kernel) in CHUNKS of FWD_GC groups of 32 splats (blend_common.cuh):
+//   stage  lane = splat : software-prefetched gathers of the 64-byte records -> shared memory (40 B per splat);
+//   P1     lane = splat : row-interval test of the region's 32 pixels, masks transposed to pixel lanes;
+//   P2     lane = pixel : every lane walks ITS OWN masks of the whole chunk front to back without re-converging at
+//                         group boundaries -- exact power / alpha / T tests and the blend in list order, so
+//                         n_contrib, final_T and the planes are bit-identical to the one-splat-at-a-time oracle;
+//                         the masks are reduced in place to the splats actually blended (consumed by K6').
 // Planes: API mode 3 colours (+ depth plane), fused mode r,g,b,z,sil,z^2.
-constexpr int FWD_WARPS = 4;          // warps (regions) per block: a tile is covered by 8 / FWD_WARPS blocks
+// Cold path of the pixel walk: the pixel saturated at `bit` of word gg -- that splat and every later one of the chunk
+// were not applied.  col = &pm[0][lane] (words are 32 apart).
+__device__ __noinline__ void clear_mask_bit(uint32_t* word, uint32_t bit) { *word &= ~bit; }
+__device__ __noinline__ void truncate_masks(uint32_t* col, int gg, int gc, uint32_t bit) {
+    col[gg * 32] &= bit - 1u;
+    for (int g2 = gg + 1; g2 < gc; ++g2) col[g2 * 32] = 0u;
+}
+
+#ifndef VTGS_FWD_WARPS
+#define VTGS_FWD_WARPS 4
+#endif
+#ifndef VTGS_FWD_GC
+#define VTGS_FWD_GC 6
+#endif
+constexpr int FWD_WARPS = VTGS_FWD_WARPS;   // warps (regions) per block: a tile is covered by 8 / FWD_WARPS blocks
+constexpr int FWD_GC = VTGS_FWD_GC;         // groups per chunk: 1408 B of shared memory per group and warp
 template <bool FUSED>
-__global__ void __launch_bounds__(32 * FWD_WARPS, 24 / FWD_WARPS)
+__global__ void __launch_bounds__(32 * FWD_WARPS, (FWD_GC <= 6 ? 24 : 20) / FWD_WARPS)
 blend_forward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __restrict__ ranges,
                      const uint2* __restrict__ region_pairs, const uint32_t* __restrict__ region_cnt,
                      uint32_t* __restrict__ region_masks, uint32_t* __restrict__ region_done,
                      const GeomRecord* __restrict__ geom,
                      float* __restrict__ out_color, float* __restrict__ out_depth,
                      float* __restrict__ final_T, uint32_t* __restrict__ n_contrib) {
-    __shared__ GroupSmem Gs[FWD_WARPS];
+    __shared__ ChunkSmem<FWD_GC> Ws[FWD_WARPS];
 
     constexpr int BPT = 8 / FWD_WARPS;                                  // blocks per tile
     const int tile = cam.row0 * cam.gx + blockIdx.x / BPT;
     const int tile_x = tile % cam.gx, tile_y = tile / cam.gx;
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = (blockIdx.x % BPT) * FWD_WARPS + (tid >> 5);       // region index inside the tile
-    GroupSmem& G = Gs[tid >> 5];
+    ChunkSmem<FWD_GC>& S = Ws[tid >> 5];
     const int rx0 = tile_x * 16 + (warp % REGIONS_X) * REGION_W, ry0 = tile_y * 16 + (warp / REGIONS_X) * REGION_H;
     const int pix_x = rx0 + (lane % REGION_W), pix_y = ry0 + (lane / REGION_W);
     const bool inside = pix_x < cam.W && pix_y < cam.H;
@@ -812,32 +830,8 @@ blend_forward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __res
 
     float T = 1.0f;
     float C0 = 0.f, C1 = 0.f, C2 = 0.f, C3 = 0.f, C4 = 0.f, C5 = 0.f;
-    uint32_t last = 0, applied = 0;
+    int last_k = -1;                    // region-list index of the last splat this pixel blended
     bool done = !inside;
-#ifdef VTGS_STATS
-    int st_c2 = 0, st_c4 = 0;
-#endif
-
-    // zz: the splat's z^2 (fused planes), staged once per splat in the slot of GroupSmem.b that P2 does not read;
-    // bit: the splat's bit in the group (isolated from the walk mask, no variable shift)
-    auto blend_one = [&](const float4 a, const float alpha, const int e, const float zz, const uint32_t bit) -> bool {
-        if (alpha < VTGS_ALPHA_MIN) return true;
-        const float test_T = fmul(T, fsub(1.0f, alpha));
-        if (test_T < VTGS_T_MIN) { done = true; return false; }
-        const float4 q2 = G.c[e];
-        C0 = ffma(fmul(q2.x, alpha), T, C0);
-        C1 = ffma(fmul(q2.y, alpha), T, C1);
-        C2 = ffma(fmul(q2.z, alpha), T, C2);
-        C3 = ffma(fmul(q2.w, alpha), T, C3);
-        if (FUSED) {
-            C4 = ffma(alpha, T, C4);                               // 1.0 * alpha * T
-            C5 = ffma(fmul(zz, alpha), T, C5);
-        }
-        T = test_T;
-        last = __float_as_uint(a.z);
-        applied |= bit;
-        return true;
-    };
 
     // software pipeline: list entries two groups ahead, records one group ahead
     uint2 ent_next = lane < n ? list[lane] : make_uint2(0u, 0u);
@@ -845,75 +839,79 @@ blend_forward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __res
     SplatRegs nxt;
     load_splat(nxt, lane < n, geom, ent_next);
     bool all_done = __all_sync(VTGS_FULL_MASK, done);
-    int g = 0;
-    for (; g < ngroups && !all_done; ++g) {
-        const SplatRegs cur = nxt;
-        const int k = g * 32 + lane;
-        const bool have = k < n;
-        ent_next = ent_next2;
-        ent_next2 = (k + 64) < n ? list[k + 64] : make_uint2(0u, 0u);
-        load_splat(nxt, (k + 32) < n, geom, ent_next);
-        __syncwarp();                                   // the previous group's P2 reads are complete
-        if (have) {
-            G.a[lane] = cur.a;
-            G.b[lane] = make_float4(cur.b.x, cur.b.y, cur.b.z, FUSED ? fmul(cur.c.w, cur.c.w) : 0.0f);     // .w: z^2 (pthr stays in registers for P1)
-            G.c[lane] = cur.c;
+    int g0 = 0;
+    for (; g0 < ngroups && !all_done; g0 += FWD_GC) {
+        const int gc = min(FWD_GC, ngroups - g0);
+        __syncwarp();                                   // the previous chunk's reads of S are complete
+        // ---- stage + P1, lane = splat
+        for (int gg = 0; gg < gc; ++gg) {
+            const SplatRegs cur = nxt;
+            const int k = (g0 + gg) * 32 + lane;
+            const bool have = k < n;
+            ent_next = ent_next2;
+            ent_next2 = (k + 64) < n ? list[k + 64] : make_uint2(0u, 0u);
+            load_splat(nxt, (k + 32) < n, geom, ent_next);
+            uint32_t em = 0u;
+            if (have) {
+                S.r0[gg * 32 + lane] = make_float4(cur.a.x, cur.a.y, cur.b.x, cur.b.y);
+                S.r1[gg * 32 + lane] = make_float4(cur.b.z, cur.a.w, cur.c.x, cur.c.y);
+                S.r2[gg * 32 + lane] = make_float2(cur.c.z, cur.c.w);
+                em = p1_rows(cur.a.x, cur.a.y, cur.b.x, cur.b.y, cur.b.z, cur.b.w, x0f, y0f);
+            }
+            const uint32_t m = warp_transpose_bits(em, lane);
+            S.pm[gg][lane] = done ? 0u : m;
         }
         __syncwarp();
-        uint32_t emask;
-        uint32_t m = p1_masks(have, cur.a, cur.b, x0f, y0f, lane, emask);       // P1: lane = splat
-        if (done) m = 0;
-        // P2: lane = pixel.  Two splats per trip: loads / power / exp are independent, only the T and
-        // colour updates are ordered.
-        while (m) {
-            const int ea = __ffs(m) - 1;
-            const uint32_t bit_a = m & (0u - m);
-            m ^= bit_a;
-            const bool two = m != 0;
-            const int eb = two ? __ffs(m) - 1 : ea;
-            const uint32_t bit_b = m & (0u - m);          // 0 when m == 0
-            m ^= bit_b;
-            const float4 a0 = G.a[ea], a1 = G.b[ea];
-            const float4 b0 = G.a[eb], b1 = G.b[eb];
-            // power is in [pthr, 0] by P1 (same arithmetic)
-            const float pa = power_of(a1.x, a1.y, a1.z, fsub(a0.x, pxf), fsub(a0.y, pyf));
-            const float pb = power_of(b1.x, b1.y, b1.z, fsub(b0.x, pxf), fsub(b0.y, pyf));
-            // fused mode: opacity = sigmoid(.) < 1, so pthr >= log(1/255) - 1e-3 and power in [-5.6, 0]: no clamp needed
-            const float alpha_a = fminf(VTGS_ALPHA_MAX, fmul(a0.w, vexpf<!FUSED>(pa)));
-            const float alpha_b = fminf(VTGS_ALPHA_MAX, fmul(b0.w, vexpf<!FUSED>(pb)));
-            if (!blend_one(a0, alpha_a, ea, a1.w, bit_a)) break;
-            if (two && !blend_one(b0, alpha_b, eb, b1.w, bit_b)) break;
-        }
-        masks[g * 32 + lane] = applied;                 // which splats of this group each pixel blended (for K6')
-#ifdef VTGS_STATS
-        {
-            const int c = __popc(applied);
-            st_c2 += c; st_c4 += c;
-            auto wmax = [&](int v) { for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(VTGS_FULL_MASK, v, o)); return v; };
-            auto wsum = [&](int v) { for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(VTGS_FULL_MASK, v, o); return v; };
-            const int mx1 = wmax(c), tot = wsum(c);
-            int mx2 = 0, mx4 = 0;
-            if ((g & 1) == 1) { mx2 = wmax(st_c2); st_c2 = 0; }
-            if ((g & 3) == 3) { mx4 = wmax(st_c4); st_c4 = 0; }
-            if (lane == 0) {
-                atomicAdd(&vtgs_stats[0], (unsigned long long)tot);
-                atomicAdd(&vtgs_stats[1], (unsigned long long)mx1);
-                atomicAdd(&vtgs_stats[2], (unsigned long long)mx2);
-                atomicAdd(&vtgs_stats[3], (unsigned long long)mx4);
-                atomicAdd(&vtgs_stats[4], 1ull);
+        // ---- P2, lane = pixel: one pass over the chunk's masks, no re-convergence between groups.  The mask corrections
+        // (P1's superset / the T test rejecting a splat) are cold and kept out of line.
+        if (!done) {
+            int gg = 0, lk = -1;
+            uint32_t m = S.pm[0][lane];
+            for (;;) {
+                while (m == 0u && ++gg < gc) m = S.pm[gg][lane];
+                if (m == 0u) break;
+                const uint32_t bit = m & (0u - m);
+                m ^= bit;
+                const int idx = gg * 32 + msb_index(bit);
+                const float4 q0 = S.r0[idx], q1 = S.r1[idx];
+                const float power = power_of(q0.z, q0.w, q1.x, fsub(q0.x, pxf), fsub(q0.y, pyf));
+                // fused mode: opacity = sigmoid(.) < 1 and power >= pthr - margins ~ -5.6: no clamp needed (same bits)
+                const float alpha = fminf(VTGS_ALPHA_MAX, fmul(q1.y, vexpf<!FUSED>(power)));
+                if (power > 0.0f || alpha < VTGS_ALPHA_MIN) {        // P1 is a superset: drop the pair from the mask
+                    clear_mask_bit(&S.pm[gg][lane], bit);
+                    continue;
+                }
+                const float test_T = fmul(T, fsub(1.0f, alpha));
+                if (test_T < VTGS_T_MIN) {                           // saturated: this and all later splats are not applied
+                    truncate_masks(&S.pm[0][lane], gg, gc, bit);
+                    done = true;
+                    break;
+                }
+                const float2 q2 = S.r2[idx];
+                C0 = ffma(fmul(q1.z, alpha), T, C0);
+                C1 = ffma(fmul(q1.w, alpha), T, C1);
+                C2 = ffma(fmul(q2.x, alpha), T, C2);
+                C3 = ffma(fmul(q2.y, alpha), T, C3);
+                if (FUSED) {
+                    C4 = ffma(alpha, T, C4);                               // 1.0 * alpha * T
+                    C5 = ffma(fmul(fmul(q2.y, q2.y), alpha), T, C5);       // z^2 channel
+                }
+                T = test_T;
+                lk = idx;
             }
+            if (lk >= 0) last_k = g0 * 32 + lk;
         }
-#endif
-        applied = 0;
+        __syncwarp();
+        for (int gg = 0; gg < gc; ++gg) masks[(g0 + gg) * 32 + lane] = S.pm[gg][lane];      // coalesced, for K6'
         all_done = __all_sync(VTGS_FULL_MASK, done);
     }
-    if (lane == 0) region_done[(size_t)tile * 8 + warp] = (uint32_t)g;
+    if (lane == 0) region_done[(size_t)tile * 8 + warp] = (uint32_t)min(g0, ngroups);
 
     if (inside) {
         const size_t P = (size_t)cam.W * cam.H;
         const size_t pid = (size_t)pix_y * cam.W + pix_x;
         final_T[pid] = T;
-        n_contrib[pid] = last;
+        n_contrib[pid] = last_k >= 0 ? list[last_k].y : 0u;         // 1-based position in the TILE list
         out_color[pid] = ffma(T, cam.bg[0], C0);
         out_color[P + pid] = ffma(T, cam.bg[1], C1);
         out_color[2 * P + pid] = ffma(T, cam.bg[2], C2);
@@ -977,32 +975,24 @@ int launch_forward(const VtgsCamera* camera, int64_t N, bool fused, const FrontE
     if (N > 0 && band_tiles > 0) {
         { VTGS_PROF("scatter_kernel", stream); scatter_kernel<<<blocks, 256, 0, stream>>>(N, cam.gx, geom, buf->tiles_touched, buf->tile_ranges, buf->tile_counts, buf->pair_keys); }
         VTGS_LAUNCH_CHECK();
-        static bool attr_set = false;
-        if (!attr_set) {
+        static std::atomic<uint64_t> sort_attr{0};
+        if (first_call_on_device(sort_attr))
             VTGS_CUDA_CHECK(cudaFuncSetAttribute(tile_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_SMEM_ELEMS * 8));
-            attr_set = true;
-        }
         { VTGS_PROF("tile_sort_kernel", stream); tile_sort_kernel<<<band_tiles, 256, SORT_SMEM_ELEMS * 8, stream>>>(cam, buf->tile_ranges, cam.row0 * cam.gx, buf->pair_keys, buf->point_list, geom, reinterpret_cast<uint2*>(buf->region_pairs), buf->region_cnt); }
         VTGS_LAUNCH_CHECK();
     }
     if (N <= 0) VTGS_CUDA_CHECK(cudaMemsetAsync(buf->region_cnt, 0, sizeof(uint32_t) * 8 * num_tiles, stream));
     if (band_tiles > 0) {
+        static std::atomic<uint64_t> fwd_attr{0};
+        if (first_call_on_device(fwd_attr)) {        // 6 blocks x 33 KB of static shared memory per SM
+            VTGS_CUDA_CHECK(cudaFuncSetAttribute(blend_forward_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            VTGS_CUDA_CHECK(cudaFuncSetAttribute(blend_forward_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        }
         if (fused)
             { VTGS_PROF("blend_forward_kernel", stream); blend_forward_kernel<true><<<band_tiles * (8 / FWD_WARPS), 32 * FWD_WARPS, 0, stream>>>(cam, buf->tile_ranges, reinterpret_cast<const uint2*>(buf->region_pairs), buf->region_cnt, buf->region_masks, buf->region_done, geom, out_color, out_depth, buf->final_T, buf->n_contrib); }
         else { VTGS_PROF("blend_forward_kernel", stream); blend_forward_kernel<false><<<band_tiles * (8 / FWD_WARPS), 32 * FWD_WARPS, 0, stream>>>(cam, buf->tile_ranges, reinterpret_cast<const uint2*>(buf->region_pairs), buf->region_cnt, buf->region_masks, buf->region_done, geom, out_color, out_depth, buf->final_T, buf->n_contrib); }
         VTGS_LAUNCH_CHECK();
     }
-#ifdef VTGS_STATS
-    {
-        unsigned long long h[8];
-        cudaStreamSynchronize(stream);
-        cudaMemcpyFromSymbol(h, vtgs_stats, sizeof(h));
-        fprintf(stderr, "[stats] contributions %llu  sum_max(SG1) %llu  sum_max(SG2) %llu  sum_max(SG4) %llu  groups %llu  -> lane efficiency SG1 %.3f SG2 %.3f SG4 %.3f\n",
-                h[0], h[1], h[2], h[3], h[4], h[0] / (32.0 * h[1]), h[0] / (32.0 * h[2]), h[0] / (32.0 * h[3]));
-        memset(h, 0, sizeof(h));
-        cudaMemcpyToSymbol(vtgs_stats, h, sizeof(h));
-    }
-#endif
     if (band_tiles < num_tiles && !fused) {       // API mode returns complete planes; the fused solvers only ever read their band
         const size_t P = (size_t)cam.W * cam.H;
         { VTGS_PROF("fill_outside_band_kernel", stream); fill_outside_band_kernel<<<(unsigned)((P + 255) / 256), 256, 0, stream>>>(cam, fused ? 6 : 3, out_color, out_depth, buf->final_T, buf->n_contrib); }
