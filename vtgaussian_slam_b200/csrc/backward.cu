@@ -77,7 +77,10 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[16], int lane)
 //   P4 lane = splat : three red.global.add.v4.f32 per (region, splat).
 // Groups in which no pixel of the region blended anything are skipped before their records are fetched.
 // Upstream: 9-10 global float atomics per contributing (pixel, splat) pair.
-constexpr int BWD_WARPS = 2;          // warps (regions) per block: a tile is covered by 8 / BWD_WARPS blocks
+#ifndef VTGS_BWD_WARPS
+#define VTGS_BWD_WARPS 2
+#endif
+constexpr int BWD_WARPS = VTGS_BWD_WARPS;   // warps (regions) per block: a tile is covered by 8 / BWD_WARPS blocks
 // BG:   the background is not black (one more term in dL/dalpha); the reference always renders on black.
 // LITE: the caller wants no colour / opacity gradients (tracking: only the pose gradient is formed, from the
 //       mean2D / conic / depth-channel sums) -- P3 drops the r,g,b and opacity sums.
@@ -92,8 +95,10 @@ blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __re
     extern __shared__ __align__(16) unsigned char smem_raw[];
     struct WarpArea {
         GroupSmem G;
-        float2 cell[32][33];        // [splat of the group][pixel], padded row: (w, g0)
-        float4 dpix[32];            // dL/dpixel of the region's pixels (r,g,b,z)
+        float2 cell[32][32];        // [splat of the group][pixel]: (w, g0).  Unpadded: a pixel lane always stores to its own
+                                    // column (bank pair = lane mod 16, conflict-free whatever the splats); the splat lanes'
+                                    // loads hit the bank pair of the pixel they are at, as with any padding
+        float4 dpix[32];            // dL/dpixel of the region's pixels (r,g,b,z); LITE: {pixel centre x, y, dL/dz, 0}
         float2 pxy[32];             // pixel centres of the region
     };
     WarpArea* areas = reinterpret_cast<WarpArea*>(smem_raw);
@@ -122,7 +127,7 @@ blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __re
     float dpix[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int ch = 0; ch < NCH; ++ch) dpix[ch] = inside ? dL_dpix[ch * P + pid] : 0.0f;
-    A.dpix[lane] = make_float4(dpix[0], dpix[1], dpix[2], dpix[3]);
+    A.dpix[lane] = LITE ? make_float4(pxf, pyf, dpix[3], 0.0f) : make_float4(dpix[0], dpix[1], dpix[2], dpix[3]);
     A.pxy[lane] = make_float2(pxf, pyf);
     const float bg_dot = BG ? cam.bg[0] * dpix[0] + cam.bg[1] * dpix[1] + cam.bg[2] * dpix[2] : 0.0f;
     const float half_w = 0.5f * cam.W, half_h = 0.5f * cam.H;
@@ -208,10 +213,11 @@ blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __re
             pm &= pm - 1;
             const float2 cw = A.cell[lane][p];
             const float4 dp = A.dpix[p];
-            const float2 pc = A.pxy[p];
+            float2 pc;
+            if (LITE) pc = make_float2(dp.x, dp.y); else pc = A.pxy[p];
             const float dx = cur.a.x - pc.x, dy = cur.a.y - pc.y;
             if (!LITE) { c0 = fmaf(cw.x, dp.x, c0); c1 = fmaf(cw.x, dp.y, c1); c2 = fmaf(cw.x, dp.z, c2); }
-            if (NCH == 4) c3 = fmaf(cw.x, dp.w, c3);
+            if (NCH == 4) c3 = fmaf(cw.x, LITE ? dp.z : dp.w, c3);
             const float gg = cw.y, gx_ = gg * dx, gy_ = gg * dy;
             if (!LITE) s0 += gg;
             sx += gx_; sy += gy_;
@@ -377,8 +383,8 @@ preprocess_backward_kernel(const __grid_constant__ CamConst cam, int64_t N,
 }
 
 // dynamic shared memory of blend_backward_kernel
-// per warp: group 1536 + cells 8448 + dpix 512 + pxy 256 bytes
-constexpr int BWD_SMEM = BWD_WARPS * (int)(sizeof(GroupSmem) + 32 * 33 * sizeof(float2) + 32 * sizeof(float4) + 32 * sizeof(float2));
+// per warp: group 1536 + cells 8192 + dpix 512 + pxy 256 bytes
+constexpr int BWD_SMEM = BWD_WARPS * (int)(sizeof(GroupSmem) + 32 * 32 * sizeof(float2) + 32 * sizeof(float4) + 32 * sizeof(float2));
 template <bool FUSED, bool BG, bool LITE>
 static int launch_blend_backward(int blocks, cudaStream_t stream, const CamConst& cam, const VtgsBuffers* buf, const GeomRecord* geom,
                                  const float* dL_dpix) {
