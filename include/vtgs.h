@@ -42,7 +42,7 @@ extern "C" {
 #define VTGS_API
 #endif
 
-#define VTGS_ABI_VERSION 1
+#define VTGS_ABI_VERSION 2
 
 /* ---- named constants of the splatting arithmetic ---------- */
 #define VTGS_TILE            16          /* BLOCK_X = BLOCK_Y                          */
@@ -264,8 +264,9 @@ typedef struct VtgsLossConfig {
     int32_t use_sil_for_loss;
     int32_t ignore_outlier_depth;   /* tracking: also mask |gt - d| (gt > 0) >= 50 * its median over the frame
                                        (reference src/vtgaussian_slam.py:525-528; exact lower median as
-                                       torch.median, four 8-bit radix-select passes on the device).  Whole frame
-                                       only: UNSUPPORTED together with a tile-row band                       */
+                                       torch.median, four 8-bit radix-select passes on the device).  With a tile-row
+                                       band the median is a frame-wide quantity: pass `median_state` computed with
+                                       vtgs_median_hist / an all-reduce / vtgs_median_pick (UNSUPPORTED otherwise)  */
     int32_t use_l1;
     float   sil_thres;
     float   w_im;
@@ -273,6 +274,10 @@ typedef struct VtgsLossConfig {
     float   far_depth_thres;        /* <= 0: disabled                                     */
     const uint8_t* pixel_mask;      /* optional [H,W] bytes, tracking: pixels with 0 are masked out (the reference's
                                        overlap-visibility mask, :536-583, computed by the caller); NULL: none */
+    const float*   sil_thres_dev;   /* optional device float: overrides sil_thres (the Replica threshold chosen on the
+                                       device by vtgs_sil_select, so that a captured iteration follows it); NULL: none */
+    const uint32_t* median_state;   /* optional: a finished radix-select state (vtgs_median_pick after pass 3), used
+                                       instead of running the four passes inside vtgs_loss; NULL: none            */
 } VtgsLossConfig;
 
 VTGS_API int vtgs_loss(const VtgsCamera* cam, const VtgsLossConfig* cfg,
@@ -280,6 +285,41 @@ VTGS_API int vtgs_loss(const VtgsCamera* cam, const VtgsLossConfig* cfg,
               float* dL_dimage6 /* [4,H,W]: r,g,b,depth */, float* loss_terms /* [8] */,
               float* scratch /* vtgs_loss_scratch_floats() floats */, void* stream);
 VTGS_API uint64_t vtgs_loss_scratch_floats(int32_t image_width, int32_t image_height, int32_t mode);
+
+/*
+ * Frame-wide median of depth_error = |gt - d| (gt > 0) (reference src/vtgaussian_slam.py:525-527, :757-758) by radix
+ * select, in a form that shards: per pass, every rank histograms ITS rows (vtgs_median_hist, cam carries the tile-row
+ * band), the first VTGS_MEDIAN_SUMMABLE_WORDS words of `state` are all-reduced (SUM, integers), and every rank picks the
+ * same bin (vtgs_median_pick).  After pass 3 the state holds the median's bit pattern (NaN if any value was NaN, as
+ * torch.median).  `state`: VTGS_MEDIAN_STATE_WORDS uint32, zero before pass 0.
+ */
+#define VTGS_MEDIAN_STATE_WORDS    264
+#define VTGS_MEDIAN_SUMMABLE_WORDS 257
+VTGS_API int vtgs_median_hist(const VtgsCamera* cam, const float* depth_plane, const float* gt_depth, int32_t pass,
+                              uint32_t* state, void* stream);
+VTGS_API int vtgs_median_pick(int64_t num_pixels_total, int32_t pass, uint32_t* state, void* stream);
+
+/*
+ * Replica's iteration-0 silhouette-threshold search (reference src/vtgaussian_slam.py:472-510): for the five
+ * thresholds {0.990, 0.993, 0.995, 0.997, 0.999} the masked colour MSE over (silhouette > thr & depth > 0).
+ *   vtgs_sil_ladder: sums10 = {sum of squared colour differences [5], masked pixel counts [5]} over the camera's
+ *                    tile-row band (all-reduce the ten floats when the frame is sharded); scratch: the loss scratch;
+ *   vtgs_sil_select: mse_i = sum_i / (3 count_i); *sil_thres_dev = the threshold of the smallest (first on ties,
+ *                    index 0 if no pixel passes), *min_mse_dev = that MSE.
+ */
+VTGS_API int vtgs_sil_ladder(const VtgsCamera* cam, const float* image6, const float* gt_rgb, const float* gt_depth,
+                             float* sums10, float* scratch, void* stream);
+VTGS_API int vtgs_sil_select(const float* sums10, float* sil_thres_dev, float* min_mse_dev, void* stream);
+
+/*
+ * Non-presence mask of the reference's silhouette-driven Gaussian addition (add_new_gaussians_base_frame,
+ * src/vtgaussian_slam.py:747-760) from a forward-only fused render:
+ *   mask = (silhouette < sil_thres) | ((depth > gt) & (|gt - depth| (gt > 0) > 50 median))
+ * median_state: a finished radix-select state of the same render (vtgs_median_hist / vtgs_median_pick).
+ * mask_out[H,W] bytes; *count_dev (optional) receives the number of set pixels.
+ */
+VTGS_API int vtgs_nonpresence_mask(const VtgsCamera* cam, const float* image6, const float* gt_depth, float sil_thres,
+                                   const uint32_t* median_state, uint8_t* mask_out, uint32_t* count_dev, void* stream);
 
 /*
  * Fused backward: K6 + K7 + the autograd chain through get_depth_and_silhouette,
@@ -326,15 +366,32 @@ VTGS_API int vtgs_adam(float* param, const float* grad, float* exp_avg, float* e
 VTGS_API int vtgs_retie(float* means3D, int64_t n, const float* w2c_old, const float* cam_unnorm_rot,
                         const float* cam_trans, void* stream);
 
+/* The same with the OLD pose given as device quaternion / translation (e.g. a copy taken before the optimiser step):
+ * nothing crosses to the host, so a mapping iteration with bundle adjustment stays free of synchronisation. */
+VTGS_API int vtgs_retie_dev(float* means3D, int64_t n, const float* old_unnorm_rot, const float* old_trans,
+                            const float* cam_unnorm_rot, const float* cam_trans, void* stream);
+
 /*
  * Tracking pose update in one launch: the reference's `optimizer.step()` on the frame's pose slices
  * (src/vtgaussian_slam.py:1890, Adam betas (0.9, 0.999)) plus its best-candidate bookkeeping (:1961-1970).
  *   msg[16]        = {dL/dq[4], dL/dt[3], pad, loss_terms[8]}  (the all-reduced message of an iteration)
  *   adam_state[14] = {m_q[4], v_q[4], m_t[3], v_t[3]};  *step_dev is incremented
- *   best[8]        = {best_loss, best_q[4], best_t[3]}: pose BEFORE this step is kept if msg loss < best_loss
+ *   best[8]        = {best_metric, best_q[4], best_t[3]}: a candidate pose is kept if this iteration's metric is smaller
+ *   flags: VTGS_TRACK_BOOK_POST_STEP  book the pose AFTER this step (what the reference does: it clones the pose after
+ *                                     optimizer.step() against the loss computed before it, :1888-1970); without it the
+ *                                     pose the loss was evaluated at is booked;
+ *          VTGS_TRACK_CALLER_METRIC   rank candidates by msg[15] (a caller-supplied metric, e.g. the reference's
+ *                                     point-to-plane distance `choose_metric`) instead of the loss msg[8].
  */
+#define VTGS_TRACK_BOOK_POST_STEP 1
+#define VTGS_TRACK_CALLER_METRIC  2
 VTGS_API int vtgs_tracking_update(float* cam_unnorm_rot, float* cam_trans, const float* msg, float* adam_state,
-                                  int32_t* step_dev, float* best, float lr_rot, float lr_trans, float eps, void* stream);
+                                  int32_t* step_dev, float* best, float lr_rot, float lr_trans, float eps, int32_t flags,
+                                  void* stream);
+
+/* FP32 FMA throughput probe (bench.py's measured FP32 peak): every thread of a full grid runs `iters` dependent-free
+ * FFMA octets; FLOP = 2 * 8 * iters * threads, threads = *threads_out.  sink: one device float (keeps the work alive). */
+VTGS_API int vtgs_ffma_probe(int64_t iters, float* sink, uint64_t* threads_out, void* stream);
 
 /*
  * Optional per-kernel timing for bench.py's roofline: while enabled, every kernel launch of

@@ -26,7 +26,7 @@ def test_every_declared_symbol_is_exported(L):
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
     for name in declared:
         assert hasattr(L, name)
-    assert L.vtgs_abi_version() == 1
+    assert L.vtgs_abi_version() == _lib.ABI_VERSION == 2
     assert b"sm_100a" in L.vtgs_build_info()
 
 
@@ -36,7 +36,7 @@ def test_struct_layouts_match_the_header(L):
     assert C.sizeof(_lib.VtgsBuffers) == 8 * 15
     assert C.sizeof(_lib.VtgsParams) == 8 * 5 + 8 + 8
     assert C.sizeof(_lib.VtgsPose) == 16 + 16
-    assert C.sizeof(_lib.VtgsLossConfig) == 32 + 8
+    assert C.sizeof(_lib.VtgsLossConfig) == 32 + 8 + 8 + 8
     assert C.sizeof(_lib.VtgsParamGrads) == 72
 
 

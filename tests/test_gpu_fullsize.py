@@ -1,6 +1,7 @@
 """-m gpu: BASELINE.json's full sizes (Replica 1200x680 ~1.0 M Gaussians, TUM 640x480, ScanNet++-shaped
-1752x1168) checked through size-independent properties -- the oracle is too slow to run these in a
-test, so parity at full size rests on:
+1752x1168).  `test_whole_frame_against_oracle` compares the ENTIRE frame -- six planes, final_T, n_contrib, radii,
+tile ranges, sorted lists, the tracking loss, the pose gradient and every per-parameter gradient -- with the CPU
+oracle (a few seconds per case on the box's host cores).  The other tests check size-independent properties:
   * structural invariants of the binning (R = sum tiles_touched, ranges partition [0,R), keys sorted with
     index-ordered ties inside every tile, n_contrib <= list length);
   * silhouette = 1 - final_T, depth plane of the API pass == z plane of the fused pass (same geometry);
@@ -169,3 +170,65 @@ def test_full_size_fused_equals_two_dropin_passes():
     assert (d_im > 1e-4).float().mean().item() < 1e-5 and (d_ds > 1e-4).float().mean().item() < 1e-5
     assert torch.equal(depth[0], ds[0])                             # the rasteriser's own depth plane == z channel
     assert (radius != radii).float().mean().item() < 1e-4
+
+
+@pytest.mark.parametrize("shape,n_edge", [("replica", 200000), ("tum_fr1", 60000), ("scannetpp", 300000)])
+def test_whole_frame_against_oracle(shape, n_edge):
+    """Full-size parity of one whole tracking / mapping iteration's render and back-propagation with the oracle:
+    integer outputs and the six planes bit-exact, loss within 1e-5, gradients within 1e-3 relative (north star)."""
+    from helpers import oracle_chain_grads, rel_err, tracking_dL
+    from vtgaussian_slam_b200.fused import FusedRenderer
+    fr = synthetic.make_frame(shape, seed=0)
+    p = synthetic.view_tied_gaussians(fr, n_edge=n_edge, opacity="trained")
+    N = p["means3D"].shape[0]
+    W, H = fr["W"], fr["H"]
+    settings, s = _settings(fr)
+    gp = {k: torch.tensor(v, device=DEV) for k, v in p.items()}
+    q, t = synthetic.perturbed_pose(seed=1)
+    q = (q * 1.3).astype(np.float32)                     # un-normalised pose quaternion
+    qd, td = torch.tensor(q, device=DEV), torch.tensor(t, device=DEV)
+    w_im, w_depth, sil = 0.5, 0.025, 0.99
+
+    # ---- oracle: front end, six-plane forward, tracking loss, backward, fp64 chain to the parameters
+    cam_o, _ = oracle_camera(W, H, fr["K"])
+    m, sc, rot, op, c6 = oracle.frontend(p["means3D"], p["rgb_colors"], p["unnorm_rotations"], p["logit_opacities"],
+                                         p["log_scales"], q, t)
+    orc = oracle.Oracle()
+    ref = orc.forward(cam_o, m, sc, rot, op, c6)
+    dL6, loss_ref = tracking_dL(ref["color"], fr["im"], fr["depth"], w_im, w_depth, sil)
+    g = orc.backward(dL6)
+    gref = oracle_chain_grads(p, q, t, g)
+
+    # ---- CUDA
+    r = FusedRenderer(settings, N, device=DEV)
+    img, radii = r.forward(gp, qd, td)
+    overflow, R = r.overflowed()
+    assert not overflow and R == ref["R"]
+    assert np.array_equal(radii.cpu().numpy(), ref["radii"])
+    assert np.array_equal(r.ws.tiles_touched[:N].cpu().numpy().astype(np.uint32), ref["tiles_touched"])
+    assert np.array_equal(r.ws.tile_ranges.cpu().numpy().astype(np.uint32), ref["ranges"])
+    assert np.array_equal(r.ws.point_list[:R].cpu().numpy().astype(np.uint32), ref["point_list"])
+    assert np.array_equal(r.ws.n_contrib.cpu().numpy().astype(np.uint32), ref["n_contrib"])
+    assert np.array_equal(r.ws.final_T.cpu().numpy(), ref["final_T"])
+    assert np.array_equal(img.cpu().numpy(), ref["color"]), "the six planes are expected to be bit-identical to the oracle"
+    terms = r.tracking_loss(torch.tensor(fr["im"], device=DEV), torch.tensor(fr["depth"], device=DEV), w_im=w_im,
+                            w_depth=w_depth, use_sil_for_loss=True, sil_thres=sil).cpu().numpy()
+    assert abs(terms[0] - loss_ref) <= 1e-5 * abs(loss_ref)
+    assert np.array_equal(r.dL_dimage4.cpu().numpy(), dL6[:4])
+
+    # tracking instantiation (pose only) and the full one (every parameter gradient)
+    dq0, dt0 = torch.zeros(4, device=DEV), torch.zeros(3, device=DEV)
+    r.backward(gp, qd, td, pose_grads=(dq0, dt0))
+    assert rel_err(dq0.cpu().numpy(), gref["cam_unnorm_rots"]) <= 1e-3
+    assert rel_err(dt0.cpu().numpy(), gref["cam_trans"]) <= 1e-3
+    pg = {k: torch.zeros_like(gp[k]) for k in gp}
+    dq, dt = torch.zeros(4, device=DEV), torch.zeros(3, device=DEV)
+    m2d = torch.zeros(N, 3, device=DEV)
+    r.backward(gp, qd, td, param_grads=pg, pose_grads=(dq, dt), means2D_grad=m2d)
+    assert rel_err(dq.cpu().numpy(), gref["cam_unnorm_rots"]) <= 1e-3
+    assert rel_err(dt.cpu().numpy(), gref["cam_trans"]) <= 1e-3
+    assert rel_err(m2d.cpu().numpy(), g["means2D"]) <= 1e-3
+    for k in ("means3D", "rgb_colors", "logit_opacities", "log_scales"):
+        assert rel_err(pg[k].cpu().numpy(), gref[k]) <= 1e-3, k
+    floor = float(np.abs(gref["log_scales"]).max())
+    assert rel_err(pg["unnorm_rotations"].cpu().numpy(), gref["unnorm_rotations"], floor=floor) <= 1e-3

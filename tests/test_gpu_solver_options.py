@@ -1,0 +1,274 @@
+"""-m gpu: the parts of get_loss / the tracking and mapping loops that round 2 moved onto the device or made shardable --
+Replica's silhouette-threshold search (reference src/vtgaussian_slam.py:472-510), the frame-wide outlier median under
+tile bands (:525-528), the reference's best-pose bookkeeping (:1888-1970), the non-presence mask of the Gaussian addition
+(:747-760), bundle adjustment + re-tie (:2545-2548, :2706-2727) and the frozen-section loss (:2552) in the mapping solver,
+and the transparent re-run when the pair buffers turn out too small."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from vtgaussian_slam_b200 import _lib, slam_ops, synthetic
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _scene(W=200, H=120, n_edge=1500, opacity="trained", seed=0):
+    fr = synthetic.make_frame("replica", W, H, seed=seed)
+    p = synthetic.view_tied_gaussians(fr, n_edge=n_edge, opacity=opacity)
+    q, t = synthetic.perturbed_pose(seed=1)
+    return fr, p, (q * 1.2).astype(np.float32), t
+
+
+def _settings(fr, dev=DEV):
+    from gpu_helpers import settings_from
+    s = synthetic.setup_camera(fr["W"], fr["H"], fr["K"], np.eye(4))
+    return settings_from(s, torch.device(dev))
+
+
+def _gp(p):
+    return {k: torch.tensor(v, device=DEV) for k, v in p.items()}
+
+
+def _render(fr, p, q, t, tile_rows=(0, 0)):
+    from vtgaussian_slam_b200.fused import FusedRenderer
+    r = FusedRenderer(_settings(fr), p["means3D"].shape[0], device=DEV, tile_rows=tile_rows)
+    img, _ = r.forward(_gp(p), torch.tensor(q, device=DEV), torch.tensor(t, device=DEV))
+    return r, img
+
+
+def test_sil_ladder_matches_the_reference_search():
+    fr, p, q, t = _scene(opacity="fresh")          # a fresh section's silhouette sits around the ladder's thresholds
+    r, img = _render(fr, p, q, t)
+    gt_rgb, gt_d = torch.tensor(fr["im"], device=DEV), torch.tensor(fr["depth"], device=DEV)
+    gt_d[0, :10, :20] = 0.0
+    res = r.sil_ladder(gt_rgb, gt_d).cpu().numpy()
+    mse_ls, cnts = [], []
+    for thr in slam_ops.REPLICA_SIL_LADDER:         # the reference's five masked MSEs (:476-497)
+        m = (img[4] > thr) & (gt_d[0] > 0)
+        cm = torch.tile(m, (3, 1, 1))
+        mse_ls.append(torch.mean((gt_rgb - img[:3])[cm] ** 2).item())
+        cnts.append(int(m.sum().item()))
+    assert len(set(cnts)) > 1, "the scene must separate the thresholds"
+    assert np.array_equal(res[5:10].astype(np.int64), np.asarray(cnts))
+    assert np.allclose(res[:5] / (3 * res[5:10]), mse_ls, rtol=1e-5)
+    assert abs(res[10] - slam_ops.REPLICA_SIL_LADDER[mse_ls.index(min(mse_ls))]) < 1e-6
+    assert abs(res[11] - min(mse_ls)) <= 1e-5 * min(mse_ls)
+    # the loss kernel follows the device threshold
+    a = r.tracking_loss(gt_rgb, gt_d, sil_thres=0.5, sil_thres_dev=r._sil[10:11]).clone()
+    b = r.tracking_loss(gt_rgb, gt_d, sil_thres=float(res[10])).clone()
+    assert torch.equal(a, b)
+
+
+def test_outlier_median_is_band_reducible():
+    """Two tile-row bands histogram into one state (what the all-reduce of the first 257 words does across ranks): the
+    frame-wide median and the banded losses add up to the whole-frame result."""
+    fr, p, q, t = _scene()
+    gt_depth = fr["depth"].copy()
+    gt_depth[0, 20:40, 30:90] *= 3.0
+    gt_rgb, gt_d = torch.tensor(fr["im"], device=DEV), torch.tensor(gt_depth, device=DEV)
+    r, img = _render(fr, p, q, t)
+    full = r.tracking_loss(gt_rgb, gt_d, w_depth=1.0, ignore_outlier_depth_loss=True).clone()
+    st_full = r.median_state(gt_depth=gt_d).clone()
+    derr = torch.abs(gt_d - img[3:4]) * (gt_d > 0)
+    assert st_full[259].item() == derr.median().view(torch.int32).item()         # bit pattern of torch.median
+    gy = (fr["H"] + 15) // 16
+    cut = gy // 2
+    bands = [(0, cut), (cut, gy)]
+    rs = [_render(fr, p, q, t, tile_rows=b)[0] for b in bands]
+    L = _lib.lib()
+    st = torch.zeros(_lib.MEDIAN_STATE_WORDS, dtype=torch.int32, device=DEV)
+    stream = torch.cuda.current_stream().cuda_stream
+    P = fr["W"] * fr["H"]
+    for ps in range(4):
+        for rb in rs:
+            _lib.check(L.vtgs_median_hist(C.byref(rb.cam), C.c_void_p(rb.image6[3].data_ptr()), C.c_void_p(gt_d.data_ptr()), ps,
+                                          C.c_void_p(st.data_ptr()), stream))
+        _lib.check(L.vtgs_median_pick(P, ps, C.c_void_p(st.data_ptr()), stream))
+    assert st[259].item() == st_full[259].item()
+    parts = [rb.tracking_loss(gt_rgb, gt_d, w_depth=1.0, ignore_outlier_depth_loss=True, median_state=st).clone() for rb in rs]
+    tot = parts[0] + parts[1]
+    assert int(tot[3].item()) == int(full[3].item())
+    assert abs(tot[0].item() - full[0].item()) <= 1e-5 * abs(full[0].item())
+    with pytest.raises(NotImplementedError):       # a band without a frame-wide median state stays an error
+        rs[0].tracking_loss(gt_rgb, gt_d, ignore_outlier_depth_loss=True)
+
+
+def test_tracking_update_books_like_the_reference():
+    L = _lib.lib()
+    stream = torch.cuda.current_stream().cuda_stream
+    f = lambda *v: torch.tensor(v, dtype=torch.float32, device=DEV)
+    for flags in (0, _lib.TRACK_BOOK_POST_STEP, _lib.TRACK_BOOK_POST_STEP | _lib.TRACK_CALLER_METRIC):
+        q, t = f(1.0, 0.1, 0.0, 0.0), f(0.1, 0.2, 0.3)
+        q0, t0 = q.clone(), t.clone()
+        msg = torch.zeros(16, device=DEV)
+        msg[:7] = f(0.3, -0.2, 0.1, 0.5, 1.0, -2.0, 0.5)
+        msg[8], msg[15] = 5.0, 7.0
+        adam = torch.zeros(14, device=DEV)
+        step = torch.zeros(1, dtype=torch.int32, device=DEV)
+        best = torch.zeros(8, device=DEV)
+        best[0] = float("inf")
+        p = lambda x: C.c_void_p(x.data_ptr())
+        _lib.check(L.vtgs_tracking_update(p(q), p(t), p(msg), p(adam), p(step), p(best), 4e-4, 2e-3, 1e-8, flags, stream))
+        b = best.cpu().numpy()
+        assert b[0] == (7.0 if flags & _lib.TRACK_CALLER_METRIC else 5.0)
+        exp_q, exp_t = (q, t) if flags & _lib.TRACK_BOOK_POST_STEP else (q0, t0)
+        assert np.array_equal(b[1:5], exp_q.cpu().numpy()) and np.array_equal(b[5:8], exp_t.cpu().numpy())
+        # first Adam step moves every component by lr against the sign of its gradient
+        assert np.allclose((q - q0).cpu().numpy(), -4e-4 * np.sign(msg[:4].cpu().numpy()), atol=1e-7)
+        assert np.allclose((t - t0).cpu().numpy(), -2e-3 * np.sign(msg[4:7].cpu().numpy()), atol=1e-7)
+
+
+def test_nonpresence_mask_matches_the_reference_expression():
+    fr, p, q, t = _scene()
+    keep = np.ones(p["means3D"].shape[0], bool)
+    keep[: fr["W"] * 30] = False                       # drop the Gaussians of the top rows: silhouette holes
+    p = {k: v[keep] for k, v in p.items()}
+    gt_depth = fr["depth"].copy()
+    gt_depth[0, 60:80, 50:120] *= 0.5                  # a new foreground object in front of the map
+    gt_depth[0, 100:110, :30] = 0.0
+    gt_d = torch.tensor(gt_depth, device=DEV)
+    r, img = _render(fr, p, q, t)
+    mask, count = r.nonpresence_mask(gt_d, sil_thres=0.5)
+    sil, d, g = img[4], img[3], gt_d[0]
+    derr = torch.abs(g - d) * (g > 0)
+    ref = (sil < 0.5) | ((d > g) & (derr > 50 * derr.median()))            # reference :749-760
+    assert torch.equal(mask.bool(), ref)
+    assert int(count.item()) == int(ref.sum().item()) > 0
+    assert bool(ref[:25].all()) and not bool(ref.all())
+
+
+def test_tracking_solver_replica_search_and_regrow():
+    from vtgaussian_slam_b200.fused import TrackingSolver
+    fr, p, q, t = _scene(240, 136, n_edge=0, opacity="fresh")
+    settings = _settings(fr)
+    gt_rgb, gt_d = torch.tensor(fr["im"]), torch.tensor(fr["depth"])
+    res = {}
+    for name, kw in (("eager", dict(use_graph=False)), ("graph", dict(use_graph=True)),
+                     ("tiny", dict(use_graph=True, pair_capacity=1000))):
+        ts = TrackingSolver(settings, _gp(p), device=DEV, replica_sil_search=True, **kw)
+        ts.set_frame(gt_rgb, gt_d, q, t)
+        best = ts.run_frame(12).numpy()
+        res[name] = (best, float(ts.r._sil[10].item()))
+    # the threshold the solver chose == the reference's search on the first render
+    r, img = _render(fr, p, q, t)
+    mse = []
+    for thr in slam_ops.REPLICA_SIL_LADDER:
+        m = (img[4] > thr) & (gt_d.to(DEV)[0] > 0)
+        mse.append(torch.mean((gt_rgb.to(DEV) - img[:3])[torch.tile(m, (3, 1, 1))] ** 2).item())
+    assert abs(res["eager"][1] - slam_ops.REPLICA_SIL_LADDER[mse.index(min(mse))]) < 1e-6
+    assert np.allclose(res["eager"][0], res["graph"][0], rtol=1e-4, atol=1e-6)
+    assert np.allclose(res["tiny"][0], res["graph"][0], rtol=1e-4, atol=1e-6)        # overflowed, regrown, re-run
+    assert np.isfinite(res["graph"][0]).all()
+
+
+def test_get_loss_regrows_overflowing_pair_buffers(monkeypatch):
+    from vtgaussian_slam_b200 import fused
+    fr, p, q, t = _scene()
+    settings = _settings(fr)
+    data = dict(cam=settings, im=torch.tensor(fr["im"], device=DEV), depth=torch.tensor(fr["depth"], device=DEV), w2c=torch.eye(4, device=DEV))
+
+    def run():
+        params = {k: torch.nn.Parameter(torch.tensor(v, device=DEV)) for k, v in p.items()}
+        params["cam_unnorm_rots"] = torch.nn.Parameter(torch.tensor(q, device=DEV).reshape(1, 4, 1).contiguous())
+        params["cam_trans"] = torch.nn.Parameter(torch.tensor(t, device=DEV).reshape(1, 3, 1).contiguous())
+        variables = dict(max_2D_radius=torch.zeros(p["means3D"].shape[0], device=DEV))
+        loss, _, _ = slam_ops.get_loss(params, data, variables, 0, dict(im=0.5, depth=1.0), True, 0.99, True, False, tracking=True,
+                                       tracking_iteration=0, dataset_name="tum")
+        loss.backward()
+        return loss.item(), params["cam_trans"].grad.cpu().numpy()
+    ref = run()
+    slam_ops._RENDERERS.clear()
+    orig = fused.FusedRenderer.__init__
+
+    def tiny(self, *a, **k):
+        k["pair_capacity"] = 512
+        orig(self, *a, **k)
+    monkeypatch.setattr(fused.FusedRenderer, "__init__", tiny)
+    got = run()
+    slam_ops._RENDERERS.clear()
+    assert got[0] == ref[0] and np.allclose(got[1], ref[1], rtol=1e-5)          # (float atomics: last-bit order effects)
+
+
+def test_mapping_solver_global_term_ba_and_retie():
+    from vtgaussian_slam_b200.fused import MappingSolver
+    from vtgaussian_slam_b200.slam_loop import matrix_from_quat, quat_from_matrix
+    poses = synthetic.trajectory(3, step_m=0.05, step_deg=2.0, seed=5)
+    frames = [synthetic.make_frame("replica", 160, 96, seed=k, c2w=poses[k]) for k in range(3)]
+    frozen = synthetic.section_gaussians(frames[0], poses[0], seed=2)
+    train = synthetic.section_gaussians(frames[2], poses[2], seed=3)
+    settings = _settings(frames[2])
+    Nf, N = frozen["means3D"].shape[0], train["means3D"].shape[0]
+    arena = {k: torch.tensor(np.concatenate([frozen[k], train[k]], 0), device=DEV) for k in train}      # frozen rows, then trainable
+    tail = {k: v[Nf:] for k, v in arena.items()}
+    w2c = np.linalg.inv(poses[2])
+    mk = lambda: dict(cam_q=torch.tensor(quat_from_matrix(w2c[:3, :3]).astype(np.float32), device=DEV),
+                      cam_t=torch.tensor((w2c[:3, 3] + [0.01, -0.005, 0.0]).astype(np.float32), device=DEV),
+                      gt_rgb=torch.tensor(frames[2]["im"], device=DEV), gt_depth=torch.tensor(frames[2]["depth"], device=DEV))
+    lrs = dict(rgb_colors=0.0025, logit_opacities=0.05, log_scales=0.005, cam_unnorm_rots=1e-4, cam_trans=1e-3)
+
+    # (1) the global term: loss and gradients are the sums of the two renders
+    ms_a = MappingSolver(settings, {k: v.clone() for k, v in tail.items()}, device=DEV, lrs=lrs)
+    ms_g = MappingSolver(settings, {k: v.clone() for k, v in arena.items()}, device=DEV, lrs=lrs)
+    kf = mk()
+    la = ms_a.iteration([kf]).item()
+    ga = {k: v.clone() for k, v in ms_a.grads.items()}
+    lg = ms_g.iteration([kf]).item()
+    gg = {k: v[Nf:].clone() for k, v in ms_g.grads.items()}
+    ms = MappingSolver(settings, tail, device=DEV, lrs=lrs, global_params=arena)
+    assert ms._global_aliases
+    before = {k: v.clone() for k, v in arena.items()}
+    l = ms.iteration([mk()]).item()
+    assert abs(l - (la + lg)) <= 1e-5 * abs(la + lg)
+    for k in ga:
+        ref = ga[k] + gg[k]
+        assert (ms.grads[k] - ref).abs().max().item() <= 1e-3 * ref.abs().max().item(), k
+    for k in ("rgb_colors", "logit_opacities", "log_scales"):
+        assert torch.equal(arena[k][:Nf], before[k][:Nf])                        # frozen rows are never updated
+        assert not torch.equal(arena[k][Nf:], before[k][Nf:])                    # trainable rows updated in place
+
+    # (2) bundle adjustment + re-tie of the section's Gaussians to the stepped pose
+    ms2 = MappingSolver(settings, {k: v.clone() for k, v in tail.items()}, device=DEV, lrs=lrs)
+    kf = mk()
+    kf["retie_last"] = N
+    q_old, t_old = kf["cam_q"].cpu().numpy().copy(), kf["cam_t"].cpu().numpy().copy()
+    pts_old = ms2.params["means3D"].cpu().numpy().astype(np.float64)
+    ms2.iteration([kf], do_ba=True)
+    q_new, t_new = kf["cam_q"].cpu().numpy(), kf["cam_t"].cpu().numpy()
+    assert not np.array_equal(q_new, q_old) and not np.array_equal(t_new, t_old)
+    assert np.allclose(np.abs(t_new - t_old), 1e-3, rtol=1e-3)                   # first Adam step: lr per component
+    Wo, Wn = matrix_from_quat(q_old, t_old), matrix_from_quat(q_new, t_new)
+    cam = pts_old @ Wo[:3, :3].T + Wo[:3, 3]
+    exp = (cam - Wn[:3, 3]) @ Wn[:3, :3]                                          # c2w_new (w2c_old p)
+    assert np.abs(ms2.params["means3D"].cpu().numpy() - exp).max() <= 1e-5
+    # pose gradient of the solver == the fused get_loss(do_ba=True) gradient on the same inputs
+    params = {k: torch.nn.Parameter(v.clone()) for k, v in tail.items()}
+    params["cam_unnorm_rots"] = torch.nn.Parameter(torch.tensor(q_old, device=DEV).reshape(1, 4, 1).contiguous())
+    params["cam_trans"] = torch.nn.Parameter(torch.tensor(t_old, device=DEV).reshape(1, 3, 1).contiguous())
+    data = dict(cam=settings, im=kf["gt_rgb"], depth=kf["gt_depth"], w2c=torch.eye(4, device=DEV))
+    variables = dict(max_2D_radius=torch.zeros(N, device=DEV))
+    loss, variables, _ = slam_ops.get_loss(params, data, variables, 0, dict(im=1.0, depth=1.0), False, 0.5, True, False, mapping=True,
+                                           do_ba=True, dataset_name="tum")
+    loss.backward()
+    st = kf["_ba"]
+    assert (st["d_t"] - params["cam_trans"].grad.reshape(3)).abs().max().item() <= 1e-3 * params["cam_trans"].grad.abs().max().item()
+    assert (st["d_q"] - params["cam_unnorm_rots"].grad.reshape(4)).abs().max().item() <= 1e-3 * params["cam_unnorm_rots"].grad.abs().max().item()
+    # the reference's contract: variables['means2D'].grad holds the screen-space gradient after backward
+    assert variables["means2D"].grad is not None and variables["means2D"].grad.abs().sum().item() > 0
+
+
+def test_ffma_probe_runs():
+    L = _lib.lib()
+    sink = torch.zeros(1, device=DEV)
+    n = C.c_uint64(0)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stream = torch.cuda.current_stream().cuda_stream
+    _lib.check(L.vtgs_ffma_probe(1000, C.c_void_p(sink.data_ptr()), C.byref(n), stream))
+    e0.record()
+    _lib.check(L.vtgs_ffma_probe(20000, C.c_void_p(sink.data_ptr()), C.byref(n), stream))
+    e1.record()
+    torch.cuda.synchronize()
+    tflops = 2 * 8 * 20000 * n.value / (e0.elapsed_time(e1) * 1e-3) / 1e12
+    assert n.value == 148 * 8 * 256 and 20.0 < tflops < 90.0, tflops

@@ -11,6 +11,11 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("VTGS_LIB_PATH") or os.path.join(_HERE, "lib", "libvtgs_cuda.so")
 CSRC = os.path.join(_HERE, "csrc")
 
+ABI_VERSION = 2
+MEDIAN_STATE_WORDS = 264
+MEDIAN_SUMMABLE_WORDS = 257
+TRACK_BOOK_POST_STEP = 1
+TRACK_CALLER_METRIC = 2
 GEOM_RECORD_BYTES = 64
 GRAD_GEOM_FLOATS = 16
 
@@ -70,6 +75,7 @@ class VtgsLossConfig(C.Structure):
         ("mode", C.c_int32), ("use_sil_for_loss", C.c_int32), ("ignore_outlier_depth", C.c_int32),
         ("use_l1", C.c_int32), ("sil_thres", C.c_float), ("w_im", C.c_float), ("w_depth", C.c_float),
         ("far_depth_thres", C.c_float), ("pixel_mask", C.c_void_p),
+        ("sil_thres_dev", C.c_void_p), ("median_state", C.c_void_p),
     ]
 
 
@@ -98,7 +104,14 @@ SYMBOLS = {
     "vtgs_fused_backward": (C.c_int, [C.POINTER(VtgsCamera), C.POINTER(VtgsParams), C.POINTER(VtgsPose), _P, C.c_int32,
                                       C.POINTER(VtgsParamGrads), C.POINTER(VtgsBuffers), _P]),
     "vtgs_retie": (C.c_int, [_P, C.c_int64, C.POINTER(C.c_float * 12), _P, _P, _P]),
-    "vtgs_tracking_update": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_float, C.c_float, C.c_float, _P]),
+    "vtgs_retie_dev": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, _P]),
+    "vtgs_tracking_update": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_float, C.c_float, C.c_float, C.c_int32, _P]),
+    "vtgs_median_hist": (C.c_int, [C.POINTER(VtgsCamera), _P, _P, C.c_int32, _P, _P]),
+    "vtgs_median_pick": (C.c_int, [C.c_int64, C.c_int32, _P, _P]),
+    "vtgs_sil_ladder": (C.c_int, [C.POINTER(VtgsCamera), _P, _P, _P, _P, _P, _P]),
+    "vtgs_sil_select": (C.c_int, [_P, _P, _P, _P]),
+    "vtgs_nonpresence_mask": (C.c_int, [C.POINTER(VtgsCamera), _P, _P, C.c_float, _P, _P, _P, _P]),
+    "vtgs_ffma_probe": (C.c_int, [C.c_int64, _P, C.POINTER(C.c_uint64), _P]),
     "vtgs_profile_enable": (C.c_int, [C.c_int32]),
     "vtgs_profile_summary": (C.c_int, [C.c_char_p, C.c_uint64]),
     "vtgs_adam": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32, _P, _P]),
@@ -132,7 +145,7 @@ def lib():
             fn = getattr(L, name)          # AttributeError if the library does not export it
             fn.restype = res
             fn.argtypes = args
-        if L.vtgs_abi_version() != 1:
+        if L.vtgs_abi_version() != ABI_VERSION:
             raise RuntimeError("libvtgs_cuda.so ABI version mismatch")
         _lib = L
     return _lib

@@ -193,13 +193,22 @@ uint64_t vtgs_pose_scratch_floats(int64_t N) { return (uint64_t)((N + 255) / 256
 uint64_t vtgs_loss_scratch_floats(int32_t W, int32_t H, int32_t mode) {
     const uint64_t P = (uint64_t)W * H;
     if (mode == 1) return 9 * P + ((uint64_t)((W + 15) / 16) * ((H + 15) / 16) * 3 + 1) * 4;
-    return ((P + 255) / 256 + 1) * 4 + 512;      /* + the radix-select state of the outlier median */
+    /* [tracking loss: 4 floats per 1024-pixel block + ticket + the radix-select state of the outlier median (320 words)
+     *  | silhouette ladder: 10 floats per block + ticket] */
+    return ((P + 1023) / 1024) * 14 + 320 + 16;
 }
 
 int vtgs_retie(float* means3D, int64_t n, const float* w2c_old, const float* cam_unnorm_rot, const float* cam_trans, void* stream) {
     VTGS_REQUIRE(n >= 0, "n < 0");
     VTGS_REQUIRE(w2c_old && cam_unnorm_rot && cam_trans && (n == 0 || means3D), "pointer is NULL");
     return launch_retie(means3D, n, w2c_old, cam_unnorm_rot, cam_trans, (cudaStream_t)stream);
+}
+
+int vtgs_retie_dev(float* means3D, int64_t n, const float* old_unnorm_rot, const float* old_trans, const float* cam_unnorm_rot,
+                   const float* cam_trans, void* stream) {
+    VTGS_REQUIRE(n >= 0, "n < 0");
+    VTGS_REQUIRE(old_unnorm_rot && old_trans && cam_unnorm_rot && cam_trans && (n == 0 || means3D), "pointer is NULL");
+    return launch_retie_dev(means3D, n, old_unnorm_rot, old_trans, cam_unnorm_rot, cam_trans, (cudaStream_t)stream);
 }
 
 int vtgs_loss(const VtgsCamera* cam, const VtgsLossConfig* cfg, const float* image6, const float* gt_rgb,
@@ -218,9 +227,46 @@ int vtgs_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq
 }
 
 int vtgs_tracking_update(float* cam_unnorm_rot, float* cam_trans, const float* msg, float* adam_state, int32_t* step_dev,
-                         float* best, float lr_rot, float lr_trans, float eps, void* stream) {
+                         float* best, float lr_rot, float lr_trans, float eps, int32_t flags, void* stream) {
     VTGS_REQUIRE(cam_unnorm_rot && cam_trans && msg && adam_state && step_dev && best, "pointer is NULL");
-    return launch_tracking_update(cam_unnorm_rot, cam_trans, msg, adam_state, step_dev, best, lr_rot, lr_trans, eps, (cudaStream_t)stream);
+    return launch_tracking_update(cam_unnorm_rot, cam_trans, msg, adam_state, step_dev, best, lr_rot, lr_trans, eps, flags, (cudaStream_t)stream);
+}
+
+int vtgs_median_hist(const VtgsCamera* cam, const float* depth_plane, const float* gt_depth, int32_t pass, uint32_t* state, void* stream) {
+    if (int e = check_cam(cam)) return e;
+    VTGS_REQUIRE(depth_plane && gt_depth && state, "pointer is NULL");
+    VTGS_REQUIRE(pass >= 0 && pass < 4, "pass must be 0..3");
+    return launch_median_hist(cam, depth_plane, gt_depth, pass, state, (cudaStream_t)stream);
+}
+
+int vtgs_median_pick(int64_t num_pixels_total, int32_t pass, uint32_t* state, void* stream) {
+    VTGS_REQUIRE(state != nullptr && num_pixels_total > 0, "bad argument");
+    VTGS_REQUIRE(pass >= 0 && pass < 4, "pass must be 0..3");
+    return launch_median_pick(num_pixels_total, pass, state, (cudaStream_t)stream);
+}
+
+int vtgs_sil_ladder(const VtgsCamera* cam, const float* image6, const float* gt_rgb, const float* gt_depth, float* sums10,
+                    float* scratch, void* stream) {
+    if (int e = check_cam(cam)) return e;
+    VTGS_REQUIRE(image6 && gt_rgb && gt_depth && sums10 && scratch, "pointer is NULL");
+    return launch_sil_ladder(cam, image6, gt_rgb, gt_depth, sums10, scratch, (cudaStream_t)stream);
+}
+
+int vtgs_sil_select(const float* sums10, float* sil_thres_dev, float* min_mse_dev, void* stream) {
+    VTGS_REQUIRE(sums10 && sil_thres_dev, "pointer is NULL");
+    return launch_sil_select(sums10, sil_thres_dev, min_mse_dev, (cudaStream_t)stream);
+}
+
+int vtgs_nonpresence_mask(const VtgsCamera* cam, const float* image6, const float* gt_depth, float sil_thres,
+                          const uint32_t* median_state, uint8_t* mask_out, uint32_t* count_dev, void* stream) {
+    if (int e = check_cam(cam)) return e;
+    VTGS_REQUIRE(image6 && gt_depth && median_state && mask_out, "pointer is NULL");
+    return launch_nonpresence_mask(cam, image6, gt_depth, sil_thres, median_state, mask_out, count_dev, (cudaStream_t)stream);
+}
+
+int vtgs_ffma_probe(int64_t iters, float* sink, uint64_t* threads_out, void* stream) {
+    VTGS_REQUIRE(iters > 0 && sink != nullptr, "bad argument");
+    return launch_ffma_probe(iters, sink, threads_out, (cudaStream_t)stream);
 }
 
 int vtgs_profile_enable(int32_t on) {

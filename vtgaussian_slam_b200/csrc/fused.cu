@@ -16,20 +16,21 @@ __device__ __forceinline__ float sgn(float v) { return v > 0.0f ? 1.0f : (v < 0.
 // ---- exact median of depth_error = |gt - d| * (gt > 0) over the frame (reference :525-527, torch.median = the
 // LOWER median, element (P - 1) / 2 of the sorted values) by radix select: four passes, each a 256-bin histogram of
 // the next byte of the float bits (non-negative floats order like their bit patterns; NaN sorts last and, as in
-// torch, makes the median NaN) among the values matching the prefix selected so far; the block that finishes last
-// picks the bin holding the target rank.  state: hist[256], prefix, rank, nan_count, ticket, result bits.
-constexpr int MEDIAN_STATE_WORDS = 264;
+// torch, makes the median NaN) among the values matching the prefix selected so far, then one block picks the bin
+// holding the target rank.  The histogram pass covers the camera's tile-row band, so a sharded frame all-reduces the
+// first VTGS_MEDIAN_SUMMABLE_WORDS words between the two kernels.
+// state: hist[0..255], nan_count[256] | prefix[257], rank[258], result bits[259].
+constexpr int MEDIAN_STATE_WORDS = VTGS_MEDIAN_STATE_WORDS;
 __global__ void __launch_bounds__(256)
-median_pass_kernel(const float* __restrict__ depth_plane, const float* __restrict__ gt_depth, size_t P, int pass,
-                   unsigned int* __restrict__ st) {
+median_hist_kernel(const float* __restrict__ depth_plane, const float* __restrict__ gt_depth, size_t pix_begin, size_t pix_end,
+                   int pass, unsigned int* __restrict__ st) {
     __shared__ unsigned int sh[256];
-    __shared__ bool s_last;
     const int tid = threadIdx.x;
     sh[tid] = 0u;
     __syncthreads();
-    const unsigned int prefix = __ldcg(st + 256);
+    const unsigned int prefix = st[257];
     unsigned int nan_local = 0u;
-    for (size_t i = (size_t)blockIdx.x * 256 + tid; i < P; i += (size_t)gridDim.x * 256) {
+    for (size_t i = pix_begin + (size_t)blockIdx.x * 256 + tid; i < pix_end; i += (size_t)gridDim.x * 256) {
         const float gd = gt_depth[i], d = depth_plane[i];
         const float e = fabsf(gd - d) * (gd > 0.0f ? 1.0f : 0.0f);
         unsigned int key = __float_as_uint(e);
@@ -38,18 +39,19 @@ median_pass_kernel(const float* __restrict__ depth_plane, const float* __restric
     }
     __syncthreads();
     if (sh[tid]) atomicAdd(st + tid, sh[tid]);
-    if (nan_local) atomicAdd(st + 258, nan_local);
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) s_last = atomicAdd(st + 259, 1u) == gridDim.x - 1;
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    sh[tid] = __ldcg(st + tid);
+    if (nan_local) atomicAdd(st + 256, nan_local);
+}
+
+__global__ void __launch_bounds__(256)
+median_pick_kernel(unsigned long long P_total, int pass, unsigned int* __restrict__ st) {
+    __shared__ unsigned int sh[256];
+    const int tid = threadIdx.x;
+    sh[tid] = st[tid];
     st[tid] = 0u;                                        // clean histogram for the next pass / call
     __syncthreads();
     if (tid == 0) {
-        unsigned int rank = pass == 0 ? (unsigned int)((P - 1) / 2) : __ldcg(st + 257);
+        const unsigned int prefix = st[257];
+        unsigned int rank = pass == 0 ? (unsigned int)((P_total - 1) / 2) : st[258];
         unsigned int cum = 0u;
         int b = 0;
         for (; b < 255; ++b) {
@@ -57,14 +59,194 @@ median_pass_kernel(const float* __restrict__ depth_plane, const float* __restric
             cum += sh[b];
         }
         const unsigned int np = (prefix << 8) | (unsigned int)b;
-        st[256] = pass == 3 ? 0u : np;
-        st[257] = rank - cum;
+        st[257] = pass == 3 ? 0u : np;
+        st[258] = rank - cum;
         if (pass == 3) {
-            st[260] = __ldcg(st + 258) > 0u ? 0x7fc00000u : np;
-            st[258] = 0u;
+            st[259] = st[256] > 0u ? 0x7fc00000u : np;
+            st[256] = 0u;
         }
-        st[259] = 0u;
     }
+}
+
+static inline void band_pixel_range(const CamConst& cam, size_t& b, size_t& e) {
+    const size_t P = (size_t)cam.W * cam.H;
+    b = (size_t)cam.row0 * 16 * cam.W;
+    e = (size_t)cam.row1 * 16 * cam.W;
+    if (e > P) e = P;
+    if (b > e) b = e;
+}
+
+int launch_median_hist(const VtgsCamera* camera, const float* depth_plane, const float* gt_depth, int pass, uint32_t* state,
+                       cudaStream_t stream) {
+    const CamConst cam = make_cam_const(*camera);
+    size_t b, e;
+    band_pixel_range(cam, b, e);
+    if (e <= b) return VTGS_OK;
+    const int mb = (int)std::min<size_t>((e - b + 1023) / 1024, 148 * 4);
+    { VTGS_PROF("median_hist_kernel", stream); median_hist_kernel<<<mb, 256, 0, stream>>>(depth_plane, gt_depth, b, e, pass, state); }
+    VTGS_LAUNCH_CHECK();
+    return VTGS_OK;
+}
+
+int launch_median_pick(int64_t P_total, int pass, uint32_t* state, cudaStream_t stream) {
+    { VTGS_PROF("median_pick_kernel", stream); median_pick_kernel<<<1, 256, 0, stream>>>((unsigned long long)P_total, pass, state); }
+    VTGS_LAUNCH_CHECK();
+    return VTGS_OK;
+}
+
+// ---- Replica iteration-0 silhouette-threshold search (reference src/vtgaussian_slam.py:472-510) --------------------
+// The five masks are nested (0.990 < 0.993 < ... < 0.999), so a pixel is binned by the number of thresholds its
+// silhouette exceeds and the per-threshold sums are suffix sums of the bins.  Per-block partials + a deterministic
+// (fixed slice order, fp64) final reduction by the block that finishes last.
+constexpr int LADDER_N = 5;
+__device__ __constant__ float c_sil_ladder[LADDER_N] = {0.990f, 0.993f, 0.995f, 0.997f, 0.999f};
+__global__ void __launch_bounds__(256)
+sil_ladder_kernel(const __grid_constant__ CamConst cam, const float* __restrict__ image6, const float* __restrict__ gt_rgb,
+                  const float* __restrict__ gt_depth, float* __restrict__ partials, unsigned int* __restrict__ ticket,
+                  float* __restrict__ sums10) {
+    __shared__ float s_part[8][2 * LADDER_N];
+    __shared__ double s_sum[2 * LADDER_N][25];
+    __shared__ bool s_last;
+    const size_t P = (size_t)cam.W * cam.H;
+    const size_t row_begin = (size_t)cam.row0 * 16 * cam.W;
+    const size_t row_end = min(P, (size_t)cam.row1 * 16 * cam.W);
+    float sq[LADDER_N], cnt[LADDER_N];
+#pragma unroll
+    for (int k = 0; k < LADDER_N; ++k) { sq[k] = 0.f; cnt[k] = 0.f; }
+    for (int rep = 0; rep < 4; ++rep) {
+        const size_t pid = row_begin + ((size_t)blockIdx.x * 4 + rep) * 256 + threadIdx.x;
+        if (pid >= row_end) break;
+        const float sil = image6[4 * P + pid];
+        if (!(gt_depth[pid] > 0.0f)) continue;
+        const float er = gt_rgb[pid] - image6[pid], eg = gt_rgb[P + pid] - image6[P + pid], eb = gt_rgb[2 * P + pid] - image6[2 * P + pid];
+        const float e2 = er * er + eg * eg + eb * eb;
+#pragma unroll
+        for (int k = 0; k < LADDER_N; ++k)
+            if (sil > c_sil_ladder[k]) { sq[k] += e2; cnt[k] += 1.0f; }
+    }
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int k = 0; k < LADDER_N; ++k) { sq[k] = warp_sum(sq[k]); cnt[k] = warp_sum(cnt[k]); }
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < LADDER_N; ++k) { s_part[warp][k] = sq[k]; s_part[warp][LADDER_N + k] = cnt[k]; }
+    }
+    __syncthreads();
+    if (tid < 2 * LADDER_N) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += s_part[w][tid];
+        partials[(size_t)blockIdx.x * 2 * LADDER_N + tid] = s;
+        __threadfence();
+    }
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const int nblocks = gridDim.x;
+    if (tid < 250) {
+        const int term = tid % (2 * LADDER_N), sl = tid / (2 * LADDER_N);          // 25 slices
+        double acc = 0.0;
+        for (int b = sl; b < nblocks; b += 25) acc += (double)__ldcg(&partials[(size_t)b * 2 * LADDER_N + term]);
+        s_sum[term][sl] = acc;
+    }
+    __syncthreads();
+    if (tid < 2 * LADDER_N) {
+        double a = 0.0;
+        for (int i = 0; i < 25; ++i) a += s_sum[tid][i];
+        sums10[tid] = (float)a;
+    }
+    if (tid == 0) *ticket = 0u;
+}
+
+__global__ void sil_select_kernel(const float* __restrict__ sums10, float* __restrict__ thr_out, float* __restrict__ mse_out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int best = 0;
+    float best_mse = 0.0f;
+    bool have = false;
+    for (int k = 0; k < LADDER_N; ++k) {
+        const float c = sums10[LADDER_N + k];
+        if (!(c > 0.0f)) continue;                       // torch.mean of an empty selection is nan: never the minimum
+        const float mse = sums10[k] / (3.0f * c);
+        if (!have || mse < best_mse) { best = k; best_mse = mse; have = true; }
+    }
+    *thr_out = c_sil_ladder[best];
+    if (mse_out) *mse_out = have ? best_mse : __uint_as_float(0x7fc00000u);
+}
+
+int launch_sil_ladder(const VtgsCamera* camera, const float* image6, const float* gt_rgb, const float* gt_depth, float* sums10,
+                      float* scratch, cudaStream_t stream) {
+    const CamConst cam = make_cam_const(*camera);
+    size_t b, e;
+    band_pixel_range(cam, b, e);
+    const int nblocks = (int)((e - b + 1023) / 1024);
+    if (nblocks <= 0) { VTGS_CUDA_CHECK(cudaMemsetAsync(sums10, 0, 10 * sizeof(float), stream)); return VTGS_OK; }
+    // the loss scratch (vtgs_loss_scratch_floats, mode 0) = [tracking-loss region: 4 floats per 1024-pixel block of the
+    // whole frame, its ticket, the median state | ladder region: 10 floats per block, its ticket]: the two never overlap,
+    // so the tracking loss's self-resetting ticket stays intact
+    const size_t nb_full = ((size_t)cam.W * cam.H + 1023) / 1024;
+    float* part = scratch + nb_full * 4 + 320;
+    unsigned int* ticket = reinterpret_cast<unsigned int*>(part + nb_full * 2 * LADDER_N);
+    VTGS_CUDA_CHECK(cudaMemsetAsync(ticket, 0, sizeof(unsigned int), stream));
+    { VTGS_PROF("sil_ladder_kernel", stream); sil_ladder_kernel<<<nblocks, 256, 0, stream>>>(cam, image6, gt_rgb, gt_depth, part, ticket, sums10); }
+    VTGS_LAUNCH_CHECK();
+    return VTGS_OK;
+}
+
+int launch_sil_select(const float* sums10, float* sil_thres_dev, float* min_mse_dev, cudaStream_t stream) {
+    { VTGS_PROF("sil_select_kernel", stream); sil_select_kernel<<<1, 32, 0, stream>>>(sums10, sil_thres_dev, min_mse_dev); }
+    VTGS_LAUNCH_CHECK();
+    return VTGS_OK;
+}
+
+// ---- non-presence mask of the silhouette-driven Gaussian addition (reference src/vtgaussian_slam.py:747-760) ----
+__global__ void __launch_bounds__(256)
+nonpresence_mask_kernel(size_t P, const float* __restrict__ image6, const float* __restrict__ gt_depth, float sil_thres,
+                        const unsigned int* __restrict__ median_state, uint8_t* __restrict__ mask_out, unsigned int* __restrict__ count) {
+    const size_t pid = (size_t)blockIdx.x * 256 + threadIdx.x;
+    const float thr = 50.0f * __uint_as_float(median_state[259]);
+    bool m = false;
+    if (pid < P) {
+        const float d = image6[3 * P + pid], sil = image6[4 * P + pid], gd = gt_depth[pid];
+        const float err = fabsf(gd - d) * (gd > 0.0f ? 1.0f : 0.0f);
+        m = (sil < sil_thres) || ((d > gd) && (err > thr));
+        mask_out[pid] = m ? 1 : 0;
+    }
+    if (count) {
+        const unsigned int b = __ballot_sync(VTGS_FULL_MASK, m);
+        if ((threadIdx.x & 31) == 0 && b) atomicAdd(count, (unsigned int)__popc(b));
+    }
+}
+
+int launch_nonpresence_mask(const VtgsCamera* camera, const float* image6, const float* gt_depth, float sil_thres,
+                            const uint32_t* median_state, uint8_t* mask_out, uint32_t* count_dev, cudaStream_t stream) {
+    const size_t P = (size_t)camera->image_width * camera->image_height;
+    if (count_dev) VTGS_CUDA_CHECK(cudaMemsetAsync(count_dev, 0, sizeof(uint32_t), stream));
+    { VTGS_PROF("nonpresence_mask_kernel", stream); nonpresence_mask_kernel<<<(unsigned)((P + 255) / 256), 256, 0, stream>>>(P, image6, gt_depth, sil_thres, median_state, mask_out, count_dev); }
+    VTGS_LAUNCH_CHECK();
+    return VTGS_OK;
+}
+
+// ---- FP32 FMA throughput probe ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ffma_probe_kernel(long long iters, float* __restrict__ sink) {
+    float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
+    const float m = 0.999f, c = 1e-4f;
+    for (long long i = 0; i < iters; ++i) {
+        a0 = fmaf(a0, m, c); a1 = fmaf(a1, m, c); a2 = fmaf(a2, m, c); a3 = fmaf(a3, m, c);
+        a4 = fmaf(a4, m, c); a5 = fmaf(a5, m, c); a6 = fmaf(a6, m, c); a7 = fmaf(a7, m, c);
+    }
+    const float r = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (r == 123456.789f) *sink = r;                     // never true: keeps the loop alive
+}
+
+int launch_ffma_probe(int64_t iters, float* sink, uint64_t* threads_out, cudaStream_t stream) {
+    const int blocks = 148 * 8;                          // 8 resident blocks of 256 threads per SM: 64 warps / SM
+    if (threads_out) *threads_out = (uint64_t)blocks * 256;
+    { VTGS_PROF("ffma_probe_kernel", stream); ffma_probe_kernel<<<blocks, 256, 0, stream>>>((long long)iters, sink); }
+    VTGS_LAUNCH_CHECK();
+    return VTGS_OK;
 }
 
 // Tracking loss (mode 0): sums of masked absolute differences; dL/dplane = w * sign * mask.
@@ -83,7 +265,8 @@ tracking_loss_kernel(const __grid_constant__ CamConst cam, VtgsLossConfig cfg, c
     const size_t row_begin = (size_t)cam.row0 * 16 * cam.W;
     const size_t row_end = min(P, (size_t)cam.row1 * 16 * cam.W);
     // outlier mask: depth_error < 50 * median(depth_error) (NaN median: nothing passes)
-    const float outlier_thr = median_state ? 50.0f * __uint_as_float(__ldcg(median_state + 260)) : 0.0f;
+    const float outlier_thr = median_state ? 50.0f * __uint_as_float(__ldcg(median_state + 259)) : 0.0f;
+    const float sil_thres = cfg.sil_thres_dev ? __ldcg(cfg.sil_thres_dev) : cfg.sil_thres;
     float ld = 0.f, li = 0.f, cnt = 0.f;
     // all of a thread's loads are issued before the first dependent use (10 planes x LOSS_PX_PER_THREAD pixels in flight)
     float in[LOSS_PX_PER_THREAD][10];
@@ -108,7 +291,7 @@ tracking_loss_kernel(const __grid_constant__ CamConst cam, VtgsLossConfig cfg, c
         const float gd = in[rep][9];
         const float unc = dsq - d * d;
         bool mask = gd > 0.0f && !(d != d) && !(unc != unc);
-        if (cfg.use_sil_for_loss) mask = mask && sil > cfg.sil_thres;
+        if (cfg.use_sil_for_loss) mask = mask && sil > sil_thres;
         if (cfg.far_depth_thres > 0.0f) mask = mask && gd < cfg.far_depth_thres;
         if (median_state) mask = mask && (fabsf(gd - d) * (gd > 0.0f ? 1.0f : 0.0f) < outlier_thr);
         if (cfg.pixel_mask) mask = mask && cfg.pixel_mask[pid] != 0;
@@ -421,6 +604,44 @@ retie_kernel(float* __restrict__ means3D, int64_t n, const Mat34 old, const floa
     means3D[3 * i + 2] = R[2] * cx + R[5] * cy + R[8] * cz;
 }
 
+// The same with the OLD pose on the device too (the mapping step snapshots the pose before its Adam update): no host
+// round trip, so the mapping iteration stays free of synchronisation.
+__global__ void __launch_bounds__(256)
+retie_dev_kernel(float* __restrict__ means3D, int64_t n, const float* __restrict__ q_old, const float* __restrict__ t_old,
+                 const float* __restrict__ q_un, const float* __restrict__ t) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    float Ro[9], Rn[9];
+    {
+        const float u0 = q_old[0], u1 = q_old[1], u2 = q_old[2], u3 = q_old[3];
+        const float n1 = fmaxf(sqrtf(u0 * u0 + u1 * u1 + u2 * u2 + u3 * u3), 1e-12f);
+        float q0 = u0 / n1, q1 = u1 / n1, q2 = u2 / n1, q3 = u3 / n1;
+        const float n2 = sqrtf(q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3);
+        quat_to_R(q0 / n2, q1 / n2, q2 / n2, q3 / n2, Ro);
+    }
+    {
+        const float u0 = q_un[0], u1 = q_un[1], u2 = q_un[2], u3 = q_un[3];
+        const float n1 = fmaxf(sqrtf(u0 * u0 + u1 * u1 + u2 * u2 + u3 * u3), 1e-12f);
+        float q0 = u0 / n1, q1 = u1 / n1, q2 = u2 / n1, q3 = u3 / n1;
+        const float n2 = sqrtf(q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3);
+        quat_to_R(q0 / n2, q1 / n2, q2 / n2, q3 / n2, Rn);
+    }
+    const float x = means3D[3 * i], y = means3D[3 * i + 1], z = means3D[3 * i + 2];
+    const float cx = Ro[0] * x + Ro[1] * y + Ro[2] * z + t_old[0] - t[0];
+    const float cy = Ro[3] * x + Ro[4] * y + Ro[5] * z + t_old[1] - t[1];
+    const float cz = Ro[6] * x + Ro[7] * y + Ro[8] * z + t_old[2] - t[2];
+    means3D[3 * i] = Rn[0] * cx + Rn[3] * cy + Rn[6] * cz;          // R_new^T (p_cam - t_new)
+    means3D[3 * i + 1] = Rn[1] * cx + Rn[4] * cy + Rn[7] * cz;
+    means3D[3 * i + 2] = Rn[2] * cx + Rn[5] * cy + Rn[8] * cz;
+}
+
+int launch_retie_dev(float* means3D, int64_t n, const float* q_old, const float* t_old, const float* q_un, const float* t, cudaStream_t stream) {
+    if (n <= 0) return VTGS_OK;
+    { VTGS_PROF("retie_kernel", stream); retie_dev_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(means3D, n, q_old, t_old, q_un, t); }
+    VTGS_LAUNCH_CHECK();
+    return VTGS_OK;
+}
+
 int launch_retie(float* means3D, int64_t n, const float* w2c_old_rowmajor12, const float* q_un, const float* t, cudaStream_t stream) {
     if (n <= 0) return VTGS_OK;
     Mat34 m;
@@ -442,8 +663,9 @@ int launch_loss(const VtgsCamera* camera, const VtgsLossConfig* cfg, const float
                 const float* gt_rgb, const float* gt_depth, float* dL_dimage4, float* loss_terms,
                 float* scratch, cudaStream_t stream) {
     const CamConst cam = make_cam_const(*camera);
-    if (cfg->ignore_outlier_depth && (cfg->mode != 0 || cam.row0 != 0 || cam.row1 != cam.gy)) {
-        set_error("ignore_outlier_depth_loss (frame-wide median mask) is fused for whole-frame tracking only");
+    if (cfg->ignore_outlier_depth && cfg->mode != 0) { set_error("ignore_outlier_depth_loss is a tracking option"); return VTGS_E_UNSUPPORTED; }
+    if (cfg->ignore_outlier_depth && cfg->median_state == nullptr && (cam.row0 != 0 || cam.row1 != cam.gy)) {
+        set_error("ignore_outlier_depth_loss with a tile-row band needs VtgsLossConfig.median_state (vtgs_median_hist / all-reduce / vtgs_median_pick)");
         return VTGS_E_UNSUPPORTED;
     }
     if (!cfg->use_l1) { set_error("use_l1 = False is not supported"); return VTGS_E_UNSUPPORTED; }
@@ -468,17 +690,18 @@ int launch_loss(const VtgsCamera* camera, const VtgsLossConfig* cfg, const float
     const int nblocks = (int)((npx + 256 * LOSS_PX_PER_THREAD - 1) / (256 * LOSS_PX_PER_THREAD));
     if (nblocks > 0) {
         unsigned int* ticket = reinterpret_cast<unsigned int*>(scratch + (size_t)nblocks * LOSS_TERMS);
-        unsigned int* median_state = nullptr;
-        if (cfg->ignore_outlier_depth) {
-            median_state = ticket + 16;
+        const unsigned int* median_state = nullptr;
+        if (cfg->ignore_outlier_depth && cfg->median_state != nullptr) {
+            median_state = cfg->median_state;
+        } else if (cfg->ignore_outlier_depth) {
+            unsigned int* st = ticket + 16;
             const size_t P = (size_t)cam.W * cam.H;
-            const int mb = (int)std::min<size_t>((P + 1023) / 1024, 148 * 4);
-            VTGS_CUDA_CHECK(cudaMemsetAsync(median_state, 0, MEDIAN_STATE_WORDS * sizeof(unsigned int), stream));
+            VTGS_CUDA_CHECK(cudaMemsetAsync(st, 0, MEDIAN_STATE_WORDS * sizeof(unsigned int), stream));
             for (int pass = 0; pass < 4; ++pass) {
-                VTGS_PROF("median_pass_kernel", stream);
-                median_pass_kernel<<<mb, 256, 0, stream>>>(image6 + 3 * P, gt_depth, P, pass, median_state);
+                if (int e = launch_median_hist(camera, image6 + 3 * P, gt_depth, pass, st, stream)) return e;
+                if (int e = launch_median_pick((int64_t)P, pass, st, stream)) return e;
             }
-            VTGS_LAUNCH_CHECK();
+            median_state = st;
         }
         { VTGS_PROF("tracking_loss_kernel", stream); tracking_loss_kernel<<<nblocks, 256, 0, stream>>>(cam, *cfg, image6, gt_rgb, gt_depth, dL_dimage4, scratch, ticket, loss_terms, median_state); }
         VTGS_LAUNCH_CHECK();
@@ -540,21 +763,21 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
 // the smallest loss; the loss of an iteration belongs to the pose BEFORE that iteration's step).
 __global__ void tracking_update_kernel(float* __restrict__ cam_q, float* __restrict__ cam_t, const float* __restrict__ msg,
                                        float* __restrict__ adam, int32_t* __restrict__ step_dev, float* __restrict__ best,
-                                       float lr_rot, float lr_trans, float b1, float b2, float eps) {
+                                       float lr_rot, float lr_trans, float b1, float b2, float eps, int flags) {
     const int k = threadIdx.x;           // 0..3 quaternion, 4..6 translation
     __shared__ int s_step;
     __shared__ bool s_better;
     if (k == 0) {
         s_step = *step_dev + 1;
         *step_dev = s_step;
-        const float loss = msg[8];
-        s_better = loss < best[0];
-        if (s_better) best[0] = loss;
+        const float metric = (flags & VTGS_TRACK_CALLER_METRIC) ? msg[15] : msg[8];
+        s_better = metric < best[0];
+        if (s_better) best[0] = metric;
     }
     __syncthreads();
     if (k >= 7) return;
     float* p = k < 4 ? cam_q + k : cam_t + (k - 4);
-    if (s_better) best[1 + k] = *p;
+    if (s_better && !(flags & VTGS_TRACK_BOOK_POST_STEP)) best[1 + k] = *p;
     const float g = msg[k];
     float* m = adam + (k < 4 ? k : 8 + (k - 4));
     float* v = adam + (k < 4 ? 4 + k : 11 + (k - 4));
@@ -564,12 +787,14 @@ __global__ void tracking_update_kernel(float* __restrict__ cam_q, float* __restr
     const float vi = b2 * *v + (1.0f - b2) * g * g;
     *m = mi; *v = vi;
     const float denom = sqrtf(vi) / (float)sqrt(bc2) + eps;
-    *p = *p - step_size * (mi / denom);
+    const float pn = *p - step_size * (mi / denom);
+    *p = pn;
+    if (s_better && (flags & VTGS_TRACK_BOOK_POST_STEP)) best[1 + k] = pn;
 }
 
 int launch_tracking_update(float* cam_q, float* cam_t, const float* msg, float* adam, int32_t* step_dev, float* best,
-                           float lr_rot, float lr_trans, float eps, cudaStream_t stream) {
-    { VTGS_PROF("tracking_update_kernel", stream); tracking_update_kernel<<<1, 32, 0, stream>>>(cam_q, cam_t, msg, adam, step_dev, best, lr_rot, lr_trans, 0.9f, 0.999f, eps); }
+                           float lr_rot, float lr_trans, float eps, int flags, cudaStream_t stream) {
+    { VTGS_PROF("tracking_update_kernel", stream); tracking_update_kernel<<<1, 32, 0, stream>>>(cam_q, cam_t, msg, adam, step_dev, best, lr_rot, lr_trans, 0.9f, 0.999f, eps, flags); }
     VTGS_LAUNCH_CHECK();
     return VTGS_OK;
 }

@@ -51,8 +51,17 @@ int launch_loss(const VtgsCamera* cam, const VtgsLossConfig* cfg, const float* i
                 const float* gt_rgb, const float* gt_depth, float* dL_dimage4, float* loss_terms,
                 float* scratch, cudaStream_t stream);
 int launch_tracking_update(float* cam_q, float* cam_t, const float* msg, float* adam, int32_t* step_dev, float* best,
-                           float lr_rot, float lr_trans, float eps, cudaStream_t stream);
+                           float lr_rot, float lr_trans, float eps, int flags, cudaStream_t stream);
+int launch_median_hist(const VtgsCamera* cam, const float* depth_plane, const float* gt_depth, int pass, uint32_t* state, cudaStream_t stream);
+int launch_median_pick(int64_t P_total, int pass, uint32_t* state, cudaStream_t stream);
+int launch_sil_ladder(const VtgsCamera* cam, const float* image6, const float* gt_rgb, const float* gt_depth, float* sums10,
+                      float* scratch, cudaStream_t stream);
+int launch_sil_select(const float* sums10, float* sil_thres_dev, float* min_mse_dev, cudaStream_t stream);
+int launch_nonpresence_mask(const VtgsCamera* cam, const float* image6, const float* gt_depth, float sil_thres,
+                            const uint32_t* median_state, uint8_t* mask_out, uint32_t* count_dev, cudaStream_t stream);
+int launch_ffma_probe(int64_t iters, float* sink, uint64_t* threads_out, cudaStream_t stream);
 int launch_retie(float* means3D, int64_t n, const float* w2c_old_rowmajor12, const float* q_un, const float* t, cudaStream_t stream);
+int launch_retie_dev(float* means3D, int64_t n, const float* q_old, const float* t_old, const float* q_un, const float* t, cudaStream_t stream);
 int launch_adam(float* param, const float* grad, float* m, float* v, int64_t n, float lr, float b1,
                 float b2, float eps, int step, const int32_t* step_dev, cudaStream_t stream);
 

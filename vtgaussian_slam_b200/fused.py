@@ -17,7 +17,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from .rasterizer import Workspace, _ptr, _require_cuda, _stream_ptr, camera_struct
+from .rasterizer import _PAIR_RATIO, Workspace, _ptr, _require_cuda, _stream_ptr, camera_struct
 
 PARAM_KEYS = ("means3D", "rgb_colors", "unnorm_rotations", "logit_opacities", "log_scales")
 
@@ -37,7 +37,9 @@ class FusedRenderer:
         self.cam = camera_struct(settings, tile_rows=tile_rows)
         self.W, self.H, self.N = self.cam.image_width, self.cam.image_height, int(num_gaussians)
         if pair_capacity is None:
-            pair_capacity = int(self.N * 6) + 65536
+            # R / N observed on this device so far (view-tied sections: ~2 tiles per Gaussian), with head room; a
+            # renderer that still overflows is grown by ensure_capacity() and the forward repeated
+            pair_capacity = int(self.N * max(6.0, 1.5 * _PAIR_RATIO.get(self.device, 0.0))) + 65536
         self.ws = Workspace(self.device, self.W, self.H, self.N, pair_capacity)
         self.ws.ensure_grad_geom()
         self.depth_row = tuple(float(v) for v in depth_row)
@@ -50,7 +52,10 @@ class FusedRenderer:
         self._loss_scratch = torch.zeros(int(L.vtgs_loss_scratch_floats(self.W, self.H, 0)), **f32)
         self._pose_scratch = torch.zeros(int(L.vtgs_pose_scratch_floats(self.N)), **f32)
         self._map_scratch = None
+        self._median_state = None
+        self._sil = None                    # [0:10] ladder sums, [10] chosen threshold, [11] its MSE
         self._bufs = self.ws.struct()
+        self.polls = 0
 
     # -- helpers ---------------------------------------------------------------------------
     def reserve_pairs(self, cap):
@@ -59,7 +64,70 @@ class FusedRenderer:
 
     def overflowed(self):
         R, overflow, _ = self.ws.read_counters()
+        if self.N > 0:
+            _PAIR_RATIO[self.device] = max(_PAIR_RATIO.get(self.device, 0.0), R / self.N)
         return bool(overflow), R
+
+    def ensure_capacity(self):
+        """One blocking read of the device counters.  -> True if the last forward overflowed the pair buffers: they
+        have been enlarged and the forward (and everything derived from it) must be repeated."""
+        overflow, R = self.overflowed()
+        if overflow:
+            self.reserve_pairs(int(R * 1.5) + 65536)
+        return overflow
+
+    @property
+    def nbytes(self):
+        """Approximate device memory held by this renderer (pool accounting in slam_ops)."""
+        cap, P = self.ws.pair_capacity, self.W * self.H
+        return int(self.N * (64 + 4 + 64 + 4) + cap * (8 + 4 + 64 + 32) + P * (6 + 4 + 2 + 12) * 4)
+
+    def median_state(self, image6=None, gt_depth=None, process_group=None, num_pixels_total=None):
+        """Radix-select state of median(|gt - depth| (gt > 0)) over the frame (reference :525-527, :757-758) for the
+        last forward.  With a process group every rank histograms its tile-row band and the histograms are
+        all-reduced between the two kernels of each pass, so all ranks pick the same (frame-wide) median."""
+        L = _lib.lib()
+        if self._median_state is None:
+            self._median_state = torch.zeros(_lib.MEDIAN_STATE_WORDS, dtype=torch.int32, device=self.device)
+        st = self._median_state
+        st.zero_()
+        img = self.image6 if image6 is None else image6
+        P = self.W * self.H if num_pixels_total is None else int(num_pixels_total)
+        with torch.cuda.device(self.device):
+            for ps in range(4):
+                _lib.check(L.vtgs_median_hist(C.byref(self.cam), _ptr(img[3]), _ptr(gt_depth), ps, _ptr(st), _stream_ptr(self.device)))
+                if process_group is not None:
+                    torch.distributed.all_reduce(st[:_lib.MEDIAN_SUMMABLE_WORDS], group=process_group)
+                _lib.check(L.vtgs_median_pick(P, ps, _ptr(st), _stream_ptr(self.device)))
+        return st
+
+    def sil_ladder(self, gt_rgb, gt_depth, image6=None, process_group=None):
+        """Replica's iteration-0 threshold search (reference :472-510) on the last forward, on the device.
+        -> tensor[12]: ten sums, the chosen threshold [10] and its MSE [11]; [10:11] can be handed to tracking_loss as
+        `sil_thres_dev`.  With a process group the ten band sums are all-reduced before the choice."""
+        L = _lib.lib()
+        if self._sil is None:
+            self._sil = torch.zeros(12, dtype=torch.float32, device=self.device)
+        img = self.image6 if image6 is None else image6
+        with torch.cuda.device(self.device):
+            _lib.check(L.vtgs_sil_ladder(C.byref(self.cam), _ptr(img), _ptr(gt_rgb), _ptr(gt_depth), _ptr(self._sil),
+                                         _ptr(self._loss_scratch), _stream_ptr(self.device)))
+            if process_group is not None:
+                torch.distributed.all_reduce(self._sil[:10], group=process_group)
+            _lib.check(L.vtgs_sil_select(_ptr(self._sil), _ptr(self._sil[10:]), _ptr(self._sil[11:]), _stream_ptr(self.device)))
+        return self._sil
+
+    def nonpresence_mask(self, gt_depth, sil_thres=0.5, image6=None):
+        """Non-presence mask of the reference's silhouette-driven Gaussian addition (add_new_gaussians_base_frame,
+        src/vtgaussian_slam.py:747-760) for the last forward: -> (mask[H,W] uint8, count[1] int32), both on the device."""
+        img = self.image6 if image6 is None else image6
+        st = self.median_state(img, gt_depth)
+        mask = torch.empty((self.H, self.W), dtype=torch.uint8, device=self.device)
+        count = torch.zeros(1, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().vtgs_nonpresence_mask(C.byref(self.cam), _ptr(img), _ptr(gt_depth), float(sil_thres), _ptr(st),
+                                                        _ptr(mask), _ptr(count), _stream_ptr(self.device)))
+        return mask, count
 
     def _params_struct(self, params):
         p = _lib.VtgsParams()
@@ -97,10 +165,13 @@ class FusedRenderer:
         return self.image6, self.radii[:self.N]
 
     def tracking_loss(self, gt_rgb, gt_depth, w_im=0.5, w_depth=0.025, use_sil_for_loss=True, sil_thres=0.99,
-                      far_depth_thres=0.0, image6=None, ignore_outlier_depth_loss=False, pixel_mask=None):
+                      far_depth_thres=0.0, image6=None, ignore_outlier_depth_loss=False, pixel_mask=None,
+                      sil_thres_dev=None, median_state=None):
         """Masked-L1 tracking loss (reference get_loss :513-605,:678-679) of the last forward.
         ignore_outlier_depth_loss: also drop pixels whose depth error is >= 50x its frame median (:525-528);
         pixel_mask: optional [H,W] uint8 / bool CUDA tensor, 0 = masked out (the overlap-visibility mask, :536-583).
+        sil_thres_dev: optional device float overriding sil_thres (sil_ladder()[10:11]); median_state: a finished
+        median_state() (needed with a tile-row band, where the median is a frame-wide quantity).
         -> loss_terms[8] (device): loss, w_im*im, w_depth*depth, mask count, ...; fills dL_dimage4."""
         pm = None
         if pixel_mask is not None:
@@ -109,7 +180,8 @@ class FusedRenderer:
             pm = (pm if pm.dtype == torch.uint8 else pm.to(torch.uint8)).contiguous()
             self._pixel_mask = pm               # keep alive until the kernel has run
         cfg = _lib.VtgsLossConfig(0, int(bool(use_sil_for_loss)), int(bool(ignore_outlier_depth_loss)), 1, float(sil_thres),
-                                  float(w_im), float(w_depth), float(far_depth_thres), _ptr(pm))
+                                  float(w_im), float(w_depth), float(far_depth_thres), _ptr(pm), _ptr(sil_thres_dev),
+                                  _ptr(median_state))
         img = self.image6 if image6 is None else image6
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().vtgs_loss(C.byref(self.cam), C.byref(cfg), _ptr(img), _ptr(gt_rgb), _ptr(gt_depth),
@@ -180,25 +252,47 @@ def adam_step(param, grad, exp_avg, exp_avg_sq, lr, step=None, step_dev=None, be
                                         _stream_ptr(param.device)))
 
 
+def retie_dev(means3D, old_q, old_t, cam_q, cam_t):
+    """retie() with the old pose on the device (un-normalised quaternion [4] + translation [3]): no host round trip."""
+    _require_cuda("means3D", means3D)
+    if not means3D.is_contiguous() or means3D.dtype != torch.float32:
+        raise ValueError("means3D must be a contiguous float32 tensor (a row slice is fine)")
+    with torch.cuda.device(means3D.device):
+        _lib.check(_lib.lib().vtgs_retie_dev(_ptr(means3D), means3D.shape[0], _ptr(old_q), _ptr(old_t), _ptr(cam_q), _ptr(cam_t),
+                                             _stream_ptr(means3D.device)))
+    return means3D
+
+
 class TrackingSolver:
     """The reference's per-frame tracking loop (src/vtgaussian_slam.py:1794-1970) for one frame:
     num_iters x (get_loss(tracking=True) -> backward -> Adam on the 7 pose numbers), keeping
     the best pose by loss.  Gaussians are frozen (their tracking LRs are 0, configs/replica/room0.py:78-86).
 
     One iteration = 9 kernel launches, no host synchronisation; with use_graph the iteration is
-    captured once and replayed."""
+    captured once and replayed.
 
-    LAUNCHES_PER_ITER = 9          # K1', scan, scatter, sort, K5', loss, K6', K7', update (+4 median passes with ignore_outlier_depth_loss)
+    replica_sil_search: the reference's Replica branch (:472-510) -- at the FIRST iteration of a frame the silhouette
+        threshold is chosen among {0.990 .. 0.999} by the masked colour MSE, on the device (one ladder kernel + a
+        one-thread choice; 10 floats all-reduced when sharded), and kept for the frame's other iterations.
+    ignore_outlier_depth_loss: the frame-wide median mask (:525-528); with a process group the radix-select
+        histograms are all-reduced, so every rank uses the same median.
+    book_post_step: keep the pose AFTER the step whose loss was the smallest (what the reference does, :1888-1970);
+        False keeps the pose the loss was evaluated at."""
+
+    LAUNCHES_PER_ITER = 9          # K1', scan, scatter, sort, K5', loss, K6', K7', update (+8 median launches with ignore_outlier_depth_loss)
 
     def __init__(self, settings, params, device="cuda:0", lr_rot=4e-4, lr_trans=2e-3, w_im=0.5, w_depth=0.025,
                  use_sil_for_loss=True, sil_thres=0.99, tile_rows=(0, 0), pair_capacity=None, use_graph=True,
-                 process_group=None, ignore_outlier_depth_loss=False, far_depth_thres=0.0):
+                 process_group=None, ignore_outlier_depth_loss=False, far_depth_thres=0.0, replica_sil_search=False,
+                 book_post_step=True):
         self.device = torch.device(device)
         self.params = {k: params[k].detach().to(self.device).float().contiguous() for k in PARAM_KEYS}
         N = self.params["means3D"].shape[0]
         self.r = FusedRenderer(settings, N, device=self.device, tile_rows=tile_rows, pair_capacity=pair_capacity)
         self.cfg = dict(w_im=w_im, w_depth=w_depth, use_sil_for_loss=use_sil_for_loss, sil_thres=sil_thres,
                         ignore_outlier_depth_loss=ignore_outlier_depth_loss, far_depth_thres=far_depth_thres)
+        self.replica_sil_search = bool(replica_sil_search) and bool(use_sil_for_loss)
+        self.flags = _lib.TRACK_BOOK_POST_STEP if book_post_step else 0
         self.lr_rot, self.lr_trans = lr_rot, lr_trans
         f32 = dict(dtype=torch.float32, device=self.device)
         self.cam_q = torch.tensor([1.0, 0, 0, 0], **f32)
@@ -217,23 +311,38 @@ class TrackingSolver:
         self.pg = process_group
         self.use_graph = use_graph
         self._graph = None
+        self._graph0 = None              # the frame's first iteration when it differs (replica_sil_search)
+        self._it = 0                     # iterations since set_frame
+        self._init = None
 
     def set_frame(self, gt_rgb, gt_depth, cam_q, cam_t):
         """New frame: targets, initial pose (e.g. constant-velocity propagated) and a fresh Adam
         state -- the reference re-creates its optimiser every frame (:1678-1758)."""
         self.gt_rgb.copy_(gt_rgb, non_blocking=True)
         self.gt_depth.copy_(gt_depth.reshape(self.gt_depth.shape), non_blocking=True)
-        self.cam_q.copy_(torch.as_tensor(cam_q).reshape(4), non_blocking=True)
-        self.cam_t.copy_(torch.as_tensor(cam_t).reshape(3), non_blocking=True)
+        self._init = (torch.as_tensor(cam_q, dtype=torch.float32).reshape(4).clone(), torch.as_tensor(cam_t, dtype=torch.float32).reshape(3).clone())
+        self._reset_pose()
+
+    def _reset_pose(self):
+        self.cam_q.copy_(self._init[0], non_blocking=True)
+        self.cam_t.copy_(self._init[1], non_blocking=True)
         self.adam.zero_()
         self.step_dev.zero_()
         self.best.zero_()
         self.best[0] = float("inf")
+        self._it = 0
 
-    def _iteration(self):
+    def _iteration(self, first=False):
         r = self.r
         r.forward(self.params, self.cam_q, self.cam_t)
-        r.tracking_loss(self.gt_rgb, self.gt_depth, **self.cfg)
+        extra = {}
+        if self.cfg["ignore_outlier_depth_loss"] and self.pg is not None:
+            extra["median_state"] = r.median_state(gt_depth=self.gt_depth, process_group=self.pg)
+        if self.replica_sil_search:
+            if first:
+                r.sil_ladder(self.gt_rgb, self.gt_depth, process_group=self.pg)
+            extra["sil_thres_dev"] = r._sil[10:11]
+        r.tracking_loss(self.gt_rgb, self.gt_depth, **self.cfg, **extra)
         r.backward(self.params, self.cam_q, self.cam_t, pose_grads=(self.d_q, self.d_t))
         if self.pg is not None:
             # tile-band sharding: every rank holds its band's partial sums; one 16-float all-reduce
@@ -242,49 +351,78 @@ class TrackingSolver:
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().vtgs_tracking_update(_ptr(self.cam_q), _ptr(self.cam_t), _ptr(self.msg), _ptr(self.adam),
                                                        _ptr(self.step_dev), _ptr(self.best), float(self.lr_rot),
-                                                       float(self.lr_trans), 1e-8, _stream_ptr(self.device)))
+                                                       float(self.lr_trans), 1e-8, int(self.flags), _stream_ptr(self.device)))
+
+    def _capture(self, first):
+        # warm-up on a side stream, then capture; the solver state is restored around both
+        s = torch.cuda.Stream(self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        state = (self.cam_q, self.cam_t, self.adam, self.step_dev, self.best)
+        snap = [t.clone() for t in state]
+        with torch.cuda.stream(s):
+            self._iteration(first)
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        for t, v in zip(state, snap):
+            t.copy_(v)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._iteration(first)
+        for t, v in zip(state, snap):
+            t.copy_(v)
+        return g
 
     def step(self):
+        first = self._it == 0 and self.replica_sil_search
+        self._it += 1
         if not self.use_graph:
-            self._iteration()
+            self._iteration(first)
+            return
+        if first:
+            if self._graph0 is None:
+                self._graph0 = self._capture(True)
+            self._graph0.replay()
             return
         if self._graph is None:
-            # warm-up on a side stream, then capture
-            s = torch.cuda.Stream(self.device)
-            s.wait_stream(torch.cuda.current_stream(self.device))
-            state = (self.cam_q, self.cam_t, self.adam, self.step_dev, self.best)
-            snap = [t.clone() for t in state]
-            with torch.cuda.stream(s):
-                self._iteration()
-            torch.cuda.current_stream(self.device).wait_stream(s)
-            for t, v in zip(state, snap):
-                t.copy_(v)
-            self._graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self._graph):
-                self._iteration()
-            for t, v in zip(state, snap):
-                t.copy_(v)
+            if self.replica_sil_search and self.r._sil is None:
+                self.r.sil_ladder(self.gt_rgb, self.gt_depth, process_group=self.pg)      # allocates the threshold the graph reads
+            self._graph = self._capture(False)
         self._graph.replay()
 
     def loss_terms(self):
         return self.msg[8:16]
 
-    def check(self, grow=True):
-        """One blocking read of the device counters (call once per frame, not per iteration): raises if the pair
-        buffers overflowed (R > pair_capacity: that iteration's render was truncated); with grow=True the buffers
-        are first enlarged so that the next frame fits."""
+    def check(self, grow=True, raise_on_overflow=True):
+        """One blocking read of the device counters (call once per frame, not per iteration).  If the pair buffers
+        overflowed (R > pair_capacity: the renders of this frame were truncated) they are enlarged (grow=True) and the
+        captured graphs dropped; then either raises or returns None so that the caller re-runs the frame
+        (`run_frame` does).  -> R otherwise."""
         overflow, R = self.r.overflowed()
         if overflow:
             if grow:
                 self.r.reserve_pairs(int(R * 1.5) + 65536)
-                self._graph = None          # buffer addresses changed: re-capture
-            raise _lib.VtgsError(f"pair buffer overflow: R = {R} > capacity; buffers "
-                                 f"{'were grown -- re-run the frame' if grow else 'unchanged'}")
+                self._graph = self._graph0 = None          # buffer addresses changed: re-capture
+            if raise_on_overflow:
+                raise _lib.VtgsError(f"pair buffer overflow: R = {R} > capacity; buffers "
+                                     f"{'were grown -- re-run the frame' if grow else 'unchanged'}")
+            return None
         return R
+
+    def run_frame(self, num_iters):
+        """num_iters iterations from the pose given to set_frame, one blocking read of the result, and -- if the pair
+        buffers turned out too small for this frame -- a transparent re-run with larger ones.
+        -> best[8] on the host: (best loss, best cam_unnorm_rot[4], best cam_trans[3])."""
+        for attempt in range(3):
+            for _ in range(num_iters):
+                self.step()
+            best = self.best.cpu()
+            if self.check(grow=True, raise_on_overflow=False) is not None:
+                return best
+            self._reset_pose()
+        raise _lib.VtgsError("pair buffer overflow persisted after regrowing")
 
 
 class MappingSolver:
-    """The reference's mapping iteration (src/vtgaussian_slam.py:2525-2702) over a set of
+    """The reference's mapping iteration (src/vtgaussian_slam.py:2525-2752) over a set of
     keyframes with the semantics of its all-keyframes branch (:2609-2666): sum of the
     per-keyframe losses, one backward, one Adam step over rgb / logit-opacity / log-scale
     (mapping LRs, configs/replica/room0.py:99-107; means3D and rotations have LR 0).
@@ -292,14 +430,27 @@ class MappingSolver:
     Parameters that are already contiguous float32 CUDA tensors are updated IN PLACE (no copy is made).
     The mapping loss (0.8 L1 + 0.2 (1-SSIM) + depth L1 mean) runs in the library's SSIM kernels; an optional
     `loss_fn(image6, kf) -> (loss, dL_dimage4)` can replace it (e.g. slam_ops.mapping_loss_and_grad, the
-    torch-autograd restatement used to check it)."""
+    torch-autograd restatement used to check it).
 
-    def __init__(self, settings, params, device="cuda:0", lrs=None, eps=1e-15, pair_capacity=None, process_group=None):
+    global_params: the reference's frozen-section term (`loss_global`, :2552, :2600, :2645): a second render of the same
+        keyframe over the frozen earlier sections PLUS the trainable ones, added to the loss.  Pass the parameter
+        tensors of that union with the trainable Gaussians LAST; when those last rows alias `params` (row views of one
+        SectionStore arena) nothing is copied, otherwise the trainable rows are refreshed before every global render.
+        The frozen rows get no update (their `fixed_lrs` are 0, configs/replica/room0.py:108-116).
+    do_ba (per iteration): the keyframes' poses get gradients and an Adam step of their own (`do_ba`, :2545-2548; LRs
+        `cam_unnorm_rots` / `cam_trans` of `lrs`); a keyframe carrying `retie_last=n` has the newest n Gaussians re-tied
+        to its pose after the step (:2706-2727)."""
+
+    def __init__(self, settings, params, device="cuda:0", lrs=None, eps=1e-15, pair_capacity=None, process_group=None,
+                 global_params=None, poll_every=16):
         self.device = torch.device(device)
         self.params = {k: params[k].detach().to(self.device).float().contiguous() for k in PARAM_KEYS}
         N = self.params["means3D"].shape[0]
+        self.settings = settings
         self.r = FusedRenderer(settings, N, device=self.device, pair_capacity=pair_capacity)
         self.lrs = dict(rgb_colors=0.0025, logit_opacities=0.05, log_scales=0.005) if lrs is None else dict(lrs)
+        self.pose_lrs = (float(self.lrs.pop("cam_unnorm_rots", 0.0)), float(self.lrs.pop("cam_trans", 0.0)))
+        self.lrs = {k: v for k, v in self.lrs.items() if k in PARAM_KEYS and v != 0.0}
         self.eps = eps
         # one flat gradient message (all learnable parameter gradients + the loss): a single all-reduce per step
         sizes = {k: self.params[k].numel() for k in self.lrs}
@@ -313,28 +464,101 @@ class MappingSolver:
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.pg = process_group
         self.total_loss = self.flat[-1:]
+        self.poll_every = int(poll_every)
+        self._iters = 0
+        self.gparams = self.r_global = self.ggrads = None
+        if global_params is not None:
+            self.set_global(global_params)
 
-    def iteration(self, keyframes, loss_fn=None, w_im=1.0, w_depth=1.0):
-        """keyframes: list of dict(cam_q, cam_t, gt_rgb, gt_depth) owned by THIS rank.  loss_fn=None uses the
-        fused mapping loss kernels (FusedRenderer.mapping_loss)."""
-        self.total_loss.zero_()
-        first = True
-        for kf in keyframes:
-            img, _ = self.r.forward(self.params, kf["cam_q"], kf["cam_t"])
-            if loss_fn is None:
-                loss, dL4 = self.r.mapping_loss(kf["gt_rgb"], kf["gt_depth"], w_im=w_im, w_depth=w_depth)[0:1], None
-            else:
-                loss, dL4 = loss_fn(img, kf)
-            self.total_loss += loss
-            self.r.backward(self.params, kf["cam_q"], kf["cam_t"], dL_dimage4=dL4, param_grads=self.grads, accumulate=not first)
-            first = False
-        if first:
-            for g in self.grads.values():
-                g.zero_()
+    def set_global(self, global_params):
+        gp = {k: global_params[k].detach().to(self.device).float().contiguous() for k in PARAM_KEYS}
+        N, Ng = self.params["means3D"].shape[0], gp["means3D"].shape[0]
+        if Ng < N:
+            raise ValueError("global_params must hold the frozen sections followed by the trainable Gaussians")
+        self.gparams = gp
+        self._global_aliases = all(gp[k][Ng - N:].data_ptr() == self.params[k].data_ptr() for k in PARAM_KEYS)
+        self.r_global = FusedRenderer(self.settings, Ng, device=self.device)
+        self.ggrads = {k: torch.zeros_like(gp[k]) for k in self.lrs}
+
+    def _render_backward(self, r, params, kf, grads, accumulate, loss_fn, w_im, w_depth, pose):
+        img, _ = r.forward(params, kf["cam_q"], kf["cam_t"])
+        if loss_fn is None:
+            loss, dL4 = r.mapping_loss(kf["gt_rgb"], kf["gt_depth"], w_im=w_im, w_depth=w_depth)[0:1], None
+        else:
+            loss, dL4 = loss_fn(img, kf)
+        self.total_loss += loss
+        r.backward(params, kf["cam_q"], kf["cam_t"], dL_dimage4=dL4, param_grads=grads, pose_grads=pose, accumulate=accumulate)
+
+    def iteration(self, keyframes, loss_fn=None, w_im=1.0, w_depth=1.0, do_ba=False):
+        """keyframes: list of dict(cam_q, cam_t, gt_rgb, gt_depth[, global=True][, retie_last=n]) owned by THIS rank.
+        loss_fn=None uses the fused mapping loss kernels (FusedRenderer.mapping_loss)."""
+        poll = self.poll_every > 0 and self._iters % self.poll_every == 0
+        for attempt in range(3):
+            self.total_loss.zero_()
+            first = True
+            for kf in keyframes:
+                pose = None
+                if do_ba:
+                    st = kf.setdefault("_ba", None)
+                    if st is None:
+                        z = lambda n: torch.zeros(n, dtype=torch.float32, device=self.device)
+                        st = kf["_ba"] = dict(d_q=z(4), d_t=z(3), m_q=z(4), v_q=z(4), m_t=z(3), v_t=z(3), old_q=z(4), old_t=z(3),
+                                              step=torch.zeros(1, dtype=torch.int32, device=self.device))
+                    pose = (st["d_q"], st["d_t"])
+                self._render_backward(self.r, self.params, kf, self.grads, not first, loss_fn, w_im, w_depth, pose)
+                first = False
+                if self.r_global is not None and kf.get("global", True):
+                    N = self.params["means3D"].shape[0]
+                    if not self._global_aliases:
+                        for k in PARAM_KEYS:
+                            self.gparams[k][-N:].copy_(self.params[k])
+                    gpose = None
+                    if do_ba:
+                        st = kf["_ba"]
+                        gpose = (st.setdefault("gd_q", torch.zeros_like(st["d_q"])), st.setdefault("gd_t", torch.zeros_like(st["d_t"])))
+                    self._render_backward(self.r_global, self.gparams, kf, self.ggrads, False, loss_fn, w_im, w_depth, gpose)
+                    for k in self.lrs:
+                        self.grads[k] += self.ggrads[k][-N:]
+                    if do_ba:
+                        st["d_q"] += st["gd_q"]
+                        st["d_t"] += st["gd_t"]
+            if first:
+                for g in self.grads.values():
+                    g.zero_()
+            if not poll:
+                break
+            # pair-buffer overflow check (one blocking read every `poll_every` iterations, before anything is updated):
+            # a truncated render would give a wrong loss and wrong gradients without any error
+            grew = self.r.ensure_capacity()
+            if self.r_global is not None:
+                grew = self.r_global.ensure_capacity() or grew
+            if not grew:
+                break
+        else:
+            raise _lib.VtgsError("pair buffer overflow persisted after regrowing")
+        self._iters += 1
         if self.pg is not None:
             # keyframe sharding: ONE all-reduce (SUM) of the flat gradient message over NVLink (5 N fp32 + loss)
             torch.distributed.all_reduce(self.flat, group=self.pg)
         self.step_dev.add_(1)
         for k, lr in self.lrs.items():
             adam_step(self.params[k], self.grads[k], self.m[k], self.v[k], lr, step_dev=self.step_dev, eps=self.eps)
+        if do_ba:
+            for kf in keyframes:
+                st = kf["_ba"]
+                n_last = int(kf.get("retie_last", 0))
+                if n_last > 0 and self.pg is not None:
+                    raise NotImplementedError("retie_last under keyframe sharding: the re-tied keyframe's pose lives on its "
+                                              "owner rank only; replicate that keyframe on every rank or broadcast its pose")
+                if n_last > 0:
+                    st["old_q"].copy_(kf["cam_q"])
+                    st["old_t"].copy_(kf["cam_t"])
+                st["step"].add_(1)
+                if self.pose_lrs[0] != 0.0:
+                    adam_step(kf["cam_q"], st["d_q"], st["m_q"], st["v_q"], self.pose_lrs[0], step_dev=st["step"], eps=self.eps)
+                if self.pose_lrs[1] != 0.0:
+                    adam_step(kf["cam_t"], st["d_t"], st["m_t"], st["v_t"], self.pose_lrs[1], step_dev=st["step"], eps=self.eps)
+                if n_last > 0:
+                    # the section's newest Gaussians stay tied to the keyframe: pts <- c2w_new (w2c_old pts), :2706-2727
+                    retie_dev(self.params["means3D"][-n_last:], st["old_q"], st["old_t"], kf["cam_q"], kf["cam_t"])
         return self.total_loss

@@ -181,6 +181,19 @@ class SectionStore:
         self.offsets.append(a + n)
         return len(self) - 1
 
+    def extend_last(self, params):
+        """Append Gaussians to the NEWEST section (it ends the arena, so its row range simply grows): the
+        silhouette-driven additions of the reference's add_new_gaussians_base_frame (src/vtgaussian_slam.py:791-798
+        concatenates them to the current parameter tensors).  Views taken before must be taken again."""
+        n = int(params["means3D"].shape[0])
+        a = self.offsets[-1]
+        if a + n > self.capacity:
+            self._grow(a + n)
+        for k in self.KEYS:
+            self.buf[k][a:a + n] = params[k].to(self.device, torch.float32).reshape(n, self.KEYS[k])
+        self.offsets[-1] = a + n
+        return n
+
     def rows(self, first, last=None):
         """Contiguous row-slice views (no copy) of sections first..last inclusive."""
         last = first if last is None else last
@@ -236,6 +249,40 @@ class ViewTiedSLAM:
                                       sil_thres=c.sil_thres, use_graph=c.use_graph)
         return sec
 
+    def add_missing_gaussians(self, idx, rgb, depth, sil_thres=0.5):
+        """Silhouette-driven Gaussian addition (reference add_new_gaussians_base_frame, src/vtgaussian_slam.py:732-813):
+        a forward-only fused render of the tracked sections from frame idx's pose, the non-presence mask
+        (silhouette < sil_thres, or rendered depth behind the measurement by more than 50x the median depth error) in one
+        kernel, and one new view-tied Gaussian per masked valid-depth pixel appended to the newest section.
+        -> number of Gaussians added.  (The reference's second, 2x-resolution pass over the Canny edge mask is what
+        densified_section builds at a section start.)"""
+        tr = self.tracker
+        M = self.w2c[idx]
+        q = torch.as_tensor(quat_from_matrix(M[:3, :3]), dtype=torch.float32, device=self.device)
+        t = torch.as_tensor(M[:3, 3], dtype=torch.float32, device=self.device)
+        for _ in range(2):
+            tr.r.forward(tr.params, q, t)
+            if not tr.r.ensure_capacity():
+                break
+        mask, count = tr.r.nonpresence_mask(depth, sil_thres=sil_thres)
+        if int(count.item()) == 0:
+            return 0
+        keep = mask.bool() & (depth[0] > 0)
+        if not bool(keep.any()):
+            return 0
+        fresh = section_from_frame(rgb, depth, self.K, np.linalg.inv(M), self.device, pixel_mask=keep)
+        n = self.store.extend_last(fresh)
+        k = len(self.store) - 1
+        for s_ in self.sections:
+            s_["params"] = self.store.rows(s_["index"])
+        c = self.cfg
+        self.mapper = MappingSolver(self.settings, self.sections[-1]["params"], device=self.device, lrs=c.map_lrs)
+        first = max(0, k - max(1, c.track_sections) + 1)
+        self.tracker = TrackingSolver(self.settings, self.store.rows(first, k), device=self.device, lr_rot=c.lr_rot,
+                                      lr_trans=c.lr_trans, w_im=c.track_w_im, w_depth=c.track_w_depth,
+                                      sil_thres=c.sil_thres, use_graph=c.use_graph)
+        return n
+
     def _keyframe(self, sec, idx, rgb, depth):
         sec["keyframes"].append((idx, rgb, depth))
 
@@ -262,12 +309,11 @@ class ViewTiedSLAM:
         tr = self.tracker
         tr.set_frame(rgb, depth, quat_from_matrix(init[:3, :3]).astype(np.float32), init[:3, 3].astype(np.float32))
         t0 = time.perf_counter()
-        for _ in range(c.track_iters + 1):          # the +1 evaluates (and books) the pose of the last Adam step
-            tr.step()
-        best = tr.best.cpu().numpy()                # one read per frame (synchronises)
+        # the +1 evaluates (and books) the pose of the last Adam step; one blocking read per frame; a frame whose pair
+        # buffers turned out too small is re-run with larger ones (TrackingSolver.run_frame)
+        best = tr.run_frame(c.track_iters + 1).numpy()
         self.stats["track_s"] += time.perf_counter() - t0
         self.stats["track_iters"] += c.track_iters + 1
-        tr.check()
         self.stats["track_loss"].append(float(best[0]))
         return matrix_from_quat(best[1:5], best[5:8])
 

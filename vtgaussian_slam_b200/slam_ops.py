@@ -228,30 +228,58 @@ def _masks_and_losses(im, depth_sil, curr_data, loss_weights, use_sil_for_loss, 
     return loss, weighted_losses
 
 
+def _give_grad(means2D, grad):
+    """The reference reads variables['means2D'].grad after loss.backward() (utils/slam_external.py:100-102): the leaf
+    handed out by get_loss receives the screen-space gradient here (accumulated, like autograd would)."""
+    if means2D is None:
+        return
+    if means2D.grad is None:
+        means2D.grad = grad
+    else:
+        means2D.grad += grad
+
+
+def _forward_checked(renderer, params, q, t, poll):
+    """renderer.forward, repeated with larger pair buffers if it overflowed them (checked when `poll`: one blocking
+    read of the device counters -- a truncated render gives a wrong loss and wrong gradients without any error)."""
+    img, radii = renderer.forward(params, q, t)
+    if poll and renderer.ensure_capacity():
+        img, radii = renderer.forward(params, q, t)
+        if renderer.ensure_capacity():
+            raise RuntimeError("pair buffer overflow persisted after regrowing")
+    return img, radii
+
+
+def _poll_due(renderer, tracking_iteration=None):
+    """Poll the overflow counter on a renderer's first use, at the first tracking iteration of a frame, and every 16th
+    call otherwise."""
+    renderer.polls += 1
+    return renderer.polls == 1 or tracking_iteration == 0 or renderer.polls % 16 == 0
+
+
 class _FusedRender(torch.autograd.Function):
     """im, depth_sil, radii = both rasteriser passes of get_loss as one fused six-plane pass,
     differentiable w.r.t. the Gaussian parameters and the frame's pose slices."""
 
     @staticmethod
-    def forward(ctx, renderer, means3D, rgb, unnorm_rot, logit_op, log_scales, cam_q, cam_t, want_gauss, want_pose):
+    def forward(ctx, renderer, means3D, rgb, unnorm_rot, logit_op, log_scales, cam_q, cam_t, want_gauss, want_pose, means2D):
         params = dict(means3D=means3D.detach().contiguous(), rgb_colors=rgb.detach().contiguous(),
                       unnorm_rotations=unnorm_rot.detach().contiguous(), logit_opacities=logit_op.detach().contiguous(),
                       log_scales=log_scales.detach().contiguous())
         q, t = cam_q.detach().contiguous().reshape(4), cam_t.detach().contiguous().reshape(3)
-        img, radii = renderer.forward(params, q, t)
+        img, radii = _forward_checked(renderer, params, q, t, _poll_due(renderer))
         renderer.pending_backward = any(ctx.needs_input_grad)
         ctx.renderer, ctx.params, ctx.q, ctx.t = renderer, params, q, t
         ctx.want = (want_gauss, want_pose)
         ctx.pose_shapes = (cam_q.shape, cam_t.shape)
         out = img.clone()
-        means2D_grad = torch.zeros_like(params["means3D"])
-        ctx.means2D_grad = means2D_grad
+        ctx.means2D = means2D              # a leaf the caller keeps in variables['means2D']: receives .grad in backward
         radii = radii.clone()
         ctx.mark_non_differentiable(radii)
-        return out[:3], out[3:6], radii, means2D_grad
+        return out[:3], out[3:6], radii
 
     @staticmethod
-    def backward(ctx, g_im, g_ds, _g_radii, _g_m2d):
+    def backward(ctx, g_im, g_ds, _g_radii):
         r, params = ctx.renderer, ctx.params
         H, W = r.H, r.W
         dL4 = torch.zeros((4, H, W), dtype=torch.float32, device=g_im.device)
@@ -265,14 +293,16 @@ class _FusedRender(torch.autograd.Function):
         want_gauss, want_pose = ctx.want
         pg = {k: torch.zeros_like(params[k]) for k in params} if want_gauss else None
         pose = (torch.zeros(4, device=g_im.device), torch.zeros(3, device=g_im.device)) if want_pose else None
-        r.backward(params, ctx.q, ctx.t, dL_dimage4=dL4, param_grads=pg, pose_grads=pose, means2D_grad=ctx.means2D_grad)
+        m2d = torch.zeros_like(params["means3D"])
+        r.backward(params, ctx.q, ctx.t, dL_dimage4=dL4, param_grads=pg, pose_grads=pose, means2D_grad=m2d)
         r.pending_backward = False
+        _give_grad(ctx.means2D, m2d)
         gq = pose[0].reshape(ctx.pose_shapes[0]) if want_pose else None
         gt = pose[1].reshape(ctx.pose_shapes[1]) if want_pose else None
         if want_gauss:
             return (None, pg["means3D"], pg["rgb_colors"], pg["unnorm_rotations"], pg["logit_opacities"], pg["log_scales"],
-                    gq, gt, None, None)
-        return (None, None, None, None, None, None, gq, gt, None, None)
+                    gq, gt, None, None, None)
+        return (None, None, None, None, None, None, gq, gt, None, None, None)
 
 
 class _FusedTrackingLoss(torch.autograd.Function):
@@ -282,13 +312,13 @@ class _FusedTrackingLoss(torch.autograd.Function):
     transform_to_frame detaches them, reference :432-436)."""
 
     @staticmethod
-    def forward(ctx, renderer, params, cam_q, cam_t, gt_rgb, gt_depth, cfg, thres_fn):
+    def forward(ctx, renderer, params, cam_q, cam_t, gt_rgb, gt_depth, cfg, thres_fn, poll):
         p = {k: params[k].detach().contiguous() for k in ("means3D", "rgb_colors", "unnorm_rotations", "logit_opacities", "log_scales")}
         q, t = cam_q.detach().contiguous().reshape(4), cam_t.detach().contiguous().reshape(3)
-        img, radii = renderer.forward(p, q, t)
+        img, radii = _forward_checked(renderer, p, q, t, poll)
         cfg = dict(cfg)
         if thres_fn is not None:
-            cfg["sil_thres"] = thres_fn(img)
+            cfg["sil_thres"] = thres_fn(renderer, gt_rgb.contiguous(), gt_depth.contiguous())
         terms = renderer.tracking_loss(gt_rgb.contiguous(), gt_depth.contiguous(), **cfg).clone()
         renderer.pending_backward = any(ctx.needs_input_grad)
         ctx.renderer, ctx.p, ctx.q, ctx.t = renderer, p, q, t
@@ -305,7 +335,7 @@ class _FusedTrackingLoss(torch.autograd.Function):
         ctx.renderer.backward(ctx.p, ctx.q, ctx.t, dL_dimage4=ctx.dL4, pose_grads=(dq, dt))
         ctx.renderer.pending_backward = False
         return (None, None, (dq * g_loss).reshape(ctx.pose_shapes[0]), (dt * g_loss).reshape(ctx.pose_shapes[1]),
-                None, None, None, None)
+                None, None, None, None, None)
 
 
 class _FusedMappingLoss(torch.autograd.Function):
@@ -314,34 +344,36 @@ class _FusedMappingLoss(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, renderer, means3D, rgb, unnorm_rot, logit_op, log_scales, cam_q, cam_t, gt_rgb, gt_depth, w_im, w_depth,
-                want_pose):
+                want_pose, means2D):
         p = dict(means3D=means3D.detach().contiguous(), rgb_colors=rgb.detach().contiguous(),
                  unnorm_rotations=unnorm_rot.detach().contiguous(), logit_opacities=logit_op.detach().contiguous(),
                  log_scales=log_scales.detach().contiguous())
         q, t = cam_q.detach().contiguous().reshape(4), cam_t.detach().contiguous().reshape(3)
-        _, radii = renderer.forward(p, q, t)
+        _, radii = _forward_checked(renderer, p, q, t, _poll_due(renderer))
         terms = renderer.mapping_loss(gt_rgb.contiguous(), gt_depth.contiguous(), w_im=w_im, w_depth=w_depth).clone()
         renderer.pending_backward = any(ctx.needs_input_grad)
         ctx.renderer, ctx.p, ctx.q, ctx.t, ctx.want_pose = renderer, p, q, t, want_pose
         ctx.pose_shapes = (cam_q.shape, cam_t.shape)
-        ctx.means2D_grad = torch.zeros_like(p["means3D"])
+        ctx.means2D = means2D              # a leaf the caller keeps in variables['means2D']: receives .grad in backward
         radii = radii.clone()
         ctx.mark_non_differentiable(radii, terms)
-        return terms[0].clone(), terms, radii, ctx.means2D_grad
+        return terms[0].clone(), terms, radii
 
     @staticmethod
-    def backward(ctx, g_loss, _g_terms, _g_radii, _g_m2d):
+    def backward(ctx, g_loss, _g_terms, _g_radii):
         p = ctx.p
         pg = {k: torch.zeros_like(v) for k, v in p.items()}
         pose = None
         if ctx.want_pose:
             pose = (torch.zeros(4, dtype=torch.float32, device=g_loss.device), torch.zeros(3, dtype=torch.float32, device=g_loss.device))
-        ctx.renderer.backward(p, ctx.q, ctx.t, param_grads=pg, pose_grads=pose, means2D_grad=ctx.means2D_grad)
+        m2d = torch.zeros_like(p["means3D"])
+        ctx.renderer.backward(p, ctx.q, ctx.t, param_grads=pg, pose_grads=pose, means2D_grad=m2d)
         ctx.renderer.pending_backward = False
+        _give_grad(ctx.means2D, m2d * g_loss)
         gq = (pose[0] * g_loss).reshape(ctx.pose_shapes[0]) if pose else None
         gt = (pose[1] * g_loss).reshape(ctx.pose_shapes[1]) if pose else None
         return (None, pg["means3D"] * g_loss, pg["rgb_colors"] * g_loss, pg["unnorm_rotations"] * g_loss,
-                pg["logit_opacities"] * g_loss, pg["log_scales"] * g_loss, gq, gt, None, None, None, None, None)
+                pg["logit_opacities"] * g_loss, pg["log_scales"] * g_loss, gq, gt, None, None, None, None, None, None)
 
 
 _RENDERERS: dict = {}
@@ -361,22 +393,39 @@ def _depth_row_of(w2c):
     return hit[0]
 
 
+RENDERER_POOL_BYTES = 24 << 30      # device memory the get_loss renderer pool may hold (B200: 180 GB of HBM)
+
+
 def _renderer_for(cam, n, device):
     """A FusedRenderer for (camera, N) whose buffers are free: a renderer that still holds the state of a forward
     whose backward has not run yet (e.g. the reference's all-keyframes mapping branch sums several get_loss calls
-    before one backward, src/vtgaussian_slam.py:2609-2666) is never handed out again."""
+    before one backward, src/vtgaussian_slam.py:2609-2666) is never handed out again.  The pool is bounded by bytes
+    and evicts the least recently used idle renderers (N changes at every base frame and differs between tracking and
+    mapping)."""
     from .fused import FusedRenderer
     key = (id(cam), n, str(device))
-    pool = _RENDERERS.get(key)
+    pool = _RENDERERS.pop(key, None)
     if pool is None:
-        if len(_RENDERERS) > 4:
-            _RENDERERS.clear()
-        pool = _RENDERERS[key] = ([], cam)
+        pool = ([], cam)                # the camera object is kept alive so that its id stays unique
+    _RENDERERS[key] = pool              # (re-)insert as most recently used
     for r in pool[0]:
         if not getattr(r, "pending_backward", False):
             return r
     r = FusedRenderer(cam, n, device=device)
     pool[0].append(r)
+    total = sum(x.nbytes for p_ in _RENDERERS.values() for x in p_[0])
+    for k in list(_RENDERERS):
+        if total <= RENDERER_POOL_BYTES:
+            break
+        if k == key:
+            continue
+        idle = [x for x in _RENDERERS[k][0] if not getattr(x, "pending_backward", False)]
+        total -= sum(x.nbytes for x in idle)
+        keep = [x for x in _RENDERERS[k][0] if getattr(x, "pending_backward", False)]
+        if keep:
+            _RENDERERS[k] = (keep, _RENDERERS[k][1])
+        else:
+            del _RENDERERS[k]
     return r
 
 
@@ -434,25 +483,22 @@ def get_loss(params, curr_data, variables, iter_time_idx, loss_weights, use_sil_
             far = 0.0
             if dataset_name == 'replica' and use_sil_for_loss:
                 if tracking_iteration == 0 and presence_sil_mask_mse_ls is not None:
-                    def thres_fn(img6):                      # :476-508 threshold ladder on the rendered planes
-                        mse_ls = []
-                        for thr in REPLICA_SIL_LADDER:
-                            m = (img6[4] > thr) & (curr_data['depth'][0] > 0)
-                            d2 = ((curr_data['im'] - img6[:3]) ** 2) * m
-                            mse_ls.append((d2.sum() / (3 * m.sum())).item())
-                        presence_sil_mask_mse_ls.append(min(mse_ls))
-                        sil_thres_ls.append(REPLICA_SIL_LADDER[mse_ls.index(min(mse_ls))])
+                    def thres_fn(renderer, gt_rgb, gt_depth):       # :476-508 threshold ladder, one kernel + one host read
+                        res = renderer.sil_ladder(gt_rgb, gt_depth).cpu()
+                        presence_sil_mask_mse_ls.append(float(res[11]))
+                        sil_thres_ls.append(min(REPLICA_SIL_LADDER, key=lambda v: abs(v - float(res[10]))))
                         return sil_thres_ls[-1]
                 elif sil_thres_ls:
                     thres = sil_thres_ls[-1]
-            elif far_depth_filter_thres is not None and dataset_name != 'scannetpp':
+            if far_depth_filter_thres is not None and dataset_name not in ('replica', 'scannetpp'):     # reference :586
                 far = float(far_depth_filter_thres)
             cfg = dict(w_im=float(loss_weights['im']), w_depth=float(loss_weights['depth']),
                        use_sil_for_loss=bool(use_sil_for_loss), sil_thres=float(thres), far_depth_thres=far,
                        ignore_outlier_depth_loss=bool(ignore_outlier_depth_loss),
                        pixel_mask=(None if (vis_mask is None or dataset_name == 'replica')
                                    else vis_mask.reshape(curr_data['depth'].shape[-2:])))
-            loss, terms, radius = _FusedTrackingLoss.apply(r, params, cam_q, cam_t, curr_data['im'], curr_data['depth'], cfg, thres_fn)
+            loss, terms, radius = _FusedTrackingLoss.apply(r, params, cam_q, cam_t, curr_data['im'], curr_data['depth'], cfg, thres_fn,
+                                                           _poll_due(r, tracking_iteration))
             weighted_losses = {'depth': terms[2], 'im': terms[1], 'loss': loss}
             seen = radius > 0
             variables['max_2D_radius'] = torch.where(seen, torch.max(radius.to(variables['max_2D_radius'].dtype),
@@ -464,10 +510,11 @@ def get_loss(params, curr_data, variables, iter_time_idx, loss_weights, use_sil_
         fused_map_ok = (mapping and not tracking and use_l1 and not ignore_outlier_depth_loss and additional_mask is None
                         and set(loss_weights) == {'im', 'depth'})
         if fused_map_ok:
-            loss, terms, radius, means2D = _FusedMappingLoss.apply(
+            means2D = torch.zeros_like(params['means3D'], requires_grad=True)        # leaf: .grad is filled by the backward
+            loss, terms, radius = _FusedMappingLoss.apply(
                 r, params['means3D'], params['rgb_colors'], params['unnorm_rotations'], params['logit_opacities'],
                 params['log_scales'], cam_q, cam_t, curr_data['im'], curr_data['depth'], float(loss_weights['im']),
-                float(loss_weights['depth']), camera_grad)
+                float(loss_weights['depth']), camera_grad, means2D)
             variables['means2D'] = means2D
             weighted_losses = {'depth': terms[2], 'im': terms[1], 'loss': loss}
             seen = radius > 0
@@ -476,10 +523,11 @@ def get_loss(params, curr_data, variables, iter_time_idx, loss_weights, use_sil_
             variables['seen'] = seen
             return loss, variables, weighted_losses
         g = (lambda t: t) if gaussians_grad else (lambda t: t.detach())
-        im, depth_sil, radius, means2D = _FusedRender.apply(
+        means2D = torch.zeros_like(params['means3D'], requires_grad=True)            # leaf: .grad is filled by the backward
+        im, depth_sil, radius = _FusedRender.apply(
             r, g(params['means3D']), g(params['rgb_colors']), g(params['unnorm_rotations']), g(params['logit_opacities']),
-            g(params['log_scales']), cam_q, cam_t, gaussians_grad, camera_grad)
-        variables['means2D'] = means2D          # .grad is not populated; the tensor itself receives dL/dmeans2D
+            g(params['log_scales']), cam_q, cam_t, gaussians_grad, camera_grad, means2D)
+        variables['means2D'] = means2D
     else:
         raise ValueError(f"unknown backend {backend!r}")
 
