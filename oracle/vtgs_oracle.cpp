@@ -30,6 +30,9 @@
 //  float->int casts saturate like CUDA's cvt.rzi.s32.f32 (the reference runs on CUDA).
 // =====================================================================================
 #include <algorithm>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -580,6 +583,18 @@ void vtgso_backward(void* h, const float* dL_dout_color, float* dL_dmeans2D, flo
 }
 
 float vtgso_expf(float x) { return vexpf(x); }
+
+// Number of OpenMP threads of the oracle's loops (bench.py's CPU arm sets it to the cores it may use, whatever
+// OMP_NUM_THREADS the launcher exported: torchrun sets it to 1).  Returns the value now in effect.
+int vtgso_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
+}
 
 void vtgso_mark_visible(const VtgsCamera* cam, int64_t N, const float* means3D, uint8_t* present) {
     for (int64_t i = 0; i < N; ++i)

@@ -27,6 +27,25 @@ def test_reference_arm_prints_the_contract_line():
     assert e2e["value"] == line["value"] and e2e["h2d_bytes_per_step"] == 0 and e2e["d2h_bytes_per_step"] == 0
 
 
+def test_reference_arm_uses_every_core_under_torchrun_env():
+    """torchrun exports OMP_NUM_THREADS=1: the CPU arm must not inherit it (SCALE's vs_reference would be void), and its
+    `config` is the product arm's config for the same --gpus."""
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="1", RANK="0", WORLD_SIZE="2", LOCAL_RANK="0")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--small", "--steps", "1", "--warmup", "0",
+                        "--gpus", "2"], capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+    assert p.returncode == 0, p.stderr[-2000:]
+    line = json.loads(p.stdout.strip().splitlines()[-1])
+    assert line["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
+    sys.path.insert(0, ROOT)
+    import bench
+    assert line["config"] == bench.config_of(bench.build_workload("small"), 2)
+    # ranks other than 0 exit without work
+    env["RANK"] = "1"
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--small", "--steps", "1", "--warmup", "0",
+                        "--gpus", "2"], capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+    assert p.returncode == 0 and p.stdout.strip() == ""
+
+
 def test_product_arm_fails_loudly_without_cuda():
     p = _run("--small", "--steps", "1", "--warmup", "0", "--no-cpu", timeout=300)
     assert p.returncode != 0

@@ -1,0 +1,76 @@
+"""torchrun --nproc-per-node 2 tools/check_multi_gpu.py : tile-band sharded tracking == the unsharded solver, for the
+plain loss, Replica's iteration-0 threshold search (10 floats all-reduced) and the frame-wide outlier median (radix-select
+histograms all-reduced); keyframe-sharded mapping == the unsharded solver."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+from vtgaussian_slam_b200 import synthetic  # noqa: E402
+from vtgaussian_slam_b200.fused import MappingSolver, TrackingSolver  # noqa: E402
+from vtgaussian_slam_b200.slam_loop import quat_from_matrix  # noqa: E402
+
+rank, world, local = bench.dist_env()
+dev = torch.device("cuda", local)
+torch.cuda.set_device(dev)
+dist.init_process_group("nccl", device_id=dev)
+pg = dist.group.WORLD
+fr = synthetic.make_frame("replica", 400, 240, seed=0)
+gt_depth = fr["depth"].copy()
+gt_depth[0, 40:70, 100:200] *= 3.0
+ok = True
+for name, opacity, kw in (("plain", "trained", {}), ("replica_search", "fresh", dict(replica_sil_search=True)),
+                          ("outlier_median", "trained", dict(ignore_outlier_depth_loss=True, w_depth=1.0))):
+    p = synthetic.view_tied_gaussians(fr, n_edge=4000, opacity=opacity)
+    wl = dict(frame=fr, params=p, settings=synthetic.setup_camera(fr["W"], fr["H"], fr["K"], np.eye(4)))
+    settings = bench.make_settings(wl, dev)
+    params = {k: torch.tensor(v, device=dev) for k, v in p.items()}
+    q, t = synthetic.perturbed_pose(seed=1)
+    gy = (fr["H"] + 15) // 16
+    cut = [0, gy // 2 + 1, gy]
+    res = []
+    for sharded in (False, True):
+        ts = TrackingSolver(settings, params, device=dev, use_graph=sharded, tile_rows=(cut[rank], cut[rank + 1]) if sharded else (0, 0),
+                            process_group=pg if sharded else None, **kw)
+        ts.set_frame(torch.tensor(fr["im"]), torch.tensor(gt_depth), q, t)
+        best = ts.run_frame(8).numpy()
+        res.append((best, ts.loss_terms().cpu().numpy().copy(), float(ts.r._sil[10].item()) if ts.r._sil is not None else 0.0))
+    a, b = res
+    good = np.allclose(a[0], b[0], rtol=2e-4, atol=1e-6) and abs(a[1][0] - b[1][0]) <= 2e-4 * abs(a[1][0]) and a[2] == b[2]
+    ok &= good
+    if rank == 0:
+        print(name, "OK" if good else "MISMATCH", "best", a[0][:1], b[0][:1], "loss", a[1][0], b[1][0], "thr", a[2], b[2], flush=True)
+
+# keyframe-sharded mapping
+p = synthetic.view_tied_gaussians(fr, n_edge=4000, opacity="trained")
+wl = dict(frame=fr, params=p, settings=synthetic.setup_camera(fr["W"], fr["H"], fr["K"], np.eye(4)))
+settings = bench.make_settings(wl, dev)
+poses = synthetic.trajectory(4, step_m=0.02, step_deg=1.0, seed=11)
+kfs = []
+for k in range(4):
+    fk = synthetic.make_frame("replica", 400, 240, seed=50 + k, c2w=poses[k])
+    w2c = np.linalg.inv(poses[k])
+    kfs.append(dict(cam_q=torch.tensor(quat_from_matrix(w2c[:3, :3]).astype(np.float32), device=dev), cam_t=torch.tensor(w2c[:3, 3].astype(np.float32), device=dev),
+                    gt_rgb=torch.tensor(fk["im"], device=dev), gt_depth=torch.tensor(fk["depth"], device=dev)))
+out = []
+for sharded in (False, True):
+    ms = MappingSolver(settings, {k: torch.tensor(v, device=dev) for k, v in p.items()}, device=dev, process_group=pg if sharded else None)
+    mine = kfs[rank::world] if sharded else kfs
+    for _ in range(5):
+        loss = ms.iteration(mine)
+    out.append((float(loss.item()), ms.params["rgb_colors"].cpu().numpy().copy()))
+good = abs(out[0][0] - out[1][0]) <= 1e-4 * abs(out[0][0]) and np.abs(out[0][1] - out[1][1]).max() <= 2e-3
+ok &= good
+if rank == 0:
+    print("mapping", "OK" if good else "MISMATCH", out[0][0], out[1][0], np.abs(out[0][1] - out[1][1]).max(), flush=True)
+flag = torch.tensor([1.0 if ok else 0.0], device=dev)
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+dist.destroy_process_group()
+if rank == 0:
+    print("MULTI_GPU_CHECK", "PASS" if flag.item() == 1.0 else "FAIL", flush=True)
+sys.exit(0 if flag.item() == 1.0 else 1)

@@ -4,7 +4,7 @@ import numpy as np, torch
 import bench
 from vtgaussian_slam_b200 import slam_ops
 from vtgaussian_slam_b200.rasterizer import GaussianRasterizationSettings
-wl = bench.build_workload(False)
+wl = bench.build_workload("c2")
 dev = torch.device("cuda:0")
 fr, s = wl["frame"], wl["settings"]
 settings = GaussianRasterizationSettings(image_height=fr["H"], image_width=fr["W"], tanfovx=s["tanfovx"], tanfovy=s["tanfovy"], bg=torch.tensor(s["bg"], device=dev),

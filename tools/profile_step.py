@@ -17,7 +17,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--small", action="store_true")
 ap.add_argument("--iters", type=int, default=3)
 a = ap.parse_args()
-wl = bench.build_workload(a.small)
+wl = bench.build_workload("small" if a.small else "c2")
 dev = torch.device("cuda:0")
 fr, s = wl["frame"], wl["settings"]
 settings = GaussianRasterizationSettings(

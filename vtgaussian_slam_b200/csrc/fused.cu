@@ -233,6 +233,7 @@ __global__ void __launch_bounds__(256)
 ffma_probe_kernel(long long iters, float* __restrict__ sink) {
     float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
     const float m = 0.999f, c = 1e-4f;
+#pragma unroll 16
     for (long long i = 0; i < iters; ++i) {
         a0 = fmaf(a0, m, c); a1 = fmaf(a1, m, c); a2 = fmaf(a2, m, c); a3 = fmaf(a3, m, c);
         a4 = fmaf(a4, m, c); a5 = fmaf(a5, m, c); a6 = fmaf(a6, m, c); a7 = fmaf(a7, m, c);
