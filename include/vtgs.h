@@ -126,6 +126,10 @@ typedef struct VtgsBuffers {
     uint32_t*     region_done;    /* [tiles][8] groups of each region list the forward walked before every
                                      pixel of the region had saturated                                   */
     uint64_t      pair_capacity;
+    uint8_t*      band_flags;     /* [ceil(N / 256)] optional (may be NULL).  Fused path with a tile-row band: per
+                                     iteration the forward marks the 256-Gaussian blocks that can reach the band at the
+                                     current pose; preprocess, scatter and backward-preprocess skip the others, so a
+                                     rank's per-Gaussian work follows its band instead of N                        */
 } VtgsBuffers;
 
 #define VTGS_GEOM_RECORD_BYTES 64
@@ -146,6 +150,7 @@ typedef struct VtgsWorkspaceSizes {
     uint64_t region_cnt_bytes;
     uint64_t region_masks_bytes;
     uint64_t region_done_bytes;
+    uint64_t band_flags_bytes;
     uint32_t tiles_x;
     uint32_t tiles_y;
 } VtgsWorkspaceSizes;

@@ -272,3 +272,41 @@ def test_ffma_probe_runs():
     torch.cuda.synchronize()
     tflops = 2 * 8 * 20000 * n.value / (e0.elapsed_time(e1) * 1e-3) / 1e12
     assert n.value == 148 * 8 * 256 and 20.0 < tflops < 90.0, tflops
+
+
+def test_band_candidate_blocks_give_the_full_frame_gradients():
+    """Tile bands with candidate blocks (K0' marks the 256-Gaussian blocks that can reach the band; K1' / scatter / K7'
+    skip the rest): per-parameter gradients of the bands add up to the full frame's, skipped blocks hold exact zeros."""
+    from vtgaussian_slam_b200.fused import FusedRenderer
+    fr, p, q, t = _scene(320, 208, n_edge=3000)             # 13 tile rows, 66 560 + 3 000 Gaussians = 272 blocks
+    settings = _settings(fr)
+    gp = _gp(p)
+    qd, td = torch.tensor(q, device=DEV), torch.tensor(t, device=DEV)
+    dL = torch.randn(4, fr["H"], fr["W"], device=DEV)
+    N = p["means3D"].shape[0]
+
+    def run(rows):
+        r = FusedRenderer(settings, N, device=DEV, tile_rows=rows)
+        r.forward(gp, qd, td)
+        pg = {k: torch.full_like(gp[k], 7.0) for k in gp}          # stale values must be overwritten everywhere
+        dq, dt = torch.zeros(4, device=DEV), torch.zeros(3, device=DEV)
+        y0, y1 = (rows[0] * 16, min(rows[1] * 16, fr["H"])) if rows[1] > rows[0] else (0, fr["H"])
+        d = torch.zeros_like(dL)
+        d[:, y0:y1] = dL[:, y0:y1]
+        r.backward(gp, qd, td, dL_dimage4=d, param_grads=pg, pose_grads=(dq, dt))
+        flags = r.ws.band_flags.clone()
+        return pg, torch.cat([dq, dt]).double(), flags
+    full = run((0, 0))
+    parts = [run((0, 4)), run((4, 9)), run((9, 13))]
+    assert all(0 < int(pt[2].sum().item()) < pt[2].numel() for pt in parts), "every band must skip some blocks"
+    for k in ("means3D", "rgb_colors", "logit_opacities", "log_scales"):
+        s = sum(pt[0][k].double() for pt in parts)
+        ref = full[0][k].double()
+        assert ((s - ref).abs().max() / ref.abs().max()).item() <= 1e-4, k
+    g = sum(pt[1] for pt in parts)
+    assert ((g - full[1]).abs().max() / full[1].abs().max()).item() <= 1e-4
+    # a skipped block's rows are exact zeros
+    pt = parts[0]
+    dead = (pt[2] == 0).nonzero().flatten()
+    b = int(dead[0].item())
+    assert float(pt[0]["rgb_colors"][b * 256:(b + 1) * 256].abs().max().item()) == 0.0

@@ -97,6 +97,7 @@ int vtgs_workspace_query(int32_t W, int32_t H, int64_t N, uint64_t pair_capacity
     s->region_cnt_bytes = gx * gy * 8 * 4;
     s->region_masks_bytes = ((pair_capacity > 0 ? pair_capacity : 1) + 32 * gx * gy) * 8 * 4;
     s->region_done_bytes = gx * gy * 8 * 4;
+    s->band_flags_bytes = (n + 255) / 256;
     s->tiles_x = (uint32_t)gx;
     s->tiles_y = (uint32_t)gy;
     return VTGS_OK;

@@ -538,7 +538,7 @@ fused_preprocess_backward_kernel(const __grid_constant__ CamConst cam, int64_t N
                                  const GeomRecord* __restrict__ geom, float* __restrict__ grad_geom,
                                  VtgsParamGrads out, int accumulate, int want_pose,
                                  const VtgsCounters* __restrict__ counters, unsigned int* __restrict__ ticket,
-                                 const uint32_t* __restrict__ tiles_touched) {
+                                 const uint32_t* __restrict__ tiles_touched, const uint8_t* __restrict__ band_flags) {
     __shared__ float s_part[8][POSE_TERMS];
     __shared__ double s_sum[POSE_TERMS][21];
     __shared__ bool s_last;
@@ -553,12 +553,7 @@ fused_preprocess_backward_kernel(const __grid_constant__ CamConst cam, int64_t N
     for (int k = 0; k < 16; ++k) pose_v[k] = 0.0f;
 
     const bool want_op = out.logit_opacities != nullptr;
-    int64_t i = (int64_t)blockIdx.x * 256 + tid;
-    K7Item nxt;
-    if (i < N) k7_load(nxt, i, prm, geom, grad_geom, rot_aligned, tiles_touched, want_op);
-    for (; i < N; i += stride) {
-        const K7Item it = nxt;
-        if (i + stride < N) k7_load(nxt, i + stride, prm, geom, grad_geom, rot_aligned, tiles_touched, want_op);
+    auto process = [&](const K7Item& it, const int64_t i) {
         const float4 g0 = it.g0, g1 = it.g1, g2 = it.g2;
         // culled splats, and splats no pixel blended (all sums exactly zero), have zero gradients: every
         // term below is linear in g0..g2
@@ -622,6 +617,35 @@ fused_preprocess_backward_kernel(const __grid_constant__ CamConst cam, int64_t N
             if (out.log_scales) out.log_scales[i] = dls;
             if (out.means2D) { out.means2D[3 * i] = g0.x; out.means2D[3 * i + 1] = g0.y; out.means2D[3 * i + 2] = 0.0f; }
         }
+    };
+    if (band_flags != nullptr) {
+        // tile-band sharding with candidate blocks (K0'): only the 256-Gaussian blocks that can reach the band are read;
+        // the others hold exact zeros (their outputs are written as such when requested)
+        const int64_t nblk = (N + 255) / 256;
+        for (int64_t b = blockIdx.x; b < nblk; b += gridDim.x) {
+            const int64_t i = b * 256 + tid;
+            if (i >= N) continue;
+            K7Item it;
+            if (band_flags[b] != 0) {
+                k7_load(it, i, prm, geom, grad_geom, rot_aligned, tiles_touched, want_op);
+            } else {
+                const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                it.g0 = z4; it.g1 = z4; it.g2 = z4; it.uq = z4;
+                it.hx = -1e30f; it.op = 0.f; it.px = 0.f; it.py = 0.f; it.pz = 0.f; it.ls = 0.f;
+                if (!accumulate && out.means3D == nullptr && out.rgb_colors == nullptr && out.unnorm_rotations == nullptr &&
+                    out.logit_opacities == nullptr && out.log_scales == nullptr && out.means2D == nullptr) continue;
+            }
+            process(it, i);
+        }
+    } else {
+        int64_t i = (int64_t)blockIdx.x * 256 + tid;
+        K7Item nxt;
+        if (i < N) k7_load(nxt, i, prm, geom, grad_geom, rot_aligned, tiles_touched, want_op);
+        for (; i < N; i += stride) {
+            const K7Item it = nxt;
+            if (i + stride < N) k7_load(nxt, i + stride, prm, geom, grad_geom, rot_aligned, tiles_touched, want_op);
+            process(it, i);
+        }
     }
     if (!want_pose) return;
     const float tot = warp_transpose_reduce<POSE_TERMS>(pose_v, lane);
@@ -669,16 +693,17 @@ int launch_fused_backward(const VtgsCamera* camera, const VtgsParams* params, co
         }
         unsigned int* ticket = reinterpret_cast<unsigned int*>(grads->pose_scratch ? grads->pose_scratch + (size_t)blocks * POSE_TERMS : nullptr);
         const uint32_t* band_touch = band_tiles < cam.gx * cam.gy ? buf->tiles_touched : nullptr;
+        const uint8_t* band_flags = band_touch ? buf->band_flags : nullptr;       // written by this iteration's forward (K0')
         if (grads->log_scales != nullptr || grads->unnorm_rotations != nullptr) {
             VTGS_PROF("fused_preprocess_backward_kernel", stream);
             fused_preprocess_backward_kernel<true><<<blocks, 256, 0, stream>>>(cam, N, *params, buf->counters->pose_R, pose->depth_row[0], pose->depth_row[1],
                                                                                pose->depth_row[2], geom, buf->grad_geom, *grads, accumulate, want_pose,
-                                                                               buf->counters, ticket, band_touch);
+                                                                               buf->counters, ticket, band_touch, band_flags);
         } else {
             VTGS_PROF("fused_preprocess_backward_kernel", stream);
             fused_preprocess_backward_kernel<false><<<blocks, 256, 0, stream>>>(cam, N, *params, buf->counters->pose_R, pose->depth_row[0], pose->depth_row[1],
                                                                                 pose->depth_row[2], geom, buf->grad_geom, *grads, accumulate, want_pose,
-                                                                                buf->counters, ticket, band_touch);
+                                                                                buf->counters, ticket, band_touch, band_flags);
         }
         VTGS_LAUNCH_CHECK();
     } else if (want_pose && !accumulate) {

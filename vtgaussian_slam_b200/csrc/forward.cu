@@ -47,6 +47,55 @@ __device__ __forceinline__ void warp_tile_walk(int minx, int miny, int maxx, int
     }
 }
 
+// =============================== K0': band candidate blocks ================================
+// Tile-band sharding (multi-GPU tracking): every rank holds all N Gaussians but renders only its band of tile rows.
+// Per iteration, one fully parallel pass over (position, log-scale) -- 16 bytes per Gaussian -- marks the 256-Gaussian
+// BLOCKS that hold at least one splat able to reach the band at the CURRENT pose (the same conservative screen-space
+// bound K1' applies per splat) and zeroes radii / tiles_touched of the others.  K1', the scatter and K7' then skip the
+// unmarked blocks outright, so their cost follows the band, not N: a view-tied section is ordered like its image, so a
+// band of rows is a few contiguous runs of blocks.  Nothing is cached across iterations: no staleness to bound.
+__global__ void __launch_bounds__(256)
+band_flags_kernel(const __grid_constant__ CamConst cam, int64_t N, FrontEnd fe, const float* __restrict__ means3D,
+                  const float* __restrict__ log_scales, int32_t* __restrict__ radii, uint32_t* __restrict__ tiles_touched,
+                  uint8_t* __restrict__ flags) {
+    __shared__ float s_Rt[12];
+    if (threadIdx.x == 0) {
+        float Rt[12], qn[4], nrm2[2];
+        pose_from_quat(fe.cam_unnorm_rot, fe.cam_trans, Rt, qn, nrm2);
+#pragma unroll
+        for (int k = 0; k < 12; ++k) s_Rt[k] = Rt[k];
+    }
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    bool reach = false;
+    if (i < N) {
+        const float x = means3D[3 * i], y = means3D[3 * i + 1], z = means3D[3 * i + 2];
+        const float X = s_Rt[0] * x + s_Rt[1] * y + s_Rt[2] * z + s_Rt[9];
+        const float Y = s_Rt[3] * x + s_Rt[4] * y + s_Rt[5] * z + s_Rt[10];
+        const float Z = s_Rt[6] * x + s_Rt[7] * y + s_Rt[8] * z + s_Rt[11];
+        float smax;
+        if (fe.log_scales_dim == 1) smax = __expf(log_scales[i]);
+        else smax = __expf(fmaxf(log_scales[3 * i], fmaxf(log_scales[3 * i + 1], log_scales[3 * i + 2])));
+        smax *= 1.001f * cam.scale_modifier;
+        const float tz_ = xform_row(cam.view, 2, X, Y, Z);
+        reach = true;                                        // (culled splats are K1's business)
+        if (tz_ > VTGS_NEAR_CULL) {
+            const float hy_ = xform_row(cam.proj, 1, X, Y, Z), hw_ = xform_row(cam.proj, 3, X, Y, Z);
+            const float py_ = ((__fdividef(hy_, hw_ + VTGS_EPS_W) + 1.0f) * (float)cam.H - 1.0f) * 0.5f;
+            const float itz = __fdividef(1.0f, tz_);
+            const float tr = smax * smax * itz * itz * (cam.focal_x * cam.focal_x * (1.0f + cam.limx * cam.limx) +
+                                                         cam.focal_y * cam.focal_y * (1.0f + cam.limy * cam.limy)) + 2.0f * VTGS_LOWPASS;
+            const float rb = cam.sigma_mult * sqrtf(tr) * 1.02f + 4.0f;          // a little wider than K1's own test
+            reach = !((py_ - rb > (float)(cam.row1 * 16)) || (py_ + rb + 16.0f < (float)(cam.row0 * 16)));
+        } else {
+            reach = false;                                   // behind the near plane: K1' would cull it anyway
+        }
+    }
+    const bool any = __syncthreads_or(reach) != 0;
+    if (threadIdx.x == 0) flags[blockIdx.x] = any ? 1 : 0;
+    if (!any && i < N) { radii[i] = 0; tiles_touched[i] = 0u; }
+}
+
 // =============================== K1': preprocess =========================================
 // Persistent grid-stride kernel, one Gaussian per thread per trip; the loads of the NEXT Gaussian are
 // in flight while the current one is projected (the math is ~1000 instructions of IEEE div / sqrt /
@@ -84,7 +133,11 @@ preprocess_kernel(const __grid_constant__ CamConst cam, int64_t N, FrontEnd fe,
                   const float* __restrict__ rotations, const float* __restrict__ opacities,
                   const float* __restrict__ colors,
                   GeomRecord* __restrict__ geom, int32_t* __restrict__ radii,
-                  uint32_t* __restrict__ tiles_touched, uint32_t* __restrict__ tile_counts) {
+                  uint32_t* __restrict__ tiles_touched, uint32_t* __restrict__ tile_counts,
+                  const uint8_t* __restrict__ band_flags) {
+    // band mode with candidate blocks: one block per 256 Gaussians, unmarked blocks were dealt with by K0'
+    // (block 0 always runs: it publishes the frame's pose for the backward)
+    if (band_flags != nullptr && blockIdx.x != 0 && band_flags[blockIdx.x] == 0) return;
     const int tid = threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * 256;
     const bool rot_aligned = (reinterpret_cast<uintptr_t>(rotations) & 15) == 0;
@@ -293,7 +346,8 @@ tile_scan_kernel(uint32_t* __restrict__ tile_counts, uint32_t* __restrict__ rang
 __global__ void __launch_bounds__(256)
 scatter_kernel(int64_t N, int gx, const GeomRecord* __restrict__ geom, const uint32_t* __restrict__ tiles_touched,
                const uint32_t* __restrict__ ranges, uint32_t* __restrict__ tile_cursor,
-               uint64_t* __restrict__ pair_keys) {
+               uint64_t* __restrict__ pair_keys, const uint8_t* __restrict__ band_flags) {
+    if (band_flags != nullptr && band_flags[blockIdx.x] == 0) return;          // no splat of this block reaches the band
     const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
     int minx = 0, miny = 0, maxx = 0, maxy = 0;
     uint64_t key = 0;
@@ -954,16 +1008,23 @@ int launch_forward(const VtgsCamera* camera, int64_t N, bool fused, const FrontE
     VTGS_CUDA_CHECK(cudaMemsetAsync(buf->tile_counts, 0, sizeof(uint32_t) * num_tiles, stream));
     const int blocks = (int)((N + 255) / 256);
     const int k1_blocks = blocks < 148 * 6 ? blocks : 148 * 6;          // persistent: 3 resident blocks per SM x 2 waves
+    const bool band_active = cam.row0 > 0 || cam.row1 < cam.gy;
+    const uint8_t* flags = (fused && band_active && N > 0) ? buf->band_flags : nullptr;
     if (N > 0) {
         const bool narrow_band = (cam.row1 - cam.row0) * 5 < cam.gy * 2;
+        if (flags) {
+            { VTGS_PROF("band_flags_kernel", stream); band_flags_kernel<<<blocks, 256, 0, stream>>>(cam, N, fe, means3D, scales, radii, buf->tiles_touched, buf->band_flags); }
+            VTGS_LAUNCH_CHECK();
+        }
+        const int k1_grid = flags ? blocks : k1_blocks;
         if (fused && narrow_band)
-            { VTGS_PROF("preprocess_kernel", stream); preprocess_kernel<true, true><<<k1_blocks, 256, 0, stream>>>(cam, N, fe, means3D, scales, rotations, opacities, colors,
-                                                                 geom, radii, buf->tiles_touched, buf->tile_counts); }
+            { VTGS_PROF("preprocess_kernel", stream); preprocess_kernel<true, true><<<k1_grid, 256, 0, stream>>>(cam, N, fe, means3D, scales, rotations, opacities, colors,
+                                                                 geom, radii, buf->tiles_touched, buf->tile_counts, flags); }
         else if (fused)
-            { VTGS_PROF("preprocess_kernel", stream); preprocess_kernel<true><<<k1_blocks, 256, 0, stream>>>(cam, N, fe, means3D, scales, rotations, opacities, colors,
-                                                                 geom, radii, buf->tiles_touched, buf->tile_counts); }
-        else { VTGS_PROF("preprocess_kernel", stream); preprocess_kernel<false><<<k1_blocks, 256, 0, stream>>>(cam, N, fe, means3D, scales, rotations, opacities, colors,
-                                                                  geom, radii, buf->tiles_touched, buf->tile_counts); }
+            { VTGS_PROF("preprocess_kernel", stream); preprocess_kernel<true><<<k1_grid, 256, 0, stream>>>(cam, N, fe, means3D, scales, rotations, opacities, colors,
+                                                                 geom, radii, buf->tiles_touched, buf->tile_counts, flags); }
+        else { VTGS_PROF("preprocess_kernel", stream); preprocess_kernel<false><<<k1_grid, 256, 0, stream>>>(cam, N, fe, means3D, scales, rotations, opacities, colors,
+                                                                  geom, radii, buf->tiles_touched, buf->tile_counts, nullptr); }
         VTGS_LAUNCH_CHECK();
     }
     // only the band's tiles hold counts (tile-band sharding: K1' clips every rect to the band); the fused solvers never
@@ -973,7 +1034,7 @@ int launch_forward(const VtgsCamera* camera, int64_t N, bool fused, const FrontE
     { VTGS_PROF("tile_scan_kernel", stream); tile_scan_kernel<<<1, 1024, 0, stream>>>(buf->tile_counts + scan0, buf->tile_ranges + 2 * (size_t)scan0, scan_n, buf->pair_capacity, buf->counters); }
     VTGS_LAUNCH_CHECK();
     if (N > 0 && band_tiles > 0) {
-        { VTGS_PROF("scatter_kernel", stream); scatter_kernel<<<blocks, 256, 0, stream>>>(N, cam.gx, geom, buf->tiles_touched, buf->tile_ranges, buf->tile_counts, buf->pair_keys); }
+        { VTGS_PROF("scatter_kernel", stream); scatter_kernel<<<blocks, 256, 0, stream>>>(N, cam.gx, geom, buf->tiles_touched, buf->tile_ranges, buf->tile_counts, buf->pair_keys, flags); }
         VTGS_LAUNCH_CHECK();
         static std::atomic<uint64_t> sort_attr{0};
         if (first_call_on_device(sort_attr))

@@ -112,6 +112,7 @@ class Workspace:
         self.counters = torch.zeros(sz.counters_bytes // 4, dtype=torch.int32, device=device)
         self.region_cnt = torch.zeros(sz.region_cnt_bytes // 4, dtype=torch.int32, device=device)
         self.region_done = torch.zeros(sz.region_done_bytes // 4, dtype=torch.int32, device=device)
+        self.band_flags = torch.zeros(max(int(sz.band_flags_bytes), 1), dtype=torch.uint8, device=device)
         self.region_pairs = self.region_masks = None
         self._num_tiles = sz.tiles_x * sz.tiles_y
         self.pair_capacity = 0
@@ -149,6 +150,7 @@ class Workspace:
         b.region_masks = self.region_masks.data_ptr()
         b.region_done = self.region_done.data_ptr()
         b.pair_capacity = self.pair_capacity
+        b.band_flags = self.band_flags.data_ptr()
         return b
 
     def read_counters(self):

@@ -151,10 +151,15 @@ def transformed_params2depthplussilhouette(params, w2c, transformed_gaussians):
 
 
 def initialize_optimizer(params, lrs_dict, tracking):
+    """torch.optim.Adam over one parameter group per tensor (reference src/vtgaussian_slam.py:180-187).  On CUDA the
+    optimiser's fused implementation is selected: the same update, one kernel per group instead of ~10 foreach calls --
+    the Python side of Adam.step() is otherwise a third of a tracking iteration's host time."""
     param_groups = [{'params': [v], 'name': k, 'lr': lrs_dict[k]} for k, v in params.items()]
+    fused = all(isinstance(v, torch.Tensor) and v.is_cuda and v.is_floating_point() for v in params.values())
+    extra = dict(fused=True) if fused else {}
     if tracking:
-        return torch.optim.Adam(param_groups)
-    return torch.optim.Adam(param_groups, lr=0.0, eps=1e-15)
+        return torch.optim.Adam(param_groups, **extra)
+    return torch.optim.Adam(param_groups, lr=0.0, eps=1e-15, **extra)
 
 
 # ---------------------------------------------------------------------------- the loss
@@ -376,6 +381,14 @@ class _FusedMappingLoss(torch.autograd.Function):
                 pg["logit_opacities"] * g_loss, pg["log_scales"] * g_loss, gq, gt, None, None, None, None, None, None)
 
 
+def _book_radii(variables, radius):
+    """reference :681-683: seen = radius > 0; max_2D_radius[seen] = max(radius[seen], max_2D_radius[seen]) -- without the
+    boolean-index gathers (two elementwise kernels; radii are >= 0, so unseen entries keep their value)."""
+    variables['seen'] = radius > 0
+    m = variables['max_2D_radius']
+    variables['max_2D_radius'] = torch.maximum(m, radius.to(m.dtype))
+
+
 _RENDERERS: dict = {}
 _DEPTH_ROWS: dict = {}
 
@@ -500,10 +513,7 @@ def get_loss(params, curr_data, variables, iter_time_idx, loss_weights, use_sil_
             loss, terms, radius = _FusedTrackingLoss.apply(r, params, cam_q, cam_t, curr_data['im'], curr_data['depth'], cfg, thres_fn,
                                                            _poll_due(r, tracking_iteration))
             weighted_losses = {'depth': terms[2], 'im': terms[1], 'loss': loss}
-            seen = radius > 0
-            variables['max_2D_radius'] = torch.where(seen, torch.max(radius.to(variables['max_2D_radius'].dtype),
-                                                                     variables['max_2D_radius']), variables['max_2D_radius'])
-            variables['seen'] = seen
+            _book_radii(variables, radius)
             if presence_sil_mask_mse_ls is not None:
                 return loss, variables, weighted_losses, presence_sil_mask_mse_ls, sil_thres_ls
             return loss, variables, weighted_losses
@@ -517,10 +527,7 @@ def get_loss(params, curr_data, variables, iter_time_idx, loss_weights, use_sil_
                 float(loss_weights['depth']), camera_grad, means2D)
             variables['means2D'] = means2D
             weighted_losses = {'depth': terms[2], 'im': terms[1], 'loss': loss}
-            seen = radius > 0
-            variables['max_2D_radius'] = torch.where(seen, torch.max(radius.to(variables['max_2D_radius'].dtype),
-                                                                     variables['max_2D_radius']), variables['max_2D_radius'])
-            variables['seen'] = seen
+            _book_radii(variables, radius)
             return loss, variables, weighted_losses
         g = (lambda t: t) if gaussians_grad else (lambda t: t.detach())
         means2D = torch.zeros_like(params['means3D'], requires_grad=True)            # leaf: .grad is filled by the backward
@@ -536,11 +543,7 @@ def get_loss(params, curr_data, variables, iter_time_idx, loss_weights, use_sil_
         additional_mask, dataset_name, tracking_iteration, presence_sil_mask_mse_ls, sil_thres_ls, far_depth_filter_thres,
         vis_mask)
 
-    # reference :681-683 (max_2D_radius[seen] = max(radius[seen], max_2D_radius[seen])) without the boolean-index sync
-    seen = radius > 0
-    variables['max_2D_radius'] = torch.where(seen, torch.max(radius.to(variables['max_2D_radius'].dtype),
-                                                             variables['max_2D_radius']), variables['max_2D_radius'])
-    variables['seen'] = seen
+    _book_radii(variables, radius)
     if presence_sil_mask_mse_ls is not None:
         return loss, variables, weighted_losses, presence_sil_mask_mse_ls, sil_thres_ls
     return loss, variables, weighted_losses
