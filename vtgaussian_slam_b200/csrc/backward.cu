@@ -139,7 +139,10 @@ blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __re
 
     // software pipeline over the forward's groups, last to first: masks two groups ahead, list entries and
     // records one group ahead (only for groups with at least one blended splat)
-    auto mask_of = [&](int g) { return g >= 0 ? masks[g * 32 + lane] : 0u; };
+    // a pixel whose incoming gradient is zero in every channel (masked out of the loss: silhouette below the threshold,
+    // invalid depth, outlier, invisible) contributes exact zeros to every sum: its lane walks nothing
+    const bool live_px = BG || dpix[0] != 0.0f || dpix[1] != 0.0f || dpix[2] != 0.0f || dpix[3] != 0.0f;
+    auto mask_of = [&](int g) { return (g >= 0 && live_px) ? masks[g * 32 + lane] : 0u; };
     int g = gdone - 1;
     uint32_t m_next = mask_of(g), m_next2 = mask_of(g - 1);
     bool nxt_live = __any_sync(VTGS_FULL_MASK, m_next != 0u);

@@ -58,13 +58,11 @@ __global__ void __launch_bounds__(256)
 band_flags_kernel(const __grid_constant__ CamConst cam, int64_t N, FrontEnd fe, const float* __restrict__ means3D,
                   const float* __restrict__ log_scales, int32_t* __restrict__ radii, uint32_t* __restrict__ tiles_touched,
                   uint8_t* __restrict__ flags) {
+    // the frame's pose matrix was published by pose_matrix_kernel just before this launch (12 broadcast loads instead
+    // of two normalisations per block)
     __shared__ float s_Rt[12];
-    if (threadIdx.x == 0) {
-        float Rt[12], qn[4], nrm2[2];
-        pose_from_quat(fe.cam_unnorm_rot, fe.cam_trans, Rt, qn, nrm2);
-#pragma unroll
-        for (int k = 0; k < 12; ++k) s_Rt[k] = Rt[k];
-    }
+    if (threadIdx.x < 9) s_Rt[threadIdx.x] = fe.counters->pose_R[threadIdx.x];
+    else if (threadIdx.x < 12) s_Rt[threadIdx.x] = fe.counters->pose_t[threadIdx.x - 9];
     __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
     bool reach = false;
@@ -284,10 +282,26 @@ tile_scan_kernel(uint32_t* __restrict__ tile_counts, uint32_t* __restrict__ rang
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_carry = 0;
     uint32_t vmax = 0;
+    // the counts of up to 8 chunks of 1024 tiles are fetched before the first dependent use (one L2 round trip for
+    // any image up to 8192 tiles instead of one per chunk)
+    constexpr int PRE = 8;
+    uint32_t pre[PRE];
+#pragma unroll
+    for (int k = 0; k < PRE; ++k) {
+        const int t = k * 1024 + tid;
+        pre[k] = t < num_tiles ? tile_counts[t] : 0u;
+    }
     __syncthreads();
-    for (int base = 0; base < num_tiles; base += 1024) {
+    int chunk = 0;
+    for (int base = 0; base < num_tiles; base += 1024, ++chunk) {
         const int t = base + tid;
-        const uint32_t c = t < num_tiles ? tile_counts[t] : 0u;
+        uint32_t c = 0u;
+        if (chunk < PRE) {
+#pragma unroll
+            for (int k = 0; k < PRE; ++k) if (k == chunk) c = pre[k];
+        } else if (t < num_tiles) {
+            c = tile_counts[t];
+        }
         vmax = max(vmax, c);
         uint32_t incl = c;
 #pragma unroll
@@ -1013,6 +1027,10 @@ int launch_forward(const VtgsCamera* camera, int64_t N, bool fused, const FrontE
     if (N > 0) {
         const bool narrow_band = (cam.row1 - cam.row0) * 5 < cam.gy * 2;
         if (flags) {
+            VtgsPose ps{};
+            ps.cam_unnorm_rot = fe.cam_unnorm_rot;
+            ps.cam_trans = fe.cam_trans;
+            if (int e = launch_pose_matrix(&ps, fe.counters, stream)) return e;
             { VTGS_PROF("band_flags_kernel", stream); band_flags_kernel<<<blocks, 256, 0, stream>>>(cam, N, fe, means3D, scales, radii, buf->tiles_touched, buf->band_flags); }
             VTGS_LAUNCH_CHECK();
         }
