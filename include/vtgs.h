@@ -108,7 +108,7 @@ typedef struct VtgsCounters {
 typedef struct VtgsBuffers {
     void*         geom;           /* N records of VTGS_GEOM_RECORD_BYTES                  */
     uint32_t*     tiles_touched;  /* [N]                                                   */
-    uint32_t*     tile_counts;    /* [tiles]  scratch (zeroed by forward)                  */
+    uint32_t*     tile_counts;    /* [tiles + 1]  scratch (zeroed by forward); the last word counts band_cand  */
     uint32_t*     tile_ranges;    /* [tiles][2] = {begin, end} into point_list             */
     uint64_t*     pair_keys;      /* [pair_capacity] depth_bits<<32 | gaussian id<<8 | region mask */
     uint32_t*     point_list;     /* [pair_capacity] sorted Gaussian ids                   */
@@ -130,6 +130,12 @@ typedef struct VtgsBuffers {
                                      iteration the forward marks the 256-Gaussian blocks that can reach the band at the
                                      current pose; preprocess, scatter and backward-preprocess skip the others, so a
                                      rank's per-Gaussian work follows its band instead of N                        */
+    uint32_t*     band_cand;      /* [ceil(N / 256)] optional, with band_flags: the marked blocks as a compact list (its
+                                     length lives in tile_counts[tiles], zeroed with the counts)                  */
+    uint32_t*     tile_order;     /* [tiles] optional (may be NULL).  The tile scan leaves the tiles of the render in
+                                     descending order of list length; the sort and blend kernels take their tile from it,
+                                     so the longest lists are started first (longest-processing-time-first scheduling of
+                                     the blocks: the tail of a launch is filled with short tiles)                   */
 } VtgsBuffers;
 
 #define VTGS_GEOM_RECORD_BYTES 64
@@ -151,6 +157,8 @@ typedef struct VtgsWorkspaceSizes {
     uint64_t region_masks_bytes;
     uint64_t region_done_bytes;
     uint64_t band_flags_bytes;
+    uint64_t band_cand_bytes;
+    uint64_t tile_order_bytes;
     uint32_t tiles_x;
     uint32_t tiles_y;
 } VtgsWorkspaceSizes;

@@ -16,6 +16,7 @@ from vtgaussian_slam_b200.rasterizer import GaussianRasterizationSettings  # noq
 ap = argparse.ArgumentParser()
 ap.add_argument("--small", action="store_true")
 ap.add_argument("--iters", type=int, default=3)
+ap.add_argument("--band", type=int, nargs=2, default=(0, 0), help="tile-row band (as one rank of a sharded run would render)")
 a = ap.parse_args()
 wl = bench.build_workload("small" if a.small else "c2")
 dev = torch.device("cuda:0")
@@ -25,7 +26,7 @@ settings = GaussianRasterizationSettings(
     scale_modifier=1.0, viewmatrix=torch.tensor(s["viewmatrix"], device=dev), projmatrix=torch.tensor(s["projmatrix"], device=dev),
     sh_degree=0, campos=torch.tensor(s["campos"], device=dev), prefiltered=False)
 params = {k: torch.tensor(v, device=dev) for k, v in wl["params"].items()}
-solver = TrackingSolver(settings, params, device=dev, w_im=0.5, w_depth=0.025, sil_thres=0.99, use_graph=False)
+solver = TrackingSolver(settings, params, device=dev, w_im=0.5, w_depth=0.025, sil_thres=0.99, use_graph=False, tile_rows=tuple(a.band))
 solver.set_frame(torch.tensor(fr["im"]), torch.tensor(fr["depth"]), wl["q"], wl["t"])
 for _ in range(a.iters):
     solver.step()

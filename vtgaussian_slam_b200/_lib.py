@@ -47,7 +47,7 @@ class VtgsBuffers(C.Structure):
         ("final_T", C.c_void_p), ("n_contrib", C.c_void_p), ("grad_geom", C.c_void_p),
         ("counters", C.c_void_p), ("region_pairs", C.c_void_p), ("region_cnt", C.c_void_p),
         ("region_masks", C.c_void_p), ("region_done", C.c_void_p), ("pair_capacity", C.c_uint64),
-        ("band_flags", C.c_void_p),
+        ("band_flags", C.c_void_p), ("band_cand", C.c_void_p), ("tile_order", C.c_void_p),
     ]
 
 
@@ -55,7 +55,7 @@ class VtgsWorkspaceSizes(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "geom_bytes", "tiles_touched_bytes", "tile_counts_bytes", "tile_ranges_bytes", "pair_keys_bytes",
         "point_list_bytes", "final_T_bytes", "n_contrib_bytes", "grad_geom_bytes", "counters_bytes",
-        "region_pairs_bytes", "region_cnt_bytes", "region_masks_bytes", "region_done_bytes", "band_flags_bytes")] + \
+        "region_pairs_bytes", "region_cnt_bytes", "region_masks_bytes", "region_done_bytes", "band_flags_bytes", "band_cand_bytes", "tile_order_bytes")] + \
         [("tiles_x", C.c_uint32), ("tiles_y", C.c_uint32)]
 
 

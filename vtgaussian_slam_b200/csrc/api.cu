@@ -85,7 +85,7 @@ int vtgs_workspace_query(int32_t W, int32_t H, int64_t N, uint64_t pair_capacity
     const uint64_t n = (uint64_t)(N > 0 ? N : 1), P = (uint64_t)W * H;
     s->geom_bytes = n * VTGS_GEOM_RECORD_BYTES;
     s->tiles_touched_bytes = n * 4;
-    s->tile_counts_bytes = gx * gy * 4;
+    s->tile_counts_bytes = (gx * gy + 1) * 4;
     s->tile_ranges_bytes = gx * gy * 8;
     s->pair_keys_bytes = (pair_capacity > 0 ? pair_capacity : 1) * 8;
     s->point_list_bytes = (pair_capacity > 0 ? pair_capacity : 1) * 4;
@@ -98,6 +98,8 @@ int vtgs_workspace_query(int32_t W, int32_t H, int64_t N, uint64_t pair_capacity
     s->region_masks_bytes = ((pair_capacity > 0 ? pair_capacity : 1) + 32 * gx * gy) * 8 * 4;
     s->region_done_bytes = gx * gy * 8 * 4;
     s->band_flags_bytes = (n + 255) / 256;
+    s->band_cand_bytes = ((n + 255) / 256) * 4;
+    s->tile_order_bytes = gx * gy * 4;
     s->tiles_x = (uint32_t)gx;
     s->tiles_y = (uint32_t)gy;
     return VTGS_OK;

@@ -90,7 +90,8 @@ blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __re
                       const uint2* __restrict__ region_pairs, const uint32_t* __restrict__ region_cnt,
                       const uint32_t* __restrict__ region_masks, const uint32_t* __restrict__ region_done,
                       const GeomRecord* __restrict__ geom,
-                      const float* __restrict__ final_T, const float* __restrict__ dL_dpix, float* __restrict__ grad_geom) {
+                      const float* __restrict__ final_T, const float* __restrict__ dL_dpix, float* __restrict__ grad_geom,
+                      const uint32_t* __restrict__ tile_order) {
     constexpr int NCH = FUSED ? 4 : 3;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     struct WarpArea {
@@ -104,7 +105,7 @@ blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __re
     WarpArea* areas = reinterpret_cast<WarpArea*>(smem_raw);
 
     constexpr int BPT = 8 / BWD_WARPS;                                  // blocks per tile
-    const int tile = cam.row0 * cam.gx + blockIdx.x / BPT;
+    const int tile = cam.row0 * cam.gx + (tile_order ? (int)tile_order[blockIdx.x / BPT] : (int)(blockIdx.x / BPT));
     const int tile_x = tile % cam.gx, tile_y = tile / cam.gx;
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = (blockIdx.x % BPT) * BWD_WARPS + (tid >> 5);       // region index inside the tile
@@ -390,7 +391,7 @@ preprocess_backward_kernel(const __grid_constant__ CamConst cam, int64_t N,
 constexpr int BWD_SMEM = BWD_WARPS * (int)(sizeof(GroupSmem) + 32 * 32 * sizeof(float2) + 32 * sizeof(float4) + 32 * sizeof(float2));
 template <bool FUSED, bool BG, bool LITE>
 static int launch_blend_backward(int blocks, cudaStream_t stream, const CamConst& cam, const VtgsBuffers* buf, const GeomRecord* geom,
-                                 const float* dL_dpix) {
+                                 const float* dL_dpix, const uint32_t* order) {
     static std::atomic<uint64_t> done{0};
     if (first_call_on_device(done)) {
         VTGS_CUDA_CHECK(cudaFuncSetAttribute(blend_backward_kernel<FUSED, BG, LITE>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
@@ -399,7 +400,7 @@ static int launch_blend_backward(int blocks, cudaStream_t stream, const CamConst
     VTGS_PROF("blend_backward_kernel", stream);
     blend_backward_kernel<FUSED, BG, LITE><<<blocks, 32 * BWD_WARPS, BWD_SMEM, stream>>>(
         cam, buf->tile_ranges, reinterpret_cast<const uint2*>(buf->region_pairs), buf->region_cnt, buf->region_masks, buf->region_done,
-        geom, buf->final_T, dL_dpix, buf->grad_geom);
+        geom, buf->final_T, dL_dpix, buf->grad_geom, order);
     VTGS_LAUNCH_CHECK();
     return VTGS_OK;
 }
@@ -418,8 +419,9 @@ int launch_backward(const VtgsCamera* camera, int64_t N,
     if (band_tiles > 0) {
         const bool has_bg = cam.bg[0] != 0.0f || cam.bg[1] != 0.0f || cam.bg[2] != 0.0f;
         const int blocks = band_tiles * (8 / BWD_WARPS);
-        if (int e = has_bg ? launch_blend_backward<false, true, false>(blocks, stream, cam, buf, geom, dL_dout_color)
-                           : launch_blend_backward<false, false, false>(blocks, stream, cam, buf, geom, dL_dout_color)) return e;
+        const uint32_t* order = nullptr;                  // (the forward orders tiles only for the fused path's tile bands)
+        if (int e = has_bg ? launch_blend_backward<false, true, false>(blocks, stream, cam, buf, geom, dL_dout_color, order)
+                           : launch_blend_backward<false, false, false>(blocks, stream, cam, buf, geom, dL_dout_color, order)) return e;
     }
     { VTGS_PROF("preprocess_backward_kernel", stream); preprocess_backward_kernel<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(cam, N, means3D, scales, rotations, nullptr, geom,
                                                                                buf->grad_geom, dL_dmeans2D, dL_dcolors, dL_dopacity,
@@ -541,7 +543,8 @@ fused_preprocess_backward_kernel(const __grid_constant__ CamConst cam, int64_t N
                                  const GeomRecord* __restrict__ geom, float* __restrict__ grad_geom,
                                  VtgsParamGrads out, int accumulate, int want_pose,
                                  const VtgsCounters* __restrict__ counters, unsigned int* __restrict__ ticket,
-                                 const uint32_t* __restrict__ tiles_touched, const uint8_t* __restrict__ band_flags) {
+                                 const uint32_t* __restrict__ tiles_touched, const uint8_t* __restrict__ band_flags,
+                                 const uint32_t* __restrict__ cand, const uint32_t* __restrict__ n_cand) {
     __shared__ float s_part[8][POSE_TERMS];
     __shared__ double s_sum[POSE_TERMS][21];
     __shared__ bool s_last;
@@ -621,24 +624,29 @@ fused_preprocess_backward_kernel(const __grid_constant__ CamConst cam, int64_t N
             if (out.means2D) { out.means2D[3 * i] = g0.x; out.means2D[3 * i + 1] = g0.y; out.means2D[3 * i + 2] = 0.0f; }
         }
     };
-    if (band_flags != nullptr) {
-        // tile-band sharding with candidate blocks (K0'): only the 256-Gaussian blocks that can reach the band are read;
-        // the others hold exact zeros (their outputs are written as such when requested)
-        const int64_t nblk = (N + 255) / 256;
-        for (int64_t b = blockIdx.x; b < nblk; b += gridDim.x) {
-            const int64_t i = b * 256 + tid;
+    if (cand != nullptr) {
+        // tile-band sharding with candidate blocks (K0'): only the 256-Gaussian blocks that can reach the band are read
+        // (persistent loop over the list); the others hold exact zeros, written as such when outputs were requested
+        const int64_t nc = (int64_t)*n_cand;
+        for (int64_t trip = blockIdx.x; trip < nc; trip += gridDim.x) {
+            const int64_t i = (int64_t)cand[trip] * 256 + tid;
             if (i >= N) continue;
             K7Item it;
-            if (band_flags[b] != 0) {
-                k7_load(it, i, prm, geom, grad_geom, rot_aligned, tiles_touched, want_op);
-            } else {
-                const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                it.g0 = z4; it.g1 = z4; it.g2 = z4; it.uq = z4;
-                it.hx = -1e30f; it.op = 0.f; it.px = 0.f; it.py = 0.f; it.pz = 0.f; it.ls = 0.f;
-                if (!accumulate && out.means3D == nullptr && out.rgb_colors == nullptr && out.unnorm_rotations == nullptr &&
-                    out.logit_opacities == nullptr && out.log_scales == nullptr && out.means2D == nullptr) continue;
-            }
+            k7_load(it, i, prm, geom, grad_geom, rot_aligned, tiles_touched, want_op);
             process(it, i);
+        }
+        const bool any_out = out.means3D != nullptr || out.rgb_colors != nullptr || out.unnorm_rotations != nullptr ||
+                             out.logit_opacities != nullptr || out.log_scales != nullptr || out.means2D != nullptr;
+        if (any_out && !accumulate) {
+            const int64_t nblk = (N + 255) / 256;
+            K7Item zit;
+            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            zit.g0 = z4; zit.g1 = z4; zit.g2 = z4; zit.uq = z4;
+            zit.hx = -1e30f; zit.op = 0.f; zit.px = 0.f; zit.py = 0.f; zit.pz = 0.f; zit.ls = 0.f;
+            for (int64_t b = blockIdx.x; b < nblk; b += gridDim.x) {
+                const int64_t i = b * 256 + tid;
+                if (band_flags[b] == 0 && i < N) process(zit, i);
+            }
         }
     } else {
         int64_t i = (int64_t)blockIdx.x * 256 + tid;
@@ -687,26 +695,32 @@ int launch_fused_backward(const VtgsCamera* camera, const VtgsParams* params, co
             // tracking asks for the pose gradient only: no colour / opacity sums are formed (K7' never reads them then)
             const bool lite = grads->rgb_colors == nullptr && grads->logit_opacities == nullptr;
             const int bblocks = band_tiles * (8 / BWD_WARPS);
+            // the fused forward left the band's tiles in longest-list-first order (tile bands only: same condition there)
+            const uint32_t* order = band_tiles < cam.gx * cam.gy ? buf->tile_order : nullptr;
             int e;
-            if (has_bg) e = lite ? launch_blend_backward<true, true, true>(bblocks, stream, cam, buf, geom, dL_dimage4)
-                                 : launch_blend_backward<true, true, false>(bblocks, stream, cam, buf, geom, dL_dimage4);
-            else e = lite ? launch_blend_backward<true, false, true>(bblocks, stream, cam, buf, geom, dL_dimage4)
-                          : launch_blend_backward<true, false, false>(bblocks, stream, cam, buf, geom, dL_dimage4);
+            if (has_bg) e = lite ? launch_blend_backward<true, true, true>(bblocks, stream, cam, buf, geom, dL_dimage4, order)
+                                 : launch_blend_backward<true, true, false>(bblocks, stream, cam, buf, geom, dL_dimage4, order);
+            else e = lite ? launch_blend_backward<true, false, true>(bblocks, stream, cam, buf, geom, dL_dimage4, order)
+                          : launch_blend_backward<true, false, false>(bblocks, stream, cam, buf, geom, dL_dimage4, order);
             if (e) return e;
         }
         unsigned int* ticket = reinterpret_cast<unsigned int*>(grads->pose_scratch ? grads->pose_scratch + (size_t)blocks * POSE_TERMS : nullptr);
         const uint32_t* band_touch = band_tiles < cam.gx * cam.gy ? buf->tiles_touched : nullptr;
-        const uint8_t* band_flags = band_touch ? buf->band_flags : nullptr;       // written by this iteration's forward (K0')
+        // candidate blocks of the band, written by this iteration's forward (K0'); the counter follows the tile counts
+        const bool use_cand = band_touch != nullptr && buf->band_flags != nullptr && buf->band_cand != nullptr;
+        const uint8_t* band_flags = use_cand ? buf->band_flags : nullptr;
+        const uint32_t* band_cand = use_cand ? buf->band_cand : nullptr;
+        const uint32_t* n_cand = buf->tile_counts + cam.gx * cam.gy;
         if (grads->log_scales != nullptr || grads->unnorm_rotations != nullptr) {
             VTGS_PROF("fused_preprocess_backward_kernel", stream);
             fused_preprocess_backward_kernel<true><<<blocks, 256, 0, stream>>>(cam, N, *params, buf->counters->pose_R, pose->depth_row[0], pose->depth_row[1],
                                                                                pose->depth_row[2], geom, buf->grad_geom, *grads, accumulate, want_pose,
-                                                                               buf->counters, ticket, band_touch, band_flags);
+                                                                               buf->counters, ticket, band_touch, band_flags, band_cand, n_cand);
         } else {
             VTGS_PROF("fused_preprocess_backward_kernel", stream);
             fused_preprocess_backward_kernel<false><<<blocks, 256, 0, stream>>>(cam, N, *params, buf->counters->pose_R, pose->depth_row[0], pose->depth_row[1],
                                                                                 pose->depth_row[2], geom, buf->grad_geom, *grads, accumulate, want_pose,
-                                                                                buf->counters, ticket, band_touch, band_flags);
+                                                                                buf->counters, ticket, band_touch, band_flags, band_cand, n_cand);
         }
         VTGS_LAUNCH_CHECK();
     } else if (want_pose && !accumulate) {

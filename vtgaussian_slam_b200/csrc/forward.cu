@@ -20,6 +20,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <atomic>
 
 #include "blend_common.cuh"
@@ -57,41 +58,64 @@ __device__ __forceinline__ void warp_tile_walk(int minx, int miny, int maxx, int
 __global__ void __launch_bounds__(256)
 band_flags_kernel(const __grid_constant__ CamConst cam, int64_t N, FrontEnd fe, const float* __restrict__ means3D,
                   const float* __restrict__ log_scales, int32_t* __restrict__ radii, uint32_t* __restrict__ tiles_touched,
-                  uint8_t* __restrict__ flags) {
-    // the frame's pose matrix was published by pose_matrix_kernel just before this launch (12 broadcast loads instead
-    // of two normalisations per block)
+                  uint8_t* __restrict__ flags, uint32_t* __restrict__ cand, uint32_t* __restrict__ n_cand) {
+    // one block = 4 candidate blocks of 256 Gaussians: all 16 loads of a thread are in flight together
     __shared__ float s_Rt[12];
-    if (threadIdx.x < 9) s_Rt[threadIdx.x] = fe.counters->pose_R[threadIdx.x];
-    else if (threadIdx.x < 12) s_Rt[threadIdx.x] = fe.counters->pose_t[threadIdx.x - 9];
-    __syncthreads();
-    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    bool reach = false;
-    if (i < N) {
-        const float x = means3D[3 * i], y = means3D[3 * i + 1], z = means3D[3 * i + 2];
-        const float X = s_Rt[0] * x + s_Rt[1] * y + s_Rt[2] * z + s_Rt[9];
-        const float Y = s_Rt[3] * x + s_Rt[4] * y + s_Rt[5] * z + s_Rt[10];
-        const float Z = s_Rt[6] * x + s_Rt[7] * y + s_Rt[8] * z + s_Rt[11];
-        float smax;
-        if (fe.log_scales_dim == 1) smax = __expf(log_scales[i]);
-        else smax = __expf(fmaxf(log_scales[3 * i], fmaxf(log_scales[3 * i + 1], log_scales[3 * i + 2])));
-        smax *= 1.001f * cam.scale_modifier;
-        const float tz_ = xform_row(cam.view, 2, X, Y, Z);
-        reach = true;                                        // (culled splats are K1's business)
-        if (tz_ > VTGS_NEAR_CULL) {
-            const float hy_ = xform_row(cam.proj, 1, X, Y, Z), hw_ = xform_row(cam.proj, 3, X, Y, Z);
-            const float py_ = ((__fdividef(hy_, hw_ + VTGS_EPS_W) + 1.0f) * (float)cam.H - 1.0f) * 0.5f;
-            const float itz = __fdividef(1.0f, tz_);
-            const float tr = smax * smax * itz * itz * (cam.focal_x * cam.focal_x * (1.0f + cam.limx * cam.limx) +
-                                                         cam.focal_y * cam.focal_y * (1.0f + cam.limy * cam.limy)) + 2.0f * VTGS_LOWPASS;
-            const float rb = cam.sigma_mult * sqrtf(tr) * 1.02f + 4.0f;          // a little wider than K1's own test
-            reach = !((py_ - rb > (float)(cam.row1 * 16)) || (py_ + rb + 16.0f < (float)(cam.row0 * 16)));
-        } else {
-            reach = false;                                   // behind the near plane: K1' would cull it anyway
+    __shared__ uint32_t s_any[4];
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        float Rt[12], qn[4], nrm2[2];
+        pose_from_quat(fe.cam_unnorm_rot, fe.cam_trans, Rt, qn, nrm2);
+#pragma unroll
+        for (int k = 0; k < 12; ++k) s_Rt[k] = Rt[k];
+    }
+    if (tid < 4) s_any[tid] = 0u;
+    float px[4], py[4], pz[4], ls[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int64_t i = ((int64_t)blockIdx.x * 4 + j) * 256 + tid;
+        px[j] = py[j] = pz[j] = ls[j] = 0.0f;
+        if (i < N) {
+            px[j] = means3D[3 * i]; py[j] = means3D[3 * i + 1]; pz[j] = means3D[3 * i + 2];
+            if (fe.log_scales_dim == 1) ls[j] = log_scales[i];
+            else ls[j] = fmaxf(log_scales[3 * i], fmaxf(log_scales[3 * i + 1], log_scales[3 * i + 2]));
         }
     }
-    const bool any = __syncthreads_or(reach) != 0;
-    if (threadIdx.x == 0) flags[blockIdx.x] = any ? 1 : 0;
-    if (!any && i < N) { radii[i] = 0; tiles_touched[i] = 0u; }
+    __syncthreads();
+    const float kx = cam.focal_x * cam.focal_x * (1.0f + cam.limx * cam.limx) + cam.focal_y * cam.focal_y * (1.0f + cam.limy * cam.limy);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int64_t i = ((int64_t)blockIdx.x * 4 + j) * 256 + tid;
+        bool reach = false;
+        if (i < N) {
+            const float X = s_Rt[0] * px[j] + s_Rt[1] * py[j] + s_Rt[2] * pz[j] + s_Rt[9];
+            const float Y = s_Rt[3] * px[j] + s_Rt[4] * py[j] + s_Rt[5] * pz[j] + s_Rt[10];
+            const float Z = s_Rt[6] * px[j] + s_Rt[7] * py[j] + s_Rt[8] * pz[j] + s_Rt[11];
+            const float tz_ = xform_row(cam.view, 2, X, Y, Z);
+            if (tz_ > VTGS_NEAR_CULL) {                  // (behind the near plane: K1' would cull it anyway)
+                const float smax = __expf(ls[j]) * 1.001f * cam.scale_modifier;
+                const float hy_ = xform_row(cam.proj, 1, X, Y, Z), hw_ = xform_row(cam.proj, 3, X, Y, Z);
+                const float py_ = ((__fdividef(hy_, hw_ + VTGS_EPS_W) + 1.0f) * (float)cam.H - 1.0f) * 0.5f;
+                const float itz = __fdividef(1.0f, tz_);
+                const float tr = smax * smax * itz * itz * kx + 2.0f * VTGS_LOWPASS;
+                const float rb = cam.sigma_mult * sqrtf(tr) * 1.02f + 4.0f;      // a little wider than K1's own test
+                reach = !((py_ - rb > (float)(cam.row1 * 16)) || (py_ + rb + 16.0f < (float)(cam.row0 * 16)));
+            }
+        }
+        if (__any_sync(VTGS_FULL_MASK, reach) && (tid & 31) == 0) s_any[j] = 1u;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int64_t blk = (int64_t)blockIdx.x * 4 + j;
+        const int64_t i = blk * 256 + tid;
+        const bool any = s_any[j] != 0u;
+        if (tid == 0 && blk * 256 < N) {
+            flags[blk] = any ? 1 : 0;
+            if (any) cand[atomicAdd(n_cand, 1u)] = (uint32_t)blk;       // (order is arbitrary: nothing downstream depends on it)
+        }
+        if (!any && i < N) { radii[i] = 0; tiles_touched[i] = 0u; }
+    }
 }
 
 // =============================== K1': preprocess =========================================
@@ -132,12 +156,10 @@ preprocess_kernel(const __grid_constant__ CamConst cam, int64_t N, FrontEnd fe,
                   const float* __restrict__ colors,
                   GeomRecord* __restrict__ geom, int32_t* __restrict__ radii,
                   uint32_t* __restrict__ tiles_touched, uint32_t* __restrict__ tile_counts,
-                  const uint8_t* __restrict__ band_flags) {
-    // band mode with candidate blocks: one block per 256 Gaussians, unmarked blocks were dealt with by K0'
-    // (block 0 always runs: it publishes the frame's pose for the backward)
-    if (band_flags != nullptr && blockIdx.x != 0 && band_flags[blockIdx.x] == 0) return;
+                  const uint32_t* __restrict__ cand, const uint32_t* __restrict__ n_cand) {
+    // Persistent loop over 256-Gaussian blocks: all of them, or (tile bands) the candidate blocks K0' listed.
     const int tid = threadIdx.x;
-    const int64_t stride = (int64_t)gridDim.x * 256;
+    const int64_t nblk = cand != nullptr ? (int64_t)*n_cand : (N + 255) / 256;
     const bool rot_aligned = (reinterpret_cast<uintptr_t>(rotations) & 15) == 0;
     const bool band_active = cam.row0 > 0 || cam.row1 < cam.gy;
     float Rt[12];
@@ -156,16 +178,23 @@ preprocess_kernel(const __grid_constant__ CamConst cam, int64_t N, FrontEnd fe,
             fe.counters->pose_qnorm[0] = nrm2[0]; fe.counters->pose_qnorm[1] = nrm2[1];
         }
     }
-    int64_t i = (int64_t)blockIdx.x * 256 + tid;
+    auto gaussian_of = [&](int64_t trip) -> int64_t {       // index handled by this thread in list trip `trip`
+        if (trip >= nblk) return N;
+        const int64_t blk = cand != nullptr ? (int64_t)cand[trip] : trip;
+        return blk * 256 + tid;
+    };
+    int64_t trip = blockIdx.x;
+    int64_t i = gaussian_of(trip);
     K1Item nxt;
     constexpr bool lite = LITE;
     if (i < N) k1_load<FUSED>(nxt, i, fe.log_scales_dim, rot_aligned, means3D, scales, rotations, opacities, colors, lite);
-    // whole warps loop together (the tile walk below is warp-collective)
-    for (int64_t wbase = i - (tid & 31); wbase < N; wbase += stride, i += stride) {
+    // whole blocks loop together (the tile walk below is warp-collective)
+    for (; trip < nblk; trip += gridDim.x) {
+        const int64_t i_next = gaussian_of(trip + gridDim.x);
         int w_minx = 0, w_maxx = 0, w_miny = 0, w_maxy = 0;       // tile rect to count (empty when culled / out of range)
         if (i < N) {
             K1Item it = nxt;
-            if (i + stride < N) k1_load<FUSED>(nxt, i + stride, fe.log_scales_dim, rot_aligned, means3D, scales, rotations, opacities, colors, lite);
+            if (i_next < N) k1_load<FUSED>(nxt, i_next, fe.log_scales_dim, rot_aligned, means3D, scales, rotations, opacities, colors, lite);
             float x = it.x, y = it.y, z = it.z;
             float sx, sy, sz, qr = it.q.x, qx = it.q.y, qy = it.q.z, qz = it.q.w, op, c3;
             if (FUSED) {
@@ -266,6 +295,7 @@ preprocess_kernel(const __grid_constant__ CamConst cam, int64_t N, FrontEnd fe,
                 }
             }
         }
+        i = i_next;
     }
 }
 
@@ -275,10 +305,11 @@ preprocess_kernel(const __grid_constant__ CamConst cam, int64_t N, FrontEnd fe,
 // scatter cursors.  Empty tiles get (0,0) like the reference's memset.
 __global__ void __launch_bounds__(1024)
 tile_scan_kernel(uint32_t* __restrict__ tile_counts, uint32_t* __restrict__ ranges, int num_tiles,
-                 uint64_t capacity, VtgsCounters* __restrict__ counters) {
+                 uint64_t capacity, VtgsCounters* __restrict__ counters, uint32_t* __restrict__ tile_order) {
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_carry;
     __shared__ uint32_t s_max[32];
+    __shared__ uint32_t s_hist[32], s_cur[32], s_vmax;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_carry = 0;
     uint32_t vmax = 0;
@@ -350,6 +381,42 @@ tile_scan_kernel(uint32_t* __restrict__ tile_counts, uint32_t* __restrict__ rang
         counters->num_rendered = total;
         counters->overflow = (uint64_t)total > capacity ? 1u : 0u;
         counters->max_tile_pairs = m;
+        s_vmax = m;
+    }
+    if (tile_order == nullptr) return;
+    // Longest lists first: a 32-bucket counting sort of the tiles by list length (descending).  Blocks are handed to the
+    // SMs in index order, so the sort / blend kernels, which take their tile from this order, start the heaviest tiles
+    // first and fill the tail of the launch with light ones (order inside a bucket is arbitrary: no output depends on it).
+    if (tid < 32) { s_hist[tid] = 0u; s_cur[tid] = 0u; }
+    __syncthreads();
+    const uint32_t denom = s_vmax + 1u;
+    if (num_tiles > PRE * 1024) {                        // larger images than the prefetch covers: raster order
+        for (int t = tid; t < num_tiles; t += 1024) tile_order[t] = (uint32_t)t;
+        return;
+    }
+    uint32_t bk[PRE];
+#pragma unroll
+    for (int k = 0; k < PRE; ++k) {
+        const int t = k * 1024 + tid;
+        bk[k] = 31u - min(31u, (uint32_t)(((uint64_t)pre[k] * 32u) / denom));
+        if (t < num_tiles) atomicAdd(&s_hist[bk[k]], 1u);
+    }
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t h = s_hist[lane];
+        uint32_t incl = h;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t n = __shfl_up_sync(VTGS_FULL_MASK, incl, o);
+            if (lane >= o) incl += n;
+        }
+        s_cur[lane] = incl - h;                          // bucket starts; bumped below as slots are claimed
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < PRE; ++k) {
+        const int t = k * 1024 + tid;
+        if (t < num_tiles) tile_order[atomicAdd(&s_cur[bk[k]], 1u)] = (uint32_t)t;
     }
 }
 
@@ -360,9 +427,11 @@ tile_scan_kernel(uint32_t* __restrict__ tile_counts, uint32_t* __restrict__ rang
 __global__ void __launch_bounds__(256)
 scatter_kernel(int64_t N, int gx, const GeomRecord* __restrict__ geom, const uint32_t* __restrict__ tiles_touched,
                const uint32_t* __restrict__ ranges, uint32_t* __restrict__ tile_cursor,
-               uint64_t* __restrict__ pair_keys, const uint8_t* __restrict__ band_flags) {
-    if (band_flags != nullptr && band_flags[blockIdx.x] == 0) return;          // no splat of this block reaches the band
-    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+               uint64_t* __restrict__ pair_keys, const uint32_t* __restrict__ cand, const uint32_t* __restrict__ n_cand) {
+    // blocks of 256 Gaussians: all of them (one per CUDA block), or the candidate blocks of a tile band (persistent loop)
+    const int64_t nblk = cand != nullptr ? (int64_t)*n_cand : (N + 255) / 256;
+    for (int64_t trip = blockIdx.x; trip < nblk; trip += gridDim.x) {
+    const int64_t i = (cand != nullptr ? (int64_t)cand[trip] : trip) * 256 + threadIdx.x;
     int minx = 0, miny = 0, maxx = 0, maxy = 0;
     uint64_t key = 0;
     float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -383,6 +452,7 @@ scatter_kernel(int64_t N, int gx, const GeomRecord* __restrict__ geom, const uin
         const uint32_t rmask = region_mask(q0, (float)(tx * 16), (float)(ty * 16));
         if (pos < ranges[2 * tile + 1]) pair_keys[pos] = key | rmask;
     });
+    }
 }
 
 // =============================== K4': per-tile sort ========================================
@@ -808,11 +878,11 @@ __device__ __forceinline__ void build_region_lists(const uint64_t* keys, int n, 
 __global__ void __launch_bounds__(256, 4)
 tile_sort_kernel(const __grid_constant__ CamConst cam, const uint32_t* __restrict__ ranges, int tile0,
                  uint64_t* __restrict__ pair_keys, uint32_t* __restrict__ point_list, const GeomRecord* __restrict__ geom,
-                 uint2* __restrict__ region_pairs, uint32_t* __restrict__ region_cnt) {
+                 uint2* __restrict__ region_pairs, uint32_t* __restrict__ region_cnt, const uint32_t* __restrict__ tile_order) {
     extern __shared__ __align__(16) uint64_t s_keys[];
     __shared__ uint32_t s_wh[8][256];
     __shared__ uint32_t s_cnt[64];
-    const int tile = tile0 + blockIdx.x;
+    const int tile = tile0 + (tile_order ? (int)tile_order[blockIdx.x] : (int)blockIdx.x);
     const uint32_t b = ranges[2 * tile], e = ranges[2 * tile + 1];
     const int n = (int)(e - b);
     if (n <= 0) {
@@ -875,11 +945,11 @@ blend_forward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __res
                      uint32_t* __restrict__ region_masks, uint32_t* __restrict__ region_done,
                      const GeomRecord* __restrict__ geom,
                      float* __restrict__ out_color, float* __restrict__ out_depth,
-                     float* __restrict__ final_T, uint32_t* __restrict__ n_contrib) {
+                     float* __restrict__ final_T, uint32_t* __restrict__ n_contrib, const uint32_t* __restrict__ tile_order) {
     __shared__ ChunkSmem<FWD_GC> Ws[FWD_WARPS];
 
     constexpr int BPT = 8 / FWD_WARPS;                                  // blocks per tile
-    const int tile = cam.row0 * cam.gx + blockIdx.x / BPT;
+    const int tile = cam.row0 * cam.gx + (tile_order ? (int)tile_order[blockIdx.x / BPT] : (int)(blockIdx.x / BPT));
     const int tile_x = tile % cam.gx, tile_y = tile / cam.gx;
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = (blockIdx.x % BPT) * FWD_WARPS + (tid >> 5);       // region index inside the tile
@@ -1019,45 +1089,48 @@ int launch_forward(const VtgsCamera* camera, int64_t N, bool fused, const FrontE
     if (cam.gx > 0xffff || cam.gy > 0xffff) { set_error("image too large for packed tile rects"); return VTGS_E_INVALID; }
     if (N >= (int64_t)1 << 24) { set_error("at most 2^24 - 1 Gaussians per render (24-bit id in the sort key)"); return VTGS_E_UNSUPPORTED; }
     GeomRecord* geom = reinterpret_cast<GeomRecord*>(buf->geom);
-    VTGS_CUDA_CHECK(cudaMemsetAsync(buf->tile_counts, 0, sizeof(uint32_t) * num_tiles, stream));
+    VTGS_CUDA_CHECK(cudaMemsetAsync(buf->tile_counts, 0, sizeof(uint32_t) * (num_tiles + 1), stream));     // + the candidate-list counter
     const int blocks = (int)((N + 255) / 256);
     const int k1_blocks = blocks < 148 * 6 ? blocks : 148 * 6;          // persistent: 3 resident blocks per SM x 2 waves
     const bool band_active = cam.row0 > 0 || cam.row1 < cam.gy;
-    const uint8_t* flags = (fused && band_active && N > 0) ? buf->band_flags : nullptr;
+    // tile bands: candidate blocks (K0').  The list's counter is the word after the per-tile counts (zeroed with them).
+    const bool use_cand = fused && band_active && N > 0 && buf->band_flags != nullptr && buf->band_cand != nullptr;
+    const uint32_t* cand = use_cand ? buf->band_cand : nullptr;
+    uint32_t* n_cand = buf->tile_counts + num_tiles;
+    const int persistent = 148 * 3;
     if (N > 0) {
         const bool narrow_band = (cam.row1 - cam.row0) * 5 < cam.gy * 2;
-        if (flags) {
-            VtgsPose ps{};
-            ps.cam_unnorm_rot = fe.cam_unnorm_rot;
-            ps.cam_trans = fe.cam_trans;
-            if (int e = launch_pose_matrix(&ps, fe.counters, stream)) return e;
-            { VTGS_PROF("band_flags_kernel", stream); band_flags_kernel<<<blocks, 256, 0, stream>>>(cam, N, fe, means3D, scales, radii, buf->tiles_touched, buf->band_flags); }
+        if (use_cand) {
+            { VTGS_PROF("band_flags_kernel", stream); band_flags_kernel<<<(blocks + 3) / 4, 256, 0, stream>>>(cam, N, fe, means3D, scales, radii, buf->tiles_touched, buf->band_flags, buf->band_cand, n_cand); }
             VTGS_LAUNCH_CHECK();
         }
-        const int k1_grid = flags ? blocks : k1_blocks;
+        const int k1_grid = use_cand ? std::min(blocks, persistent) : k1_blocks;
         if (fused && narrow_band)
             { VTGS_PROF("preprocess_kernel", stream); preprocess_kernel<true, true><<<k1_grid, 256, 0, stream>>>(cam, N, fe, means3D, scales, rotations, opacities, colors,
-                                                                 geom, radii, buf->tiles_touched, buf->tile_counts, flags); }
+                                                                 geom, radii, buf->tiles_touched, buf->tile_counts, cand, n_cand); }
         else if (fused)
             { VTGS_PROF("preprocess_kernel", stream); preprocess_kernel<true><<<k1_grid, 256, 0, stream>>>(cam, N, fe, means3D, scales, rotations, opacities, colors,
-                                                                 geom, radii, buf->tiles_touched, buf->tile_counts, flags); }
+                                                                 geom, radii, buf->tiles_touched, buf->tile_counts, cand, n_cand); }
         else { VTGS_PROF("preprocess_kernel", stream); preprocess_kernel<false><<<k1_grid, 256, 0, stream>>>(cam, N, fe, means3D, scales, rotations, opacities, colors,
-                                                                  geom, radii, buf->tiles_touched, buf->tile_counts, nullptr); }
+                                                                  geom, radii, buf->tiles_touched, buf->tile_counts, nullptr, nullptr); }
         VTGS_LAUNCH_CHECK();
     }
     // only the band's tiles hold counts (tile-band sharding: K1' clips every rect to the band); the fused solvers never
     // look at another tile's range, so they scan the band alone -- API mode keeps (0,0) ranges for the other tiles
     const int band_tiles = (cam.row1 - cam.row0) * cam.gx;
     const int scan0 = fused ? cam.row0 * cam.gx : 0, scan_n = fused ? band_tiles : num_tiles;
-    { VTGS_PROF("tile_scan_kernel", stream); tile_scan_kernel<<<1, 1024, 0, stream>>>(buf->tile_counts + scan0, buf->tile_ranges + 2 * (size_t)scan0, scan_n, buf->pair_capacity, buf->counters); }
+    // the tile order is relative to the scanned range: usable when that is exactly what the sort / blend kernels cover
+    // (worth its ~4 us in the scan only when a launch is about one wave of blocks: tile bands)
+    uint32_t* order = (fused && band_active) ? buf->tile_order : nullptr;
+    { VTGS_PROF("tile_scan_kernel", stream); tile_scan_kernel<<<1, 1024, 0, stream>>>(buf->tile_counts + scan0, buf->tile_ranges + 2 * (size_t)scan0, scan_n, buf->pair_capacity, buf->counters, order); }
     VTGS_LAUNCH_CHECK();
     if (N > 0 && band_tiles > 0) {
-        { VTGS_PROF("scatter_kernel", stream); scatter_kernel<<<blocks, 256, 0, stream>>>(N, cam.gx, geom, buf->tiles_touched, buf->tile_ranges, buf->tile_counts, buf->pair_keys, flags); }
+        { VTGS_PROF("scatter_kernel", stream); scatter_kernel<<<use_cand ? std::min(blocks, 148 * 8) : blocks, 256, 0, stream>>>(N, cam.gx, geom, buf->tiles_touched, buf->tile_ranges, buf->tile_counts, buf->pair_keys, cand, n_cand); }
         VTGS_LAUNCH_CHECK();
         static std::atomic<uint64_t> sort_attr{0};
         if (first_call_on_device(sort_attr))
             VTGS_CUDA_CHECK(cudaFuncSetAttribute(tile_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_SMEM_ELEMS * 8));
-        { VTGS_PROF("tile_sort_kernel", stream); tile_sort_kernel<<<band_tiles, 256, SORT_SMEM_ELEMS * 8, stream>>>(cam, buf->tile_ranges, cam.row0 * cam.gx, buf->pair_keys, buf->point_list, geom, reinterpret_cast<uint2*>(buf->region_pairs), buf->region_cnt); }
+        { VTGS_PROF("tile_sort_kernel", stream); tile_sort_kernel<<<band_tiles, 256, SORT_SMEM_ELEMS * 8, stream>>>(cam, buf->tile_ranges, cam.row0 * cam.gx, buf->pair_keys, buf->point_list, geom, reinterpret_cast<uint2*>(buf->region_pairs), buf->region_cnt, order); }
         VTGS_LAUNCH_CHECK();
     }
     if (N <= 0) VTGS_CUDA_CHECK(cudaMemsetAsync(buf->region_cnt, 0, sizeof(uint32_t) * 8 * num_tiles, stream));
@@ -1068,8 +1141,8 @@ int launch_forward(const VtgsCamera* camera, int64_t N, bool fused, const FrontE
             VTGS_CUDA_CHECK(cudaFuncSetAttribute(blend_forward_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         }
         if (fused)
-            { VTGS_PROF("blend_forward_kernel", stream); blend_forward_kernel<true><<<band_tiles * (8 / FWD_WARPS), 32 * FWD_WARPS, 0, stream>>>(cam, buf->tile_ranges, reinterpret_cast<const uint2*>(buf->region_pairs), buf->region_cnt, buf->region_masks, buf->region_done, geom, out_color, out_depth, buf->final_T, buf->n_contrib); }
-        else { VTGS_PROF("blend_forward_kernel", stream); blend_forward_kernel<false><<<band_tiles * (8 / FWD_WARPS), 32 * FWD_WARPS, 0, stream>>>(cam, buf->tile_ranges, reinterpret_cast<const uint2*>(buf->region_pairs), buf->region_cnt, buf->region_masks, buf->region_done, geom, out_color, out_depth, buf->final_T, buf->n_contrib); }
+            { VTGS_PROF("blend_forward_kernel", stream); blend_forward_kernel<true><<<band_tiles * (8 / FWD_WARPS), 32 * FWD_WARPS, 0, stream>>>(cam, buf->tile_ranges, reinterpret_cast<const uint2*>(buf->region_pairs), buf->region_cnt, buf->region_masks, buf->region_done, geom, out_color, out_depth, buf->final_T, buf->n_contrib, order); }
+        else { VTGS_PROF("blend_forward_kernel", stream); blend_forward_kernel<false><<<band_tiles * (8 / FWD_WARPS), 32 * FWD_WARPS, 0, stream>>>(cam, buf->tile_ranges, reinterpret_cast<const uint2*>(buf->region_pairs), buf->region_cnt, buf->region_masks, buf->region_done, geom, out_color, out_depth, buf->final_T, buf->n_contrib, order); }
         VTGS_LAUNCH_CHECK();
     }
     if (band_tiles < num_tiles && !fused) {       // API mode returns complete planes; the fused solvers only ever read their band

@@ -113,6 +113,8 @@ class Workspace:
         self.region_cnt = torch.zeros(sz.region_cnt_bytes // 4, dtype=torch.int32, device=device)
         self.region_done = torch.zeros(sz.region_done_bytes // 4, dtype=torch.int32, device=device)
         self.band_flags = torch.zeros(max(int(sz.band_flags_bytes), 1), dtype=torch.uint8, device=device)
+        self.band_cand = torch.zeros(max(int(sz.band_cand_bytes) // 4, 1), dtype=torch.int32, device=device)
+        self.tile_order = torch.zeros(max(int(sz.tile_order_bytes) // 4, 1), dtype=torch.int32, device=device)
         self.region_pairs = self.region_masks = None
         self._num_tiles = sz.tiles_x * sz.tiles_y
         self.pair_capacity = 0
@@ -151,6 +153,8 @@ class Workspace:
         b.region_done = self.region_done.data_ptr()
         b.pair_capacity = self.pair_capacity
         b.band_flags = self.band_flags.data_ptr()
+        b.band_cand = self.band_cand.data_ptr()
+        b.tile_order = self.tile_order.data_ptr()
         return b
 
     def read_counters(self):
