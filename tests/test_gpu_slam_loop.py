@@ -71,3 +71,32 @@ def test_loop_tracks_against_two_consecutive_sections():
     # two overlapping sections are displaced against each other by the pose error of the newer one's base frame, so the
     # optimum is a compromise: tracking still follows the camera, but less tightly than against the newest section alone
     assert err < 0.6 * still, (err, still)
+
+
+def test_silhouette_driven_addition_fills_uncovered_pixels():
+    """add_missing_gaussians (reference add_new_gaussians_base_frame, src/vtgaussian_slam.py:732-813): the camera has moved
+    so that part of the view is not covered by the section; the non-presence mask finds those pixels, one Gaussian per
+    masked valid-depth pixel is appended to the newest section, and a re-render is covered."""
+    W, H, K = synthetic.intrinsics("tum_fr1", 320, 240)
+    poses = synthetic.trajectory(2, step_m=0.25, step_deg=8.0, seed=7)       # a large step: a strip of new content
+    f0 = synthetic.make_frame("tum_fr1", 320, 240, seed=0, c2w=poses[0])
+    f1 = synthetic.make_frame("tum_fr1", 320, 240, seed=1, c2w=poses[1])
+    slam = ViewTiedSLAM(W, H, K, LoopConfig(track_iters=5, map_iters=2, baseframe_every=100), device=DEV)
+    slam.process(f0)
+    slam.w2c.append(np.linalg.inv(poses[1]))                                  # ground-truth pose of frame 1
+    rgb = torch.as_tensor(f1["im"]).to(DEV)
+    depth = torch.as_tensor(f1["depth"]).to(DEV).reshape(1, H, W)
+    n0 = slam.store.num_gaussians
+    tr = slam.tracker
+    from vtgaussian_slam_b200.slam_loop import quat_from_matrix
+    q = torch.as_tensor(quat_from_matrix(slam.w2c[1][:3, :3]), dtype=torch.float32, device=DEV)
+    t = torch.as_tensor(slam.w2c[1][:3, 3], dtype=torch.float32, device=DEV)
+    img, _ = tr.r.forward(tr.params, q, t)
+    holes_before = int((img[4] < 0.5).sum().item())
+    assert holes_before > 500
+    added = slam.add_missing_gaussians(1, rgb, depth)
+    assert added >= holes_before * 0.9 and slam.store.num_gaussians == n0 + added and len(slam.store) == 1
+    tr = slam.tracker                                                          # rebuilt over the grown section
+    assert tr.params["means3D"].shape[0] == n0 + added
+    img, _ = tr.r.forward(tr.params, q, t)
+    assert int((img[4] < 0.5).sum().item()) < 0.05 * holes_before

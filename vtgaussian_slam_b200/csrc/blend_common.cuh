@@ -143,7 +143,8 @@ struct ChunkSmem {
     float4 r0[GC * 32];      // {px, py, A, B}
     float4 r1[GC * 32];      // {C, opacity, c0, c1}
     float2 r2[GC * 32];      // {c2, c3}
-    uint32_t pm[GC][32];     // [group][pixel lane]: candidate mask from P1; after P2 the mask of APPLIED splats
+    uint32_t pm[GC + 1][32]; // [group][pixel lane]: candidate mask from P1; after P2 the mask of APPLIED splats.
+                             // The row after the chunk's last group holds a non-zero sentinel (ends the word search)
 };
 
 // P1 by rows, lane = splat: a conservative SUPERSET of the region's pixels whose spec'd `power` can be >= pthr.

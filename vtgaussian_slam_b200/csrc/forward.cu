@@ -999,6 +999,7 @@ blend_forward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __res
             const uint32_t m = warp_transpose_bits(em, lane);
             S.pm[gg][lane] = done ? 0u : m;
         }
+        S.pm[gc][lane] = 0xffffffffu;                   // sentinel: the search for a lane's next non-empty word stops here
         __syncwarp();
         // ---- P2, lane = pixel: one pass over the chunk's masks, no re-convergence between groups.  The mask corrections
         // (P1's superset / the T test rejecting a splat) are cold and kept out of line.
@@ -1006,8 +1007,8 @@ blend_forward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __res
             int gg = 0, lk = -1;
             uint32_t m = S.pm[0][lane];
             for (;;) {
-                while (m == 0u && ++gg < gc) m = S.pm[gg][lane];
-                if (m == 0u) break;
+                while (m == 0u) m = S.pm[++gg][lane];      // (the sentinel row bounds it)
+                if (gg >= gc) break;
                 const uint32_t bit = m & (0u - m);
                 m ^= bit;
                 const int idx = gg * 32 + msb_index(bit);
