@@ -94,13 +94,15 @@ blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __re
                       const uint32_t* __restrict__ tile_order) {
     constexpr int NCH = FUSED ? 4 : 3;
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    // Every table a lane indexes with ITS OWN splat or pixel number is a plain float[32]: 32 entries over 32 banks, so
+    // a gather is conflict-free whatever the indices (equal indices broadcast) -- 16-byte records would collide whenever
+    // two lanes of a quarter-warp pick entries that are 8 apart.
     struct WarpArea {
-        GroupSmem G;
+        float rec[10][32];          // splats of the group: px, py, opacity, A, B, C, c0, c1, c2, c3
         float2 cell[32][32];        // [splat of the group][pixel]: (w, g0).  Unpadded: a pixel lane always stores to its own
                                     // column (bank pair = lane mod 16, conflict-free whatever the splats); the splat lanes'
                                     // loads hit the bank pair of the pixel they are at, as with any padding
-        float4 dpix[32];            // dL/dpixel of the region's pixels (r,g,b,z); LITE: {pixel centre x, y, dL/dz, 0}
-        float2 pxy[32];             // pixel centres of the region
+        float pix[6][32];           // pixels of the region: centre x, y, dL/d(r, g, b, z)
     };
     WarpArea* areas = reinterpret_cast<WarpArea*>(smem_raw);
 
@@ -110,7 +112,6 @@ blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __re
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = (blockIdx.x % BPT) * BWD_WARPS + (tid >> 5);       // region index inside the tile
     WarpArea& A = areas[tid >> 5];
-    GroupSmem& G = A.G;
     const int rx0 = tile_x * 16 + (warp % REGIONS_X) * REGION_W, ry0 = tile_y * 16 + (warp / REGIONS_X) * REGION_H;
     const int pix_x = rx0 + (lane % REGION_W), pix_y = ry0 + (lane / REGION_W);
     const bool inside = pix_x < cam.W && pix_y < cam.H;
@@ -128,8 +129,9 @@ blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __re
     float dpix[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int ch = 0; ch < NCH; ++ch) dpix[ch] = inside ? dL_dpix[ch * P + pid] : 0.0f;
-    A.dpix[lane] = LITE ? make_float4(pxf, pyf, dpix[3], 0.0f) : make_float4(dpix[0], dpix[1], dpix[2], dpix[3]);
-    A.pxy[lane] = make_float2(pxf, pyf);
+    A.pix[0][lane] = pxf; A.pix[1][lane] = pyf;
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) A.pix[2 + ch][lane] = dpix[ch];
     const float bg_dot = BG ? cam.bg[0] * dpix[0] + cam.bg[1] * dpix[1] + cam.bg[2] * dpix[2] : 0.0f;
     const float half_w = 0.5f * cam.W, half_h = 0.5f * cam.H;
 
@@ -170,19 +172,21 @@ blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __re
         if (!cur_live) continue;
         const bool have = g * 32 + lane < n;
         __syncwarp();                                   // previous group's P3 reads are complete
-        if (have) { G.a[lane] = cur.a; G.b[lane] = cur.b; G.c[lane] = cur.c; }
+        if (have) {
+            A.rec[0][lane] = cur.a.x; A.rec[1][lane] = cur.a.y; A.rec[2][lane] = cur.a.w;
+            A.rec[3][lane] = cur.b.x; A.rec[4][lane] = cur.b.y; A.rec[5][lane] = cur.b.z;
+            A.rec[6][lane] = cur.c.x; A.rec[7][lane] = cur.c.y; A.rec[8][lane] = cur.c.z; A.rec[9][lane] = cur.c.w;
+        }
         __syncwarp();
         const uint32_t emask = warp_transpose_bits(m, lane);      // lane = splat: the pixels that blended it
         // ---- P2: lane = pixel; descending bits = descending list position.  Two splats per trip: loads /
         // power / exp are independent, the T / accum recursion is ordered.
-        auto back_one = [&](const float4 q0, const float Gv, const int e) -> float2 {
-            const float alpha = fminf(VTGS_ALPHA_MAX, q0.w * Gv);
-            const float4 q2 = G.c[e];
-            const float col[4] = {q2.x, q2.y, q2.z, q2.w};
+        auto back_one = [&](const float op, const float Gv, const int e) -> float2 {
+            const float alpha = fminf(VTGS_ALPHA_MAX, op * Gv);
             const float inv = rcp_approx(1.0f - alpha);             // 1 - alpha in [0.01, 1]
             T = T * inv;
-            float cdot = col[0] * dpix[0] + col[1] * dpix[1] + col[2] * dpix[2];
-            if (NCH == 4) cdot += col[3] * dpix[3];
+            float cdot = A.rec[6][e] * dpix[0] + A.rec[7][e] * dpix[1] + A.rec[8][e] * dpix[2];
+            if (NCH == 4) cdot += A.rec[9][e] * dpix[3];
             acc_dot = last_alpha * last_dot + (1.0f - last_alpha) * acc_dot;
             last_dot = cdot;
             float dL_dalpha = (cdot - acc_dot) * T;
@@ -196,16 +200,14 @@ blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __re
             const bool two = m != 0;
             const int eb = two ? msb_index(m) : ea;
             m &= ~(1u << eb);
-            const float4 a0 = G.a[ea], a1 = G.b[ea];
-            const float4 b0 = G.a[eb], b1 = G.b[eb];
             // no decision depends on G any more (the forward's masks fix which splats were blended), so the
             // backward may use the hardware exp2 and free contraction: gradients are judged to 1e-3 relative
-            const float dxa = a0.x - pxf, dya = a0.y - pyf, dxb = b0.x - pxf, dyb = b0.y - pyf;
+            const float dxa = A.rec[0][ea] - pxf, dya = A.rec[1][ea] - pyf, dxb = A.rec[0][eb] - pxf, dyb = A.rec[1][eb] - pyf;
             // (power is in [pthr, 0], |pthr| a few units: the forward blended these pairs)
-            const float Ga = ex2_approx(1.44269504f * (-0.5f * (a1.x * dxa * dxa + a1.z * dya * dya) - a1.y * dxa * dya));
-            const float Gb = ex2_approx(1.44269504f * (-0.5f * (b1.x * dxb * dxb + b1.z * dyb * dyb) - b1.y * dxb * dyb));
-            A.cell[ea][lane] = back_one(a0, Ga, ea);
-            if (two) A.cell[eb][lane] = back_one(b0, Gb, eb);
+            const float Ga = ex2_approx(1.44269504f * (-0.5f * (A.rec[3][ea] * dxa * dxa + A.rec[5][ea] * dya * dya) - A.rec[4][ea] * dxa * dya));
+            const float Gb = ex2_approx(1.44269504f * (-0.5f * (A.rec[3][eb] * dxb * dxb + A.rec[5][eb] * dyb * dyb) - A.rec[4][eb] * dxb * dyb));
+            A.cell[ea][lane] = back_one(A.rec[2][ea], Ga, ea);
+            if (two) A.cell[eb][lane] = back_one(A.rec[2][eb], Gb, eb);
         }
         __syncwarp();
         // ---- P3: lane = splat: reduce my row of cells
@@ -216,12 +218,9 @@ blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __re
             const int p = __ffs(pm) - 1;
             pm &= pm - 1;
             const float2 cw = A.cell[lane][p];
-            const float4 dp = A.dpix[p];
-            float2 pc;
-            if (LITE) pc = make_float2(dp.x, dp.y); else pc = A.pxy[p];
-            const float dx = cur.a.x - pc.x, dy = cur.a.y - pc.y;
-            if (!LITE) { c0 = fmaf(cw.x, dp.x, c0); c1 = fmaf(cw.x, dp.y, c1); c2 = fmaf(cw.x, dp.z, c2); }
-            if (NCH == 4) c3 = fmaf(cw.x, LITE ? dp.z : dp.w, c3);
+            const float dx = cur.a.x - A.pix[0][p], dy = cur.a.y - A.pix[1][p];
+            if (!LITE) { c0 = fmaf(cw.x, A.pix[2][p], c0); c1 = fmaf(cw.x, A.pix[3][p], c1); c2 = fmaf(cw.x, A.pix[4][p], c2); }
+            if (NCH == 4) c3 = fmaf(cw.x, A.pix[5][p], c3);
             const float gg = cw.y, gx_ = gg * dx, gy_ = gg * dy;
             if (!LITE) s0 += gg;
             sx += gx_; sy += gy_;
@@ -387,8 +386,8 @@ preprocess_backward_kernel(const __grid_constant__ CamConst cam, int64_t N,
 }
 
 // dynamic shared memory of blend_backward_kernel
-// per warp: group 1536 + cells 8192 + dpix 512 + pxy 256 bytes
-constexpr int BWD_SMEM = BWD_WARPS * (int)(sizeof(GroupSmem) + 32 * 32 * sizeof(float2) + 32 * sizeof(float4) + 32 * sizeof(float2));
+// per warp: splat table 1280 + cells 8192 + pixel table 768 bytes
+constexpr int BWD_SMEM = BWD_WARPS * (int)(10 * 32 * sizeof(float) + 32 * 32 * sizeof(float2) + 6 * 32 * sizeof(float));
 template <bool FUSED, bool BG, bool LITE>
 static int launch_blend_backward(int blocks, cudaStream_t stream, const CamConst& cam, const VtgsBuffers* buf, const GeomRecord* geom,
                                  const float* dL_dpix, const uint32_t* order) {

@@ -938,8 +938,11 @@ __device__ __noinline__ void truncate_masks(uint32_t* col, int gg, int gc, uint3
 #endif
 constexpr int FWD_WARPS = VTGS_FWD_WARPS;   // warps (regions) per block: a tile is covered by 8 / FWD_WARPS blocks
 constexpr int FWD_GC = VTGS_FWD_GC;         // groups per chunk: 1408 B of shared memory per group and warp
+#ifndef VTGS_FWD_BLOCKS
+#define VTGS_FWD_BLOCKS ((FWD_GC <= 6 ? 24 : 20) / FWD_WARPS)
+#endif
 template <bool FUSED>
-__global__ void __launch_bounds__(32 * FWD_WARPS, (FWD_GC <= 6 ? 24 : 20) / FWD_WARPS)
+__global__ void __launch_bounds__(32 * FWD_WARPS, VTGS_FWD_BLOCKS)
 blend_forward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __restrict__ ranges,
                      const uint2* __restrict__ region_pairs, const uint32_t* __restrict__ region_cnt,
                      uint32_t* __restrict__ region_masks, uint32_t* __restrict__ region_done,
