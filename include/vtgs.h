@@ -42,7 +42,7 @@ extern "C" {
 #define VTGS_API
 #endif
 
-#define VTGS_ABI_VERSION 2
+#define VTGS_ABI_VERSION 3
 
 /* ---- named constants of the splatting arithmetic ---------- */
 #define VTGS_TILE            16          /* BLOCK_X = BLOCK_Y                          */
@@ -401,6 +401,38 @@ VTGS_API int vtgs_retie_dev(float* means3D, int64_t n, const float* old_unnorm_r
 VTGS_API int vtgs_tracking_update(float* cam_unnorm_rot, float* cam_trans, const float* msg, float* adam_state,
                                   int32_t* step_dev, float* best, float lr_rot, float lr_trans, float eps, int32_t flags,
                                   void* stream);
+
+/*
+ * Per-frame evaluation metrics of the reference's `eval` (utils/eval_helpers.py:431-477) on a fused six-plane render:
+ * valid = gt_depth > 0, presence = silhouette > sil_thres; the images are weighted by valid (and by presence when
+ * use_presence != 0: the reference's `mapping_iters == 0 and not add_new_gaussians` configuration).
+ *   out8 (device) = {sum sq err r, g, b, sum |depth - gt| (masked), valid count, PSNR (mean over channels of
+ *                    20 log10(1 / sqrt(mse_c)), mse over ALL pixels as calc_psnr does), depth L1, depth "RMSE" (the
+ *                    reference takes sqrt(x^2) per pixel, i.e. the same number as the L1)}
+ *   scratch: vtgs_eval_scratch_floats() floats.  One launch, fixed-order reduction.
+ */
+VTGS_API uint64_t vtgs_eval_scratch_floats(void);
+VTGS_API int vtgs_eval_metrics(const VtgsCamera* cam, const float* image6, const float* gt_rgb, const float* gt_depth,
+                               float sil_thres, int32_t use_presence, float* out8, float* scratch, void* stream);
+
+/*
+ * Device point-to-plane metric: the reference's compute_point2plane_dist (src/vtgaussian_slam.py:1070-1155, called
+ * inside the tracking loop at :1929 / :1956) without its CPU round trips (kornia normals -> numpy -> Open3D KD-tree).
+ * vtgs_p2p_prepare: one frame's depth[H,W] (device) -> world points pts[H*W,3] (get_pointcloud, factor 1), optional
+ *   world normals nrm[H*W,3] (kornia depth_to_normals, rotated as trans_normal_c2w does; NULL to skip) and
+ *   valid[H*W] = depth > 0 [& mask] [& inside the other frame's view: get_frustum_mask when other_w2c12 != NULL].
+ *   intr4 = {fx, fy, cx, cy}, c2w12 / other_w2c12 = rows of 3x4 matrices; all three on the HOST.
+ * vtgs_p2p_match: for every valid source point the nearest valid target point within max_dist (Open3D
+ *   evaluate_registration's correspondence set, threshold 0.02 in the reference) through a uniform hash grid
+ *   (table: table_size int32, a power of two; next: n_tgt int32; both device scratch);
+ *   out_dist[n_src] = n_target . (p_source - p_target), NaN where there is no correspondence; out_idx (optional) the
+ *   target index or -1.  The caller reduces out_dist (sum of squares / max / top-100 mean: `p2p_method`).
+ */
+VTGS_API int vtgs_p2p_prepare(int32_t W, int32_t H, const float* intr4, const float* c2w12, const float* other_w2c12,
+                              const float* depth, const uint8_t* mask, float* pts, float* nrm, uint8_t* valid, void* stream);
+VTGS_API int vtgs_p2p_match(int64_t n_tgt, const float* tgt_pts, const float* tgt_nrm, const uint8_t* tgt_valid,
+                            int64_t n_src, const float* src_pts, const uint8_t* src_valid, float max_dist,
+                            int32_t* table, int64_t table_size, int32_t* next, float* out_dist, int32_t* out_idx, void* stream);
 
 /* FP32 FMA throughput probe (bench.py's measured FP32 peak): every thread of a full grid runs `iters` dependent-free
  * FFMA octets; FLOP = 2 * 8 * iters * threads, threads = *threads_out.  sink: one device float (keeps the work alive). */

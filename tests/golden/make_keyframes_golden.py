@@ -114,10 +114,50 @@ def visbased_goldens():
     return out
 
 
+def topkbase_goldens():
+    """keyframe_selection_overlap_visbased_earliest_dynamic_new_topkbase (utils/keyframe_selection.py:581-703), the
+    section choice of the main loop (src/vtgaussian_slam.py:1549-1553), on a 24-keyframe orbit: several thresholds,
+    topk_base 3 / 2 / None, a short list and a list nothing overlaps with."""
+    import contextlib
+    import io
+    from utils.keyframe_selection import keyframe_selection_overlap_visbased_earliest_dynamic_new_topkbase as ref_fn
+    from vtgaussian_slam_b200 import synthetic
+    out = {}
+    W, H, K = synthetic.intrinsics("tum_fr1", 80, 60)
+    poses = synthetic.trajectory(25, step_m=0.10, step_deg=5.0, seed=21)
+    cur = synthetic.make_frame("tum_fr1", 80, 60, seed=0, c2w=poses[24])
+    gt_depth = torch.tensor(cur["depth"])
+    gt_depth[0, :8, 60:] = 0.0
+    intr = torch.tensor(K.astype(np.float32))
+    w2c = torch.tensor(np.linalg.inv(poses[24]), dtype=torch.float32)
+    depths = [synthetic.make_frame("tum_fr1", 80, 60, seed=50 + i, c2w=poses[i])["depth"] for i in range(24)]
+    mk = lambda n: [dict(est_w2c=torch.tensor(np.linalg.inv(poses[i]), dtype=torch.float32), depth=torch.tensor(depths[i])) for i in range(n)]
+    cfg = dict(baseframe_every=8, overlap_every=2)
+    cases = [dict(n=24, earliest_thres=0.5, topk_base=3), dict(n=24, earliest_thres=0.9, topk_base=3),
+             dict(n=24, earliest_thres=0.3, topk_base=2), dict(n=24, earliest_thres=0.5, topk_base=None),
+             dict(n=6, earliest_thres=0.5, topk_base=3), dict(n=24, earliest_thres=0.999, topk_base=3, lower=0.5),
+             dict(n=4, earliest_thres=0.5, topk_base=3, far=True)]
+    out["tk.depth"], out["tk.K"], out["tk.poses"], out["tk.kf_depths"] = gt_depth.numpy(), intr.numpy(), poses, np.stack(depths)
+    for j, c in enumerate(cases):
+        kfs = mk(c["n"])
+        if c.get("far"):                                   # keyframes that look away: nothing overlaps
+            for kf in kfs:
+                kf["est_w2c"] = torch.tensor(np.diag([-1.0, 1.0, -1.0, 1.0]), dtype=torch.float32) @ kf["est_w2c"]
+        with contextlib.redirect_stdout(io.StringIO()):
+            got = ref_fn(gt_depth, w2c, intr, kfs, 3, cfg, edge_value=6, kf_depth_thresh=0.02, earliest_thres=c["earliest_thres"],
+                         lower_earliest_thres_percent=c.get("lower", 0.8), topk_base=c["topk_base"])
+        out[f"tk.case{j}"] = np.array(sorted(got))
+        out[f"tk.cfg{j}"] = np.array([c["n"], c["earliest_thres"], -1 if c["topk_base"] is None else c["topk_base"], c.get("lower", 0.8), float(bool(c.get("far")))])
+    out["tk.ncases"] = np.array(len(cases))
+    return out
+
+
 if __name__ == "__main__":
     g = dict(np.load(os.path.join(HERE, "keyframes_golden.npz")))
     g.update(vis_mask_goldens())
     g.update(visbased_goldens())
+    g.update(topkbase_goldens())
+    print({k: v.tolist() for k, v in g.items() if k.startswith("tk.case")})
     print({k: v for k, v in g.items() if k in ("vb.sel", "vb.early", "vb.early2", "vb.ranked_frac")})
     np.savez_compressed(os.path.join(HERE, "keyframes_golden.npz"), **g)
     print({k: float(v.mean()) for k, v in g.items() if k.startswith("vis.mask")})

@@ -86,3 +86,21 @@ def test_visibility_based_selection_matches_the_reference():
     a = keyframes.overlap_fractions_visible(pts, K, stack, deps, 80, 60, 6, 0.02, chunk=2)
     b = keyframes.overlap_fractions_visible(pts, K, stack, deps, 80, 60, 6, 0.02, chunk=64)
     assert torch.equal(a, b)
+
+
+def test_section_choice_of_the_main_loop_matches_the_reference():
+    """keyframe_selection_overlap_visbased_earliest_dynamic_new_topkbase: dynamic threshold + earliest top-k sections."""
+    depth, K, poses = torch.tensor(G["tk.depth"]), torch.tensor(G["tk.K"]), G["tk.poses"]
+    w2c = torch.tensor(np.linalg.inv(poses[24]), dtype=torch.float32)
+    cfg = dict(baseframe_every=8, overlap_every=2)
+    for j in range(int(G["tk.ncases"])):
+        n, thres, topk, lower, far = G[f"tk.cfg{j}"]
+        kfs = [dict(est_w2c=torch.tensor(np.linalg.inv(poses[i]), dtype=torch.float32), depth=torch.tensor(G["tk.kf_depths"][i])) for i in range(int(n))]
+        if far:
+            for kf in kfs:
+                kf["est_w2c"] = torch.tensor(np.diag([-1.0, 1.0, -1.0, 1.0]), dtype=torch.float32) @ kf["est_w2c"]
+        got = keyframes.keyframe_selection_overlap_visbased_earliest_dynamic_new_topkbase(
+            depth, w2c, K, kfs, 3, cfg, edge_value=6, kf_depth_thresh=0.02, earliest_thres=float(thres),
+            lower_earliest_thres_percent=float(lower), topk_base=None if topk < 0 else int(topk))
+        assert got == list(G[f"tk.case{j}"]), (j, got, G[f"tk.case{j}"])
+    assert sorted(keyframes.quantize_selected_time_idx([0, 1, 5, 9, 9, 11], 4)) == [0, 1, 2]

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("VTGS_LIB_PATH") or os.path.join(_HERE, "lib", "libvtgs_cuda.so")
 CSRC = os.path.join(_HERE, "csrc")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MEDIAN_STATE_WORDS = 264
 MEDIAN_SUMMABLE_WORDS = 257
 TRACK_BOOK_POST_STEP = 1
@@ -112,6 +112,10 @@ SYMBOLS = {
     "vtgs_sil_ladder": (C.c_int, [C.POINTER(VtgsCamera), _P, _P, _P, _P, _P, _P]),
     "vtgs_sil_select": (C.c_int, [_P, _P, _P, _P]),
     "vtgs_nonpresence_mask": (C.c_int, [C.POINTER(VtgsCamera), _P, _P, C.c_float, _P, _P, _P, _P]),
+    "vtgs_eval_scratch_floats": (C.c_uint64, []),
+    "vtgs_eval_metrics": (C.c_int, [C.POINTER(VtgsCamera), _P, _P, _P, C.c_float, C.c_int32, _P, _P, _P]),
+    "vtgs_p2p_prepare": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_float * 4), C.POINTER(C.c_float * 12), _P, _P, _P, _P, _P, _P, _P]),
+    "vtgs_p2p_match": (C.c_int, [C.c_int64, _P, _P, _P, C.c_int64, _P, _P, C.c_float, _P, C.c_int64, _P, _P, _P, _P]),
     "vtgs_ffma_probe": (C.c_int, [C.c_int64, _P, C.POINTER(C.c_uint64), _P]),
     "vtgs_profile_enable": (C.c_int, [C.c_int32]),
     "vtgs_profile_summary": (C.c_int, [C.c_char_p, C.c_uint64]),

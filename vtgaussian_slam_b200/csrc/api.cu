@@ -267,6 +267,34 @@ int vtgs_nonpresence_mask(const VtgsCamera* cam, const float* image6, const floa
     return launch_nonpresence_mask(cam, image6, gt_depth, sil_thres, median_state, mask_out, count_dev, (cudaStream_t)stream);
 }
 
+uint64_t vtgs_eval_scratch_floats(void) { return eval_scratch_floats(); }
+
+int vtgs_eval_metrics(const VtgsCamera* cam, const float* image6, const float* gt_rgb, const float* gt_depth, float sil_thres,
+                      int32_t use_presence, float* out8, float* scratch, void* stream) {
+    if (int e = check_cam(cam)) return e;
+    VTGS_REQUIRE(image6 && gt_rgb && gt_depth && out8 && scratch, "pointer is NULL");
+    return launch_eval_metrics(cam, image6, gt_rgb, gt_depth, sil_thres, use_presence, out8, scratch, (cudaStream_t)stream);
+}
+
+int vtgs_p2p_prepare(int32_t W, int32_t H, const float* intr4, const float* c2w12, const float* other_w2c12, const float* depth,
+                     const uint8_t* mask, float* pts, float* nrm, uint8_t* valid, void* stream) {
+    VTGS_REQUIRE(W > 0 && H > 0 && (int64_t)W * H < (int64_t)1 << 31, "bad image size");
+    VTGS_REQUIRE(intr4 && c2w12 && depth && pts && valid, "pointer is NULL");
+    return launch_p2p_prepare(W, H, intr4, c2w12, other_w2c12, depth, mask, pts, nrm, valid, (cudaStream_t)stream);
+}
+
+int vtgs_p2p_match(int64_t n_tgt, const float* tgt_pts, const float* tgt_nrm, const uint8_t* tgt_valid, int64_t n_src,
+                   const float* src_pts, const uint8_t* src_valid, float max_dist, int32_t* table, int64_t table_size,
+                   int32_t* next, float* out_dist, int32_t* out_idx, void* stream) {
+    VTGS_REQUIRE(n_tgt >= 0 && n_src >= 0 && n_tgt < (int64_t)1 << 31, "bad point count");
+    VTGS_REQUIRE(max_dist > 0.0f, "max_dist must be positive");
+    VTGS_REQUIRE(table && table_size > 0 && (table_size & (table_size - 1)) == 0 && table_size <= (int64_t)1 << 31, "table_size must be a power of two");
+    if (n_tgt > 0) VTGS_REQUIRE(tgt_pts && tgt_nrm && tgt_valid && next, "pointer is NULL");
+    if (n_src > 0) VTGS_REQUIRE(src_pts && src_valid && out_dist, "pointer is NULL");
+    return launch_p2p_match(n_tgt, tgt_pts, tgt_nrm, tgt_valid, n_src, src_pts, src_valid, max_dist, table, table_size, next, out_dist,
+                            out_idx, (cudaStream_t)stream);
+}
+
 int vtgs_ffma_probe(int64_t iters, float* sink, uint64_t* threads_out, void* stream) {
     VTGS_REQUIRE(iters > 0 && sink != nullptr, "bad argument");
     return launch_ffma_probe(iters, sink, threads_out, (cudaStream_t)stream);

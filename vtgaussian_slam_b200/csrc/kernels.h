@@ -59,6 +59,14 @@ int launch_sil_ladder(const VtgsCamera* cam, const float* image6, const float* g
 int launch_sil_select(const float* sums10, float* sil_thres_dev, float* min_mse_dev, cudaStream_t stream);
 int launch_nonpresence_mask(const VtgsCamera* cam, const float* image6, const float* gt_depth, float sil_thres,
                             const uint32_t* median_state, uint8_t* mask_out, uint32_t* count_dev, cudaStream_t stream);
+int launch_eval_metrics(const VtgsCamera* cam, const float* image6, const float* gt_rgb, const float* gt_depth, float sil_thres,
+                        int use_presence, float* out8, float* scratch, cudaStream_t stream);
+uint64_t eval_scratch_floats();
+int launch_p2p_prepare(int W, int H, const float* intr4, const float* c2w12, const float* other_w2c12, const float* depth,
+                       const uint8_t* mask, float* pts, float* nrm, uint8_t* valid, cudaStream_t stream);
+int launch_p2p_match(int64_t n_tgt, const float* tgt_pts, const float* tgt_nrm, const uint8_t* tgt_valid, int64_t n_src,
+                     const float* src_pts, const uint8_t* src_valid, float max_dist, int32_t* table, int64_t table_size,
+                     int32_t* next, float* out_dist, int32_t* out_idx, cudaStream_t stream);
 int launch_ffma_probe(int64_t iters, float* sink, uint64_t* threads_out, cudaStream_t stream);
 int launch_retie(float* means3D, int64_t n, const float* w2c_old_rowmajor12, const float* q_un, const float* t, cudaStream_t stream);
 int launch_retie_dev(float* means3D, int64_t n, const float* q_old, const float* t_old, const float* q_un, const float* t, cudaStream_t stream);

@@ -147,3 +147,101 @@ def keyframe_selection_overlap_visbased(gt_depth, w2c, intrinsics, keyframe_list
     selected = [r["id"] for r in ranked if r["percent_inside"] > 0.0][:k]
     earliest = [r["id"] for r in ranked if r["percent_inside"] > earliest_thres][-1:]
     return selected, (earliest if earliest else selected)
+
+
+# ---- section ("base frame") choice of the main loop (reference utils/keyframe_selection.py:568-703, called at
+# src/vtgaussian_slam.py:1549-1553 to pick the sections a new frame is tracked against) ---------------------------------
+def quantize_selected_time_idx(selected_time_idx, num_frames_each_base_frame):
+    """Keyframe ids -> ids of the sections they belong to, without duplicates (reference :568-577; it returns the set's
+    iteration order, every caller sorts it)."""
+    return list({int(i / num_frames_each_base_frame) for i in selected_time_idx})
+
+
+def keyframe_selection_overlap_visbased_earliest_dynamic_new_topkbase(gt_depth, w2c, intrinsics, keyframe_list, k, config, pixels=1600,
+                                                                      edge_value=20, kf_depth_thresh=0.01, earliest_thres=0.5,
+                                                                      lower_earliest_thres_percent=0.8, topk_base=3):
+    """Signature and results of the reference's function of the same name: the visibility-based overlap of every keyframe
+    with the current frame (all valid-depth pixels; `k` and `pixels` are ignored, as upstream), a threshold that starts at
+    `earliest_thres` and is lowered by `lower_earliest_thres_percent` until at least three sections hold a keyframe above
+    it (or the list is short, or the threshold falls under 1 %), and then the EARLIEST `topk_base` such sections (the
+    earliest one alone when topk_base is None).  config needs 'baseframe_every' and 'overlap_every'."""
+    width, height = gt_depth.shape[2], gt_depth.shape[1]
+    valid = torch.stack(torch.where(gt_depth[0] > 0), dim=1)
+    pts = backproject_samples(gt_depth, intrinsics, w2c, valid)
+    stack = torch.stack([kf["est_w2c"].to(pts.device) for kf in keyframe_list])
+    depths = torch.stack([kf["depth"].reshape(1, height, width) for kf in keyframe_list])
+    frac = overlap_fractions_visible(pts, intrinsics[:3, :3].to(pts.device), stack, depths, width, height, edge_value, kf_depth_thresh).tolist()
+    per_section = int(config["baseframe_every"] / config["overlap_every"])
+    thres, first = earliest_thres, True
+    while True:
+        thres = thres if first else lower_earliest_thres_percent * thres
+        first = False
+        above = [i for i, f in enumerate(frac) if f > thres]
+        sections = sorted(quantize_selected_time_idx(above, per_section))
+        if len(sections) >= 3 or (len(frac) <= 3 * per_section and len(sections) > 0) or thres < 0.01:
+            break
+    if not above:
+        above = [len(frac) - 1]                          # nothing overlaps: the latest keyframe
+    above = sorted(above)
+    if topk_base is None:
+        return sorted(quantize_selected_time_idx(above[:1], per_section))
+    sections = sorted(quantize_selected_time_idx(above, per_section))
+    return sections[:min(topk_base, len(sections))]
+
+
+# ---- point-to-plane metric on the device (reference compute_point2plane_dist, src/vtgaussian_slam.py:1070-1155) --------
+def _rows12(m):
+    import ctypes as C
+    a = torch.as_tensor(m).detach().to(torch.float64).cpu().reshape(4, 4)[:3].reshape(-1).tolist()
+    return (C.c_float * 12)(*a)
+
+
+def point2plane_dist(latest_depth, curr_depth, intrinsics, latest_w2c, curr_w2c, frustum=True, latest_varmask=None,
+                     curr_varmask=None, method="sum", threshold=0.02, return_pairs=False):
+    """The reference's `choose_metric` of a base frame's tracking iterations: the current frame's points (curr_depth at
+    curr_w2c) are paired with their nearest neighbours within `threshold` among the latest (overlapping) frame's points
+    (latest_depth at latest_w2c), both restricted to the other view's frustum, and the point-to-plane distances along the
+    latest frame's depth normals are reduced ('sum' of squares, 'max', or the mean of the 100 largest: `p2p_method`).
+    Everything runs in three kernels of libvtgs_cuda.so on the depth maps' device (CUDA only); the reference goes through
+    kornia, numpy and an Open3D KD-tree on the CPU.  depth maps: [1,H,W] or [H,W] float32; -> 0-dim tensor."""
+    import ctypes as C
+    from . import _lib
+    from .rasterizer import _ptr, _require_cuda, _stream_ptr
+    d0 = latest_depth.reshape(latest_depth.shape[-2:]).contiguous().float()
+    d1 = curr_depth.reshape(curr_depth.shape[-2:]).contiguous().float()
+    _require_cuda("latest_depth", d0)
+    _require_cuda("curr_depth", d1)
+    H, W = d0.shape
+    dev = d0.device
+    K = torch.as_tensor(intrinsics).detach().cpu()
+    intr = (C.c_float * 4)(float(K[0][0]), float(K[1][1]), float(K[0][2]), float(K[1][2]))
+    w0, w1 = torch.as_tensor(latest_w2c).detach().double().cpu(), torch.as_tensor(curr_w2c).detach().double().cpu()
+    c0, c1 = torch.linalg.inv(w0), torch.linalg.inv(w1)
+    P = H * W
+    f32 = dict(dtype=torch.float32, device=dev)
+    pts0, nrm0, pts1 = torch.empty((P, 3), **f32), torch.empty((P, 3), **f32), torch.empty((P, 3), **f32)
+    ok0, ok1 = torch.empty(P, dtype=torch.uint8, device=dev), torch.empty(P, dtype=torch.uint8, device=dev)
+    u8 = lambda m: None if m is None else m.reshape(-1).to(device=dev, dtype=torch.uint8).contiguous()
+    m0, m1 = u8(latest_varmask), u8(curr_varmask)
+    table = torch.empty(1 << max(16, (2 * P - 1).bit_length()), dtype=torch.int32, device=dev)
+    nxt = torch.empty(P, dtype=torch.int32, device=dev)
+    dist = torch.empty(P, **f32)
+    idx = torch.empty(P, dtype=torch.int32, device=dev) if return_pairs else None
+    L, s = _lib.lib(), _stream_ptr(dev)
+    with torch.cuda.device(dev):
+        _lib.check(L.vtgs_p2p_prepare(W, H, C.byref(intr), C.byref(_rows12(c0)), C.byref(_rows12(w1)) if frustum else None,
+                                      _ptr(d0), _ptr(m0), _ptr(pts0), _ptr(nrm0), _ptr(ok0), s))
+        _lib.check(L.vtgs_p2p_prepare(W, H, C.byref(intr), C.byref(_rows12(c1)), C.byref(_rows12(w0)) if frustum else None,
+                                      _ptr(d1), _ptr(m1), _ptr(pts1), None, _ptr(ok1), s))
+        _lib.check(L.vtgs_p2p_match(P, _ptr(pts0), _ptr(nrm0), _ptr(ok0), P, _ptr(pts1), _ptr(ok1), float(threshold),
+                                    _ptr(table), table.numel(), _ptr(nxt), _ptr(dist), _ptr(idx), s))
+    d = torch.nan_to_num(dist, nan=0.0)
+    if method == "sum":
+        out = (d * d).sum()
+    elif method == "max":
+        out = d.abs().max()
+    elif method == "max100":
+        out = d.abs()[~torch.isnan(dist)].topk(100)[0].mean()
+    else:
+        raise ValueError(f"unknown p2p_method {method!r}")
+    return (out, dist, idx) if return_pairs else out

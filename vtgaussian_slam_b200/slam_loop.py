@@ -201,6 +201,17 @@ class SectionStore:
         return {k: v[a:b] for k, v in self.buf.items()}
 
 
+    def gather(self, indices):
+        """Parameters of the listed sections as one contiguous set: row-slice views when the sections are consecutive
+        (no copy), otherwise one concatenated copy (what the reference does on every iteration, :2734)."""
+        idx = sorted(set(int(i) for i in indices))
+        if not idx:
+            raise ValueError("no section selected")
+        if idx == list(range(idx[0], idx[-1] + 1)):
+            return self.rows(idx[0], idx[-1])
+        return {k: torch.cat([v[self.offsets[i]:self.offsets[i + 1]] for i in idx], dim=0) for k, v in self.buf.items()}
+
+
 def ate_rmse(est_c2w, gt_c2w):
     """Translation RMSE between two trajectories that share their first pose (no alignment: both are relative to frame 0)."""
     e = np.asarray(est_c2w)[:, :3, 3] - np.asarray(gt_c2w)[:, :3, 3]
