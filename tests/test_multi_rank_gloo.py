@@ -60,7 +60,7 @@ def _worker(rank, world, port, ret):
     import bench
     q, t = np.array([0.9999, 0.005, -0.003, 0.002], np.float32), np.array([0.01, -0.004, 0.006], np.float32)
     _, gy = _tracking_terms((0, 1), q, t)
-    band = bench.band_for_rank(gy, rank, world)
+    band = bench.balanced_bands(np.ones(gy), world)[rank]
     msg, _ = _tracking_terms(band, q, t)
     tmsg = torch.tensor(msg)
     dist.all_reduce(tmsg)                              # the one collective of a tracking iteration
@@ -81,7 +81,7 @@ def test_band_partition_covers_all_rows():
     import bench
     for gy in (43, 30, 73, 7):
         for world in (1, 2, 4, 8):
-            bands = [bench.band_for_rank(gy, r, world) for r in range(world)]
+            bands = bench.balanced_bands(np.ones(gy), world)          # uniform work: an even split
             assert bands[0][0] == 0 and bands[-1][1] == gy
             assert all(bands[i][1] == bands[i + 1][0] for i in range(world - 1))
             sizes = [b - a for a, b in bands]
