@@ -100,3 +100,32 @@ def test_silhouette_driven_addition_fills_uncovered_pixels():
     assert tr.params["means3D"].shape[0] == n0 + added
     img, _ = tr.r.forward(tr.params, q, t)
     assert int((img[4] < 0.5).sum().item()) < 0.05 * holes_before
+
+
+@pytest.mark.parametrize("metric", ["p2p", "loss"])
+def test_overlap_driven_section_choice_at_base_frames(metric):
+    """LoopConfig.section_selection = "overlap" (reference :1526-1553, :1891-1970): a new section's first frame is tracked
+    against the earliest overlapping sections plus the newest one -- non-adjacent sections go through SectionStore.gather
+    -- and, with base_metric = "p2p", ranked by the device point-to-plane metric."""
+    n = 13
+    W, H, K = synthetic.intrinsics("tum_fr1", 320, 240)
+    poses = synthetic.trajectory(n, step_m=0.01, step_deg=0.3)
+    cfg = LoopConfig(track_iters=40, map_iters=8, baseframe_every=4, map_every=2, section_selection="overlap", overlap_every=2,
+                     topk_base=1, base_metric=metric)
+    slam = ViewTiedSLAM(W, H, K, cfg, device=DEV)
+    for i in range(n):
+        slam.process(synthetic.make_frame("tum_fr1", 320, 240, seed=i, c2w=poses[i]))
+    # frame 4: one finished section; frame 8: two (earliest alone + newest); frame 12: three, top-1 earliest + newest
+    assert slam.section_choices == [(4, [0]), (8, [0, 1]), (12, [0, 2])]
+    assert [k["id"] for k in slam.keyframe_list] == [0, 2, 4, 6, 8, 10, 12]
+    est = np.stack([np.linalg.inv(m) for m in slam.w2c])
+    err = ate_rmse(est, poses)
+    still = ate_rmse(np.tile(np.eye(4), (n, 1, 1)), poses)
+    # several overlapping sections are displaced against each other by their base frames' pose errors: ranked by the
+    # loss the optimum is a compromise; the point-to-plane metric (the reference's choice for base frames) is tighter
+    assert (err < 0.25 * still and err < 0.012) if metric == "p2p" else err < 0.6 * still, (err, still)
+    g = slam.store.gather([0, 2])
+    assert g["means3D"].shape[0] == 2 * 320 * 240 and g["means3D"].data_ptr() != slam.store.rows(0)["means3D"].data_ptr()
+    assert slam.store.gather([1, 2])["means3D"].data_ptr() == slam.store.rows(1)["means3D"].data_ptr()       # consecutive: views
+    with pytest.raises(ValueError):
+        ViewTiedSLAM(W, H, K, LoopConfig(baseframe_every=5, overlap_every=2, section_selection="overlap"), device=DEV)

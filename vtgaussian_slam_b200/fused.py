@@ -420,6 +420,26 @@ class TrackingSolver:
             self._reset_pose()
         raise _lib.VtgsError("pair buffer overflow persisted after regrowing")
 
+    def run_frame_with_metric(self, num_iters, metric_fn):
+        """run_frame with the reference's `choose_metric` of a section's base frame (:1891-1970): after every Adam step
+        `metric_fn(cam_unnorm_rot[4], cam_trans[3])` (host tensors of the POST-step pose; e.g. the point-to-plane distance
+        to the overlapping keyframe, keyframes.point2plane_dist) ranks the candidate, and the pose with the smallest
+        metric is kept.  One blocking pose read per iteration -- the reference runs an Open3D KD-tree there.
+        -> best[8] on the host: (best metric, cam_unnorm_rot[4], cam_trans[3])."""
+        for attempt in range(3):
+            best = torch.full((8,), float("inf"))
+            for _ in range(num_iters):
+                self.step()
+                q, t = self.cam_q.cpu(), self.cam_t.cpu()
+                m = float(metric_fn(q, t))
+                if m < float(best[0]):
+                    best[0] = m
+                    best[1:5], best[5:8] = q, t
+            if self.check(grow=True, raise_on_overflow=False) is not None:
+                return best
+            self._reset_pose()
+        raise _lib.VtgsError("pair buffer overflow persisted after regrowing")
+
 
 class MappingSolver:
     """The reference's mapping iteration (src/vtgaussian_slam.py:2525-2752) over a set of

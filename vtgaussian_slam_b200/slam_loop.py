@@ -12,8 +12,13 @@ What it mirrors of the reference's `rgbd_slam` (src/vtgaussian_slam.py:1574-2876
     loss kept -- TrackingSolver, one CUDA graph replay per iteration;
   * mapping (:2525-2702): `map_iters` x (sum of keyframe losses -> backward -> Adam over rgb / opacity / scale of
     the current section) over the section's most recent keyframes -- MappingSolver.
-  Left out (not on the hot path, SURVEY.md 8 "out of scope" / later rows): edge-mask densification on the 2x grid,
-  cross-section overlap selection and the frozen-section loss, silhouette-driven Gaussian addition, checkpoints.
+  * section choice at a section's base frame (:1526-1553, :1891-1970; LoopConfig.section_selection = "overlap"): the
+    earliest sections that still overlap the new frame (keyframes.keyframe_selection_overlap_visbased_earliest_dynamic_
+    new_topkbase) are rendered together with the newest one, candidates ranked by the device point-to-plane metric;
+  * silhouette-driven Gaussian addition (:732-813): add_missing_gaussians.
+  Left out (not on the hot path, SURVEY.md 8 "out of scope" / later rows): edge-mask densification on the 2x grid inside
+  the loop (densified_section builds such a section), the frozen-section loss inside the loop (MappingSolver has it),
+  checkpoints.
 
 Everything on the device runs through the CUDA library; there is no CPU fallback.
 """
@@ -48,6 +53,19 @@ class LoopConfig:
     map_w_depth: float = 1.0
     map_lrs: dict = field(default_factory=lambda: dict(rgb_colors=0.0025, logit_opacities=0.05, log_scales=0.005))
     use_graph: bool = True
+    # -- section choice at a section's base frame (reference :1526-1553, :1891-1970; `onlybase_overlap` configs) --
+    section_selection: str = "latest"     # "overlap": the first frame of a new section is tracked against the EARLIEST
+                                          # sections that still overlap it (visibility-based, dynamic threshold) plus
+                                          # the newest one, which ties the new section to old geometry instead of
+                                          # chaining it to the drift of its predecessor
+    overlap_every: int = 5                # a keyframe (pose + depth) is kept every this many frames (fr1_config.py:38)
+    kf_depth_thresh: float = 0.01         # fr1_config.py tracking.kf_depth_thresh
+    earliest_thres: float = 0.5
+    lower_earliest_thres_percent: float = 0.8
+    topk_base: int = 3
+    base_metric: str = "loss"             # "p2p": rank the base frame's candidate poses by the point-to-plane distance
+                                          # to the earliest overlapping section's base frame (reference choose_metric)
+    p2p_method: str = "sum"
 
 
 def quat_from_matrix(R):
@@ -236,6 +254,10 @@ class ViewTiedSLAM:
         self.store = None                  # SectionStore, created with the first section
         self.tracker = None
         self.mapper = None
+        if self.cfg.section_selection == "overlap" and self.cfg.baseframe_every % self.cfg.overlap_every != 0:
+            raise ValueError("overlap-driven section choice needs baseframe_every to be a multiple of overlap_every")
+        self.keyframe_list = []            # every `overlap_every` frames: dict(id, est_w2c, depth) for the section choice
+        self.section_choices = []          # per base frame: the sections it was tracked against
         self.stats = dict(track_iters=0, map_iters=0, track_s=0.0, map_s=0.0, track_loss=[])
 
     # -- sections -------------------------------------------------------------------------------------------
@@ -328,6 +350,44 @@ class ViewTiedSLAM:
         self.stats["track_loss"].append(float(best[0]))
         return matrix_from_quat(best[1:5], best[5:8])
 
+    def _track_base_frame(self, idx, rgb, depth):
+        """First frame of a new section with section_selection == "overlap": choose the sections to track against by
+        their visibility-based overlap with this frame at its propagated pose (reference :1526-1553:
+        keyframe_selection_overlap_visbased_earliest_dynamic_new_topkbase over the keyframes of all finished sections but
+        the tail of the newest; the earliest one alone while there are at most two sections), render them together
+        (zero-copy when consecutive, one gather otherwise) and, with base_metric == "p2p", keep the candidate pose
+        with the smallest point-to-plane distance to the earliest chosen section's base frame (:1891-1970)."""
+        from . import keyframes as kfsel
+        c = self.cfg
+        init = propagate_pose(self.w2c[idx - 1], self.w2c[idx - 2]) if idx >= 2 else self.w2c[idx - 1].copy()
+        per_section = max(1, int(c.baseframe_every / c.overlap_every))
+        n_sections = len(self.store)
+        kfs = self.keyframe_list[:len(self.keyframe_list) - per_section + 1] if per_section > 1 else self.keyframe_list
+        Kt = torch.as_tensor(self.K[:3, :3], dtype=torch.float32, device=self.device)
+        w2c_t = torch.as_tensor(init, dtype=torch.float32, device=self.device)
+        chosen = kfsel.keyframe_selection_overlap_visbased_earliest_dynamic_new_topkbase(
+            depth, w2c_t, Kt, kfs, c.topk_base, dict(baseframe_every=c.baseframe_every, overlap_every=c.overlap_every),
+            kf_depth_thresh=c.kf_depth_thresh, earliest_thres=c.earliest_thres,
+            lower_earliest_thres_percent=c.lower_earliest_thres_percent, topk_base=None if n_sections <= 2 else c.topk_base)
+        chosen = [s_ for s_ in chosen if s_ < n_sections]
+        sel = sorted(set(chosen) | {n_sections - 1})
+        self.section_choices.append((idx, sel))
+        tr = TrackingSolver(self.settings, self.store.gather(sel), device=self.device, lr_rot=c.lr_rot, lr_trans=c.lr_trans,
+                            w_im=c.track_w_im, w_depth=c.track_w_depth, sil_thres=c.sil_thres, use_graph=c.use_graph)
+        tr.set_frame(rgb, depth, quat_from_matrix(init[:3, :3]).astype(np.float32), init[:3, 3].astype(np.float32))
+        t0 = time.perf_counter()
+        if c.base_metric == "p2p":
+            anchor = next(k for k in self.keyframe_list if k["id"] == self.sections[sel[0]]["base"])
+            metric = lambda q, t: kfsel.point2plane_dist(anchor["depth"], depth, self.K[:3, :3], anchor["est_w2c"],
+                                                         matrix_from_quat(q.numpy(), t.numpy()), method=c.p2p_method)
+            best = tr.run_frame_with_metric(c.track_iters, metric).numpy()
+        else:
+            best = tr.run_frame(c.track_iters + 1).numpy()
+        self.stats["track_s"] += time.perf_counter() - t0
+        self.stats["track_iters"] += c.track_iters + (0 if c.base_metric == "p2p" else 1)
+        self.stats["track_loss"].append(float(best[0]))
+        return matrix_from_quat(best[1:5], best[5:8])
+
     # -- driver ---------------------------------------------------------------------------------------------
     def process(self, frame):
         idx = len(self.w2c)
@@ -336,8 +396,13 @@ class ViewTiedSLAM:
         c = self.cfg
         if idx == 0:
             self.w2c.append(np.eye(4))
+        elif c.section_selection == "overlap" and idx % c.baseframe_every == 0 and self.keyframe_list:
+            self.w2c.append(self._track_base_frame(idx, rgb, depth))
         else:
             self.w2c.append(self._track(idx, rgb, depth))
+        if c.section_selection == "overlap" and idx % c.overlap_every == 0:
+            self.keyframe_list.append(dict(id=idx, est_w2c=torch.as_tensor(self.w2c[idx], dtype=torch.float32, device=self.device),
+                                           depth=depth))
         if idx % c.baseframe_every == 0:
             sec = self._new_section(idx, rgb, depth)
             self._keyframe(sec, idx, rgb, depth)
