@@ -434,6 +434,16 @@ VTGS_API int vtgs_p2p_match(int64_t n_tgt, const float* tgt_pts, const float* tg
                             int64_t n_src, const float* src_pts, const uint8_t* src_valid, float max_dist,
                             int32_t* table, int64_t table_size, int32_t* next, float* out_dist, int32_t* out_idx, void* stream);
 
+/*
+ * Frame conversion on the device: the raw decoded frame -- colour uint8 [src_h, src_w, 3], depth uint16
+ * [src_h, src_w] -- to the planes the loop consumes, im[3, dst_h, dst_w] float32 in [0, 1] and depth[dst_h, dst_w] float32
+ * metres, as the reference's loader produces them on the CPU (datasets/gradslam_datasets/basedataset.py:215-272: colour
+ * through cv2.resize INTER_LINEAR as float64, depth through INTER_NEAREST then / png_depth_scale; then
+ * src/vtgaussian_slam.py:201-202).  Either pair of pointers may be NULL.  All pointers are device pointers.
+ */
+VTGS_API int vtgs_frame_convert(int32_t src_w, int32_t src_h, int32_t dst_w, int32_t dst_h, const uint8_t* rgb_hwc,
+                                const uint16_t* depth_u16, double png_depth_scale, float* im_chw, float* depth_out, void* stream);
+
 /* FP32 FMA throughput probe (bench.py's measured FP32 peak): every thread of a full grid runs `iters` dependent-free
  * FFMA octets; FLOP = 2 * 8 * iters * threads, threads = *threads_out.  sink: one device float (keeps the work alive). */
 VTGS_API int vtgs_ffma_probe(int64_t iters, float* sink, uint64_t* threads_out, void* stream);

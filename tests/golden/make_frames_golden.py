@@ -98,6 +98,27 @@ def write_fixture():
         json.dump(dict(train=[names[i] for i in range(5)], test=[names[5], names[6]]), f)
 
 
+SCANNET_CAM = dict(image_height=48, image_width=64, fx=57.7, fy=57.9, cx=31.9, cy=23.8, png_depth_scale=1000.0)
+
+
+def write_scannet_fixture():
+    """ScanNet (v2) export layout: color/<i>.jpg, depth/<i>.png (mm), pose/<i>.txt (4x4 c2w); 11 frames so that natural
+    order (0, 1, 2, ..., 10) differs from lexicographic order (0, 1, 10, 2, ...)."""
+    from PIL import Image
+    from vtgaussian_slam_b200 import synthetic
+    sdir = os.path.join(FIX, "scannet", "scene0000_00")
+    for d in ("color", "depth", "pose"):
+        os.makedirs(os.path.join(sdir, d), exist_ok=True)
+    poses = synthetic.trajectory(11, step_m=0.04, step_deg=1.5, seed=15)
+    world = np.eye(4)
+    world[:3, 3] = [-0.3, 0.5, 0.2]
+    for i in range(11):
+        fr = synthetic.make_frame("tum_fr1", 64, 48, seed=40 + i, c2w=poses[i])
+        Image.fromarray((fr["im"].transpose(1, 2, 0) * 255 + 0.5).astype(np.uint8)).save(os.path.join(sdir, "color", f"{i}.jpg"), quality=92)
+        Image.fromarray(np.clip(fr["depth"][0] * 1000.0 + 0.5, 0, 65535).astype(np.uint16)).save(os.path.join(sdir, "depth", f"{i}.png"))
+        np.savetxt(os.path.join(sdir, "pose", f"{i}.txt"), world @ poses[i])
+
+
 def shim_missing_modules():
     from PIL import Image
     iio = types.ModuleType("imageio")
@@ -152,13 +173,17 @@ def reference_outputs():
         return m
     for n in ("geometryutils", "datautils", "basedataset"):
         load(n)
-    replica, tum, spp = load("replica"), load("tum"), load("scannetpp")
+    replica, tum, spp, scannet = load("replica"), load("tum"), load("scannetpp"), load("scannet")
     out = {}
     cases = [
         ("replica_native", replica.ReplicaDataset, dict(dataset_name="replica", camera_params=REPLICA_CAM), os.path.join(FIX, "replica"), "room0", dict(desired_height=48, desired_width=64)),
         ("replica_resized", replica.ReplicaDataset, dict(dataset_name="replica", camera_params=REPLICA_CAM), os.path.join(FIX, "replica"), "room0", dict(desired_height=30, desired_width=44, start=1, end=6, stride=2)),
         ("tum_native", tum.TUMDataset, dict(dataset_name="tum", camera_params=TUM_CAM), os.path.join(FIX, "tum"), "fr1", dict(desired_height=48, desired_width=64)),
         ("tum_resized", tum.TUMDataset, dict(dataset_name="tum", camera_params=TUM_CAM), os.path.join(FIX, "tum"), "fr1", dict(desired_height=24, desired_width=32, start=1)),
+    ]
+    cases += [
+        ("scannet_native", scannet.ScannetDataset, dict(dataset_name="scannet", camera_params=SCANNET_CAM), os.path.join(FIX, "scannet"), "scene0000_00", dict(desired_height=48, desired_width=64)),
+        ("scannet_resized", scannet.ScannetDataset, dict(dataset_name="scannet", camera_params=SCANNET_CAM), os.path.join(FIX, "scannet"), "scene0000_00", dict(desired_height=33, desired_width=50, start=2, stride=3)),
     ]
     spp_cases = [
         ("scannetpp_train", dict(desired_height=48, desired_width=72)),
@@ -183,6 +208,7 @@ def reference_outputs():
 
 if __name__ == "__main__":
     write_fixture()
+    write_scannet_fixture()
     g = reference_outputs()
     np.savez_compressed(os.path.join(HERE, "frames_golden.npz"), **g)
     for k, v in g.items():

@@ -16,7 +16,12 @@ G = np.load(os.path.join(HERE, "golden", "frames_golden.npz"))
 REPLICA_CAM = dict(image_height=48, image_width=64, fx=32.0, fy=32.0, cx=31.5, cy=23.5, png_depth_scale=6553.5)
 TUM_CAM = dict(image_height=48, image_width=64, fx=51.73, fy=51.65, cx=31.86, cy=25.53, png_depth_scale=5000.0)
 
+SCANNET_CAM = dict(image_height=48, image_width=64, fx=57.7, fy=57.9, cx=31.9, cy=23.8, png_depth_scale=1000.0)
+
 CASES = {
+    "scannet_native": lambda: frames.ScannetSource(SCANNET_CAM, os.path.join(FIX, "scannet"), "scene0000_00", desired_height=48, desired_width=64),
+    "scannet_resized": lambda: frames.ScannetSource(SCANNET_CAM, os.path.join(FIX, "scannet"), "scene0000_00", desired_height=33, desired_width=50,
+                                                    start=2, stride=3),
     "replica_native": lambda: frames.ReplicaSource(REPLICA_CAM, os.path.join(FIX, "replica"), "room0", desired_height=48, desired_width=64),
     "replica_resized": lambda: frames.ReplicaSource(REPLICA_CAM, os.path.join(FIX, "replica"), "room0", desired_height=30, desired_width=44,
                                                     start=1, end=6, stride=2),
@@ -94,3 +99,12 @@ def test_quaternion_rows_are_normalised_like_scipy():
     R = frames.quat_xyzw_to_matrix(q)
     from scipy.spatial.transform import Rotation
     assert np.allclose(R, Rotation.from_quat(q).as_matrix(), atol=1e-12)
+
+
+def test_scannet_frames_come_in_natural_order():
+    src = CASES["scannet_native"]()
+    assert [os.path.basename(p) for p in src.colour_paths] == [f"{i}.jpg" for i in range(11)]      # not 0, 1, 10, 2, ...
+    raw = src.decode_raw(3)
+    assert raw[0].dtype == np.uint8 and raw[0].shape == (48, 64, 3) and raw[1].dtype == np.uint16 and raw[1].shape == (48, 64)
+    with pytest.raises(RuntimeError):
+        src.convert_on_device(raw[0], raw[1], "cpu")          # the device path has no CPU fallback (the CPU path is src[i])

@@ -123,3 +123,25 @@ def test_rendered_sequence_evaluation_of_a_short_run():
     res2 = eval_sequence(frames, store, w2c, slam.settings, baseframe_every=4, sil_thres=0.5, eval_every=4,
                          baseframe_corr_list=[[0, 4], [0, 8]], gt_c2w=list(poses))
     assert res2["frame"] == [0, 4, 8] and res2["avg_psnr"] > 20.0
+
+
+@pytest.mark.parametrize("size", [(48, 64), (33, 50), (96, 128), (30, 44)])
+def test_device_frame_conversion_matches_the_cpu_loader(size):
+    """vtgs_frame_convert on the raw decoded bytes == the reference-pinned CPU path (cv2.resize on float64, tests/test_frames.py)."""
+    from vtgaussian_slam_b200 import frames
+    fix = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "frames_fixture")
+    cam = dict(image_height=48, image_width=64, fx=57.7, fy=57.9, cx=31.9, cy=23.8, png_depth_scale=1000.0)
+    src = frames.ScannetSource(cam, os.path.join(fix, "scannet"), "scene0000_00", desired_height=size[0], desired_width=size[1])
+    for i in (0, 5, 10):
+        cpu = src[i]
+        raw = src.decode_raw(i)
+        im, depth = src.convert_on_device(raw[0], raw[1], DEV)
+        assert im.shape == cpu["im"].shape and depth.shape == cpu["depth"].shape
+        assert torch.equal(depth.cpu(), cpu["depth"])                              # nearest + fp64 division: bit-exact
+        d = (im.cpu() - cpu["im"]).abs()
+        assert float(d.max()) <= 6e-8 and float((d > 0).float().mean()) < 1e-3    # fp64 bilinear, last float32 bit at most
+    got = list(src.prefetch(DEV, ahead=2, device_convert=True))
+    assert [f["index"] for f in got] == list(range(len(src)))
+    assert got[4]["im"].is_cuda and torch.allclose(got[4]["im"].cpu(), src[4]["im"], atol=6e-8) and torch.equal(got[4]["depth"].cpu(), src[4]["depth"])
+    plain = list(src.prefetch(DEV, ahead=2))                                        # CPU conversion + pinned upload
+    assert torch.equal(plain[7]["im"].cpu(), src[7]["im"])

@@ -116,6 +116,7 @@ SYMBOLS = {
     "vtgs_eval_metrics": (C.c_int, [C.POINTER(VtgsCamera), _P, _P, _P, C.c_float, C.c_int32, _P, _P, _P]),
     "vtgs_p2p_prepare": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_float * 4), C.POINTER(C.c_float * 12), _P, _P, _P, _P, _P, _P, _P]),
     "vtgs_p2p_match": (C.c_int, [C.c_int64, _P, _P, _P, C.c_int64, _P, _P, C.c_float, _P, C.c_int64, _P, _P, _P, _P]),
+    "vtgs_frame_convert": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, C.c_double, _P, _P, _P]),
     "vtgs_ffma_probe": (C.c_int, [C.c_int64, _P, C.POINTER(C.c_uint64), _P]),
     "vtgs_profile_enable": (C.c_int, [C.c_int32]),
     "vtgs_profile_summary": (C.c_int, [C.c_char_p, C.c_uint64]),

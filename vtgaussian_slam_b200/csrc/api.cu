@@ -295,6 +295,14 @@ int vtgs_p2p_match(int64_t n_tgt, const float* tgt_pts, const float* tgt_nrm, co
                             out_idx, (cudaStream_t)stream);
 }
 
+int vtgs_frame_convert(int32_t src_w, int32_t src_h, int32_t dst_w, int32_t dst_h, const uint8_t* rgb_hwc, const uint16_t* depth_u16,
+                       double png_depth_scale, float* im_chw, float* depth_out, void* stream) {
+    VTGS_REQUIRE(src_w > 0 && src_h > 0 && dst_w > 0 && dst_h > 0, "bad image size");
+    VTGS_REQUIRE((rgb_hwc == nullptr) == (im_chw == nullptr) && (depth_u16 == nullptr) == (depth_out == nullptr), "input / output pointers must come in pairs");
+    VTGS_REQUIRE(depth_u16 == nullptr || png_depth_scale > 0.0, "png_depth_scale must be positive");
+    return launch_frame_convert(src_w, src_h, dst_w, dst_h, rgb_hwc, depth_u16, png_depth_scale, im_chw, depth_out, (cudaStream_t)stream);
+}
+
 int vtgs_ffma_probe(int64_t iters, float* sink, uint64_t* threads_out, void* stream) {
     VTGS_REQUIRE(iters > 0 && sink != nullptr, "bad argument");
     return launch_ffma_probe(iters, sink, threads_out, (cudaStream_t)stream);

@@ -248,4 +248,66 @@ int launch_p2p_match(int64_t n_tgt, const float* tgt_pts, const float* tgt_nrm, 
     return VTGS_OK;
 }
 
+// =============================== frame conversion on the device ==============================
+// What the reference's dataset does to a decoded frame on the CPU before every use (datasets/gradslam_datasets/
+// basedataset.py:215-272 + src/vtgaussian_slam.py:198-202): colour uint8 HWC -> float64 -> cv2.resize(INTER_LINEAR) ->
+// float32 CHW / 255; depth uint16 -> float64 -> cv2.resize(INTER_NEAREST) -> / png_depth_scale -> float32.  Done here
+// from the RAW decoded bytes, so a frame crosses PCIe as 3 + 2 bytes per pixel instead of 16, and the arithmetic follows
+// OpenCV's generic path for CV_64F (double coefficients and accumulation, horizontal pass first: checked against
+// cv2 4.13 to 1e-13 before the float32 cast) so the planes agree with the CPU loader's to the last bit of the float32 result.
+struct ResizeGeom { int sw, sh, dw, dh; double scale_x, scale_y; };
+
+__device__ __forceinline__ void linear_tap(int d, double scale, int ssize, int& s0, double& f, bool& edge) {
+    f = ((double)d + 0.5) * scale - 0.5;
+    s0 = (int)floor(f);
+    f -= (double)s0;
+    edge = false;
+    if (s0 < 0) { f = 0.0; s0 = 0; }
+    if (s0 + 1 >= ssize) { edge = true; if (s0 >= ssize - 1) { f = 0.0; s0 = ssize - 1; } }
+}
+
+__global__ void __launch_bounds__(256)
+frame_convert_kernel(const __grid_constant__ ResizeGeom g, const uint8_t* __restrict__ rgb, const uint16_t* __restrict__ depth,
+                     double depth_scale, float* __restrict__ im, float* __restrict__ depth_out) {
+    const int pid = blockIdx.x * 256 + threadIdx.x;
+    if (pid >= g.dw * g.dh) return;
+    const int x = pid % g.dw, y = pid / g.dw;
+    if (rgb) {
+        int sx; double fx; bool xedge;
+        linear_tap(x, g.scale_x, g.sw, sx, fx, xedge);
+        // vertical taps: rows sy, sy + 1 clipped, weights (1 - fy, fy) kept as they are (cv::resizeGeneric_Invoker)
+        double fy = ((double)y + 0.5) * g.scale_y - 0.5;
+        const int sy = (int)floor(fy);
+        fy -= (double)sy;
+        const int r0 = min(max(sy, 0), g.sh - 1), r1 = min(max(sy + 1, 0), g.sh - 1);
+        const double a0 = 1.0 - fx, a1 = fx, b0 = 1.0 - fy, b1 = fy;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            double h[2];
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const uint8_t* row = rgb + ((size_t)(k ? r1 : r0) * g.sw) * 3;
+                const double s0 = (double)row[sx * 3 + c];
+                // past xmax OpenCV copies the source sample (x 1); before it, both taps
+                h[k] = xedge ? s0 : __dadd_rn(__dmul_rn(s0, a0), __dmul_rn((double)row[(sx + 1) * 3 + c], a1));
+            }
+            const double v = __dadd_rn(__dmul_rn(h[0], b0), __dmul_rn(h[1], b1));
+            im[(size_t)c * g.dw * g.dh + pid] = __fdiv_rn((float)v, 255.0f);
+        }
+    }
+    if (depth) {
+        const int sx = min((int)floor((double)x * g.scale_x), g.sw - 1), sy = min((int)floor((double)y * g.scale_y), g.sh - 1);
+        depth_out[pid] = (float)((double)depth[(size_t)sy * g.sw + sx] / depth_scale);
+    }
+}
+
+int launch_frame_convert(int sw, int sh, int dw, int dh, const uint8_t* rgb, const uint16_t* depth, double depth_scale, float* im,
+                         float* depth_out, cudaStream_t stream) {
+    ResizeGeom g{sw, sh, dw, dh, 1.0 / ((double)dw / (double)sw), 1.0 / ((double)dh / (double)sh)};      // cv::resize: 1 / inv_scale
+    { VTGS_PROF("frame_convert_kernel", stream);
+      frame_convert_kernel<<<(dw * dh + 255) / 256, 256, 0, stream>>>(g, rgb, depth, depth_scale, im, depth_out); }
+    VTGS_LAUNCH_CHECK();
+    return VTGS_OK;
+}
+
 }  // namespace vtgs

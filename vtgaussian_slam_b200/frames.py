@@ -17,6 +17,7 @@ Reference behaviour mirrored (datasets/gradslam_datasets/):
   * replica.py:44-66         results/frame*.jpg, results/depth*.png in natural order, traj.txt = one row-major c2w per line
   * tum.py:44-160            rgb.txt / depth.txt / groundtruth.txt, nearest-timestamp association within 0.08 s, frames
                              at least 1/32 s apart, pose rows (tx ty tz qx qy qz qw)
+  * scannet.py:14-61         color/*.jpg, depth/*.png, pose/*.txt (4x4 c2w per frame) in natural order
   * scannetpp.py:18-135      dslr/train_test_lists.json + dslr/nerfstudio/transforms_undistorted.json (intrinsics and
                              per-image OpenGL c2w, converted with P c2w P^T, P = diag(1,-1,-1,1)), undistorted_images /
                              undistorted_depths (mm); the test split is prefixed with the first training frame
@@ -123,6 +124,37 @@ class FrameSource:
         im = torch.from_numpy(colour).to(torch.float32).permute(2, 0, 1) / 255
         return im.contiguous(), torch.from_numpy(depth).to(torch.float32)[None].contiguous()
 
+    def decode_raw(self, i):
+        """The frame as decoded from disk, before any arithmetic: (colour uint8 [h,w,3], depth uint16 [h,w]) or None when
+        the files hold other types (then only the CPU path applies)."""
+        colour, depth = _read_image(self.colour_paths[i]), _read_image(self.depth_paths[i])
+        if colour.dtype != np.uint8 or colour.ndim != 3 or colour.shape[2] != 3 or depth.dtype != np.uint16 or depth.ndim != 2:
+            return None
+        return np.array(colour), np.array(depth)          # writable copies (Pillow hands out read-only views)
+
+    def convert_on_device(self, colour_u8, depth_u16, device, stream=None):
+        """Raw frame (host arrays or device tensors) -> (im[3,H,W], depth[1,H,W]) float32 on `device` in one kernel of
+        libvtgs_cuda.so (vtgs_frame_convert): resize + scaling follow the CPU loader (`_decode`), but the frame crosses
+        PCIe as 5 bytes per source pixel instead of 16 per target pixel."""
+        import ctypes as C
+        from . import _lib
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("convert_on_device needs a CUDA device (the CPU path is __getitem__)")
+        up = lambda a: (a if isinstance(a, torch.Tensor) else torch.from_numpy(a).pin_memory()).to(device, non_blocking=True)
+        c, d = up(colour_u8), up(depth_u16 if isinstance(depth_u16, torch.Tensor) else depth_u16.view(np.int16))
+        sh, sw = int(c.shape[0]), int(c.shape[1])
+        im = torch.empty((3, self.H, self.W), dtype=torch.float32, device=device)
+        depth = torch.empty((1, self.H, self.W), dtype=torch.float32, device=device)
+        st = stream if stream is not None else torch.cuda.current_stream(device)
+        with torch.cuda.device(device):
+            _lib.check(_lib.lib().vtgs_frame_convert(sw, sh, self.W, self.H, C.c_void_p(c.data_ptr()), C.c_void_p(d.data_ptr()),
+                                                     float(self.png_depth_scale), C.c_void_p(im.data_ptr()),
+                                                     C.c_void_p(depth.data_ptr()), C.c_void_p(st.cuda_stream)))
+        for t in (c, d):
+            t.record_stream(st)
+        return im, depth
+
     def __getitem__(self, i):
         if i < 0:
             i += len(self)
@@ -132,9 +164,11 @@ class FrameSource:
         return dict(im=im, depth=depth, K=torch.from_numpy(self.K.copy()), c2w=self.c2w[i].clone(), index=self.retained[i],
                     W=self.W, H=self.H)
 
-    def prefetch(self, device="cpu", ahead=2, indices=None):
+    def prefetch(self, device="cpu", ahead=2, indices=None, device_convert=False):
         """Iterate frames with decoding `ahead` frames in advance on a worker thread; on a CUDA device the planes
-        arrive there through pinned staging buffers on a copy stream (the consumer's stream waits on the copy)."""
+        arrive there through pinned staging buffers on a copy stream (the consumer's stream waits on the copy).
+        device_convert: upload the raw decoded bytes and resize / scale on the GPU (convert_on_device) instead of
+        converting on the CPU; frames whose files are not uint8 colour + uint16 depth take the CPU path."""
         device = torch.device(device)
         order = list(range(len(self))) if indices is None else list(indices)
         q = queue.Queue(maxsize=max(1, ahead))
@@ -147,6 +181,15 @@ class FrameSource:
                 for i in order:
                     if stop.is_set():
                         return
+                    raw = self.decode_raw(i) if (cuda and device_convert and hasattr(self, "png_depth_scale")) else None
+                    if raw is not None:
+                        with torch.cuda.stream(stream):
+                            im, dep = self.convert_on_device(raw[0], raw[1], device, stream)
+                            ev = torch.cuda.Event()
+                            ev.record(stream)
+                        q.put(dict(im=im, depth=dep, K=torch.from_numpy(self.K.copy()), c2w=self.c2w[i].clone(), index=self.retained[i],
+                                   W=self.W, H=self.H, _ready=ev))
+                        continue
                     fr = self[i]
                     if cuda:
                         with torch.cuda.stream(stream):
@@ -250,6 +293,22 @@ class TumSource(FrameSource):
             M[:3, 3] = vec[k, :3]
             out.append(M)
         return out
+
+
+class ScannetSource(FrameSource):
+    """ScanNet (v2) export layout (scannet.py): <basedir>/<sequence>/color/*.jpg, depth/*.png, pose/*.txt (one 4x4 c2w
+    per frame), all in natural order."""
+
+    def __init__(self, camera_params, basedir, sequence, desired_height=968, desired_width=1296, **kw):
+        self.folder = os.path.join(basedir, sequence)
+        super().__init__(camera_params, desired_height=desired_height, desired_width=desired_width, **kw)
+
+    def _paths(self):
+        return (sorted(glob.glob(os.path.join(self.folder, "color", "*.jpg")), key=_natural_key),
+                sorted(glob.glob(os.path.join(self.folder, "depth", "*.png")), key=_natural_key))
+
+    def _poses(self, n):
+        return [np.loadtxt(p) for p in sorted(glob.glob(os.path.join(self.folder, "pose", "*.txt")), key=_natural_key)]
 
 
 class ScannetPPSource(FrameSource):
