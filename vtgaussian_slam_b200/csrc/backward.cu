@@ -81,11 +81,19 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[16], int lane)
 #define VTGS_BWD_WARPS 2
 #endif
 constexpr int BWD_WARPS = VTGS_BWD_WARPS;   // warps (regions) per block: a tile is covered by 8 / BWD_WARPS blocks
+#ifndef VTGS_BWD_LITEPIX
+#define VTGS_BWD_LITEPIX 1                  // the pose-only instantiation keeps a 3-row pixel table (x, y, dL/dz): 9.6 instead of 10 KB per
+#endif                                      // warp -> 11 instead of 10 blocks per SM (measured: K6' 273 -> 265 us at C2)
+__host__ __device__ constexpr int bwd_pix_rows(bool lite) { return (VTGS_BWD_LITEPIX && lite) ? 3 : 6; }
+constexpr int bwd_smem_bytes(bool lite) {
+    return BWD_WARPS * (int)(10 * 32 * sizeof(float) + 32 * 32 * sizeof(float2) + bwd_pix_rows(lite) * 32 * sizeof(float));
+}
+constexpr int bwd_min_blocks(bool lite) { return ((VTGS_BWD_LITEPIX && lite) ? 22 : 20) / BWD_WARPS; }
 // BG:   the background is not black (one more term in dL/dalpha); the reference always renders on black.
 // LITE: the caller wants no colour / opacity gradients (tracking: only the pose gradient is formed, from the
 //       mean2D / conic / depth-channel sums) -- P3 drops the r,g,b and opacity sums.
 template <bool FUSED, bool BG, bool LITE>
-__global__ void __launch_bounds__(32 * BWD_WARPS, 20 / BWD_WARPS)
+__global__ void __launch_bounds__(32 * BWD_WARPS, bwd_min_blocks(LITE))
 blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __restrict__ ranges,
                       const uint2* __restrict__ region_pairs, const uint32_t* __restrict__ region_cnt,
                       const uint32_t* __restrict__ region_masks, const uint32_t* __restrict__ region_done,
@@ -102,7 +110,7 @@ blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __re
         float2 cell[32][32];        // [splat of the group][pixel]: (w, g0).  Unpadded: a pixel lane always stores to its own
                                     // column (bank pair = lane mod 16, conflict-free whatever the splats); the splat lanes'
                                     // loads hit the bank pair of the pixel they are at, as with any padding
-        float pix[6][32];           // pixels of the region: centre x, y, dL/d(r, g, b, z)
+        float pix[bwd_pix_rows(LITE)][32];   // pixels of the region: centre x, y, dL/d(r, g, b, z)  (x, y, dL/dz in the 3-row form)
     };
     WarpArea* areas = reinterpret_cast<WarpArea*>(smem_raw);
 
@@ -131,7 +139,10 @@ blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __re
     for (int ch = 0; ch < NCH; ++ch) dpix[ch] = inside ? dL_dpix[ch * P + pid] : 0.0f;
     A.pix[0][lane] = pxf; A.pix[1][lane] = pyf;
 #pragma unroll
-    for (int ch = 0; ch < 4; ++ch) A.pix[2 + ch][lane] = dpix[ch];
+    for (int ch = 0; ch < 4; ++ch)
+        if (bwd_pix_rows(LITE) == 6) A.pix[2 + ch][lane] = dpix[ch];
+    if (bwd_pix_rows(LITE) == 3) A.pix[2][lane] = dpix[3];
+    constexpr int PIX_Z = bwd_pix_rows(LITE) == 3 ? 2 : 5;
     const float bg_dot = BG ? cam.bg[0] * dpix[0] + cam.bg[1] * dpix[1] + cam.bg[2] * dpix[2] : 0.0f;
     const float half_w = 0.5f * cam.W, half_h = 0.5f * cam.H;
 
@@ -220,7 +231,7 @@ blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __re
             const float2 cw = A.cell[lane][p];
             const float dx = cur.a.x - A.pix[0][p], dy = cur.a.y - A.pix[1][p];
             if (!LITE) { c0 = fmaf(cw.x, A.pix[2][p], c0); c1 = fmaf(cw.x, A.pix[3][p], c1); c2 = fmaf(cw.x, A.pix[4][p], c2); }
-            if (NCH == 4) c3 = fmaf(cw.x, A.pix[5][p], c3);
+            if (NCH == 4) c3 = fmaf(cw.x, A.pix[PIX_Z][p], c3);
             const float gg = cw.y, gx_ = gg * dx, gy_ = gg * dy;
             if (!LITE) s0 += gg;
             sx += gx_; sy += gy_;
@@ -385,19 +396,18 @@ preprocess_backward_kernel(const __grid_constant__ CamConst cam, int64_t N,
     for (int k = 0; k < 4; ++k) dL_drot[4 * i + k] = dq[k];
 }
 
-// dynamic shared memory of blend_backward_kernel
-// per warp: splat table 1280 + cells 8192 + pixel table 768 bytes
-constexpr int BWD_SMEM = BWD_WARPS * (int)(10 * 32 * sizeof(float) + 32 * 32 * sizeof(float2) + 6 * 32 * sizeof(float));
+// dynamic shared memory of blend_backward_kernel: bwd_smem_bytes(LITE)
+// per warp: splat table 1280 + cells 8192 + pixel table 768 (384 in the 3-row form) bytes
 template <bool FUSED, bool BG, bool LITE>
 static int launch_blend_backward(int blocks, cudaStream_t stream, const CamConst& cam, const VtgsBuffers* buf, const GeomRecord* geom,
                                  const float* dL_dpix, const uint32_t* order) {
     static std::atomic<uint64_t> done{0};
     if (first_call_on_device(done)) {
-        VTGS_CUDA_CHECK(cudaFuncSetAttribute(blend_backward_kernel<FUSED, BG, LITE>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
+        VTGS_CUDA_CHECK(cudaFuncSetAttribute(blend_backward_kernel<FUSED, BG, LITE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem_bytes(LITE)));
         VTGS_CUDA_CHECK(cudaFuncSetAttribute(blend_backward_kernel<FUSED, BG, LITE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     }
     VTGS_PROF("blend_backward_kernel", stream);
-    blend_backward_kernel<FUSED, BG, LITE><<<blocks, 32 * BWD_WARPS, BWD_SMEM, stream>>>(
+    blend_backward_kernel<FUSED, BG, LITE><<<blocks, 32 * BWD_WARPS, bwd_smem_bytes(LITE), stream>>>(
         cam, buf->tile_ranges, reinterpret_cast<const uint2*>(buf->region_pairs), buf->region_cnt, buf->region_masks, buf->region_done,
         geom, buf->final_T, dL_dpix, buf->grad_geom, order);
     VTGS_LAUNCH_CHECK();
