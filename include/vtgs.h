@@ -108,7 +108,9 @@ typedef struct VtgsCounters {
 typedef struct VtgsBuffers {
     void*         geom;           /* N records of VTGS_GEOM_RECORD_BYTES                  */
     uint32_t*     tiles_touched;  /* [N]                                                   */
-    uint32_t*     tile_counts;    /* [tiles + 1]  scratch (zeroed by forward); the last word counts band_cand  */
+    uint32_t*     tile_counts;    /* [tiles + 3]  scratch (zeroed by forward); word [tiles] counts band_cand, [tiles + 1] and
+                                     [tiles + 2] hold the bit patterns of max |colour| of the rendered Gaussians and of
+                                     max |dL/dpixel| (the scales of the deterministic gradient accumulation)          */
     uint32_t*     tile_ranges;    /* [tiles][2] = {begin, end} into point_list             */
     uint64_t*     pair_keys;      /* [pair_capacity] depth_bits<<32 | gaussian id<<8 | region mask */
     uint32_t*     point_list;     /* [pair_capacity] sorted Gaussian ids                   */
@@ -136,10 +138,20 @@ typedef struct VtgsBuffers {
                                      descending order of list length; the sort and blend kernels take their tile from it,
                                      so the longest lists are started first (longest-processing-time-first scheduling of
                                      the blocks: the tail of a launch is filled with short tiles)                   */
+    uint32_t      flags;          /* VTGS_BUF_*                                                                       */
+    uint32_t      reserved;
 } VtgsBuffers;
 
+/* VtgsBuffers.flags.  VTGS_BUF_DETERMINISTIC: the backward blend accumulates its per-(region, splat) partial sums into
+ * grad_geom as 64-bit FIXED-POINT integers (integer addition is associative, so the order in which the tiles' warps
+ * arrive does not matter) instead of fp32 `red.global.add`: every gradient of the backward is then bitwise reproducible
+ * run to run and across ranks.  The power-of-two scale is chosen per Gaussian and per quantity from a rigorous bound of
+ * the sum (max |dL/dpixel| and max |colour| measured on the device, the splat's opacity / conic / extent), so nothing can
+ * overflow and at least ~30 bits stay below the bound's leading bit.  Upstream: global float atomics in arbitrary order. */
+#define VTGS_BUF_DETERMINISTIC 1u
+
 #define VTGS_GEOM_RECORD_BYTES 64
-#define VTGS_GRAD_GEOM_FLOATS  16
+#define VTGS_GRAD_GEOM_FLOATS  32   /* 16 floats per Gaussian without, 16 int64 with VTGS_BUF_DETERMINISTIC */
 
 typedef struct VtgsWorkspaceSizes {
     uint64_t geom_bytes;

@@ -17,7 +17,8 @@ MEDIAN_SUMMABLE_WORDS = 257
 TRACK_BOOK_POST_STEP = 1
 TRACK_CALLER_METRIC = 2
 GEOM_RECORD_BYTES = 64
-GRAD_GEOM_FLOATS = 16
+GRAD_GEOM_FLOATS = 32
+BUF_DETERMINISTIC = 1
 
 
 class VtgsCamera(C.Structure):
@@ -48,6 +49,7 @@ class VtgsBuffers(C.Structure):
         ("counters", C.c_void_p), ("region_pairs", C.c_void_p), ("region_cnt", C.c_void_p),
         ("region_masks", C.c_void_p), ("region_done", C.c_void_p), ("pair_capacity", C.c_uint64),
         ("band_flags", C.c_void_p), ("band_cand", C.c_void_p), ("tile_order", C.c_void_p),
+        ("flags", C.c_uint32), ("reserved", C.c_uint32),
     ]
 
 

@@ -85,7 +85,7 @@ int vtgs_workspace_query(int32_t W, int32_t H, int64_t N, uint64_t pair_capacity
     const uint64_t n = (uint64_t)(N > 0 ? N : 1), P = (uint64_t)W * H;
     s->geom_bytes = n * VTGS_GEOM_RECORD_BYTES;
     s->tiles_touched_bytes = n * 4;
-    s->tile_counts_bytes = (gx * gy + 1) * 4;
+    s->tile_counts_bytes = (gx * gy + 3) * 4;
     s->tile_ranges_bytes = gx * gy * 8;
     s->pair_keys_bytes = (pair_capacity > 0 ? pair_capacity : 1) * 8;
     s->point_list_bytes = (pair_capacity > 0 ? pair_capacity : 1) * 4;

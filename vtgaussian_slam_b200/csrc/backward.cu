@@ -60,6 +60,48 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[16], int lane)
     return v[0];
 }
 
+
+// ---- deterministic accumulation (VTGS_BUF_DETERMINISTIC, include/vtgs.h) --------------------------------------------
+// grad_geom record of a Gaussian in this mode: 16 int64 slots --
+//   [0,1] dL/dmean2D  [2,3,4] dL/dconic  [5] dL/d(colour 3: the depth channel)  [6] low word: the three exponents
+//   [7] dL/dopacity   [8,9,10] dL/d(r, g, b)
+// (what the pose-only instantiation touches sits in the first 64 bytes).  A value v of a quantity whose per-Gaussian sum
+// is bounded by B < 2^e is added as the integer round(v * 2^(61 - e)): integer addition is associative, so the sums do
+// not depend on the order in which the warps of different tiles and regions arrive.
+constexpr int DET_STRIDE = 32;        // floats per record (= 16 int64)
+constexpr int DET_EXP_WORD = 12;      // uint32 index of the exponent word (slot 6)
+
+__device__ __forceinline__ int det_exponent(float bound) {          // smallest e (clamped) with bound < 2^e
+    const int e = (int)((__float_as_uint(bound) >> 23) & 0xffu) - 126;
+    return min(max(e, -60), 120);
+}
+__device__ __forceinline__ float det_pow2(int s) { return __uint_as_float((uint32_t)(s + 127) << 23); }   // 2^s, s in [-126, 127]
+__device__ __forceinline__ void det_add(float* rec, int slot, float v, float scale) {
+    atomicAdd(reinterpret_cast<unsigned long long*>(rec) + slot, (unsigned long long)__float2ll_rn(v * scale));
+}
+__device__ __forceinline__ float det_read(long long q, int e) { return (float)((double)q * (double)det_pow2(e - 61)); }
+
+// max |dL/dpixel| over the band's rows and the NCH planes -> *out_bits (atomicMax on the bit pattern; zeroed by the forward)
+__global__ void __launch_bounds__(256)
+dpix_max_kernel(const float* __restrict__ dL_dpix, size_t P, size_t begin, size_t end, int nch, uint32_t* __restrict__ out_bits) {
+    float m = 0.0f;
+    for (size_t i = begin + (size_t)blockIdx.x * 256 + threadIdx.x; i < end; i += (size_t)gridDim.x * 256)
+        for (int ch = 0; ch < nch; ++ch) m = fmaxf(m, fabsf(__ldg(dL_dpix + ch * P + i)));
+    uint32_t b = __float_as_uint(m);            // (NaN compares as small: fmaxf drops it)
+    b = __reduce_max_sync(VTGS_FULL_MASK, b);
+    if ((threadIdx.x & 31) == 0 && b != 0u) atomicMax(out_bits, b);
+}
+
+static int launch_dpix_max(const CamConst& cam, const float* dL_dpix, int nch, uint32_t* out_bits, cudaStream_t stream) {
+    const size_t P = (size_t)cam.W * cam.H;
+    const size_t begin = (size_t)cam.row0 * 16 * cam.W, end = std::min(P, (size_t)cam.row1 * 16 * cam.W);
+    if (end <= begin) return VTGS_OK;
+    const int blocks = (int)std::min<size_t>((end - begin + 1023) / 1024, 148 * 8);
+    { VTGS_PROF("dpix_max_kernel", stream); dpix_max_kernel<<<blocks, 256, 0, stream>>>(dL_dpix, P, begin, end, nch, out_bits); }
+    VTGS_LAUNCH_CHECK();
+    return VTGS_OK;
+}
+
 // =============================== K6': backward blend =======================================
 // grad_geom record per Gaussian (VTGS_GRAD_GEOM_FLOATS = 16):
 //   [0,1] dL/dmean2D (NDC-scaled)  [2,3,4] dL/dconic (xx, xy, yy)  [5] dL/dopacity
@@ -92,14 +134,15 @@ constexpr int bwd_min_blocks(bool lite) { return ((VTGS_BWD_LITEPIX && lite) ? 2
 // BG:   the background is not black (one more term in dL/dalpha); the reference always renders on black.
 // LITE: the caller wants no colour / opacity gradients (tracking: only the pose gradient is formed, from the
 //       mean2D / conic / depth-channel sums) -- P3 drops the r,g,b and opacity sums.
-template <bool FUSED, bool BG, bool LITE>
+// DET:  fixed-point accumulation of the partial sums (VTGS_BUF_DETERMINISTIC); det_scalars = {max |colour| bits, max |dL/dpixel| bits}.
+template <bool FUSED, bool BG, bool LITE, bool DET>
 __global__ void __launch_bounds__(32 * BWD_WARPS, bwd_min_blocks(LITE))
 blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __restrict__ ranges,
                       const uint2* __restrict__ region_pairs, const uint32_t* __restrict__ region_cnt,
                       const uint32_t* __restrict__ region_masks, const uint32_t* __restrict__ region_done,
                       const GeomRecord* __restrict__ geom,
                       const float* __restrict__ final_T, const float* __restrict__ dL_dpix, float* __restrict__ grad_geom,
-                      const uint32_t* __restrict__ tile_order) {
+                      const uint32_t* __restrict__ tile_order, const uint32_t* __restrict__ det_scalars) {
     constexpr int NCH = FUSED ? 4 : 3;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // Every table a lane indexes with ITS OWN splat or pixel number is a plain float[32]: 32 entries over 32 banks, so
@@ -243,7 +286,34 @@ blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __re
             const float v0 = -half_w * o * (ca * sx + cb * sy);
             const float v1 = -half_h * o * (cc * sy + cb * sx);
             const float v2 = -0.5f * o * sxx, v3 = -0.5f * o * sxy, v4 = -0.5f * o * syy;
-            float* dst = grad_geom + (size_t)cur_ent.x * VTGS_GRAD_GEOM_FLOATS;
+            if (DET) {
+                // bounds of this Gaussian's sums over ALL its partials (every partial derives the same three exponents):
+                // |g0| <= |dL/dalpha| <= 2 max|c| sum_ch |dL/dpix| (+ the background term), |w| <= 1, the splat's blended
+                // pixels lie within its alpha >= 1/255 box (half extents hx, hy of the record)
+                const float4 q0 = geom[cur_ent.x].q0;
+                const float cmax = __uint_as_float(__ldg(det_scalars)), dmax = __uint_as_float(__ldg(det_scalars + 1));
+                const float d1 = (float)NCH * dmax;
+                float g0max = 2.0f * cmax * d1;
+                if (BG) g0max += 100.0f * (fabsf(cam.bg[0]) + fabsf(cam.bg[1]) + fabsf(cam.bg[2])) * dmax;
+                const float ex = q0.z + 1.5f, ey = q0.w + 1.5f;
+                const float npix = (2.0f * ex) * (2.0f * ey);
+                const float S = npix * g0max;
+                const float bm = fmaxf(half_w, half_h) * o * (fabsf(ca) * ex + fabsf(cb) * (ex + ey) + fabsf(cc) * ey) * S;
+                const float bc = 0.5f * o * S * fmaxf(ex, ey) * fmaxf(ex, ey);
+                const float bk = npix * fmaxf(d1, g0max);
+                const int em = det_exponent(bm), ec = det_exponent(bc), ek = det_exponent(bk);
+                float* dst = grad_geom + (size_t)cur_ent.x * DET_STRIDE;
+                reinterpret_cast<uint32_t*>(dst)[DET_EXP_WORD] = (uint32_t)(em + 128) | ((uint32_t)(ec + 128) << 8) | ((uint32_t)(ek + 128) << 16) | (1u << 24);
+                const float fm = det_pow2(61 - em), fc = det_pow2(61 - ec), fk = det_pow2(61 - ek);
+                det_add(dst, 0, v0, fm); det_add(dst, 1, v1, fm);
+                det_add(dst, 2, v2, fc); det_add(dst, 3, v3, fc); det_add(dst, 4, v4, fc);
+                if (NCH == 4) det_add(dst, 5, c3, fk);
+                if (!LITE) {
+                    det_add(dst, 7, s0, fk);
+                    det_add(dst, 8, c0, fk); det_add(dst, 9, c1, fk); det_add(dst, 10, c2, fk);
+                }
+            } else {
+            float* dst = grad_geom + (size_t)cur_ent.x * 16;
             asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v0), "f"(v1), "f"(v2), "f"(v3) : "memory");
             if (LITE) {                 // slots 5..8 (opacity, r, g, b) stay zero
                 atomicAdd(dst + 4, v4);
@@ -253,8 +323,48 @@ blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __re
                 if (NCH == 4) asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(dst + 8), "f"(c2), "f"(c3) : "memory");
                 else atomicAdd(dst + 8, c2);
             }
+            }
         }
     }
+}
+
+// One Gaussian's accumulated sums as the three float4 of the fp32 record layout
+// ({mean2D.xy, conic.xx, conic.xy}, {conic.yy, opacity, r, g}, {b, colour 3, -, -}); *dirty: the record must be re-zeroed.
+template <bool DET>
+__device__ __forceinline__ void load_grad_record(const float* __restrict__ grad_geom, int64_t i, bool want_colour_opacity,
+                                                 float4& g0, float4& g1, float4& g2, bool& dirty) {
+    if (!DET) {
+        const float4* gg = reinterpret_cast<const float4*>(grad_geom + (size_t)i * 16);
+        g0 = gg[0]; g1 = gg[1]; g2 = gg[2];
+        dirty = (g0.x != 0.f) | (g0.y != 0.f) | (g0.z != 0.f) | (g0.w != 0.f) | (g1.x != 0.f) | (g1.y != 0.f) |
+                (g1.z != 0.f) | (g1.w != 0.f) | (g2.x != 0.f) | (g2.y != 0.f);
+        return;
+    }
+    const longlong2* rec = reinterpret_cast<const longlong2*>(grad_geom + (size_t)i * DET_STRIDE);
+    const longlong2 a = rec[0], b = rec[1], c = rec[2], d = rec[3];          // slots 0..7
+    const uint32_t word = (uint32_t)(unsigned long long)d.x;
+    dirty = word != 0u;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    g0 = z4; g1 = z4; g2 = z4;
+    if (!dirty) return;
+    const int em = (int)(word & 0xffu) - 128, ec = (int)((word >> 8) & 0xffu) - 128, ek = (int)((word >> 16) & 0xffu) - 128;
+    g0 = make_float4(det_read(a.x, em), det_read(a.y, em), det_read(b.x, ec), det_read(b.y, ec));
+    g1.x = det_read(c.x, ec);
+    g2.y = det_read(c.y, ek);
+    if (want_colour_opacity) {
+        const longlong2 e = rec[4], f = rec[5];                               // slots 8..11
+        g1.y = det_read(d.y, ek);
+        g1.z = det_read(e.x, ek); g1.w = det_read(e.y, ek);
+        g2.x = det_read(f.x, ek);
+    }
+}
+
+template <bool DET>
+__device__ __forceinline__ void zero_grad_record(float* __restrict__ grad_geom, int64_t i, bool want_colour_opacity) {
+    float4* gg = reinterpret_cast<float4*>(grad_geom + (size_t)i * (DET ? DET_STRIDE : 16));
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    gg[0] = zero4; gg[1] = zero4; gg[2] = zero4;
+    if (DET) { gg[3] = zero4; if (want_colour_opacity) { gg[4] = zero4; gg[5] = zero4; } }
 }
 
 // ---- shared pieces of K7' -------------------------------------------------------------------
@@ -355,6 +465,7 @@ __device__ __forceinline__ void cov3d_backward(const float dS[3][3], const float
 }
 
 // =============================== K7' (API mode) ==============================================
+template <bool DET>
 __global__ void __launch_bounds__(256)
 preprocess_backward_kernel(const __grid_constant__ CamConst cam, int64_t N,
                            const float* __restrict__ means3D, const float* __restrict__ scales,
@@ -365,10 +476,10 @@ preprocess_backward_kernel(const __grid_constant__ CamConst cam, int64_t N,
                            float* __restrict__ dL_dscales, float* __restrict__ dL_drot) {
     const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (i >= N) return;
-    float4* gg = reinterpret_cast<float4*>(grad_geom + (size_t)i * VTGS_GRAD_GEOM_FLOATS);
-    const float4 g0 = gg[0], g1 = gg[1], g2 = gg[2];
-    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    gg[0] = zero4; gg[1] = zero4; gg[2] = zero4;       // leave the scratch zeroed for the next backward
+    float4 g0, g1, g2;
+    bool dirty;
+    load_grad_record<DET>(grad_geom, i, true, g0, g1, g2, dirty);
+    if (dirty) zero_grad_record<DET>(grad_geom, i, true);       // leave the scratch zeroed for the next backward
     // visible <=> the forward wrote a record with a non-empty full rect; q1.w (hx) = -1e30 marks culled
     // culled splats (and splats whose opacity can never reach alpha >= 1/255) carry hx = -1e30:
     // nothing was blended from them, every gradient is exactly zero
@@ -398,20 +509,31 @@ preprocess_backward_kernel(const __grid_constant__ CamConst cam, int64_t N,
 
 // dynamic shared memory of blend_backward_kernel: bwd_smem_bytes(LITE)
 // per warp: splat table 1280 + cells 8192 + pixel table 768 (384 in the 3-row form) bytes
+template <bool FUSED, bool BG, bool LITE, bool DET>
+static int launch_blend_backward_det(int blocks, cudaStream_t stream, const CamConst& cam, const VtgsBuffers* buf, const GeomRecord* geom,
+                                     const float* dL_dpix, const uint32_t* order) {
+    static std::atomic<uint64_t> done{0};
+    if (first_call_on_device(done)) {
+        VTGS_CUDA_CHECK(cudaFuncSetAttribute(blend_backward_kernel<FUSED, BG, LITE, DET>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem_bytes(LITE)));
+        VTGS_CUDA_CHECK(cudaFuncSetAttribute(blend_backward_kernel<FUSED, BG, LITE, DET>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    }
+    uint32_t* scalars = buf->tile_counts + cam.gx * cam.gy + 1;         // {max |colour|, max |dL/dpixel|} bit patterns
+    if (DET) {
+        if (int e = launch_dpix_max(cam, dL_dpix, FUSED ? 4 : 3, scalars + 1, stream)) return e;
+    }
+    VTGS_PROF("blend_backward_kernel", stream);
+    blend_backward_kernel<FUSED, BG, LITE, DET><<<blocks, 32 * BWD_WARPS, bwd_smem_bytes(LITE), stream>>>(
+        cam, buf->tile_ranges, reinterpret_cast<const uint2*>(buf->region_pairs), buf->region_cnt, buf->region_masks, buf->region_done,
+        geom, buf->final_T, dL_dpix, buf->grad_geom, order, scalars);
+    VTGS_LAUNCH_CHECK();
+    return VTGS_OK;
+}
+
 template <bool FUSED, bool BG, bool LITE>
 static int launch_blend_backward(int blocks, cudaStream_t stream, const CamConst& cam, const VtgsBuffers* buf, const GeomRecord* geom,
                                  const float* dL_dpix, const uint32_t* order) {
-    static std::atomic<uint64_t> done{0};
-    if (first_call_on_device(done)) {
-        VTGS_CUDA_CHECK(cudaFuncSetAttribute(blend_backward_kernel<FUSED, BG, LITE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem_bytes(LITE)));
-        VTGS_CUDA_CHECK(cudaFuncSetAttribute(blend_backward_kernel<FUSED, BG, LITE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    }
-    VTGS_PROF("blend_backward_kernel", stream);
-    blend_backward_kernel<FUSED, BG, LITE><<<blocks, 32 * BWD_WARPS, bwd_smem_bytes(LITE), stream>>>(
-        cam, buf->tile_ranges, reinterpret_cast<const uint2*>(buf->region_pairs), buf->region_cnt, buf->region_masks, buf->region_done,
-        geom, buf->final_T, dL_dpix, buf->grad_geom, order);
-    VTGS_LAUNCH_CHECK();
-    return VTGS_OK;
+    return (buf->flags & VTGS_BUF_DETERMINISTIC) ? launch_blend_backward_det<FUSED, BG, LITE, true>(blocks, stream, cam, buf, geom, dL_dpix, order)
+                                                 : launch_blend_backward_det<FUSED, BG, LITE, false>(blocks, stream, cam, buf, geom, dL_dpix, order);
 }
 
 int launch_backward(const VtgsCamera* camera, int64_t N,
@@ -432,9 +554,15 @@ int launch_backward(const VtgsCamera* camera, int64_t N,
         if (int e = has_bg ? launch_blend_backward<false, true, false>(blocks, stream, cam, buf, geom, dL_dout_color, order)
                            : launch_blend_backward<false, false, false>(blocks, stream, cam, buf, geom, dL_dout_color, order)) return e;
     }
-    { VTGS_PROF("preprocess_backward_kernel", stream); preprocess_backward_kernel<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(cam, N, means3D, scales, rotations, nullptr, geom,
-                                                                               buf->grad_geom, dL_dmeans2D, dL_dcolors, dL_dopacity,
-                                                                               dL_dmeans3D, dL_dscales, dL_drotations); }
+    if (buf->flags & VTGS_BUF_DETERMINISTIC) {
+        VTGS_PROF("preprocess_backward_kernel", stream);
+        preprocess_backward_kernel<true><<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(cam, N, means3D, scales, rotations, nullptr, geom, buf->grad_geom, dL_dmeans2D,
+                                                                                          dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dscales, dL_drotations);
+    } else {
+        VTGS_PROF("preprocess_backward_kernel", stream);
+        preprocess_backward_kernel<false><<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(cam, N, means3D, scales, rotations, nullptr, geom, buf->grad_geom, dL_dmeans2D,
+                                                                                           dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dscales, dL_drotations);
+    }
     VTGS_LAUNCH_CHECK();
     return VTGS_OK;
 }
@@ -519,21 +647,23 @@ __device__ __forceinline__ void pose_finalize_block(const float* __restrict__ pa
 struct K7Item {
     float4 g0, g1, g2, uq;
     float hx, op, px, py, pz, ls;
+    bool dirty;
 };
 
+template <bool DET>
 __device__ __forceinline__ void k7_load(K7Item& it, int64_t i, const VtgsParams& prm, const GeomRecord* __restrict__ geom,
                                         const float* __restrict__ grad_geom, bool rot_aligned, const uint32_t* __restrict__ tiles_touched,
-                                        bool want_op) {
+                                        bool want_op, bool want_colour_opacity) {
     // a Gaussian with no tile in this rank's band (tile-band sharding) or culled received no gradient here:
     // 4 bytes decide that instead of ~190
     if (tiles_touched != nullptr && tiles_touched[i] == 0u) {
         const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
         it.g0 = z4; it.g1 = z4; it.g2 = z4; it.uq = z4;
         it.hx = -1e30f; it.op = 0.f; it.px = 0.f; it.py = 0.f; it.pz = 0.f; it.ls = 0.f;
+        it.dirty = false;
         return;
     }
-    const float4* gg = reinterpret_cast<const float4*>(grad_geom + (size_t)i * VTGS_GRAD_GEOM_FLOATS);
-    it.g0 = gg[0]; it.g1 = gg[1]; it.g2 = gg[2];
+    load_grad_record<DET>(grad_geom, i, want_colour_opacity, it.g0, it.g1, it.g2, it.dirty);
     // a culled splat is in no list, so its sums are zero: only dL/dlogit needs the record (the activated opacity)
     it.hx = 0.0f;
     it.op = want_op ? geom[i].q1.w : 0.0f;
@@ -545,7 +675,7 @@ __device__ __forceinline__ void k7_load(K7Item& it, int64_t i, const VtgsParams&
 }
 
 // SHAPE = false (tracking: no dL/dlog_scale, dL/dquaternion wanted) drops the cov3D chain at compile time.
-template <bool SHAPE>
+template <bool SHAPE, bool DET>
 __global__ void __launch_bounds__(256, 2)
 fused_preprocess_backward_kernel(const __grid_constant__ CamConst cam, int64_t N, VtgsParams prm,
                                  const float* __restrict__ pose_Rt, float dr0, float dr1, float dr2,
@@ -568,17 +698,15 @@ fused_preprocess_backward_kernel(const __grid_constant__ CamConst cam, int64_t N
     for (int k = 0; k < 16; ++k) pose_v[k] = 0.0f;
 
     const bool want_op = out.logit_opacities != nullptr;
+    // the blend kernel formed the colour / opacity sums unless it ran in its pose-only form (same condition as there)
+    const bool want_colour_opacity = out.rgb_colors != nullptr || out.logit_opacities != nullptr;
     auto process = [&](const K7Item& it, const int64_t i) {
         const float4 g0 = it.g0, g1 = it.g1, g2 = it.g2;
         // culled splats, and splats no pixel blended (all sums exactly zero), have zero gradients: every
         // term below is linear in g0..g2
         const bool any_grad = (g0.x != 0.f) | (g0.y != 0.f) | (g0.z != 0.f) | (g0.w != 0.f) | (g1.x != 0.f) | (g1.y != 0.f) |
                               (g1.z != 0.f) | (g1.w != 0.f) | (g2.x != 0.f) | (g2.y != 0.f);
-        if (any_grad) {                                   // leave the scratch zeroed for the next backward
-            float4* gg = reinterpret_cast<float4*>(grad_geom + (size_t)i * VTGS_GRAD_GEOM_FLOATS);
-            const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            gg[0] = zero4; gg[1] = zero4; gg[2] = zero4;
-        }
+        if (it.dirty) zero_grad_record<DET>(grad_geom, i, want_colour_opacity);     // leave the scratch zeroed for the next backward
         const bool visible = it.hx > -1e29f && any_grad;
         float dmeanw[3] = {0.f, 0.f, 0.f}, dls = 0.f, dlogit = 0.f, dqu[4] = {0.f, 0.f, 0.f, 0.f};
         if (visible) {
@@ -641,7 +769,7 @@ fused_preprocess_backward_kernel(const __grid_constant__ CamConst cam, int64_t N
             const int64_t i = (int64_t)cand[trip] * 256 + tid;
             if (i >= N) continue;
             K7Item it;
-            k7_load(it, i, prm, geom, grad_geom, rot_aligned, tiles_touched, want_op);
+            k7_load<DET>(it, i, prm, geom, grad_geom, rot_aligned, tiles_touched, want_op, want_colour_opacity);
             process(it, i);
         }
         const bool any_out = out.means3D != nullptr || out.rgb_colors != nullptr || out.unnorm_rotations != nullptr ||
@@ -652,6 +780,7 @@ fused_preprocess_backward_kernel(const __grid_constant__ CamConst cam, int64_t N
             const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
             zit.g0 = z4; zit.g1 = z4; zit.g2 = z4; zit.uq = z4;
             zit.hx = -1e30f; zit.op = 0.f; zit.px = 0.f; zit.py = 0.f; zit.pz = 0.f; zit.ls = 0.f;
+            zit.dirty = false;
             for (int64_t b = blockIdx.x; b < nblk; b += gridDim.x) {
                 const int64_t i = b * 256 + tid;
                 if (band_flags[b] == 0 && i < N) process(zit, i);
@@ -660,10 +789,10 @@ fused_preprocess_backward_kernel(const __grid_constant__ CamConst cam, int64_t N
     } else {
         int64_t i = (int64_t)blockIdx.x * 256 + tid;
         K7Item nxt;
-        if (i < N) k7_load(nxt, i, prm, geom, grad_geom, rot_aligned, tiles_touched, want_op);
+        if (i < N) k7_load<DET>(nxt, i, prm, geom, grad_geom, rot_aligned, tiles_touched, want_op, want_colour_opacity);
         for (; i < N; i += stride) {
             const K7Item it = nxt;
-            if (i + stride < N) k7_load(nxt, i + stride, prm, geom, grad_geom, rot_aligned, tiles_touched, want_op);
+            if (i + stride < N) k7_load<DET>(nxt, i + stride, prm, geom, grad_geom, rot_aligned, tiles_touched, want_op, want_colour_opacity);
             process(it, i);
         }
     }
@@ -720,16 +849,18 @@ int launch_fused_backward(const VtgsCamera* camera, const VtgsParams* params, co
         const uint8_t* band_flags = use_cand ? buf->band_flags : nullptr;
         const uint32_t* band_cand = use_cand ? buf->band_cand : nullptr;
         const uint32_t* n_cand = buf->tile_counts + cam.gx * cam.gy;
-        if (grads->log_scales != nullptr || grads->unnorm_rotations != nullptr) {
+        const bool shape = grads->log_scales != nullptr || grads->unnorm_rotations != nullptr;
+        const bool det = (buf->flags & VTGS_BUF_DETERMINISTIC) != 0;
+        {
             VTGS_PROF("fused_preprocess_backward_kernel", stream);
-            fused_preprocess_backward_kernel<true><<<blocks, 256, 0, stream>>>(cam, N, *params, buf->counters->pose_R, pose->depth_row[0], pose->depth_row[1],
-                                                                               pose->depth_row[2], geom, buf->grad_geom, *grads, accumulate, want_pose,
-                                                                               buf->counters, ticket, band_touch, band_flags, band_cand, n_cand);
-        } else {
-            VTGS_PROF("fused_preprocess_backward_kernel", stream);
-            fused_preprocess_backward_kernel<false><<<blocks, 256, 0, stream>>>(cam, N, *params, buf->counters->pose_R, pose->depth_row[0], pose->depth_row[1],
-                                                                                pose->depth_row[2], geom, buf->grad_geom, *grads, accumulate, want_pose,
-                                                                                buf->counters, ticket, band_touch, band_flags, band_cand, n_cand);
+#define VTGS_K7_LAUNCH(SHAPE_, DET_)                                                                                                             \
+    fused_preprocess_backward_kernel<SHAPE_, DET_><<<blocks, 256, 0, stream>>>(cam, N, *params, buf->counters->pose_R, pose->depth_row[0],         \
+                                                                               pose->depth_row[1], pose->depth_row[2], geom, buf->grad_geom, *grads, \
+                                                                               accumulate, want_pose, buf->counters, ticket, band_touch, band_flags, \
+                                                                               band_cand, n_cand)
+            if (shape) { if (det) VTGS_K7_LAUNCH(true, true); else VTGS_K7_LAUNCH(true, false); }
+            else { if (det) VTGS_K7_LAUNCH(false, true); else VTGS_K7_LAUNCH(false, false); }
+#undef VTGS_K7_LAUNCH
         }
         VTGS_LAUNCH_CHECK();
     } else if (want_pose && !accumulate) {

@@ -156,8 +156,9 @@ preprocess_kernel(const __grid_constant__ CamConst cam, int64_t N, FrontEnd fe,
                   const float* __restrict__ colors,
                   GeomRecord* __restrict__ geom, int32_t* __restrict__ radii,
                   uint32_t* __restrict__ tiles_touched, uint32_t* __restrict__ tile_counts,
-                  const uint32_t* __restrict__ cand, const uint32_t* __restrict__ n_cand) {
+                  const uint32_t* __restrict__ cand, const uint32_t* __restrict__ n_cand, uint32_t* __restrict__ colour_max_bits) {
     // Persistent loop over 256-Gaussian blocks: all of them, or (tile bands) the candidate blocks K0' listed.
+    float cmax = 0.0f;          // max |colour| over the splats this thread emitted (deterministic backward: bound of c . dL/dpixel)
     const int tid = threadIdx.x;
     const int64_t nblk = cand != nullptr ? (int64_t)*n_cand : (N + 255) / 256;
     const bool rot_aligned = (reinterpret_cast<uintptr_t>(rotations) & 15) == 0;
@@ -266,6 +267,7 @@ preprocess_kernel(const __grid_constant__ CamConst cam, int64_t N, FrontEnd fe,
                 rec.q3 = make_float4(g.depth, pthr, __uint_as_float((uint32_t)g.minx | ((uint32_t)miny << 16)),
                                      __uint_as_float((uint32_t)g.maxx | ((uint32_t)(hgt > 0 ? maxy : miny) << 16)));
                 w_minx = g.minx; w_maxx = g.maxx; w_miny = miny; w_maxy = hgt > 0 ? maxy : miny;
+                cmax = fmaxf(cmax, fmaxf(fmaxf(fabsf(it.c0), fabsf(it.c1)), fmaxf(fabsf(it.c2), fabsf(c3))));
             } else {
                 rec.q0 = make_float4(0.f, 0.f, -1e30f, -1e30f);
                 rec.q1 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -296,6 +298,11 @@ preprocess_kernel(const __grid_constant__ CamConst cam, int64_t N, FrontEnd fe,
             }
         }
         i = i_next;
+    }
+    if (colour_max_bits != nullptr) {                     // non-negative floats order like their bit patterns
+        uint32_t b = __float_as_uint(cmax);
+        b = __reduce_max_sync(VTGS_FULL_MASK, b);
+        if ((tid & 31) == 0 && b != 0u) atomicMax(colour_max_bits, b);
     }
 }
 
@@ -1093,7 +1100,7 @@ int launch_forward(const VtgsCamera* camera, int64_t N, bool fused, const FrontE
     if (cam.gx > 0xffff || cam.gy > 0xffff) { set_error("image too large for packed tile rects"); return VTGS_E_INVALID; }
     if (N >= (int64_t)1 << 24) { set_error("at most 2^24 - 1 Gaussians per render (24-bit id in the sort key)"); return VTGS_E_UNSUPPORTED; }
     GeomRecord* geom = reinterpret_cast<GeomRecord*>(buf->geom);
-    VTGS_CUDA_CHECK(cudaMemsetAsync(buf->tile_counts, 0, sizeof(uint32_t) * (num_tiles + 1), stream));     // + the candidate-list counter
+    VTGS_CUDA_CHECK(cudaMemsetAsync(buf->tile_counts, 0, sizeof(uint32_t) * (num_tiles + 3), stream));     // + the candidate-list counter, max |colour|, max |dL/dpixel|
     const int blocks = (int)((N + 255) / 256);
     const int k1_blocks = blocks < 148 * 6 ? blocks : 148 * 6;          // persistent: 3 resident blocks per SM x 2 waves
     const bool band_active = cam.row0 > 0 || cam.row1 < cam.gy;
@@ -1101,6 +1108,7 @@ int launch_forward(const VtgsCamera* camera, int64_t N, bool fused, const FrontE
     const bool use_cand = fused && band_active && N > 0 && buf->band_flags != nullptr && buf->band_cand != nullptr;
     const uint32_t* cand = use_cand ? buf->band_cand : nullptr;
     uint32_t* n_cand = buf->tile_counts + num_tiles;
+    uint32_t* cmax_bits = (buf->flags & VTGS_BUF_DETERMINISTIC) ? buf->tile_counts + num_tiles + 1 : nullptr;
     const int persistent = 148 * 3;
     if (N > 0) {
         const bool narrow_band = (cam.row1 - cam.row0) * 5 < cam.gy * 2;
@@ -1111,12 +1119,12 @@ int launch_forward(const VtgsCamera* camera, int64_t N, bool fused, const FrontE
         const int k1_grid = use_cand ? std::min(blocks, persistent) : k1_blocks;
         if (fused && narrow_band)
             { VTGS_PROF("preprocess_kernel", stream); preprocess_kernel<true, true><<<k1_grid, 256, 0, stream>>>(cam, N, fe, means3D, scales, rotations, opacities, colors,
-                                                                 geom, radii, buf->tiles_touched, buf->tile_counts, cand, n_cand); }
+                                                                 geom, radii, buf->tiles_touched, buf->tile_counts, cand, n_cand, cmax_bits); }
         else if (fused)
             { VTGS_PROF("preprocess_kernel", stream); preprocess_kernel<true><<<k1_grid, 256, 0, stream>>>(cam, N, fe, means3D, scales, rotations, opacities, colors,
-                                                                 geom, radii, buf->tiles_touched, buf->tile_counts, cand, n_cand); }
+                                                                 geom, radii, buf->tiles_touched, buf->tile_counts, cand, n_cand, cmax_bits); }
         else { VTGS_PROF("preprocess_kernel", stream); preprocess_kernel<false><<<k1_grid, 256, 0, stream>>>(cam, N, fe, means3D, scales, rotations, opacities, colors,
-                                                                  geom, radii, buf->tiles_touched, buf->tile_counts, nullptr, nullptr); }
+                                                                  geom, radii, buf->tiles_touched, buf->tile_counts, nullptr, nullptr, cmax_bits); }
         VTGS_LAUNCH_CHECK();
     }
     // only the band's tiles hold counts (tile-band sharding: K1' clips every rect to the band); the fused solvers never

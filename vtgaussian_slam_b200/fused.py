@@ -30,7 +30,7 @@ class FusedRenderer:
     `reserve_pairs` to grow."""
 
     def __init__(self, settings, num_gaussians, device="cuda:0", pair_capacity=None, tile_rows=(0, 0),
-                 depth_row=(0.0, 0.0, 1.0, 0.0)):
+                 depth_row=(0.0, 0.0, 1.0, 0.0), deterministic=None):
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("FusedRenderer needs a CUDA device: vtgaussian_slam_b200 has no CPU fallback")
@@ -40,7 +40,8 @@ class FusedRenderer:
             # R / N observed on this device so far (view-tied sections: ~2 tiles per Gaussian), with head room; a
             # renderer that still overflows is grown by ensure_capacity() and the forward repeated
             pair_capacity = int(self.N * max(6.0, 1.5 * _PAIR_RATIO.get(self.device, 0.0))) + 65536
-        self.ws = Workspace(self.device, self.W, self.H, self.N, pair_capacity)
+        # deterministic: fixed-point gradient accumulation (rasterizer.set_deterministic is the default when None)
+        self.ws = Workspace(self.device, self.W, self.H, self.N, pair_capacity, deterministic=deterministic)
         self.ws.ensure_grad_geom()
         self.depth_row = tuple(float(v) for v in depth_row)
         L = _lib.lib()
@@ -284,11 +285,12 @@ class TrackingSolver:
     def __init__(self, settings, params, device="cuda:0", lr_rot=4e-4, lr_trans=2e-3, w_im=0.5, w_depth=0.025,
                  use_sil_for_loss=True, sil_thres=0.99, tile_rows=(0, 0), pair_capacity=None, use_graph=True,
                  process_group=None, ignore_outlier_depth_loss=False, far_depth_thres=0.0, replica_sil_search=False,
-                 book_post_step=True):
+                 book_post_step=True, deterministic=None):
         self.device = torch.device(device)
         self.params = {k: params[k].detach().to(self.device).float().contiguous() for k in PARAM_KEYS}
         N = self.params["means3D"].shape[0]
-        self.r = FusedRenderer(settings, N, device=self.device, tile_rows=tile_rows, pair_capacity=pair_capacity)
+        self.r = FusedRenderer(settings, N, device=self.device, tile_rows=tile_rows, pair_capacity=pair_capacity,
+                               deterministic=deterministic)
         self.cfg = dict(w_im=w_im, w_depth=w_depth, use_sil_for_loss=use_sil_for_loss, sil_thres=sil_thres,
                         ignore_outlier_depth_loss=ignore_outlier_depth_loss, far_depth_thres=far_depth_thres)
         self.replica_sil_search = bool(replica_sil_search) and bool(use_sil_for_loss)
@@ -462,12 +464,13 @@ class MappingSolver:
         to its pose after the step (:2706-2727)."""
 
     def __init__(self, settings, params, device="cuda:0", lrs=None, eps=1e-15, pair_capacity=None, process_group=None,
-                 global_params=None, poll_every=16):
+                 global_params=None, poll_every=16, deterministic=None):
         self.device = torch.device(device)
         self.params = {k: params[k].detach().to(self.device).float().contiguous() for k in PARAM_KEYS}
         N = self.params["means3D"].shape[0]
         self.settings = settings
-        self.r = FusedRenderer(settings, N, device=self.device, pair_capacity=pair_capacity)
+        self.deterministic = deterministic
+        self.r = FusedRenderer(settings, N, device=self.device, pair_capacity=pair_capacity, deterministic=deterministic)
         self.lrs = dict(rgb_colors=0.0025, logit_opacities=0.05, log_scales=0.005) if lrs is None else dict(lrs)
         self.pose_lrs = (float(self.lrs.pop("cam_unnorm_rots", 0.0)), float(self.lrs.pop("cam_trans", 0.0)))
         self.lrs = {k: v for k, v in self.lrs.items() if k in PARAM_KEYS and v != 0.0}
@@ -497,7 +500,7 @@ class MappingSolver:
             raise ValueError("global_params must hold the frozen sections followed by the trainable Gaussians")
         self.gparams = gp
         self._global_aliases = all(gp[k][Ng - N:].data_ptr() == self.params[k].data_ptr() for k in PARAM_KEYS)
-        self.r_global = FusedRenderer(self.settings, Ng, device=self.device)
+        self.r_global = FusedRenderer(self.settings, Ng, device=self.device, deterministic=self.deterministic)
         self.ggrads = {k: torch.zeros_like(gp[k]) for k in self.lrs}
 
     def _render_backward(self, r, params, kf, grads, accumulate, loss_fn, w_im, w_depth, pose):

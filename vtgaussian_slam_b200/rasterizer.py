@@ -92,12 +92,25 @@ def _ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+_DETERMINISTIC = os.environ.get("VTGS_DETERMINISTIC", "0") not in ("", "0")
+
+
+def set_deterministic(on: bool):
+    """Process-wide default of the backward's gradient accumulation (VTGS_BUF_DETERMINISTIC, include/vtgs.h): 64-bit
+    fixed-point sums, bitwise reproducible run to run and across ranks, instead of fp32 atomics of arbitrary order.
+    Takes effect for workspaces whose own `deterministic` is None, at their next forward (captured CUDA graphs keep
+    what they were captured with).  Also settable with the environment variable VTGS_DETERMINISTIC=1."""
+    global _DETERMINISTIC
+    _DETERMINISTIC = bool(on)
+
+
 class Workspace:
     """Device buffers of one forward (VtgsBuffers), owned as torch tensors.  Pair buffers grow
     geometrically; `grad_geom` must be zero on entry to a backward and is left zeroed by it."""
 
-    def __init__(self, device, width, height, n, pair_capacity):
+    def __init__(self, device, width, height, n, pair_capacity, deterministic=None):
         self.device, self.W, self.H, self.N = device, int(width), int(height), int(n)
+        self.deterministic = deterministic                 # None: follow set_deterministic()
         sz = _lib.VtgsWorkspaceSizes()
         _lib.check(_lib.lib().vtgs_workspace_query(self.W, self.H, self.N, int(pair_capacity), C.byref(sz)))
         u8 = dict(dtype=torch.uint8, device=device)
@@ -155,6 +168,8 @@ class Workspace:
         b.band_flags = self.band_flags.data_ptr()
         b.band_cand = self.band_cand.data_ptr()
         b.tile_order = self.tile_order.data_ptr()
+        det = _DETERMINISTIC if self.deterministic is None else self.deterministic
+        b.flags = _lib.BUF_DETERMINISTIC if det else 0
         return b
 
     def read_counters(self):
