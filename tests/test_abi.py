@@ -33,7 +33,7 @@ def test_every_declared_symbol_is_exported(L):
 def test_struct_layouts_match_the_header(L):
     assert C.sizeof(_lib.VtgsCamera) == 4 * (2 + 2 + 16 + 16 + 3 + 1 + 1 + 2)
     assert C.sizeof(_lib.VtgsCounters) == 4 * (4 + 9 + 3 + 4 + 2 + 10)
-    assert C.sizeof(_lib.VtgsBuffers) == 8 * 18
+    assert C.sizeof(_lib.VtgsBuffers) == 8 * 19            # 18 pointers / sizes + flags, reserved
     assert C.sizeof(_lib.VtgsParams) == 8 * 5 + 8 + 8
     assert C.sizeof(_lib.VtgsPose) == 16 + 16
     assert C.sizeof(_lib.VtgsLossConfig) == 32 + 8 + 8 + 8
