@@ -142,16 +142,17 @@ typedef struct VtgsBuffers {
     uint32_t      reserved;
 } VtgsBuffers;
 
-/* VtgsBuffers.flags.  VTGS_BUF_DETERMINISTIC: the backward blend accumulates its per-(region, splat) partial sums into
- * grad_geom as 64-bit FIXED-POINT integers (integer addition is associative, so the order in which the tiles' warps
- * arrive does not matter) instead of fp32 `red.global.add`: every gradient of the backward is then bitwise reproducible
- * run to run and across ranks.  The power-of-two scale is chosen per Gaussian and per quantity from a rigorous bound of
- * the sum (max |dL/dpixel| and max |colour| measured on the device, the splat's opacity / conic / extent), so nothing can
- * overflow and at least ~30 bits stay below the bound's leading bit.  Upstream: global float atomics in arbitrary order. */
+/* VtgsBuffers.flags.  VTGS_BUF_DETERMINISTIC: the backward blend splits every per-(region, splat) partial sum into a
+ * coarse and a fine part on per-Gaussian power-of-two grids before the fp32 `red.global.add` into grad_geom.  Sums of
+ * grid multiples that stay below 2^24 grid steps are EXACT in fp32, hence independent of the order in which the tiles'
+ * warps arrive: every gradient of the backward is then bitwise reproducible run to run and across ranks, with the same
+ * number of memory operations as without the flag.  The grids come from rigorous bounds of the sums (max |dL/dpixel| and
+ * max |colour| measured on the device, the splat's opacity / conic / extent / tile count), so the exactness conditions
+ * cannot be violated; 22 + (21 - log2 tiles) bits lie below the bound.  Upstream: float atomics in arbitrary order. */
 #define VTGS_BUF_DETERMINISTIC 1u
 
 #define VTGS_GEOM_RECORD_BYTES 64
-#define VTGS_GRAD_GEOM_FLOATS  32   /* 16 floats per Gaussian without, 16 int64 with VTGS_BUF_DETERMINISTIC */
+#define VTGS_GRAD_GEOM_FLOATS  32   /* records of 16 floats without, 32 (20 used) with VTGS_BUF_DETERMINISTIC */
 
 typedef struct VtgsWorkspaceSizes {
     uint64_t geom_bytes;

@@ -62,24 +62,30 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[16], int lane)
 
 
 // ---- deterministic accumulation (VTGS_BUF_DETERMINISTIC, include/vtgs.h) --------------------------------------------
-// grad_geom record of a Gaussian in this mode: 16 int64 slots --
-//   [0,1] dL/dmean2D  [2,3,4] dL/dconic  [5] dL/d(colour 3: the depth channel)  [6] low word: the three exponents
-//   [7] dL/dopacity   [8,9,10] dL/d(r, g, b)
-// (what the pose-only instantiation touches sits in the first 64 bytes).  A value v of a quantity whose per-Gaussian sum
-// is bounded by B < 2^e is added as the integer round(v * 2^(61 - e)): integer addition is associative, so the sums do
-// not depend on the order in which the warps of different tiles and regions arrive.
-constexpr int DET_STRIDE = 32;        // floats per record (= 16 int64)
-constexpr int DET_EXP_WORD = 12;      // uint32 index of the exponent word (slot 6)
+// Every partial sum v of a quantity whose per-Gaussian total of |v| is bounded by B < 2^e is split into
+//   hi = v rounded to a multiple of q_hi = 2^(e - 22),   lo = (v - hi) rounded to a multiple of q_lo = q_hi 2^(-s_lo)
+// and the two are accumulated with the ordinary fp32 vector reductions.  Sums of multiples of q that stay below 2^24 q
+// are EXACT in fp32, so they do not depend on the order in which the warps of different tiles and regions arrive:
+// |sum hi| <= B + (#partials) q_hi / 2 < 2^24 q_hi, and |sum lo| <= (#partials) q_hi / 2 < 2^24 q_lo with
+// s_lo = 21 - ceil(log2(tiles)) (at most 8 partials per tile).  K7' adds hi + lo: 22 + s_lo bits below the bound.
+// grad_geom record in this mode (32-float stride):
+//   [0..3] hi{mean2D.x, mean2D.y, conic.xx, conic.xy}   [4..7] hi{conic.yy, colour 3}, lo{mean2D.x, mean2D.y}
+//   [8..11] lo{conic.xx, conic.xy, conic.yy, colour 3}  [12..15] hi{opacity, r, g, b}   [16..19] lo{opacity, r, g, b}
+// (the pose-only instantiation touches the first 48 bytes: three vector reductions per partial, as many memory
+// operations as without the flag).
+constexpr int DET_STRIDE = 32;        // floats per record
 
 __device__ __forceinline__ int det_exponent(float bound) {          // smallest e (clamped) with bound < 2^e
     const int e = (int)((__float_as_uint(bound) >> 23) & 0xffu) - 126;
-    return min(max(e, -60), 120);
+    return min(max(e, -80), 100);
 }
 __device__ __forceinline__ float det_pow2(int s) { return __uint_as_float((uint32_t)(s + 127) << 23); }   // 2^s, s in [-126, 127]
-__device__ __forceinline__ void det_add(float* rec, int slot, float v, float scale) {
-    atomicAdd(reinterpret_cast<unsigned long long*>(rec) + slot, (unsigned long long)__float2ll_rn(v * scale));
+// v -> (hi, lo) on the grids of exponent e: c_hi = 3 * 2^e (rounds to multiples of 2^(e-22)), c_lo = 3 * 2^(e - s_lo)
+__device__ __forceinline__ float2 det_split(float v, float c_hi, float c_lo) {
+    const float hi = __fsub_rn(__fadd_rn(v, c_hi), c_hi);
+    const float r = __fsub_rn(v, hi);                                 // exact
+    return make_float2(hi, __fsub_rn(__fadd_rn(r, c_lo), c_lo));
 }
-__device__ __forceinline__ float det_read(long long q, int e) { return (float)((double)q * (double)det_pow2(e - 61)); }
 
 // max |dL/dpixel| over the band's rows and the NCH planes -> *out_bits (atomicMax on the bit pattern; zeroed by the forward)
 __global__ void __launch_bounds__(256)
@@ -287,10 +293,11 @@ blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __re
             const float v1 = -half_h * o * (cc * sy + cb * sx);
             const float v2 = -0.5f * o * sxx, v3 = -0.5f * o * sxy, v4 = -0.5f * o * syy;
             if (DET) {
-                // bounds of this Gaussian's sums over ALL its partials (every partial derives the same three exponents):
-                // |g0| <= |dL/dalpha| <= 2 max|c| sum_ch |dL/dpix| (+ the background term), |w| <= 1, the splat's blended
-                // pixels lie within its alpha >= 1/255 box (half extents hx, hy of the record)
-                const float4 q0 = geom[cur_ent.x].q0;
+                // bounds of this Gaussian's sums of |partial| over ALL its partials (every partial derives the same three
+                // grids): |g0| <= |dL/dalpha| <= 2 max|c| sum_ch |dL/dpix| (+ the background term), |w| <= 1, the splat's
+                // blended pixels lie within its alpha >= 1/255 box (half extents hx, hy of the record)
+                const GeomRecord* rec = geom + cur_ent.x;
+                const float4 q0 = rec->q0, q3 = rec->q3;
                 const float cmax = __uint_as_float(__ldg(det_scalars)), dmax = __uint_as_float(__ldg(det_scalars + 1));
                 const float d1 = (float)NCH * dmax;
                 float g0max = 2.0f * cmax * d1;
@@ -302,15 +309,22 @@ blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __re
                 const float bc = 0.5f * o * S * fmaxf(ex, ey) * fmaxf(ex, ey);
                 const float bk = npix * fmaxf(d1, g0max);
                 const int em = det_exponent(bm), ec = det_exponent(bc), ek = det_exponent(bk);
+                const uint32_t rmin = __float_as_uint(q3.z), rmax = __float_as_uint(q3.w);
+                const int tiles = max(1, (int)((rmax & 0xffffu) - (rmin & 0xffffu)) * (int)((rmax >> 16) - (rmin >> 16)));
+                const int s_lo = max(1, 21 - (32 - __clz(tiles - 1)));                  // 21 - ceil(log2(tiles))
+                const float hm = 3.0f * det_pow2(em), hc = 3.0f * det_pow2(ec), hk = 3.0f * det_pow2(ek), ls = det_pow2(-s_lo);
+                const float2 a0 = det_split(v0, hm, hm * ls), a1 = det_split(v1, hm, hm * ls);
+                const float2 a2 = det_split(v2, hc, hc * ls), a3 = det_split(v3, hc, hc * ls), a4 = det_split(v4, hc, hc * ls);
+                const float2 a5 = det_split(NCH == 4 ? c3 : 0.0f, hk, hk * ls);
                 float* dst = grad_geom + (size_t)cur_ent.x * DET_STRIDE;
-                reinterpret_cast<uint32_t*>(dst)[DET_EXP_WORD] = (uint32_t)(em + 128) | ((uint32_t)(ec + 128) << 8) | ((uint32_t)(ek + 128) << 16) | (1u << 24);
-                const float fm = det_pow2(61 - em), fc = det_pow2(61 - ec), fk = det_pow2(61 - ek);
-                det_add(dst, 0, v0, fm); det_add(dst, 1, v1, fm);
-                det_add(dst, 2, v2, fc); det_add(dst, 3, v3, fc); det_add(dst, 4, v4, fc);
-                if (NCH == 4) det_add(dst, 5, c3, fk);
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a0.x), "f"(a1.x), "f"(a2.x), "f"(a3.x) : "memory");
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(a4.x), "f"(a5.x), "f"(a0.y), "f"(a1.y) : "memory");
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 8), "f"(a2.y), "f"(a3.y), "f"(a4.y), "f"(a5.y) : "memory");
                 if (!LITE) {
-                    det_add(dst, 7, s0, fk);
-                    det_add(dst, 8, c0, fk); det_add(dst, 9, c1, fk); det_add(dst, 10, c2, fk);
+                    const float2 b0 = det_split(s0, hk, hk * ls), b1 = det_split(c0, hk, hk * ls), b2 = det_split(c1, hk, hk * ls),
+                                 b3 = det_split(c2, hk, hk * ls);
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 12), "f"(b0.x), "f"(b1.x), "f"(b2.x), "f"(b3.x) : "memory");
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 16), "f"(b0.y), "f"(b1.y), "f"(b2.y), "f"(b3.y) : "memory");
                 }
             } else {
             float* dst = grad_geom + (size_t)cur_ent.x * 16;
@@ -340,23 +354,17 @@ __device__ __forceinline__ void load_grad_record(const float* __restrict__ grad_
                 (g1.z != 0.f) | (g1.w != 0.f) | (g2.x != 0.f) | (g2.y != 0.f);
         return;
     }
-    const longlong2* rec = reinterpret_cast<const longlong2*>(grad_geom + (size_t)i * DET_STRIDE);
-    const longlong2 a = rec[0], b = rec[1], c = rec[2], d = rec[3];          // slots 0..7
-    const uint32_t word = (uint32_t)(unsigned long long)d.x;
-    dirty = word != 0u;
+    const float4* rec = reinterpret_cast<const float4*>(grad_geom + (size_t)i * DET_STRIDE);
+    const float4 a = rec[0], b = rec[1], c = rec[2];
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    g0 = z4; g1 = z4; g2 = z4;
-    if (!dirty) return;
-    const int em = (int)(word & 0xffu) - 128, ec = (int)((word >> 8) & 0xffu) - 128, ek = (int)((word >> 16) & 0xffu) - 128;
-    g0 = make_float4(det_read(a.x, em), det_read(a.y, em), det_read(b.x, ec), det_read(b.y, ec));
-    g1.x = det_read(c.x, ec);
-    g2.y = det_read(c.y, ek);
-    if (want_colour_opacity) {
-        const longlong2 e = rec[4], f = rec[5];                               // slots 8..11
-        g1.y = det_read(d.y, ek);
-        g1.z = det_read(e.x, ek); g1.w = det_read(e.y, ek);
-        g2.x = det_read(f.x, ek);
-    }
+    float4 d = z4, e = z4;
+    if (want_colour_opacity) { d = rec[3]; e = rec[4]; }
+    auto nz = [](const float4& v) { return (v.x != 0.f) | (v.y != 0.f) | (v.z != 0.f) | (v.w != 0.f); };
+    dirty = nz(a) | nz(b) | nz(c) | nz(d) | nz(e);
+    auto sum = [](float hi, float lo) { return (float)((double)hi + (double)lo); };
+    g0 = make_float4(sum(a.x, b.z), sum(a.y, b.w), sum(a.z, c.x), sum(a.w, c.y));
+    g1 = make_float4(sum(b.x, c.z), sum(d.x, e.x), sum(d.y, e.y), sum(d.z, e.z));
+    g2 = make_float4(sum(d.w, e.w), sum(b.y, c.w), 0.f, 0.f);
 }
 
 template <bool DET>
@@ -364,7 +372,7 @@ __device__ __forceinline__ void zero_grad_record(float* __restrict__ grad_geom, 
     float4* gg = reinterpret_cast<float4*>(grad_geom + (size_t)i * (DET ? DET_STRIDE : 16));
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     gg[0] = zero4; gg[1] = zero4; gg[2] = zero4;
-    if (DET) { gg[3] = zero4; if (want_colour_opacity) { gg[4] = zero4; gg[5] = zero4; } }
+    if (DET && want_colour_opacity) { gg[3] = zero4; gg[4] = zero4; }
 }
 
 // ---- shared pieces of K7' -------------------------------------------------------------------

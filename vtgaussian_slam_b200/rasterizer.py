@@ -96,8 +96,9 @@ _DETERMINISTIC = os.environ.get("VTGS_DETERMINISTIC", "0") not in ("", "0")
 
 
 def set_deterministic(on: bool):
-    """Process-wide default of the backward's gradient accumulation (VTGS_BUF_DETERMINISTIC, include/vtgs.h): 64-bit
-    fixed-point sums, bitwise reproducible run to run and across ranks, instead of fp32 atomics of arbitrary order.
+    """Process-wide default of the backward's gradient accumulation (VTGS_BUF_DETERMINISTIC, include/vtgs.h): partial
+    sums split onto exact power-of-two grids, bitwise reproducible run to run and across ranks, instead of plain fp32
+    atomics whose result depends on their arrival order.
     Takes effect for workspaces whose own `deterministic` is None, at their next forward (captured CUDA graphs keep
     what they were captured with).  Also settable with the environment variable VTGS_DETERMINISTIC=1."""
     global _DETERMINISTIC
