@@ -342,29 +342,33 @@ blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __re
     }
 }
 
-// One Gaussian's accumulated sums as the three float4 of the fp32 record layout
+// One Gaussian's accumulated sums.  fetch_grad_record only ISSUES the loads (K7' keeps them in flight behind the previous
+// Gaussian's arithmetic); decode_grad_record turns them into the three float4 of the fp32 record layout
 // ({mean2D.xy, conic.xx, conic.xy}, {conic.yy, opacity, r, g}, {b, colour 3, -, -}); *dirty: the record must be re-zeroed.
+struct GradRecordRaw { float4 a, b, c, d, e; };
+
 template <bool DET>
-__device__ __forceinline__ void load_grad_record(const float* __restrict__ grad_geom, int64_t i, bool want_colour_opacity,
-                                                 float4& g0, float4& g1, float4& g2, bool& dirty) {
+__device__ __forceinline__ void fetch_grad_record(const float* __restrict__ grad_geom, int64_t i, bool want_colour_opacity, GradRecordRaw& r) {
+    const float4* rec = reinterpret_cast<const float4*>(grad_geom + (size_t)i * (DET ? DET_STRIDE : 16));
+    r.a = rec[0]; r.b = rec[1]; r.c = rec[2];
+    if (DET && want_colour_opacity) { r.d = rec[3]; r.e = rec[4]; }
+}
+
+template <bool DET>
+__device__ __forceinline__ void decode_grad_record(const GradRecordRaw& r, bool want_colour_opacity, float4& g0, float4& g1, float4& g2, bool& dirty) {
+    auto nz = [](const float4& v) { return (v.x != 0.f) | (v.y != 0.f) | (v.z != 0.f) | (v.w != 0.f); };
     if (!DET) {
-        const float4* gg = reinterpret_cast<const float4*>(grad_geom + (size_t)i * 16);
-        g0 = gg[0]; g1 = gg[1]; g2 = gg[2];
-        dirty = (g0.x != 0.f) | (g0.y != 0.f) | (g0.z != 0.f) | (g0.w != 0.f) | (g1.x != 0.f) | (g1.y != 0.f) |
-                (g1.z != 0.f) | (g1.w != 0.f) | (g2.x != 0.f) | (g2.y != 0.f);
+        g0 = r.a; g1 = r.b; g2 = r.c;
+        dirty = nz(r.a) | nz(r.b) | (r.c.x != 0.f) | (r.c.y != 0.f);
         return;
     }
-    const float4* rec = reinterpret_cast<const float4*>(grad_geom + (size_t)i * DET_STRIDE);
-    const float4 a = rec[0], b = rec[1], c = rec[2];
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 d = z4, e = z4;
-    if (want_colour_opacity) { d = rec[3]; e = rec[4]; }
-    auto nz = [](const float4& v) { return (v.x != 0.f) | (v.y != 0.f) | (v.z != 0.f) | (v.w != 0.f); };
-    dirty = nz(a) | nz(b) | nz(c) | nz(d) | nz(e);
+    const float4 d = want_colour_opacity ? r.d : z4, e = want_colour_opacity ? r.e : z4;
+    dirty = nz(r.a) | nz(r.b) | nz(r.c) | nz(d) | nz(e);
     auto sum = [](float hi, float lo) { return (float)((double)hi + (double)lo); };
-    g0 = make_float4(sum(a.x, b.z), sum(a.y, b.w), sum(a.z, c.x), sum(a.w, c.y));
-    g1 = make_float4(sum(b.x, c.z), sum(d.x, e.x), sum(d.y, e.y), sum(d.z, e.z));
-    g2 = make_float4(sum(d.w, e.w), sum(b.y, c.w), 0.f, 0.f);
+    g0 = make_float4(sum(r.a.x, r.b.z), sum(r.a.y, r.b.w), sum(r.a.z, r.c.x), sum(r.a.w, r.c.y));
+    g1 = make_float4(sum(r.b.x, r.c.z), sum(d.x, e.x), sum(d.y, e.y), sum(d.z, e.z));
+    g2 = make_float4(sum(d.w, e.w), sum(r.b.y, r.c.w), 0.f, 0.f);
 }
 
 template <bool DET>
@@ -486,7 +490,9 @@ preprocess_backward_kernel(const __grid_constant__ CamConst cam, int64_t N,
     if (i >= N) return;
     float4 g0, g1, g2;
     bool dirty;
-    load_grad_record<DET>(grad_geom, i, true, g0, g1, g2, dirty);
+    GradRecordRaw raw;
+    fetch_grad_record<DET>(grad_geom, i, true, raw);
+    decode_grad_record<DET>(raw, true, g0, g1, g2, dirty);
     if (dirty) zero_grad_record<DET>(grad_geom, i, true);       // leave the scratch zeroed for the next backward
     // visible <=> the forward wrote a record with a non-empty full rect; q1.w (hx) = -1e30 marks culled
     // culled splats (and splats whose opacity can never reach alpha >= 1/255) carry hx = -1e30:
@@ -653,9 +659,9 @@ __device__ __forceinline__ void pose_finalize_block(const float* __restrict__ pa
 // ~700-instruction dependent chain only for the Gaussians that received gradient), accumulates the 12
 // pose terms in registers across its Gaussians and reduces them once at the end.
 struct K7Item {
-    float4 g0, g1, g2, uq;
+    GradRecordRaw raw;
+    float4 uq;
     float hx, op, px, py, pz, ls;
-    bool dirty;
 };
 
 template <bool DET>
@@ -666,12 +672,11 @@ __device__ __forceinline__ void k7_load(K7Item& it, int64_t i, const VtgsParams&
     // 4 bytes decide that instead of ~190
     if (tiles_touched != nullptr && tiles_touched[i] == 0u) {
         const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        it.g0 = z4; it.g1 = z4; it.g2 = z4; it.uq = z4;
+        it.raw.a = z4; it.raw.b = z4; it.raw.c = z4; it.raw.d = z4; it.raw.e = z4; it.uq = z4;
         it.hx = -1e30f; it.op = 0.f; it.px = 0.f; it.py = 0.f; it.pz = 0.f; it.ls = 0.f;
-        it.dirty = false;
         return;
     }
-    load_grad_record<DET>(grad_geom, i, want_colour_opacity, it.g0, it.g1, it.g2, it.dirty);
+    fetch_grad_record<DET>(grad_geom, i, want_colour_opacity, it.raw);
     // a culled splat is in no list, so its sums are zero: only dL/dlogit needs the record (the activated opacity)
     it.hx = 0.0f;
     it.op = want_op ? geom[i].q1.w : 0.0f;
@@ -709,12 +714,14 @@ fused_preprocess_backward_kernel(const __grid_constant__ CamConst cam, int64_t N
     // the blend kernel formed the colour / opacity sums unless it ran in its pose-only form (same condition as there)
     const bool want_colour_opacity = out.rgb_colors != nullptr || out.logit_opacities != nullptr;
     auto process = [&](const K7Item& it, const int64_t i) {
-        const float4 g0 = it.g0, g1 = it.g1, g2 = it.g2;
+        float4 g0, g1, g2;
+        bool dirty;
+        decode_grad_record<DET>(it.raw, want_colour_opacity, g0, g1, g2, dirty);
         // culled splats, and splats no pixel blended (all sums exactly zero), have zero gradients: every
         // term below is linear in g0..g2
         const bool any_grad = (g0.x != 0.f) | (g0.y != 0.f) | (g0.z != 0.f) | (g0.w != 0.f) | (g1.x != 0.f) | (g1.y != 0.f) |
                               (g1.z != 0.f) | (g1.w != 0.f) | (g2.x != 0.f) | (g2.y != 0.f);
-        if (it.dirty) zero_grad_record<DET>(grad_geom, i, want_colour_opacity);     // leave the scratch zeroed for the next backward
+        if (dirty) zero_grad_record<DET>(grad_geom, i, want_colour_opacity);        // leave the scratch zeroed for the next backward
         const bool visible = it.hx > -1e29f && any_grad;
         float dmeanw[3] = {0.f, 0.f, 0.f}, dls = 0.f, dlogit = 0.f, dqu[4] = {0.f, 0.f, 0.f, 0.f};
         if (visible) {
@@ -786,9 +793,8 @@ fused_preprocess_backward_kernel(const __grid_constant__ CamConst cam, int64_t N
             const int64_t nblk = (N + 255) / 256;
             K7Item zit;
             const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            zit.g0 = z4; zit.g1 = z4; zit.g2 = z4; zit.uq = z4;
+            zit.raw.a = z4; zit.raw.b = z4; zit.raw.c = z4; zit.raw.d = z4; zit.raw.e = z4; zit.uq = z4;
             zit.hx = -1e30f; zit.op = 0.f; zit.px = 0.f; zit.py = 0.f; zit.pz = 0.f; zit.ls = 0.f;
-            zit.dirty = false;
             for (int64_t b = blockIdx.x; b < nblk; b += gridDim.x) {
                 const int64_t i = b * 256 + tid;
                 if (band_flags[b] == 0 && i < N) process(zit, i);

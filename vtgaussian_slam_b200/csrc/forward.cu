@@ -943,6 +943,9 @@ __device__ __noinline__ void truncate_masks(uint32_t* col, int gg, int gc, uint3
 #ifndef VTGS_FWD_GC
 #define VTGS_FWD_GC 6
 #endif
+#ifndef VTGS_FWD_NZ
+#define VTGS_FWD_NZ 1                       // 1: per-pixel bitmap of the chunk's non-empty mask words instead of the sentinel search
+#endif
 constexpr int FWD_WARPS = VTGS_FWD_WARPS;   // warps (regions) per block: a tile is covered by 8 / FWD_WARPS blocks
 constexpr int FWD_GC = VTGS_FWD_GC;         // groups per chunk: 1408 B of shared memory per group and warp
 #ifndef VTGS_FWD_BLOCKS
@@ -992,6 +995,9 @@ blend_forward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __res
         const int gc = min(FWD_GC, ngroups - g0);
         __syncwarp();                                   // the previous chunk's reads of S are complete
         // ---- stage + P1, lane = splat
+#if VTGS_FWD_NZ
+        uint32_t nz = 0u;                               // groups of the chunk in which this pixel has a candidate
+#endif
         for (int gg = 0; gg < gc; ++gg) {
             const SplatRegs cur = nxt;
             const int k = (g0 + gg) * 32 + lane;
@@ -1008,17 +1014,33 @@ blend_forward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __res
             }
             const uint32_t m = warp_transpose_bits(em, lane);
             S.pm[gg][lane] = done ? 0u : m;
+#if VTGS_FWD_NZ
+            nz |= (m != 0u && !done) ? (1u << gg) : 0u;
+#endif
         }
+#if !VTGS_FWD_NZ
         S.pm[gc][lane] = 0xffffffffu;                   // sentinel: the search for a lane's next non-empty word stops here
+#endif
         __syncwarp();
         // ---- P2, lane = pixel: one pass over the chunk's masks, no re-convergence between groups.  The mask corrections
         // (P1's superset / the T test rejecting a splat) are cold and kept out of line.
         if (!done) {
             int gg = 0, lk = -1;
+#if VTGS_FWD_NZ
+            uint32_t m = 0u;
+            for (;;) {
+                if (m == 0u) {                             // next group with a candidate for this pixel: one step, whatever the gap
+                    if (nz == 0u) break;
+                    gg = __ffs(nz) - 1;
+                    nz &= nz - 1u;
+                    m = S.pm[gg][lane];
+                }
+#else
             uint32_t m = S.pm[0][lane];
             for (;;) {
                 while (m == 0u) m = S.pm[++gg][lane];      // (the sentinel row bounds it)
                 if (gg >= gc) break;
+#endif
                 const uint32_t bit = m & (0u - m);
                 m ^= bit;
                 const int idx = gg * 32 + msb_index(bit);
