@@ -365,6 +365,8 @@ typedef struct VtgsParamGrads {
     float* cam_unnorm_rot;   /* [4] */
     float* cam_trans;        /* [3] */
     float* pose_scratch;     /* vtgs_pose_scratch_floats(N) floats                        */
+    const float* pose_scale; /* optional device scalar: the pose gradient is multiplied by it (the incoming dL/dloss of
+                                an autograd backward), saving the caller two launches                          */
 } VtgsParamGrads;
 
 VTGS_API uint64_t vtgs_pose_scratch_floats(int64_t num_gaussians);
@@ -456,6 +458,13 @@ VTGS_API int vtgs_p2p_match(int64_t n_tgt, const float* tgt_pts, const float* tg
  */
 VTGS_API int vtgs_frame_convert(int32_t src_w, int32_t src_h, int32_t dst_w, int32_t dst_h, const uint8_t* rgb_hwc,
                                 const uint16_t* depth_u16, double png_depth_scale, float* im_chw, float* depth_out, void* stream);
+
+/*
+ * Radius bookkeeping of get_loss (reference src/vtgaussian_slam.py:681-683) in one launch:
+ *   seen[i] = radii[i] > 0;  max_2D_radius[i] = max(max_2D_radius[i], radii[i])   (radii >= 0, so unseen entries keep theirs)
+ * radii: int32 [n] as the forward wrote them; max_2D_radius: float [n] in place; seen: 1 byte per Gaussian (torch.bool).
+ */
+VTGS_API int vtgs_book_radii(int64_t n, const int32_t* radii, float* max_2D_radius, uint8_t* seen, void* stream);
 
 /* FP32 FMA throughput probe (bench.py's measured FP32 peak): every thread of a full grid runs `iters` dependent-free
  * FFMA octets; FLOP = 2 * 8 * iters * threads, threads = *threads_out.  sink: one device float (keeps the work alive). */

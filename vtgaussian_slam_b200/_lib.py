@@ -85,7 +85,7 @@ class VtgsLossConfig(C.Structure):
 class VtgsParamGrads(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "means3D", "rgb_colors", "unnorm_rotations", "logit_opacities", "log_scales", "means2D",
-        "cam_unnorm_rot", "cam_trans", "pose_scratch")]
+        "cam_unnorm_rot", "cam_trans", "pose_scratch", "pose_scale")]
 
 
 # every symbol include/vtgs.h declares: (restype, argtypes)
@@ -119,6 +119,7 @@ SYMBOLS = {
     "vtgs_p2p_prepare": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_float * 4), C.POINTER(C.c_float * 12), _P, _P, _P, _P, _P, _P, _P]),
     "vtgs_p2p_match": (C.c_int, [C.c_int64, _P, _P, _P, C.c_int64, _P, _P, C.c_float, _P, C.c_int64, _P, _P, _P, _P]),
     "vtgs_frame_convert": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, C.c_double, _P, _P, _P]),
+    "vtgs_book_radii": (C.c_int, [C.c_int64, _P, _P, _P, _P]),
     "vtgs_ffma_probe": (C.c_int, [C.c_int64, _P, C.POINTER(C.c_uint64), _P]),
     "vtgs_profile_enable": (C.c_int, [C.c_int32]),
     "vtgs_profile_summary": (C.c_int, [C.c_char_p, C.c_uint64]),

@@ -303,6 +303,12 @@ int vtgs_frame_convert(int32_t src_w, int32_t src_h, int32_t dst_w, int32_t dst_
     return launch_frame_convert(src_w, src_h, dst_w, dst_h, rgb_hwc, depth_u16, png_depth_scale, im_chw, depth_out, (cudaStream_t)stream);
 }
 
+int vtgs_book_radii(int64_t n, const int32_t* radii, float* max_2D_radius, uint8_t* seen, void* stream) {
+    VTGS_REQUIRE(n >= 0, "n < 0");
+    if (n > 0) VTGS_REQUIRE(radii && max_2D_radius && seen, "pointer is NULL");
+    return launch_book_radii(n, radii, max_2D_radius, seen, (cudaStream_t)stream);
+}
+
 int vtgs_ffma_probe(int64_t iters, float* sink, uint64_t* threads_out, void* stream) {
     VTGS_REQUIRE(iters > 0 && sink != nullptr, "bad argument");
     return launch_ffma_probe(iters, sink, threads_out, (cudaStream_t)stream);

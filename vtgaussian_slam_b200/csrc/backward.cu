@@ -608,7 +608,8 @@ constexpr int POSE_TERMS = 12;       // sum g (3) and sum g p^T (9)
 // Executed by the K7' block that finishes last (256 threads): no extra launch.
 __device__ __forceinline__ void pose_finalize_block(const float* __restrict__ partials, int nblocks,
                                                     const VtgsCounters* __restrict__ c, float* __restrict__ d_rot,
-                                                    float* __restrict__ d_trans, int accumulate, double (*s_sum)[21]) {
+                                                    float* __restrict__ d_trans, int accumulate, double (*s_sum)[21],
+                                                    const float* __restrict__ out_scale) {
     constexpr int SLICES = 21;                    // 12 terms x 21 slices = 252 threads, coalesced reads
     const int tid = threadIdx.x;
     if (tid < POSE_TERMS * SLICES) {
@@ -643,12 +644,15 @@ __device__ __forceinline__ void pose_finalize_block(const float* __restrict__ pa
         // q = u / max(|u|, eps)
         const double d1 = n1 > 1e-12 ? n1 : 1e-12;
         dot = q[0] * dq[0] + q[1] * dq[1] + q[2] * dq[2] + q[3] * dq[3];
+        const float sc = out_scale ? __ldcg(out_scale) : 1.0f;        // (float result) * scale, as a separate torch multiply would do
         for (int k = 0; k < 4; ++k) {
             const double du = n1 >= 1e-12 ? (dq[k] - q[k] * dot) / d1 : dq[k] / d1;
-            if (accumulate) d_rot[k] += (float)du; else d_rot[k] = (float)du;
+            const float v = out_scale ? (float)du * sc : (float)du;
+            if (accumulate) d_rot[k] += v; else d_rot[k] = v;
         }
         for (int k = 0; k < 3; ++k) {
-            if (accumulate) d_trans[k] += (float)tot[k]; else d_trans[k] = (float)tot[k];
+            const float v = out_scale ? (float)tot[k] * sc : (float)tot[k];
+            if (accumulate) d_trans[k] += v; else d_trans[k] = v;
         }
     }
 }
@@ -826,7 +830,7 @@ fused_preprocess_backward_kernel(const __grid_constant__ CamConst cam, int64_t N
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    pose_finalize_block(out.pose_scratch, (int)gridDim.x, counters, out.cam_unnorm_rot, out.cam_trans, accumulate, s_sum);
+    pose_finalize_block(out.pose_scratch, (int)gridDim.x, counters, out.cam_unnorm_rot, out.cam_trans, accumulate, s_sum, out.pose_scale);
     if (tid == 0) *ticket = 0u;
 }
 

@@ -310,4 +310,22 @@ int launch_frame_convert(int sw, int sh, int dw, int dh, const uint8_t* rgb, con
     return VTGS_OK;
 }
 
+// ---- radius bookkeeping of get_loss (reference src/vtgaussian_slam.py:681-683) ---------------------------------------
+__global__ void __launch_bounds__(256)
+book_radii_kernel(int64_t n, const int32_t* __restrict__ radii, float* __restrict__ max_radius, uint8_t* __restrict__ seen) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const int32_t r = radii[i];
+    seen[i] = r > 0 ? 1 : 0;
+    const float m = max_radius[i], rf = (float)r;
+    if (rf > m) max_radius[i] = rf;
+}
+
+int launch_book_radii(int64_t n, const int32_t* radii, float* max_radius, uint8_t* seen, cudaStream_t stream) {
+    if (n <= 0) return VTGS_OK;
+    { VTGS_PROF("book_radii_kernel", stream); book_radii_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(n, radii, max_radius, seen); }
+    VTGS_LAUNCH_CHECK();
+    return VTGS_OK;
+}
+
 }  // namespace vtgs

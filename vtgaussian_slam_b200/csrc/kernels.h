@@ -69,6 +69,7 @@ int launch_p2p_match(int64_t n_tgt, const float* tgt_pts, const float* tgt_nrm, 
                      int32_t* next, float* out_dist, int32_t* out_idx, cudaStream_t stream);
 int launch_frame_convert(int sw, int sh, int dw, int dh, const uint8_t* rgb, const uint16_t* depth, double depth_scale, float* im,
                          float* depth_out, cudaStream_t stream);
+int launch_book_radii(int64_t n, const int32_t* radii, float* max_radius, uint8_t* seen, cudaStream_t stream);
 int launch_ffma_probe(int64_t iters, float* sink, uint64_t* threads_out, cudaStream_t stream);
 int launch_retie(float* means3D, int64_t n, const float* w2c_old_rowmajor12, const float* q_un, const float* t, cudaStream_t stream);
 int launch_retie_dev(float* means3D, int64_t n, const float* q_old, const float* t_old, const float* q_un, const float* t, cudaStream_t stream);

@@ -206,9 +206,9 @@ class FusedRenderer:
         return self.loss_terms
 
     def backward(self, params, cam_q, cam_t, dL_dimage4=None, param_grads=None, pose_grads=None, means2D_grad=None,
-                 accumulate=False):
+                 accumulate=False, pose_scale=None):
         """param_grads: dict key -> tensor to receive dL/dparams[key] (any subset of PARAM_KEYS).
-        pose_grads: (d_cam_q[4], d_cam_t[3]) tensors or None."""
+        pose_grads: (d_cam_q[4], d_cam_t[3]) tensors or None; pose_scale: optional device scalar multiplied into them."""
         p, ps = self._params_struct(params), self._pose_struct(cam_q, cam_t)
         g = _lib.VtgsParamGrads()
         for k in PARAM_KEYS:
@@ -222,10 +222,23 @@ class FusedRenderer:
         if pose_grads is not None:
             g.cam_unnorm_rot, g.cam_trans = pose_grads[0].data_ptr(), pose_grads[1].data_ptr()
             g.pose_scratch = self._pose_scratch.data_ptr()
+            if pose_scale is not None:
+                g.pose_scale = pose_scale.data_ptr()
         dL = self.dL_dimage4 if dL_dimage4 is None else dL_dimage4
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().vtgs_fused_backward(C.byref(self.cam), C.byref(p), C.byref(ps), _ptr(dL), int(bool(accumulate)),
                                                       C.byref(g), C.byref(self._bufs), _stream_ptr(self.device)))
+
+
+def book_radii(radii, max_2D_radius, seen=None):
+    """get_loss's radius bookkeeping (reference src/vtgaussian_slam.py:681-683) in one launch: -> seen (bool[N]);
+    max_2D_radius (float[N]) is updated in place."""
+    n = int(radii.shape[0])
+    if seen is None:
+        seen = torch.empty(n, dtype=torch.bool, device=radii.device)
+    with torch.cuda.device(radii.device):
+        _lib.check(_lib.lib().vtgs_book_radii(n, _ptr(radii), _ptr(max_2D_radius), _ptr(seen), _stream_ptr(radii.device)))
+    return seen
 
 
 def retie(means3D, w2c_old, cam_q, cam_t):

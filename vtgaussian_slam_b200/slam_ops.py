@@ -329,18 +329,19 @@ class _FusedTrackingLoss(torch.autograd.Function):
         ctx.renderer, ctx.p, ctx.q, ctx.t = renderer, p, q, t
         ctx.pose_shapes = (cam_q.shape, cam_t.shape)
         ctx.dL4 = renderer.dL_dimage4          # valid until the renderer's next loss call
-        radii = radii.clone()
+        # radii: the renderer's own buffer (valid until its next forward; get_loss books it at once): no N-sized copy
         ctx.mark_non_differentiable(radii, terms)
         return terms[0].clone(), terms, radii
 
     @staticmethod
     def backward(ctx, g_loss, _g_terms, _g_radii):
-        dq = torch.zeros(4, dtype=torch.float32, device=g_loss.device)
-        dt = torch.zeros(3, dtype=torch.float32, device=g_loss.device)
-        ctx.renderer.backward(ctx.p, ctx.q, ctx.t, dL_dimage4=ctx.dL4, pose_grads=(dq, dt))
+        # the backward overwrites both (no zero fill) and multiplies the incoming dL/dloss in its final reduction
+        dq = torch.empty(4, dtype=torch.float32, device=g_loss.device)
+        dt = torch.empty(3, dtype=torch.float32, device=g_loss.device)
+        scale = g_loss.detach().to(torch.float32).contiguous()
+        ctx.renderer.backward(ctx.p, ctx.q, ctx.t, dL_dimage4=ctx.dL4, pose_grads=(dq, dt), pose_scale=scale)
         ctx.renderer.pending_backward = False
-        return (None, None, (dq * g_loss).reshape(ctx.pose_shapes[0]), (dt * g_loss).reshape(ctx.pose_shapes[1]),
-                None, None, None, None, None)
+        return (None, None, dq.reshape(ctx.pose_shapes[0]), dt.reshape(ctx.pose_shapes[1]), None, None, None, None, None)
 
 
 class _FusedMappingLoss(torch.autograd.Function):
@@ -383,9 +384,14 @@ class _FusedMappingLoss(torch.autograd.Function):
 
 def _book_radii(variables, radius):
     """reference :681-683: seen = radius > 0; max_2D_radius[seen] = max(radius[seen], max_2D_radius[seen]) -- without the
-    boolean-index gathers (two elementwise kernels; radii are >= 0, so unseen entries keep their value)."""
-    variables['seen'] = radius > 0
+    boolean-index gathers (one library launch on CUDA, two elementwise torch ops otherwise; radii are >= 0, so unseen
+    entries keep their value)."""
     m = variables['max_2D_radius']
+    if radius.is_cuda and radius.dtype == torch.int32 and m.dtype == torch.float32 and m.is_contiguous() and radius.is_contiguous():
+        from .fused import book_radii
+        variables['seen'] = book_radii(radius, m)              # one launch; max_2D_radius updated in place
+        return
+    variables['seen'] = radius > 0
     variables['max_2D_radius'] = torch.maximum(m, radius.to(m.dtype))
 
 
