@@ -110,8 +110,9 @@ static int launch_dpix_max(const CamConst& cam, const float* dL_dpix, int nch, u
 
 // =============================== K6': backward blend =======================================
 // grad_geom record per Gaussian (VTGS_GRAD_GEOM_FLOATS = 16):
-//   [0,1] dL/dmean2D (NDC-scaled)  [2,3,4] dL/dconic (xx, xy, yy)  [5] dL/dopacity
-//   [6..6+NCH) dL/dcolour  (API: r,g,b   fused: r,g,b,z)
+//   [0,1] dL/dmean2D (NDC-scaled)  [2,3,4] dL/dconic (xx, xy, yy)  [5] dL/dcolour 3 (fused: z; API: unused)
+//   [6,7,8] dL/d(r, g, b)  [9] dL/dopacity
+// (everything the pose-only instantiation writes sits in the first 32-byte sector: one v4 + one v2 reduction)
 //
 // Block = one 16x16 tile, 8 independent warps (no block barrier), warp w = pixel region w.
 // Each warp walks ITS REGION'S LIST (built by the sort kernel) BACK TO FRONT in the forward's groups of 32
@@ -129,14 +130,16 @@ static int launch_dpix_max(const CamConst& cam, const float* dL_dpix, int nch, u
 #define VTGS_BWD_WARPS 2
 #endif
 constexpr int BWD_WARPS = VTGS_BWD_WARPS;   // warps (regions) per block: a tile is covered by 8 / BWD_WARPS blocks
-#ifndef VTGS_BWD_LITEPIX
-#define VTGS_BWD_LITEPIX 1                  // the pose-only instantiation keeps a 3-row pixel table (x, y, dL/dz): 9.6 instead of 10 KB per
-#endif                                      // warp -> 11 instead of 10 blocks per SM (measured: K6' 273 -> 265 us at C2)
-__host__ __device__ constexpr int bwd_pix_rows(bool lite) { return (VTGS_BWD_LITEPIX && lite) ? 3 : 6; }
+// Pixel table of a warp: dL/d(r, g, b, z) of the region's 32 pixels.  The pose-only instantiation needs none: P2 hands over
+// w dL/dz instead of w (the only use of w there), and P3 derives the pixel coordinates from the pixel index.
+__host__ __device__ constexpr int bwd_pix_rows(bool lite) { return lite ? 0 : 4; }
 constexpr int bwd_smem_bytes(bool lite) {
-    return BWD_WARPS * (int)(10 * 32 * sizeof(float) + 32 * 32 * sizeof(float2) + bwd_pix_rows(lite) * 32 * sizeof(float));
+    return BWD_WARPS * (int)(10 * 32 * sizeof(float) + 32 * 32 * sizeof(float2) + (bwd_pix_rows(lite) ? bwd_pix_rows(lite) : 1) * 32 * sizeof(float));
 }
-constexpr int bwd_min_blocks(bool lite) { return ((VTGS_BWD_LITEPIX && lite) ? 22 : 20) / BWD_WARPS; }
+#ifndef VTGS_BWD_LITE_WARPS_PER_SM
+#define VTGS_BWD_LITE_WARPS_PER_SM 22
+#endif
+constexpr int bwd_min_blocks(bool lite) { return (lite ? VTGS_BWD_LITE_WARPS_PER_SM : 20) / BWD_WARPS; }
 // BG:   the background is not black (one more term in dL/dalpha); the reference always renders on black.
 // LITE: the caller wants no colour / opacity gradients (tracking: only the pose gradient is formed, from the
 //       mean2D / conic / depth-channel sums) -- P3 drops the r,g,b and opacity sums.
@@ -159,7 +162,7 @@ blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __re
         float2 cell[32][32];        // [splat of the group][pixel]: (w, g0).  Unpadded: a pixel lane always stores to its own
                                     // column (bank pair = lane mod 16, conflict-free whatever the splats); the splat lanes'
                                     // loads hit the bank pair of the pixel they are at, as with any padding
-        float pix[bwd_pix_rows(LITE)][32];   // pixels of the region: centre x, y, dL/d(r, g, b, z)  (x, y, dL/dz in the 3-row form)
+        float pix[bwd_pix_rows(LITE) ? bwd_pix_rows(LITE) : 1][32];   // pixels of the region: dL/d(r, g, b, z) (unused in the pose-only form)
     };
     WarpArea* areas = reinterpret_cast<WarpArea*>(smem_raw);
 
@@ -186,12 +189,11 @@ blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __re
     float dpix[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int ch = 0; ch < NCH; ++ch) dpix[ch] = inside ? dL_dpix[ch * P + pid] : 0.0f;
-    A.pix[0][lane] = pxf; A.pix[1][lane] = pyf;
+    if (!LITE) {
 #pragma unroll
-    for (int ch = 0; ch < 4; ++ch)
-        if (bwd_pix_rows(LITE) == 6) A.pix[2 + ch][lane] = dpix[ch];
-    if (bwd_pix_rows(LITE) == 3) A.pix[2][lane] = dpix[3];
-    constexpr int PIX_Z = bwd_pix_rows(LITE) == 3 ? 2 : 5;
+        for (int ch = 0; ch < 4; ++ch) A.pix[ch][lane] = dpix[ch];
+    }
+    const float rx0f = (float)rx0, ry0f = (float)ry0;
     const float bg_dot = BG ? cam.bg[0] * dpix[0] + cam.bg[1] * dpix[1] + cam.bg[2] * dpix[2] : 0.0f;
     const float half_w = 0.5f * cam.W, half_h = 0.5f * cam.H;
 
@@ -252,7 +254,7 @@ blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __re
             float dL_dalpha = (cdot - acc_dot) * T;
             last_alpha = alpha;
             if (BG) dL_dalpha -= T_final * inv * bg_dot;
-            return make_float2(alpha * T, Gv * dL_dalpha);
+            return make_float2(LITE ? alpha * T * dpix[3] : alpha * T, Gv * dL_dalpha);
         };
         while (m) {
             const int ea = msb_index(m);
@@ -273,14 +275,20 @@ blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __re
         // ---- P3: lane = splat: reduce my row of cells
         float s0 = 0.f, sx = 0.f, sy = 0.f, sxx = 0.f, sxy = 0.f, syy = 0.f;
         float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
+        // pixel p of the region sits at (rx0 + p % REGION_W, ry0 + p / REGION_W): small integers -> floats through the
+        // 2^23 mantissa trick (ALU / FMA pipes; a table lookup would cost two more shared-memory wavefronts per trip,
+        // and this kernel is bound by exactly those)
+        const float mxl = cur.a.x - rx0f, myl = cur.a.y - ry0f;
         uint32_t pm = emask;
         while (pm) {
             const int p = __ffs(pm) - 1;
             pm &= pm - 1;
             const float2 cw = A.cell[lane][p];
-            const float dx = cur.a.x - A.pix[0][p], dy = cur.a.y - A.pix[1][p];
-            if (!LITE) { c0 = fmaf(cw.x, A.pix[2][p], c0); c1 = fmaf(cw.x, A.pix[3][p], c1); c2 = fmaf(cw.x, A.pix[4][p], c2); }
-            if (NCH == 4) c3 = fmaf(cw.x, A.pix[PIX_Z][p], c3);
+            const float dx = mxl - (__uint_as_float(0x4B000000u | (uint32_t)(p % REGION_W)) - 8388608.0f);
+            const float dy = myl - (__uint_as_float(0x4B000000u | (uint32_t)(p / REGION_W)) - 8388608.0f);
+            if (!LITE) { c0 = fmaf(cw.x, A.pix[0][p], c0); c1 = fmaf(cw.x, A.pix[1][p], c1); c2 = fmaf(cw.x, A.pix[2][p], c2); }
+            if (LITE) c3 += cw.x;
+            else if (NCH == 4) c3 = fmaf(cw.x, A.pix[3][p], c3);
             const float gg = cw.y, gx_ = gg * dx, gy_ = gg * dy;
             if (!LITE) s0 += gg;
             sx += gx_; sy += gy_;
@@ -329,13 +337,12 @@ blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __re
             } else {
             float* dst = grad_geom + (size_t)cur_ent.x * 16;
             asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v0), "f"(v1), "f"(v2), "f"(v3) : "memory");
-            if (LITE) {                 // slots 5..8 (opacity, r, g, b) stay zero
-                atomicAdd(dst + 4, v4);
-                if (NCH == 4) atomicAdd(dst + 9, c3);
+            if (LITE) {                 // slots 6..9 (r, g, b, opacity) stay zero
+                if (NCH == 4) asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(dst + 4), "f"(v4), "f"(c3) : "memory");
+                else atomicAdd(dst + 4, v4);
             } else {
-                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(v4), "f"(s0), "f"(c0), "f"(c1) : "memory");
-                if (NCH == 4) asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(dst + 8), "f"(c2), "f"(c3) : "memory");
-                else atomicAdd(dst + 8, c2);
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(v4), "f"(c3), "f"(c0), "f"(c1) : "memory");
+                asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(dst + 8), "f"(c2), "f"(s0) : "memory");
             }
             }
         }
@@ -358,7 +365,9 @@ template <bool DET>
 __device__ __forceinline__ void decode_grad_record(const GradRecordRaw& r, bool want_colour_opacity, float4& g0, float4& g1, float4& g2, bool& dirty) {
     auto nz = [](const float4& v) { return (v.x != 0.f) | (v.y != 0.f) | (v.z != 0.f) | (v.w != 0.f); };
     if (!DET) {
-        g0 = r.a; g1 = r.b; g2 = r.c;
+        g0 = r.a;                                           // memory order: {.., conic.yy, colour 3, r, g}, {b, opacity}
+        g1 = make_float4(r.b.x, r.c.y, r.b.z, r.b.w);
+        g2 = make_float4(r.c.x, r.b.y, 0.f, 0.f);
         dirty = nz(r.a) | nz(r.b) | (r.c.x != 0.f) | (r.c.y != 0.f);
         return;
     }
