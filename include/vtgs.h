@@ -42,7 +42,7 @@ extern "C" {
 #define VTGS_API
 #endif
 
-#define VTGS_ABI_VERSION 3
+#define VTGS_ABI_VERSION 4
 
 /* ---- named constants of the splatting arithmetic ---------- */
 #define VTGS_TILE            16          /* BLOCK_X = BLOCK_Y                          */
@@ -375,6 +375,19 @@ VTGS_API int vtgs_fused_backward(const VtgsCamera* cam, const VtgsParams* params
                         const float* dL_dimage4 /* [4,H,W]: r,g,b,depth */,
                         int32_t accumulate /* 0: overwrite grads, 1: += (multi-keyframe) */,
                         VtgsParamGrads* grads, VtgsBuffers* buf, void* stream);
+
+/*
+ * One reference tracking iteration's render work in ONE call: get_loss(tracking=True) followed by loss.backward()
+ * (reference src/vtgaussian_slam.py:1886-1889, get_loss :407-689) = vtgs_fused_forward, vtgs_loss (tracking mode),
+ * vtgs_fused_backward to the 7 pose numbers (grads->cam_unnorm_rot / cam_trans; Gaussian-parameter pointers may be set as
+ * well) and, when max_2D_radius != NULL, vtgs_book_radii -- the same kernels in the same order on `stream`.  A caller
+ * that steps from a host loop (one Python / FFI crossing per iteration) is otherwise paced by its four crossings.
+ */
+VTGS_API int vtgs_fused_tracking_step(const VtgsCamera* cam, const VtgsParams* params, const VtgsPose* pose,
+                        const VtgsLossConfig* cfg, const float* gt_rgb, const float* gt_depth,
+                        float* out_image6, int32_t* radii, float* dL_dimage4, float* loss_terms, float* loss_scratch,
+                        VtgsParamGrads* grads, float* max_2D_radius /* may be NULL */, uint8_t* seen /* may be NULL */,
+                        VtgsBuffers* buf, void* stream);
 
 /*
  * Adam exactly as torch.optim.Adam(betas=(0.9,0.999), eps, weight_decay=0) applies it to

@@ -26,7 +26,7 @@ def test_every_declared_symbol_is_exported(L):
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
     for name in declared:
         assert hasattr(L, name)
-    assert L.vtgs_abi_version() == _lib.ABI_VERSION == 3
+    assert L.vtgs_abi_version() == _lib.ABI_VERSION == 4
     assert b"sm_100a" in L.vtgs_build_info()
 
 

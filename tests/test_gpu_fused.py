@@ -155,6 +155,40 @@ def test_adam_matches_torch():
         assert (p.cpu() - ref.detach()).abs().max().item() <= 2e-6
 
 
+def test_initialize_optimizer_native_adam_matches_torch():
+    """slam_ops.initialize_optimizer on CUDA parameters returns slam_ops.Adam (library kernel): same parameter groups, same
+    state layout and the same updates as torch.optim.Adam -- including a group that never receives a gradient, lr = 0
+    groups and a state entry replaced the way the reference's densification helpers do (utils/slam_external.py)."""
+    g = torch.Generator().manual_seed(1)
+    shapes = dict(means3D=(500, 3), rgb_colors=(500, 3), logit_opacities=(500, 1), cam_unnorm_rots=(1, 4, 1), cam_trans=(1, 3, 1))
+    lrs = dict(means3D=0.0, rgb_colors=0.0025, logit_opacities=0.05, cam_unnorm_rots=0.0004, cam_trans=0.002)
+    for tracking in (True, False):
+        init = {k: torch.randn(*sh, generator=g) for k, sh in shapes.items()}
+        ours = {k: torch.nn.Parameter(v.clone().to(DEV)) for k, v in init.items()}
+        ref = {k: torch.nn.Parameter(v.clone()) for k, v in init.items()}
+        o = slam_ops.initialize_optimizer(ours, lrs, tracking)
+        assert isinstance(o, slam_ops.Adam) and [grp["name"] for grp in o.param_groups] == list(shapes)
+        groups = [{'params': [v], 'name': k, 'lr': lrs[k]} for k, v in ref.items()]
+        r = torch.optim.Adam(groups) if tracking else torch.optim.Adam(groups, lr=0.0, eps=1e-15)
+        assert o.defaults["eps"] == r.defaults["eps"]
+        for it in range(6):
+            for k in shapes:
+                if k == "logit_opacities" and it < 2:
+                    continue                                  # no gradient yet: its step count starts later
+                gr = torch.randn(*shapes[k], generator=g) * (1e-3 if k.startswith("cam") else 1.0)
+                ref[k].grad = gr.clone()
+                ours[k].grad = gr.clone().to(DEV)
+            o.step(); r.step()
+            o.zero_grad(set_to_none=True); r.zero_grad(set_to_none=True)
+            if it == 3:                                       # the reference swaps moments when it edits the Gaussians
+                for opt_, prm in ((o, ours["rgb_colors"]), (r, ref["rgb_colors"])):
+                    st = opt_.state[prm]
+                    st["exp_avg"] = torch.zeros_like(st["exp_avg"]); st["exp_avg_sq"] = torch.zeros_like(st["exp_avg_sq"])
+        for k in shapes:
+            assert (ours[k].detach().cpu() - ref[k].detach()).abs().max().item() <= 3e-6, k
+            assert int(o.state[ours[k]]["step"]) == int(r.state[ref[k]]["step"])
+
+
 def test_tracking_solver_converges_and_graph_matches_eager():
     from vtgaussian_slam_b200.fused import TrackingSolver
     fr = synthetic.make_frame("replica", 240, 136, seed=0)

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("VTGS_LIB_PATH") or os.path.join(_HERE, "lib", "libvtgs_cuda.so")
 CSRC = os.path.join(_HERE, "csrc")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 MEDIAN_STATE_WORDS = 264
 MEDIAN_SUMMABLE_WORDS = 257
 TRACK_BOOK_POST_STEP = 1
@@ -106,6 +106,8 @@ SYMBOLS = {
     "vtgs_pose_scratch_floats": (C.c_uint64, [C.c_int64]),
     "vtgs_fused_backward": (C.c_int, [C.POINTER(VtgsCamera), C.POINTER(VtgsParams), C.POINTER(VtgsPose), _P, C.c_int32,
                                       C.POINTER(VtgsParamGrads), C.POINTER(VtgsBuffers), _P]),
+    "vtgs_fused_tracking_step": (C.c_int, [C.POINTER(VtgsCamera), C.POINTER(VtgsParams), C.POINTER(VtgsPose), C.POINTER(VtgsLossConfig)] +
+                                 [_P] * 7 + [C.POINTER(VtgsParamGrads), _P, _P, C.POINTER(VtgsBuffers), _P]),
     "vtgs_retie": (C.c_int, [_P, C.c_int64, C.POINTER(C.c_float * 12), _P, _P, _P]),
     "vtgs_retie_dev": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, _P]),
     "vtgs_tracking_update": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_float, C.c_float, C.c_float, C.c_int32, _P]),

@@ -191,6 +191,20 @@ int vtgs_fused_backward(const VtgsCamera* cam, const VtgsParams* p, const VtgsPo
     return launch_fused_backward(cam, p, pose, dL_dimage4, accumulate, grads, buf, (cudaStream_t)stream);
 }
 
+int vtgs_fused_tracking_step(const VtgsCamera* cam, const VtgsParams* p, const VtgsPose* pose, const VtgsLossConfig* cfg,
+                             const float* gt_rgb, const float* gt_depth, float* out_image6, int32_t* radii, float* dL_dimage4,
+                             float* loss_terms, float* loss_scratch, VtgsParamGrads* grads, float* max_2D_radius, uint8_t* seen,
+                             VtgsBuffers* buf, void* stream) {
+    VTGS_REQUIRE(cfg && cfg->mode == 0, "vtgs_fused_tracking_step needs a tracking-mode loss configuration");
+    VTGS_REQUIRE((max_2D_radius == nullptr) == (seen == nullptr), "max_2D_radius and seen come as a pair");
+    if (int e = vtgs_fused_forward(cam, p, pose, out_image6, radii, buf, stream)) return e;
+    if (int e = vtgs_loss(cam, cfg, out_image6, gt_rgb, gt_depth, dL_dimage4, loss_terms, loss_scratch, stream)) return e;
+    if (int e = vtgs_fused_backward(cam, p, pose, dL_dimage4, 0, grads, buf, stream)) return e;
+    if (max_2D_radius != nullptr)
+        if (int e = vtgs_book_radii(p->num_gaussians, radii, max_2D_radius, seen, stream)) return e;
+    return VTGS_OK;
+}
+
 uint64_t vtgs_pose_scratch_floats(int64_t N) { return (uint64_t)((N + 255) / 256 + 1) * 12; }
 
 uint64_t vtgs_loss_scratch_floats(int32_t W, int32_t H, int32_t mode) {

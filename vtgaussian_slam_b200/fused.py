@@ -190,6 +190,31 @@ class FusedRenderer:
                                             _stream_ptr(self.device)))
         return self.loss_terms
 
+    def tracking_step(self, params, cam_q, cam_t, gt_rgb, gt_depth, pose_grads, w_im=0.5, w_depth=0.025, use_sil_for_loss=True,
+                      sil_thres=0.99, far_depth_thres=0.0, ignore_outlier_depth_loss=False, pixel_mask=None,
+                      max_2D_radius=None, seen=None):
+        """forward + tracking_loss + backward (to the 7 pose numbers, unscaled) [+ book_radii] in ONE library call
+        (`vtgs_fused_tracking_step`): what get_loss(tracking=True) followed by loss.backward() launches, with one
+        Python / ctypes crossing instead of four.  -> (loss_terms[8], radii[N]); fills pose_grads = (d_cam_q[4], d_cam_t[3])."""
+        p, ps = self._params_struct(params), self._pose_struct(cam_q, cam_t)
+        pm = None
+        if pixel_mask is not None:
+            _require_cuda("pixel_mask", pixel_mask)
+            pm = pixel_mask.reshape(self.H, self.W)
+            pm = (pm if pm.dtype == torch.uint8 else pm.to(torch.uint8)).contiguous()
+            self._pixel_mask = pm
+        cfg = _lib.VtgsLossConfig(0, int(bool(use_sil_for_loss)), int(bool(ignore_outlier_depth_loss)), 1, float(sil_thres),
+                                  float(w_im), float(w_depth), float(far_depth_thres), _ptr(pm), None, None)
+        g = _lib.VtgsParamGrads()
+        g.cam_unnorm_rot, g.cam_trans = pose_grads[0].data_ptr(), pose_grads[1].data_ptr()
+        g.pose_scratch = self._pose_scratch.data_ptr()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().vtgs_fused_tracking_step(
+                C.byref(self.cam), C.byref(p), C.byref(ps), C.byref(cfg), _ptr(gt_rgb), _ptr(gt_depth), _ptr(self.image6),
+                _ptr(self.radii), _ptr(self.dL_dimage4), _ptr(self.loss_terms), _ptr(self._loss_scratch), C.byref(g),
+                _ptr(max_2D_radius), _ptr(seen), C.byref(self._bufs), _stream_ptr(self.device)))
+        return self.loss_terms, self.radii[:self.N]
+
     def mapping_loss(self, gt_rgb, gt_depth, w_im=1.0, w_depth=1.0, image6=None):
         """Mapping loss of get_loss (reference :597,:608): w_depth * mean|gt-d|[gt>0] + w_im * (0.8 L1mean +
         0.2 (1 - SSIM)) of the last forward, SSIM forward+backward in hand-written kernels.

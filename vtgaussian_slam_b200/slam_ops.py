@@ -150,16 +150,55 @@ def transformed_params2depthplussilhouette(params, w2c, transformed_gaussians):
     return _activated(params, transformed_gaussians, get_depth_and_silhouette(transformed_gaussians['means3D'], w2c))
 
 
+class Adam(torch.optim.Optimizer):
+    """torch.optim.Adam(betas, eps, weight_decay=0, amsgrad=False) for CUDA float32 tensors through `vtgs_adam`: one
+    library launch per tensor that has a gradient, no foreach / dispatcher work on the host (a third of the host time of
+    a reference-style tracking iteration went into the Python of torch's Adam.step()).  Parameter groups, `defaults` and
+    the per-parameter state (`step`, `exp_avg`, `exp_avg_sq`) are laid out as torch.optim.Adam lays them out, so code
+    that edits `optimizer.state[p]` / `param_groups` (the reference's densification helpers, utils/slam_external.py)
+    keeps working."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=0, amsgrad=False, maximize=False))
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        from .fused import adam_step
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        for group in self.param_groups:
+            b1, b2 = group['betas']
+            for prm in group['params']:
+                g = prm.grad
+                if g is None:
+                    continue
+                if not (prm.is_cuda and prm.dtype == torch.float32 and prm.is_contiguous()):
+                    raise ValueError("slam_ops.Adam updates contiguous float32 CUDA tensors")
+                st = self.state[prm]
+                if len(st) == 0:
+                    st['step'] = torch.tensor(0.0)
+                    st['exp_avg'] = torch.zeros_like(prm, memory_format=torch.preserve_format)
+                    st['exp_avg_sq'] = torch.zeros_like(prm, memory_format=torch.preserve_format)
+                st['step'] += 1
+                if g.dtype != torch.float32 or not g.is_contiguous():
+                    g = g.float().contiguous()
+                adam_step(prm, g, st['exp_avg'], st['exp_avg_sq'], group['lr'], step=int(st['step']), beta1=b1, beta2=b2,
+                          eps=group['eps'])
+        return loss
+
+
 def initialize_optimizer(params, lrs_dict, tracking):
-    """torch.optim.Adam over one parameter group per tensor (reference src/vtgaussian_slam.py:180-187).  On CUDA the
-    optimiser's fused implementation is selected: the same update, one kernel per group instead of ~10 foreach calls --
-    the Python side of Adam.step() is otherwise a third of a tracking iteration's host time."""
+    """Adam over one parameter group per tensor (reference src/vtgaussian_slam.py:180-187: eps 1e-8 for tracking, lr 0 /
+    eps 1e-15 defaults for mapping).  CUDA float32 parameters get `slam_ops.Adam` (the same update through the library's
+    Adam kernel); anything else torch.optim.Adam."""
     param_groups = [{'params': [v], 'name': k, 'lr': lrs_dict[k]} for k, v in params.items()]
-    fused = all(isinstance(v, torch.Tensor) and v.is_cuda and v.is_floating_point() for v in params.values())
-    extra = dict(fused=True) if fused else {}
+    native = all(isinstance(v, torch.Tensor) and v.is_cuda and v.dtype == torch.float32 for v in params.values())
+    cls = Adam if native else torch.optim.Adam
     if tracking:
-        return torch.optim.Adam(param_groups, **extra)
-    return torch.optim.Adam(param_groups, lr=0.0, eps=1e-15, **extra)
+        return cls(param_groups)
+    return cls(param_groups, lr=0.0, eps=1e-15)
 
 
 # ---------------------------------------------------------------------------- the loss
@@ -317,9 +356,28 @@ class _FusedTrackingLoss(torch.autograd.Function):
     transform_to_frame detaches them, reference :432-436)."""
 
     @staticmethod
-    def forward(ctx, renderer, params, cam_q, cam_t, gt_rgb, gt_depth, cfg, thres_fn, poll):
+    def forward(ctx, renderer, params, cam_q, cam_t, gt_rgb, gt_depth, cfg, thres_fn, poll, book):
         p = {k: params[k].detach().contiguous() for k in ("means3D", "rgb_colors", "unnorm_rotations", "logit_opacities", "log_scales")}
         q, t = cam_q.detach().contiguous().reshape(4), cam_t.detach().contiguous().reshape(3)
+        ctx.pose_shapes = (cam_q.shape, cam_t.shape)
+        # A tracking iteration always back-propagates to the pose (reference :1886-1889), so when a pose gradient is
+        # wanted the whole iteration -- render, loss, backward, radius bookkeeping -- goes down in ONE library call and
+        # backward() only hands the stored gradient over: the host side of a reference-style step is what paces it.
+        ctx.eager = thres_fn is None and (ctx.needs_input_grad[2] or ctx.needs_input_grad[3])
+        if ctx.eager:
+            g7 = torch.empty(7, dtype=torch.float32, device=q.device)
+            rgb, dep = gt_rgb.contiguous(), gt_depth.contiguous()
+            m2r, seen = book if book is not None else (None, None)
+            for attempt in range(2):
+                terms, radii = renderer.tracking_step(p, q, t, rgb, dep, (g7[:4], g7[4:]), max_2D_radius=m2r, seen=seen, **cfg)
+                if not (poll and renderer.ensure_capacity()):      # (the bookkeeping only reads the radii: repeatable)
+                    break
+                if attempt == 1:
+                    raise RuntimeError("pair buffer overflow persisted after regrowing")
+            ctx.g7 = g7
+            terms = terms.clone()
+            ctx.mark_non_differentiable(radii, terms)
+            return terms[0].clone(), terms, radii
         img, radii = _forward_checked(renderer, p, q, t, poll)
         cfg = dict(cfg)
         if thres_fn is not None:
@@ -327,21 +385,27 @@ class _FusedTrackingLoss(torch.autograd.Function):
         terms = renderer.tracking_loss(gt_rgb.contiguous(), gt_depth.contiguous(), **cfg).clone()
         renderer.pending_backward = any(ctx.needs_input_grad)
         ctx.renderer, ctx.p, ctx.q, ctx.t = renderer, p, q, t
-        ctx.pose_shapes = (cam_q.shape, cam_t.shape)
         ctx.dL4 = renderer.dL_dimage4          # valid until the renderer's next loss call
+        if book is not None:
+            from .fused import book_radii
+            book_radii(radii, book[0], book[1])
         # radii: the renderer's own buffer (valid until its next forward; get_loss books it at once): no N-sized copy
         ctx.mark_non_differentiable(radii, terms)
         return terms[0].clone(), terms, radii
 
     @staticmethod
     def backward(ctx, g_loss, _g_terms, _g_radii):
+        if ctx.eager:
+            g7 = ctx.g7 * g_loss.detach().to(torch.float32)
+            return (None, None, g7[:4].reshape(ctx.pose_shapes[0]), g7[4:].reshape(ctx.pose_shapes[1]), None, None, None, None,
+                    None, None)
         # the backward overwrites both (no zero fill) and multiplies the incoming dL/dloss in its final reduction
         dq = torch.empty(4, dtype=torch.float32, device=g_loss.device)
         dt = torch.empty(3, dtype=torch.float32, device=g_loss.device)
         scale = g_loss.detach().to(torch.float32).contiguous()
         ctx.renderer.backward(ctx.p, ctx.q, ctx.t, dL_dimage4=ctx.dL4, pose_grads=(dq, dt), pose_scale=scale)
         ctx.renderer.pending_backward = False
-        return (None, None, dq.reshape(ctx.pose_shapes[0]), dt.reshape(ctx.pose_shapes[1]), None, None, None, None, None)
+        return (None, None, dq.reshape(ctx.pose_shapes[0]), dt.reshape(ctx.pose_shapes[1]), None, None, None, None, None, None)
 
 
 class _FusedMappingLoss(torch.autograd.Function):
@@ -516,10 +580,18 @@ def get_loss(params, curr_data, variables, iter_time_idx, loss_weights, use_sil_
                        ignore_outlier_depth_loss=bool(ignore_outlier_depth_loss),
                        pixel_mask=(None if (vis_mask is None or dataset_name == 'replica')
                                    else vis_mask.reshape(curr_data['depth'].shape[-2:])))
+            # radius bookkeeping (:681-683) inside the same library call when the buffers allow it
+            m2r = variables['max_2D_radius']
+            book = None
+            if m2r.is_cuda and m2r.dtype == torch.float32 and m2r.is_contiguous() and m2r.shape[0] == r.N:
+                book = (m2r, torch.empty(r.N, dtype=torch.bool, device=m2r.device))
             loss, terms, radius = _FusedTrackingLoss.apply(r, params, cam_q, cam_t, curr_data['im'], curr_data['depth'], cfg, thres_fn,
-                                                           _poll_due(r, tracking_iteration))
+                                                           _poll_due(r, tracking_iteration), book)
             weighted_losses = {'depth': terms[2], 'im': terms[1], 'loss': loss}
-            _book_radii(variables, radius)
+            if book is not None:
+                variables['seen'] = book[1]
+            else:
+                _book_radii(variables, radius)
             if presence_sil_mask_mse_ls is not None:
                 return loss, variables, weighted_losses, presence_sil_mask_mse_ls, sil_thres_ls
             return loss, variables, weighted_losses
