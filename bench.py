@@ -613,6 +613,37 @@ def run_mapping_leg(args, wl, rank, world, dev, pg, iters=None, keyframes=8, sha
             "per_kernel_us_per_step": {k: round(t * 1e3 / 2, 2) for k, (n, t) in prof.items()}}
 
 
+def run_deterministic_leg(args, wl, dev, plain_ms):
+    """VTGS_BUF_DETERMINISTIC: the same tracking iteration with the order-independent (exact fp32 hi / lo grid) gradient
+    accumulation.  Reports its cost against the plain path and checks that two runs of the same 30 iterations end in
+    bitwise identical poses and losses."""
+    import torch
+    from vtgaussian_slam_b200.fused import TrackingSolver
+    fr = wl["frame"]
+    params = {k: torch.tensor(v, device=dev) for k, v in wl["params"].items()}
+    solver = TrackingSolver(make_settings(wl, dev), params, device=dev, w_im=LOSS_W["im"], w_depth=LOSS_W["depth"],
+                            sil_thres=SIL_THRES, use_graph=True, deterministic=True)
+    gt_rgb, gt_depth = torch.tensor(fr["im"]), torch.tensor(fr["depth"])
+    ends = []
+    for _ in range(2):
+        solver.set_frame(gt_rgb, gt_depth, wl["q"], wl["t"])
+        for _ in range(30):
+            solver.step()
+        torch.cuda.synchronize(dev)
+        ends.append(torch.cat([solver.cam_q, solver.cam_t, solver.msg]).cpu().numpy().tobytes())
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k = max(3, min(args.steps, 100))
+    e0.record()
+    for _ in range(k):
+        solver.step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / k
+    return {"value": 1e3 / ms, "unit": UNIT, "ms_per_step": ms, "slowdown_vs_plain": ms / plain_ms - 1.0,
+            "bitwise_repeatable_30_iterations": ends[0] == ends[1],
+            "how": "TrackingSolver(deterministic=True): K6' partial sums split onto per-Gaussian power-of-two grids (exact, order-independent fp32 sums), K7' adds hi + lo"}
+
+
 def run_c1_leg(dev, with_cpu):
     """configs[0]: one fwd+bwd of the ~300 k-Gaussian frame (tracking loss), GPU (CUDA events) and CPU oracle."""
     import torch
@@ -742,6 +773,9 @@ def run_ours(args, wl):
         cpu, parity, exact = run_cpu_and_parity(wl, dev)
     mapping = None if args.no_extra else run_mapping_leg(args, wl, rank, world, dev, pg)
     configs = None
+    det = None
+    if not args.no_extra and world == 1 and rank == 0:
+        det = run_deterministic_leg(args, wl, dev, ms_per_step)
     if not args.no_extra and args.workload == "c2":
         configs = {}
         if world == 1:
@@ -812,7 +846,7 @@ def run_ours(args, wl):
             "counters": {"pairs_R": R, "pair_tests_S": S, "contributing_pairs_K": K, "pixels_P": P, "loss_after_run": tr["loss_now"]},
             "clocks": tr["clocks"], "e2e": tr["e2e"], "gpu_launches": tr["launches_per_step"] * args.steps,
             "launches_per_step": tr["launches_per_step"], "roofline": roofline, "cpu_baseline": cpu, "parity_check": parity,
-            "mapping": mapping, "configs": configs,
+            "mapping": mapping, "configs": configs, "deterministic": det,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -188,7 +188,8 @@ VTGS_API int vtgs_workspace_query(int32_t image_width, int32_t image_height, int
  * Forward: replaces _C.rasterize_gaussians (K1..K5 of SURVEY.md section 2.3), the call behind the reference's
  * `Renderer(raster_settings=curr_data['cam'])(**rendervar)` (src/vtgaussian_slam.py:461, :466, :747;
  * utils/eval_helpers.py:240, :247, :431, :443, :728, :733; settings built at utils/recon_helpers.py:14-26).
- * num_gaussians < 2^24 (24-bit Gaussian id in the sort key): VTGS_E_UNSUPPORTED beyond.
+ * num_gaussians < 2^32 (32-bit Gaussian ids, as in the reference's keys; below 2^24 the low key byte also carries the
+ * splat's region mask, from 2^24 on it is re-derived from the record): VTGS_E_UNSUPPORTED beyond.
  *   means3D[N,3] scales[N,3] rotations[N,4] opacities[N] colors[N,3]  ->
  *   out_color[3,H,W]  out_depth[H,W]  radii[N]
  * Colours are precomputed (the reference never passes SHs: sh_degree = 0).

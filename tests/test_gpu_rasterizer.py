@@ -207,3 +207,65 @@ def test_giant_offscreen_and_degenerate_splats():
     assert bit_exact
     gx, gy = (W + 15) // 16, (H + 15) // 16
     assert ref["tiles_touched"].max() == gx * gy                 # at least one giant covers every tile
+
+
+def test_gaussian_ids_beyond_24_bits():
+    """N >= 2^24: the sort key carries the full 32-bit Gaussian index (the reference's ids are 32-bit) and the region
+    masks are re-derived from the records.  2^24 culled Gaussians in front of a small scene must leave every stage
+    output of that scene unchanged (ids shifted by 2^24), forward and backward, in both entry points."""
+    from gpu_helpers import cuda_forward_all
+    from vtgaussian_slam_b200 import rasterizer
+    from vtgaussian_slam_b200.fused import FusedRenderer
+    from gpu_helpers import settings_from
+    W, H, n, PAD = 160, 96, 3000, 1 << 24
+    K, sc = synthetic.random_scene(n, W, H, seed=11)
+    _, s = oracle_camera(W, H, K)
+    ref, cam, ws = cuda_forward_all(s, sc)
+    dL = torch.randn(3, H, W, generator=torch.Generator().manual_seed(3)).cuda()
+    g_ref = [t.clone() for t in rasterizer.rasterize_backward(cam, ws, dL)]
+    pad = dict(means3D=np.tile(np.array([[0.0, 0.0, -5.0]], np.float32), (PAD, 1)),          # behind the camera: culled
+               scales=np.full((PAD, 3), 0.01, np.float32), rotations=np.tile(np.array([[1.0, 0, 0, 0]], np.float32), (PAD, 1)),
+               opacities=np.full((PAD,), 0.5, np.float32), colors=np.zeros((PAD, 3), np.float32))
+    big = {k: np.concatenate([pad[k], sc[k]]) for k in sc}
+    del pad
+    got, cam2, ws2 = cuda_forward_all(s, big)
+    assert got["R"] == ref["R"] and np.array_equal(got["ranges"], ref["ranges"])
+    assert np.array_equal(got["point_list"].astype(np.int64), ref["point_list"].astype(np.int64) + PAD)
+    assert np.array_equal(got["keys"], ref["keys"])
+    assert not got["radii"][:PAD].any() and np.array_equal(got["radii"][PAD:], ref["radii"])
+    for k in ("color", "depth", "final_T", "n_contrib"):
+        assert np.array_equal(got[k], ref[k]), k
+    g = rasterizer.rasterize_backward(cam2, ws2, dL)
+    for a, b in zip(g, g_ref):
+        a = a.reshape(PAD + n, -1)
+        assert not a[:PAD].any()
+        assert rel_err(a[PAD:].cpu().numpy(), b.reshape(n, -1).cpu().numpy()) <= 1e-5
+    del g, ws2, got, big
+    torch.cuda.empty_cache()
+    # fused six-plane path (isotropic parameters)
+    fr = synthetic.make_frame("replica", 160, 96, seed=0)
+    p = synthetic.view_tied_gaussians(fr, n_edge=500, opacity="trained")
+    settings = settings_from(synthetic.setup_camera(fr["W"], fr["H"], fr["K"], np.eye(4)), torch.device("cuda:0"))
+    q, t = synthetic.perturbed_pose(seed=1, trans_sigma=0.01, rot_deg=0.5)
+    q, t = torch.tensor(q).cuda(), torch.tensor(t).cuda()
+    small = {k: torch.tensor(v).cuda() for k, v in p.items()}
+    n2 = small["means3D"].shape[0]
+    r0 = FusedRenderer(settings, n2)
+    img0 = r0.forward(small, q, t)[0].clone()
+    far = {k: torch.zeros((PAD,) + v.shape[1:], device="cuda") for k, v in small.items()}
+    far["means3D"][:, 2] = -5.0
+    far["unnorm_rotations"][:, 0] = 1.0
+    bigp = {k: torch.cat([far[k], small[k]]).contiguous() for k in small}
+    del far
+    r1 = FusedRenderer(settings, PAD + n2)
+    img1, radii1 = r1.forward(bigp, q, t)
+    assert torch.equal(img1, img0) and not radii1[:PAD].any()
+    gt_rgb, gt_d = torch.tensor(fr["im"]).cuda(), torch.tensor(fr["depth"]).cuda()
+    grads = []
+    for r, prm in ((r0, small), (r1, bigp)):
+        r.forward(prm, q, t)
+        r.tracking_loss(gt_rgb, gt_d)
+        dq, dt = torch.zeros(4).cuda(), torch.zeros(3).cuda()
+        r.backward(prm, q, t, pose_grads=(dq, dt))
+        grads.append(torch.cat([dq, dt]).cpu().numpy())
+    assert rel_err(grads[1], grads[0]) <= 1e-5

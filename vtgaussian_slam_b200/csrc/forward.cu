@@ -431,6 +431,12 @@ tile_scan_kernel(uint32_t* __restrict__ tile_counts, uint32_t* __restrict__ rang
 // One thread per Gaussian: for every touched tile claim a slot in that tile's segment and
 // store (depth_bits << 32 | id).  Slot order inside a segment is arbitrary; the per-tile
 // sort on the composite key makes the final order deterministic.
+// WIDE (N >= 2^24): the low word is the full 32-bit Gaussian index, as in the reference's keys; the region mask that
+// otherwise rides in the low byte is re-derived from the record when the tile's region lists are built.
+template <bool WIDE>
+__device__ __forceinline__ uint32_t key_id(uint32_t lo) { return WIDE ? lo : lo >> 8; }
+
+template <bool WIDE>
 __global__ void __launch_bounds__(256)
 scatter_kernel(int64_t N, int gx, const GeomRecord* __restrict__ geom, const uint32_t* __restrict__ tiles_touched,
                const uint32_t* __restrict__ ranges, uint32_t* __restrict__ tile_cursor,
@@ -447,7 +453,7 @@ scatter_kernel(int64_t N, int gx, const GeomRecord* __restrict__ geom, const uin
         q0 = geom[i].q0;
         const uint32_t rmin = __float_as_uint(q3.z), rmax = __float_as_uint(q3.w);
         minx = rmin & 0xffff; miny = rmin >> 16; maxx = rmax & 0xffff; maxy = rmax >> 16;
-        key = ((uint64_t)__float_as_uint(q3.x) << 32) | ((uint64_t)(uint32_t)i << 8);
+        key = ((uint64_t)__float_as_uint(q3.x) << 32) | (WIDE ? (uint64_t)(uint32_t)i : ((uint64_t)(uint32_t)i << 8));
     }
     warp_tile_walk(minx, miny, maxx, maxy, gx, [&](int tile, int tx, int ty, uint32_t peers, int rank, bool leader) {
         uint32_t base = 0;
@@ -456,7 +462,7 @@ scatter_kernel(int64_t N, int gx, const GeomRecord* __restrict__ geom, const uin
         const uint32_t pos = base + (uint32_t)rank;
         // low 8 bits: which of this tile's 8 warp regions the splat's alpha >= 1/255 box touches (ids are unique, so
         // these bits never decide the order; the sort kernel reads them back instead of gathering the record again)
-        const uint32_t rmask = region_mask(q0, (float)(tx * 16), (float)(ty * 16));
+        const uint32_t rmask = WIDE ? 0u : region_mask(q0, (float)(tx * 16), (float)(ty * 16));
         if (pos < ranges[2 * tile + 1]) pair_keys[pos] = key | rmask;
     });
     }
@@ -550,7 +556,7 @@ __device__ __forceinline__ void bitonic_regs(uint64_t (&v)[E], uint64_t* __restr
     }
 }
 
-template <int E>
+template <int E, bool WIDE>
 __device__ __forceinline__ void sort_segment_regs(uint64_t* __restrict__ s_x, uint64_t* __restrict__ keys, uint32_t* __restrict__ ids,
                                                   int n, int tid) {
     uint64_t v[E];
@@ -565,7 +571,7 @@ __device__ __forceinline__ void sort_segment_regs(uint64_t* __restrict__ s_x, ui
 #pragma unroll
     for (int e = 0; e < E; ++e) {
         const int i = tid * E + e;
-        if (i < n) { keys[i] = v[e]; ids[i] = (uint32_t)v[e] >> 8; }
+        if (i < n) { keys[i] = v[e]; ids[i] = key_id<WIDE>((uint32_t)v[e]); }
     }
 }
 
@@ -852,8 +858,9 @@ __device__ __noinline__ void sort_segment_radix_long(uint64_t* keys, uint64_t* s
 // walk only their own region's list: the culling is done once per (tile, splat) here instead of once per
 // (warp, splat) in each of the two blend kernels.
 // Arena: region r of a tile with list [rb, re) owns slots [8 rb + r (re - rb), 8 rb + (r + 1)(re - rb)).
-__device__ __forceinline__ void build_region_lists(const uint64_t* keys, int n, uint32_t rb, int tile,
-                                                   uint2* __restrict__ region_pairs, uint32_t* __restrict__ region_cnt) {
+template <bool WIDE>
+__device__ __forceinline__ void build_region_lists(const uint64_t* keys, int n, uint32_t rb, int tile, const GeomRecord* __restrict__ geom,
+                                                   float tox, float toy, uint2* __restrict__ region_pairs, uint32_t* __restrict__ region_cnt) {
     // warp r compacts region r's entries of the whole (sorted) list: ballot + prefix popcount keep the list order,
     // the running base lives in a register -- no shared counters, no block barriers between chunks
     const int tid = threadIdx.x, lane = tid & 31, r = tid >> 5;
@@ -864,24 +871,27 @@ __device__ __forceinline__ void build_region_lists(const uint64_t* keys, int n, 
     int i0 = 0;
     for (; i0 + 64 <= n; i0 += 64) {                   // two chunks per trip: independent loads
         const uint32_t lo0 = (uint32_t)keys[i0 + lane], lo1 = (uint32_t)keys[i0 + 32 + lane];
-        const bool h0 = (lo0 >> r) & 1u, h1 = (lo1 >> r) & 1u;
+        const uint32_t rm0 = WIDE ? region_mask(geom[lo0].q0, tox, toy) : lo0, rm1 = WIDE ? region_mask(geom[lo1].q0, tox, toy) : lo1;
+        const bool h0 = (rm0 >> r) & 1u, h1 = (rm1 >> r) & 1u;
         const uint32_t b0 = __ballot_sync(VTGS_FULL_MASK, h0), b1 = __ballot_sync(VTGS_FULL_MASK, h1);
         const uint32_t base1 = base + (uint32_t)__popc(b0);
-        if (h0) out[base + __popc(b0 & lt)] = make_uint2(lo0 >> 8, (uint32_t)(i0 + lane) + 1u);
-        if (h1) out[base1 + __popc(b1 & lt)] = make_uint2(lo1 >> 8, (uint32_t)(i0 + 32 + lane) + 1u);
+        if (h0) out[base + __popc(b0 & lt)] = make_uint2(key_id<WIDE>(lo0), (uint32_t)(i0 + lane) + 1u);
+        if (h1) out[base1 + __popc(b1 & lt)] = make_uint2(key_id<WIDE>(lo1), (uint32_t)(i0 + 32 + lane) + 1u);
         base = base1 + (uint32_t)__popc(b1);
     }
     for (; i0 < n; i0 += 32) {
         const int i = i0 + lane;
         const uint32_t lo = i < n ? (uint32_t)keys[i] : 0u;
-        const bool h = (lo >> r) & 1u;
+        const uint32_t rm = WIDE ? (i < n ? region_mask(geom[lo].q0, tox, toy) : 0u) : lo;
+        const bool h = (rm >> r) & 1u;
         const uint32_t bal = __ballot_sync(VTGS_FULL_MASK, h);
-        if (h) out[base + __popc(bal & lt)] = make_uint2(lo >> 8, (uint32_t)i + 1u);
+        if (h) out[base + __popc(bal & lt)] = make_uint2(key_id<WIDE>(lo), (uint32_t)i + 1u);
         base += (uint32_t)__popc(bal);
     }
     if (lane == 0) region_cnt[(size_t)tile * 8 + r] = base;
 }
 
+template <bool WIDE>
 __global__ void __launch_bounds__(256, 4)
 tile_sort_kernel(const __grid_constant__ CamConst cam, const uint32_t* __restrict__ ranges, int tile0,
                  uint64_t* __restrict__ pair_keys, uint32_t* __restrict__ point_list, const GeomRecord* __restrict__ geom,
@@ -897,7 +907,7 @@ tile_sort_kernel(const __grid_constant__ CamConst cam, const uint32_t* __restric
         return;
     }
     const uint64_t* sorted = pair_keys + b;
-    if (n <= 256) sort_segment_regs<2>(s_keys, pair_keys + b, point_list + b, n, threadIdx.x);
+    if (n <= 256) sort_segment_regs<2, WIDE>(s_keys, pair_keys + b, point_list + b, n, threadIdx.x);
     else if (n <= 2048) {
         const uint64_t* in = pair_keys + b;
         const int tid = threadIdx.x;
@@ -909,14 +919,14 @@ tile_sort_kernel(const __grid_constant__ CamConst cam, const uint32_t* __restric
         for (int i = tid; i < n; i += 256) {
             const uint64_t k = s_keys[i];
             pair_keys[b + i] = k;
-            point_list[b + i] = (uint32_t)k >> 8;
+            point_list[b + i] = key_id<WIDE>((uint32_t)k);
         }
         sorted = s_keys;
     } else {
         sort_segment_radix_long(pair_keys + b, reinterpret_cast<uint64_t*>(region_pairs + (size_t)8 * b), s_wh, s_cnt, n, threadIdx.x);
-        for (int i = threadIdx.x; i < n; i += 256) point_list[b + i] = (uint32_t)pair_keys[b + i] >> 8;
+        for (int i = threadIdx.x; i < n; i += 256) point_list[b + i] = key_id<WIDE>((uint32_t)pair_keys[b + i]);
     }
-    build_region_lists(sorted, n, b, tile, region_pairs, region_cnt);
+    build_region_lists<WIDE>(sorted, n, b, tile, geom, (float)((tile % cam.gx) * 16), (float)((tile / cam.gx) * 16), region_pairs, region_cnt);
 }
 
 // =============================== K5': forward blend ========================================
@@ -1120,7 +1130,8 @@ int launch_forward(const VtgsCamera* camera, int64_t N, bool fused, const FrontE
     const CamConst cam = make_cam_const(*camera);
     const int num_tiles = cam.gx * cam.gy;
     if (cam.gx > 0xffff || cam.gy > 0xffff) { set_error("image too large for packed tile rects"); return VTGS_E_INVALID; }
-    if (N >= (int64_t)1 << 24) { set_error("at most 2^24 - 1 Gaussians per render (24-bit id in the sort key)"); return VTGS_E_UNSUPPORTED; }
+    if (N > (int64_t)0xffffffffll) { set_error("at most 2^32 - 1 Gaussians per render (32-bit id in the sort key, as in the reference)"); return VTGS_E_UNSUPPORTED; }
+    const bool wide = N >= ((int64_t)1 << 24);          // the compact key (id << 8 | region mask) holds 24-bit ids
     GeomRecord* geom = reinterpret_cast<GeomRecord*>(buf->geom);
     VTGS_CUDA_CHECK(cudaMemsetAsync(buf->tile_counts, 0, sizeof(uint32_t) * (num_tiles + 3), stream));     // + the candidate-list counter, max |colour|, max |dL/dpixel|
     const int blocks = (int)((N + 255) / 256);
@@ -1159,12 +1170,18 @@ int launch_forward(const VtgsCamera* camera, int64_t N, bool fused, const FrontE
     { VTGS_PROF("tile_scan_kernel", stream); tile_scan_kernel<<<1, 1024, 0, stream>>>(buf->tile_counts + scan0, buf->tile_ranges + 2 * (size_t)scan0, scan_n, buf->pair_capacity, buf->counters, order); }
     VTGS_LAUNCH_CHECK();
     if (N > 0 && band_tiles > 0) {
-        { VTGS_PROF("scatter_kernel", stream); scatter_kernel<<<use_cand ? std::min(blocks, 148 * 8) : blocks, 256, 0, stream>>>(N, cam.gx, geom, buf->tiles_touched, buf->tile_ranges, buf->tile_counts, buf->pair_keys, cand, n_cand); }
+        { VTGS_PROF("scatter_kernel", stream); const int sb = use_cand ? std::min(blocks, 148 * 8) : blocks;
+          if (wide) scatter_kernel<true><<<sb, 256, 0, stream>>>(N, cam.gx, geom, buf->tiles_touched, buf->tile_ranges, buf->tile_counts, buf->pair_keys, cand, n_cand);
+          else scatter_kernel<false><<<sb, 256, 0, stream>>>(N, cam.gx, geom, buf->tiles_touched, buf->tile_ranges, buf->tile_counts, buf->pair_keys, cand, n_cand); }
         VTGS_LAUNCH_CHECK();
         static std::atomic<uint64_t> sort_attr{0};
-        if (first_call_on_device(sort_attr))
-            VTGS_CUDA_CHECK(cudaFuncSetAttribute(tile_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_SMEM_ELEMS * 8));
-        { VTGS_PROF("tile_sort_kernel", stream); tile_sort_kernel<<<band_tiles, 256, SORT_SMEM_ELEMS * 8, stream>>>(cam, buf->tile_ranges, cam.row0 * cam.gx, buf->pair_keys, buf->point_list, geom, reinterpret_cast<uint2*>(buf->region_pairs), buf->region_cnt, order); }
+        if (first_call_on_device(sort_attr)) {
+            VTGS_CUDA_CHECK(cudaFuncSetAttribute(tile_sort_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_SMEM_ELEMS * 8));
+            VTGS_CUDA_CHECK(cudaFuncSetAttribute(tile_sort_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_SMEM_ELEMS * 8));
+        }
+        { VTGS_PROF("tile_sort_kernel", stream);
+          if (wide) tile_sort_kernel<true><<<band_tiles, 256, SORT_SMEM_ELEMS * 8, stream>>>(cam, buf->tile_ranges, cam.row0 * cam.gx, buf->pair_keys, buf->point_list, geom, reinterpret_cast<uint2*>(buf->region_pairs), buf->region_cnt, order);
+          else tile_sort_kernel<false><<<band_tiles, 256, SORT_SMEM_ELEMS * 8, stream>>>(cam, buf->tile_ranges, cam.row0 * cam.gx, buf->pair_keys, buf->point_list, geom, reinterpret_cast<uint2*>(buf->region_pairs), buf->region_cnt, order); }
         VTGS_LAUNCH_CHECK();
     }
     if (N <= 0) VTGS_CUDA_CHECK(cudaMemsetAsync(buf->region_cnt, 0, sizeof(uint32_t) * 8 * num_tiles, stream));
