@@ -541,7 +541,9 @@ def run_cpu_and_parity(wl, dev):
 def run_mapping_leg(args, wl, rank, world, dev, pg, iters=None, keyframes=8, shape="replica"):
     """BASELINE configs[2]: one mapping iteration = a batch of `keyframes` posed keyframes of one section split over the
     ranks (keyframe k -> rank k mod world): fused six-plane render, SSIM mapping loss, backward to the Gaussian
-    parameters; ONE flat all-reduce of the parameter gradients and a replicated Adam step.  Strong scaling (fixed batch).
+    parameters; then ONE kernel over NVLink peer memory that reduce-scatters the gradients, steps Adam on the rank's slice
+    and all-gathers the new parameters (NCCL all-reduce + replicated Adam where peer mapping is unavailable; the plain
+    all-reduce of the same message is timed beside it).  Strong scaling (fixed batch).
     -> dict (identical on every rank)."""
     import torch
     import torch.distributed as dist
@@ -577,7 +579,7 @@ def run_mapping_leg(args, wl, rank, world, dev, pg, iters=None, keyframes=8, sha
     e1.record()
     torch.cuda.synchronize(dev)
     ms_t = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    ar_us = None
+    ar_us = step_us = None
     if world > 1:
         dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
         # the collective alone (same message, same stream), max over ranks
@@ -594,6 +596,20 @@ def run_mapping_leg(args, wl, rank, world, dev, pg, iters=None, keyframes=8, sha
         dist.all_reduce(at, op=dist.ReduceOp.MAX)
         ar_us = at.item() * 1e3
         ms.flat.zero_()
+        if ms.sharded is not None:
+            # the fused step alone: barrier + reduce-scatter / Adam / all-gather kernel + barrier (on zero gradients)
+            for _ in range(3):
+                ms._sharded_step()
+            torch.cuda.synchronize(dev)
+            dist.barrier()
+            e0.record()
+            for _ in range(10):
+                ms._sharded_step()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            st = torch.tensor([e0.elapsed_time(e1) / 10], device=dev)
+            dist.all_reduce(st, op=dist.ReduceOp.MAX)
+            step_us = st.item() * 1e3
     _lib.profile_enable(True)
     torch.cuda.synchronize(dev)
     for _ in range(2):
@@ -602,13 +618,20 @@ def run_mapping_leg(args, wl, rank, world, dev, pg, iters=None, keyframes=8, sha
     prof = _lib.profile_summary()
     _lib.profile_enable(False)
     msps = ms_t.item() / iters
-    loss = float(ms.total_loss.item())
+    loss = float((ms.total_loss if ms.sharded is None else ms.sharded["loss"]).item())
+    fused_step = ms.sharded is not None
+    multicast = bool(fused_step and ms.sharded["mc"])
+    sharded_error = ms.sharded_error
     del ms, kf
     torch.cuda.empty_cache()
     return {"workload": wl["name"].replace("tracking", "mapping"), "keyframes_per_step": K_total, "keyframes_per_rank": (K_total + world - 1) // world,
             "n_gpus": world, "steps": iters, "ms_per_step": msps, "value": K_total * 1e3 / msps, "unit": "keyframe fwd+bwd iters/s",
             "scaling": "strong", "loss_last": loss,
-            "collective": "all-reduce(SUM) of dL/d{rgb, logit_opacity, log_scale} = 5 N fp32 + loss",
+            "collective": ("ONE kernel over NVLink peer memory (vtgs_sharded_adam): reduce-scatter of dL/d{rgb, logit_opacity, "
+                           "log_scale} (5 N fp32) in rank order + Adam on the rank's slice (sharded moments) + all-gather of the "
+                           "new parameters, between two cross-device barriers") if fused_step else
+                          "NCCL all-reduce(SUM) of dL/d{rgb, logit_opacity, log_scale} = 5 N fp32 + loss, then a replicated Adam",
+            "fused_step": fused_step, "fused_step_nvls_multicast": multicast, "fused_step_us": step_us, "fused_step_unavailable": sharded_error,
             "allreduce_bytes": int(4 * (5 * N + 1)) if world > 1 else 0, "allreduce_us": ar_us,
             "per_kernel_us_per_step": {k: round(t * 1e3 / 2, 2) for k, (n, t) in prof.items()}}
 

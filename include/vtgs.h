@@ -401,6 +401,28 @@ VTGS_API int vtgs_adam(float* param, const float* grad, float* exp_avg, float* e
               const int32_t* step_dev, void* stream);
 
 /*
+ * Keyframe-sharded mapping step over NVLink peer memory (one process per GPU; reference: the optimizer.step() after the
+ * summed keyframe losses, src/vtgaussian_slam.py:2686-2694, when the keyframes of a mapping iteration are split over
+ * the ranks): reduce-scatter of the gradients + Adam + all-gather of the parameters in ONE kernel.
+ *   peer_bases[world]  HOST array: base address, in THIS process, of every rank's symmetric block (rank order); every
+ *                      block holds the flat parameters at float offset param_off, the rank's flat gradients at grad_off
+ *                      (n floats each, n % 4 == 0, 16-byte aligned) and the rank's loss at loss_off
+ *   multicast_base     0, or the address of the blocks' NVLS multicast object: the gradients are then reduced inside the
+ *                      NVSwitch (multimem.ld_reduce) and the parameters broadcast by it (multimem.st); the order of
+ *                      that in-switch sum is the hardware's
+ *   exp_avg, exp_avg_sq  THIS rank's slice of the moments: ceil(n / 4 / world) * 4 floats each
+ *   seg_end / lr [nseg <= 4]  the flat vector is nseg tensors laid end to end: tensor s ends at element seg_end[s]
+ *   step_dev           device int32: 1-based step count;   loss_out: device float, receives the summed loss
+ * Rank r sums slice r of all ranks' gradients in rank order (fixed order), updates it with torch.optim.Adam's rule and
+ * stores the new parameters into every rank's block.  The caller must run a cross-device barrier before the call
+ * (every rank's gradients are complete) and after it (every rank's parameters have landed).  world <= 8.
+ */
+VTGS_API int vtgs_sharded_adam(int32_t world, int32_t rank, const uint64_t* peer_bases, uint64_t multicast_base, int64_t param_off, int64_t grad_off,
+                       int64_t loss_off, float* exp_avg, float* exp_avg_sq, int64_t n, int32_t nseg, const int64_t* seg_end,
+                       const float* lr, float beta1, float beta2, float eps, const int32_t* step_dev, float* loss_out,
+                       void* stream);
+
+/*
  * Re-tie a section's view-tied Gaussians to its optimised pose (reference src/vtgaussian_slam.py:2706-2727):
  * means3D[i] <- inv([R(q)|t]) * (w2c_old * means3D[i]) for i in [0, n).  w2c_old: 12 HOST floats (rows of the 3x4
  * matrix the section was tied to); q = cam_unnorm_rot[4], t = cam_trans[3] on the DEVICE (the just-stepped pose).

@@ -471,3 +471,44 @@ def test_tile_band_shards_sum_to_the_full_frame():
     assert ((terms[:3] - full[2][:3]).abs() / full[2][:3].abs()).max().item() <= 1e-5
     g = sum(pt[3] for pt in parts)
     assert ((g - full[3]).abs().max() / full[3].abs().max()).item() <= 1e-4
+
+
+def test_sharded_adam_kernel_world1_matches_adam_step():
+    """vtgs_sharded_adam (the keyframe-sharded mapping step: reduce-scatter + Adam + all-gather over peer memory) with a
+    world of one rank: three tensors of different learning rates laid end to end in one block must move exactly as three
+    vtgs_adam calls move them (the multi-rank path is checked by tools/check_multi_gpu.py on 2 GPUs)."""
+    import ctypes as C
+    from vtgaussian_slam_b200 import _lib
+    from vtgaussian_slam_b200.fused import adam_step
+    g = torch.Generator().manual_seed(5)
+    sizes, lrs = [3 * 1001, 1001, 1001], [0.0025, 0.05, 0.005]
+    n = sum(sizes)
+    n_pad = (n + 3) // 4 * 4
+    block = torch.zeros(2 * n_pad + 4, device=DEV)
+    p0 = torch.randn(n, generator=g).to(DEV)
+    block[:n] = p0
+    ref_p = [p0[sum(sizes[:i]):sum(sizes[:i + 1])].clone() for i in range(3)]
+    ref_m = [torch.zeros_like(x) for x in ref_p]
+    ref_v = [torch.zeros_like(x) for x in ref_p]
+    m, v = torch.zeros(n_pad, device=DEV), torch.zeros(n_pad, device=DEV)
+    step = torch.zeros(1, dtype=torch.int32, device=DEV)
+    loss_out = torch.zeros(1, device=DEV)
+    seg_end = [sum(sizes[:i + 1]) for i in range(3)]
+    seg_end[-1] = n_pad
+    bases = (C.c_uint64 * 1)(block.data_ptr())
+    for it in range(4):
+        grad = torch.randn(n, generator=g).to(DEV)
+        block[n_pad:n_pad + n] = grad
+        block[2 * n_pad] = 1.5 + it
+        step.add_(1)
+        _lib.check(_lib.lib().vtgs_sharded_adam(1, 0, bases, 0, 0, n_pad, 2 * n_pad, C.c_void_p(m.data_ptr()), C.c_void_p(v.data_ptr()),
+                                                n_pad, 3, (C.c_int64 * 3)(*seg_end), (C.c_float * 3)(*lrs), 0.9, 0.999, 1e-15,
+                                                C.c_void_p(step.data_ptr()), C.c_void_p(loss_out.data_ptr()),
+                                                torch.cuda.current_stream().cuda_stream))
+        for i in range(3):
+            gi = grad[sum(sizes[:i]):sum(sizes[:i + 1])].contiguous()
+            adam_step(ref_p[i], gi, ref_m[i], ref_v[i], lrs[i], step_dev=step, eps=1e-15)
+        assert float(loss_out) == 1.5 + it
+    got = block[:n]
+    assert (got - torch.cat(ref_p)).abs().max().item() <= 1e-6          # (same update; the two kernels may contract differently)
+    assert not block[n:n_pad].any()

@@ -60,17 +60,24 @@ for k in range(4):
     kfs.append(dict(cam_q=torch.tensor(quat_from_matrix(w2c[:3, :3]).astype(np.float32), device=dev), cam_t=torch.tensor(w2c[:3, 3].astype(np.float32), device=dev),
                     gt_rgb=torch.tensor(fk["im"], device=dev), gt_depth=torch.tensor(fk["depth"], device=dev)))
 out = []
-for sharded in (False, True):
-    print(f"[rank {rank}] mapping sharded={sharded}", file=sys.stderr, flush=True)
-    ms = MappingSolver(settings, {k: torch.tensor(v, device=dev) for k, v in p.items()}, device=dev, process_group=pg if sharded else None)
+for mode in ("single", "nccl", "fused"):
+    print(f"[rank {rank}] mapping {mode}", file=sys.stderr, flush=True)
+    sharded = mode != "single"
+    ms = MappingSolver(settings, {k: torch.tensor(v, device=dev) for k, v in p.items()}, device=dev, process_group=pg if sharded else None,
+                       sharded_step=(mode == "fused") and "auto")
+    if mode == "fused" and rank == 0:
+        print("fused step (vtgs_sharded_adam over peer memory):", ("ON, NVLS multicast" if ms.sharded["mc"] else "ON, peer loads / stores") if ms.sharded is not None else f"unavailable: {ms.sharded_error}", flush=True)
     mine = kfs[rank::world] if sharded else kfs
     for _ in range(5):
         loss = ms.iteration(mine)
-    out.append((float(loss.item()), ms.params["rgb_colors"].cpu().numpy().copy()))
-good = abs(out[0][0] - out[1][0]) <= 1e-4 * abs(out[0][0]) and np.abs(out[0][1] - out[1][1]).max() <= 2e-3
+    out.append((float(loss.item()), ms.params["rgb_colors"].cpu().numpy().copy(), ms.params["log_scales"].cpu().numpy().copy()))
+good = True
+for o in out[1:]:
+    good &= abs(out[0][0] - o[0]) <= 1e-4 * abs(out[0][0]) and np.abs(out[0][1] - o[1]).max() <= 2e-3 and np.abs(out[0][2] - o[2]).max() <= 2e-3
 ok &= good
 if rank == 0:
-    print("mapping", "OK" if good else "MISMATCH", out[0][0], out[1][0], np.abs(out[0][1] - out[1][1]).max(), flush=True)
+    print("mapping", "OK" if good else "MISMATCH", [o[0] for o in out], [float(np.abs(out[0][1] - o[1]).max()) for o in out[1:]],
+          "fused vs nccl:", float(np.abs(out[1][1] - out[2][1]).max()), flush=True)
 flag = torch.tensor([1.0 if ok else 0.0], device=dev)
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 passed = flag.item() == 1.0

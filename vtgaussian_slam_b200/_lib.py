@@ -108,6 +108,8 @@ SYMBOLS = {
                                       C.POINTER(VtgsParamGrads), C.POINTER(VtgsBuffers), _P]),
     "vtgs_fused_tracking_step": (C.c_int, [C.POINTER(VtgsCamera), C.POINTER(VtgsParams), C.POINTER(VtgsPose), C.POINTER(VtgsLossConfig)] +
                                  [_P] * 7 + [C.POINTER(VtgsParamGrads), _P, _P, C.POINTER(VtgsBuffers), _P]),
+    "vtgs_sharded_adam": (C.c_int, [C.c_int32, C.c_int32, _P, C.c_uint64, C.c_int64, C.c_int64, C.c_int64, _P, _P, C.c_int64, C.c_int32, _P, _P,
+                                    C.c_float, C.c_float, C.c_float, _P, _P, _P]),
     "vtgs_retie": (C.c_int, [_P, C.c_int64, C.POINTER(C.c_float * 12), _P, _P, _P]),
     "vtgs_retie_dev": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, _P]),
     "vtgs_tracking_update": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_float, C.c_float, C.c_float, C.c_int32, _P]),

@@ -243,6 +243,19 @@ int vtgs_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq
     return launch_adam(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step, step_dev, (cudaStream_t)stream);
 }
 
+int vtgs_sharded_adam(int32_t world, int32_t rank, const uint64_t* peer_bases, uint64_t multicast_base, int64_t param_off, int64_t grad_off, int64_t loss_off,
+                      float* exp_avg, float* exp_avg_sq, int64_t n, int32_t nseg, const int64_t* seg_end, const float* lr, float beta1,
+                      float beta2, float eps, const int32_t* step_dev, float* loss_out, void* stream) {
+    VTGS_REQUIRE(world >= 1 && world <= 8 && rank >= 0 && rank < world, "world must be 1..8 and rank inside it");
+    VTGS_REQUIRE(peer_bases && exp_avg && exp_avg_sq && seg_end && lr && step_dev && loss_out, "pointer is NULL");
+    VTGS_REQUIRE(n >= 0 && n % 4 == 0 && param_off % 4 == 0 && grad_off % 4 == 0, "flat vectors must be multiples of 4 floats");
+    VTGS_REQUIRE(nseg >= 1 && nseg <= 4, "1..4 segments");
+    for (int k = 0; k < world; ++k) VTGS_REQUIRE(peer_bases[k] != 0 && (peer_bases[k] & 15) == 0, "peer base must be a 16-byte aligned address");
+    VTGS_REQUIRE((multicast_base & 15) == 0, "multicast base must be 16-byte aligned");
+    return launch_sharded_adam(world, rank, peer_bases, multicast_base, param_off, grad_off, loss_off, exp_avg, exp_avg_sq, n, nseg, seg_end, lr,
+                               beta1, beta2, eps, step_dev, loss_out, (cudaStream_t)stream);
+}
+
 int vtgs_tracking_update(float* cam_unnorm_rot, float* cam_trans, const float* msg, float* adam_state, int32_t* step_dev,
                          float* best, float lr_rot, float lr_trans, float eps, int32_t flags, void* stream) {
     VTGS_REQUIRE(cam_unnorm_rot && cam_trans && msg && adam_state && step_dev && best, "pointer is NULL");

@@ -3,6 +3,7 @@
 // with its gradient w.r.t. the rendered planes, and the Adam update
 // (torch.optim.Adam as configured at src/vtgaussian_slam.py:180-187).
 #include <algorithm>
+#include <cstdlib>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -757,6 +758,173 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
     float pi = p[i], mi = m[i], vi = v[i];
     upd(pi, g[i], mi, vi);
     p[i] = pi; m[i] = mi; v[i] = vi;
+}
+
+// ---- keyframe-sharded mapping step: reduce-scatter + Adam + all-gather in ONE kernel over NVLink peer memory ----------
+// Every rank holds the same symmetric block [params | gradients | loss] (torch symmetric memory: each rank's block is
+// mapped into every other rank's address space).  Rank r owns the r-th slice of the flat vectors: it reads that slice of
+// the gradients from ALL ranks (peer loads over NVLink, summed in rank order: a fixed order), applies Adam with ITS
+// slice of the moments (the optimiser state is sharded: 1 / world of the memory and of the work), and stores the
+// updated parameters into every rank's block (peer stores).  Per rank and step: n floats in, n floats out over NVLink,
+// against the all-reduce's 2 n (world - 1) / world each way plus a replicated Adam over all n.
+// The caller brackets the launch with two cross-device barriers (gradients complete before / parameters landed after).
+constexpr int SHARD_MAX_WORLD = 8;
+struct ShardedAdamArgs {
+    uint64_t base[SHARD_MAX_WORLD];   // peer base pointers of the symmetric block
+    uint64_t pbase[SHARD_MAX_WORLD];  // (the same blocks: where the new parameters are stored)
+    int64_t seg_end[4];               // flat layout: segment s = [seg_end[s-1], seg_end[s]) elements, learning rate lr[s]
+    float lr[4];
+    int nseg, world, rank;
+};
+
+// W: ranks (compile-time: the peer loads of one element are issued together), U: float4 per thread and trip, so that
+// about eight remote 16-byte loads are in flight per thread whatever the world size (an NVLink round trip is ~3 us)
+template <int W, int U>
+__global__ void __launch_bounds__(256)
+sharded_adam_kernel(const __grid_constant__ ShardedAdamArgs a, int64_t param_off, int64_t grad_off, int64_t loss_off,
+                    float* __restrict__ m, float* __restrict__ v, int64_t n4, float b1, float b2, float eps,
+                    const int32_t* __restrict__ step_dev, float* __restrict__ loss_out) {
+    __shared__ float s_step[4], s_bc2s;
+    if (threadIdx.x == 0) {
+        const int t = *step_dev;
+        const double bc1 = 1.0 - ipow((double)b1, t);
+        for (int k = 0; k < a.nseg; ++k) s_step[k] = (float)((double)a.lr[k] / bc1);
+        s_bc2s = (float)sqrt(1.0 - ipow((double)b2, t));
+        if (blockIdx.x == 0) {
+            float L = 0.0f;
+            for (int k = 0; k < a.world; ++k) L += reinterpret_cast<const float*>(a.base[k])[loss_off];
+            *loss_out = L;
+        }
+    }
+    __syncthreads();
+    const float bc2s = s_bc2s;
+    const int64_t per = (n4 + a.world - 1) / a.world;
+    const int64_t begin = per * a.rank, end = min(n4, begin + per);
+    const float4* gsrc[W];
+    float4* pdst[W];
+#pragma unroll
+    for (int k = 0; k < W; ++k) {
+        const int kk = k < a.world ? k : a.rank;          // (W > world: the spare slots alias this rank and are skipped)
+        gsrc[k] = reinterpret_cast<const float4*>(a.base[kk]) + grad_off / 4;
+        pdst[k] = reinterpret_cast<float4*>(a.pbase[kk]) + param_off / 4;
+    }
+    const float4* my_p = reinterpret_cast<const float4*>(a.base[a.rank]) + param_off / 4;   // identical everywhere: local copy
+    auto upd = [&](float& pi, const float gi, float& mi_, float& vi_, int64_t e) {
+        int sg = 0;
+        while (sg + 1 < a.nseg && e >= a.seg_end[sg]) ++sg;
+        const float mi = mi_ + (1.0f - b1) * (gi - mi_);
+        const float vi = b2 * vi_ + (1.0f - b2) * gi * gi;
+        mi_ = mi; vi_ = vi;
+        const float denom = sqrtf(vi) / bc2s + eps;
+        pi = pi - s_step[sg] * (mi / denom);
+    };
+    const int64_t stride = (int64_t)gridDim.x * 256;
+    for (int64_t j0 = begin + (int64_t)blockIdx.x * 256 + threadIdx.x; j0 < end; j0 += stride * U) {
+        float4 g[U][W];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t j = j0 + u * stride;
+#pragma unroll
+            for (int k = 0; k < W; ++k)
+                if (k < a.world && j < end) g[u][k] = gsrc[k][j];
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t j = j0 + u * stride;
+            if (j >= end) break;
+            float4 gs = g[u][0];
+#pragma unroll
+            for (int k = 1; k < W; ++k)
+                if (k < a.world) { gs.x += g[u][k].x; gs.y += g[u][k].y; gs.z += g[u][k].z; gs.w += g[u][k].w; }
+            float4 p4 = my_p[j], m4 = reinterpret_cast<float4*>(m)[j - begin], v4 = reinterpret_cast<float4*>(v)[j - begin];
+            upd(p4.x, gs.x, m4.x, v4.x, 4 * j); upd(p4.y, gs.y, m4.y, v4.y, 4 * j + 1);
+            upd(p4.z, gs.z, m4.z, v4.z, 4 * j + 2); upd(p4.w, gs.w, m4.w, v4.w, 4 * j + 3);
+            reinterpret_cast<float4*>(m)[j - begin] = m4; reinterpret_cast<float4*>(v)[j - begin] = v4;
+#pragma unroll
+            for (int k = 0; k < W; ++k)
+                if (k < a.world) pdst[k][j] = p4;
+        }
+    }
+}
+
+// The same step through the NVSwitch's multicast object (NVLS), when torch's symmetric memory could bind one: ONE
+// multimem.ld_reduce pulls the sum of a 16-byte vector over all ranks (reduced inside the switch: the rank receives its
+// slice once instead of `world` times) and ONE multimem.st pushes the new parameters to every rank.
+__global__ void __launch_bounds__(256)
+sharded_adam_mc_kernel(const __grid_constant__ ShardedAdamArgs a, uint64_t mc_base, int64_t param_off, int64_t grad_off,
+                       int64_t loss_off, float* __restrict__ m, float* __restrict__ v, int64_t n4, float b1, float b2, float eps,
+                       const int32_t* __restrict__ step_dev, float* __restrict__ loss_out) {
+    __shared__ float s_step[4], s_bc2s;
+    if (threadIdx.x == 0) {
+        const int t = *step_dev;
+        const double bc1 = 1.0 - ipow((double)b1, t);
+        for (int k = 0; k < a.nseg; ++k) s_step[k] = (float)((double)a.lr[k] / bc1);
+        s_bc2s = (float)sqrt(1.0 - ipow((double)b2, t));
+        if (blockIdx.x == 0) {
+            float L;
+            asm volatile("multimem.ld_reduce.relaxed.sys.global.add.f32 %0, [%1];" : "=f"(L) : "l"(reinterpret_cast<const float*>(mc_base) + loss_off) : "memory");
+            *loss_out = L;
+        }
+    }
+    __syncthreads();
+    const float bc2s = s_bc2s;
+    const int64_t per = (n4 + a.world - 1) / a.world;
+    const int64_t begin = per * a.rank, end = min(n4, begin + per);
+    const float4* mc_g = reinterpret_cast<const float4*>(mc_base) + grad_off / 4;
+    float4* mc_p = reinterpret_cast<float4*>(mc_base) + param_off / 4;
+    const float4* my_p = reinterpret_cast<const float4*>(a.base[a.rank]) + param_off / 4;
+    auto upd = [&](float& pi, const float gi, float& mi_, float& vi_, int64_t e) {
+        int sg = 0;
+        while (sg + 1 < a.nseg && e >= a.seg_end[sg]) ++sg;
+        const float mi = mi_ + (1.0f - b1) * (gi - mi_);
+        const float vi = b2 * vi_ + (1.0f - b2) * gi * gi;
+        mi_ = mi; vi_ = vi;
+        const float denom = sqrtf(vi) / bc2s + eps;
+        pi = pi - s_step[sg] * (mi / denom);
+    };
+    constexpr int U = 4;
+    const int64_t stride = (int64_t)gridDim.x * 256;
+    for (int64_t j0 = begin + (int64_t)blockIdx.x * 256 + threadIdx.x; j0 < end; j0 += stride * U) {
+        float4 gs[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t j = j0 + u * stride;
+            if (j < end)
+                asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                             : "=f"(gs[u].x), "=f"(gs[u].y), "=f"(gs[u].z), "=f"(gs[u].w) : "l"(mc_g + j) : "memory");
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t j = j0 + u * stride;
+            if (j >= end) break;
+            float4 p4 = my_p[j], m4 = reinterpret_cast<float4*>(m)[j - begin], v4 = reinterpret_cast<float4*>(v)[j - begin];
+            upd(p4.x, gs[u].x, m4.x, v4.x, 4 * j); upd(p4.y, gs[u].y, m4.y, v4.y, 4 * j + 1);
+            upd(p4.z, gs[u].z, m4.z, v4.z, 4 * j + 2); upd(p4.w, gs[u].w, m4.w, v4.w, 4 * j + 3);
+            reinterpret_cast<float4*>(m)[j - begin] = m4; reinterpret_cast<float4*>(v)[j - begin] = v4;
+            asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
+                         :: "l"(mc_p + j), "f"(p4.x), "f"(p4.y), "f"(p4.z), "f"(p4.w) : "memory");
+        }
+    }
+}
+
+int launch_sharded_adam(int world, int rank, const uint64_t* bases, uint64_t mc_base, int64_t param_off, int64_t grad_off, int64_t loss_off,
+                        float* m, float* v, int64_t n, int nseg, const int64_t* seg_end, const float* lr, float b1, float b2,
+                        float eps, const int32_t* step_dev, float* loss_out, cudaStream_t stream) {
+    ShardedAdamArgs a{};
+    a.nseg = nseg; a.world = world; a.rank = rank;
+    for (int k = 0; k < world; ++k) a.base[k] = bases[k];
+    for (int k = 0; k < world; ++k) a.pbase[k] = bases[k];
+    for (int k = 0; k < nseg; ++k) { a.seg_end[k] = seg_end[k]; a.lr[k] = lr[k]; }
+    const int64_t n4 = n / 4;
+    int blocks = 148 * 4;
+    if (const char* e = getenv("VTGS_SHARD_BLOCKS")) blocks = std::max(1, atoi(e));      // tools/bench_sharded_step.py (8 B200: flat from 296 blocks on)
+    { VTGS_PROF("sharded_adam_kernel", stream);
+      if (mc_base != 0) sharded_adam_mc_kernel<<<blocks, 256, 0, stream>>>(a, mc_base, param_off, grad_off, loss_off, m, v, n4, b1, b2, eps, step_dev, loss_out);
+      else if (world <= 2) sharded_adam_kernel<2, 4><<<blocks, 256, 0, stream>>>(a, param_off, grad_off, loss_off, m, v, n4, b1, b2, eps, step_dev, loss_out);
+      else if (world <= 4) sharded_adam_kernel<4, 2><<<blocks, 256, 0, stream>>>(a, param_off, grad_off, loss_off, m, v, n4, b1, b2, eps, step_dev, loss_out);
+      else sharded_adam_kernel<8, 1><<<blocks, 256, 0, stream>>>(a, param_off, grad_off, loss_off, m, v, n4, b1, b2, eps, step_dev, loss_out); }
+    VTGS_LAUNCH_CHECK();
+    return VTGS_OK;
 }
 
 // ---- tracking pose update: best-candidate bookkeeping + Adam on the 7 pose numbers, one launch ----

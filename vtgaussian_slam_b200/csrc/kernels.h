@@ -75,5 +75,8 @@ int launch_retie(float* means3D, int64_t n, const float* w2c_old_rowmajor12, con
 int launch_retie_dev(float* means3D, int64_t n, const float* q_old, const float* t_old, const float* q_un, const float* t, cudaStream_t stream);
 int launch_adam(float* param, const float* grad, float* m, float* v, int64_t n, float lr, float b1,
                 float b2, float eps, int step, const int32_t* step_dev, cudaStream_t stream);
+int launch_sharded_adam(int world, int rank, const uint64_t* bases, uint64_t mc_base, int64_t param_off, int64_t grad_off, int64_t loss_off,
+                        float* m, float* v, int64_t n, int nseg, const int64_t* seg_end, const float* lr, float b1, float b2,
+                        float eps, const int32_t* step_dev, float* loss_out, cudaStream_t stream);
 
 }  // namespace vtgs

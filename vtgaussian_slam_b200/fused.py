@@ -13,6 +13,7 @@ All compute is in libvtgs_cuda.so (include/vtgs.h); no CPU path.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 
@@ -502,7 +503,7 @@ class MappingSolver:
         to its pose after the step (:2706-2727)."""
 
     def __init__(self, settings, params, device="cuda:0", lrs=None, eps=1e-15, pair_capacity=None, process_group=None,
-                 global_params=None, poll_every=16, deterministic=None):
+                 global_params=None, poll_every=16, deterministic=None, sharded_step="auto"):
         self.device = torch.device(device)
         self.params = {k: params[k].detach().to(self.device).float().contiguous() for k in PARAM_KEYS}
         N = self.params["means3D"].shape[0]
@@ -525,11 +526,69 @@ class MappingSolver:
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.pg = process_group
         self.total_loss = self.flat[-1:]
+        # keyframe shards: the step after the backward is ONE kernel over NVLink peer memory (reduce-scatter + Adam on
+        # this rank's slice + all-gather of the new parameters, `vtgs_sharded_adam`) when torch's symmetric memory can
+        # map the ranks' blocks into each other; otherwise one NCCL all-reduce followed by a replicated Adam
+        self.sharded = None
+        self.sharded_error = None
+        world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
+        if world > 1 and sharded_step and os.environ.get("VTGS_SHARDED_STEP", "1") != "0":
+            try:
+                self._setup_sharded(sizes, world)
+            except Exception as e:             # no peer mapping on this box: NCCL path
+                if sharded_step is True:
+                    raise
+                self.sharded, self.sharded_error = None, repr(e)[:300]
         self.poll_every = int(poll_every)
         self._iters = 0
         self.gparams = self.r_global = self.ggrads = None
         if global_params is not None:
             self.set_global(global_params)
+
+    def _setup_sharded(self, sizes, world):
+        import torch.distributed._symmetric_memory as symm
+        if world > 8:
+            raise RuntimeError("vtgs_sharded_adam supports up to 8 ranks")
+        n = sum(sizes.values())
+        n_pad = (n + 3) // 4 * 4
+        block = symm.empty(2 * n_pad + 4, dtype=torch.float32, device=self.device)
+        hdl = symm.rendezvous(block, self.pg)
+        block.zero_()
+        pflat, gflat = block[:n_pad], block[n_pad:2 * n_pad]
+        off, seg_end = 0, []
+        for k, cnt in sizes.items():
+            view = pflat[off:off + cnt].view(self.params[k].shape)
+            view.copy_(self.params[k])
+            self.params[k] = view                       # the learnable parameters now live in the symmetric block
+            self.grads[k] = gflat[off:off + cnt].view(self.params[k].shape)
+            off += cnt
+            seg_end.append(off)
+        seg_end[-1] = n_pad
+        rank = torch.distributed.get_rank(self.pg)
+        per = ((n_pad // 4 + world - 1) // world) * 4
+        self.flat = gflat                               # (kept for callers that time the plain all-reduce of the message)
+        self.total_loss = block[2 * n_pad:2 * n_pad + 1]
+        nseg = len(seg_end)
+        self.sharded = dict(
+            hdl=hdl, block=block, n=n_pad, world=world, rank=rank, nseg=nseg,
+            mc=(int(getattr(hdl, "multicast_ptr", 0) or 0) if os.environ.get("VTGS_SHARDED_MULTICAST", "0") == "1" else 0),
+            bases=(C.c_uint64 * world)(*[int(p_) for p_ in hdl.buffer_ptrs]),
+            seg_end=(C.c_int64 * nseg)(*seg_end), lr=(C.c_float * nseg)(*[float(self.lrs[k]) for k in sizes]),
+            m=torch.zeros(per, dtype=torch.float32, device=self.device), v=torch.zeros(per, dtype=torch.float32, device=self.device),
+            loss=torch.zeros(1, dtype=torch.float32, device=self.device))
+        self.m = self.v = None                          # the moments are sharded: this rank keeps its slice only
+        torch.cuda.synchronize(self.device)
+        hdl.barrier(channel=0)
+
+    def _sharded_step(self):
+        sh = self.sharded
+        sh["hdl"].barrier(channel=0)                    # every rank's gradients are complete
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().vtgs_sharded_adam(sh["world"], sh["rank"], sh["bases"], sh["mc"], 0, sh["n"], 2 * sh["n"], _ptr(sh["m"]),
+                                                    _ptr(sh["v"]), sh["n"], sh["nseg"], sh["seg_end"], sh["lr"], 0.9, 0.999,
+                                                    float(self.eps), _ptr(self.step_dev), _ptr(sh["loss"]),
+                                                    _stream_ptr(self.device)))
+        sh["hdl"].barrier(channel=0)                    # every rank's new parameters have landed
 
     def set_global(self, global_params):
         gp = {k: global_params[k].detach().to(self.device).float().contiguous() for k in PARAM_KEYS}
@@ -598,12 +657,15 @@ class MappingSolver:
         else:
             raise _lib.VtgsError("pair buffer overflow persisted after regrowing")
         self._iters += 1
-        if self.pg is not None:
-            # keyframe sharding: ONE all-reduce (SUM) of the flat gradient message over NVLink (5 N fp32 + loss)
-            torch.distributed.all_reduce(self.flat, group=self.pg)
         self.step_dev.add_(1)
-        for k, lr in self.lrs.items():
-            adam_step(self.params[k], self.grads[k], self.m[k], self.v[k], lr, step_dev=self.step_dev, eps=self.eps)
+        if self.sharded is not None:
+            self._sharded_step()
+        else:
+            if self.pg is not None:
+                # keyframe sharding: ONE all-reduce (SUM) of the flat gradient message over NVLink (5 N fp32 + loss)
+                torch.distributed.all_reduce(self.flat, group=self.pg)
+            for k, lr in self.lrs.items():
+                adam_step(self.params[k], self.grads[k], self.m[k], self.v[k], lr, step_dev=self.step_dev, eps=self.eps)
         if do_ba:
             for kf in keyframes:
                 st = kf["_ba"]
@@ -622,4 +684,4 @@ class MappingSolver:
                 if n_last > 0:
                     # the section's newest Gaussians stay tied to the keyframe: pts <- c2w_new (w2c_old pts), :2706-2727
                     retie_dev(self.params["means3D"][-n_last:], st["old_q"], st["old_t"], kf["cam_q"], kf["cam_t"])
-        return self.total_loss
+        return self.total_loss if self.sharded is None else self.sharded["loss"]
