@@ -630,7 +630,8 @@ def run_mapping_leg(args, wl, rank, world, dev, pg, iters=None, keyframes=8, sha
             "collective": ("ONE kernel over NVLink peer memory (vtgs_sharded_adam): reduce-scatter of dL/d{rgb, logit_opacity, "
                            "log_scale} (5 N fp32) in rank order + Adam on the rank's slice (sharded moments) + all-gather of the "
                            "new parameters, between two cross-device barriers") if fused_step else
-                          "NCCL all-reduce(SUM) of dL/d{rgb, logit_opacity, log_scale} = 5 N fp32 + loss, then a replicated Adam",
+                          ("NCCL all-reduce(SUM) of dL/d{rgb, logit_opacity, log_scale} = 5 N fp32 + loss, then a replicated Adam" if world > 1
+                           else "none (single GPU): per-tensor Adam"),
             "fused_step": fused_step, "fused_step_nvls_multicast": multicast, "fused_step_us": step_us, "fused_step_unavailable": sharded_error,
             "allreduce_bytes": int(4 * (5 * N + 1)) if world > 1 else 0, "allreduce_us": ar_us,
             "per_kernel_us_per_step": {k: round(t * 1e3 / 2, 2) for k, (n, t) in prof.items()}}
