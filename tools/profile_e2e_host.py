@@ -35,3 +35,12 @@ pr = cProfile.Profile(); pr.enable()
 for _ in range(100): step()
 pr.disable(); torch.cuda.synchronize()
 st = io.StringIO(); pstats.Stats(pr, stream=st).sort_stats("tottime").print_stats(22); print(st.getvalue()[:5000])
+st = io.StringIO(); pstats.Stats(pr, stream=st).sort_stats("cumulative").print_stats(30); print(st.getvalue()[:7000])
+# the same loop with the device kept idle-free: how long does the DEVICE need per step on this path?
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+import time as _t
+e0.record()
+for _ in range(100): step()
+e1.record(); torch.cuda.synchronize()
+print("device-timed ms/step:", e0.elapsed_time(e1) / 100)

@@ -58,11 +58,14 @@ class FusedRenderer:
         self._sil = None                    # [0:10] ladder sums, [10] chosen threshold, [11] its MSE
         self._bufs = self.ws.struct()
         self.polls = 0
+        self._step_graphs = {}              # tracking_step_cached: pointer set -> captured launch sequence
+        self._cap_stream = None
 
     # -- helpers ---------------------------------------------------------------------------
     def reserve_pairs(self, cap):
         self.ws.reserve_pairs(cap)
         self._bufs = self.ws.struct()
+        self._step_graphs.clear()           # the captured launches point into the old buffers
 
     def overflowed(self):
         R, overflow, _ = self.ws.read_counters()
@@ -215,6 +218,47 @@ class FusedRenderer:
                 _ptr(self.radii), _ptr(self.dL_dimage4), _ptr(self.loss_terms), _ptr(self._loss_scratch), C.byref(g),
                 _ptr(max_2D_radius), _ptr(seen), C.byref(self._bufs), _stream_ptr(self.device)))
         return self.loss_terms, self.radii[:self.N]
+
+    STEP_GRAPHS_MAX = 8
+
+    def tracking_step_cached(self, params, cam_q, cam_t, gt_rgb, gt_depth, max_2D_radius=None, **cfg):
+        """tracking_step for callers that step from a host loop with the SAME buffers (the reference's tracking loop: 40-200
+        iterations per frame on one pose slice and one frame): the second call with a given set of pointers and loss
+        settings captures the launch sequence in a CUDA graph, later ones replay it (one launch, and back-to-back kernels
+        overlap their tails as in TrackingSolver).  The entry owns the outputs that must not move: -> (loss_terms, radii,
+        pose_grad[7] = d_cam_q | d_cam_t, seen or None), valid until the entry's next call."""
+        pm = cfg.get("pixel_mask")
+        key = (tuple(params[k].data_ptr() for k in PARAM_KEYS), cam_q.data_ptr(), cam_t.data_ptr(), gt_rgb.data_ptr(), gt_depth.data_ptr(),
+               0 if pm is None else pm.data_ptr(), 0 if max_2D_radius is None else max_2D_radius.data_ptr(),
+               tuple(sorted((k, v) for k, v in cfg.items() if k != "pixel_mask")))
+        ent = self._step_graphs.pop(key, None)
+        if ent is None:
+            if len(self._step_graphs) >= self.STEP_GRAPHS_MAX:
+                self._step_graphs.pop(next(iter(self._step_graphs)))          # least recently used
+            ent = dict(calls=0, graph=None, g7=torch.empty(7, dtype=torch.float32, device=self.device),
+                       seen=None if max_2D_radius is None else torch.empty(self.N, dtype=torch.bool, device=self.device))
+        self._step_graphs[key] = ent
+        ent["calls"] += 1
+        run = lambda: self.tracking_step(params, cam_q, cam_t, gt_rgb, gt_depth, (ent["g7"][:4], ent["g7"][4:]),
+                                         max_2D_radius=max_2D_radius, seen=ent["seen"], **cfg)
+        pm_stable = pm is None or (pm.dtype == torch.uint8 and pm.is_contiguous())
+        if ent["graph"] is None and ent["calls"] == 2 and pm_stable and os.environ.get("VTGS_STEP_GRAPH", "1") != "0":
+            if self._cap_stream is None:
+                self._cap_stream = torch.cuda.Stream(self.device)
+            cur = torch.cuda.current_stream(self.device)
+            self._cap_stream.wait_stream(cur)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(self._cap_stream):
+                g.capture_begin(capture_error_mode="thread_local")      # (a frame-prefetch worker may be allocating)
+                run()
+                g.capture_end()
+            cur.wait_stream(self._cap_stream)
+            ent["graph"] = g
+        if ent["graph"] is not None:
+            ent["graph"].replay()
+        else:
+            run()
+        return self.loss_terms, self.radii[:self.N], ent["g7"], ent["seen"]
 
     def mapping_loss(self, gt_rgb, gt_depth, w_im=1.0, w_depth=1.0, image6=None):
         """Mapping loss of get_loss (reference :597,:608): w_depth * mean|gt-d|[gt>0] + w_im * (0.8 L1mean +

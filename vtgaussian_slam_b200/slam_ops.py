@@ -356,7 +356,7 @@ class _FusedTrackingLoss(torch.autograd.Function):
     transform_to_frame detaches them, reference :432-436)."""
 
     @staticmethod
-    def forward(ctx, renderer, params, cam_q, cam_t, gt_rgb, gt_depth, cfg, thres_fn, poll, book):
+    def forward(ctx, renderer, params, cam_q, cam_t, gt_rgb, gt_depth, cfg, thres_fn, poll, book, seen_box):
         p = {k: params[k].detach().contiguous() for k in ("means3D", "rgb_colors", "unnorm_rotations", "logit_opacities", "log_scales")}
         q, t = cam_q.detach().contiguous().reshape(4), cam_t.detach().contiguous().reshape(3)
         ctx.pose_shapes = (cam_q.shape, cam_t.shape)
@@ -365,17 +365,16 @@ class _FusedTrackingLoss(torch.autograd.Function):
         # backward() only hands the stored gradient over: the host side of a reference-style step is what paces it.
         ctx.eager = thres_fn is None and (ctx.needs_input_grad[2] or ctx.needs_input_grad[3])
         if ctx.eager:
-            g7 = torch.empty(7, dtype=torch.float32, device=q.device)
             rgb, dep = gt_rgb.contiguous(), gt_depth.contiguous()
-            m2r, seen = book if book is not None else (None, None)
             for attempt in range(2):
-                terms, radii = renderer.tracking_step(p, q, t, rgb, dep, (g7[:4], g7[4:]), max_2D_radius=m2r, seen=seen, **cfg)
+                terms, radii, g7, seen = renderer.tracking_step_cached(p, q, t, rgb, dep, max_2D_radius=book, **cfg)
                 if not (poll and renderer.ensure_capacity()):      # (the bookkeeping only reads the radii: repeatable)
                     break
                 if attempt == 1:
                     raise RuntimeError("pair buffer overflow persisted after regrowing")
-            ctx.g7 = g7
+            ctx.g7 = g7.clone()                     # the renderer's entry is overwritten by its next step
             terms = terms.clone()
+            seen_box.append(seen)
             ctx.mark_non_differentiable(radii, terms)
             return terms[0].clone(), terms, radii
         img, radii = _forward_checked(renderer, p, q, t, poll)
@@ -388,7 +387,7 @@ class _FusedTrackingLoss(torch.autograd.Function):
         ctx.dL4 = renderer.dL_dimage4          # valid until the renderer's next loss call
         if book is not None:
             from .fused import book_radii
-            book_radii(radii, book[0], book[1])
+            seen_box.append(book_radii(radii, book))
         # radii: the renderer's own buffer (valid until its next forward; get_loss books it at once): no N-sized copy
         ctx.mark_non_differentiable(radii, terms)
         return terms[0].clone(), terms, radii
@@ -398,14 +397,14 @@ class _FusedTrackingLoss(torch.autograd.Function):
         if ctx.eager:
             g7 = ctx.g7 * g_loss.detach().to(torch.float32)
             return (None, None, g7[:4].reshape(ctx.pose_shapes[0]), g7[4:].reshape(ctx.pose_shapes[1]), None, None, None, None,
-                    None, None)
+                    None, None, None)
         # the backward overwrites both (no zero fill) and multiplies the incoming dL/dloss in its final reduction
         dq = torch.empty(4, dtype=torch.float32, device=g_loss.device)
         dt = torch.empty(3, dtype=torch.float32, device=g_loss.device)
         scale = g_loss.detach().to(torch.float32).contiguous()
         ctx.renderer.backward(ctx.p, ctx.q, ctx.t, dL_dimage4=ctx.dL4, pose_grads=(dq, dt), pose_scale=scale)
         ctx.renderer.pending_backward = False
-        return (None, None, dq.reshape(ctx.pose_shapes[0]), dt.reshape(ctx.pose_shapes[1]), None, None, None, None, None, None)
+        return (None, None, dq.reshape(ctx.pose_shapes[0]), dt.reshape(ctx.pose_shapes[1]), None, None, None, None, None, None, None)
 
 
 class _FusedMappingLoss(torch.autograd.Function):
@@ -582,14 +581,13 @@ def get_loss(params, curr_data, variables, iter_time_idx, loss_weights, use_sil_
                                    else vis_mask.reshape(curr_data['depth'].shape[-2:])))
             # radius bookkeeping (:681-683) inside the same library call when the buffers allow it
             m2r = variables['max_2D_radius']
-            book = None
-            if m2r.is_cuda and m2r.dtype == torch.float32 and m2r.is_contiguous() and m2r.shape[0] == r.N:
-                book = (m2r, torch.empty(r.N, dtype=torch.bool, device=m2r.device))
+            book = m2r if (m2r.is_cuda and m2r.dtype == torch.float32 and m2r.is_contiguous() and m2r.shape[0] == r.N) else None
+            seen_box = []
             loss, terms, radius = _FusedTrackingLoss.apply(r, params, cam_q, cam_t, curr_data['im'], curr_data['depth'], cfg, thres_fn,
-                                                           _poll_due(r, tracking_iteration), book)
+                                                           _poll_due(r, tracking_iteration), book, seen_box)
             weighted_losses = {'depth': terms[2], 'im': terms[1], 'loss': loss}
             if book is not None:
-                variables['seen'] = book[1]
+                variables['seen'] = seen_box[0]        # (the renderer's buffer: valid until its next tracking step)
             else:
                 _book_radii(variables, radius)
             if presence_sil_mask_mse_ls is not None:
