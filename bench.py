@@ -764,7 +764,8 @@ def run_c5_leg(args, rank, world, dev, pg):
         del solver, params
         torch.cuda.empty_cache()
     m = run_mapping_leg(args, wl, rank, world, dev, pg, iters=5, keyframes=max(4, world), shape="scannetpp")
-    res["mapping"] = {k: m[k] for k in ("keyframes_per_step", "ms_per_step", "value", "unit", "allreduce_bytes", "allreduce_us")}
+    res["mapping"] = {k: m[k] for k in ("keyframes_per_step", "ms_per_step", "value", "unit", "fused_step", "fused_step_us", "allreduce_bytes",
+                                        "allreduce_us")}
     return res
 
 
