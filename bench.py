@@ -288,7 +288,7 @@ def run_tracking(args, wl, rank, world, dev, pg):
         del probe, nc, pad
         torch.cuda.empty_cache()
     solver = TrackingSolver(settings, params, device=dev, w_im=LOSS_W["im"], w_depth=LOSS_W["depth"], sil_thres=SIL_THRES,
-                            tile_rows=band, use_graph=True, process_group=pg)
+                            tile_rows=band, use_graph=True, process_group=pg, deterministic=True if args.deterministic else None)
     gt_rgb = torch.tensor(fr["im"]).pin_memory()
     gt_depth = torch.tensor(fr["depth"]).pin_memory()
     solver.set_frame(gt_rgb, gt_depth, wl["q"], wl["t"])
@@ -890,6 +890,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity_check leg")
     ap.add_argument("--no-extra", action="store_true", help="skip the mapping block and the c1 / c4 / c5 legs")
     ap.add_argument("--kernels-only", action="store_true", help="kernel experiments: device-timed value + per-kernel durations only")
+    ap.add_argument("--deterministic", action="store_true", help="kernel experiments: the headline leg with VTGS_BUF_DETERMINISTIC")
     ap.add_argument("--mode", default="tracking", choices=["tracking", "mapping"],
                     help="tracking = configs[1] (the driver's line, which also carries the mapping block); mapping = only the keyframe-sharded leg")
     ap.add_argument("--keyframes", type=int, default=8, help="--mode mapping: keyframes per mapping iteration (configs[2]: 8)")

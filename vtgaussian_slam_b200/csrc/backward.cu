@@ -73,7 +73,8 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[16], int lane)
 //   [8..11] lo{conic.xx, conic.xy, conic.yy, colour 3}  [12..15] hi{opacity, r, g, b}   [16..19] lo{opacity, r, g, b}
 // (the pose-only instantiation touches the first 48 bytes: three vector reductions per partial, as many memory
 // operations as without the flag).
-constexpr int DET_STRIDE = 32;        // floats per record
+constexpr int DET_STRIDE = 32;        // floats per record; the pose-only form (12 floats) keeps the plain path's 16-float stride: same sectors for K7'
+__host__ __device__ constexpr int det_stride(bool pose_only) { return pose_only ? 16 : DET_STRIDE; }
 
 __device__ __forceinline__ int det_exponent(float bound) {          // smallest e (clamped) with bound < 2^e
     const int e = (int)((__float_as_uint(bound) >> 23) & 0xffu) - 126;
@@ -140,6 +141,18 @@ constexpr int bwd_smem_bytes(bool lite) {
 #define VTGS_BWD_LITE_WARPS_PER_SM 22
 #endif
 constexpr int bwd_min_blocks(bool lite) { return (lite ? VTGS_BWD_LITE_WARPS_PER_SM : 20) / BWD_WARPS; }
+// Splat registers for the backward: load_splat's packing, except that the two slots the backward never reads -- the list
+// position (a.z) and pthr (b.w) -- carry the half extents (hx, hy) of the splat's alpha >= 1/255 box, which the
+// deterministic accumulation needs for its bounds (no second gather of the record per partial).
+__device__ __forceinline__ void load_splat_bwd(SplatRegs& r, bool valid, const GeomRecord* __restrict__ geom, uint2 ent) {
+    if (valid) {
+        const GeomRecord* rec = geom + ent.x;
+        const float4 q0 = rec->q0, q1 = rec->q1;
+        r.c = rec->q2;
+        r.a = make_float4(q0.x, q0.y, q0.w, q1.w);
+        r.b = make_float4(q1.x, q1.y, q1.z, q0.z);
+    }
+}
 // BG:   the background is not black (one more term in dL/dalpha); the reference always renders on black.
 // LITE: the caller wants no colour / opacity gradients (tracking: only the pose gradient is formed, from the
 //       mean2D / conic / depth-channel sums) -- P3 drops the r,g,b and opacity sums.
@@ -216,7 +229,7 @@ blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __re
     if (nxt_live) {
         const bool v = g * 32 + lane < n;
         if (v) ent_next = list[g * 32 + lane];
-        load_splat(nxt, v, geom, ent_next);
+        load_splat_bwd(nxt, v, geom, ent_next);
     }
     for (; g >= 0; --g) {
         const SplatRegs cur = nxt;
@@ -229,7 +242,7 @@ blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __re
         if (nxt_live) {
             const bool v = (g - 1) * 32 + lane < n;
             if (v) ent_next = list[(g - 1) * 32 + lane];
-            load_splat(nxt, v, geom, ent_next);
+            load_splat_bwd(nxt, v, geom, ent_next);
         }
         if (!cur_live) continue;
         const bool have = g * 32 + lane < n;
@@ -304,27 +317,25 @@ blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __re
                 // bounds of this Gaussian's sums of |partial| over ALL its partials (every partial derives the same three
                 // grids): |g0| <= |dL/dalpha| <= 2 max|c| sum_ch |dL/dpix| (+ the background term), |w| <= 1, the splat's
                 // blended pixels lie within its alpha >= 1/255 box (half extents hx, hy of the record)
-                const GeomRecord* rec = geom + cur_ent.x;
-                const float4 q0 = rec->q0, q3 = rec->q3;
                 const float cmax = __uint_as_float(__ldg(det_scalars)), dmax = __uint_as_float(__ldg(det_scalars + 1));
                 const float d1 = (float)NCH * dmax;
                 float g0max = 2.0f * cmax * d1;
                 if (BG) g0max += 100.0f * (fabsf(cam.bg[0]) + fabsf(cam.bg[1]) + fabsf(cam.bg[2])) * dmax;
-                const float ex = q0.z + 1.5f, ey = q0.w + 1.5f;
+                const float ex = cur.b.w + 1.5f, ey = cur.a.z + 1.5f;
                 const float npix = (2.0f * ex) * (2.0f * ey);
                 const float S = npix * g0max;
                 const float bm = fmaxf(half_w, half_h) * o * (fabsf(ca) * ex + fabsf(cb) * (ex + ey) + fabsf(cc) * ey) * S;
                 const float bc = 0.5f * o * S * fmaxf(ex, ey) * fmaxf(ex, ey);
                 const float bk = npix * fmaxf(d1, g0max);
                 const int em = det_exponent(bm), ec = det_exponent(bc), ek = det_exponent(bk);
-                const uint32_t rmin = __float_as_uint(q3.z), rmax = __float_as_uint(q3.w);
-                const int tiles = max(1, (int)((rmax & 0xffffu) - (rmin & 0xffffu)) * (int)((rmax >> 16) - (rmin >> 16)));
+                // tiles the box can touch (an upper bound is as good as the count: every partial of a Gaussian derives the same grids)
+                const int tiles = (int)fminf(ex * 0.125f + 2.0f, 4096.0f) * (int)fminf(ey * 0.125f + 2.0f, 4096.0f);
                 const int s_lo = max(1, 21 - (32 - __clz(tiles - 1)));                  // 21 - ceil(log2(tiles))
                 const float hm = 3.0f * det_pow2(em), hc = 3.0f * det_pow2(ec), hk = 3.0f * det_pow2(ek), ls = det_pow2(-s_lo);
                 const float2 a0 = det_split(v0, hm, hm * ls), a1 = det_split(v1, hm, hm * ls);
                 const float2 a2 = det_split(v2, hc, hc * ls), a3 = det_split(v3, hc, hc * ls), a4 = det_split(v4, hc, hc * ls);
                 const float2 a5 = det_split(NCH == 4 ? c3 : 0.0f, hk, hk * ls);
-                float* dst = grad_geom + (size_t)cur_ent.x * DET_STRIDE;
+                float* dst = grad_geom + (size_t)cur_ent.x * det_stride(LITE);
                 asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a0.x), "f"(a1.x), "f"(a2.x), "f"(a3.x) : "memory");
                 asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(a4.x), "f"(a5.x), "f"(a0.y), "f"(a1.y) : "memory");
                 asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 8), "f"(a2.y), "f"(a3.y), "f"(a4.y), "f"(a5.y) : "memory");
@@ -356,7 +367,7 @@ struct GradRecordRaw { float4 a, b, c, d, e; };
 
 template <bool DET>
 __device__ __forceinline__ void fetch_grad_record(const float* __restrict__ grad_geom, int64_t i, bool want_colour_opacity, GradRecordRaw& r) {
-    const float4* rec = reinterpret_cast<const float4*>(grad_geom + (size_t)i * (DET ? DET_STRIDE : 16));
+    const float4* rec = reinterpret_cast<const float4*>(grad_geom + (size_t)i * (DET ? det_stride(!want_colour_opacity) : 16));
     r.a = rec[0]; r.b = rec[1]; r.c = rec[2];
     if (DET && want_colour_opacity) { r.d = rec[3]; r.e = rec[4]; }
 }
@@ -382,7 +393,7 @@ __device__ __forceinline__ void decode_grad_record(const GradRecordRaw& r, bool 
 
 template <bool DET>
 __device__ __forceinline__ void zero_grad_record(float* __restrict__ grad_geom, int64_t i, bool want_colour_opacity) {
-    float4* gg = reinterpret_cast<float4*>(grad_geom + (size_t)i * (DET ? DET_STRIDE : 16));
+    float4* gg = reinterpret_cast<float4*>(grad_geom + (size_t)i * (DET ? det_stride(!want_colour_opacity) : 16));
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     gg[0] = zero4; gg[1] = zero4; gg[2] = zero4;
     if (DET && want_colour_opacity) { gg[3] = zero4; gg[4] = zero4; }
