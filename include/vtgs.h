@@ -368,6 +368,9 @@ typedef struct VtgsParamGrads {
     float* pose_scratch;     /* vtgs_pose_scratch_floats(N) floats                        */
     const float* pose_scale; /* optional device scalar: the pose gradient is multiplied by it (the incoming dL/dloss of
                                 an autograd backward), saving the caller two launches                          */
+    const float* dL_abs_bound; /* optional device scalar >= max |dL_dimage4| (VTGS_BUF_DETERMINISTIC only: the grids of
+                                the order-independent sums derive from it; NULL = measured by one more pass over
+                                dL_dimage4).  vtgs_loss in tracking mode leaves max(w_im, w_depth) in loss_terms[6]. */
 } VtgsParamGrads;
 
 VTGS_API uint64_t vtgs_pose_scratch_floats(int64_t num_gaussians);

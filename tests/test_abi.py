@@ -37,7 +37,7 @@ def test_struct_layouts_match_the_header(L):
     assert C.sizeof(_lib.VtgsParams) == 8 * 5 + 8 + 8
     assert C.sizeof(_lib.VtgsPose) == 16 + 16
     assert C.sizeof(_lib.VtgsLossConfig) == 32 + 8 + 8 + 8
-    assert C.sizeof(_lib.VtgsParamGrads) == 80
+    assert C.sizeof(_lib.VtgsParamGrads) == 88
 
 
 def test_workspace_query_and_validation(L):

@@ -85,7 +85,7 @@ class VtgsLossConfig(C.Structure):
 class VtgsParamGrads(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "means3D", "rgb_colors", "unnorm_rotations", "logit_opacities", "log_scales", "means2D",
-        "cam_unnorm_rot", "cam_trans", "pose_scratch", "pose_scale")]
+        "cam_unnorm_rot", "cam_trans", "pose_scratch", "pose_scale", "dL_abs_bound")]
 
 
 # every symbol include/vtgs.h declares: (restype, argtypes)

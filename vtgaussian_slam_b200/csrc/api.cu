@@ -199,7 +199,9 @@ int vtgs_fused_tracking_step(const VtgsCamera* cam, const VtgsParams* p, const V
     VTGS_REQUIRE((max_2D_radius == nullptr) == (seen == nullptr), "max_2D_radius and seen come as a pair");
     if (int e = vtgs_fused_forward(cam, p, pose, out_image6, radii, buf, stream)) return e;
     if (int e = vtgs_loss(cam, cfg, out_image6, gt_rgb, gt_depth, dL_dimage4, loss_terms, loss_scratch, stream)) return e;
-    if (int e = vtgs_fused_backward(cam, p, pose, dL_dimage4, 0, grads, buf, stream)) return e;
+    VtgsParamGrads g = *grads;
+    if (g.dL_abs_bound == nullptr) g.dL_abs_bound = loss_terms + 6;     // the tracking loss's own bound of |dL/dplane|
+    if (int e = vtgs_fused_backward(cam, p, pose, dL_dimage4, 0, &g, buf, stream)) return e;
     if (max_2D_radius != nullptr)
         if (int e = vtgs_book_radii(p->num_gaussians, radii, max_2D_radius, seen, stream)) return e;
     return VTGS_OK;

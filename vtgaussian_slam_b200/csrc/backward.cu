@@ -164,7 +164,8 @@ blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __re
                       const uint32_t* __restrict__ region_masks, const uint32_t* __restrict__ region_done,
                       const GeomRecord* __restrict__ geom,
                       const float* __restrict__ final_T, const float* __restrict__ dL_dpix, float* __restrict__ grad_geom,
-                      const uint32_t* __restrict__ tile_order, const uint32_t* __restrict__ det_scalars) {
+                      const uint32_t* __restrict__ tile_order, const uint32_t* __restrict__ det_scalars,
+                      const float* __restrict__ det_dl_bound) {
     constexpr int NCH = FUSED ? 4 : 3;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // Every table a lane indexes with ITS OWN splat or pixel number is a plain float[32]: 32 entries over 32 banks, so
@@ -317,7 +318,8 @@ blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __re
                 // bounds of this Gaussian's sums of |partial| over ALL its partials (every partial derives the same three
                 // grids): |g0| <= |dL/dalpha| <= 2 max|c| sum_ch |dL/dpix| (+ the background term), |w| <= 1, the splat's
                 // blended pixels lie within its alpha >= 1/255 box (half extents hx, hy of the record)
-                const float cmax = __uint_as_float(__ldg(det_scalars)), dmax = __uint_as_float(__ldg(det_scalars + 1));
+                const float cmax = __uint_as_float(__ldg(det_scalars));
+                const float dmax = det_dl_bound ? __ldg(det_dl_bound) : __uint_as_float(__ldg(det_scalars + 1));
                 const float d1 = (float)NCH * dmax;
                 float g0max = 2.0f * cmax * d1;
                 if (BG) g0max += 100.0f * (fabsf(cam.bg[0]) + fabsf(cam.bg[1]) + fabsf(cam.bg[2])) * dmax;
@@ -545,29 +547,29 @@ preprocess_backward_kernel(const __grid_constant__ CamConst cam, int64_t N,
 // per warp: splat table 1280 + cells 8192 + pixel table 768 (384 in the 3-row form) bytes
 template <bool FUSED, bool BG, bool LITE, bool DET>
 static int launch_blend_backward_det(int blocks, cudaStream_t stream, const CamConst& cam, const VtgsBuffers* buf, const GeomRecord* geom,
-                                     const float* dL_dpix, const uint32_t* order) {
+                                     const float* dL_dpix, const uint32_t* order, const float* dl_bound) {
     static std::atomic<uint64_t> done{0};
     if (first_call_on_device(done)) {
         VTGS_CUDA_CHECK(cudaFuncSetAttribute(blend_backward_kernel<FUSED, BG, LITE, DET>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem_bytes(LITE)));
         VTGS_CUDA_CHECK(cudaFuncSetAttribute(blend_backward_kernel<FUSED, BG, LITE, DET>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     }
     uint32_t* scalars = buf->tile_counts + cam.gx * cam.gy + 1;         // {max |colour|, max |dL/dpixel|} bit patterns
-    if (DET) {
+    if (DET && dl_bound == nullptr) {          // no caller-supplied bound of |dL/dpixel|: measure it
         if (int e = launch_dpix_max(cam, dL_dpix, FUSED ? 4 : 3, scalars + 1, stream)) return e;
     }
     VTGS_PROF("blend_backward_kernel", stream);
     blend_backward_kernel<FUSED, BG, LITE, DET><<<blocks, 32 * BWD_WARPS, bwd_smem_bytes(LITE), stream>>>(
         cam, buf->tile_ranges, reinterpret_cast<const uint2*>(buf->region_pairs), buf->region_cnt, buf->region_masks, buf->region_done,
-        geom, buf->final_T, dL_dpix, buf->grad_geom, order, scalars);
+        geom, buf->final_T, dL_dpix, buf->grad_geom, order, scalars, DET ? dl_bound : nullptr);
     VTGS_LAUNCH_CHECK();
     return VTGS_OK;
 }
 
 template <bool FUSED, bool BG, bool LITE>
 static int launch_blend_backward(int blocks, cudaStream_t stream, const CamConst& cam, const VtgsBuffers* buf, const GeomRecord* geom,
-                                 const float* dL_dpix, const uint32_t* order) {
-    return (buf->flags & VTGS_BUF_DETERMINISTIC) ? launch_blend_backward_det<FUSED, BG, LITE, true>(blocks, stream, cam, buf, geom, dL_dpix, order)
-                                                 : launch_blend_backward_det<FUSED, BG, LITE, false>(blocks, stream, cam, buf, geom, dL_dpix, order);
+                                 const float* dL_dpix, const uint32_t* order, const float* dl_bound = nullptr) {
+    return (buf->flags & VTGS_BUF_DETERMINISTIC) ? launch_blend_backward_det<FUSED, BG, LITE, true>(blocks, stream, cam, buf, geom, dL_dpix, order, dl_bound)
+                                                 : launch_blend_backward_det<FUSED, BG, LITE, false>(blocks, stream, cam, buf, geom, dL_dpix, order, dl_bound);
 }
 
 int launch_backward(const VtgsCamera* camera, int64_t N,
@@ -874,10 +876,11 @@ int launch_fused_backward(const VtgsCamera* camera, const VtgsParams* params, co
             // the fused forward left the band's tiles in longest-list-first order (tile bands only: same condition there)
             const uint32_t* order = band_tiles < cam.gx * cam.gy ? buf->tile_order : nullptr;
             int e;
-            if (has_bg) e = lite ? launch_blend_backward<true, true, true>(bblocks, stream, cam, buf, geom, dL_dimage4, order)
-                                 : launch_blend_backward<true, true, false>(bblocks, stream, cam, buf, geom, dL_dimage4, order);
-            else e = lite ? launch_blend_backward<true, false, true>(bblocks, stream, cam, buf, geom, dL_dimage4, order)
-                          : launch_blend_backward<true, false, false>(bblocks, stream, cam, buf, geom, dL_dimage4, order);
+            const float* dlb = grads->dL_abs_bound;
+            if (has_bg) e = lite ? launch_blend_backward<true, true, true>(bblocks, stream, cam, buf, geom, dL_dimage4, order, dlb)
+                                 : launch_blend_backward<true, true, false>(bblocks, stream, cam, buf, geom, dL_dimage4, order, dlb);
+            else e = lite ? launch_blend_backward<true, false, true>(bblocks, stream, cam, buf, geom, dL_dimage4, order, dlb)
+                          : launch_blend_backward<true, false, false>(bblocks, stream, cam, buf, geom, dL_dimage4, order, dlb);
             if (e) return e;
         }
         unsigned int* ticket = reinterpret_cast<unsigned int*>(grads->pose_scratch ? grads->pose_scratch + (size_t)blocks * POSE_TERMS : nullptr);

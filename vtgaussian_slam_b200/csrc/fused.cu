@@ -343,7 +343,9 @@ tracking_loss_kernel(const __grid_constant__ CamConst cam, VtgsLossConfig cfg, c
         loss_terms[2] = (float)wd;
         loss_terms[3] = (float)tot[2];
         loss_terms[4] = (float)tot[1];
-        loss_terms[5] = 0.0f; loss_terms[6] = 0.0f; loss_terms[7] = 0.0f;
+        loss_terms[5] = 0.0f;
+        loss_terms[6] = fmaxf(fabsf(cfg.w_im), fabsf(cfg.w_depth));      // >= |dL/dplane| everywhere: VtgsParamGrads.dL_abs_bound
+        loss_terms[7] = 0.0f;
         *ticket = 0u;
     }
 }

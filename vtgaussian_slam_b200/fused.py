@@ -276,7 +276,7 @@ class FusedRenderer:
         return self.loss_terms
 
     def backward(self, params, cam_q, cam_t, dL_dimage4=None, param_grads=None, pose_grads=None, means2D_grad=None,
-                 accumulate=False, pose_scale=None):
+                 accumulate=False, pose_scale=None, dl_bound=None):
         """param_grads: dict key -> tensor to receive dL/dparams[key] (any subset of PARAM_KEYS).
         pose_grads: (d_cam_q[4], d_cam_t[3]) tensors or None; pose_scale: optional device scalar multiplied into them."""
         p, ps = self._params_struct(params), self._pose_struct(cam_q, cam_t)
@@ -294,6 +294,8 @@ class FusedRenderer:
             g.pose_scratch = self._pose_scratch.data_ptr()
             if pose_scale is not None:
                 g.pose_scale = pose_scale.data_ptr()
+        if dl_bound is not None:            # deterministic mode: a device scalar >= max |dL_dimage4| (else it is measured)
+            g.dL_abs_bound = dl_bound.data_ptr()
         dL = self.dL_dimage4 if dL_dimage4 is None else dL_dimage4
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().vtgs_fused_backward(C.byref(self.cam), C.byref(p), C.byref(ps), _ptr(dL), int(bool(accumulate)),
@@ -428,7 +430,7 @@ class TrackingSolver:
                 r.sil_ladder(self.gt_rgb, self.gt_depth, process_group=self.pg)
             extra["sil_thres_dev"] = r._sil[10:11]
         r.tracking_loss(self.gt_rgb, self.gt_depth, **self.cfg, **extra)
-        r.backward(self.params, self.cam_q, self.cam_t, pose_grads=(self.d_q, self.d_t))
+        r.backward(self.params, self.cam_q, self.cam_t, pose_grads=(self.d_q, self.d_t), dl_bound=r.loss_terms[6:7])
         if self.pg is not None:
             # tile-band sharding: every rank holds its band's partial sums; one 16-float all-reduce
             torch.distributed.all_reduce(self.msg, group=self.pg)

@@ -402,7 +402,8 @@ class _FusedTrackingLoss(torch.autograd.Function):
         dq = torch.empty(4, dtype=torch.float32, device=g_loss.device)
         dt = torch.empty(3, dtype=torch.float32, device=g_loss.device)
         scale = g_loss.detach().to(torch.float32).contiguous()
-        ctx.renderer.backward(ctx.p, ctx.q, ctx.t, dL_dimage4=ctx.dL4, pose_grads=(dq, dt), pose_scale=scale)
+        ctx.renderer.backward(ctx.p, ctx.q, ctx.t, dL_dimage4=ctx.dL4, pose_grads=(dq, dt), pose_scale=scale,
+                              dl_bound=ctx.renderer.loss_terms[6:7])
         ctx.renderer.pending_backward = False
         return (None, None, dq.reshape(ctx.pose_shapes[0]), dt.reshape(ctx.pose_shapes[1]), None, None, None, None, None, None, None)
 
