@@ -1,6 +1,7 @@
 // api.cu -- the extern "C" boundary declared in include/vtgs.h.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -13,6 +14,11 @@
 
 namespace vtgs {
 static thread_local char g_err[512] = "";
+bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("VTGS_PDL"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
 void set_error(const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);

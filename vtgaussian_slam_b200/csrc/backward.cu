@@ -91,6 +91,7 @@ __device__ __forceinline__ float2 det_split(float v, float c_hi, float c_lo) {
 // max |dL/dpixel| over the band's rows and the NCH planes -> *out_bits (atomicMax on the bit pattern; zeroed by the forward)
 __global__ void __launch_bounds__(256)
 dpix_max_kernel(const float* __restrict__ dL_dpix, size_t P, size_t begin, size_t end, int nch, uint32_t* __restrict__ out_bits) {
+    VTGS_PDL_PROLOGUE();
     float m = 0.0f;
     for (size_t i = begin + (size_t)blockIdx.x * 256 + threadIdx.x; i < end; i += (size_t)gridDim.x * 256)
         for (int ch = 0; ch < nch; ++ch) m = fmaxf(m, fabsf(__ldg(dL_dpix + ch * P + i)));
@@ -104,7 +105,7 @@ static int launch_dpix_max(const CamConst& cam, const float* dL_dpix, int nch, u
     const size_t begin = (size_t)cam.row0 * 16 * cam.W, end = std::min(P, (size_t)cam.row1 * 16 * cam.W);
     if (end <= begin) return VTGS_OK;
     const int blocks = (int)std::min<size_t>((end - begin + 1023) / 1024, 148 * 8);
-    { VTGS_PROF("dpix_max_kernel", stream); dpix_max_kernel<<<blocks, 256, 0, stream>>>(dL_dpix, P, begin, end, nch, out_bits); }
+    { VTGS_PROF("dpix_max_kernel", stream); launch_k(dpix_max_kernel, dim3(blocks), dim3(256), 0, stream, dL_dpix, P, begin, end, nch, out_bits); }
     VTGS_LAUNCH_CHECK();
     return VTGS_OK;
 }
@@ -166,6 +167,7 @@ blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __re
                       const float* __restrict__ final_T, const float* __restrict__ dL_dpix, float* __restrict__ grad_geom,
                       const uint32_t* __restrict__ tile_order, const uint32_t* __restrict__ det_scalars,
                       const float* __restrict__ det_dl_bound) {
+    VTGS_PDL_PROLOGUE();
     constexpr int NCH = FUSED ? 4 : 3;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // Every table a lane indexes with ITS OWN splat or pixel number is a plain float[32]: 32 entries over 32 banks, so
@@ -558,7 +560,7 @@ static int launch_blend_backward_det(int blocks, cudaStream_t stream, const CamC
         if (int e = launch_dpix_max(cam, dL_dpix, FUSED ? 4 : 3, scalars + 1, stream)) return e;
     }
     VTGS_PROF("blend_backward_kernel", stream);
-    blend_backward_kernel<FUSED, BG, LITE, DET><<<blocks, 32 * BWD_WARPS, bwd_smem_bytes(LITE), stream>>>(
+    launch_k(blend_backward_kernel<FUSED, BG, LITE, DET>, dim3(blocks), dim3(32 * BWD_WARPS), bwd_smem_bytes(LITE), stream, 
         cam, buf->tile_ranges, reinterpret_cast<const uint2*>(buf->region_pairs), buf->region_cnt, buf->region_masks, buf->region_done,
         geom, buf->final_T, dL_dpix, buf->grad_geom, order, scalars, DET ? dl_bound : nullptr);
     VTGS_LAUNCH_CHECK();
@@ -723,6 +725,7 @@ fused_preprocess_backward_kernel(const __grid_constant__ CamConst cam, int64_t N
                                  const VtgsCounters* __restrict__ counters, unsigned int* __restrict__ ticket,
                                  const uint32_t* __restrict__ tiles_touched, const uint8_t* __restrict__ band_flags,
                                  const uint32_t* __restrict__ cand, const uint32_t* __restrict__ n_cand) {
+    VTGS_PDL_PROLOGUE();
     __shared__ float s_part[8][POSE_TERMS];
     __shared__ double s_sum[POSE_TERMS][21];
     __shared__ bool s_last;
@@ -895,7 +898,7 @@ int launch_fused_backward(const VtgsCamera* camera, const VtgsParams* params, co
         {
             VTGS_PROF("fused_preprocess_backward_kernel", stream);
 #define VTGS_K7_LAUNCH(SHAPE_, DET_)                                                                                                             \
-    fused_preprocess_backward_kernel<SHAPE_, DET_><<<blocks, 256, 0, stream>>>(cam, N, *params, buf->counters->pose_R, pose->depth_row[0],         \
+    launch_k(fused_preprocess_backward_kernel<SHAPE_, DET_>, dim3(blocks), dim3(256), 0, stream, cam, N, *params, buf->counters->pose_R, pose->depth_row[0],         \
                                                                                pose->depth_row[1], pose->depth_row[2], geom, buf->grad_geom, *grads, \
                                                                                accumulate, want_pose, buf->counters, ticket, band_touch, band_flags, \
                                                                                band_cand, n_cand)

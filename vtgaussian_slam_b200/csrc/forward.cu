@@ -59,6 +59,7 @@ __global__ void __launch_bounds__(256)
 band_flags_kernel(const __grid_constant__ CamConst cam, int64_t N, FrontEnd fe, const float* __restrict__ means3D,
                   const float* __restrict__ log_scales, int32_t* __restrict__ radii, uint32_t* __restrict__ tiles_touched,
                   uint8_t* __restrict__ flags, uint32_t* __restrict__ cand, uint32_t* __restrict__ n_cand) {
+    VTGS_PDL_PROLOGUE();
     // one block = 4 candidate blocks of 256 Gaussians: all 16 loads of a thread are in flight together
     __shared__ float s_Rt[12];
     __shared__ uint32_t s_any[4];
@@ -157,6 +158,7 @@ preprocess_kernel(const __grid_constant__ CamConst cam, int64_t N, FrontEnd fe,
                   GeomRecord* __restrict__ geom, int32_t* __restrict__ radii,
                   uint32_t* __restrict__ tiles_touched, uint32_t* __restrict__ tile_counts,
                   const uint32_t* __restrict__ cand, const uint32_t* __restrict__ n_cand, uint32_t* __restrict__ colour_max_bits) {
+    VTGS_PDL_PROLOGUE();
     // Persistent loop over 256-Gaussian blocks: all of them, or (tile bands) the candidate blocks K0' listed.
     float cmax = 0.0f;          // max |colour| over the splats this thread emitted (deterministic backward: bound of c . dL/dpixel)
     const int tid = threadIdx.x;
@@ -313,6 +315,7 @@ preprocess_kernel(const __grid_constant__ CamConst cam, int64_t N, FrontEnd fe,
 __global__ void __launch_bounds__(1024)
 tile_scan_kernel(uint32_t* __restrict__ tile_counts, uint32_t* __restrict__ ranges, int num_tiles,
                  uint64_t capacity, VtgsCounters* __restrict__ counters, uint32_t* __restrict__ tile_order) {
+    VTGS_PDL_PROLOGUE();
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_carry;
     __shared__ uint32_t s_max[32];
@@ -441,6 +444,7 @@ __global__ void __launch_bounds__(256)
 scatter_kernel(int64_t N, int gx, const GeomRecord* __restrict__ geom, const uint32_t* __restrict__ tiles_touched,
                const uint32_t* __restrict__ ranges, uint32_t* __restrict__ tile_cursor,
                uint64_t* __restrict__ pair_keys, const uint32_t* __restrict__ cand, const uint32_t* __restrict__ n_cand) {
+    VTGS_PDL_PROLOGUE();
     // blocks of 256 Gaussians: all of them (one per CUDA block), or the candidate blocks of a tile band (persistent loop)
     const int64_t nblk = cand != nullptr ? (int64_t)*n_cand : (N + 255) / 256;
     for (int64_t trip = blockIdx.x; trip < nblk; trip += gridDim.x) {
@@ -896,6 +900,7 @@ __global__ void __launch_bounds__(256, 4)
 tile_sort_kernel(const __grid_constant__ CamConst cam, const uint32_t* __restrict__ ranges, int tile0,
                  uint64_t* __restrict__ pair_keys, uint32_t* __restrict__ point_list, const GeomRecord* __restrict__ geom,
                  uint2* __restrict__ region_pairs, uint32_t* __restrict__ region_cnt, const uint32_t* __restrict__ tile_order) {
+    VTGS_PDL_PROLOGUE();
     extern __shared__ __align__(16) uint64_t s_keys[];
     __shared__ uint32_t s_wh[8][256];
     __shared__ uint32_t s_cnt[64];
@@ -969,6 +974,7 @@ blend_forward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __res
                      const GeomRecord* __restrict__ geom,
                      float* __restrict__ out_color, float* __restrict__ out_depth,
                      float* __restrict__ final_T, uint32_t* __restrict__ n_contrib, const uint32_t* __restrict__ tile_order) {
+    VTGS_PDL_PROLOGUE();
     __shared__ ChunkSmem<FWD_GC> Ws[FWD_WARPS];
 
     constexpr int BPT = 8 / FWD_WARPS;                                  // blocks per tile
@@ -1110,6 +1116,7 @@ blend_forward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __res
 __global__ void fill_outside_band_kernel(const __grid_constant__ CamConst cam, int planes,
                                          float* __restrict__ out_color, float* __restrict__ out_depth,
                                          float* __restrict__ final_T, uint32_t* __restrict__ n_contrib) {
+    VTGS_PDL_PROLOGUE();
     const size_t P = (size_t)cam.W * cam.H;
     const size_t pid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (pid >= P) return;
@@ -1146,17 +1153,17 @@ int launch_forward(const VtgsCamera* camera, int64_t N, bool fused, const FrontE
     if (N > 0) {
         const bool narrow_band = (cam.row1 - cam.row0) * 5 < cam.gy * 2;
         if (use_cand) {
-            { VTGS_PROF("band_flags_kernel", stream); band_flags_kernel<<<(blocks + 3) / 4, 256, 0, stream>>>(cam, N, fe, means3D, scales, radii, buf->tiles_touched, buf->band_flags, buf->band_cand, n_cand); }
+            { VTGS_PROF("band_flags_kernel", stream); launch_k(band_flags_kernel, dim3((blocks + 3) / 4), dim3(256), 0, stream, cam, N, fe, means3D, scales, radii, buf->tiles_touched, buf->band_flags, buf->band_cand, n_cand); }
             VTGS_LAUNCH_CHECK();
         }
         const int k1_grid = use_cand ? std::min(blocks, persistent) : k1_blocks;
         if (fused && narrow_band)
-            { VTGS_PROF("preprocess_kernel", stream); preprocess_kernel<true, true><<<k1_grid, 256, 0, stream>>>(cam, N, fe, means3D, scales, rotations, opacities, colors,
+            { VTGS_PROF("preprocess_kernel", stream); launch_k(preprocess_kernel<true, true>, dim3(k1_grid), dim3(256), 0, stream, cam, N, fe, means3D, scales, rotations, opacities, colors,
                                                                  geom, radii, buf->tiles_touched, buf->tile_counts, cand, n_cand, cmax_bits); }
         else if (fused)
-            { VTGS_PROF("preprocess_kernel", stream); preprocess_kernel<true><<<k1_grid, 256, 0, stream>>>(cam, N, fe, means3D, scales, rotations, opacities, colors,
+            { VTGS_PROF("preprocess_kernel", stream); launch_k(preprocess_kernel<true>, dim3(k1_grid), dim3(256), 0, stream, cam, N, fe, means3D, scales, rotations, opacities, colors,
                                                                  geom, radii, buf->tiles_touched, buf->tile_counts, cand, n_cand, cmax_bits); }
-        else { VTGS_PROF("preprocess_kernel", stream); preprocess_kernel<false><<<k1_grid, 256, 0, stream>>>(cam, N, fe, means3D, scales, rotations, opacities, colors,
+        else { VTGS_PROF("preprocess_kernel", stream); launch_k(preprocess_kernel<false>, dim3(k1_grid), dim3(256), 0, stream, cam, N, fe, means3D, scales, rotations, opacities, colors,
                                                                   geom, radii, buf->tiles_touched, buf->tile_counts, nullptr, nullptr, cmax_bits); }
         VTGS_LAUNCH_CHECK();
     }
@@ -1167,12 +1174,12 @@ int launch_forward(const VtgsCamera* camera, int64_t N, bool fused, const FrontE
     // the tile order is relative to the scanned range: usable when that is exactly what the sort / blend kernels cover
     // (worth its ~4 us in the scan only when a launch is about one wave of blocks: tile bands)
     uint32_t* order = (fused && band_active) ? buf->tile_order : nullptr;
-    { VTGS_PROF("tile_scan_kernel", stream); tile_scan_kernel<<<1, 1024, 0, stream>>>(buf->tile_counts + scan0, buf->tile_ranges + 2 * (size_t)scan0, scan_n, buf->pair_capacity, buf->counters, order); }
+    { VTGS_PROF("tile_scan_kernel", stream); launch_k(tile_scan_kernel, dim3(1), dim3(1024), 0, stream, buf->tile_counts + scan0, buf->tile_ranges + 2 * (size_t)scan0, scan_n, buf->pair_capacity, buf->counters, order); }
     VTGS_LAUNCH_CHECK();
     if (N > 0 && band_tiles > 0) {
         { VTGS_PROF("scatter_kernel", stream); const int sb = use_cand ? std::min(blocks, 148 * 8) : blocks;
-          if (wide) scatter_kernel<true><<<sb, 256, 0, stream>>>(N, cam.gx, geom, buf->tiles_touched, buf->tile_ranges, buf->tile_counts, buf->pair_keys, cand, n_cand);
-          else scatter_kernel<false><<<sb, 256, 0, stream>>>(N, cam.gx, geom, buf->tiles_touched, buf->tile_ranges, buf->tile_counts, buf->pair_keys, cand, n_cand); }
+          if (wide) launch_k(scatter_kernel<true>, dim3(sb), dim3(256), 0, stream, N, cam.gx, geom, buf->tiles_touched, buf->tile_ranges, buf->tile_counts, buf->pair_keys, cand, n_cand);
+          else launch_k(scatter_kernel<false>, dim3(sb), dim3(256), 0, stream, N, cam.gx, geom, buf->tiles_touched, buf->tile_ranges, buf->tile_counts, buf->pair_keys, cand, n_cand); }
         VTGS_LAUNCH_CHECK();
         static std::atomic<uint64_t> sort_attr{0};
         if (first_call_on_device(sort_attr)) {
@@ -1180,8 +1187,8 @@ int launch_forward(const VtgsCamera* camera, int64_t N, bool fused, const FrontE
             VTGS_CUDA_CHECK(cudaFuncSetAttribute(tile_sort_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_SMEM_ELEMS * 8));
         }
         { VTGS_PROF("tile_sort_kernel", stream);
-          if (wide) tile_sort_kernel<true><<<band_tiles, 256, SORT_SMEM_ELEMS * 8, stream>>>(cam, buf->tile_ranges, cam.row0 * cam.gx, buf->pair_keys, buf->point_list, geom, reinterpret_cast<uint2*>(buf->region_pairs), buf->region_cnt, order);
-          else tile_sort_kernel<false><<<band_tiles, 256, SORT_SMEM_ELEMS * 8, stream>>>(cam, buf->tile_ranges, cam.row0 * cam.gx, buf->pair_keys, buf->point_list, geom, reinterpret_cast<uint2*>(buf->region_pairs), buf->region_cnt, order); }
+          if (wide) launch_k(tile_sort_kernel<true>, dim3(band_tiles), dim3(256), SORT_SMEM_ELEMS * 8, stream, cam, buf->tile_ranges, cam.row0 * cam.gx, buf->pair_keys, buf->point_list, geom, reinterpret_cast<uint2*>(buf->region_pairs), buf->region_cnt, order);
+          else launch_k(tile_sort_kernel<false>, dim3(band_tiles), dim3(256), SORT_SMEM_ELEMS * 8, stream, cam, buf->tile_ranges, cam.row0 * cam.gx, buf->pair_keys, buf->point_list, geom, reinterpret_cast<uint2*>(buf->region_pairs), buf->region_cnt, order); }
         VTGS_LAUNCH_CHECK();
     }
     if (N <= 0) VTGS_CUDA_CHECK(cudaMemsetAsync(buf->region_cnt, 0, sizeof(uint32_t) * 8 * num_tiles, stream));
@@ -1192,13 +1199,13 @@ int launch_forward(const VtgsCamera* camera, int64_t N, bool fused, const FrontE
             VTGS_CUDA_CHECK(cudaFuncSetAttribute(blend_forward_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         }
         if (fused)
-            { VTGS_PROF("blend_forward_kernel", stream); blend_forward_kernel<true><<<band_tiles * (8 / FWD_WARPS), 32 * FWD_WARPS, 0, stream>>>(cam, buf->tile_ranges, reinterpret_cast<const uint2*>(buf->region_pairs), buf->region_cnt, buf->region_masks, buf->region_done, geom, out_color, out_depth, buf->final_T, buf->n_contrib, order); }
-        else { VTGS_PROF("blend_forward_kernel", stream); blend_forward_kernel<false><<<band_tiles * (8 / FWD_WARPS), 32 * FWD_WARPS, 0, stream>>>(cam, buf->tile_ranges, reinterpret_cast<const uint2*>(buf->region_pairs), buf->region_cnt, buf->region_masks, buf->region_done, geom, out_color, out_depth, buf->final_T, buf->n_contrib, order); }
+            { VTGS_PROF("blend_forward_kernel", stream); launch_k(blend_forward_kernel<true>, dim3(band_tiles * (8 / FWD_WARPS)), dim3(32 * FWD_WARPS), 0, stream, cam, buf->tile_ranges, reinterpret_cast<const uint2*>(buf->region_pairs), buf->region_cnt, buf->region_masks, buf->region_done, geom, out_color, out_depth, buf->final_T, buf->n_contrib, order); }
+        else { VTGS_PROF("blend_forward_kernel", stream); launch_k(blend_forward_kernel<false>, dim3(band_tiles * (8 / FWD_WARPS)), dim3(32 * FWD_WARPS), 0, stream, cam, buf->tile_ranges, reinterpret_cast<const uint2*>(buf->region_pairs), buf->region_cnt, buf->region_masks, buf->region_done, geom, out_color, out_depth, buf->final_T, buf->n_contrib, order); }
         VTGS_LAUNCH_CHECK();
     }
     if (band_tiles < num_tiles && !fused) {       // API mode returns complete planes; the fused solvers only ever read their band
         const size_t P = (size_t)cam.W * cam.H;
-        { VTGS_PROF("fill_outside_band_kernel", stream); fill_outside_band_kernel<<<(unsigned)((P + 255) / 256), 256, 0, stream>>>(cam, fused ? 6 : 3, out_color, out_depth, buf->final_T, buf->n_contrib); }
+        { VTGS_PROF("fill_outside_band_kernel", stream); launch_k(fill_outside_band_kernel, dim3((unsigned)((P + 255) / 256)), dim3(256), 0, stream, cam, fused ? 6 : 3, out_color, out_depth, buf->final_T, buf->n_contrib); }
         VTGS_LAUNCH_CHECK();
     }
     return VTGS_OK;

@@ -25,6 +25,7 @@ constexpr int MEDIAN_STATE_WORDS = VTGS_MEDIAN_STATE_WORDS;
 __global__ void __launch_bounds__(256)
 median_hist_kernel(const float* __restrict__ depth_plane, const float* __restrict__ gt_depth, size_t pix_begin, size_t pix_end,
                    int pass, unsigned int* __restrict__ st) {
+    VTGS_PDL_PROLOGUE();
     __shared__ unsigned int sh[256];
     const int tid = threadIdx.x;
     sh[tid] = 0u;
@@ -45,6 +46,7 @@ median_hist_kernel(const float* __restrict__ depth_plane, const float* __restric
 
 __global__ void __launch_bounds__(256)
 median_pick_kernel(unsigned long long P_total, int pass, unsigned int* __restrict__ st) {
+    VTGS_PDL_PROLOGUE();
     __shared__ unsigned int sh[256];
     const int tid = threadIdx.x;
     sh[tid] = st[tid];
@@ -84,13 +86,13 @@ int launch_median_hist(const VtgsCamera* camera, const float* depth_plane, const
     band_pixel_range(cam, b, e);
     if (e <= b) return VTGS_OK;
     const int mb = (int)std::min<size_t>((e - b + 1023) / 1024, 148 * 4);
-    { VTGS_PROF("median_hist_kernel", stream); median_hist_kernel<<<mb, 256, 0, stream>>>(depth_plane, gt_depth, b, e, pass, state); }
+    { VTGS_PROF("median_hist_kernel", stream); launch_k(median_hist_kernel, dim3(mb), dim3(256), 0, stream, depth_plane, gt_depth, b, e, pass, state); }
     VTGS_LAUNCH_CHECK();
     return VTGS_OK;
 }
 
 int launch_median_pick(int64_t P_total, int pass, uint32_t* state, cudaStream_t stream) {
-    { VTGS_PROF("median_pick_kernel", stream); median_pick_kernel<<<1, 256, 0, stream>>>((unsigned long long)P_total, pass, state); }
+    { VTGS_PROF("median_pick_kernel", stream); launch_k(median_pick_kernel, dim3(1), dim3(256), 0, stream, (unsigned long long)P_total, pass, state); }
     VTGS_LAUNCH_CHECK();
     return VTGS_OK;
 }
@@ -260,6 +262,7 @@ tracking_loss_kernel(const __grid_constant__ CamConst cam, VtgsLossConfig cfg, c
                      const float* __restrict__ gt_rgb, const float* __restrict__ gt_depth,
                      float* __restrict__ dL_dimage4, float* __restrict__ partials, unsigned int* __restrict__ ticket,
                      float* __restrict__ loss_terms, const unsigned int* __restrict__ median_state) {
+    VTGS_PDL_PROLOGUE();
     __shared__ float s_part[8][LOSS_TERMS];
     __shared__ double s_sum[LOSS_TERMS][64];
     __shared__ bool s_last;
@@ -386,6 +389,7 @@ __global__ void __launch_bounds__(256)
 ssim_forward_kernel(int W, int H, const SsimWindow win, const float* __restrict__ image6, const float* __restrict__ gt_rgb,
                     const float* __restrict__ gt_depth, float* __restrict__ maps /* [3 ch][3 maps][P] */,
                     float* __restrict__ partials) {
+    VTGS_PDL_PROLOGUE();
     __shared__ float sx[SSIM_H][SSIM_H + 1], sy[SSIM_H][SSIM_H + 1];
     __shared__ float hb[5][SSIM_H][SSIM_T + 1];
     __shared__ float s_part[8][MAP_TERMS];
@@ -478,6 +482,7 @@ ssim_forward_kernel(int W, int H, const SsimWindow win, const float* __restrict_
 
 __global__ void __launch_bounds__(1024)
 mapping_finalize_kernel(const float* __restrict__ partials, int nblocks, int W, int H, VtgsLossConfig cfg, float* __restrict__ loss_terms) {
+    VTGS_PDL_PROLOGUE();
     __shared__ double s_sum[MAP_TERMS][256];
     __shared__ double s_tot[MAP_TERMS];
     const int tid = threadIdx.x;
@@ -515,6 +520,7 @@ __global__ void __launch_bounds__(256)
 ssim_backward_kernel(int W, int H, const SsimWindow win, VtgsLossConfig cfg, const float* __restrict__ image6,
                      const float* __restrict__ gt_rgb, const float* __restrict__ gt_depth, const float* __restrict__ maps,
                      const float* __restrict__ loss_terms, float* __restrict__ dL_dimage4) {
+    VTGS_PDL_PROLOGUE();
     __shared__ float sm[3][SSIM_H][SSIM_H + 1];
     __shared__ float hb[3][SSIM_H][SSIM_T + 1];
     const int ch = blockIdx.z;
@@ -681,11 +687,11 @@ int launch_loss(const VtgsCamera* camera, const VtgsLossConfig* cfg, const float
         const int nb = (int)(grid.x * grid.y * grid.z);
         float* maps = scratch;                      // 9 P floats
         float* partials = scratch + 9 * P;          // nb * 4
-        { VTGS_PROF("ssim_forward_kernel", stream); ssim_forward_kernel<<<grid, block, 0, stream>>>(cam.W, cam.H, win, image6, gt_rgb, gt_depth, maps, partials); }
+        { VTGS_PROF("ssim_forward_kernel", stream); launch_k(ssim_forward_kernel, dim3(grid), dim3(block), 0, stream, cam.W, cam.H, win, image6, gt_rgb, gt_depth, maps, partials); }
         VTGS_LAUNCH_CHECK();
-        { VTGS_PROF("mapping_finalize_kernel", stream); mapping_finalize_kernel<<<1, 1024, 0, stream>>>(partials, nb, cam.W, cam.H, *cfg, loss_terms); }
+        { VTGS_PROF("mapping_finalize_kernel", stream); launch_k(mapping_finalize_kernel, dim3(1), dim3(1024), 0, stream, partials, nb, cam.W, cam.H, *cfg, loss_terms); }
         VTGS_LAUNCH_CHECK();
-        { VTGS_PROF("ssim_backward_kernel", stream); ssim_backward_kernel<<<grid, block, 0, stream>>>(cam.W, cam.H, win, *cfg, image6, gt_rgb, gt_depth, maps, loss_terms, dL_dimage4); }
+        { VTGS_PROF("ssim_backward_kernel", stream); launch_k(ssim_backward_kernel, dim3(grid), dim3(block), 0, stream, cam.W, cam.H, win, *cfg, image6, gt_rgb, gt_depth, maps, loss_terms, dL_dimage4); }
         VTGS_LAUNCH_CHECK();
         return VTGS_OK;
     }
@@ -707,7 +713,7 @@ int launch_loss(const VtgsCamera* camera, const VtgsLossConfig* cfg, const float
             }
             median_state = st;
         }
-        { VTGS_PROF("tracking_loss_kernel", stream); tracking_loss_kernel<<<nblocks, 256, 0, stream>>>(cam, *cfg, image6, gt_rgb, gt_depth, dL_dimage4, scratch, ticket, loss_terms, median_state); }
+        { VTGS_PROF("tracking_loss_kernel", stream); launch_k(tracking_loss_kernel, dim3(nblocks), dim3(256), 0, stream, cam, *cfg, image6, gt_rgb, gt_depth, dL_dimage4, scratch, ticket, loss_terms, median_state); }
         VTGS_LAUNCH_CHECK();
     } else {
         VTGS_CUDA_CHECK(cudaMemsetAsync(loss_terms, 0, 8 * sizeof(float), stream));
@@ -730,6 +736,7 @@ __device__ __forceinline__ double ipow(double b, int t) {
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,
             float lr, float b1, float b2, float eps, int step, const int32_t* __restrict__ step_dev, int vec4) {
+    VTGS_PDL_PROLOGUE();
     __shared__ float s_c[2];
     if (threadIdx.x == 0) {
         const int t = step_dev ? *step_dev : step;
@@ -935,6 +942,7 @@ int launch_sharded_adam(int world, int rank, const uint64_t* bases, uint64_t mc_
 __global__ void tracking_update_kernel(float* __restrict__ cam_q, float* __restrict__ cam_t, const float* __restrict__ msg,
                                        float* __restrict__ adam, int32_t* __restrict__ step_dev, float* __restrict__ best,
                                        float lr_rot, float lr_trans, float b1, float b2, float eps, int flags) {
+    VTGS_PDL_PROLOGUE();
     const int k = threadIdx.x;           // 0..3 quaternion, 4..6 translation
     __shared__ int s_step;
     __shared__ bool s_better;
@@ -965,7 +973,7 @@ __global__ void tracking_update_kernel(float* __restrict__ cam_q, float* __restr
 
 int launch_tracking_update(float* cam_q, float* cam_t, const float* msg, float* adam, int32_t* step_dev, float* best,
                            float lr_rot, float lr_trans, float eps, int flags, cudaStream_t stream) {
-    { VTGS_PROF("tracking_update_kernel", stream); tracking_update_kernel<<<1, 32, 0, stream>>>(cam_q, cam_t, msg, adam, step_dev, best, lr_rot, lr_trans, 0.9f, 0.999f, eps, flags); }
+    { VTGS_PROF("tracking_update_kernel", stream); launch_k(tracking_update_kernel, dim3(1), dim3(32), 0, stream, cam_q, cam_t, msg, adam, step_dev, best, lr_rot, lr_trans, 0.9f, 0.999f, eps, flags); }
     VTGS_LAUNCH_CHECK();
     return VTGS_OK;
 }
@@ -975,7 +983,7 @@ int launch_adam(float* param, const float* grad, float* m, float* v, int64_t n, 
     if (n <= 0) return VTGS_OK;
     const bool vec4 = (n % 4 == 0) && (((uintptr_t)param | (uintptr_t)grad | (uintptr_t)m | (uintptr_t)v) & 15) == 0;
     const int64_t threads = vec4 ? n / 4 : n;
-    { VTGS_PROF("adam_kernel", stream); adam_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(param, grad, m, v, n, lr, b1, b2, eps, step, step_dev, vec4 ? 1 : 0); }
+    { VTGS_PROF("adam_kernel", stream); launch_k(adam_kernel, dim3((unsigned)((threads + 255) / 256)), dim3(256), 0, stream, param, grad, m, v, n, lr, b1, b2, eps, step, step_dev, vec4 ? 1 : 0); }
     VTGS_LAUNCH_CHECK();
     return VTGS_OK;
 }
