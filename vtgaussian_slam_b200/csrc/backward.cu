@@ -138,6 +138,12 @@ __host__ __device__ constexpr int bwd_pix_rows(bool lite) { return lite ? 0 : 4;
 constexpr int bwd_smem_bytes(bool lite) {
     return BWD_WARPS * (int)(10 * 32 * sizeof(float) + 32 * 32 * sizeof(float2) + (bwd_pix_rows(lite) ? bwd_pix_rows(lite) : 1) * 32 * sizeof(float));
 }
+// P2 evaluates log2(alpha) = log2(opacity) + log2(e) * power as ONE quadratic polynomial of the pixel's region-local
+// coordinates (six per-splat coefficients staged instead of centre / conic / opacity: five FMAs per pair instead of
+// ~12 operations), and hands over opacity * G * dL/dalpha, so that P4 needs no multiplication by the opacity either.
+#ifndef VTGS_BWD_POLY
+#define VTGS_BWD_POLY 1
+#endif
 #ifndef VTGS_BWD_LITE_WARPS_PER_SM
 #define VTGS_BWD_LITE_WARPS_PER_SM 22
 #endif
@@ -210,6 +216,8 @@ blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __re
         for (int ch = 0; ch < 4; ++ch) A.pix[ch][lane] = dpix[ch];
     }
     const float rx0f = (float)rx0, ry0f = (float)ry0;
+    const float plx = (float)(lane % REGION_W), ply = (float)(lane / REGION_W);      // region-local pixel coordinates
+    const float pxx = plx * plx, pxy = plx * ply, pyy = ply * ply;
     const float bg_dot = BG ? cam.bg[0] * dpix[0] + cam.bg[1] * dpix[1] + cam.bg[2] * dpix[2] : 0.0f;
     const float half_w = 0.5f * cam.W, half_h = 0.5f * cam.H;
 
@@ -251,16 +259,27 @@ blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __re
         const bool have = g * 32 + lane < n;
         __syncwarp();                                   // previous group's P3 reads are complete
         if (have) {
+#if VTGS_BWD_POLY
+            // E(x, y) = a (mx - x)^2 + b (mx - x)(my - y) + c (my - y)^2 + log2(opacity), (x, y) region-local
+            const float ka = -0.72134752f * cur.b.x, kb = -1.44269504f * cur.b.y, kc = -0.72134752f * cur.b.z;
+            const float mx = cur.a.x - rx0f, my = cur.a.y - ry0f;
+            A.rec[0][lane] = fmaf(ka * mx, mx, fmaf(kb * mx, my, fmaf(kc * my, my, __log2f(cur.a.w))));
+            A.rec[1][lane] = -fmaf(2.0f * ka, mx, kb * my);
+            A.rec[2][lane] = -fmaf(2.0f * kc, my, kb * mx);
+            A.rec[3][lane] = ka; A.rec[4][lane] = kb; A.rec[5][lane] = kc;
+#else
             A.rec[0][lane] = cur.a.x; A.rec[1][lane] = cur.a.y; A.rec[2][lane] = cur.a.w;
             A.rec[3][lane] = cur.b.x; A.rec[4][lane] = cur.b.y; A.rec[5][lane] = cur.b.z;
+#endif
             A.rec[6][lane] = cur.c.x; A.rec[7][lane] = cur.c.y; A.rec[8][lane] = cur.c.z; A.rec[9][lane] = cur.c.w;
         }
         __syncwarp();
         const uint32_t emask = warp_transpose_bits(m, lane);      // lane = splat: the pixels that blended it
         // ---- P2: lane = pixel; descending bits = descending list position.  Two splats per trip: loads /
         // power / exp are independent, the T / accum recursion is ordered.
+        // (POLY: op == 1 and Gv == opacity * G: the hand-over is opacity * G * dL/dalpha)
         auto back_one = [&](const float op, const float Gv, const int e) -> float2 {
-            const float alpha = fminf(VTGS_ALPHA_MAX, op * Gv);
+            const float alpha = fminf(VTGS_ALPHA_MAX, VTGS_BWD_POLY ? Gv : op * Gv);
             const float inv = rcp_approx(1.0f - alpha);             // 1 - alpha in [0.01, 1]
             T = T * inv;
             float cdot = A.rec[6][e] * dpix[0] + A.rec[7][e] * dpix[1] + A.rec[8][e] * dpix[2];
@@ -280,12 +299,19 @@ blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __re
             m &= ~(1u << eb);
             // no decision depends on G any more (the forward's masks fix which splats were blended), so the
             // backward may use the hardware exp2 and free contraction: gradients are judged to 1e-3 relative
+#if VTGS_BWD_POLY
+            const float Ga = ex2_approx(fmaf(A.rec[5][ea], pyy, fmaf(A.rec[4][ea], pxy, fmaf(A.rec[3][ea], pxx, fmaf(A.rec[2][ea], ply, fmaf(A.rec[1][ea], plx, A.rec[0][ea]))))));
+            const float Gb = ex2_approx(fmaf(A.rec[5][eb], pyy, fmaf(A.rec[4][eb], pxy, fmaf(A.rec[3][eb], pxx, fmaf(A.rec[2][eb], ply, fmaf(A.rec[1][eb], plx, A.rec[0][eb]))))));
+            A.cell[ea][lane] = back_one(1.0f, Ga, ea);
+            if (two) A.cell[eb][lane] = back_one(1.0f, Gb, eb);
+#else
             const float dxa = A.rec[0][ea] - pxf, dya = A.rec[1][ea] - pyf, dxb = A.rec[0][eb] - pxf, dyb = A.rec[1][eb] - pyf;
             // (power is in [pthr, 0], |pthr| a few units: the forward blended these pairs)
             const float Ga = ex2_approx(1.44269504f * (-0.5f * (A.rec[3][ea] * dxa * dxa + A.rec[5][ea] * dya * dya) - A.rec[4][ea] * dxa * dya));
             const float Gb = ex2_approx(1.44269504f * (-0.5f * (A.rec[3][eb] * dxb * dxb + A.rec[5][eb] * dyb * dyb) - A.rec[4][eb] * dxb * dyb));
             A.cell[ea][lane] = back_one(A.rec[2][ea], Ga, ea);
             if (two) A.cell[eb][lane] = back_one(A.rec[2][eb], Gb, eb);
+#endif
         }
         __syncwarp();
         // ---- P3: lane = splat: reduce my row of cells
@@ -313,9 +339,11 @@ blend_backward_kernel(const __grid_constant__ CamConst cam, const uint32_t* __re
         // ---- P4: finalize (dL/dG * G = opacity * g0) and one vector reduction per (region, splat)
         if (emask) {
             const float o = cur.a.w, ca = cur.b.x, cb = cur.b.y, cc = cur.b.z;
-            const float v0 = -half_w * o * (ca * sx + cb * sy);
-            const float v1 = -half_h * o * (cc * sy + cb * sx);
-            const float v2 = -0.5f * o * sxx, v3 = -0.5f * o * sxy, v4 = -0.5f * o * syy;
+            const float og = VTGS_BWD_POLY ? 1.0f : o;                        // (POLY: the opacity is inside the sums already)
+            const float v0 = -half_w * og * (ca * sx + cb * sy);
+            const float v1 = -half_h * og * (cc * sy + cb * sx);
+            const float v2 = -0.5f * og * sxx, v3 = -0.5f * og * sxy, v4 = -0.5f * og * syy;
+            if (VTGS_BWD_POLY && !LITE) s0 = __fdividef(s0, o);                 // dL/dopacity = sum G dL/dalpha
             if (DET) {
                 // bounds of this Gaussian's sums of |partial| over ALL its partials (every partial derives the same three
                 // grids): |g0| <= |dL/dalpha| <= 2 max|c| sum_ch |dL/dpix| (+ the background term), |w| <= 1, the splat's
