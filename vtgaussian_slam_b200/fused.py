@@ -242,7 +242,8 @@ class FusedRenderer:
         run = lambda: self.tracking_step(params, cam_q, cam_t, gt_rgb, gt_depth, (ent["g7"][:4], ent["g7"][4:]),
                                          max_2D_radius=max_2D_radius, seen=ent["seen"], **cfg)
         pm_stable = pm is None or (pm.dtype == torch.uint8 and pm.is_contiguous())
-        if ent["graph"] is None and ent["calls"] == 2 and pm_stable and os.environ.get("VTGS_STEP_GRAPH", "1") != "0":
+        if (ent["graph"] is None and ent["calls"] == 2 and pm_stable and os.environ.get("VTGS_STEP_GRAPH", "1") != "0"
+                and not torch.cuda.is_current_stream_capturing()):          # (a caller capturing its own graph keeps plain launches)
             if self._cap_stream is None:
                 self._cap_stream = torch.cuda.Stream(self.device)
             cur = torch.cuda.current_stream(self.device)
