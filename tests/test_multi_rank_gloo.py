@@ -118,3 +118,92 @@ def test_two_rank_gloo_allreduce_equals_single_rank():
     scale = np.abs(full[:12]).max()
     assert np.abs(got[:12] - full[:12]).max() <= 1e-5 * scale          # pose-gradient partial sums
     np.testing.assert_allclose(ret["map"], np.full(5, 10.0))
+
+
+# ---- keyframe-sharded mapping step (vtgs_sharded_adam): the algorithm over gloo ---------------------------------------
+def _adam_slice(p, g, m, v, lr, step, eps=1e-15, b1=0.9, b2=0.999):
+    """vtgs_adam's update (csrc/fused.cu adam_kernel) in float32 numpy."""
+    f = np.float32
+    m[:] = m + f(1 - b1) * (g - m)
+    v[:] = f(b2) * v + f(1 - b2) * g * g
+    step_size = (lr / (1.0 - b1 ** step)).astype(np.float32)
+    bc2s = f(np.sqrt(1.0 - b2 ** step))
+    p[:] = p - step_size * (m / (np.sqrt(v) / bc2s + f(eps)))
+
+
+def _sharded_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from vtgaussian_slam_b200.fused import MappingSolver
+    sizes, lrs = [3 * 1001, 1001, 1001], [0.0025, 0.05, 0.005]          # rgb, logit opacity, log scale of 1001 Gaussians
+    n = sum(sizes)
+    n_pad = (n + 3) // 4 * 4
+    lr_el = np.zeros(n_pad, np.float32)
+    off = 0
+    for c, lr in zip(sizes, lrs):
+        lr_el[off:off + c] = lr
+        off += c
+    lr_el[off:] = lrs[-1]
+    rng = np.random.default_rng(7)
+    p = np.zeros(n_pad, np.float32)
+    p[:n] = rng.normal(size=n).astype(np.float32)
+    b, e = MappingSolver.sharded_slices(n_pad, world)[rank]
+    m, v = np.zeros(e - b, np.float32), np.zeros(e - b, np.float32)       # this rank's slice of the moments only
+    for step in range(1, 5):
+        g_all = [np.zeros(n_pad, np.float32) for _ in range(world)]       # every rank's keyframe gradients (same seeds everywhere)
+        for r in range(world):
+            g_all[r][:n] = np.random.default_rng(100 * step + r).normal(size=n).astype(np.float32)
+        mine = torch.tensor(g_all[rank])
+        gathered = [torch.zeros(n_pad) for _ in range(world)]
+        dist.all_gather(gathered, mine)                                   # stands in for the peer loads over NVLink
+        gs = gathered[0][b:e].numpy().copy()
+        for r in range(1, world):                                         # rank order: a fixed order
+            gs = gs + gathered[r][b:e].numpy()
+        sl = p[b:e].copy()
+        _adam_slice(sl, gs, m, v, lr_el[b:e], step)
+        per = max(x[1] - x[0] for x in MappingSolver.sharded_slices(n_pad, world))
+        padded = torch.zeros(per)
+        padded[:e - b] = torch.tensor(sl)
+        outs = [torch.zeros(per) for _ in range(world)]
+        dist.all_gather(outs, padded)                                     # stands in for the peer stores
+        for r, (rb, re_) in enumerate(MappingSolver.sharded_slices(n_pad, world)):
+            p[rb:re_] = outs[r][:re_ - rb].numpy()
+    ret[rank] = p.copy()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_step_algorithm_equals_replicated_adam(world):
+    """Reduce-scatter in rank order + Adam on the owned slice (sharded moments) + all-gather == torch.optim.Adam applied by
+    every rank to the all-reduced gradients, and the ranks end bitwise equal.  (The CUDA kernel is checked against vtgs_adam
+    in tests/test_gpu_fused.py and across 2 GPUs by tools/check_multi_gpu.py.)"""
+    sys.path.insert(0, ROOT)
+    from vtgaussian_slam_b200.fused import MappingSolver
+    sizes, lrs = [3 * 1001, 1001, 1001], [0.0025, 0.05, 0.005]
+    n = sum(sizes)
+    n_pad = (n + 3) // 4 * 4
+    sl = MappingSolver.sharded_slices(n_pad, world)
+    assert sl[0][0] == 0 and sl[-1][1] == n_pad and all(a[1] == b[0] for a, b in zip(sl, sl[1:])) and all(b % 4 == 0 for b, _ in sl)
+    assert MappingSolver.sharded_slices(8, 8) == [(0, 4), (4, 8)] + [(8, 8)] * 6          # more ranks than float4s
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_sharded_worker, args=(world, 29600 + world, ret), nprocs=world, join=True)
+    for r in range(1, world):
+        assert np.array_equal(ret[0], ret[r])
+    # single process: torch.optim.Adam per tensor on the summed gradients
+    rng = np.random.default_rng(7)
+    p0 = rng.normal(size=n).astype(np.float32)
+    offs = np.cumsum([0] + sizes)
+    ts = [torch.nn.Parameter(torch.tensor(p0[offs[i]:offs[i + 1]].copy())) for i in range(3)]
+    opt = torch.optim.Adam([{"params": [t], "lr": lr} for t, lr in zip(ts, lrs)], lr=0.0, eps=1e-15)
+    for step in range(1, 5):
+        g = sum(np.random.default_rng(100 * step + r).normal(size=n).astype(np.float32) for r in range(world))
+        for i, t in enumerate(ts):
+            t.grad = torch.tensor(g[offs[i]:offs[i + 1]].copy())
+        opt.step()
+    ref = np.concatenate([t.detach().numpy() for t in ts])
+    assert np.abs(ret[0][:n] - ref).max() <= 5e-6
+    assert not ret[0][n:].any()
+

@@ -592,6 +592,15 @@ class MappingSolver:
         if global_params is not None:
             self.set_global(global_params)
 
+    @staticmethod
+    def sharded_slices(n_pad, world):
+        """Element ranges [begin, end) of the flat vectors that each rank owns in `vtgs_sharded_adam` (whole float4s,
+        ceil-divided; trailing ranks may own less or nothing): the kernel's partition, restated for the host (sizing of
+        the sharded moments, the 2-rank gloo test of the step's algorithm)."""
+        n4 = n_pad // 4
+        per = (n4 + world - 1) // world
+        return [(4 * min(n4, per * r), 4 * min(n4, per * (r + 1))) for r in range(world)]
+
     def _setup_sharded(self, sizes, world):
         import torch.distributed._symmetric_memory as symm
         if world > 8:
@@ -612,7 +621,7 @@ class MappingSolver:
             seg_end.append(off)
         seg_end[-1] = n_pad
         rank = torch.distributed.get_rank(self.pg)
-        per = ((n_pad // 4 + world - 1) // world) * 4
+        per = max(e - b for b, e in self.sharded_slices(n_pad, world))
         self.flat = gflat                               # (kept for callers that time the plain all-reduce of the message)
         self.total_loss = block[2 * n_pad:2 * n_pad + 1]
         nseg = len(seg_end)
